@@ -1,0 +1,78 @@
+"""ctypes binding of libgvf_b200.so (the C ABI declared in include/gvf_b200.h).
+
+There is deliberately NO fallback: if the shared object is missing or a call fails the
+product raises.  PyTorch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgvf_b200.so")
+_lib = None
+
+
+class GvfError(RuntimeError):
+    pass
+
+
+class RasterParams(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("tanfovx", C.c_float), ("tanfovy", C.c_float),
+                ("kernel_size", C.c_float), ("scale_modifier", C.c_float), ("bg", C.c_float * 3),
+                ("aabb", C.c_float * 6), ("scale_bias", C.c_float), ("min_kernel", C.c_float),
+                ("opacity_bias", C.c_float), ("softplus", C.c_int32)]
+
+
+_P = C.c_void_p
+_SIGS = {
+    # name: (restype, argtypes)
+    "gvf_status_string": (C.c_char_p, [C.c_int]),
+    "gvf_abi_version": (C.c_int, []),
+    "gvf_raster_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
+    "gvf_raster_workspace_offset": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
+    "gvf_raster_forward": (C.c_int, [C.POINTER(RasterParams), C.c_int, C.c_int, C.c_int,
+                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
+}
+
+
+def declared_symbols():
+    return sorted(_SIGS)
+
+
+def lib():
+    """Load the library (building it first when nvcc is available and sources changed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if os.environ.get("GVF_NO_AUTOBUILD") != "1":
+        try:
+            from . import build as _b
+            _b.build()
+        except Exception as e:  # stale/missing toolchain: fall through to the existence check
+            if not os.path.exists(LIB_PATH):
+                raise GvfError(f"libgvf_b200.so is missing and could not be built: {e}") from e
+    if not os.path.exists(LIB_PATH):
+        raise GvfError(f"{LIB_PATH} not found: run `python -m gvfdiffusion_b200.build` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib().gvf_status_string(status).decode()
+        raise GvfError(f"{what} failed: {msg} ({status})")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

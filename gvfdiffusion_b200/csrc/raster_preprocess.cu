@@ -1,0 +1,225 @@
+// raster_preprocess.cu -- per-(frame, Gaussian) activation + projection + tile counting.
+//
+// Replaces, fused in one pass: GaussianModel.get_{xyz,scaling,rotation,features,opacity}
+// _with_delta (reference representations/gaussian/gaussian_model.py:98-114, five
+// elementwise torch kernels + dtype copies per render, renderers/gaussian_render.py:154-193)
+// and the `preprocessCUDA` stage of diff_gaussian_rasterization (mip-splatting fork; call
+// site renderers/gaussian_render.py:198-206).
+//
+// COMPILED WITH -fmad=false.  Everything that feeds an integer output (radius, tile
+// rectangle, depth-sort key) is evaluated in the exact operation order of the CPU oracle
+// with correctly rounded IEEE ops and the reproducible transcendentals of gvf_math.h, so
+// radii / rectangles / keys are bit-identical to the oracle's (north_star: "bit-exact on
+// tile/sort indices").
+//
+// HBM-bound: reads 56 B canonical + 56 B delta per (frame, Gaussian), writes a 48 B splat
+// record + 8 B rect (+4 B radius); one global atomic per touched tile (1-4 typical).
+#include "../../include/gvf_math.h"
+#include "raster_common.h"
+
+namespace gvf {
+
+__device__ __forceinline__ int f2i_clamped(float v) {
+  v = fminf(fmaxf(v, -1.0e6f), 1.0e6f);
+  return (int)v;
+}
+
+struct PreArgs {
+  gvf_raster_params prm;
+  int F, P, activated;
+  const float *xyz, *dc, *scaling, *rotation, *opacity, *delta, *cams;
+  float4* splat;
+  ushort4* rect;
+  uint32_t* tile_count;
+  int32_t* radii;
+};
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long FP = (long long)a.F * a.P;
+  if (gid >= FP) return;
+  const int f = (int)(gid / a.P);
+  const int i = (int)(gid - (long long)f * a.P);
+  const gvf_raster_params& prm = a.prm;
+  const int W = prm.W, H = prm.H;
+  const int gx = (W + GVF_TILE - 1) / GVF_TILE, gy = (H + GVF_TILE - 1) / GVF_TILE;
+
+  // ---------------- activation (GaussianModel.get_*_with_delta) ----------------
+  float m3[3], sc[3], q[4], sh[3], opac;
+  if (a.activated) {
+    const size_t b = (size_t)gid;
+    m3[0] = a.xyz[b * 3 + 0]; m3[1] = a.xyz[b * 3 + 1]; m3[2] = a.xyz[b * 3 + 2];
+    sh[0] = a.dc[b * 3 + 0]; sh[1] = a.dc[b * 3 + 1]; sh[2] = a.dc[b * 3 + 2];
+    sc[0] = a.scaling[b * 3 + 0]; sc[1] = a.scaling[b * 3 + 1]; sc[2] = a.scaling[b * 3 + 2];
+    q[0] = a.rotation[b * 4 + 0]; q[1] = a.rotation[b * 4 + 1];
+    q[2] = a.rotation[b * 4 + 2]; q[3] = a.rotation[b * 4 + 3];
+    opac = a.opacity[b];
+  } else {
+    float d[14];
+    if (a.delta) {
+      // [F,P,14] rows are 56 B: 8-byte aligned -> seven float2 loads
+      const float2* dp = reinterpret_cast<const float2*>(a.delta + (size_t)gid * 14);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const float2 v = __ldg(dp + k);
+        d[2 * k] = v.x;
+        d[2 * k + 1] = v.y;
+      }
+    }
+    const float k2 = prm.min_kernel * prm.min_kernel;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = a.xyz[(size_t)i * 3 + c] * prm.aabb[3 + c] + prm.aabb[c];
+      m3[c] = a.delta ? v + d[c] : v;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s = a.scaling[(size_t)i * 3 + c] + prm.scale_bias;
+      if (a.delta) s = s + d[3 + c];
+      s = prm.softplus ? gvf_softplusf(s) : gvf_expf(s);
+      sc[c] = sqrtf(s * s + k2);
+    }
+    float qq[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float r = a.rotation[(size_t)i * 4 + c] + (c == 0 ? 1.0f : 0.0f);
+      qq[c] = a.delta ? r + d[6 + c] : r;
+    }
+    float n = sqrtf(qq[0] * qq[0] + qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3]);
+    n = fmaxf(n, 1e-12f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) q[c] = qq[c] / n;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      sh[c] = a.delta ? a.dc[(size_t)i * 3 + c] + d[10 + c] : a.dc[(size_t)i * 3 + c];
+    float o = a.opacity[i] + prm.opacity_bias;
+    if (a.delta) o = o + d[13];
+    opac = gvf_sigmoidf(o);
+  }
+
+  // ---------------- projection ----------------
+  const float* view = a.cams + (size_t)f * 32;
+  const float* proj = view + 16;
+  const float px = m3[0], py = m3[1], pz = m3[2];
+  const float tx = view[0] * px + view[4] * py + view[8] * pz + view[12];
+  const float ty = view[1] * px + view[5] * py + view[9] * pz + view[13];
+  const float tz = view[2] * px + view[6] * py + view[10] * pz + view[14];
+
+  int radius = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+  bool ok = tz > 0.2f;
+  if (ok) {
+    const float hx = proj[0] * px + proj[4] * py + proj[8] * pz + proj[12];
+    const float hy = proj[1] * px + proj[5] * py + proj[9] * pz + proj[13];
+    const float hw = proj[3] * px + proj[7] * py + proj[11] * pz + proj[15];
+    const float pw = 1.0f / (hw + 0.0000001f);
+    const float ndcx = hx * pw, ndcy = hy * pw;
+
+    const float s0 = prm.scale_modifier * sc[0], s1 = prm.scale_modifier * sc[1],
+                s2 = prm.scale_modifier * sc[2];
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - r * z), R02 = 2.f * (x * z + r * y);
+    const float R10 = 2.f * (x * y + r * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - r * x);
+    const float R20 = 2.f * (x * z - r * y), R21 = 2.f * (y * z + r * x), R22 = 1.f - 2.f * (x * x + y * y);
+    const float L00 = R00 * s0, L01 = R01 * s1, L02 = R02 * s2;
+    const float L10 = R10 * s0, L11 = R11 * s1, L12 = R12 * s2;
+    const float L20 = R20 * s0, L21 = R21 * s1, L22 = R22 * s2;
+    const float S00 = L00 * L00 + L01 * L01 + L02 * L02;
+    const float S01 = L00 * L10 + L01 * L11 + L02 * L12;
+    const float S02 = L00 * L20 + L01 * L21 + L02 * L22;
+    const float S11 = L10 * L10 + L11 * L11 + L12 * L12;
+    const float S12 = L10 * L20 + L11 * L21 + L12 * L22;
+    const float S22 = L20 * L20 + L21 * L21 + L22 * L22;
+
+    const float fx = (float)W / (2.0f * prm.tanfovx), fy = (float)H / (2.0f * prm.tanfovy);
+    const float limx = 1.3f * prm.tanfovx, limy = 1.3f * prm.tanfovy;
+    const float txtz = tx / tz, tytz = ty / tz;
+    const float cx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+    const float cy = fminf(limy, fmaxf(-limy, tytz)) * tz;
+    const float J00 = fx / tz, J02 = -(fx * cx) / (tz * tz);
+    const float J11 = fy / tz, J12 = -(fy * cy) / (tz * tz);
+    const float W00 = view[0], W01 = view[4], W02 = view[8];
+    const float W10 = view[1], W11 = view[5], W12 = view[9];
+    const float W20 = view[2], W21 = view[6], W22 = view[10];
+    const float T00 = J00 * W00 + J02 * W20, T01 = J00 * W01 + J02 * W21, T02 = J00 * W02 + J02 * W22;
+    const float T10 = J11 * W10 + J12 * W20, T11 = J11 * W11 + J12 * W21, T12 = J11 * W12 + J12 * W22;
+    const float V00 = T00 * S00 + T01 * S01 + T02 * S02;
+    const float V01 = T00 * S01 + T01 * S11 + T02 * S12;
+    const float V02 = T00 * S02 + T01 * S12 + T02 * S22;
+    const float V10 = T10 * S00 + T11 * S01 + T12 * S02;
+    const float V11 = T10 * S01 + T11 * S11 + T12 * S12;
+    const float V12 = T10 * S02 + T11 * S12 + T12 * S22;
+    float ca = V00 * T00 + V01 * T01 + V02 * T02;
+    const float cb = V00 * T10 + V01 * T11 + V02 * T12;
+    float cc = V10 * T10 + V11 * T11 + V12 * T12;
+
+    const float ks = prm.kernel_size;
+    const float det0 = fmaxf(1e-6f, ca * cc - cb * cb);
+    const float det1 = fmaxf(1e-6f, (ca + ks) * (cc + ks) - cb * cb);
+    float coef = sqrtf(det0 / (det1 + 1e-6f) + 1e-6f);
+    if (det0 <= 1e-6f || det1 <= 1e-6f) coef = 0.0f;
+    ca = ca + ks;
+    cc = cc + ks;
+    const float det = ca * cc - cb * cb;
+    ok = det != 0.0f;
+    if (ok) {
+      const float det_inv = 1.0f / det;
+      const float mid = 0.5f * (ca + cc);
+      const float disc = sqrtf(fmaxf(0.1f, mid * mid - det));
+      const float lambda1 = mid + disc, lambda2 = mid - disc;
+      const float rad = ceilf(3.0f * sqrtf(fmaxf(lambda1, lambda2)));
+      const float pix_x = ((ndcx + 1.0f) * (float)W - 1.0f) * 0.5f;
+      const float pix_y = ((ndcy + 1.0f) * (float)H - 1.0f) * 0.5f;
+      const int irad = f2i_clamped(rad);
+      x0 = f2i_clamped((pix_x - (float)irad) / (float)GVF_TILE);
+      y0 = f2i_clamped((pix_y - (float)irad) / (float)GVF_TILE);
+      x1 = f2i_clamped((pix_x + (float)irad + (float)(GVF_TILE - 1)) / (float)GVF_TILE);
+      y1 = f2i_clamped((pix_y + (float)irad + (float)(GVF_TILE - 1)) / (float)GVF_TILE);
+      x0 = x0 < 0 ? 0 : (x0 > gx ? gx : x0);
+      y0 = y0 < 0 ? 0 : (y0 > gy ? gy : y0);
+      x1 = x1 < 0 ? 0 : (x1 > gx ? gx : x1);
+      y1 = y1 < 0 ? 0 : (y1 > gy ? gy : y1);
+      ok = (x1 - x0) * (y1 - y0) != 0;
+      if (ok) {
+        radius = irad;
+        const float SH_C0 = 0.28209479177387814f;
+        r0 = make_float4(pix_x, pix_y, cc * det_inv, -cb * det_inv);
+        r1 = make_float4(ca * det_inv, opac * coef, fmaxf(SH_C0 * sh[0] + 0.5f, 0.0f),
+                         fmaxf(SH_C0 * sh[1] + 0.5f, 0.0f));
+        r2 = make_float4(fmaxf(SH_C0 * sh[2] + 0.5f, 0.0f), tz, __int_as_float(irad),
+                         __int_as_float((x1 - x0) * (y1 - y0)));
+      }
+    }
+  }
+  if (!ok) { x0 = y0 = x1 = y1 = 0; }
+  float4* sp = a.splat + (size_t)gid * 3;
+  sp[0] = r0;
+  sp[1] = r1;
+  sp[2] = r2;
+  a.rect[gid] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1,
+                             (unsigned short)y1);
+  if (a.radii) a.radii[gid] = radius;
+  if (ok) {
+    uint32_t* tc = a.tile_count + (size_t)f * gx * gy;
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) atomicAdd(tc + yy * gx + xx, 1u);
+  }
+}
+
+cudaError_t launch_preprocess(const gvf_raster_params& prm, int F, int P, int activated,
+                              const float* xyz, const float* dc, const float* scaling,
+                              const float* rotation, const float* opacity, const float* delta,
+                              const float* cams, const RasterWs& ws, int32_t* radii,
+                              cudaStream_t st) {
+  PreArgs a;
+  a.prm = prm; a.F = F; a.P = P; a.activated = activated;
+  a.xyz = xyz; a.dc = dc; a.scaling = scaling; a.rotation = rotation; a.opacity = opacity;
+  a.delta = delta; a.cams = cams;
+  a.splat = ws.splat; a.rect = ws.rect; a.tile_count = ws.tile_count; a.radii = radii;
+  const long long n = (long long)F * P;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  preprocess_kernel<<<blocks, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gvf

@@ -1,0 +1,135 @@
+"""Host side of the frame-batched canonical+delta Gaussian rasteriser.
+
+Mirrors what the reference does per render call in `renderers/gaussian_render.py:85-238`
+(`render`) and `:269-353` (`GaussianRenderer.render`): camera matrices, GaussianModel
+activations with delta, one `diff_gaussian_rasterization` call -- but for F frames at once
+and through the C ABI (`gvf_raster_forward`, include/gvf_b200.h).  torch supplies device
+memory and the current stream only.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+TILE = 16
+RB = {"splat": 0, "rect": 1, "tile_count": 2, "tile_start": 3, "keys": 4, "point_list": 5,
+      "final_T": 6, "n_contrib": 7, "status": 8, "scan_tmp": 9}
+
+
+def intrinsics_to_projection(intrinsics, near, far):
+    """reference renderers/gaussian_render.py:57-82, batched: (..., 3, 3) -> (..., 4, 4)."""
+    ret = torch.zeros(intrinsics.shape[:-2] + (4, 4), dtype=intrinsics.dtype, device=intrinsics.device)
+    ret[..., 0, 0] = 2 * intrinsics[..., 0, 0]
+    ret[..., 1, 1] = 2 * intrinsics[..., 1, 1]
+    ret[..., 0, 2] = 2 * intrinsics[..., 0, 2] - 1
+    ret[..., 1, 2] = -2 * intrinsics[..., 1, 2] + 1
+    ret[..., 2, 2] = far / (far - near)
+    ret[..., 2, 3] = near * far / (near - far)
+    ret[..., 3, 2] = 1.0
+    return ret
+
+
+def pack_cameras(extrinsics, intrinsics, near, far):
+    """(F,4,4) world->camera, (3,3)|(F,3,3) normalised intrinsics -> cams (F,32) =
+    [view^T | (persp @ view)^T] exactly as `GaussianRenderer.render` hands them over
+    (renderers/gaussian_render.py:302-321), plus tanfovx/tanfovy = 0.5 / focal (host floats
+    taken from frame 0: the reference uses one intrinsics matrix per object)."""
+    ext = extrinsics.float()
+    if ext.dim() == 2:
+        ext = ext[None]
+    intr = intrinsics.float()
+    if intr.dim() == 2:
+        intr = intr[None].expand(ext.shape[0], 3, 3)
+    persp = intrinsics_to_projection(intr, near, far)
+    full = persp @ ext
+    cams = torch.cat([ext.transpose(1, 2).reshape(-1, 16), full.transpose(1, 2).reshape(-1, 16)], dim=1)
+    i0 = intr[0].detach().cpu()
+    # tan(0.5 * 2 * atan(0.5 / f)) == 0.5 / f up to rounding; the reference goes through
+    # atan/tan in fp32 (renderers/gaussian_render.py:307-308, 102-103)
+    import math
+    tanfovx = math.tan(float(2 * torch.atan(0.5 / i0[0, 0])) * 0.5)
+    tanfovy = math.tan(float(2 * torch.atan(0.5 / i0[1, 1])) * 0.5)
+    return cams.contiguous(), tanfovx, tanfovy
+
+
+def make_params(H, W, tanfovx, tanfovy, const=None, kernel_size=0.1, scale_modifier=1.0,
+                bg=(1.0, 1.0, 1.0)):
+    p = _lib.RasterParams()
+    p.H, p.W, p.tanfovx, p.tanfovy = int(H), int(W), float(tanfovx), float(tanfovy)
+    p.kernel_size, p.scale_modifier = float(kernel_size), float(scale_modifier)
+    p.bg = (C.c_float * 3)(*[float(b) for b in bg])
+    if const is not None:
+        p.aabb = (C.c_float * 6)(*const["aabb"])
+        p.scale_bias, p.min_kernel = float(const["scale_bias"]), float(const["min_kernel"])
+        p.opacity_bias, p.softplus = float(const["opacity_bias"]), int(const["softplus"])
+    return p
+
+
+class Rasterizer:
+    """Owns the workspace for (F, P, H, W); grows `cap` when the tile-instance count needs it."""
+
+    def __init__(self, device="cuda", tiles_per_gaussian=8):
+        self.device = torch.device(device)
+        self.tpg = tiles_per_gaussian
+        self._key = None
+        self._ws = None
+        self.cap = 0
+
+    def _ensure(self, F, P, H, W, cap=None):
+        cap = int(cap or max(self.cap if self._key == (F, P, H, W) else 0, self.tpg * F * P, 1024))
+        if self._key != (F, P, H, W) or cap != self.cap:
+            nbytes = _lib.lib().gvf_raster_workspace_bytes(F, P, H, W, cap)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._key, self.cap = (F, P, H, W), cap
+        return self._ws
+
+    def buffer(self, name, dtype, count=None):
+        """View of a workspace sub-buffer (tests / backward)."""
+        F, P, H, W = self._key
+        L = _lib.lib()
+        off = L.gvf_raster_workspace_offset(RB[name], F, P, H, W, self.cap)
+        nxt = [L.gvf_raster_workspace_offset(i, F, P, H, W, self.cap) for i in range(len(RB))]
+        ends = sorted(o for o in nxt if o > off) + [self._ws.numel()]
+        v = self._ws[off:ends[0]].view(dtype)
+        return v if count is None else v[:count]
+
+    def status(self):
+        """(num_rendered, overflow, longest global-sorted tile) -- synchronises."""
+        s = self.buffer("status", torch.int32, 4).cpu()
+        return int(s[0]) & 0xffffffff, bool(s[1]), int(s[2])
+
+    def forward(self, prm, arrays, delta, cams, activated=False, subpixel_offset=None,
+                want_radii=True, out=None, check_overflow=True):
+        """arrays = (xyz, dc, scaling, rotation, opacity) fp32 contiguous device tensors.
+        Returns rgba (F,4,H,W) fp32 and radii (F,P) int32 (or None)."""
+        L = _lib.lib()
+        F = cams.shape[0]
+        P = arrays[0].shape[-2] if arrays[0].dim() >= 2 else arrays[0].shape[0]
+        for t in tuple(arrays) + (cams,) + ((delta,) if delta is not None else ()):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("rasteriser inputs must be contiguous fp32 CUDA tensors")
+        H, W = prm.H, prm.W
+        while True:
+            ws = self._ensure(F, P, H, W)
+            rgba = out if out is not None else torch.empty((F, 4, H, W), dtype=torch.float32, device=self.device)
+            radii = torch.empty((F, P), dtype=torch.int32, device=self.device) if want_radii else None
+            st = L.gvf_raster_forward(C.byref(prm), F, P, int(activated), *[_lib.ptr(a) for a in arrays],
+                                      _lib.ptr(delta), _lib.ptr(cams), _lib.ptr(subpixel_offset),
+                                      _lib.ptr(rgba), _lib.ptr(radii), _lib.ptr(ws), ws.numel(),
+                                      self.cap, _lib.current_stream())
+            _lib.check(st, "gvf_raster_forward")
+            if not check_overflow:
+                return rgba, radii
+            R, overflow, _ = self.status()
+            if not overflow:
+                return rgba, radii
+            self._ensure(F, P, H, W, cap=int(R * 1.25) + 1024)
+
+
+def canon_arrays(canon, device):
+    """GaussianModel raw tensors -> the five contiguous fp32 device arrays of the C ABI."""
+    P = canon["_xyz"].shape[0]
+    f = lambda t, n: t.detach().to(device=device, dtype=torch.float32).reshape(P, n).contiguous()
+    return (f(canon["_xyz"], 3), f(canon["_features_dc"], 3), f(canon["_scaling"], 3),
+            f(canon["_rotation"], 4), f(canon["_opacity"], 1).reshape(P).contiguous())
