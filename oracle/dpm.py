@@ -26,6 +26,22 @@ def cosine_betas(n=1000, max_beta=0.999):
                     dtype=np.float64)
 
 
+def spaced_betas(betas):
+    """SpacedDiffusion with every timestep kept still re-derives betas from the cumulative
+    product (model/respace.py:123-131); `diffusion.betas` handed to NoiseScheduleVP at
+    inference_dpm_latent.py:156 are these (last-bit different from cosine_betas)."""
+    ac = np.cumprod(1.0 - np.asarray(betas, dtype=np.float64), axis=0)
+    out, last = [], 1.0
+    for a in ac:
+        out.append(1 - a / last)
+        last = a
+    return np.array(out, dtype=np.float64)
+
+
+def reference_betas(n=1000):
+    return spaced_betas(cosine_betas(n))
+
+
 # ---------------------------------------------------------------- noise schedule
 def interpolate_fn(x, xp, yp):
     """model/dpmsolver.py:1270-1309, x [N,1], xp/yp [1,K]."""
@@ -228,13 +244,8 @@ class GaussianDiffusionV:
     rescale_timesteps=True) with no respacing: SpacedDiffusion == base diffusion."""
 
     def __init__(self, steps=1000):
-        betas = cosine_betas(steps)
-        self.betas = betas
+        betas = reference_betas(steps)
         self.num_timesteps = steps
-        ac = np.cumprod(1.0 - betas)
-        ac_prev = np.append(1.0, ac[:-1])
-        # SpacedDiffusion recomputes betas from alphas_cumprod (model/respace.py:123-131)
-        betas = np.array([1 - a / b for a, b in zip(ac, ac_prev)], dtype=np.float64)
         self.betas = betas
         ac = np.cumprod(1.0 - betas)
         ac_prev = np.append(1.0, ac[:-1])

@@ -1,0 +1,185 @@
+"""Generates tests/golden/*.pt by running the REFERENCE's own Python (imported from
+/root/reference with the stubs of _ref_import.py) on seeded inputs, CPU.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The fixtures are committed; tests/test_oracle_golden.py checks the oracle against them on
+any machine (the reference tree does not exist on the GPU box).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _ref_import  # noqa: E402
+
+_ref_import.install()
+
+from model.dit import DiT  # noqa: E402
+from model import dpmsolver as ref_dpm  # noqa: E402
+from model.autoencoder import GSKLTemporalVariationalAutoEncoder  # noqa: E402
+from utils.script_util import create_gaussian_diffusion  # noqa: E402
+
+DIFF_CFG = dict(steps=1000, learn_sigma=False, sigma_small=False, use_kl=False, noise_schedule="cosine",
+                predict_type="v", predict_xstart=False, rescale_timesteps=True, rescale_learned_sigmas=True)
+TINY_DIT = dict(resolution=32, in_channels=16, model_channels=64, static_cond_channels=14,
+                image_cond_channels=48, out_channels=16, num_blocks=2, num_heads=2, mlp_ratio=4,
+                pe_mode="ape", qk_rms_norm=True, use_fp16=True, no_temporal_attn=False)
+TINY_VAE = dict(depth=2, dim=96, queries_dim=96, output_dim=14, num_inputs=64, num_latents=32,
+                latent_dim=16, heads=3, dim_head=-1, weight_tie_layers=False, decoder_ff=False,
+                enable_flash_attn=False, num_timesteps=3)
+
+
+def rerandomise_zero_layers(model, std=0.02, seed=123):
+    """The reference zero-initialises adaLN / final layers (model/dit.py:414-427): re-draw them
+    so the golden outputs are non-trivial."""
+    g = torch.Generator().manual_seed(seed)
+    for p in model.parameters():
+        if p.abs().sum() == 0:
+            p.data = torch.randn(p.shape, generator=g) * std
+
+
+def gen_schedule():
+    diffusion = create_gaussian_diffusion(**DIFF_CFG)
+    ns = ref_dpm.NoiseScheduleVP("discrete", betas=torch.from_numpy(diffusion.betas))
+    ts = torch.tensor([1.0, 0.999, 0.75, 0.5, 0.123456, 0.01, 0.002, 0.001])
+    out = {"betas": torch.from_numpy(diffusion.betas), "total_N": ns.total_N,
+           "log_alpha_array": ns.log_alpha_array, "t_array": ns.t_array, "ts": ts,
+           "log_alpha": torch.stack([ns.marginal_log_mean_coeff(t[None]) for t in ts]),
+           "lambda": torch.stack([ns.marginal_lambda(t[None]) for t in ts]),
+           "std": torch.stack([ns.marginal_std(t[None]) for t in ts])}
+    lam = torch.tensor([-5.0, -2.0, 0.0, 1.5, 4.0])
+    out["inv_lambda_in"] = lam
+    out["inv_lambda"] = ns.inverse_lambda(lam)
+    return out, diffusion, ns
+
+
+def gen_dit(ns):
+    torch.manual_seed(0)
+    m = DiT(**TINY_DIT).eval()
+    rerandomise_zero_layers(m)
+    B, T, N = 2, 3, 32
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, T, N, 16, generator=g)
+    t = torch.tensor([812.25, 3.5])
+    cond = {"cond_images": torch.randn(B, T, 10, 48, generator=g),
+            "static_latent": torch.randn(B, 40, 14, generator=g),
+            "deformation_position_xyz": torch.rand(B, N, 3, generator=g) - 0.5}
+    out = {"cfg": TINY_DIT, "state_dict": {k: v.clone() for k, v in m.state_dict().items()},
+           "x": x, "t": t, **cond}
+    with torch.no_grad():
+        out["y_fp32"] = m(x, t, **cond)
+        with torch.autocast("cpu", dtype=torch.float16):
+            out["y_autocast_fp16"] = m(x, t, **cond).float()
+
+        # sampler goldens (B = 1 object)
+        c1 = {k: v[:1] for k, v in cond.items()}
+        u1 = dict(c1)
+        u1["cond_images"] = torch.zeros_like(c1["cond_images"])
+        noise = torch.randn(1, T, N, 16, generator=g)
+        out["noise"] = noise
+        for name, gs1, gs2 in (("g1", 1.0, 1.0), ("cfg", 2.0, 1.5)):
+            fn = ref_dpm.model_wrapper(m, ns, model_type="v", model_kwargs={}, guidance_type="classifier-free",
+                                       guidance_scale=gs1, guidance_scale2=gs2, condition=c1,
+                                       unconditional_condition=u1)
+            solver = ref_dpm.DPM_Solver(fn, ns, algorithm_type="dpmsolver++")
+            for steps in (6, 12):
+                out[f"sample_{name}_{steps}"] = solver.sample(x=noise, steps=steps, t_start=1.0, t_end=1 / 1000,
+                                                              order=2, skip_type="time_uniform", method="multistep")
+        fn = ref_dpm.model_wrapper(m, ns, model_type="v", model_kwargs={}, guidance_type="classifier-free",
+                                   guidance_scale=1.0, guidance_scale2=1.0, condition=c1, unconditional_condition=u1)
+        solver = ref_dpm.DPM_Solver(fn, ns, algorithm_type="dpmsolver++")
+        out["sample_adaptive"] = solver.sample(x=noise, steps=0, t_start=1.0, t_end=1 / 1000, order=2,
+                                               skip_type="time_uniform", method="adaptive")
+        out["eps_g1_t0.37"] = fn(noise, torch.tensor([0.37]))
+    return out
+
+
+def gen_vae():
+    torch.manual_seed(1)
+    vae = GSKLTemporalVariationalAutoEncoder(**TINY_VAE).eval()
+    rerandomise_zero_layers(vae, std=0.05)     # to_outputs and every bias are zero-initialised (:422-436)
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(2 * 3, 32, 16, generator=g)
+    q = torch.randn(2, 50, 14, generator=g) * 0.3
+    q[1, 40:] = 0.0
+    q[1, 40:, 10] = 1.0           # pad rows as pad_static_gs writes them (train_vae.py:478-479)
+    keep = ("layers.", "proj.", "gs_embedding.", "decoder_cross_attn.", "to_outputs.")   # decode-only weights
+    out = {"cfg": TINY_VAE, "z": z, "queries": q,
+           "state_dict": {k: v.clone() for k, v in vae.state_dict().items() if k.startswith(keep)}}
+    with torch.no_grad():
+        out["delta_fp32"] = vae.decode(z, q)
+        with torch.autocast("cpu", dtype=torch.float16):
+            out["delta_autocast_fp16"] = vae.decode(z, q).float()
+        vae.chunk_size = 16       # exercises the chunked path (autoencoder.py:592-607)
+        out["delta_fp32_chunked"] = vae.decode(z, q)
+    return out
+
+
+def gen_p_sample(diffusion):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 4, 8, 8, 8, generator=g)
+    W = torch.randn(4, 4, generator=g) * 0.5
+    model = lambda x, ts: torch.einsum("oc,bcdhw->bodhw", W, x) * torch.cos(ts / 1000.0).view(-1, 1, 1, 1, 1)
+    outs = {}
+    for tt in (999, 500, 1, 0):
+        torch.manual_seed(100 + tt)
+        o = diffusion.p_sample(model, x, torch.tensor([tt]))
+        torch.manual_seed(100 + tt)
+        noise = torch.randn_like(x)
+        outs[tt] = {"sample": o["sample"], "pred_xstart": o["pred_xstart"], "noise": noise}
+    return {"x": x, "W": W, "outs": outs}
+
+
+def gen_gaussian():
+    """GaussianModel activations (+ delta).  The reference hard-codes .cuda() at construction:
+    patch Tensor.cuda to identity for this CPU run."""
+    import types
+    for name in ("utils3d", "plyfile", "easydict"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["plyfile"].PlyData = sys.modules["plyfile"].PlyElement = object
+    sys.modules["easydict"].EasyDict = dict
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        from representations.gaussian.gaussian_model import GaussianModel
+        gm = GaussianModel(sh_degree=0, aabb=[-0.5, -0.5, -0.5, 1.0, 1.0, 1.0], mininum_kernel_size=0.0009,
+                           scaling_bias=0.004, opacity_bias=0.1, scaling_activation="softplus", device="cpu")
+        g = torch.Generator().manual_seed(5)
+        P = 257
+        gm._xyz = torch.rand(P, 3, generator=g)
+        gm._features_dc = torch.randn(P, 1, 3, generator=g)
+        gm._scaling = torch.randn(P, 3, generator=g) * 2
+        gm._rotation = torch.randn(P, 4, generator=g) * 0.1
+        gm._opacity = torch.randn(P, 1, generator=g) * 2
+        delta = torch.randn(P, 14, generator=g) * 0.1
+        out = {"raw": {k: getattr(gm, k).clone() for k in ("_xyz", "_features_dc", "_scaling", "_rotation", "_opacity")},
+               "delta": delta,
+               "scale_bias": gm.scale_bias.clone(), "opacity_bias": gm.opacity_bias.clone(),
+               "plain": [gm.get_xyz, gm.get_scaling, gm.get_rotation, gm.get_features, gm.get_opacity],
+               "with_delta": [gm.get_xyz_with_delta(delta[:, :3]), gm.get_scaling_with_delta(delta[:, 3:6]),
+                              gm.get_rotation_with_delta(delta[:, 6:10]),
+                              gm.get_features_with_delta(delta[:, 10:13].unsqueeze(1)),
+                              gm.get_opacity_with_delta(delta[:, 13:])]}
+    finally:
+        torch.Tensor.cuda = orig
+    return out
+
+
+def main():
+    sched, diffusion, ns = gen_schedule()
+    torch.save(sched, os.path.join(HERE, "schedule.pt"))
+    torch.save(gen_dit(ns), os.path.join(HERE, "dit_tiny.pt"))
+    torch.save(gen_vae(), os.path.join(HERE, "vae_tiny.pt"))
+    torch.save(gen_p_sample(diffusion), os.path.join(HERE, "p_sample.pt"))
+    torch.save(gen_gaussian(), os.path.join(HERE, "gaussian.pt"))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

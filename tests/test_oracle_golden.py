@@ -1,0 +1,134 @@
+"""Pins the CPU oracle to the reference: every fixture in tests/golden/ was produced by the
+reference's own Python (tests/golden/make_golden.py, run where /root/reference exists)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dit as ODIT
+from oracle import dpm as ODPM
+from oracle import gaussian as OG
+from oracle import raster as OR
+from oracle import vae as OVAE
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+load = lambda n: torch.load(os.path.join(G, n), weights_only=False)
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+# ------------------------------------------------------------------ schedule / DPM
+def test_noise_schedule_matches_reference():
+    g = load("schedule.pt")
+    betas = ODPM.reference_betas(1000)
+    assert np.array_equal(betas, g["betas"].numpy())          # float64, bit-exact
+    ns = ODPM.NoiseScheduleVP(betas)
+    assert ns.total_N == g["total_N"] == 996
+    assert torch.equal(ns.log_alpha_array, g["log_alpha_array"])
+    assert torch.equal(ns.t_array, g["t_array"])
+    for i, t in enumerate(g["ts"]):
+        assert torch.equal(ns.marginal_log_mean_coeff(t[None]), g["log_alpha"][i])
+        assert torch.equal(ns.marginal_lambda(t[None]), g["lambda"][i])
+        assert torch.equal(ns.marginal_std(t[None]), g["std"][i])
+    assert torch.equal(ns.inverse_lambda(g["inv_lambda_in"]), g["inv_lambda"])
+
+
+def _tiny_dit(g, precision="fp32"):
+    H = g["cfg"]["num_heads"]
+    sd = g["state_dict"]
+    return lambda x, t, **c: ODIT.dit_forward(sd, x, t, c["cond_images"], c["static_latent"],
+                                              c["deformation_position_xyz"], H, precision)
+
+
+def test_dit_forward_matches_reference_fp32():
+    g = load("dit_tiny.pt")
+    m = _tiny_dit(g)
+    y = m(g["x"], g["t"], cond_images=g["cond_images"], static_latent=g["static_latent"],
+          deformation_position_xyz=g["deformation_position_xyz"])
+    assert torch.allclose(y, g["y_fp32"], rtol=1e-4, atol=2e-6), (y - g["y_fp32"]).abs().max()
+
+
+def test_dit_forward_fp16_emulation_tracks_reference_autocast():
+    # the reference under (CPU) fp16 autocast vs our fp16-emulating oracle: same rounding points,
+    # different fp16 attention kernel -> agreement at the fp16 level, tolerance 2e-3 relative L2
+    g = load("dit_tiny.pt")
+    m = _tiny_dit(g, "fp16")
+    y = m(g["x"], g["t"], cond_images=g["cond_images"], static_latent=g["static_latent"],
+          deformation_position_xyz=g["deformation_position_xyz"])
+    assert rel(y, g["y_autocast_fp16"]) < 2e-3
+    assert rel(y, g["y_fp32"]) < 3e-3
+
+
+@pytest.mark.parametrize("name,gs", [("g1", (1.0, 1.0)), ("cfg", (2.0, 1.5))])
+@pytest.mark.parametrize("steps", [6, 12])
+def test_dpm_multistep_matches_reference(name, gs, steps):
+    g = load("dit_tiny.pt")
+    ns = ODPM.NoiseScheduleVP(ODPM.reference_betas(1000))
+    cond = {k: g[k][:1] for k in ("cond_images", "static_latent", "deformation_position_xyz")}
+    unc = dict(cond)
+    unc["cond_images"] = torch.zeros_like(cond["cond_images"])
+    fn = ODPM.make_model_fn(_tiny_dit(g), ns, cond, unc, *gs)
+    s = ODPM.DPMSolverPP(fn, ns)
+    x = s.sample(g["noise"], steps=steps, t_start=1.0, t_end=1 / 1000, order=2, method="multistep")
+    assert s.nfe == steps
+    ref = g[f"sample_{name}_{steps}"]
+    assert torch.allclose(x, ref, rtol=1e-3, atol=2e-5), (x - ref).abs().max()
+
+
+def test_dpm_adaptive_and_eps_match_reference():
+    g = load("dit_tiny.pt")
+    ns = ODPM.NoiseScheduleVP(ODPM.reference_betas(1000))
+    cond = {k: g[k][:1] for k in ("cond_images", "static_latent", "deformation_position_xyz")}
+    fn = ODPM.make_model_fn(_tiny_dit(g), ns, cond, None)
+    eps = fn(g["noise"], torch.tensor([0.37]))
+    assert torch.allclose(eps, g["eps_g1_t0.37"], rtol=1e-4, atol=1e-5)
+    s = ODPM.DPMSolverPP(fn, ns)
+    x = s.sample(g["noise"], t_start=1.0, t_end=1 / 1000, order=2, method="adaptive")
+    assert s.nfe == 28                                            # the reference prints "adaptive solver nfe 28"
+    assert torch.allclose(x, g["sample_adaptive"], rtol=1e-3, atol=5e-5), (x - g["sample_adaptive"]).abs().max()
+
+
+def test_p_sample_matches_reference():
+    g = load("p_sample.pt")
+    gd = ODPM.GaussianDiffusionV(1000)
+    W = g["W"]
+    model = lambda x, ts: torch.einsum("oc,bcdhw->bodhw", W, x) * torch.cos(ts / 1000.0).view(-1, 1, 1, 1, 1)
+    for tt, o in g["outs"].items():
+        r = gd.p_sample(model, g["x"], torch.tensor([tt]), o["noise"])
+        assert torch.allclose(r["pred_xstart"], o["pred_xstart"], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(r["sample"], o["sample"], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ VAE decode
+def test_vae_decode_matches_reference():
+    g = load("vae_tiny.pt")
+    heads, T = g["cfg"]["heads"], g["cfg"]["num_timesteps"]
+    d32 = OVAE.vae_decode(g["state_dict"], g["z"], g["queries"], heads, T, "fp32")
+    assert d32.shape == g["delta_fp32"].shape
+    assert torch.allclose(d32, g["delta_fp32"], rtol=1e-4, atol=1e-5), (d32 - g["delta_fp32"]).abs().max()
+    dc = OVAE.vae_decode(g["state_dict"], g["z"], g["queries"], heads, T, "fp32", chunk_size=16)
+    assert torch.allclose(dc, g["delta_fp32_chunked"], rtol=1e-4, atol=1e-5)
+    d16 = OVAE.vae_decode(g["state_dict"], g["z"], g["queries"], heads, T, "fp16")
+    assert rel(d16, g["delta_autocast_fp16"]) < 4e-3
+    assert rel(d16, g["delta_fp32"]) < 6e-3
+
+
+# ------------------------------------------------------------------ Gaussian activations
+def test_gaussian_activations_match_reference():
+    g = load("gaussian.pt")
+    const = OG.model_constants()
+    assert const["scale_bias"] == pytest.approx(float(g["scale_bias"]), abs=0)
+    assert const["opacity_bias"] == pytest.approx(float(g["opacity_bias"]), abs=0)
+    for key, delta in (("plain", None), ("with_delta", g["delta"])):
+        ours = OG.activate(g["raw"], delta, const)
+        for a, b in zip(ours, g[key]):
+            assert torch.equal(a, b)
+    # the C oracle (reproducible gvf_math transcendentals) agrees with torch to a few ulp
+    prm = OR.make_params(64, 64, 0.4, 0.4, const)
+    c = OR.activate(prm, {k: v.numpy() for k, v in g["raw"].items()}, g["delta"].numpy())
+    t = [x.reshape(x.shape[0], -1).numpy() for x in g["with_delta"]]
+    for a, b in zip(c, t):
+        np.testing.assert_allclose(a, b, rtol=3e-6, atol=1e-7)

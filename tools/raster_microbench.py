@@ -1,0 +1,41 @@
+"""Times the rasteriser alone: F frames x P Gaussians, CUDA events on the current stream."""
+import argparse, json, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gvfdiffusion_b200 import raster as R, synthetic as S
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=24)
+ap.add_argument("--voxels", type=int, default=2048)
+ap.add_argument("--res", type=int, default=512)
+ap.add_argument("--iters", type=int, default=20)
+a = ap.parse_args()
+dev = "cuda"
+canon = S.canonical_gaussians(num_voxels=a.voxels)
+P = canon["_xyz"].shape[0]
+delta = S.raster_delta(a.frames, P).to(dev)
+cams, tfx, tfy = R.pack_cameras(S.orbit_extrinsics(a.frames), S.intrinsics(), 0.8, 1.6)
+cams = cams.to(dev)
+prm = R.make_params(a.res, a.res, tfx, tfy, S.gaussian_constants())
+rz = R.Rasterizer(dev)
+arrays = R.canon_arrays(canon, dev)
+out = torch.empty((a.frames, 4, a.res, a.res), device=dev)
+for _ in range(3):
+    rz.forward(prm, arrays, delta, cams, out=out, want_radii=False)
+Rn, ovf, longest = rz.status()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ts = []
+for _ in range(a.iters):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rz.forward(prm, arrays, delta, cams, out=out, want_radii=False, check_overflow=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ts.sort()
+ms = ts[len(ts) // 2]
+alg = a.frames * (112 * P + 16 * a.res * a.res) + 64 * Rn
+print(json.dumps({"frames": a.frames, "P": P, "res": a.res, "num_rendered": Rn, "overflow": ovf,
+                  "ms_median": ms, "ms_min": ts[0], "alg_bytes": alg, "GBps": alg / ms / 1e6,
+                  "frames_per_s": a.frames / ms * 1e3}))
