@@ -1,0 +1,390 @@
+// attn.cu -- dense multi-head attention forward on tcgen05 tensor cores (sm_100a).
+//
+// Replaces `flash_attn.flash_attn_{func,kvpacked_func,qkvpacked_func}` (FA2, mma.sync) as
+// reached from reference model/attention/full_attn.py:74-140 (DiT spatial / image-cross /
+// static-cross attention, head dim 32) and model/autoencoder.py:132-144 (motion-VAE self /
+// decoder cross attention, head dim 64).  fp16 in / out, fp32 softmax statistics, no mask,
+// softmax scale passed in.  Layout [N, L, H, d] with arbitrary (16 B aligned) strides, so
+// packed qkv / kv tensors and the temporal (strided) view are addressed in place by TMA.
+//
+// One CTA = one (batch, head) x up to two 128-row query tiles ("A" and "B", ping-pong):
+//   warp 0      TMA producer: Q tiles once, then K/V tiles [128 x d] through a 4-stage
+//               mbarrier ring (SWIZZLE_64B for d=32, SWIZZLE_128B for d=64)
+//   warp 1      single-thread tcgen05.mma issuer:
+//                 S = Q K^T   (SS: A,B K-major from smem, M=128 N=128 K=d)   -> TMEM [128 cols]
+//                 O' = P V    (TS: A = P from TMEM, B = V tile MN-major, M=128 N=d K=128)
+//               issue order QK(j+1,X) right behind PV(j,X) so the tensor pipe works on one
+//               query tile while the other tile's softmax runs
+//   warps 2-5   softmax of tile A, warps 6-9 softmax of tile B: thread = one query row
+//               (TMEM lane); tcgen05.ld S -> running max / exp2 / row sum in registers ->
+//               P (fp16) written back over S's columns with tcgen05.st; the per-tile partial
+//               product O' is read back from TMEM one iteration later and accumulated in
+//               registers (O <- O * alpha + O'), so no TMEM read-modify-write and no
+//               correction warpgroup is needed for d <= 64.
+// With d = 32 the MUFU exp2 (1 per score) bounds the kernel, not the MMA pipe: 128x128 scores
+// cost 1024 MUFU cycles/SM vs 256 tensor cycles -- see DESIGN.md for the roofline.
+#include "../../include/gvf_b200.h"
+#include "tc_common.cuh"
+#include "tma_host.h"
+
+namespace gvf {
+using namespace tc;
+
+constexpr int kAttnStages = 4;
+
+__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnArgs {
+  __half* o;
+  long long o_stride_b, o_stride_l, o_stride_h;   // elements
+  int Lq, Lk, H;
+  int q_batch_mul, kv_batch_mul;                  // 0: tensor shared across the batch
+  float scale_log2e;
+};
+
+template <int D>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  constexpr int ROWB = D * 2;                      // bytes per smem row
+  constexpr int TILE_BYTES = 128 * ROWB;           // one [128 x D] fp16 tile
+  constexpr uint64_t SWZ = (D == 32) ? SWZ_64B : SWZ_128B;
+  constexpr uint32_t SBO = 8 * ROWB;
+  constexpr int S = kAttnStages;
+  constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, kv_full[S], kv_empty[S], s_full[2], p_full[2], o_final[2];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                              // 2 tiles
+  uint8_t* sKV = smem + 2 * TILE_BYTES;            // S x (K tile, V tile)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qblk = blockIdx.x, h = blockIdx.y, nb = blockIdx.z;
+  const int q0 = qblk * 256;
+  const int nq = (a.Lq - q0 > 128) ? 2 : 1;
+  const int n_kv = (a.Lk + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&o_final[x], 1); }
+    fence_barrier_init();
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&q_full, nq * TILE_BYTES);
+      for (int x = 0; x < nq; ++x)
+        tma_load_4d(sQ + x * TILE_BYTES, &mapQ, &q_full, 0, h, q0 + x * 128, nb * a.q_batch_mul);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % S;
+        mbar_wait(&kv_empty[s], ((j / S) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+        tma_load_4d(sKV + s * 2 * TILE_BYTES, &mapK, &kv_full[s], 0, h, j * 128, nb * a.kv_batch_mul);
+        tma_load_4d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &mapV, &kv_full[s], 0, h, j * 128,
+                    nb * a.kv_batch_mul);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
+      const uint32_t idesc_pv = make_idesc_f16(128, D, 0, 1);
+      const uint32_t sq = smem_u32(sQ), skv = smem_u32(sKV);
+      auto issue_qk = [&](int x, int stage) {
+        const uint32_t qa = sq + x * TILE_BYTES, ka = skv + stage * 2 * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          mma_ss(tmem + (x ? TM_S1 : TM_S0), make_smem_desc(qa + k * 32, 16, SBO, SWZ),
+                 make_smem_desc(ka + k * 32, 16, SBO, SWZ), idesc_qk, k != 0);
+      };
+      auto issue_pv = [&](int x, int stage) {
+        const uint32_t va = skv + stage * 2 * TILE_BYTES + TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          mma_ts(tmem + (x ? TM_O1 : TM_O0), tmem + (x ? TM_S1 : TM_S0) + k * 8,
+                 make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv, k != 0);
+      };
+      mbar_wait(&q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      for (int x = 0; x < nq; ++x) {
+        issue_qk(x, 0);
+        tc_commit(&s_full[x]);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % S;
+        const bool more = j + 1 < n_kv;
+        const int s1 = (j + 1) % S;
+        if (more) {
+          mbar_wait(&kv_full[s1], ((j + 1) / S) & 1);
+          tc_fence_after();
+        }
+        for (int x = 0; x < nq; ++x) {
+          mbar_wait(&p_full[x], j & 1);
+          tc_fence_after();
+          issue_pv(x, s);
+          if (more) {
+            issue_qk(x, s1);
+            tc_commit(&s_full[x]);
+          } else {
+            tc_commit(&o_final[x]);
+          }
+        }
+        tc_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int x = (warp - 2) >> 2;                 // 0: tile A, 1: tile B
+    if (x < nq) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;         // row inside the tile == TMEM lane
+      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+      const uint32_t tS = tmem + (x ? TM_S1 : TM_S0) + lane_addr;
+      const uint32_t tO = tmem + (x ? TM_O1 : TM_O0) + lane_addr;
+      const float c = a.scale_log2e;
+      float O[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) O[i] = 0.f;
+      float m = -INFINITY, l = 0.f;
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&s_full[x], j & 1);
+        tc_fence_after();
+        if (j > 0) {                               // fold in O' = P_{j-1} V_{j-1}
+#pragma unroll
+          for (int d0 = 0; d0 < D; d0 += 32) {
+            uint32_t r[32];
+            tmem_ld_x32(tO + d0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) O[d0 + i] += __uint_as_float(r[i]);
+          }
+        }
+        const int valid = a.Lk - j * 128;          // columns >= valid are padding (last tile)
+        // pass 1: row max
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(tS + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float sv = (c0 + i < valid) ? __uint_as_float(r[i]) : -INFINITY;
+            mx = fmaxf(mx, sv);
+          }
+        }
+        const float m_new = fmaxf(m, mx);
+        const float alpha = fast_exp2((m - m_new) * c);
+        m = m_new;
+        l *= alpha;
+#pragma unroll
+        for (int i = 0; i < D; ++i) O[i] *= alpha;
+        const float mc = m_new * c;
+        // pass 2: p = exp2(s*c - m*c), row sum, P -> TMEM (fp16 pairs over S's first 64 columns)
+        float lsum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(tS + c0, r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), c, -mc));
+            float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), c, -mc));
+            if (c0 + i >= valid) p0 = 0.f;
+            if (c0 + i + 1 >= valid) p1 = 0.f;
+            lsum += p0 + p1;
+            const __half2 hp = __floats2half2_rn(p0, p1);
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+          }
+          tmem_st_x16(tS + (c0 >> 1), pk);
+        }
+        l += lsum;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
+      }
+      // last partial product
+      mbar_wait(&o_final[x], 0);
+      tc_fence_after();
+#pragma unroll
+      for (int d0 = 0; d0 < D; d0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(tO + d0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) O[d0 + i] += __uint_as_float(r[i]);
+      }
+      const int qi = q0 + x * 128 + row;
+      if (qi < a.Lq) {
+        const float inv = 1.0f / l;
+        __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h;
+#pragma unroll
+        for (int i = 0; i < D; i += 8) {
+          __align__(16) __half hh[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(O[i + t] * inv);
+          *reinterpret_cast<uint4*>(op + i) = *reinterpret_cast<uint4*>(hh);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------
+// Short-sequence attention on CUDA cores (L <= 32): the DiT temporal self-attention
+// (reference model/dit.py:254-260: sequences of T = 24 frames per latent token, d = 32).
+// 0.6 GFLOP per block -- latency-, not tensor-bound; a 128-row MMA tile would be 81 % padding.
+// One warp per (batch, head); lane = query; K/V rows staged in shared memory.
+template <int D>
+__global__ void __launch_bounds__(256) attn_small_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                         const __half* __restrict__ v, __half* __restrict__ o,
+                                                         long long nbh, int H, int L, long long sb, long long sl,
+                                                         long long sh, long long osb, long long osl, long long osh,
+                                                         float scale) {
+  __shared__ __align__(16) __half sK[8][32][D];
+  __shared__ __align__(16) __half sV[8][32][D];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long bh = (long long)blockIdx.x * 8 + w;
+  if (bh >= nbh) return;
+  const long long b = bh / H;
+  const int h = (int)(bh - b * H);
+  const __half* qb = q + b * sb + (long long)h * sh;
+  const __half* kb = k + b * sb + (long long)h * sh;
+  const __half* vb = v + b * sb + (long long)h * sh;
+  float qv[D];
+  if (lane < L) {
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      const uint4 tq = *reinterpret_cast<const uint4*>(qb + (long long)lane * sl + i * 8);
+      const __half* hq = reinterpret_cast<const __half*>(&tq);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) qv[i * 8 + t] = __half2float(hq[t]);
+      *reinterpret_cast<uint4*>(&sK[w][lane][i * 8]) = *reinterpret_cast<const uint4*>(kb + (long long)lane * sl + i * 8);
+      *reinterpret_cast<uint4*>(&sV[w][lane][i * 8]) = *reinterpret_cast<const uint4*>(vb + (long long)lane * sl + i * 8);
+    }
+  }
+  __syncwarp();
+  if (lane >= L) return;
+  float sc[32];
+  float mx = -INFINITY;
+  for (int j = 0; j < L; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc += qv[i] * __half2float(sK[w][j][i]);
+    sc[j] = acc * scale;
+    mx = fmaxf(mx, sc[j]);
+  }
+  float l = 0.f;
+  float ov[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) ov[i] = 0.f;
+  for (int j = 0; j < L; ++j) {
+    const float p = __expf(sc[j] - mx);
+    l += p;
+    const float ph = __half2float(__float2half_rn(p));
+#pragma unroll
+    for (int i = 0; i < D; ++i) ov[i] += ph * __half2float(sV[w][j][i]);
+  }
+  const float inv = 1.0f / l;
+  __half* ob = o + b * osb + (long long)lane * osl + (long long)h * osh;
+#pragma unroll
+  for (int i = 0; i < D; i += 8) {
+    __align__(16) __half hh[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(ov[i + t] * inv);
+    *reinterpret_cast<uint4*>(ob + i) = *reinterpret_cast<uint4*>(hh);
+  }
+}
+
+template <int D>
+static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
+                       int Nb, cudaStream_t st) {
+  constexpr int SMEM = (2 + 2 * kAttnStages) * 128 * D * 2 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+      return GVF_ERR_CUDA;
+    configured = true;
+  }
+  dim3 grid((a.Lq + 255) / 256, a.H, Nb);
+  attn_fwd_kernel<D><<<grid, 320, SMEM, st>>>(mq, mk, mv, a);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+}  // namespace gvf
+
+using namespace gvf;
+
+// q [Nb_q, Lq, H, D], k/v [Nb_kv, Lk, H, D] fp16 with element strides (batch, seq, head);
+// innermost dim contiguous.  Nb_q / Nb_kv may be 1 (tensor shared by all Nb batches).
+extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void* v, void* o, int Nb, int Lq,
+                                        int Lk, int H, int D, const long long* q_strides,
+                                        const long long* k_strides, const long long* v_strides,
+                                        const long long* o_strides, int q_shared, int kv_shared,
+                                        float scale, void* stream) {
+  if (!q || !k || !v || !o || !q_strides || !k_strides || !v_strides || !o_strides) return GVF_ERR_INVALID;
+  if (Nb <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return GVF_ERR_INVALID;
+  if (D != 32 && D != 64) return GVF_ERR_UNSUPPORTED;
+  for (int i = 0; i < 3; ++i)
+    if ((q_strides[i] % 8) || (k_strides[i] % 8) || (v_strides[i] % 8) || (o_strides[i] % 8)) return GVF_ERR_INVALID;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15) return GVF_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (D == 32 && Lq <= 32 && Lk == Lq && !q_shared && !kv_shared && q_strides[0] == k_strides[0] &&
+      q_strides[1] == k_strides[1] && q_strides[2] == k_strides[2] && q_strides[0] == v_strides[0] &&
+      q_strides[1] == v_strides[1] && q_strides[2] == v_strides[2]) {
+    const long long nbh = (long long)Nb * H;
+    const unsigned blocks = (unsigned)((nbh + 7) / 8);
+    attn_small_kernel<32><<<blocks, 256, 0, st>>>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o,
+                                                  nbh, H, Lq, q_strides[0], q_strides[1], q_strides[2],
+                                                  o_strides[0], o_strides[1], o_strides[2], scale);
+    return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+  }
+
+  CUtensorMap mq, mk, mv;
+  const CUtensorMapSwizzle sw = swizzle_for_bytes(D * 2);
+  const uint32_t box[4] = {(uint32_t)D, 1, 128, 1};
+  auto mk_map = [&](CUtensorMap* m, const void* p, int L, int nbt, const long long* s) {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)L, (uint64_t)nbt};
+    // a shared tensor has a single batch entry; give it a harmless non-zero stride
+    const uint64_t strides[4] = {1, (uint64_t)s[2], (uint64_t)s[1], (uint64_t)(nbt > 1 ? s[0] : (long long)L * s[1])};
+    return make_tmap_f16(m, p, 4, dims, strides, box, sw);
+  };
+  if (!mk_map(&mq, q, Lq, q_shared ? 1 : Nb, q_strides)) return GVF_ERR_CUDA;
+  if (!mk_map(&mk, k, Lk, kv_shared ? 1 : Nb, k_strides)) return GVF_ERR_CUDA;
+  if (!mk_map(&mv, v, Lk, kv_shared ? 1 : Nb, v_strides)) return GVF_ERR_CUDA;
+  AttnArgs a;
+  a.o = (__half*)o;
+  a.o_stride_b = o_strides[0]; a.o_stride_l = o_strides[1]; a.o_stride_h = o_strides[2];
+  a.Lq = Lq; a.Lk = Lk; a.H = H;
+  a.q_batch_mul = q_shared ? 0 : 1;
+  a.kv_batch_mul = kv_shared ? 0 : 1;
+  a.scale_log2e = scale * 1.4426950408889634f;
+  return D == 32 ? launch_attn<32>(mq, mk, mv, a, Nb, st) : launch_attn<64>(mq, mk, mv, a, Nb, st);
+}

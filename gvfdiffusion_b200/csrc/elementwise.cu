@@ -1,0 +1,577 @@
+// elementwise.cu -- the small fused kernels around the GEMM / attention tiles of the DiT and
+// motion-VAE paths: LayerNorm+adaLN modulate, per-head q/k RMS-norm, timestep embedding + all
+// adaLN modulation vectors of a forward in two launches, small-K linears (K = 14 / 16),
+// position embeddings, GEGLU, the final layer and the DPM-Solver++ state update.
+//
+// Each kernel names the reference lines it replaces.  Rounding points follow the fp16
+// autocast the reference runs under (inference_dpm_latent.py:122-125): Linear outputs are
+// fp16, LayerNorm / residual stream / sampler state fp32.  HBM-bound, one pass over the data.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gvf_b200.h"
+
+namespace gvf {
+
+__device__ __forceinline__ float r16f(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm (no affine or affine) + optional adaLN modulate -> fp16 GEMM operand.
+// reference model/dit.py:246-247,254-255,263,268,273-274 (norm1..5 + modulate) and
+// model/autoencoder.py:73-88 (PreNorm).  One warp per row, row kept in registers.
+template <typename TIn, int C, bool VEC>
+__global__ void __launch_bounds__(256) ln_mod_kernel(const TIn* __restrict__ x, __half* __restrict__ out,
+                                                     int M, float eps, const float* __restrict__ w,
+                                                     const float* __restrict__ bvec,
+                                                     const __half* __restrict__ shift,
+                                                     const __half* __restrict__ scale, int mod_stride,
+                                                     int rows_per_batch) {
+  constexpr int PER = C / 32;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[PER];
+  const TIn* xr = x + (size_t)row * C;
+  if constexpr (!VEC) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      if constexpr (sizeof(TIn) == 4) v[i] = xr[i * 32 + lane];
+      else v[i] = __half2float(xr[i * 32 + lane]);
+    }
+  } else
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if constexpr (sizeof(TIn) == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(xr + c);
+      v[i * 4] = t.x; v[i * 4 + 1] = t.y; v[i * 4 + 2] = t.z; v[i * 4 + 3] = t.w;
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(xr + c);
+      const __half2 a = *reinterpret_cast<const __half2*>(&t.x), b2 = *reinterpret_cast<const __half2*>(&t.y);
+      v[i * 4] = __low2float(a); v[i * 4 + 1] = __high2float(a);
+      v[i * 4 + 2] = __low2float(b2); v[i * 4 + 3] = __high2float(b2);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+  const int b = (shift || scale) ? row / rows_per_batch : 0;
+  __half* orow = out + (size_t)row * C;
+  if constexpr (!VEC) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = i * 32 + lane;
+      float y = (v[i] - mean) * rstd;
+      if (w) y = y * w[c] + bvec[c];
+      if (scale) y = y * (1.0f + __half2float(scale[(size_t)b * mod_stride + c])) +
+                     __half2float(shift[(size_t)b * mod_stride + c]);
+      orow[c] = __float2half_rn(y);
+    }
+  } else
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    __align__(8) __half h[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float y = (v[i * 4 + t] - mean) * rstd;
+      if (w) y = y * w[c + t] + bvec[c + t];
+      if (scale) y = y * (1.0f + __half2float(scale[(size_t)b * mod_stride + c + t])) +
+                     __half2float(shift[(size_t)b * mod_stride + c + t]);
+      h[t] = __float2half_rn(y);
+    }
+    *reinterpret_cast<uint2*>(orow + c) = *reinterpret_cast<uint2*>(h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// MultiHeadRMSNorm on q and k in place (reference model/attention/modules.py:8-15,122-125):
+// x <- fp16( x.float() / max(||x||, 1e-12) * gamma[h] * sqrt(d) ).  buf rows of `ld` halfs;
+// q heads start at column 0, k heads at column k_off.  One thread per (row, head, q|k).
+template <int D>
+__global__ void __launch_bounds__(256) rmsnorm_heads_kernel(__half* __restrict__ buf, long long rows, int ld,
+                                                            int H, int k_off,
+                                                            const float* __restrict__ gq,
+                                                            const float* __restrict__ gk) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * H * 2) return;
+  const int which = (int)(gid % 2);
+  const int h = (int)((gid / 2) % H);
+  const long long row = gid / (2 * H);
+  __half* p = buf + row * ld + (which ? k_off : 0) + h * D;
+  const float* g = (which ? gk : gq) + h * D;
+  float v[D];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p + i * 8);
+    const __half* hh = reinterpret_cast<const __half*>(&t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[i * 8 + j] = __half2float(hh[j]); ss += v[i * 8 + j] * v[i * 8 + j]; }
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  const float sq = sqrtf((float)D);
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) {
+    __align__(16) __half o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(v[i * 8 + j] * inv * g[i * 8 + j] * sq);
+    *reinterpret_cast<uint4*>(p + i * 8) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// TimestepEmbedder (reference model/dit.py:59-100): t[B] -> silu(t_emb)[B,C] as fp16 values.
+// One CTA per batch element, C threads.  W0 [C,256], W2 [C,C] fp16; biases fp32 (fp16-valued).
+__global__ void temb_kernel(const float* __restrict__ t, const __half* __restrict__ W0,
+                            const float* __restrict__ b0, const __half* __restrict__ W2,
+                            const float* __restrict__ b2, int C, int F,
+                            __half* __restrict__ temb_out, __half* __restrict__ silu_out) {
+  extern __shared__ float sh[];
+  float* emb = sh;        // F
+  float* hid = sh + F;    // C
+  const int b = blockIdx.x, j = threadIdx.x;
+  const float tv = t[b];
+  const int half = F / 2;
+  for (int i = j; i < half; i += blockDim.x) {
+    const float freq = expf(-9.210340371976184f * (float)i / (float)half);
+    const float a = tv * freq;
+    emb[i] = r16f(cosf(a));
+    emb[half + i] = r16f(sinf(a));
+  }
+  __syncthreads();
+  if (j < C) {
+    float acc = 0.f;
+    const __half* wr = W0 + (size_t)j * F;
+    for (int i = 0; i < F; ++i) acc += __half2float(wr[i]) * emb[i];
+    hid[j] = r16f(silu(r16f(acc + b0[j])));
+  }
+  __syncthreads();
+  if (j < C) {
+    float acc = 0.f;
+    const __half* wr = W2 + (size_t)j * C;
+    for (int i = 0; i < C; ++i) acc += __half2float(wr[i]) * hid[i];
+    const float te = r16f(acc + b2[j]);
+    temb_out[(size_t)b * C + j] = __float2half_rn(te);
+    silu_out[(size_t)b * C + j] = __float2half_rn(silu(te));
+  }
+}
+
+// All adaLN modulation vectors of one forward: out[b, r] = fp16( W[r,:] . s[b,:] + bias[r] ),
+// W = the 12 x (adaLN_modulation.1 | adaLN_modulation_temporal.1) + final adaLN rows
+// concatenated [R, C] (reference model/dit.py:240-242,299).  One warp per output row.
+template <int MAXB>
+__global__ void __launch_bounds__(256) mod_gemv_kernel(const __half* __restrict__ W, const float* __restrict__ bias,
+                                                       const __half* __restrict__ s, int B, int R, int C,
+                                                       __half* __restrict__ out) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float acc[MAXB];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+  const __half* wr = W + (size_t)r * C;
+  for (int c = lane * 8; c < C; c += 256) {
+    const uint4 t = *reinterpret_cast<const uint4*>(wr + c);
+    const __half* wh = reinterpret_cast<const __half*>(&t);
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+      if (b < B) {
+        const uint4 u = *reinterpret_cast<const uint4*>(s + (size_t)b * C + c);
+        const __half* sh = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[b] += __half2float(wh[k]) * __half2float(sh[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) {
+    if (b < B) {
+      const float v = warp_sum(acc[b]);
+      if (lane == 0) out[(size_t)b * R + r] = __float2half_rn(v + bias[r]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Small-K linear on CUDA cores: y[m, n] = fp16( x[m,:K] . W[n,:K] + b[n] ) (+ add[m % add_rows, n])
+// used for input_layer (16->512, + APE; reference model/dit.py:457,470-472), static_cond_proj
+// (14->512, :465), VAE proj (16->768, autoencoder.py:585) and gs_embedding (14->768, :389).
+// x fp32 (rounded to fp16 on load like autocast does), W fp16 [N,K], out fp32 or fp16.
+template <typename TOut>
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, int ldx,
+                                                           const __half* __restrict__ W,
+                                                           const float* __restrict__ bias, int M, int N,
+                                                           int K, const float* __restrict__ add,
+                                                           int add_rows, TOut* __restrict__ out) {
+  __shared__ float xs[8][32];
+  const int row0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 8 * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    xs[r][k] = (row0 + r < M) ? r16f(x[(size_t)(row0 + r) * ldx + k]) : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  float wv[32];
+  for (int k = 0; k < K; ++k) wv[k] = __half2float(W[(size_t)n * K + k]);
+  const float bn = bias ? bias[n] : 0.f;
+  for (int r = 0; r < 8 && row0 + r < M; ++r) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc += xs[r][k] * wv[k];
+    float y = r16f(acc + bn);
+    if (add) y += add[(size_t)((row0 + r) % add_rows) * N + n];
+    if constexpr (sizeof(TOut) == 4) out[(size_t)(row0 + r) * N + n] = y;
+    else out[(size_t)(row0 + r) * N + n] = __float2half_rn(y);
+  }
+}
+
+// AbsolutePositionEmbedder (reference model/dit.py:16-56): xyz [R,3] -> [R, C] fp32:
+// per coordinate [sin(fd), cos(fd)], fd = C/3/2, freq_j = 10000^(-j/fd); zero padded to C.
+__global__ void ape_kernel(const float* __restrict__ xyz, int R, int C, float* __restrict__ out) {
+  const int fd = C / 3 / 2;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)R * C) return;
+  const int r = (int)(gid / C), c = (int)(gid - (long long)r * C);
+  float v = 0.f;
+  if (c < 6 * fd) {
+    const int coord = c / (2 * fd), w = c - coord * 2 * fd;
+    const int j = w < fd ? w : w - fd;
+    const float freq = 1.0f / powf(10000.0f, (float)j / (float)fd);
+    const float a = xyz[(size_t)r * 3 + coord] * freq;
+    v = w < fd ? sinf(a) : cosf(a);
+  }
+  out[gid] = v;
+}
+
+// VAE query embedding (reference model/autoencoder.py:250-301,389-391,560):
+//   out = fp16( LN_1e-6( LN_1e-5(gs[q]) + LN_1e-5(PointEmbed(q.xyz)) ) )
+// gs [Q, C] fp16 = Linear(14->C)(q) (small_linear above).  PointEmbed runs under fp16 autocast
+// in the reference (einsum is autocast-to-fp16): coordinate, omega and their product are
+// rounded to fp16 before sin/cos, whose results are rounded to fp16 too.
+// omega_j = 10000^(-j / (E/2)), E = C/6, computed in float64 then rounded.  Warp per query.
+template <int C>
+__global__ void __launch_bounds__(256) query_embed_kernel(const float* __restrict__ queries, int ldq,
+                                                          const __half* __restrict__ gs, int Q,
+                                                          __half* __restrict__ out) {
+  constexpr int PER = C / 32, E = C / 6;
+  const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (qi >= Q) return;
+  float g[PER], p[PER];
+  float sg = 0.f, sp = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = i * 32 + lane;
+    g[i] = __half2float(gs[(size_t)qi * C + c]);
+    const int coord = c / (2 * E), w = c - coord * 2 * E;
+    const int j = w < E ? w : w - E;
+    const double om = 1.0 / pow(10000.0, (double)j / ((double)E / 2.0));
+    const float x16 = r16f(queries[(size_t)qi * ldq + coord]);
+    const float a = r16f(x16 * r16f((float)om));
+    p[i] = r16f(w < E ? sinf(a) : cosf(a));
+    sg += g[i];
+    sp += p[i];
+  }
+  const float mg = warp_sum(sg) / C, mp = warp_sum(sp) / C;
+  float vg = 0.f, vp = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { vg += (g[i] - mg) * (g[i] - mg); vp += (p[i] - mp) * (p[i] - mp); }
+  const float rg = rsqrtf(warp_sum(vg) / C + 1e-5f), rp = rsqrtf(warp_sum(vp) / C + 1e-5f);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { g[i] = (g[i] - mg) * rg + (p[i] - mp) * rp; s += g[i]; }
+  const float m = warp_sum(s) / C;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) v += (g[i] - m) * (g[i] - m);
+  const float rs = rsqrtf(warp_sum(v) / C + 1e-6f);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) out[(size_t)qi * C + i * 32 + lane] = __float2half_rn((g[i] - m) * rs);
+}
+
+// GEGLU (reference model/autoencoder.py:90-93): h [M, 2F] fp16 -> out [M, F] = a * gelu_erf(gate)
+__global__ void __launch_bounds__(256) geglu_kernel(const __half* __restrict__ h, long long M, int F,
+                                                    __half* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n8 = M * (F / 8);
+  if (gid >= n8) return;
+  const long long row = gid / (F / 8);
+  const int c = (int)(gid - row * (F / 8)) * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(h + row * 2 * F + c);
+  const uint4 g = *reinterpret_cast<const uint4*>(h + row * 2 * F + F + c);
+  const __half* ah = reinterpret_cast<const __half*>(&a);
+  const __half* gh = reinterpret_cast<const __half*>(&g);
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x = __half2float(gh[j]);
+    const float ge = r16f(0.5f * x * (1.0f + erff(x * 0.7071067811865476f)));
+    o[j] = __float2half_rn(__half2float(ah[j]) * ge);
+  }
+  *reinterpret_cast<uint4*>(out + row * F + c) = *reinterpret_cast<uint4*>(o);
+}
+
+__global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__ x, long long n,
+                                                       __half* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i), b = *reinterpret_cast<const float4*>(x + i + 4);
+    __align__(16) __half h[8] = {__float2half_rn(a.x), __float2half_rn(a.y), __float2half_rn(a.z),
+                                 __float2half_rn(a.w), __float2half_rn(b.x), __float2half_rn(b.y),
+                                 __float2half_rn(b.z), __float2half_rn(b.w)};
+    *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<uint4*>(h);
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2half_rn(x[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// FinalLayer (reference model/dit.py:287-303): LN -> modulate(shift, scale) -> Linear(C -> O<=16)
+// X fp32 [M,C] -> out fp32 [M,O] (fp16-valued, as the autocast module returns).  Warp per row.
+template <int C, int O>
+__global__ void __launch_bounds__(256) final_layer_kernel(const float* __restrict__ x, int M,
+                                                          const __half* __restrict__ shift,
+                                                          const __half* __restrict__ scale, int mod_stride,
+                                                          int rows_per_batch, const __half* __restrict__ W,
+                                                          const float* __restrict__ bias,
+                                                          float* __restrict__ out) {
+  constexpr int PER = C / 32;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { v[i] = x[(size_t)row * C + i * 32 + lane]; s += v[i]; }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) q += (v[i] - mean) * (v[i] - mean);
+  const float rstd = rsqrtf(warp_sum(q) / C + 1e-6f);
+  const int b = row / rows_per_batch;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = i * 32 + lane;
+    const float y = (v[i] - mean) * rstd * (1.0f + __half2float(scale[(size_t)b * mod_stride + c])) +
+                    __half2float(shift[(size_t)b * mod_stride + c]);
+    v[i] = r16f(y);
+  }
+  for (int o = 0; o < O; ++o) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) acc += v[i] * __half2float(W[(size_t)o * C + i * 32 + lane]);
+    acc = warp_sum(acc);
+    if (lane == 0) out[(size_t)row * O + o] = r16f(acc + bias[o]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// DPM-Solver++ data prediction with the reference's model wrapper folded in
+// (reference model/dpmsolver.py:284-300 v -> eps, :328-347 3-way CFG, :450-459 x0):
+//   eps_k = alpha * v_k + sigma * x ;  eps = eps_fu + s1 (eps_u - eps_fu) + s2 (eps_c - eps_u)
+//   x0 = (x - sigma * eps) / alpha
+// v: [branches, n] (branch order full-uncond, image-uncond, cond; 1 branch = cond only).
+__global__ void __launch_bounds__(256) dpm_x0_kernel(const float* __restrict__ x, const float* __restrict__ v,
+                                                     long long n, int branches, float alpha, float sigma,
+                                                     float s1, float s2, float* __restrict__ x0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float xv = x[i];
+  float eps;
+  if (branches == 1) {
+    eps = alpha * v[i] + sigma * xv;
+  } else {
+    const float efu = alpha * v[i] + sigma * xv;
+    const float eu = alpha * v[n + i] + sigma * xv;
+    const float ec = alpha * v[2 * n + i] + sigma * xv;
+    eps = efu + s1 * (eu - efu) + s2 * (ec - eu);
+  }
+  x0[i] = (xv - sigma * eps) / alpha;
+}
+
+// out = a*x + b*y + c*z  (y, z optional) -- first / second order updates written exactly in the
+// reference's evaluation order by the host (model/dpmsolver.py:589-597, 843-848).
+//   first order : x_t = (sig_t/sig_s) x - (alpha_t phi1) m0
+//   second order: x_t = (sig_t/sig_0) x - (alpha_t phi1) m0 - 0.5 (alpha_t phi1) * ((1/r0) (m0 - m1))
+__global__ void __launch_bounds__(256) dpm_update_kernel(const float* __restrict__ x,
+                                                         const float* __restrict__ m0,
+                                                         const float* __restrict__ m1, long long n,
+                                                         float cx, float cm, float inv_r0, int order,
+                                                         float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float r = cx * x[i] - cm * m0[i];
+  if (order == 2) {
+    const float d1 = inv_r0 * (m0[i] - m1[i]);
+    r = r - 0.5f * cm * d1;
+  }
+  out[i] = r;
+}
+
+// out = x * a[c] + b[c]  over the last dim (latent de-normalisation, inference_dpm_latent.py:250)
+__global__ void __launch_bounds__(256) affine_lastdim_kernel(const float* __restrict__ x, long long n, int C,
+                                                             const float* __restrict__ a,
+                                                             const float* __restrict__ b, float as, float bs,
+                                                             float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  out[i] = x[i] * (a ? a[c] : as) + (b ? b[c] : bs);
+}
+
+}  // namespace gvf
+
+using namespace gvf;
+#define ST(s) ((cudaStream_t)(s))
+#define RET() return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA
+
+extern "C" {
+
+GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
+                           const float* w, const float* b, const void* shift, const void* scale,
+                           int mod_stride, int rows_per_batch, void* stream) {
+  if (!x || !out || M <= 0) return GVF_ERR_INVALID;
+  if ((w == nullptr) != (b == nullptr) || (shift == nullptr) != (scale == nullptr)) return GVF_ERR_INVALID;
+  const int rpb = rows_per_batch > 0 ? rows_per_batch : M;
+  const dim3 grid((M + 7) / 8);
+#define LN_CASE(T, CC, V)                                                                          \
+  ln_mod_kernel<T, CC, V><<<grid, 256, 0, ST(stream)>>>((const T*)x, (__half*)out, M, eps, w, b,    \
+                                                        (const __half*)shift, (const __half*)scale, \
+                                                        mod_stride, rpb)
+#define LN_BOTH(CC, V)                       \
+  if (C == CC) {                             \
+    if (x_is_f16) LN_CASE(__half, CC, V);    \
+    else LN_CASE(float, CC, V);              \
+    RET();                                   \
+  }
+  LN_BOTH(512, true)
+  LN_BOTH(768, true)
+  LN_BOTH(64, false)
+  LN_BOTH(96, false)
+  LN_BOTH(128, true)
+  LN_BOTH(384, true)
+#undef LN_BOTH
+#undef LN_CASE
+  return GVF_ERR_UNSUPPORTED;
+  RET();
+}
+
+GVF_API int gvf_rmsnorm_heads_f16(void* buf, long long rows, int ld, int H, int D, int k_off,
+                                  const float* gamma_q, const float* gamma_k, void* stream) {
+  if (!buf || !gamma_q || !gamma_k || rows <= 0 || (ld % 8) || (k_off % 8)) return GVF_ERR_INVALID;
+  const long long n = rows * H * 2;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (D == 32) rmsnorm_heads_kernel<32><<<blocks, 256, 0, ST(stream)>>>((__half*)buf, rows, ld, H, k_off, gamma_q, gamma_k);
+  else if (D == 64) rmsnorm_heads_kernel<64><<<blocks, 256, 0, ST(stream)>>>((__half*)buf, rows, ld, H, k_off, gamma_q, gamma_k);
+  else return GVF_ERR_UNSUPPORTED;
+  RET();
+}
+
+GVF_API int gvf_dit_modulation(const float* t, int B, int C, int F, const void* W0, const float* b0,
+                               const void* W2, const float* b2, const void* Wmod, const float* bmod,
+                               int R, void* temb, void* silu_temb, void* mod_out, void* stream) {
+  if (!t || !W0 || !W2 || !Wmod || !mod_out || B <= 0 || B > 8 || C > 1024 || (C % 32)) return GVF_ERR_INVALID;
+  temb_kernel<<<B, C, (F + C) * sizeof(float), ST(stream)>>>(t, (const __half*)W0, b0, (const __half*)W2, b2, C,
+                                                             F, (__half*)temb, (__half*)silu_temb);
+  if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
+  mod_gemv_kernel<8><<<(R + 7) / 8, 256, 0, ST(stream)>>>((const __half*)Wmod, bmod, (const __half*)silu_temb, B,
+                                                          R, C, (__half*)mod_out);
+  RET();
+}
+
+GVF_API int gvf_small_linear(const float* x, int ldx, const void* W, const float* bias, int M, int N,
+                             int K, const float* add, int add_rows, void* out, int out_is_f16,
+                             void* stream) {
+  if (!x || !W || !out || K > 32 || K <= 0 || M <= 0 || N <= 0) return GVF_ERR_INVALID;
+  const dim3 grid((N + 255) / 256, (M + 7) / 8);
+  const int ar = add_rows > 0 ? add_rows : 1;
+  if (out_is_f16)
+    small_linear_kernel<__half><<<grid, 256, 0, ST(stream)>>>(x, ldx, (const __half*)W, bias, M, N, K, add, ar, (__half*)out);
+  else
+    small_linear_kernel<float><<<grid, 256, 0, ST(stream)>>>(x, ldx, (const __half*)W, bias, M, N, K, add, ar, (float*)out);
+  RET();
+}
+
+GVF_API int gvf_ape(const float* xyz, int R, int C, float* out, void* stream) {
+  if (!xyz || !out || R <= 0 || C < 6) return GVF_ERR_INVALID;
+  const long long n = (long long)R * C;
+  ape_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(xyz, R, C, out);
+  RET();
+}
+
+GVF_API int gvf_vae_query_embed(const float* queries, int ldq, const void* gs, int Q, int C, void* out,
+                                void* stream) {
+  if (!queries || !gs || !out || Q <= 0) return GVF_ERR_INVALID;
+  const dim3 grid((Q + 7) / 8);
+  if (C == 768) query_embed_kernel<768><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
+  else if (C == 96) query_embed_kernel<96><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
+  else if (C == 384) query_embed_kernel<384><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
+  else return GVF_ERR_UNSUPPORTED;
+  RET();
+}
+
+GVF_API int gvf_geglu_f16(const void* h, long long M, int F, void* out, void* stream) {
+  if (!h || !out || M <= 0 || (F % 8)) return GVF_ERR_INVALID;
+  const long long n8 = M * (F / 8);
+  geglu_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)h, M, F, (__half*)out);
+  RET();
+}
+
+GVF_API int gvf_cast_f32_f16(const float* x, long long n, void* out, void* stream) {
+  if (!x || !out || n <= 0) return GVF_ERR_INVALID;
+  const long long th = (n + 7) / 8;
+  cast_f16_kernel<<<(unsigned)((th + 255) / 256), 256, 0, ST(stream)>>>(x, n, (__half*)out);
+  RET();
+}
+
+GVF_API int gvf_dit_final_layer(const float* x, int M, int C, int O, const void* shift, const void* scale,
+                                int mod_stride, int rows_per_batch, const void* W, const float* bias,
+                                float* out, void* stream) {
+  if (!x || !shift || !scale || !W || !bias || !out || M <= 0 || rows_per_batch <= 0) return GVF_ERR_INVALID;
+  const dim3 grid((M + 7) / 8);
+  if (C == 512 && O == 16)
+    final_layer_kernel<512, 16><<<grid, 256, 0, ST(stream)>>>(x, M, (const __half*)shift, (const __half*)scale,
+                                                              mod_stride, rows_per_batch, (const __half*)W, bias, out);
+  else if (C == 128 && O == 16)
+    final_layer_kernel<128, 16><<<grid, 256, 0, ST(stream)>>>(x, M, (const __half*)shift, (const __half*)scale,
+                                                              mod_stride, rows_per_batch, (const __half*)W, bias, out);
+  else if (C == 64 && O == 16)
+    final_layer_kernel<64, 16><<<grid, 256, 0, ST(stream)>>>(x, M, (const __half*)shift, (const __half*)scale,
+                                                             mod_stride, rows_per_batch, (const __half*)W, bias, out);
+  else return GVF_ERR_UNSUPPORTED;
+  RET();
+}
+
+GVF_API int gvf_dpm_x0(const float* x, const float* v, long long n, int branches, float alpha, float sigma,
+                       float s1, float s2, float* x0, void* stream) {
+  if (!x || !v || !x0 || n <= 0 || (branches != 1 && branches != 3)) return GVF_ERR_INVALID;
+  dpm_x0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, v, n, branches, alpha, sigma, s1, s2, x0);
+  RET();
+}
+
+GVF_API int gvf_dpm_update(const float* x, const float* m0, const float* m1, long long n, float cx, float cm,
+                           float inv_r0, int order, float* out, void* stream) {
+  if (!x || !m0 || !out || n <= 0 || (order == 2 && !m1) || order < 1 || order > 2) return GVF_ERR_INVALID;
+  dpm_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, m0, m1, n, cx, cm, inv_r0, order, out);
+  RET();
+}
+
+GVF_API int gvf_affine_lastdim(const float* x, long long n, int C, const float* a, const float* b, float as,
+                               float bs, float* out, void* stream) {
+  if (!x || !out || n <= 0 || C <= 0) return GVF_ERR_INVALID;
+  affine_lastdim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, n, C, a, b, as, bs, out);
+  RET();
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+"""Thin torch-tensor front-ends of the C ABI (include/gvf_b200.h sections 2-5).
+
+torch is used for device memory and the current stream; every computation happens in
+libgvf_b200.so.  All functions enqueue on the current CUDA stream and never synchronise.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, ptr
+
+F16, F32 = torch.float16, torch.float32
+EPI_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_RESID_F16, EPI_F32 = 0, 1, 2, 3, 4
+
+
+def _ll(vals):
+    return (C.c_longlong * len(vals))(*[int(v) for v in vals])
+
+
+def _req(t, dtype, name):
+    if not (t.is_cuda and t.dtype == dtype):
+        raise ValueError(f"{name}: expected a CUDA {dtype} tensor, got {t.dtype} on {t.device}")
+
+
+def gemm(a, w, bias=None, epilogue=EPI_F16, out=None, gate=None, gate_stride=0, rows_per_batch=0):
+    """out = epilogue(a[M,K] @ w[N,K]^T + bias).  a, w fp16 with contiguous rows."""
+    _req(a, F16, "a")
+    _req(w, F16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        assert epilogue in (EPI_F16, EPI_GELU_F16, EPI_F32)
+        out = torch.empty((M, N), dtype=F32 if epilogue == EPI_F32 else F16, device=a.device)
+    assert out.stride(1) == 1 and out.dtype == (F32 if epilogue in (EPI_RESID_F32, EPI_F32) else F16)
+    st = _lib.lib().gvf_gemm_f16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
+                                 ptr(out), out.stride(0), ptr(gate), gate_stride, rows_per_batch,
+                                 current_stream())
+    check(st, "gvf_gemm_f16")
+    return out
+
+
+def attention(q, k, v, scale, out=None, q_shared=False, kv_shared=False):
+    """q [Nb,Lq,H,D] (or [Lq,H,D] if q_shared), k/v [Nb,Lk,H,D] (or [Lk,H,D] if kv_shared): fp16
+    views with contiguous last dim (any strides that are multiples of 8).  -> [Nb,Lq,H,D] fp16."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, F16, n)
+        assert t.stride(-1) == 1
+    if q_shared:
+        Lq, H, D = q.shape
+        qs = (0, q.stride(0), q.stride(1))
+    else:
+        _, Lq, H, D = q.shape
+        qs = (q.stride(0), q.stride(1), q.stride(2))
+    if kv_shared:
+        Lk = k.shape[0]
+        ks, vs = (0, k.stride(0), k.stride(1)), (0, v.stride(0), v.stride(1))
+        Nb = q.shape[0]
+    else:
+        Nb, Lk = k.shape[0], k.shape[1]
+        ks, vs = (k.stride(0), k.stride(1), k.stride(2)), (v.stride(0), v.stride(1), v.stride(2))
+    if out is None:
+        out = torch.empty((Nb, Lq, H, D), dtype=F16, device=q.device)
+    os_ = (out.stride(0), out.stride(1), out.stride(2))
+    st = _lib.lib().gvf_attn_fwd_f16(ptr(q), ptr(k), ptr(v), ptr(out), Nb, Lq, Lk, H, D, _ll(qs), _ll(ks),
+                                     _ll(vs), _ll(os_), int(q_shared), int(kv_shared), float(scale),
+                                     current_stream())
+    check(st, "gvf_attn_fwd_f16")
+    return out
+
+
+def small_linear(x, w, bias, out_f16, add=None, add_rows=0, out=None):
+    _req(x, F32, "x")
+    _req(w, F16, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.stride(1) == 1 and w.is_contiguous()
+    if out is None:
+        out = torch.empty((M, N), dtype=F16 if out_f16 else F32, device=x.device)
+    st = _lib.lib().gvf_small_linear(ptr(x), x.stride(0), ptr(w), ptr(bias), M, N, K, ptr(add), add_rows,
+                                     ptr(out), int(out_f16), current_stream())
+    check(st, "gvf_small_linear")
+    return out
+
+
+def ln_mod(x, out=None, eps=1e-6, w=None, b=None, shift=None, scale=None, mod_stride=0, rows_per_batch=0):
+    M, Cc = x.shape
+    assert x.is_contiguous() and x.dtype in (F16, F32)
+    if out is None:
+        out = torch.empty((M, Cc), dtype=F16, device=x.device)
+    st = _lib.lib().gvf_ln_mod_f16(ptr(x), int(x.dtype == F16), ptr(out), M, Cc, eps, ptr(w), ptr(b),
+                                   ptr(shift), ptr(scale), mod_stride, rows_per_batch, current_stream())
+    check(st, "gvf_ln_mod_f16")
+    return out
+
+
+def rmsnorm_heads_(buf, H, D, k_off, gamma_q, gamma_k):
+    rows, ld = buf.shape[0], buf.stride(0)
+    st = _lib.lib().gvf_rmsnorm_heads_f16(ptr(buf), rows, ld, H, D, k_off, ptr(gamma_q), ptr(gamma_k),
+                                          current_stream())
+    check(st, "gvf_rmsnorm_heads_f16")
+    return buf
+
+
+def dit_modulation(t, W0, b0, W2, b2, Wmod, bmod, temb, silu_temb, mod_out):
+    B = t.shape[0]
+    Cc, Fq = W0.shape
+    R = Wmod.shape[0]
+    st = _lib.lib().gvf_dit_modulation(ptr(t), B, Cc, Fq, ptr(W0), ptr(b0), ptr(W2), ptr(b2), ptr(Wmod),
+                                       ptr(bmod), R, ptr(temb), ptr(silu_temb), ptr(mod_out), current_stream())
+    check(st, "gvf_dit_modulation")
+    return mod_out
+
+
+def ape(xyz, Cc):
+    R = xyz.shape[0]
+    out = torch.empty((R, Cc), dtype=F32, device=xyz.device)
+    check(_lib.lib().gvf_ape(ptr(xyz), R, Cc, ptr(out), current_stream()), "gvf_ape")
+    return out
+
+
+def vae_query_embed(queries, gs):
+    Q, Cc = gs.shape
+    out = torch.empty((Q, Cc), dtype=F16, device=gs.device)
+    check(_lib.lib().gvf_vae_query_embed(ptr(queries), queries.stride(0), ptr(gs), Q, Cc, ptr(out),
+                                         current_stream()), "gvf_vae_query_embed")
+    return out
+
+
+def geglu(h, out=None):
+    M, F2 = h.shape
+    if out is None:
+        out = torch.empty((M, F2 // 2), dtype=F16, device=h.device)
+    check(_lib.lib().gvf_geglu_f16(ptr(h), M, F2 // 2, ptr(out), current_stream()), "gvf_geglu_f16")
+    return out
+
+
+def cast_f16(x, out=None):
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=F16, device=x.device)
+    check(_lib.lib().gvf_cast_f32_f16(ptr(x), x.numel(), ptr(out), current_stream()), "gvf_cast_f32_f16")
+    return out
+
+
+def dit_final_layer(x, shift, scale, mod_stride, rows_per_batch, W, bias, out=None):
+    M, Cc = x.shape
+    O = W.shape[0]
+    if out is None:
+        out = torch.empty((M, O), dtype=F32, device=x.device)
+    check(_lib.lib().gvf_dit_final_layer(ptr(x), M, Cc, O, ptr(shift), ptr(scale), mod_stride, rows_per_batch,
+                                         ptr(W), ptr(bias), ptr(out), current_stream()), "gvf_dit_final_layer")
+    return out
+
+
+def dpm_x0(x, v, branches, alpha, sigma, s1, s2, out):
+    check(_lib.lib().gvf_dpm_x0(ptr(x), ptr(v), x.numel(), branches, alpha, sigma, s1, s2, ptr(out),
+                                current_stream()), "gvf_dpm_x0")
+    return out
+
+
+def dpm_update(x, m0, m1, cx, cm, inv_r0, order, out):
+    check(_lib.lib().gvf_dpm_update(ptr(x), ptr(m0), ptr(m1), x.numel(), cx, cm, inv_r0, order, ptr(out),
+                                    current_stream()), "gvf_dpm_update")
+    return out
+
+
+def affine_lastdim(x, a=None, b=None, a_scalar=1.0, b_scalar=0.0, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().gvf_affine_lastdim(ptr(x), x.numel(), x.shape[-1], ptr(a), ptr(b), a_scalar, b_scalar,
+                                        ptr(out), current_stream()), "gvf_affine_lastdim")
+    return out

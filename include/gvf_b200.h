@@ -101,6 +101,92 @@ GVF_API int gvf_raster_forward(const gvf_raster_params* prm, int F, int P, int a
                        int32_t* radii, void* workspace, size_t workspace_bytes, int64_t cap,
                        void* stream);
 
+
+/* ------------------------------------------------------------------------------------
+ * 2. Dense attention -- replaces flash_attn.flash_attn_{func,kvpacked_func,qkvpacked_func}
+ *    as dispatched by reference model/attention/full_attn.py:74-140
+ *    (scaled_dot_product_attention, layout [N, L, H, d]) and called directly at
+ *    model/autoencoder.py:132-144.  fp16 in/out, fp32 statistics, no mask, no dropout.
+ *    q [Nb, Lq, H, D], k / v [Nb, Lk, H, D], o [Nb, Lq, H, D]; *_strides = element strides
+ *    {batch, sequence, head} (innermost contiguous, all multiples of 8), so packed qkv / kv
+ *    tensors and transposed (temporal) views are consumed in place.  q_shared / kv_shared:
+ *    the tensor has no batch dimension and is reused by every batch entry.
+ *    D in {32, 64}.  Lq <= 32 self-attention (the temporal attention of model/dit.py:254-260)
+ *    runs on CUDA cores; everything else on tcgen05 tensor cores fed by TMA.
+ * ---------------------------------------------------------------------------------- */
+GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void* v, void* o, int Nb, int Lq,
+                             int Lk, int H, int D, const long long* q_strides,
+                             const long long* k_strides, const long long* v_strides,
+                             const long long* o_strides, int q_shared, int kv_shared, float scale,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 3. Linear layers -- replace nn.Linear (cuBLAS under fp16 autocast) plus the elementwise
+ *    kernels around it (reference model/dit.py:128-138,240-277, model/attention/modules.py:
+ *    98-146, model/autoencoder.py:90-163).  out = epilogue(A[M,K] * W[N,K]^T + bias).
+ *    A, W fp16 row-major (lda/ldw in elements, multiples of 8); tcgen05 + TMA, fp32 accumulate.
+ *    epilogue: 0 fp16 store | 1 GELU(tanh) then fp16 store | 2 fp32 residual:
+ *    out[m,n] += fp16(gate[m / rows_per_batch, n] * fp16(acc + bias)) (gate optional, fp16)
+ *    | 3 fp16 residual: out = fp16(fp16(acc + bias) + out) | 4 fp32 store.
+ * ---------------------------------------------------------------------------------- */
+GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                         int epilogue, const float* bias, void* out, int ldo, const void* gate,
+                         int gate_stride, int rows_per_batch, void* stream);
+
+/* y = fp16(x[M,K] W[N,K]^T + b) (+ add[m % add_rows, n], fp32) for K <= 32 on CUDA cores:
+ * input_layer + APE (model/dit.py:457,470-472), static_cond_proj (:465), VAE proj
+ * (model/autoencoder.py:585), gs_embedding (:389).  x fp32, W fp16, out fp32 or fp16. */
+GVF_API int gvf_small_linear(const float* x, int ldx, const void* W, const float* bias, int M, int N,
+                             int K, const float* add, int add_rows, void* out, int out_is_f16,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 4. Fused elementwise kernels of the DiT / VAE blocks.
+ * ---------------------------------------------------------------------------------- */
+/* LayerNorm(eps; optional affine w,b) then optional adaLN modulate y*(1+scale[b])+shift[b]
+ * (shift/scale fp16 [batches, mod_stride]) -> fp16.  x fp32 or fp16 [M,C].
+ * reference model/dit.py:246-247,254-255,263,268,273-274; model/autoencoder.py:73-88. */
+GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
+                           const float* w, const float* b, const void* shift, const void* scale,
+                           int mod_stride, int rows_per_batch, void* stream);
+/* MultiHeadRMSNorm on q and k, in place (model/attention/modules.py:8-15,122-125). */
+GVF_API int gvf_rmsnorm_heads_f16(void* buf, long long rows, int ld, int H, int D, int k_off,
+                                  const float* gamma_q, const float* gamma_k, void* stream);
+/* TimestepEmbedder + every adaLN modulation vector of one forward (model/dit.py:59-100,
+ * 240-242,299): t[B] -> temb, silu(temb) [B,C] fp16 and mod_out [B,R] fp16 where the R rows of
+ * Wmod are the blocks' adaLN_modulation.1 / adaLN_modulation_temporal.1 and the final
+ * layer's adaLN_modulation.1 concatenated. */
+GVF_API int gvf_dit_modulation(const float* t, int B, int C, int F, const void* W0, const float* b0,
+                               const void* W2, const float* b2, const void* Wmod, const float* bmod,
+                               int R, void* temb, void* silu_temb, void* mod_out, void* stream);
+/* AbsolutePositionEmbedder (model/dit.py:16-56): xyz [R,3] -> [R,C] fp32 */
+GVF_API int gvf_ape(const float* xyz, int R, int C, float* out, void* stream);
+/* VAE query embedding LN(LN(gs_embedding(q)) + LN(PointEmbed(q.xyz))) -> fp16
+ * (model/autoencoder.py:250-301,389-391,560; PreNorm of :562). */
+GVF_API int gvf_vae_query_embed(const float* queries, int ldq, const void* gs, int Q, int C, void* out,
+                                void* stream);
+/* GEGLU (model/autoencoder.py:90-93): h [M,2F] fp16 -> [M,F] */
+GVF_API int gvf_geglu_f16(const void* h, long long M, int F, void* out, void* stream);
+GVF_API int gvf_cast_f32_f16(const float* x, long long n, void* out, void* stream);
+/* FinalLayer (model/dit.py:287-303): LN -> modulate -> Linear(C -> O) ; out fp32 [M,O] */
+GVF_API int gvf_dit_final_layer(const float* x, int M, int C, int O, const void* shift, const void* scale,
+                                int mod_stride, int rows_per_batch, const void* W, const float* bias,
+                                float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 5. DPM-Solver++ state kernels -- replace the ~15 elementwise torch launches per step of
+ *    reference model/dpmsolver.py:284-300 (v -> eps), :328-347 (3-way CFG), :450-459 (x0),
+ *    :589-597 / :843-848 (first / second order multistep update).
+ * ---------------------------------------------------------------------------------- */
+GVF_API int gvf_dpm_x0(const float* x, const float* v, long long n, int branches, float alpha, float sigma,
+                       float s1, float s2, float* x0, void* stream);
+GVF_API int gvf_dpm_update(const float* x, const float* m0, const float* m1, long long n, float cx, float cm,
+                           float inv_r0, int order, float* out, void* stream);
+/* out = x * a[c] + b[c] over the last dim (or scalars as/bs when a/b are NULL):
+ * latent de-normalisation, inference_dpm_latent.py:250 */
+GVF_API int gvf_affine_lastdim(const float* x, long long n, int C, const float* a, const float* b, float as,
+                               float bs, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

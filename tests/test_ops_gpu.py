@@ -1,0 +1,209 @@
+"""GPU numerics of each sm_100a kernel (through the C ABI) against a plain PyTorch fp32
+reference of the same op.  Tolerances: fp16 outputs -> 2e-3 relative to the tensor's max
+(one fp16 ulp at the top of the range is 1e-3), stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _g(seed=0):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def _rand(shape, g, scale=1.0):
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+def _close(a, b, tol, what=""):
+    err = (a.float() - b.float()).abs().max().item()
+    ref = b.float().abs().max().item()
+    assert err <= tol * max(ref, 1e-6), f"{what}: max err {err:.3e} vs max |ref| {ref:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (1000, 512, 512), (12288, 1536, 512), (384, 2048, 512),
+                                   (130, 72, 200), (12288, 512, 2048)])
+def test_gemm_bias_f16(M, N, K):
+    from gvfdiffusion_b200 import ops
+    g = _g(M + N + K)
+    a = _rand((M, K), g).half()
+    w = _rand((N, K), g, 0.05).half()
+    b = _rand((N,), g, 0.1)
+    ref = a.float() @ w.float().T + b
+    _close(ops.gemm(a, w, b, ops.EPI_F16), ref, 2e-3, "bias f16")
+    _close(ops.gemm(a, w, None, ops.EPI_F32), a.float() @ w.float().T, 2e-4, "f32")
+    _close(ops.gemm(a, w, b, ops.EPI_GELU_F16), F.gelu(ref.half().float(), approximate="tanh"), 2e-3, "gelu")
+
+
+def test_gemm_residual_epilogues():
+    from gvfdiffusion_b200 import ops
+    g = _g(5)
+    M, N, K, rpb = 768, 256, 128, 256
+    a = _rand((M, K), g).half()
+    w = _rand((N, K), g, 0.05).half()
+    b = _rand((N,), g, 0.1)
+    gate = _rand((3, 2 * N), g).half()
+    x = _rand((M, N), g)
+    lin = (a.float() @ w.float().T + b).half().float()
+    ref = x + (lin * gate[:, N:].float().repeat_interleave(rpb, 0)).half().float()
+    out = x.clone()
+    ops.gemm(a, w, b, ops.EPI_RESID_F32, out=out, gate=gate[:, N:], gate_stride=2 * N, rows_per_batch=rpb)
+    _close(out, ref, 1e-3, "gate+resid f32")
+    out = x.clone()
+    ops.gemm(a, w, b, ops.EPI_RESID_F32, out=out)
+    _close(out, x + lin, 1e-3, "resid f32")
+    xh = x.half()
+    out = xh.clone()
+    ops.gemm(a, w, b, ops.EPI_RESID_F16, out=out)
+    _close(out, (lin + xh.float()).half(), 2e-3, "resid f16")
+
+
+def _ref_attn(q, k, v, scale):
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    return (torch.softmax(s, dim=-1) @ vf).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("Nb,Lq,Lk,H,D", [(2, 512, 512, 4, 32), (3, 512, 1370, 2, 32), (2, 256, 4096, 3, 32),
+                                          (2, 100, 70, 2, 32), (5, 24, 24, 4, 32), (2, 512, 512, 3, 64),
+                                          (2, 700, 512, 2, 64), (1, 128, 128, 1, 32), (1, 129, 257, 1, 64)])
+def test_attention_matches_fp32(Nb, Lq, Lk, H, D):
+    from gvfdiffusion_b200 import ops
+    g = _g(Nb * Lq + Lk + D)
+    q = _rand((Nb, Lq, H, D), g).half()
+    k = _rand((Nb, Lk, H, D), g).half()
+    v = _rand((Nb, Lk, H, D), g).half()
+    scale = 1.0 / math.sqrt(D)
+    o = ops.attention(q, k, v, scale)
+    torch.cuda.synchronize()
+    _close(o, _ref_attn(q, k, v, scale), 2e-3, "attention")
+
+
+def test_attention_packed_and_shared_views():
+    from gvfdiffusion_b200 import ops
+    g = _g(77)
+    Nb, L, H, D = 3, 384, 4, 32
+    qkv = _rand((Nb, L, 3, H, D), g).half()          # packed qkv, the DiT self-attention layout
+    q, k, v = qkv.unbind(2)
+    scale = 1.0 / math.sqrt(D)
+    _close(ops.attention(q, k, v, scale), _ref_attn(q, k, v, scale), 2e-3, "packed qkv")
+    # kv shared by all batch entries (static cross-attention), kv packed [L, 2, H, D]
+    kv = _rand((640, 2, H, D), g).half()
+    ks, vs = kv[:, 0], kv[:, 1]
+    ref = _ref_attn(q, ks[None].expand(Nb, -1, -1, -1), vs[None].expand(Nb, -1, -1, -1), scale)
+    _close(ops.attention(q, ks, vs, scale, kv_shared=True), ref, 2e-3, "kv shared")
+    # q shared (VAE decoder queries), d = 64, kv chunked along the last dim like autoencoder.py:130
+    Hh, Dd = 2, 64
+    qs = _rand((300, Hh, Dd), g).half()
+    kvc = _rand((Nb, 512, 2 * Hh * Dd), g).half()
+    kk, vv = kvc[..., :Hh * Dd].unflatten(-1, (Hh, Dd)), kvc[..., Hh * Dd:].unflatten(-1, (Hh, Dd))
+    ref = _ref_attn(qs[None].expand(Nb, -1, -1, -1), kk, vv, 0.125)
+    _close(ops.attention(qs, kk, vv, 0.125, q_shared=True), ref, 2e-3, "q shared")
+    # temporal view: sequences strided by N tokens (DiT temporal attention, T = 24)
+    T, Nt = 24, 40
+    x = _rand((T, Nt, 3, H, D), g).half()
+    xt = x.permute(1, 0, 2, 3, 4)                    # [Nt, T, 3, H, D] strided view
+    qt, kt, vt = xt.unbind(2)
+    out = torch.empty((T, Nt, H, D), dtype=torch.float16, device=DEV)
+    ops.attention(qt, kt, vt, scale, out=out.permute(1, 0, 2, 3))
+    _close(out.permute(1, 0, 2, 3), _ref_attn(qt, kt, vt, scale), 2e-3, "temporal view")
+
+
+@pytest.mark.parametrize("C,dt", [(512, torch.float32), (768, torch.float16), (64, torch.float32), (384, torch.float16)])
+def test_ln_mod(C, dt):
+    from gvfdiffusion_b200 import ops
+    g = _g(C)
+    M, rpb = 96, 32
+    x = _rand((M, C), g).to(dt)
+    mod = _rand((3, 2 * C), g, 0.3).half()
+    w, b = _rand((C,), g), _rand((C,), g)
+    ln = F.layer_norm(x.float(), (C,), None, None, 1e-6)
+    ref = ln * (1 + mod[:, C:].float().repeat_interleave(rpb, 0)) + mod[:, :C].float().repeat_interleave(rpb, 0)
+    _close(ops.ln_mod(x, shift=mod[:, :C], scale=mod[:, C:], mod_stride=2 * C, rows_per_batch=rpb), ref, 1e-3)
+    _close(ops.ln_mod(x, w=w, b=b), ln * w + b, 1e-3)
+    _close(ops.ln_mod(x, eps=1e-5), F.layer_norm(x.float(), (C,), None, None, 1e-5), 1e-3)
+
+
+def test_rmsnorm_heads():
+    from gvfdiffusion_b200 import ops
+    g = _g(9)
+    rows, H, D = 200, 4, 32
+    qkv = _rand((rows, 3 * H * D), g).half()
+    gq, gk = _rand((H, D), g) + 1, _rand((H, D), g) + 1
+    q, k, v = qkv.float().reshape(rows, 3, H, D).unbind(1)
+    rq = F.normalize(q, dim=-1) * gq * D ** 0.5
+    rk = F.normalize(k, dim=-1) * gk * D ** 0.5
+    buf = qkv.clone()
+    ops.rmsnorm_heads_(buf, H, D, H * D, gq, gk)
+    o = buf.float().reshape(rows, 3, H, D)
+    _close(o[:, 0], rq, 1e-3)
+    _close(o[:, 1], rk, 1e-3)
+    assert torch.equal(o[:, 2], v)
+
+
+def test_modulation_small_linear_ape_final():
+    from gvfdiffusion_b200 import ops
+    g = _g(21)
+    B, C, Fq, R = 3, 512, 256, 1000
+    t = torch.tensor([998.996, 500.25, -0.004], device=DEV)
+    W0, W2, Wm = _rand((C, Fq), g, 0.02).half(), _rand((C, C), g, 0.02).half(), _rand((R, C), g, 0.05).half()
+    b0, b2, bm = _rand((C,), g, 0.02), _rand((C,), g, 0.02), _rand((R,), g, 0.02)
+    temb = torch.empty((B, C), dtype=torch.float16, device=DEV)
+    st = torch.empty_like(temb)
+    mod = torch.empty((B, R), dtype=torch.float16, device=DEV)
+    ops.dit_modulation(t, W0, b0, W2, b2, Wm, bm, temb, st, mod)
+    half = Fq // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, device=DEV, dtype=torch.float32) / half)
+    emb = torch.cat([torch.cos(t[:, None] * freqs), torch.sin(t[:, None] * freqs)], -1)
+    te = F.linear(F.silu(F.linear(emb, W0.float(), b0)), W2.float(), b2)
+    _close(temb, te, 3e-3, "t_emb")
+    _close(mod, F.linear(F.silu(te), Wm.float(), bm), 4e-3, "modulation")
+    # small linear + APE
+    x = _rand((70, 16), g)
+    W = _rand((512, 16), g, 0.2).half()
+    bb = _rand((512,), g, 0.1)
+    xyz = torch.rand((35, 3), generator=g).to(DEV) - 0.5
+    pos = ops.ape(xyz, 512)
+    fd = 512 // 3 // 2
+    fr = 1.0 / (10000 ** (torch.arange(fd, device=DEV, dtype=torch.float32) / fd))
+    o = torch.outer(xyz.reshape(-1), fr)
+    pref = torch.cat([torch.sin(o), torch.cos(o)], -1).reshape(35, -1)
+    pref = torch.cat([pref, torch.zeros(35, 512 - pref.shape[1], device=DEV)], -1)
+    _close(pos, pref, 1e-5, "APE")
+    y = ops.small_linear(x, W, bb, out_f16=False, add=pos, add_rows=35)
+    _close(y, F.linear(x.half().float(), W.float(), bb) + pref.repeat(2, 1), 1e-3, "small linear + add")
+    # final layer
+    X = _rand((64, 512), g)
+    modf = _rand((2, 1024), g, 0.3).half()
+    Wf, bf = _rand((16, 512), g, 0.05).half(), _rand((16,), g, 0.1)
+    ln = F.layer_norm(X, (512,), None, None, 1e-6)
+    ref = F.linear(ln * (1 + modf[:, 512:].float().repeat_interleave(32, 0)) + modf[:, :512].float().repeat_interleave(32, 0),
+                   Wf.float(), bf)
+    _close(ops.dit_final_layer(X, modf[:, :512], modf[:, 512:], 1024, 32, Wf, bf), ref, 2e-3, "final layer")
+
+
+def test_geglu_cast_dpm():
+    from gvfdiffusion_b200 import ops
+    g = _g(31)
+    h = _rand((50, 256), g).half()
+    a, gt = h.float().chunk(2, -1)
+    _close(ops.geglu(h), a * F.gelu(gt), 2e-3, "geglu")
+    x = _rand((1000,), g)
+    assert torch.equal(ops.cast_f16(x), x.half())
+    n = 3000
+    xs, v = _rand((n,), g), _rand((3, n), g)
+    al, sg, s1, s2 = 0.8, 0.6, 2.0, 1.5
+    eps = [al * v[i] + sg * xs for i in range(3)]
+    e = eps[0] + s1 * (eps[1] - eps[0]) + s2 * (eps[2] - eps[1])
+    out = torch.empty_like(xs)
+    _close(ops.dpm_x0(xs, v, 3, al, sg, s1, s2, out), (xs - sg * e) / al, 1e-5, "x0 cfg")
+    _close(ops.dpm_x0(xs, v[2], 1, al, sg, 1.0, 1.0, out), (xs - sg * eps[2]) / al, 1e-5, "x0")
+    m0, m1 = _rand((n,), g), _rand((n,), g)
+    _close(ops.dpm_update(xs, m0, m1, 0.9, -0.3, 1.2, 2, torch.empty_like(xs)),
+           0.9 * xs + 0.3 * m0 + 0.5 * 0.3 * (1.2 * (m0 - m1)), 1e-5, "update2")
+    _close(ops.dpm_update(xs, m0, None, 0.9, -0.3, 0.0, 1, torch.empty_like(xs)), 0.9 * xs + 0.3 * m0, 1e-5, "update1")
