@@ -31,6 +31,8 @@ _SIGS = {
     "gvf_raster_workspace_offset": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "gvf_raster_forward": (C.c_int, [C.POINTER(RasterParams), C.c_int, C.c_int, C.c_int,
                                      _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
+    "gvf_gaussian_tensor": (C.c_int, [C.POINTER(RasterParams), C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gvf_fps": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "gvf_attn_fwd_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                    C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_float, _P]),
@@ -45,7 +47,9 @@ _SIGS = {
     "gvf_geglu_f16": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P]),
     "gvf_cast_f32_f16": (C.c_int, [_P, C.c_longlong, _P, _P]),
     "gvf_dit_final_layer": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
-    "gvf_dpm_x0": (C.c_int, [_P, _P, C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
+    "gvf_dpm_x0": (C.c_int, [_P, _P, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                             _P, _P]),
+    "gvf_dpm_error_sq": (C.c_int, [_P, _P, _P, C.c_int, C.c_longlong, C.c_float, C.c_float, _P, _P]),
     "gvf_dpm_update": (C.c_int, [_P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_int, _P, _P]),
     "gvf_affine_lastdim": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, C.c_float, C.c_float, _P, _P]),
 }

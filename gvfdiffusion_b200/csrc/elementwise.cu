@@ -383,21 +383,46 @@ __global__ void __launch_bounds__(256) final_layer_kernel(const float* __restric
 //   x0 = (x - sigma * eps) / alpha
 // v: [branches, n] (branch order full-uncond, image-uncond, cond; 1 branch = cond only).
 __global__ void __launch_bounds__(256) dpm_x0_kernel(const float* __restrict__ x, const float* __restrict__ v,
-                                                     long long n, int branches, float alpha, float sigma,
-                                                     float s1, float s2, float* __restrict__ x0) {
+                                                     long long n, int branches, int vpred, float alpha,
+                                                     float sigma, float s1, float s2, float* __restrict__ x0) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float xv = x[i];
   float eps;
   if (branches == 1) {
-    eps = alpha * v[i] + sigma * xv;
+    eps = vpred ? alpha * v[i] + sigma * xv : v[i];
   } else {
-    const float efu = alpha * v[i] + sigma * xv;
-    const float eu = alpha * v[n + i] + sigma * xv;
-    const float ec = alpha * v[2 * n + i] + sigma * xv;
+    const float efu = vpred ? alpha * v[i] + sigma * xv : v[i];
+    const float eu = vpred ? alpha * v[n + i] + sigma * xv : v[n + i];
+    const float ec = vpred ? alpha * v[2 * n + i] + sigma * xv : v[2 * n + i];
     eps = efu + s1 * (eu - efu) + s2 * (ec - eu);
   }
   x0[i] = (xv - sigma * eps) / alpha;
+}
+
+__global__ void __launch_bounds__(256) dpm_error_sq_kernel(const float* __restrict__ xh, const float* __restrict__ xl,
+                                                           const float* __restrict__ xp, long long n_per_batch,
+                                                           float atol, float rtol, float* __restrict__ E2) {
+  const int b = blockIdx.y;
+  const float* h = xh + (size_t)b * n_per_batch;
+  const float* l = xl + (size_t)b * n_per_batch;
+  const float* p = xp + (size_t)b * n_per_batch;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_batch;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float delta = fmaxf(atol, rtol * fmaxf(fabsf(l[i]), fabsf(p[i])));
+    const float e = (h[i] - l[i]) / delta;
+    acc += e * e;
+  }
+  acc = warp_sum(acc);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    atomicAdd(E2 + b, t);
+  }
 }
 
 // out = a*x + b*y + c*z  (y, z optional) -- first / second order updates written exactly in the
@@ -553,10 +578,21 @@ GVF_API int gvf_dit_final_layer(const float* x, int M, int C, int O, const void*
   RET();
 }
 
-GVF_API int gvf_dpm_x0(const float* x, const float* v, long long n, int branches, float alpha, float sigma,
-                       float s1, float s2, float* x0, void* stream) {
+GVF_API int gvf_dpm_x0(const float* x, const float* v, long long n, int branches, int model_type,
+                       float alpha, float sigma, float s1, float s2, float* x0, void* stream) {
   if (!x || !v || !x0 || n <= 0 || (branches != 1 && branches != 3)) return GVF_ERR_INVALID;
-  dpm_x0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, v, n, branches, alpha, sigma, s1, s2, x0);
+  if (model_type != 0 && model_type != 1) return GVF_ERR_UNSUPPORTED;
+  dpm_x0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, v, n, branches, model_type, alpha, sigma,
+                                                                     s1, s2, x0);
+  RET();
+}
+
+GVF_API int gvf_dpm_error_sq(const float* x_higher, const float* x_lower, const float* x_prev, int B,
+                             long long n_per_batch, float atol, float rtol, float* E2, void* stream) {
+  if (!x_higher || !x_lower || !x_prev || !E2 || B <= 0 || n_per_batch <= 0) return GVF_ERR_INVALID;
+  const unsigned bx = (unsigned)((n_per_batch + 256 * 8 - 1) / (256 * 8));
+  dpm_error_sq_kernel<<<dim3(bx > 1024 ? 1024 : bx, B), 256, 0, ST(stream)>>>(x_higher, x_lower, x_prev, n_per_batch,
+                                                                               atol, rtol, E2);
   RET();
 }
 

@@ -26,7 +26,7 @@ constexpr int kBM = 128, kBK = 64;
 struct GemmEpi {
   int mode;
   const float* bias;        // [N] or null
-  void* out;                // fp16 [M,N] (modes 0,1,3) or fp32 [M,N] (modes 2,4)
+  void* out;                // fp16 [M,N] (modes 0,1,3) or fp32 [M,N] (modes 2,4,5)
   const __half* gate;       // mode 2: [batches, gate_stride] fp16-valued gates or null
   int gate_stride;          // elements between batches in gate
   int rows_per_batch;       // mode 2: row -> batch index
@@ -172,11 +172,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             *reinterpret_cast<uint4*>(o + j) = *reinterpret_cast<uint4*>(h);
           }
         }
-      } else {
+      } else if (ep.mode == 4) {
         float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           if (j < ncol) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        // mode 5: compact fp32 rows of ldo (<= N) fp16-rounded values, e.g. Linear(768 -> 14)
+        float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < ep.ldo) o[col0 + j] = r16(v[j]);
       }
     }
   }
@@ -210,7 +216,7 @@ extern "C" GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int l
                                     const void* gate, int gate_stride, int rows_per_batch,
                                     void* stream) {
   if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return GVF_ERR_INVALID;
-  if ((N % 8) || (K % 8) || (lda % 8) || (ldw % 8) || epilogue < 0 || epilogue > 4) return GVF_ERR_INVALID;
+  if ((N % 8) || (K % 8) || (lda % 8) || (ldw % 8) || epilogue < 0 || epilogue > 5) return GVF_ERR_INVALID;
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
   if (epilogue == 2 && gate && rows_per_batch <= 0) return GVF_ERR_INVALID;
   const bool wide = (N % 128) == 0 && N >= 1024;   // BN = 128 everywhere for now; see DESIGN.md

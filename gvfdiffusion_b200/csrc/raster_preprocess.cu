@@ -223,3 +223,109 @@ cudaError_t launch_preprocess(const gvf_raster_params& prm, int F, int P, int ac
 }
 
 }  // namespace gvf
+
+// =======================================================================================
+// get_gaussian_tensor (reference train_vae.py:466-472): activated canonical Gaussians packed
+// [xyz3 | rgb(features_dc)3 | opacity1 | scale3 | rot4] = the motion-VAE decoder queries and
+// the source of `static_latent` / `deformation_position_xyz` (inference_dpm_latent.py:205-216).
+// Same activation code (and -fmad=false) as the rasteriser preprocess above.
+namespace gvf {
+
+__global__ void __launch_bounds__(256) gaussian_tensor_kernel(const gvf_raster_params prm, int P,
+                                                              const float* __restrict__ xyz,
+                                                              const float* __restrict__ dc,
+                                                              const float* __restrict__ scaling,
+                                                              const float* __restrict__ rotation,
+                                                              const float* __restrict__ opacity,
+                                                              float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float* o = out + (size_t)i * 14;
+  const float k2 = prm.min_kernel * prm.min_kernel;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = xyz[(size_t)i * 3 + c] * prm.aabb[3 + c] + prm.aabb[c];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[3 + c] = dc[(size_t)i * 3 + c];
+  o[6] = gvf_sigmoidf(opacity[i] + prm.opacity_bias);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s = scaling[(size_t)i * 3 + c] + prm.scale_bias;
+    s = prm.softplus ? gvf_softplusf(s) : gvf_expf(s);
+    o[7 + c] = sqrtf(s * s + k2);
+  }
+  float q[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) q[c] = rotation[(size_t)i * 4 + c] + (c == 0 ? 1.0f : 0.0f);
+  float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  n = fmaxf(n, 1e-12f);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) o[10 + c] = q[c] / n;
+}
+
+// Farthest point sampling (replaces torch_cluster.fps as used by sample_gs,
+// reference utils/inference_utils.py:180-198).  One CTA per cloud, 1024 threads; deterministic:
+// starts at point `start` (torch_cluster's default start is random), ties -> lowest index.
+__global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ pts, int ld, int P, int K,
+                                                   int start, float* __restrict__ mind,
+                                                   int* __restrict__ out_idx) {
+  __shared__ float sd[32];
+  __shared__ int si[32];
+  __shared__ int cur_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* p = pts + (size_t)blockIdx.y * 0;   // single cloud per launch (blockIdx unused)
+  for (int i = tid; i < P; i += 1024) mind[i] = 3.0e38f;
+  int cur = start;
+  if (tid == 0) out_idx[0] = cur;
+  __syncthreads();
+  for (int k = 1; k < K; ++k) {
+    const float cx = p[(size_t)cur * ld], cy = p[(size_t)cur * ld + 1], cz = p[(size_t)cur * ld + 2];
+    float best = -1.0f;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < P; i += 1024) {
+      const float dx = p[(size_t)i * ld] - cx, dy = p[(size_t)i * ld + 1] - cy, dz = p[(size_t)i * ld + 2] - cz;
+      const float d = fminf(mind[i], dx * dx + dy * dy + dz * dz);
+      mind[i] = d;
+      if (d > best) { best = d; bi = i; }     // ascending i per thread: first max kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { sd[w] = best; si[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+      best = sd[lane];
+      bi = si[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) { cur_s = bi; out_idx[k] = bi; }
+    }
+    __syncthreads();
+    cur = cur_s;
+  }
+}
+
+}  // namespace gvf
+
+extern "C" GVF_API int gvf_gaussian_tensor(const gvf_raster_params* prm, int P, const float* xyz,
+                                           const float* dc, const float* scaling, const float* rotation,
+                                           const float* opacity, float* out, void* stream) {
+  if (!prm || !xyz || !dc || !scaling || !rotation || !opacity || !out || P <= 0) return GVF_ERR_INVALID;
+  gvf::gaussian_tensor_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, P, xyz, dc, scaling,
+                                                                                rotation, opacity, out);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+extern "C" GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start, float* workspace,
+                               int32_t* out_idx, void* stream) {
+  if (!pts || !workspace || !out_idx || P <= 0 || K <= 0 || K > P || start < 0 || start >= P || ld < 3)
+    return GVF_ERR_INVALID;
+  gvf::fps_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pts, ld, P, K, start, workspace, out_idx);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}

@@ -86,8 +86,8 @@ class DiTEngine:
             self.blocks.append(blk)
         mods_w.append(sd["final_layer.adaLN_modulation.1.weight"])
         mods_b.append(sd["final_layer.adaLN_modulation.1.bias"])
-        self.w_mod = _h(torch.cat([w.detach().float() for w in mods_w], 0), dev)
-        self.b_mod = _b(torch.cat([b.detach().float() for b in mods_b], 0), dev)
+        self.w_mod = _h(torch.cat([w.detach().float().cpu() for w in mods_w], 0), dev)
+        self.b_mod = _b(torch.cat([b.detach().float().cpu() for b in mods_b], 0), dev)
         self.R = self.w_mod.shape[0]          # nblk * 9C + 2C
         assert self.R == self.nblk * 9 * C + 2 * C
         self._ws_key = None

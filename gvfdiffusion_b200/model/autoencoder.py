@@ -1,0 +1,85 @@
+"""`GSKLTemporalVariationalAutoEncoder`: drop-in for the DECODE side of the reference's motion
+VAE (model/autoencoder.py:345-609): same constructor keywords, same state-dict names for the
+decode weights (`proj`, `layers.{i}.{0,1}.fn.*`, `gs_embedding.0`, `decoder_cross_attn.fn.*`,
+`to_outputs`), `decode(x, queries)` on the sm_100a engine.  `encode` (FPS + KNN interpolation +
+cross-attention, training / dataset preparation only) is out of scope.
+"""
+import torch
+import torch.nn as nn
+
+from ..vae_engine import VAEDecodeEngine
+
+
+class _Fn(nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+class _Attn(nn.Module):
+    def __init__(self, qd, cd, inner):
+        super().__init__()
+        self.to_q = nn.Linear(qd, inner, bias=False)
+        self.to_kv = nn.Linear(cd, inner * 2, bias=False)
+        self.to_out = nn.Linear(inner, qd)
+
+
+class _FF(nn.Module):
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, dim * mult * 2), nn.Identity(), nn.Linear(dim * mult, dim))
+
+
+class GSKLTemporalVariationalAutoEncoder(nn.Module):
+    def __init__(self, *, depth=24, dim=512, queries_dim=512, input_dim=3, gs_dim=14, output_dim=10,
+                 num_inputs=8192, num_latents=1024, latent_dim=128, heads=8, dim_head=-1, weight_tie_layers=False,
+                 decoder_ff=False, enable_flash_attn=False, num_timesteps=24, chunk_size=8192, knn_k=8, beta=7.0):
+        super().__init__()
+        if decoder_ff or weight_tie_layers or queries_dim != dim:
+            raise NotImplementedError("shipped config: decoder_ff=False, weight_tie_layers=False, queries_dim=dim")
+        if dim_head == -1:
+            dim_head = dim // heads
+        if dim_head * heads != dim or dim_head not in (32, 64):
+            raise NotImplementedError("the sm_100a attention kernels cover head dims 32 and 64")
+        self.depth, self.dim, self.heads, self.num_timesteps, self.chunk_size = depth, dim, heads, num_timesteps, chunk_size
+        self.num_latents, self.num_inputs = num_latents, num_inputs
+        self.layers = nn.ModuleList([nn.ModuleList([_Fn(_Attn(dim, dim, dim)), _Fn(_FF(dim))]) for _ in range(depth)])
+        self.gs_embedding = nn.Sequential(nn.Linear(gs_dim, dim), nn.LayerNorm(dim, elementwise_affine=False))
+        self.decoder_cross_attn = _Fn(_Attn(queries_dim, dim, dim))
+        self.to_outputs = nn.Linear(queries_dim, output_dim)
+        self.proj = nn.Linear(latent_dim, dim)
+        for m in self.modules():                       # reference _init_weights :422-436
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.to_outputs.weight, 0)
+        nn.init.constant_(self.to_outputs.bias, 0)
+        self._engine, self._sig = None, None
+
+    def load_state_dict(self, state_dict, strict=False, **kw):
+        # reference checkpoints also carry the encoder; only the decode weights are consumed here
+        own = self.state_dict()
+        sub = {k: v for k, v in state_dict.items() if k in own}
+        missing = [k for k in own if k not in sub]
+        if missing:
+            raise KeyError(f"decode weights missing from checkpoint: {missing[:4]}...")
+        return super().load_state_dict(sub, strict=True)
+
+    def engine(self):
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._engine is None or sig != self._sig:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("decode runs on a CUDA device only (no CPU fallback)")
+            self._engine = VAEDecodeEngine(self.state_dict(), self.heads, self.num_timesteps, dev, self.chunk_size)
+            self._sig = sig
+        return self._engine
+
+    @torch.no_grad()
+    def decode(self, x, queries):
+        """x ((B*T), L, latent_dim), queries (B, Q, 14) -> (B, T, Q, output_dim) fp32."""
+        return self.engine().decode(x, queries)
+
+    def encode(self, *a, **k):
+        raise NotImplementedError("encode() is training-data preparation, outside the inference hot path")

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import check, current_stream, ptr
 
 F16, F32 = torch.float16, torch.float32
-EPI_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_RESID_F16, EPI_F32 = 0, 1, 2, 3, 4
+EPI_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_RESID_F16, EPI_F32, EPI_F32_COMPACT = 0, 1, 2, 3, 4, 5
 
 
 def _ll(vals):
@@ -33,7 +33,7 @@ def gemm(a, w, bias=None, epilogue=EPI_F16, out=None, gate=None, gate_stride=0, 
     if out is None:
         assert epilogue in (EPI_F16, EPI_GELU_F16, EPI_F32)
         out = torch.empty((M, N), dtype=F32 if epilogue == EPI_F32 else F16, device=a.device)
-    assert out.stride(1) == 1 and out.dtype == (F32 if epilogue in (EPI_RESID_F32, EPI_F32) else F16)
+    assert out.stride(1) == 1 and out.dtype == (F32 if epilogue in (EPI_RESID_F32, EPI_F32, EPI_F32_COMPACT) else F16)
     st = _lib.lib().gvf_gemm_f16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
                                  ptr(out), out.stride(0), ptr(gate), gate_stride, rows_per_batch,
                                  current_stream())
@@ -154,10 +154,17 @@ def dit_final_layer(x, shift, scale, mod_stride, rows_per_batch, W, bias, out=No
     return out
 
 
-def dpm_x0(x, v, branches, alpha, sigma, s1, s2, out):
-    check(_lib.lib().gvf_dpm_x0(ptr(x), ptr(v), x.numel(), branches, alpha, sigma, s1, s2, ptr(out),
+def dpm_x0(x, v, branches, alpha, sigma, s1, s2, out, model_type=1):
+    check(_lib.lib().gvf_dpm_x0(ptr(x), ptr(v), x.numel(), branches, model_type, alpha, sigma, s1, s2, ptr(out),
                                 current_stream()), "gvf_dpm_x0")
     return out
+
+
+def dpm_error_sq(x_higher, x_lower, x_prev, atol, rtol, E2):
+    B = x_higher.shape[0]
+    check(_lib.lib().gvf_dpm_error_sq(ptr(x_higher), ptr(x_lower), ptr(x_prev), B, x_higher.numel() // B, atol,
+                                      rtol, ptr(E2), current_stream()), "gvf_dpm_error_sq")
+    return E2
 
 
 def dpm_update(x, m0, m1, cx, cm, inv_r0, order, out):

@@ -102,6 +102,17 @@ GVF_API int gvf_raster_forward(const gvf_raster_params* prm, int F, int P, int a
                        void* stream);
 
 
+/* get_gaussian_tensor (reference train_vae.py:466-472): raw canonical GaussianModel tensors ->
+ * activated [P,14] = [xyz3 | rgb3 | opacity1 | scale3 | rot4] (decoder queries, static_latent). */
+GVF_API int gvf_gaussian_tensor(const gvf_raster_params* prm, int P, const float* xyz, const float* dc,
+                                const float* scaling, const float* rotation, const float* opacity,
+                                float* out, void* stream);
+/* Farthest point sampling of K of P points (rows of `ld` floats, xyz first) -- replaces
+ * torch_cluster.fps in sample_gs (reference utils/inference_utils.py:180-198).  Deterministic
+ * (starts at `start`, ties -> lowest index).  workspace: P floats.  out_idx: K int32. */
+GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start, float* workspace,
+                    int32_t* out_idx, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * 2. Dense attention -- replaces flash_attn.flash_attn_{func,kvpacked_func,qkvpacked_func}
  *    as dispatched by reference model/attention/full_attn.py:74-140
@@ -127,7 +138,9 @@ GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void* v, void* 
  *    A, W fp16 row-major (lda/ldw in elements, multiples of 8); tcgen05 + TMA, fp32 accumulate.
  *    epilogue: 0 fp16 store | 1 GELU(tanh) then fp16 store | 2 fp32 residual:
  *    out[m,n] += fp16(gate[m / rows_per_batch, n] * fp16(acc + bias)) (gate optional, fp16)
- *    | 3 fp16 residual: out = fp16(fp16(acc + bias) + out) | 4 fp32 store.
+ *    | 3 fp16 residual: out = fp16(fp16(acc + bias) + out) | 4 fp32 store
+ *    | 5 fp32 store of the fp16-rounded result into compact rows of ldo <= N columns (W rows
+ *    padded to a multiple of 8, e.g. the VAE's Linear(768 -> 14)).
  * ---------------------------------------------------------------------------------- */
 GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                          int epilogue, const float* bias, void* out, int ldo, const void* gate,
@@ -178,8 +191,14 @@ GVF_API int gvf_dit_final_layer(const float* x, int M, int C, int O, const void*
  *    reference model/dpmsolver.py:284-300 (v -> eps), :328-347 (3-way CFG), :450-459 (x0),
  *    :589-597 / :843-848 (first / second order multistep update).
  * ---------------------------------------------------------------------------------- */
-GVF_API int gvf_dpm_x0(const float* x, const float* v, long long n, int branches, float alpha, float sigma,
-                       float s1, float s2, float* x0, void* stream);
+/* model_type 1: the model predicts v (eps = alpha v + sigma x); 0: it predicts eps. */
+GVF_API int gvf_dpm_x0(const float* x, const float* v, long long n, int branches, int model_type,
+                       float alpha, float sigma, float s1, float s2, float* x0, void* stream);
+/* adaptive solver error (model/dpmsolver.py:1016-1018): per batch b,
+ * E2[b] += sum(((xh - xl) / max(atol, rtol max(|xl|, |xprev|)))^2); caller zeroes E2, then
+ * E = max_b sqrt(E2[b] / n_per_batch). */
+GVF_API int gvf_dpm_error_sq(const float* x_higher, const float* x_lower, const float* x_prev, int B,
+                             long long n_per_batch, float atol, float rtol, float* E2, void* stream);
 GVF_API int gvf_dpm_update(const float* x, const float* m0, const float* m1, long long n, float cx, float cm,
                            float inv_r0, int order, float* out, void* stream);
 /* out = x * a[c] + b[c] over the last dim (or scalars as/bs when a/b are NULL):
