@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- 4D frames/sec of the GVFDiffusion sampling + decode + render hot path.
+
+    python bench.py --gpus N --steps K --warmup W           (torchrun for N > 1)
+    python bench.py --impl reference ...                     (CPU oracle port of the same path)
+
+One "step" = one object end to end: 32-step DPM-Solver++(2M) over the 12-block DiT
+(B=1, T=24 frames, 512 latent tokens, 1370 image / 4096 static context tokens), motion-VAE
+decode to 16 384 x 14 deltas per frame, and rasterisation of the 24 frames at 512 x 512.
+value = objects * 24 frames / time, whole job over all ranks (one object per rank and step:
+weak scaling, no data-path collective).  Synthetic inputs and random-init weights of the
+reference architecture (no network for checkpoints), see gvfdiffusion_b200/synthetic.py.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_FRAMES, N_LAT, C_LAT, L_IMG, C_IMG, N_STATIC, VOXELS, RES, NFE = 24, 512, 16, 1370, 1024, 4096, 2048, 512, 32
+DIT_CFG = dict(resolution=512, in_channels=16, model_channels=512, static_cond_channels=14, image_cond_channels=1024,
+               out_channels=16, num_blocks=12, num_heads=16, mlp_ratio=4, pe_mode="ape", qk_rms_norm=True,
+               use_fp16=True, no_temporal_attn=False)
+VAE_CFG = dict(depth=12, dim=768, queries_dim=768, output_dim=14, num_inputs=8192, num_latents=512, latent_dim=16,
+               heads=12, dim_head=-1, weight_tie_layers=False, decoder_ff=False, enable_flash_attn=True,
+               num_timesteps=T_FRAMES)
+WORKLOAD = ("inference_dpm_latent 32-step DPM-Solver++(2M), 1 object/GPU, 24f x 512^2, 16384 Gaussians "
+            "(BASELINE.json configs[1])")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=0)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_models(device, seed=0):
+    from gvfdiffusion_b200.model.autoencoder import GSKLTemporalVariationalAutoEncoder
+    from gvfdiffusion_b200.model.dit import DiT
+    torch.manual_seed(seed)
+    dit, vae = DiT(**DIT_CFG), GSKLTemporalVariationalAutoEncoder(**VAE_CFG)
+    g = torch.Generator().manual_seed(seed + 1)
+    for m, std in ((dit, 0.02), (vae, 0.02)):          # zero-initialised layers re-drawn
+        for p in m.parameters():
+            if p.abs().sum() == 0:
+                p.data = torch.randn(p.shape, generator=g) * std
+    return dit.to(device).eval(), vae.to(device).eval()
+
+
+def host_inputs(seed):
+    from gvfdiffusion_b200 import synthetic as S
+    canon = S.canonical_gaussians(num_voxels=VOXELS, seed=seed)
+    si = S.sampler_inputs(1, T_FRAMES, N_LAT, C_LAT, L_IMG, C_IMG, seed=seed)
+    pin = lambda t: t.contiguous().pin_memory()
+    return {"canon": {k: pin(v) for k, v in canon.items()}, "noise": pin(si["noise"]),
+            "cond_images": pin(si["cond_images"]), "ext": S.orbit_extrinsics(T_FRAMES), "intr": S.intrinsics()}
+
+
+def reference_betas():
+    import numpy as np
+    import math
+    f = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+    b = np.array([min(1 - f((i + 1) / 1000) / f(i / 1000), 0.999) for i in range(1000)], dtype=np.float64)
+    ac = np.cumprod(1.0 - b)
+    out, last = [], 1.0
+    for a in ac:
+        out.append(1 - a / last)
+        last = a
+    return torch.from_numpy(np.array(out, dtype=np.float64))
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_baseline(threads=None):
+    """The oracle port of the same path on the host cores, bounded sample, extrapolated:
+    1 of 12 DiT blocks at the full shape (x12 blocks x32 NFE), 1 of 12 VAE latent layers (x12) + the
+    decoder cross-attention on 1 of 24 frames (x24), 2 of 24 raster frames (x12)."""
+    import numpy as np
+    from gvfdiffusion_b200 import synthetic as S
+    from oracle import dit as ODIT, gaussian as OG, raster as OR, vae as OVAE
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    g = torch.Generator().manual_seed(0)
+    C, H = 512, 16
+    rnd = lambda *s: torch.randn(*s, generator=g) * 0.02
+    sd = {}
+    p = "blocks.0."
+    for n, (o, i) in {"adaLN_modulation.1": (6 * C, C), "adaLN_modulation_temporal.1": (3 * C, C),
+                      "spatial_self_attn.to_qkv": (3 * C, C), "spatial_self_attn.to_out": (C, C),
+                      "temporal_self_attn.to_qkv": (3 * C, C), "temporal_self_attn.to_out": (C, C),
+                      "image_cross_attn.to_q": (C, C), "image_cross_attn.to_kv": (2 * C, C), "image_cross_attn.to_out": (C, C),
+                      "static_cross_attn.to_q": (C, C), "static_cross_attn.to_kv": (2 * C, C), "static_cross_attn.to_out": (C, C),
+                      "mlp.mlp.0": (4 * C, C), "mlp.mlp.2": (C, 4 * C)}.items():
+        sd[p + n + ".weight"], sd[p + n + ".bias"] = rnd(o, i), rnd(o)
+    for n in ("spatial_self_attn", "temporal_self_attn"):
+        sd[p + n + ".q_rms_norm.gamma"], sd[p + n + ".k_rms_norm.gamma"] = torch.ones(H, 32), torch.ones(H, 32)
+    for n in ("norm3", "norm4"):
+        sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.ones(C), torch.zeros(C)
+    x = torch.randn(1, T_FRAMES, N_LAT, C, generator=g)
+    img = torch.randn(1, T_FRAMES, L_IMG, C, generator=g)
+    st = torch.randn(1, N_STATIC, C, generator=g)
+    mod = torch.randn(1, C, generator=g)
+    P_ = ODIT._P("fp32")
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ODIT.block_forward(sd, p, x, mod, img, st, H, P_)
+    t_block = time.perf_counter() - t0
+    # VAE: one latent layer + decoder cross-attention for one frame
+    D = 768
+    vsd = {"layers.0.0.fn.to_q.weight": rnd(D, D), "layers.0.0.fn.to_kv.weight": rnd(2 * D, D),
+           "layers.0.0.fn.to_out.weight": rnd(D, D), "layers.0.0.fn.to_out.bias": rnd(D),
+           "layers.0.1.fn.net.0.weight": rnd(8 * D, D), "layers.0.1.fn.net.0.bias": rnd(8 * D),
+           "layers.0.1.fn.net.2.weight": rnd(D, 4 * D), "layers.0.1.fn.net.2.bias": rnd(D),
+           "decoder_cross_attn.fn.to_q.weight": rnd(D, D), "decoder_cross_attn.fn.to_kv.weight": rnd(2 * D, D),
+           "decoder_cross_attn.fn.to_out.weight": rnd(D, D), "decoder_cross_attn.fn.to_out.bias": rnd(D),
+           "to_outputs.weight": rnd(14, D), "to_outputs.bias": rnd(14)}
+    xv = torch.randn(T_FRAMES, N_LAT, D, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        n_ = OVAE._ln(xv, 1e-6)
+        xv2 = OVAE.attention(vsd, "layers.0.0.fn.", n_, n_, 12, P_) + xv
+        xv2 = OVAE.feed_forward(vsd, "layers.0.1.fn.", OVAE._ln(xv2, 1e-6), P_) + xv2
+    t_vlayer = time.perf_counter() - t0
+    qe = torch.randn(1, VOXELS * 8, D, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        lat = OVAE.attention(vsd, "decoder_cross_attn.fn.", OVAE._ln(qe, 1e-6), OVAE._ln(xv[:1], 1e-6), 12, P_)
+        torch.nn.functional.linear(lat, vsd["to_outputs.weight"], vsd["to_outputs.bias"])
+    t_vdec = time.perf_counter() - t0
+    # raster: 2 frames
+    canon = S.canonical_gaussians(num_voxels=VOXELS, seed=0)
+    delta = S.raster_delta(2, VOXELS * 8).numpy()
+    ext, intr, const = S.orbit_extrinsics(T_FRAMES)[:2], S.intrinsics(), S.gaussian_constants()
+    vt, pt = [], []
+    for f in range(2):
+        v, p_, _, tfx, tfy = OG.camera_matrices(ext[f], intr, 0.8, 1.6)
+        vt.append(v.numpy())
+        pt.append(p_.numpy())
+    prm = OR.make_params(RES, RES, tfx, tfy, const)
+    t0 = time.perf_counter()
+    OR.render_frames(prm, {k: v.numpy() for k, v in canon.items()}, delta, np.stack(vt), np.stack(pt))
+    t_r2 = time.perf_counter() - t0
+    total = NFE * 12 * t_block + 12 * t_vlayer + T_FRAMES * t_vdec + (T_FRAMES / 2) * t_r2
+    return {"value": T_FRAMES / total, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": (f"timed on host: 1 DiT block fwd at full shape ({t_block:.2f}s) x12 blocks x{NFE} NFE; 1 VAE latent "
+                       f"layer ({t_vlayer:.2f}s) x12; decoder cross-attn 1 frame ({t_vdec:.2f}s) x{T_FRAMES}; raster 2 "
+                       f"frames ({t_r2:.2f}s) x{T_FRAMES // 2}; extrapolated total {total:.0f}s/object; oracle port "
+                       "(torch fp32 + C raster), the reference itself has no CPU rasteriser")}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):
+        vals.append(cpu_baseline())
+    cb = vals[-1]
+    line = {"impl": "reference", "metric": "4D frames/sec (32-step DPM, 24f x 512^2, 16k Gaussians)",
+            "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * T_FRAMES / cb["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
+                                        "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gvfdiffusion_b200 import ops
+    from gvfdiffusion_b200.pipeline import GVFPipeline
+
+    dit, vae = build_models(dev, seed=0)                      # replicated weights
+    pipe = GVFPipeline(dit, vae, reference_betas(), device=dev, resolution=RES)
+    hin = host_inputs(seed=rank)                              # a different object per rank
+    out_host = torch.empty((T_FRAMES, 4, RES, RES), dtype=torch.float32).pin_memory()
+    out_dev = torch.empty((T_FRAMES, 4, RES, RES), dtype=torch.float32, device=dev)
+
+    # resident inputs for the device-timed run
+    canon_d = {k: v.to(dev, non_blocking=True) for k, v in hin["canon"].items()}
+    noise_d, cond_d = hin["noise"].to(dev), hin["cond_images"].to(dev)
+    obj = pipe.prepare_object(canon_d)
+
+    timer = ops.LaunchTimer()
+    launches = [0]
+
+    def step_resident():
+        dit.reset_conditioning()                              # per-object projections are part of the step
+        lat = pipe.sample(obj, cond_d, noise_d, steps=NFE)
+        delta = pipe.decode(lat, obj)
+        pipe.render(obj, delta, hin["ext"], hin["intr"], out=out_dev)
+
+    def step_profiled():
+        """One more step with eager launches (no graph replay) and CUDA events around every attention
+        launch and around the three stages: the per-kernel numbers behind `roofline`."""
+        eng = dit.engine()
+        orig, eng.use_graphs = ops.attention, False
+        ops.attention = _tagged_attention(orig, timer)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        try:
+            dit.reset_conditioning()
+            ev[0].record()
+            lat = pipe.sample(obj, cond_d, noise_d, steps=NFE)
+            ev[1].record()
+            delta = pipe.decode(lat, obj)
+            ev[2].record()
+            pipe.render(obj, delta, hin["ext"], hin["intr"], out=out_dev)
+            ev[3].record()
+        finally:
+            ops.attention, eng.use_graphs = orig, True
+        torch.cuda.synchronize()
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+
+    def step_e2e():
+        dit.reset_conditioning()
+        c = {k: v.to(dev, non_blocking=True) for k, v in hin["canon"].items()}
+        n, ci = hin["noise"].to(dev, non_blocking=True), hin["cond_images"].to(dev, non_blocking=True)
+        o = pipe.prepare_object(c)
+        lat = pipe.sample(o, ci, n, steps=NFE)
+        delta = pipe.decode(lat, o)
+        pipe.render(o, delta, hin["ext"], hin["intr"], out=out_dev)
+        out_host.copy_(out_dev, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    sampler.stop_flag = True
+    sampler.join()
+    Rn, overflow, _ = pipe.rz.status()
+    if overflow:
+        raise SystemExit("rasteriser tile-instance capacity overflowed: result invalid")
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    stage_ms = step_profiled()
+    # rasteriser alone (24 frames), graph-free, for the HBM-side roofline
+    torch.cuda.synchronize()
+    lat = pipe.sample(obj, cond_d, noise_d, steps=2)
+    delta = pipe.decode(lat, obj)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(5):
+        pipe.render(obj, delta, hin["ext"], hin["intr"], out=out_dev)
+    r1.record()
+    torch.cuda.synchronize()
+    raster_ms = r0.elapsed_time(r1) / 5
+
+    if rank != 0:
+        return
+    pk = peaks()
+    ms_step = ms_total / args.steps
+    value = world * T_FRAMES / (ms_step / 1e3)
+    e2e_val = world * T_FRAMES / (ms_e2e / args.steps / 1e3)
+    rec = timer.summary()
+    roof_detail = {}
+    for tag, (n, ms) in rec.items():
+        fl = ATTN_FLOPS.get(tag)
+        if fl:
+            roof_detail[tag] = {"launches": n, "avg_ms": ms / n, "tflops": fl / (ms / n) / 1e9,
+                                "frac_of_sustained": fl / (ms / n) / 1e9 / pk["tf_sustained"]}
+    dom = roof_detail.get("attn_static", {})
+    h2d = sum(v.numel() * 4 for v in hin["canon"].values()) + hin["noise"].numel() * 4 + hin["cond_images"].numel() * 4
+    line = {
+        "metric": "4D frames/sec (32-step DPM, 24f x 512^2, 16k Gaussians)", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate/state)",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "objects_per_step": world, "nfe": NFE, "guidance": "1.0/1.0 (1 branch)",
+                   "l2": "inputs larger than L2 (808 MB hoisted image K/V + 1.2 GB activations per step; no flush)",
+                   "num_rendered": Rn},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": launch_estimate() * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel<32> (static cross-attention, kv 4096)",
+                     "achieved": dom.get("tflops"), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": dom.get("frac_of_sustained"), "traffic": None, "peak_source": pk["source"] + " sustained bf16"},
+        "roofline_detail": roof_detail,
+        "stage_ms_eager": {"sample_32nfe": stage_ms[0], "vae_decode": stage_ms[1], "raster_24f": stage_ms[2]},
+        "roofline_raster": {"bound": "hbm", "kernel": "gvf_raster_forward (4 kernels, 24 frames)",
+                            "achieved": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6,
+                            "peak": pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6 / pk["hbm_gbs"],
+                            "ms": raster_ms, "traffic": None},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as e:   # the oracle is a checker; never let it take the GPU number down
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line))
+
+
+# attention FLOPs per launch (4 * Nb * H * Lq * Lk * d), tagged by shape
+ATTN_FLOPS = {
+    "attn_static": 4 * T_FRAMES * 16 * N_LAT * N_STATIC * 32,
+    "attn_image": 4 * T_FRAMES * 16 * N_LAT * L_IMG * 32,
+    "attn_spatial": 4 * T_FRAMES * 16 * N_LAT * N_LAT * 32,
+    "attn_temporal": 4 * N_LAT * 16 * T_FRAMES * T_FRAMES * 32,
+    "attn_vae_self": 4 * T_FRAMES * 12 * N_LAT * N_LAT * 64,
+    "attn_vae_dec": 4 * T_FRAMES * 12 * 8192 * N_LAT * 64,
+}
+
+
+def _tagged_attention(fn, timer):
+    """CUDA events around every attention launch of the timed region, bucketed by shape."""
+    def call(q, k, v, scale, out=None, q_shared=False, kv_shared=False):
+        D, Lq = q.shape[-1], q.shape[-3]
+        Lk = k.shape[-3]
+        tag = ("attn_static" if kv_shared else "attn_vae_dec" if q_shared else "attn_vae_self" if D == 64 else
+               "attn_temporal" if Lq <= 32 else "attn_image" if Lk == L_IMG else "attn_spatial")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(q, k, v, scale, out=out, q_shared=q_shared, kv_shared=kv_shared)
+        e1.record()
+        timer.records.setdefault(tag, []).append((e0, e1))
+        return r
+    return call
+
+
+def launch_estimate():
+    """Kernel launches of ours per object: counted from the engine structure (dit_engine.py,
+    vae_engine.py, raster_api.cu): per NFE 2 (modulation) + 1 (input) + 12 x 21 + 1 (final) + 2 (DPM)."""
+    per_nfe = 2 + 1 + 12 * 21 + 1 + 2
+    hoist = 2 + 12 + 1 + 12 + 1 + 3
+    vae = 1 + 12 * 7 + 2 + 2 * (2 + 1 + 1 + 1 + 1)
+    return NFE * per_nfe + hoist + vae + 4
+
+
+if __name__ == "__main__":
+    main()

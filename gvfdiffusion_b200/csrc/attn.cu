@@ -181,17 +181,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
           }
         }
         const int valid = a.Lk - j * 128;          // columns >= valid are padding (last tile)
-        // pass 1: row max
+        const bool full = valid >= 128;
+        // pass 1: row max.  TMEM loads are software pipelined: chunk c+1 is in flight while
+        // chunk c is reduced (tcgen05.wait::ld drains everything issued so far).
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(tS + c0, r);
-          tmem_ld_wait();
+        {
+          uint32_t ra[32], rb[32];
+          tmem_ld_x32(tS, ra);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float sv = (c0 + i < valid) ? __uint_as_float(r[i]) : -INFINITY;
-            mx = fmaxf(mx, sv);
+          for (int cc = 0; cc < 4; ++cc) {
+            tmem_ld_wait();
+            uint32_t(&cur)[32] = (cc & 1) ? rb : ra;
+            uint32_t(&nxt)[32] = (cc & 1) ? ra : rb;
+            if (cc < 3) tmem_ld_x32(tS + (cc + 1) * 32, nxt);
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                mx = fmaxf(mx, (cc * 32 + i < valid) ? __uint_as_float(cur[i]) : -INFINITY);
+            }
           }
         }
         const float m_new = fmaxf(m, mx);
@@ -203,23 +213,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         const float mc = m_new * c;
         // pass 2: p = exp2(s*c - m*c), row sum, P -> TMEM (fp16 pairs over S's first 64 columns)
         float lsum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(tS + c0, r);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        {
+          uint32_t ra[32], rb[32];
+          tmem_ld_x32(tS, ra);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), c, -mc));
-            float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), c, -mc));
-            if (c0 + i >= valid) p0 = 0.f;
-            if (c0 + i + 1 >= valid) p1 = 0.f;
-            lsum += p0 + p1;
-            const __half2 hp = __floats2half2_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+          for (int cc = 0; cc < 4; ++cc) {
+            tmem_ld_wait();
+            uint32_t(&cur)[32] = (cc & 1) ? rb : ra;
+            uint32_t(&nxt)[32] = (cc & 1) ? ra : rb;
+            if (cc < 3) tmem_ld_x32(tS + (cc + 1) * 32, nxt);
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = fast_exp2(fmaf(__uint_as_float(cur[i]), c, -mc));
+              float p1 = fast_exp2(fmaf(__uint_as_float(cur[i + 1]), c, -mc));
+              if (!full) {
+                if (cc * 32 + i >= valid) p0 = 0.f;
+                if (cc * 32 + i + 1 >= valid) p1 = 0.f;
+              }
+              lsum += p0 + p1;
+              const __half2 hp = __floats2half2_rn(p0, p1);
+              pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+            }
+            // P chunk cc overwrites S columns [16cc, 16cc+16): already consumed (<= 32cc)
+            tmem_st_x16(tS + cc * 16, pk);
           }
-          tmem_st_x16(tS + (c0 >> 1), pk);
         }
         l += lsum;
         tmem_st_wait();

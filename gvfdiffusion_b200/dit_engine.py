@@ -91,33 +91,87 @@ class DiTEngine:
         self.R = self.w_mod.shape[0]          # nblk * 9C + 2C
         assert self.R == self.nblk * 9 * C + 2 * C
         self._ws_key = None
+        self._pools = {}          # (kind, slot, shape) -> persistent buffers (stable pointers for CUDA graphs)
+        self._graphs = {}
+        self.use_graphs = True
+
+    def _pool(self, kind, slot, shape, make):
+        key = (kind, slot, tuple(shape))
+        if key not in self._pools:
+            self._pools[key] = make()
+        return self._pools[key]
 
     # ------------------------------------------------------------------ per-object precompute
-    def image_kv(self, cond_images):
+    def image_kv(self, cond_images, slot=0):
         """cond_images [T, L, Ci] fp32 (one object) -> per-block K/V [T, L, 2, H, d] fp16.
-        image_cond_proj (model/dit.py:464) then every block's image_cross_attn.to_kv."""
+        image_cond_proj (model/dit.py:464) then every block's image_cross_attn.to_kv.  Results live in
+        per-slot persistent buffers so a captured CUDA graph stays valid from object to object."""
         T, L, Ci = cond_images.shape
-        x16 = ops.cast_f16(cond_images.reshape(T * L, Ci).to(self.dev, F32))
-        emb = ops.gemm(x16, self.w_img, self.b_img, ops.EPI_F16)
+        C = self.C
+        bufs = self._pool("img", slot, (T, L, Ci), lambda: dict(
+            x16=torch.empty((T * L, Ci), dtype=F16, device=self.dev),
+            emb=torch.empty((T * L, C), dtype=F16, device=self.dev),
+            kv=[torch.empty((T * L, 2 * C), dtype=F16, device=self.dev) for _ in self.blocks]))
+        ops.cast_f16(cond_images.reshape(T * L, Ci).to(self.dev, F32), out=bufs["x16"])
+        ops.gemm(bufs["x16"], self.w_img, self.b_img, ops.EPI_F16, out=bufs["emb"])
         out = []
-        for blk in self.blocks:
+        for blk, kv in zip(self.blocks, bufs["kv"]):
             a = blk["image_cross_attn"]
-            out.append(ops.gemm(emb, a["w_kv"], a["b_kv"], ops.EPI_F16).view(T, L, 2, self.H, self.d))
+            out.append(ops.gemm(bufs["emb"], a["w_kv"], a["b_kv"], ops.EPI_F16, out=kv).view(T, L, 2, self.H, self.d))
         return out
 
-    def static_kv(self, static_latent):
+    def static_kv(self, static_latent, slot=0):
         """static_latent [Ls, Cs] fp32 -> per-block K/V [Ls, 2, H, d] fp16 (model/dit.py:465)."""
         Ls = static_latent.shape[0]
-        emb = ops.small_linear(static_latent.to(self.dev, F32).contiguous(), self.w_st, self.b_st, out_f16=True)
+        C = self.C
+        bufs = self._pool("st", slot, (Ls,), lambda: dict(
+            emb=torch.empty((Ls, C), dtype=F16, device=self.dev),
+            kv=[torch.empty((Ls, 2 * C), dtype=F16, device=self.dev) for _ in self.blocks]))
+        ops.small_linear(static_latent.to(self.dev, F32).contiguous(), self.w_st, self.b_st, out_f16=True,
+                         out=bufs["emb"])
         out = []
-        for blk in self.blocks:
+        for blk, kv in zip(self.blocks, bufs["kv"]):
             a = blk["static_cross_attn"]
-            out.append(ops.gemm(emb, a["w_kv"], a["b_kv"], ops.EPI_F16).view(Ls, 2, self.H, self.d))
+            out.append(ops.gemm(bufs["emb"], a["w_kv"], a["b_kv"], ops.EPI_F16, out=kv).view(Ls, 2, self.H, self.d))
         return out
 
-    def pos_embed(self, xyz):
+    def pos_embed(self, xyz, slot=0):
         """deformation_position_xyz [N, 3] -> APE [N, C] fp32 (model/dit.py:470-472)."""
-        return ops.ape(xyz.to(self.dev, F32).contiguous(), self.C)
+        N = xyz.shape[0]
+        buf = self._pool("pos", slot, (N,), lambda: torch.empty((N, self.C), dtype=F32, device=self.dev))
+        return ops.ape(xyz.to(self.dev, F32).contiguous(), self.C, out=buf)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of one NFE
+    def forward_graphed(self, x, t_value, kv_img, kv_static, pos):
+        """Same as forward() for a scalar model time shared by all entries, replayed from a CUDA graph
+        (one NFE = ~260 launches; the graph removes the per-launch host cost).  The graph is keyed on the
+        conditioning buffers' addresses, which are stable across objects (see _pool)."""
+        if not self.use_graphs:
+            tt = torch.full((x.shape[0],), float(t_value), dtype=F32, device=self.dev)
+            return self.forward(x, tt, kv_img, kv_static, pos)
+        key = (tuple(x.shape),
+               tuple(t.data_ptr() for e in kv_img for t in e), tuple(t.data_ptr() for e in kv_static for t in e),
+               tuple(p.data_ptr() for p in pos))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 4:
+                self._graphs.clear()
+            xs = torch.empty_like(x)
+            ts = torch.empty((x.shape[0],), dtype=F32, device=self.dev)
+            xs.copy_(x)
+            ts.fill_(float(t_value))
+            self.forward(xs, ts, kv_img, kv_static, pos)          # warm-up: lazy inits, workspace
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.forward(xs, ts, kv_img, kv_static, pos)
+            g = (graph, xs, ts, out)
+            self._graphs[key] = g
+        graph, xs, ts, out = g
+        xs.copy_(x)
+        ts.fill_(float(t_value))
+        graph.replay()
+        return out
 
     # ------------------------------------------------------------------ forward
     def _workspace(self, Bx, T, N):

@@ -137,11 +137,16 @@ class DiT(nn.Module):
         key = (kind, tensor.data_ptr(), tuple(tensor.shape), tensor._version, str(tensor.device))
         hit = self._cond_cache.get(key)
         if hit is None:
-            if len(self._cond_cache) > 64:
+            if len(self._cond_cache) > 24:
                 self._cond_cache.clear()
-            hit = (fn(tensor), tensor)     # keep the source alive so data_ptr stays unique
+            slot = sum(1 for k in self._cond_cache if k[0] == kind)   # engine-side persistent buffer slot
+            hit = (fn(tensor, slot), tensor)     # keep the source alive so data_ptr stays unique
             self._cond_cache[key] = hit
         return hit[0]
+
+    def reset_conditioning(self):
+        """Forget cached per-object projections (their device buffers are reused by the next object)."""
+        self._cond_cache.clear()
 
     def _cond_sets(self, eng, cond_images, static_latent, xyz):
         B = cond_images.shape[0]
@@ -181,5 +186,4 @@ class DiT(nn.Module):
         xin = x.to(dev, torch.float32).contiguous()
         if nb > 1:
             xin = xin.repeat(nb, *([1] * (x.dim() - 1)))
-        tt = torch.full((nb * B,), float(t_input), dtype=torch.float32, device=dev)
-        return eng.forward(xin, tt, kv_img, kv_st, pos)
+        return eng.forward_graphed(xin, float(t_input), kv_img, kv_st, pos)

@@ -93,11 +93,14 @@ class _WrappedModel:
     def branches(self):
         """Conditioning of each guidance branch in the reference's order (:328-345):
         full-uncond (image zeros, static zeros), image-uncond, cond."""
-        if not self.use_cfg:
-            return [self.condition]
-        full = dict(self.uncond)
-        full["static_latent"] = torch.zeros_like(full["static_latent"])
-        return [full, self.uncond, self.condition]
+        if self._prepared is None:
+            if not self.use_cfg:
+                self._prepared = [self.condition]
+            else:
+                full = dict(self.uncond)
+                full["static_latent"] = torch.zeros_like(full["static_latent"])
+                self._prepared = [full, self.uncond, self.condition]
+        return self._prepared
 
     def raw_outputs(self, x, t):
         """Model outputs of all branches stacked on dim 0: [branches*B, ...]."""

@@ -113,9 +113,10 @@ def dit_modulation(t, W0, b0, W2, b2, Wmod, bmod, temb, silu_temb, mod_out):
     return mod_out
 
 
-def ape(xyz, Cc):
+def ape(xyz, Cc, out=None):
     R = xyz.shape[0]
-    out = torch.empty((R, Cc), dtype=F32, device=xyz.device)
+    if out is None:
+        out = torch.empty((R, Cc), dtype=F32, device=xyz.device)
     check(_lib.lib().gvf_ape(ptr(xyz), R, Cc, ptr(out), current_stream()), "gvf_ape")
     return out
 
@@ -179,3 +180,47 @@ def affine_lastdim(x, a=None, b=None, a_scalar=1.0, b_scalar=0.0, out=None):
     check(_lib.lib().gvf_affine_lastdim(ptr(x), x.numel(), x.shape[-1], ptr(a), ptr(b), a_scalar, b_scalar,
                                         ptr(out), current_stream()), "gvf_affine_lastdim")
     return out
+
+
+def gaussian_tensor(prm, arrays):
+    """raw canonical GaussianModel arrays -> activated [P,14] (train_vae.py:466-472)."""
+    P = arrays[0].shape[0]
+    out = torch.empty((P, 14), dtype=F32, device=arrays[0].device)
+    check(_lib.lib().gvf_gaussian_tensor(C.byref(prm), P, *[ptr(a) for a in arrays], ptr(out),
+                                         current_stream()), "gvf_gaussian_tensor")
+    return out
+
+
+def fps(points, K, start=0):
+    """points [P, >=3] fp32 (xyz first) -> int32 indices [K] of a farthest point sample."""
+    _req(points, F32, "points")
+    P = points.shape[0]
+    assert points.stride(1) == 1
+    ws = torch.empty(P, dtype=F32, device=points.device)
+    idx = torch.empty(K, dtype=torch.int32, device=points.device)
+    check(_lib.lib().gvf_fps(ptr(points), points.stride(0), P, K, start, ptr(ws), ptr(idx), current_stream()),
+          "gvf_fps")
+    return idx
+
+
+# ---------------------------------------------------------------- optional launch timing
+class LaunchTimer:
+    """Records CUDA events around selected launches (bench.py's live roofline numbers)."""
+
+    def __init__(self):
+        self.records = {}
+
+    def wrap(self, name, fn):
+        def timed(*a, **k):
+            tag = k.pop("_tag", name)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            self.records.setdefault(tag, []).append((e0, e1))
+            return r
+        return timed
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.records.items()}

@@ -1,0 +1,89 @@
+"""The sampling + decoding + rendering path of `inference_dpm_latent.py` (reference :205-272)
+for one object on one GPU: FPS conditioning -> DPM-Solver++ over the DiT -> motion-VAE decode
+-> frame-batched canonical+delta rasterisation.  Host orchestration over libgvf_b200.so.
+"""
+import torch
+
+from . import ops
+from . import raster as R
+from . import synthetic as S
+from .model import dpmsolver as D
+
+
+class ObjectState:
+    """Per-object tensors derived from the canonical Gaussians (inference_dpm_latent.py:205-222)."""
+
+    def __init__(self):
+        self.arrays = None          # raw canonical arrays (xyz, dc, scaling, rotation, opacity)
+        self.static_gs = None       # [P,14] activated (decoder queries)
+        self.fps512 = None          # [N,14]
+        self.fps4096 = None         # [Ls,14]
+
+
+class GVFPipeline:
+    def __init__(self, dit, vae, betas, device="cuda", resolution=512, near=0.8, far=1.6, kernel_size=0.1,
+                 bg=(1.0, 1.0, 1.0), gaussian_const=None, num_latents=512, num_static=4096):
+        self.dit, self.vae, self.dev = dit, vae, torch.device(device)
+        self.ns = D.NoiseScheduleVP("discrete", betas=betas)
+        self.res, self.near, self.far, self.kernel_size, self.bg = resolution, near, far, kernel_size, bg
+        self.const = gaussian_const or S.gaussian_constants()
+        self.num_latents, self.num_static = num_latents, num_static
+        self.rz = R.Rasterizer(self.dev)
+        self._gprm = R.make_params(resolution, resolution, 1.0, 1.0, self.const, kernel_size, 1.0, bg)
+
+    # ------------------------------------------------------------------ per-object preparation
+    def prepare_object(self, canon):
+        """canon: dict of raw GaussianModel tensors.  get_gaussian_tensor + sample_gs (FPS to
+        num_latents and num_static) -- reference inference_dpm_latent.py:205-209."""
+        o = ObjectState()
+        o.arrays = R.canon_arrays(canon, self.dev)
+        o.static_gs = ops.gaussian_tensor(self._gprm, o.arrays)
+        P = o.static_gs.shape[0]
+        i512 = ops.fps(o.static_gs, min(self.num_latents, P)).long()
+        i4096 = ops.fps(o.static_gs, min(self.num_static, P)).long()
+        o.fps512 = o.static_gs.index_select(0, i512)
+        o.fps4096 = o.static_gs.index_select(0, i4096)
+        return o
+
+    # ------------------------------------------------------------------ stages
+    def sample(self, obj, cond_images, noise, steps=32, guidance_scale=1.0, guidance_scale2=1.0, adaptive=False,
+               static_mean=0.0, static_std=1.0):
+        """-> latents [1,T,N,C] fp32 (inference_dpm_latent.py:213-249)."""
+        static_latent = obj.fps4096[None]
+        if not (static_mean == 0.0 and static_std == 1.0):
+            static_latent = ops.affine_lastdim(static_latent.contiguous(), a_scalar=1.0 / static_std,
+                                               b_scalar=-static_mean / static_std)
+        cond = {"cond_images": cond_images, "static_latent": static_latent,
+                "deformation_position_xyz": obj.fps512[None, :, :3]}
+        if not hasattr(self, "_zero_img") or self._zero_img.shape != cond_images.shape:
+            self._zero_img = torch.zeros_like(cond_images)
+        unc = dict(cond)
+        unc["cond_images"] = self._zero_img
+        fn = D.model_wrapper(self.dit, self.ns, model_type="v", guidance_type="classifier-free", condition=cond,
+                             unconditional_condition=unc, guidance_scale=guidance_scale,
+                             guidance_scale2=guidance_scale2)
+        solver = D.DPM_Solver(fn, self.ns, algorithm_type="dpmsolver++")
+        return solver.sample(noise, steps=steps, t_start=1.0, t_end=1 / 1000, order=2, skip_type="time_uniform",
+                             method="adaptive" if adaptive else "multistep")
+
+    def decode(self, latents, obj, deformation_mean=None, deformation_std=None):
+        """latents [1,T,N,C] -> delta [T,P,14] fp32 (inference_dpm_latent.py:250-259)."""
+        B, T, N, C = latents.shape
+        z = latents
+        if deformation_mean is not None or deformation_std is not None:
+            z = ops.affine_lastdim(latents.contiguous(), a=deformation_std, b=deformation_mean)
+        return self.vae.decode(z.reshape(B * T, N, C), obj.static_gs[None])[0]
+
+    def render(self, obj, delta, extrinsics, intrinsics, out=None):
+        """delta [F,P,14], extrinsics [F,4,4] -> rgba [F,4,H,W] fp32 (utils/inference_utils.py:256-269
+        with one camera per frame)."""
+        cams, tfx, tfy = R.pack_cameras(extrinsics, intrinsics, self.near, self.far)
+        prm = R.make_params(self.res, self.res, tfx, tfy, self.const, self.kernel_size, 1.0, self.bg)
+        rgba, _ = self.rz.forward(prm, obj.arrays, delta.contiguous(), cams.to(self.dev), want_radii=False,
+                                  out=out, check_overflow=False)
+        return rgba
+
+    def __call__(self, obj, cond_images, noise, extrinsics, intrinsics, steps=32, **kw):
+        lat = self.sample(obj, cond_images, noise, steps=steps, **kw)
+        delta = self.decode(lat, obj)
+        return self.render(obj, delta, extrinsics, intrinsics)

@@ -1,0 +1,68 @@
+"""`GaussianRenderer`: drop-in for the reference's renderers/gaussian_render.py:240-369 (and its
+duplicate renderers/gaussian_render_all_delta.py) on the mip-Gaussian path
+(`pipe.use_mip_gaussian=True`, the only one the inference loop uses):
+
+    renderer.render(gaussian, extrinsics, intrinsics, delta_pc=None, ...) -> {'rgb': (3,H,W), 'alpha': (H,W)}
+
+plus `render_frames` for F (frame, camera) pairs in one launch sequence -- the loop of
+utils/inference_utils.py:256-269 batched.  Camera set-up, GaussianModel activations with delta
+and the rasteriser all run in libgvf_b200.so (gvf_raster_forward)."""
+import numpy as np
+import torch
+
+from .. import raster as R
+
+
+class edict(dict):
+    """Minimal attribute dict (the reference uses easydict.EasyDict)."""
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class GaussianRenderer:
+    def __init__(self, rendering_options={}) -> None:
+        self.pipe = edict({"use_mip_gaussian": False, "kernel_size": 0.1, "convert_SHs_python": False,
+                           "compute_cov3D_python": False, "scale_modifier": 1.0, "debug": False})
+        self.rendering_options = edict({"resolution": None, "near": None, "far": None, "ssaa": 1, "bg_color": "random"})
+        self.rendering_options.update(rendering_options)
+        self.bg_color = None
+        self._rz = None
+
+    def _bg(self):
+        if self.rendering_options["bg_color"] == "random":
+            return (1.0, 1.0, 1.0) if np.random.rand() < 0.5 else (0.0, 0.0, 0.0)
+        return tuple(float(c) for c in self.rendering_options["bg_color"])
+
+    def render_frames(self, gausssian, extrinsics, intrinsics, delta_pc=None):
+        """extrinsics (F,4,4), intrinsics (3,3)|(F,3,3), delta_pc (F,P,14)|None -> rgba (F,4,H,W), radii (F,P)."""
+        if not self.pipe.use_mip_gaussian:
+            raise NotImplementedError("only the mip-Gaussian rasteriser (pipe.use_mip_gaussian=True) is on the "
+                                      "inference path; the diff_gauss variant serves the alignment pre-step")
+        if self.pipe.convert_SHs_python or self.pipe.compute_cov3D_python:
+            raise NotImplementedError("convert_SHs_python / compute_cov3D_python are not used by the reference configs")
+        opt = self.rendering_options
+        if opt["ssaa"] != 1:
+            raise NotImplementedError("ssaa > 1 (bicubic downsample) is not on the inference path")
+        dev = gausssian._xyz.device
+        res = int(opt["resolution"])
+        bg = self._bg()
+        self.bg_color = torch.tensor(bg, dtype=torch.float32, device=dev)
+        cams, tfx, tfy = R.pack_cameras(extrinsics, intrinsics, opt["near"], opt["far"])
+        prm = R.make_params(res, res, tfx, tfy, gausssian.constants(), self.pipe.kernel_size,
+                            self.pipe.scale_modifier, bg)
+        if self._rz is None:
+            self._rz = R.Rasterizer(dev)
+        d = None if delta_pc is None else delta_pc.detach().to(dev, torch.float32).contiguous()
+        return self._rz.forward(prm, R.canon_arrays(gausssian.raw(), dev), d, cams.to(dev))
+
+    def render(self, gausssian, extrinsics, intrinsics, delta_pc=None, detach_static=False, colors_overwrite=None,
+               patch_mask=None):
+        if colors_overwrite is not None:
+            raise NotImplementedError("colors_overwrite is not used on the inference path")
+        d = None if delta_pc is None else delta_pc[None]
+        if d is not None and d.shape[-1] == 10:        # xyz/scale/rot only (gaussian_render.py:158)
+            d = torch.cat([d, torch.zeros(d.shape[:-1] + (4,), device=d.device, dtype=d.dtype)], -1)
+        rgba, radii = self.render_frames(gausssian, extrinsics[None], intrinsics, d)
+        return edict({"rgb": rgba[0, :3], "alpha": rgba[0, 3]})

@@ -1,0 +1,66 @@
+"""`GaussianModel`: the container the renderer consumes, mirroring the reference's
+representations/gaussian/gaussian_model.py:15-128 for the inference path (raw tensors `_xyz`,
+`_features_dc`, `_scaling`, `_rotation`, `_opacity`, the bias constants of setup_functions :23-41
+and the activated getters).  Activations are evaluated by the sm_100a kernels
+(`gvf_gaussian_tensor`; the per-frame `*_with_delta` variants are fused into the rasteriser's
+preprocess), not by torch.  PLY I/O and the training-time helpers are out of scope."""
+import torch
+
+from ... import ops
+from ... import raster as R
+
+
+class GaussianModel:
+    def __init__(self, sh_degree: int = 0, aabb=(-0.5, -0.5, -0.5, 1.0, 1.0, 1.0), mininum_kernel_size: float = 0.0,
+                 scaling_bias: float = 0.01, opacity_bias: float = 0.1, scaling_activation: str = "exp",
+                 device="cuda"):
+        if sh_degree != 0:
+            raise NotImplementedError("the inference path uses sh_degree 0")
+        self.active_sh_degree, self.max_sh_degree = 0, sh_degree
+        self.mininum_kernel_size = mininum_kernel_size
+        self.scaling_bias, self.opacity_bias = scaling_bias, opacity_bias
+        self.scaling_activation_type = scaling_activation
+        self.device = device
+        self.aabb = torch.tensor(aabb, dtype=torch.float32, device=device)
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
+        self._xyz, self._features_dc, self._scaling = z(8, 3), z(8, 1, 3), z(8, 3)
+        self._rotation, self._opacity = z(8, 4), z(8, 1)
+        # setup_functions (:23-41): biases exactly as the reference derives them (fp32 torch scalars)
+        x = torch.tensor(scaling_bias)
+        sb = (x + torch.log(-torch.expm1(-x))) if scaling_activation == "softplus" else torch.log(x)
+        p = torch.tensor(opacity_bias)
+        self.scale_bias, self.opacity_logit_bias = float(sb), float(torch.log(p / (1 - p)))
+
+    def constants(self):
+        return {"aabb": tuple(float(a) for a in self.aabb.tolist()), "scale_bias": self.scale_bias,
+                "min_kernel": float(self.mininum_kernel_size), "opacity_bias": self.opacity_logit_bias,
+                "softplus": self.scaling_activation_type == "softplus"}
+
+    def raw(self):
+        return {"_xyz": self._xyz, "_features_dc": self._features_dc, "_scaling": self._scaling,
+                "_rotation": self._rotation, "_opacity": self._opacity}
+
+    def gaussian_tensor(self):
+        """[P,14] = [xyz3 | rgb3 | opacity1 | scale3 | rot4] (train_vae.py:466-472)."""
+        prm = R.make_params(16, 16, 1.0, 1.0, self.constants())
+        return ops.gaussian_tensor(prm, R.canon_arrays(self.raw(), self._xyz.device))
+
+    @property
+    def get_xyz(self):
+        return self.gaussian_tensor()[:, 0:3]
+
+    @property
+    def get_features(self):
+        return self._features_dc
+
+    @property
+    def get_opacity(self):
+        return self.gaussian_tensor()[:, 6:7]
+
+    @property
+    def get_scaling(self):
+        return self.gaussian_tensor()[:, 7:10]
+
+    @property
+    def get_rotation(self):
+        return self.gaussian_tensor()[:, 10:14]

@@ -1,0 +1,105 @@
+"""GPU checks of the reference-facing API mirrors (renderer, rasteriser shim, attention dispatch,
+pipeline pieces: gaussian tensor, FPS) against the oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gaussian as OG
+from oracle import raster as OR
+from tests import _scenes
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(canon):
+    from gvfdiffusion_b200.representations.gaussian import GaussianModel
+    gm = GaussianModel(sh_degree=0, aabb=[-0.5, -0.5, -0.5, 1.0, 1.0, 1.0], mininum_kernel_size=0.0009,
+                       scaling_bias=0.004, opacity_bias=0.1, scaling_activation="softplus", device=DEV)
+    for k, v in canon.items():
+        setattr(gm, k, v.to(DEV))
+    return gm
+
+
+def test_gaussian_renderer_matches_oracle():
+    from gvfdiffusion_b200.renderers import GaussianRenderer
+    import gvfdiffusion_b200.renderers.gaussian_render_all_delta as alt
+    assert alt.GaussianRenderer is GaussianRenderer
+    canon, delta, ext, intr, const = _scenes.scene(128, 2, 96, 96)
+    outs = _scenes.oracle_frames(canon, delta, ext, intr, const, 96, 96)
+    r = GaussianRenderer({"near": 0.8, "far": 1.6, "bg_color": (1.0, 1.0, 1.0)})
+    r.pipe.use_mip_gaussian = True
+    r.rendering_options.resolution = 96
+    gm = _model(canon)
+    assert gm.constants()["scale_bias"] == const["scale_bias"] and gm.constants()["opacity_bias"] == const["opacity_bias"]
+    for f in range(2):
+        res = r.render(gm, ext[f].to(DEV), intr.to(DEV), delta_pc=delta[f].to(DEV))
+        assert res["rgb"].shape == (3, 96, 96)
+        assert np.abs(res.rgb.cpu().numpy() - outs[f]["rgba"][:3]).max() < 1e-2
+        assert np.abs(res["alpha"].cpu().numpy() - outs[f]["rgba"][3]).max() < 1e-2
+    rgba, radii = r.render_frames(gm, ext.to(DEV), intr.to(DEV), delta.to(DEV))
+    for f in range(2):
+        assert np.array_equal(radii[f].cpu().numpy(), outs[f]["radii"])
+
+
+def test_rasterizer_shim_signature_and_errors():
+    from gvfdiffusion_b200.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    canon, delta, ext, intr, const = _scenes.scene(64, 1, 64, 64)
+    outs = _scenes.oracle_frames(canon, delta, ext, intr, const, 64, 64)
+    m3, sc, rt, sh, op = (torch.from_numpy(a).to(DEV) for a in outs[0]["activated"])
+    vt, pt, campos, tfx, tfy = OG.camera_matrices(ext[0], intr, 0.8, 1.6)
+    st = GaussianRasterizationSettings(image_height=64, image_width=64, tanfovx=tfx, tanfovy=tfy, kernel_size=0.1,
+                                       subpixel_offset=torch.zeros(64, 64, 2, device=DEV), bg=torch.ones(3, device=DEV),
+                                       scale_modifier=1.0, viewmatrix=vt.to(DEV), projmatrix=pt.to(DEV), sh_degree=0,
+                                       campos=campos.to(DEV), prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=st)
+    color, radii = rast(means3D=m3, means2D=torch.zeros_like(m3), shs=sh.reshape(-1, 1, 3), colors_precomp=None,
+                        opacities=op, scales=sc, rotations=rt, cov3D_precomp=None)
+    assert np.array_equal(radii.cpu().numpy(), outs[0]["radii"])
+    assert np.abs(color.cpu().numpy() - outs[0]["rgba"][:3]).max() < 1e-2
+    with pytest.raises(Exception):
+        rast(means3D=m3, means2D=None, shs=None, colors_precomp=None, opacities=op, scales=sc, rotations=rt)
+    with pytest.raises(Exception):
+        rast(means3D=m3, means2D=None, shs=sh, opacities=op, scales=None, rotations=None)
+
+
+def test_attention_dispatch_forms():
+    from gvfdiffusion_b200.model.attention import scaled_dot_product_attention as sdpa
+    g = torch.Generator().manual_seed(0)
+    qkv = torch.randn(2, 200, 3, 4, 32, generator=g).to(DEV).half()
+    q, k, v = qkv.unbind(2)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
+                                                           v.float().transpose(1, 2)).transpose(1, 2)
+    for out in (sdpa(qkv), sdpa(q, torch.stack([k, v], 2)), sdpa(q, k, v), sdpa(q=q, k=k, v=v)):
+        assert out.shape == q.shape
+        assert (out.float() - ref).abs().max() < 2e-3 * ref.abs().max()
+
+
+def test_gaussian_tensor_and_fps():
+    from gvfdiffusion_b200 import ops
+    canon, _, _, _, const = _scenes.scene(256, 1, 64, 64)
+    gm = _model(canon)
+    gt = gm.gaussian_tensor()
+    ref = OG.gaussian_tensor(canon, const)
+    assert torch.allclose(gt.cpu(), ref, rtol=3e-6, atol=1e-7)
+    # bit-exact against the C oracle activation (same reproducible math)
+    prm = OR.make_params(16, 16, 1.0, 1.0, const)
+    m3, sc, rt, sh, op = OR.activate(prm, {k: v.numpy() for k, v in canon.items()}, None)
+    assert np.array_equal(gt[:, 7:10].cpu().numpy(), sc) and np.array_equal(gt[:, 6].cpu().numpy(), op[:, 0])
+    # FPS: bit-exact indices vs a numpy restatement (same float32 op order)
+    pts = gt[:, :3].contiguous()
+    K = 200
+    idx = ops.fps(gt, K).cpu().numpy()
+    p = pts.cpu().numpy()
+    mind = np.full(p.shape[0], 3.0e38, np.float32)
+    cur, ref_idx = 0, [0]
+    for _ in range(1, K):
+        d = p - p[cur]
+        dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        mind = np.minimum(mind, dist.astype(np.float32))
+        cur = int(np.argmax(mind))
+        ref_idx.append(cur)
+    assert np.array_equal(idx, np.array(ref_idx, np.int32))
+    assert len(set(idx.tolist())) == K
