@@ -38,6 +38,8 @@ _SIGS = {
                                    C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_float, _P]),
     "gvf_gemm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                _P, C.c_int, C.c_int, _P]),
+    "gvf_gemm_qkv_rmsnorm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
+                                           _P, _P, C.c_int, _P]),
     "gvf_small_linear": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "gvf_ln_mod_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gvf_rmsnorm_heads_f16": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -8,18 +8,19 @@
 // packed qkv / kv tensors and the temporal (strided) view are addressed in place by TMA.
 //
 // One CTA = one (batch, head) x up to two 128-row query tiles ("A" and "B", ping-pong):
+//   (12 warps: 0 TMA, 1-2 MMA issuers, 3 TMEM allocator, 4-7 / 8-11 the two softmax warpgroups)
 //   warp 0      TMA producer: Q tiles once, then K/V tiles [128 x d] through a 4-stage
 //               mbarrier ring (SWIZZLE_64B for d=32, SWIZZLE_128B for d=64)
-//   warp 1      single-thread tcgen05.mma issuer:
+//   warps 1,2   single-thread tcgen05.mma issuers, one per query tile:
 //                 S = Q K^T   (SS: A,B K-major from smem, M=128 N=128 K=d)   -> TMEM [128 cols]
 //                 O' = P V    (TS: A = P from TMEM, B = V tile MN-major, M=128 N=d K=128)
-//               issue order QK(j+1,X) right behind PV(j,X) so the tensor pipe works on one
-//               query tile while the other tile's softmax runs
-//   warps 2-5   softmax of tile A, warps 6-9 softmax of tile B: thread = one query row
+//               S(j+1) is issued as soon as the softmax warps have pulled S(j) into registers
+//               (s_free), so the next scores are ready before the current exponentials finish
+//   warps 4-7   softmax of tile A, warps 8-11 softmax of tile B: thread = one query row
 //               (TMEM lane); tcgen05.ld S -> running max / exp2 / row sum in registers ->
-//               P (fp16) written back over S's columns with tcgen05.st; the per-tile partial
+//               P (fp16 pairs) to its own TMEM columns with tcgen05.st; the per-tile partial
 //               product O' is read back from TMEM one iteration later and accumulated in
-//               registers (O <- O * alpha + O'), so no TMEM read-modify-write and no
+//               registers (O <- (O + O') * alpha), so no TMEM read-modify-write and no
 //               correction warpgroup is needed for d <= 64.
 // With d = 32 the MUFU exp2 (1 per score) bounds the kernel, not the MMA pipe: 128x128 scores
 // cost 1024 MUFU cycles/SM vs 256 tensor cycles -- see DESIGN.md for the roofline.
@@ -47,7 +48,7 @@ struct AttnArgs {
 };
 
 template <int D>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
   constexpr int ROWB = D * 2;                      // bytes per smem row
@@ -55,10 +56,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   constexpr uint64_t SWZ = (D == 32) ? SWZ_64B : SWZ_128B;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int S = kAttnStages;
-  constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
+  // TMEM columns: S (fp32 scores) and P (fp16 probabilities, 2 per column) of both query tiles, O'
+  constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 384 + D;
+  constexpr bool kSinglePass = (D == 32);          // whole score row in registers -> S released early
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t q_full, kv_full[S], kv_empty[S], s_full[2], p_full[2], o_final[2];
+  __shared__ uint64_t q_full, kv_full[S], kv_empty[S], s_full[2], s_free[2], p_full[2], o_full[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                              // 2 tiles
@@ -72,14 +75,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
-    for (int s = 0; s < S; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&o_final[x], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], nq); }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&s_free[x], 128);
+      mbar_init(&p_full[x], 128);
+      mbar_init(&o_full[x], 1);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
   }
-  if (warp == 2) {
+  if (warp == 3) {
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
   }
@@ -88,6 +96,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  // Register re-distribution between warpgroups (setmaxnreg): warps 0-3 only issue TMA / MMA and
+  // keep 56 registers; the two softmax warpgroups (warps 4-7, 8-11) grow to 216 so that a whole
+  // 128-wide score row plus the output accumulator stay in registers without spilling.
+  // (each setmaxnreg sits at the top of the branch it governs so ptxas budgets that region only)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -103,63 +117,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
                     nb * a.kv_batch_mul);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer of tile x
+    const int x = (warp == 1) ? 0 : 1;
+    if (lane == 0 && x < nq) {
       const uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
       const uint32_t idesc_pv = make_idesc_f16(128, D, 0, 1);
-      const uint32_t sq = smem_u32(sQ), skv = smem_u32(sKV);
-      auto issue_qk = [&](int x, int stage) {
-        const uint32_t qa = sq + x * TILE_BYTES, ka = skv + stage * 2 * TILE_BYTES;
+      const uint32_t qa = smem_u32(sQ) + x * TILE_BYTES, skv = smem_u32(sKV);
+      const uint32_t tS = tmem + (x ? TM_S1 : TM_S0), tP = tmem + (x ? TM_P1 : TM_P0),
+                     tO = tmem + (x ? TM_O1 : TM_O0);
+      auto issue_qk = [&](int stage) {
+        const uint32_t ka = skv + stage * 2 * TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          mma_ss(tmem + (x ? TM_S1 : TM_S0), make_smem_desc(qa + k * 32, 16, SBO, SWZ),
-                 make_smem_desc(ka + k * 32, 16, SBO, SWZ), idesc_qk, k != 0);
+          mma_ss(tS, make_smem_desc(qa + k * 32, 16, SBO, SWZ), make_smem_desc(ka + k * 32, 16, SBO, SWZ),
+                 idesc_qk, k != 0);
       };
-      auto issue_pv = [&](int x, int stage) {
+      auto issue_pv = [&](int stage) {
         const uint32_t va = skv + stage * 2 * TILE_BYTES + TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          mma_ts(tmem + (x ? TM_O1 : TM_O0), tmem + (x ? TM_S1 : TM_S0) + k * 8,
-                 make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv, k != 0);
+          mma_ts(tO, tP + k * 8, make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv, k != 0);
       };
       mbar_wait(&q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      for (int x = 0; x < nq; ++x) {
-        issue_qk(x, 0);
-        tc_commit(&s_full[x]);
-      }
+      issue_qk(0);
+      tc_commit(&s_full[x]);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j % S;
-        const bool more = j + 1 < n_kv;
-        const int s1 = (j + 1) % S;
-        if (more) {
+        if (j + 1 < n_kv) {
+          // S(j+1) = Q K(j+1)^T as soon as the softmax warps have pulled S(j) out of TMEM
+          const int s1 = (j + 1) % S;
           mbar_wait(&kv_full[s1], ((j + 1) / S) & 1);
+          mbar_wait(&s_free[x], j & 1);
           tc_fence_after();
+          issue_qk(s1);
+          tc_commit(&s_full[x]);
         }
-        for (int x = 0; x < nq; ++x) {
-          mbar_wait(&p_full[x], j & 1);
-          tc_fence_after();
-          issue_pv(x, s);
-          if (more) {
-            issue_qk(x, s1);
-            tc_commit(&s_full[x]);
-          } else {
-            tc_commit(&o_final[x]);
-          }
-        }
+        mbar_wait(&p_full[x], j & 1);              // P(j) is in TMEM
+        tc_fence_after();
+        issue_pv(s);
+        tc_commit(&o_full[x]);
         tc_commit(&kv_empty[s]);
       }
     }
+  }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
-    const int x = (warp - 2) >> 2;                 // 0: tile A, 1: tile B
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int x = (warp - 4) >> 2;                 // 0: tile A (warps 4-7), 1: tile B (warps 8-11)
     if (x < nq) {
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;         // row inside the tile == TMEM lane
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
       const uint32_t tS = tmem + (x ? TM_S1 : TM_S0) + lane_addr;
+      const uint32_t tP = tmem + (x ? TM_P1 : TM_P0) + lane_addr;
       const uint32_t tO = tmem + (x ? TM_O1 : TM_O0) + lane_addr;
       const float c = a.scale_log2e;
       float O[D];
@@ -167,94 +180,129 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       for (int i = 0; i < D; ++i) O[i] = 0.f;
       float m = -INFINITY, l = 0.f;
 
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&s_full[x], j & 1);
-        tc_fence_after();
-        if (j > 0) {                               // fold in O' = P_{j-1} V_{j-1}
+      auto fold_o = [&](float alpha) {             // O <- (O + O'(j-1)) * alpha
 #pragma unroll
-          for (int d0 = 0; d0 < D; d0 += 32) {
-            uint32_t r[32];
-            tmem_ld_x32(tO + d0, r);
-            tmem_ld_wait();
+        for (int d0 = 0; d0 < D; d0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(tO + d0, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) O[d0 + i] += __uint_as_float(r[i]);
-          }
+          for (int i = 0; i < 32; ++i) O[d0 + i] = (O[d0 + i] + __uint_as_float(r[i])) * alpha;
         }
+      };
+
+      for (int j = 0; j < n_kv; ++j) {
         const int valid = a.Lk - j * 128;          // columns >= valid are padding (last tile)
         const bool full = valid >= 128;
-        // pass 1: row max.  TMEM loads are software pipelined: chunk c+1 is in flight while
-        // chunk c is reduced (tcgen05.wait::ld drains everything issued so far).
-        float mx = -INFINITY;
-        {
-          uint32_t ra[32], rb[32];
-          tmem_ld_x32(tS, ra);
+        mbar_wait(&s_full[x], j & 1);
+        tc_fence_after();
+        if constexpr (kSinglePass) {
+          // whole score row -> registers, then hand S back to the MMA warp at once
+          uint32_t sv[128];
+          tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+          tmem_ld_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+          tmem_ld_x32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[64]));
+          tmem_ld_x32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&sv[96]));
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&s_free[x]);
+          float mx = -INFINITY;
+          if (full) {
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            tmem_ld_wait();
-            uint32_t(&cur)[32] = (cc & 1) ? rb : ra;
-            uint32_t(&nxt)[32] = (cc & 1) ? ra : rb;
-            if (cc < 3) tmem_ld_x32(tS + (cc + 1) * 32, nxt);
-            if (full) {
+            for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+          } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
-            } else {
+            for (int i = 0; i < 128; ++i) {
+              if (i >= valid) sv[i] = 0xff800000u;   // -inf
+              mx = fmaxf(mx, __uint_as_float(sv[i]));
+            }
+          }
+          const float m_new = fmaxf(m, mx);
+          const float alpha = fast_exp2((m - m_new) * c);
+          m = m_new;
+          const float mc = m_new * c;
+          float lsum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 128; i += 2) {         // packed fp16 pairs overwrite sv[0..63] in place
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), c, -mc));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
+            lsum += p0 + p1;
+            const __half2 hp = __floats2half2_rn(p0, p1);
+            sv[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+          }
+          l = l * alpha + lsum;
+          if (j > 0) {                             // PV(j-1) finished long ago; P region is free again
+            mbar_wait(&o_full[x], (j - 1) & 1);
+            tc_fence_after();
+            fold_o(alpha);
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            tmem_st_x16(tP + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&sv[cc * 16]));
+        } else {
+          // two passes over S in TMEM (d = 64: 64 accumulator registers leave no room for the row)
+          float mx = -INFINITY;
+          {
+            uint32_t ra[32], rb[32];
+            tmem_ld_x32(tS, ra);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              tmem_ld_wait();
+              uint32_t(&cur)[32] = (cc & 1) ? rb : ra;
+              uint32_t(&nxt)[32] = (cc & 1) ? ra : rb;
+              if (cc < 3) tmem_ld_x32(tS + (cc + 1) * 32, nxt);
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                mx = fmaxf(mx, (cc * 32 + i < valid) ? __uint_as_float(cur[i]) : -INFINITY);
+                mx = fmaxf(mx, (full || cc * 32 + i < valid) ? __uint_as_float(cur[i]) : -INFINITY);
             }
           }
-        }
-        const float m_new = fmaxf(m, mx);
-        const float alpha = fast_exp2((m - m_new) * c);
-        m = m_new;
-        l *= alpha;
+          const float m_new = fmaxf(m, mx);
+          const float alpha = fast_exp2((m - m_new) * c);
+          m = m_new;
+          const float mc = m_new * c;
+          if (j > 0) {
+            mbar_wait(&o_full[x], (j - 1) & 1);
+            tc_fence_after();
+            fold_o(alpha);
+          }
+          float lsum = 0.f;
+          {
+            uint32_t ra[32], rb[32];
+            tmem_ld_x32(tS, ra);
 #pragma unroll
-        for (int i = 0; i < D; ++i) O[i] *= alpha;
-        const float mc = m_new * c;
-        // pass 2: p = exp2(s*c - m*c), row sum, P -> TMEM (fp16 pairs over S's first 64 columns)
-        float lsum = 0.f;
-        {
-          uint32_t ra[32], rb[32];
-          tmem_ld_x32(tS, ra);
+            for (int cc = 0; cc < 4; ++cc) {
+              tmem_ld_wait();
+              uint32_t(&cur)[32] = (cc & 1) ? rb : ra;
+              uint32_t(&nxt)[32] = (cc & 1) ? ra : rb;
+              if (cc < 3) tmem_ld_x32(tS + (cc + 1) * 32, nxt);
+              uint32_t pk[16];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            tmem_ld_wait();
-            uint32_t(&cur)[32] = (cc & 1) ? rb : ra;
-            uint32_t(&nxt)[32] = (cc & 1) ? ra : rb;
-            if (cc < 3) tmem_ld_x32(tS + (cc + 1) * 32, nxt);
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float p0 = fast_exp2(fmaf(__uint_as_float(cur[i]), c, -mc));
-              float p1 = fast_exp2(fmaf(__uint_as_float(cur[i + 1]), c, -mc));
-              if (!full) {
-                if (cc * 32 + i >= valid) p0 = 0.f;
-                if (cc * 32 + i + 1 >= valid) p1 = 0.f;
+              for (int i = 0; i < 32; i += 2) {
+                float p0 = fast_exp2(fmaf(__uint_as_float(cur[i]), c, -mc));
+                float p1 = fast_exp2(fmaf(__uint_as_float(cur[i + 1]), c, -mc));
+                if (!full) {
+                  if (cc * 32 + i >= valid) p0 = 0.f;
+                  if (cc * 32 + i + 1 >= valid) p1 = 0.f;
+                }
+                lsum += p0 + p1;
+                const __half2 hp = __floats2half2_rn(p0, p1);
+                pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
               }
-              lsum += p0 + p1;
-              const __half2 hp = __floats2half2_rn(p0, p1);
-              pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+              tmem_st_x16(tP + cc * 16, pk);
             }
-            // P chunk cc overwrites S columns [16cc, 16cc+16): already consumed (<= 32cc)
-            tmem_st_x16(tS + cc * 16, pk);
           }
+          l = l * alpha + lsum;
+          tc_fence_before();
+          mbar_arrive(&s_free[x]);
         }
-        l += lsum;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
       }
       // last partial product
-      mbar_wait(&o_final[x], 0);
+      mbar_wait(&o_full[x], (n_kv - 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int d0 = 0; d0 < D; d0 += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(tO + d0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) O[d0 + i] += __uint_as_float(r[i]);
-      }
+      fold_o(1.0f);
       const int qi = q0 + x * 128 + row;
       if (qi < a.Lq) {
         const float inv = 1.0f / l;
@@ -271,7 +319,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 3) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -351,7 +399,7 @@ static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
     configured = true;
   }
   dim3 grid((a.Lq + 255) / 256, a.H, Nb);
-  attn_fwd_kernel<D><<<grid, 320, SMEM, st>>>(mq, mk, mv, a);
+  attn_fwd_kernel<D><<<grid, 384, SMEM, st>>>(mq, mk, mv, a);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 

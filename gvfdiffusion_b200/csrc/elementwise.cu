@@ -135,37 +135,41 @@ __global__ void __launch_bounds__(256) rmsnorm_heads_kernel(__half* __restrict__
 // ---------------------------------------------------------------------------------------
 // TimestepEmbedder (reference model/dit.py:59-100): t[B] -> silu(t_emb)[B,C] as fp16 values.
 // One CTA per batch element, C threads.  W0 [C,256], W2 [C,C] fp16; biases fp32 (fp16-valued).
-__global__ void temb_kernel(const float* __restrict__ t, const __half* __restrict__ W0,
-                            const float* __restrict__ b0, const __half* __restrict__ W2,
-                            const float* __restrict__ b2, int C, int F,
-                            __half* __restrict__ temb_out, __half* __restrict__ silu_out) {
+__global__ void __launch_bounds__(1024) temb_kernel(const float* __restrict__ t, const __half* __restrict__ W0,
+                                                    const float* __restrict__ b0, const __half* __restrict__ W2,
+                                                    const float* __restrict__ b2, int C, int F,
+                                                    __half* __restrict__ temb_out, __half* __restrict__ silu_out) {
   extern __shared__ float sh[];
   float* emb = sh;        // F
   float* hid = sh + F;    // C
-  const int b = blockIdx.x, j = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   const float tv = t[b];
   const int half = F / 2;
-  for (int i = j; i < half; i += blockDim.x) {
+  for (int i = tid; i < half; i += blockDim.x) {
     const float freq = expf(-9.210340371976184f * (float)i / (float)half);
     const float a = tv * freq;
     emb[i] = r16f(cosf(a));
     emb[half + i] = r16f(sinf(a));
   }
   __syncthreads();
-  if (j < C) {
-    float acc = 0.f;
+  for (int j = w; j < C; j += nw) {                 // one warp per output row: coalesced weight reads
     const __half* wr = W0 + (size_t)j * F;
-    for (int i = 0; i < F; ++i) acc += __half2float(wr[i]) * emb[i];
-    hid[j] = r16f(silu(r16f(acc + b0[j])));
+    float acc = 0.f;
+    for (int i = lane; i < F; i += 32) acc += __half2float(wr[i]) * emb[i];
+    acc = warp_sum(acc);
+    if (lane == 0) hid[j] = r16f(silu(r16f(acc + b0[j])));
   }
   __syncthreads();
-  if (j < C) {
-    float acc = 0.f;
+  for (int j = w; j < C; j += nw) {
     const __half* wr = W2 + (size_t)j * C;
-    for (int i = 0; i < C; ++i) acc += __half2float(wr[i]) * hid[i];
-    const float te = r16f(acc + b2[j]);
-    temb_out[(size_t)b * C + j] = __float2half_rn(te);
-    silu_out[(size_t)b * C + j] = __float2half_rn(silu(te));
+    float acc = 0.f;
+    for (int i = lane; i < C; i += 32) acc += __half2float(wr[i]) * hid[i];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float te = r16f(acc + b2[j]);
+      temb_out[(size_t)b * C + j] = __float2half_rn(te);
+      silu_out[(size_t)b * C + j] = __float2half_rn(silu(te));
+    }
   }
 }
 
@@ -507,7 +511,7 @@ GVF_API int gvf_dit_modulation(const float* t, int B, int C, int F, const void* 
                                const void* W2, const float* b2, const void* Wmod, const float* bmod,
                                int R, void* temb, void* silu_temb, void* mod_out, void* stream) {
   if (!t || !W0 || !W2 || !Wmod || !mod_out || B <= 0 || B > 8 || C > 1024 || (C % 32)) return GVF_ERR_INVALID;
-  temb_kernel<<<B, C, (F + C) * sizeof(float), ST(stream)>>>(t, (const __half*)W0, b0, (const __half*)W2, b2, C,
+  temb_kernel<<<B, 1024, (F + C) * sizeof(float), ST(stream)>>>(t, (const __half*)W0, b0, (const __half*)W2, b2, C,
                                                              F, (__half*)temb, (__half*)silu_temb);
   if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
   mod_gemv_kernel<8><<<(R + 7) / 8, 256, 0, ST(stream)>>>((const __half*)Wmod, bmod, (const __half*)silu_temb, B,

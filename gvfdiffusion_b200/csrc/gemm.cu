@@ -26,19 +26,27 @@ constexpr int kBM = 128, kBK = 64;
 struct GemmEpi {
   int mode;
   const float* bias;        // [N] or null
-  void* out;                // fp16 [M,N] (modes 0,1,3) or fp32 [M,N] (modes 2,4,5)
+  void* out;                // fp16 [M,N] (modes 0,1,3,6) or fp32 [M,N] (modes 2,4,5)
   const __half* gate;       // mode 2: [batches, gate_stride] fp16-valued gates or null
   int gate_stride;          // elements between batches in gate
   int rows_per_batch;       // mode 2: row -> batch index
   int ldo;                  // leading dimension of out (elements)
+  const float* gamma_q;     // mode 6: per-head RMS-norm gains [H, 32] for columns [0, norm_cols/2)
+  const float* gamma_k;     //         and [norm_cols/2, norm_cols)
+  int norm_cols;            // mode 6: columns below this are RMS-normalised per 32-wide head
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh(u)), tanh(u) = 1 - 2 / (exp(2u) + 1): two MUFU ops, ~1e-6 accurate
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  const float u = k0 * (x + k1 * x * x * x);
+  const float t = 1.0f - __fdividef(2.0f, __expf(2.0f * u) + 1.0f);
+  return 0.5f * x * (1.0f + t);
 }
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
+
+constexpr int kEpiCols = 64;                 // columns per epilogue chunk
+constexpr int kStgLd = kEpiCols + 1;         // padded row of the per-warp staging tile (floats)
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 2)
@@ -47,8 +55,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[BN];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = BN * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  static_assert(4 * 32 * kStgLd * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline smem");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x, tile_m = blockIdx.y;
   const int kblocks = (K + kBK - 1) / kBK;
@@ -66,6 +76,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   if (warp == 2) {
     tmem_alloc(&tmem_base_s, BN);
     tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {   // bias of this tile's columns -> smem (epilogue warps)
+    const int c = tile_n * BN + (threadIdx.x - 64);
+    s_bias[threadIdx.x - 64] = (ep.bias && c < N) ? __ldg(ep.bias + c) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -104,85 +118,136 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       tc_commit(&accum_bar);
     }
   } else {
-    // epilogue: warp (2..5) owns TMEM lanes 32*(warp%4) .. +31
+    // ---------------------------------------------------------------- epilogue (warps 2..5)
+    // Phase 1 (thread = row): tcgen05.ld 64 columns, bias + row-wise math (GELU / fp16 rounding /
+    // per-head RMS norm), park the values in a per-warp staging tile (the pipeline smem is free
+    // once accum_bar fires).  Phase 2 (lane = column pair): walk the 32 rows so that every global
+    // access of the warp is one contiguous 128 B (fp16) / 256 B (fp32) row segment.
     const int q = warp & 3;
-    const int row = tile_m * kBM + q * 32 + lane;
+    const int row0 = tile_m * kBM + q * 32;
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    const bool row_ok = row < M;
-    const int b = (ep.mode == 2 && ep.gate) ? row / ep.rows_per_batch : 0;
+    float* stg = reinterpret_cast<float*>(smem) + q * 32 * kStgLd;
+    const int mode = ep.mode;
+    const int rows_here = min(32, M - row0);
+    const int b_first = row0 / ep.rows_per_batch;
+    const bool one_batch = rows_here <= 0 || (row0 + rows_here - 1) / ep.rows_per_batch == b_first;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the divergent stores
-      tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + c0, r);
-      tmem_ld_wait();
+    for (int c0 = 0; c0 < BN; c0 += kEpiCols) {
       const int col0 = tile_n * BN + c0;
-      if (!row_ok || col0 >= N) continue;
-      float v[32];
+      float v[kEpiCols];
+      __syncwarp();
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + c0, r0);
+        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + c0 + 32, r1);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = __uint_as_float(r[j]);
-        if (ep.bias) v[j] += (col0 + j < N) ? __ldg(ep.bias + col0 + j) : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r0[j]) + s_bias[c0 + j];
+          v[32 + j] = __uint_as_float(r1[j]) + s_bias[c0 + 32 + j];
+        }
       }
-      const int ncol = min(32, N - col0);   // N % 8 == 0
-      if (ep.mode == 0 || ep.mode == 1) {
-        __half* o = reinterpret_cast<__half*>(ep.out) + (size_t)row * ep.ldo + col0;
+      if (col0 >= N || rows_here <= 0) continue;       // warp-uniform
+      if (mode == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (j < ncol) {
-            __align__(16) __half h[8];
+        for (int j = 0; j < kEpiCols; ++j) v[j] = gelu_tanh(r16(v[j]));
+      } else if (mode == 6) {
+        // MultiHeadRMSNorm on the fp16-rounded Linear output, one head = 32 columns
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              float x = v[j + t];
-              if (ep.mode == 1) x = gelu_tanh(r16(x));
-              h[t] = __float2half_rn(x);
+        for (int hh = 0; hh < kEpiCols / 32; ++hh) {
+          const int hc = col0 + hh * 32;
+          if (hc < ep.norm_cols) {
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[hh * 32 + j] = r16(v[hh * 32 + j]); ss += v[hh * 32 + j] * v[hh * 32 + j]; }
+            const float inv = 5.656854249492381f / fmaxf(sqrtf(ss), 1e-12f);   // sqrt(32) / max(||x||, eps)
+            const int half_cols = ep.norm_cols >> 1;
+            const float* g = (hc < half_cols) ? ep.gamma_q + hc : ep.gamma_k + (hc - half_cols);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[hh * 32 + j] = v[hh * 32 + j] * inv * __ldg(g + j);
+          }
+        }
+      } else if (mode == 2 || mode == 3 || mode == 5) {
+#pragma unroll
+        for (int j = 0; j < kEpiCols; ++j) v[j] = r16(v[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kEpiCols; ++j) stg[lane * kStgLd + j] = v[j];
+      __syncwarp();
+      // ---- phase 2: lane owns columns (2*lane, 2*lane+1) of the chunk
+      const int cc = col0 + 2 * lane;
+      const bool col_ok = cc < N;                       // N % 8 == 0, so the pair is in or out together
+      if (mode == 0 || mode == 1 || mode == 6) {
+        __half* o = reinterpret_cast<__half*>(ep.out) + (size_t)row0 * ep.ldo + cc;
+        if (col_ok)
+#pragma unroll 8
+          for (int r = 0; r < rows_here; ++r)
+            *reinterpret_cast<__half2*>(o + (size_t)r * ep.ldo) =
+                __floats2half2_rn(stg[r * kStgLd + 2 * lane], stg[r * kStgLd + 2 * lane + 1]);
+      } else if (mode == 2) {
+        // fp32 residual read-modify-write; loads of 8 rows are issued before their stores so the
+        // DRAM latency is paid once per batch, not once per row
+        float* o = reinterpret_cast<float*>(ep.out) + (size_t)row0 * ep.ldo + cc;
+        if (col_ok) {
+          float g0 = 1.f, g1 = 1.f;
+          if (ep.gate && one_batch) {
+            const __half2 gg = *reinterpret_cast<const __half2*>(ep.gate + (size_t)b_first * ep.gate_stride + cc);
+            g0 = __low2float(gg); g1 = __high2float(gg);
+          }
+          for (int rb = 0; rb < rows_here; rb += 8) {
+            float2 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (rb + k < rows_here) x[k] = *reinterpret_cast<const float2*>(o + (size_t)(rb + k) * ep.ldo);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int r = rb + k;
+              if (r < rows_here) {
+                if (ep.gate && !one_batch) {
+                  const __half2 gg = *reinterpret_cast<const __half2*>(
+                      ep.gate + (size_t)((row0 + r) / ep.rows_per_batch) * ep.gate_stride + cc);
+                  g0 = __low2float(gg); g1 = __high2float(gg);
+                }
+                float h0 = stg[r * kStgLd + 2 * lane], h1 = stg[r * kStgLd + 2 * lane + 1];
+                if (ep.gate) { h0 = r16(h0 * g0); h1 = r16(h1 * g1); }
+                x[k].x += h0; x[k].y += h1;
+                *reinterpret_cast<float2*>(o + (size_t)r * ep.ldo) = x[k];
+              }
             }
-            *reinterpret_cast<uint4*>(o + j) = *reinterpret_cast<uint4*>(h);
           }
         }
-      } else if (ep.mode == 2) {
-        float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-        const __half* g = ep.gate ? ep.gate + (size_t)b * ep.gate_stride + col0 : nullptr;
+      } else if (mode == 3) {
+        __half* o = reinterpret_cast<__half*>(ep.out) + (size_t)row0 * ep.ldo + cc;
+        if (col_ok)
+          for (int rb = 0; rb < rows_here; rb += 8) {
+            __half2 old[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (j < ncol) {
-            float4 x = *reinterpret_cast<float4*>(o + j);
-            float h0 = r16(v[j]), h1 = r16(v[j + 1]), h2 = r16(v[j + 2]), h3 = r16(v[j + 3]);
-            if (g) {
-              h0 = r16(h0 * __half2float(g[j]));
-              h1 = r16(h1 * __half2float(g[j + 1]));
-              h2 = r16(h2 * __half2float(g[j + 2]));
-              h3 = r16(h3 * __half2float(g[j + 3]));
+            for (int k = 0; k < 8; ++k)
+              if (rb + k < rows_here) old[k] = *reinterpret_cast<const __half2*>(o + (size_t)(rb + k) * ep.ldo);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int r = rb + k;
+              if (r < rows_here)
+                *reinterpret_cast<__half2*>(o + (size_t)r * ep.ldo) =
+                    __floats2half2_rn(stg[r * kStgLd + 2 * lane] + __low2float(old[k]),
+                                      stg[r * kStgLd + 2 * lane + 1] + __high2float(old[k]));
             }
-            x.x += h0; x.y += h1; x.z += h2; x.w += h3;
-            *reinterpret_cast<float4*>(o + j) = x;
           }
-        }
-      } else if (ep.mode == 3) {
-        __half* o = reinterpret_cast<__half*>(ep.out) + (size_t)row * ep.ldo + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (j < ncol) {
-            uint4 old = *reinterpret_cast<uint4*>(o + j);
-            __half* oh = reinterpret_cast<__half*>(&old);
-            __align__(16) __half h[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) h[t] = __float2half_rn(r16(v[j + t]) + __half2float(oh[t]));
-            *reinterpret_cast<uint4*>(o + j) = *reinterpret_cast<uint4*>(h);
-          }
-        }
-      } else if (ep.mode == 4) {
-        float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (j < ncol) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else if (mode == 4) {
+        float* o = reinterpret_cast<float*>(ep.out) + (size_t)row0 * ep.ldo + cc;
+        if (col_ok)
+#pragma unroll 8
+          for (int r = 0; r < rows_here; ++r)
+            *reinterpret_cast<float2*>(o + (size_t)r * ep.ldo) =
+                make_float2(stg[r * kStgLd + 2 * lane], stg[r * kStgLd + 2 * lane + 1]);
       } else {
-        // mode 5: compact fp32 rows of ldo (<= N) fp16-rounded values, e.g. Linear(768 -> 14)
-        float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo;
+        // mode 5: compact fp32 rows of ldo (<= N) columns, e.g. Linear(768 -> 14)
+        float* o = reinterpret_cast<float*>(ep.out) + (size_t)row0 * ep.ldo;
+        for (int r = 0; r < rows_here; ++r)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < ep.ldo) o[col0 + j] = r16(v[j]);
+          for (int t = 0; t < 2; ++t)
+            if (cc + t < ep.ldo) o[(size_t)r * ep.ldo + cc + t] = stg[r * kStgLd + 2 * lane + t];
       }
     }
   }
@@ -211,12 +276,17 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mW, int M, int 
 
 using namespace gvf;
 
-extern "C" GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N,
-                                    int K, int epilogue, const float* bias, void* out, int ldo,
-                                    const void* gate, int gate_stride, int rows_per_batch,
-                                    void* stream) {
+static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue,
+                     const float* bias, void* out, int ldo, const void* gate, int gate_stride,
+                     int rows_per_batch, const float* gamma_q, const float* gamma_k, int norm_cols,
+                     void* stream) {
   if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return GVF_ERR_INVALID;
-  if ((N % 8) || (K % 8) || (lda % 8) || (ldw % 8) || epilogue < 0 || epilogue > 5) return GVF_ERR_INVALID;
+  if ((N % 8) || (K % 8) || (lda % 8) || (ldw % 8) || epilogue < 0 || epilogue > 6) return GVF_ERR_INVALID;
+  if (epilogue == 6 && (!gamma_q || !gamma_k || norm_cols <= 0 || (norm_cols % 64) || norm_cols > N))
+    return GVF_ERR_INVALID;
+  if ((epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6) && (ldo % 2)) return GVF_ERR_INVALID;
+  if ((epilogue == 2 || epilogue == 4) && (ldo % 2)) return GVF_ERR_INVALID;
+  if (gate && (gate_stride % 2)) return GVF_ERR_INVALID;
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
   if (epilogue == 2 && gate && rows_per_batch <= 0) return GVF_ERR_INVALID;
   const bool wide = (N % 128) == 0 && N >= 1024;   // BN = 128 everywhere for now; see DESIGN.md
@@ -232,5 +302,26 @@ extern "C" GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int l
   ep.mode = epilogue; ep.bias = bias; ep.out = out; ep.gate = (const __half*)gate;
   ep.gate_stride = gate_stride; ep.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   ep.ldo = ldo;
+  ep.gamma_q = gamma_q; ep.gamma_k = gamma_k; ep.norm_cols = norm_cols;
   return launch_gemm<BN, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
+}
+
+extern "C" GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N,
+                                    int K, int epilogue, const float* bias, void* out, int ldo,
+                                    const void* gate, int gate_stride, int rows_per_batch,
+                                    void* stream) {
+  if (epilogue == 6) return GVF_ERR_INVALID;
+  return gemm_impl(A, lda, W, ldw, M, N, K, epilogue, bias, out, ldo, gate, gate_stride, rows_per_batch,
+                   nullptr, nullptr, 0, stream);
+}
+
+// QKV projection with MultiHeadRMSNorm fused into the epilogue (reference
+// model/attention/modules.py:113-125): out fp16 [M,N]; columns [0, norm_cols) are split into
+// 32-wide heads, first half normalised with gamma_q [norm_cols/64, 32], second half with gamma_k.
+extern "C" GVF_API int gvf_gemm_qkv_rmsnorm_f16(const void* A, int lda, const void* W, int ldw, int M,
+                                                int N, int K, const float* bias, void* out, int ldo,
+                                                const float* gamma_q, const float* gamma_k,
+                                                int norm_cols, void* stream) {
+  return gemm_impl(A, lda, W, ldw, M, N, K, 6, bias, out, ldo, nullptr, 0, 0, gamma_q, gamma_k, norm_cols,
+                   stream);
 }

@@ -191,6 +191,14 @@ class DiTEngine:
             self._ws_key = key
         return self.X
 
+    def _qkv(self, A16, p, QKV):
+        """to_qkv + q/k MultiHeadRMSNorm (model/attention/modules.py:113-125)."""
+        if self.d == 32 and (2 * self.C) % 64 == 0:
+            ops.gemm_qkv_rmsnorm(A16, p["w_qkv"], p["b_qkv"], p["gq"], p["gk"], QKV)      # norm fused in the epilogue
+        else:
+            ops.gemm(A16, p["w_qkv"], p["b_qkv"], ops.EPI_F16, out=QKV)
+            ops.rmsnorm_heads_(QKV, self.H, self.d, self.C, p["gq"], p["gk"])
+
     def forward(self, x, t, kv_img, kv_static, pos):
         """x [Bx,T,N,Cin] fp32, t [Bx] fp32 (model time, 0..1000) on device;
         kv_img / kv_static / pos: per-entry lists (len Bx) from image_kv / static_kv / pos_embed.
@@ -216,16 +224,14 @@ class DiTEngine:
             # --- spatial self-attention (model/dit.py:246-250)
             sa = blk["spatial_self_attn"]
             ops.ln_mod(X, out=A16, shift=m(0), scale=m(1), mod_stride=R, rows_per_batch=TN)
-            ops.gemm(A16, sa["w_qkv"], sa["b_qkv"], ops.EPI_F16, out=QKV)
-            ops.rmsnorm_heads_(QKV, H, d, C, sa["gq"], sa["gk"])
+            self._qkv(A16, sa, QKV)
             ops.attention(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], scale, out=ao4)
             ops.gemm(AO, sa["w_out"], sa["b_out"], ops.EPI_RESID_F32, out=X, gate=m(2), gate_stride=R,
                      rows_per_batch=TN)
             # --- temporal self-attention (:254-260), strided view instead of transposes
             ta = blk["temporal_self_attn"]
             ops.ln_mod(X, out=A16, shift=m(6), scale=m(7), mod_stride=R, rows_per_batch=TN)
-            ops.gemm(A16, ta["w_qkv"], ta["b_qkv"], ops.EPI_F16, out=QKV)
-            ops.rmsnorm_heads_(QKV, H, d, C, ta["gq"], ta["gk"])
+            self._qkv(A16, ta, QKV)
             for b in range(Bx):
                 tv = QKV[b * TN:(b + 1) * TN].view(T, N, 3, H, d).permute(1, 0, 2, 3, 4)   # [N,T,3,H,d]
                 to = AO[b * TN:(b + 1) * TN].view(T, N, H, d).permute(1, 0, 2, 3)

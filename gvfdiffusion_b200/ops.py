@@ -41,6 +41,18 @@ def gemm(a, w, bias=None, epilogue=EPI_F16, out=None, gate=None, gate_stride=0, 
     return out
 
 
+def gemm_qkv_rmsnorm(a, w, bias, gamma_q, gamma_k, out):
+    """QKV Linear + per-head q/k RMS norm (head dim 32) in one kernel; out fp16 [M, 3C]."""
+    M, K = a.shape
+    N = w.shape[0]
+    norm_cols = 2 * gamma_q.numel()
+    assert gamma_q.shape[-1] == 32 and norm_cols <= N
+    st = _lib.lib().gvf_gemm_qkv_rmsnorm_f16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, ptr(bias), ptr(out),
+                                             out.stride(0), ptr(gamma_q), ptr(gamma_k), norm_cols, current_stream())
+    check(st, "gvf_gemm_qkv_rmsnorm_f16")
+    return out
+
+
 def attention(q, k, v, scale, out=None, q_shared=False, kv_shared=False):
     """q [Nb,Lq,H,D] (or [Lq,H,D] if q_shared), k/v [Nb,Lk,H,D] (or [Lk,H,D] if kv_shared): fp16
     views with contiguous last dim (any strides that are multiples of 8).  -> [Nb,Lq,H,D] fp16."""

@@ -146,6 +146,14 @@ GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, 
                          int epilogue, const float* bias, void* out, int ldo, const void* gate,
                          int gate_stride, int rows_per_batch, void* stream);
 
+/* Self-attention QKV projection with MultiHeadRMSNorm fused into the epilogue (reference
+ * model/attention/modules.py:113-125): out fp16 [M,N]; columns [0, norm_cols) are 32-wide heads,
+ * the first half normalised with gamma_q [norm_cols/64, 32], the second half with gamma_k;
+ * columns >= norm_cols (v) are stored as is. */
+GVF_API int gvf_gemm_qkv_rmsnorm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                                     const float* bias, void* out, int ldo, const float* gamma_q,
+                                     const float* gamma_k, int norm_cols, void* stream);
+
 /* y = fp16(x[M,K] W[N,K]^T + b) (+ add[m % add_rows, n], fp32) for K <= 32 on CUDA cores:
  * input_layer + APE (model/dit.py:457,470-472), static_cond_proj (:465), VAE proj
  * (model/autoencoder.py:585), gs_embedding (:389).  x fp32, W fp16, out fp32 or fp16. */

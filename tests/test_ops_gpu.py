@@ -207,3 +207,41 @@ def test_geglu_cast_dpm():
     _close(ops.dpm_update(xs, m0, m1, 0.9, -0.3, 1.2, 2, torch.empty_like(xs)),
            0.9 * xs + 0.3 * m0 + 0.5 * 0.3 * (1.2 * (m0 - m1)), 1e-5, "update2")
     _close(ops.dpm_update(xs, m0, None, 0.9, -0.3, 0.0, 1, torch.empty_like(xs)), 0.9 * xs + 0.3 * m0, 1e-5, "update1")
+
+
+def test_gemm_qkv_rmsnorm_fused():
+    from gvfdiffusion_b200 import ops
+    g = _g(41)
+    M, C, H, D = 640, 256, 8, 32
+    a = _rand((M, C), g).half()
+    w = _rand((3 * C, C), g, 0.05).half()
+    b = _rand((3 * C,), g, 0.1)
+    gq, gk = _rand((H, D), g) + 1, _rand((H, D), g) + 1
+    out = torch.empty((M, 3 * C), dtype=torch.float16, device=DEV)
+    ops.gemm_qkv_rmsnorm(a, w, b, gq, gk, out)
+    lin = (a.float() @ w.float().T + b).half().float().reshape(M, 3, H, D)
+    rq = F.normalize(lin[:, 0], dim=-1) * gq * D ** 0.5
+    rk = F.normalize(lin[:, 1], dim=-1) * gk * D ** 0.5
+    o = out.float().reshape(M, 3, H, D)
+    _close(o[:, 0], rq, 2e-3, "q")
+    _close(o[:, 1], rk, 2e-3, "k")
+    _close(o[:, 2], lin[:, 2], 1e-3, "v")
+
+
+def test_gemm_ragged_rows_and_multi_batch_gate():
+    from gvfdiffusion_b200 import ops
+    g = _g(43)
+    M, N, K, rpb = 200, 136, 72, 50          # tiles span several batches, ragged M / N / K
+    a = _rand((M, K), g).half()
+    w = _rand((N, K), g, 0.05).half()
+    b = _rand((N,), g, 0.1)
+    gate = _rand((4, N), g).half()
+    x = _rand((M, N), g)
+    lin = (a.float() @ w.float().T + b).half().float()
+    out = x.clone()
+    ops.gemm(a, w, b, ops.EPI_RESID_F32, out=out, gate=gate, gate_stride=N, rows_per_batch=rpb)
+    _close(out, x + (lin * gate.float().repeat_interleave(rpb, 0)).half().float(), 1e-3, "ragged gate")
+    o14 = torch.empty((M, 14), dtype=torch.float32, device=DEV)
+    w16 = torch.cat([w[:14], torch.zeros(2, K, dtype=torch.float16, device=DEV)])
+    ops.gemm(a, w16, torch.cat([b[:14], torch.zeros(2, device=DEV)]), ops.EPI_F32_COMPACT, out=o14)
+    _close(o14, lin[:, :14], 1e-3, "compact")
