@@ -31,6 +31,8 @@ _SIGS = {
     "gvf_raster_workspace_offset": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "gvf_raster_forward": (C.c_int, [C.POINTER(RasterParams), C.c_int, C.c_int, C.c_int,
                                      _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
+    "gvf_raster_backward": (C.c_int, [C.POINTER(RasterParams), C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
+                                      _P, _P, _P, C.c_size_t, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_gaussian_tensor": (C.c_int, [C.POINTER(RasterParams), C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_fps": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "gvf_attn_fwd_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

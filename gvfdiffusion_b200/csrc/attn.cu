@@ -359,10 +359,21 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __half* __restric
   if (lane >= L) return;
   float sc[32];
   float mx = -INFINITY;
-  for (int j = 0; j < L; ++j) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {                           // unrolled so sc[] stays in registers
+    if (j >= L) break;
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < D; ++i) acc += qv[i] * __half2float(sK[w][j][i]);
+    for (int i = 0; i < D / 8; ++i) {                      // one LDS.128 (broadcast) per 8 MACs
+      const uint4 kk = *reinterpret_cast<const uint4*>(&sK[w][j][i * 8]);
+      const __half2* k2 = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 kf = __half22float2(k2[t]);
+        acc = fmaf(qv[i * 8 + 2 * t], kf.x, acc);
+        acc = fmaf(qv[i * 8 + 2 * t + 1], kf.y, acc);
+      }
+    }
     sc[j] = acc * scale;
     mx = fmaxf(mx, sc[j]);
   }
@@ -370,12 +381,23 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __half* __restric
   float ov[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) ov[i] = 0.f;
-  for (int j = 0; j < L; ++j) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j >= L) break;
     const float p = __expf(sc[j] - mx);
     l += p;
     const float ph = __half2float(__float2half_rn(p));
 #pragma unroll
-    for (int i = 0; i < D; ++i) ov[i] += ph * __half2float(sV[w][j][i]);
+    for (int i = 0; i < D / 8; ++i) {
+      const uint4 vv = *reinterpret_cast<const uint4*>(&sV[w][j][i * 8]);
+      const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 vf = __half22float2(v2[t]);
+        ov[i * 8 + 2 * t] = fmaf(ph, vf.x, ov[i * 8 + 2 * t]);
+        ov[i * 8 + 2 * t + 1] = fmaf(ph, vf.y, ov[i * 8 + 2 * t + 1]);
+      }
+    }
   }
   const float inv = 1.0f / l;
   __half* ob = o + b * osb + (long long)lane * osl + (long long)h * osh;

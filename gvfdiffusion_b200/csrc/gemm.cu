@@ -186,7 +186,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             *reinterpret_cast<__half2*>(o + (size_t)r * ep.ldo) =
                 __floats2half2_rn(stg[r * kStgLd + 2 * lane], stg[r * kStgLd + 2 * lane + 1]);
       } else if (mode == 2) {
-        // fp32 residual read-modify-write; loads of 8 rows are issued before their stores so the
+        // fp32 residual read-modify-write; loads of 16 rows are issued before their stores so the
         // DRAM latency is paid once per batch, not once per row
         float* o = reinterpret_cast<float*>(ep.out) + (size_t)row0 * ep.ldo + cc;
         if (col_ok) {
@@ -195,13 +195,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             const __half2 gg = *reinterpret_cast<const __half2*>(ep.gate + (size_t)b_first * ep.gate_stride + cc);
             g0 = __low2float(gg); g1 = __high2float(gg);
           }
-          for (int rb = 0; rb < rows_here; rb += 8) {
-            float2 x[8];
+          for (int rb = 0; rb < rows_here; rb += 16) {
+            float2 x[16];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < 16; ++k)
               if (rb + k < rows_here) x[k] = *reinterpret_cast<const float2*>(o + (size_t)(rb + k) * ep.ldo);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 16; ++k) {
               const int r = rb + k;
               if (r < rows_here) {
                 if (ep.gate && !one_batch) {

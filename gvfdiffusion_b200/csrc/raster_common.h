@@ -47,6 +47,7 @@ inline RasterLayout raster_layout(int F, int P, int H, int W, int64_t cap) {
   sz[GVF_RB_N_CONTRIB] = (size_t)F * HW * sizeof(uint32_t);
   sz[GVF_RB_STATUS] = 4 * sizeof(uint32_t);
   sz[GVF_RB_SCAN_TMP] = (chunks + 2) * sizeof(uint32_t);
+  sz[GVF_RB_DSPLAT] = FP * 12 * sizeof(float);
   RasterLayout L;
   size_t o = 0;
   for (int i = 0; i < GVF_RB_COUNT_; ++i) {

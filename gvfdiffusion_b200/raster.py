@@ -14,7 +14,7 @@ from . import _lib
 
 TILE = 16
 RB = {"splat": 0, "rect": 1, "tile_count": 2, "tile_start": 3, "keys": 4, "point_list": 5,
-      "final_T": 6, "n_contrib": 7, "status": 8, "scan_tmp": 9}
+      "final_T": 6, "n_contrib": 7, "status": 8, "scan_tmp": 9, "dsplat": 10}
 
 
 def intrinsics_to_projection(intrinsics, near, far):
@@ -125,6 +125,48 @@ class Rasterizer:
             if not overflow:
                 return rgba, radii
             self._ensure(F, P, H, W, cap=int(R * 1.25) + 1024)
+
+
+    def backward(self, prm, arrays, delta, cams, grad_rgba, activated=False, subpixel_offset=None,
+                 want_delta_grad=True, want_means2D=False):
+        """Backward of the last forward() with the same arguments.  Returns (five gradients of
+        `arrays`, grad of delta or None, grad of means2D or None)."""
+        L = _lib.lib()
+        F, P, H, W = self._key
+        dev = self.device
+        g = grad_rgba.detach().to(dev, torch.float32).contiguous()
+        lead = (F, P) if activated else (P,)
+        outs = [torch.empty(lead + (n,), dtype=torch.float32, device=dev) for n in (3, 3, 3, 4)]
+        outs.append(torch.empty(lead, dtype=torch.float32, device=dev))
+        gdelta = torch.empty((F, P, 14), dtype=torch.float32, device=dev) if (want_delta_grad and not activated) else None
+        gm2 = torch.empty((F, P, 2), dtype=torch.float32, device=dev) if want_means2D else None
+        st = L.gvf_raster_backward(C.byref(prm), F, P, int(activated), *[_lib.ptr(a) for a in arrays],
+                                   _lib.ptr(delta), _lib.ptr(cams), _lib.ptr(subpixel_offset), _lib.ptr(g),
+                                   _lib.ptr(self._ws), self._ws.numel(), self.cap, *[_lib.ptr(o) for o in outs],
+                                   _lib.ptr(gdelta), _lib.ptr(gm2), _lib.current_stream())
+        _lib.check(st, "gvf_raster_backward")
+        return outs, gdelta, gm2
+
+
+class RasterizeFrames(torch.autograd.Function):
+    """autograd node: (raw canonical tensors, delta) -> RGBA for F frames (train_vae.py:313-334)."""
+
+    @staticmethod
+    def forward(ctx, rz, prm, cams, xyz, dc, scaling, rotation, opacity, delta):
+        arrays = tuple(t.detach().contiguous() for t in (xyz, dc, scaling, rotation, opacity))
+        d = None if delta is None else delta.detach().contiguous()
+        rgba, radii = rz.forward(prm, arrays, d, cams)
+        ctx.rz, ctx.prm, ctx.cams, ctx.arrays, ctx.delta = rz, prm, cams, arrays, d
+        ctx.shapes = [t.shape for t in (xyz, dc, scaling, rotation, opacity)]
+        ctx.mark_non_differentiable(radii)
+        return rgba, radii
+
+    @staticmethod
+    def backward(ctx, g_rgba, _g_radii):
+        outs, gdelta, _ = ctx.rz.backward(ctx.prm, ctx.arrays, ctx.delta, ctx.cams, g_rgba,
+                                          want_delta_grad=ctx.delta is not None)
+        outs = [o.reshape(s) for o, s in zip(outs, ctx.shapes)]
+        return (None, None, None, *outs, gdelta)
 
 
 def canon_arrays(canon, device):

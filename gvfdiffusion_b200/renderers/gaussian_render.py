@@ -35,8 +35,9 @@ class GaussianRenderer:
             return (1.0, 1.0, 1.0) if np.random.rand() < 0.5 else (0.0, 0.0, 0.0)
         return tuple(float(c) for c in self.rendering_options["bg_color"])
 
-    def render_frames(self, gausssian, extrinsics, intrinsics, delta_pc=None):
-        """extrinsics (F,4,4), intrinsics (3,3)|(F,3,3), delta_pc (F,P,14)|None -> rgba (F,4,H,W), radii (F,P)."""
+    def render_frames(self, gausssian, extrinsics, intrinsics, delta_pc=None, detach_static=False):
+        """extrinsics (F,4,4), intrinsics (3,3)|(F,3,3), delta_pc (F,P,14)|None -> rgba (F,4,H,W), radii (F,P).
+        Differentiable w.r.t. delta_pc and (unless detach_static) the GaussianModel's raw tensors."""
         if not self.pipe.use_mip_gaussian:
             raise NotImplementedError("only the mip-Gaussian rasteriser (pipe.use_mip_gaussian=True) is on the "
                                       "inference path; the diff_gauss variant serves the alignment pre-step")
@@ -54,8 +55,19 @@ class GaussianRenderer:
                             self.pipe.scale_modifier, bg)
         if self._rz is None:
             self._rz = R.Rasterizer(dev)
+        raw = gausssian.raw()
+        needs_grad = torch.is_grad_enabled() and (
+            (delta_pc is not None and delta_pc.requires_grad) or
+            (not detach_static and any(t.requires_grad for t in raw.values())))
+        if needs_grad:
+            P = raw["_xyz"].shape[0]
+            t = {k: (v.detach() if detach_static else v) for k, v in raw.items()}
+            return R.RasterizeFrames.apply(self._rz, prm, cams.to(dev), t["_xyz"].reshape(P, 3).float(),
+                                           t["_features_dc"].reshape(P, 3).float(), t["_scaling"].reshape(P, 3).float(),
+                                           t["_rotation"].reshape(P, 4).float(), t["_opacity"].reshape(P).float(),
+                                           None if delta_pc is None else delta_pc.float())
         d = None if delta_pc is None else delta_pc.detach().to(dev, torch.float32).contiguous()
-        return self._rz.forward(prm, R.canon_arrays(gausssian.raw(), dev), d, cams.to(dev))
+        return self._rz.forward(prm, R.canon_arrays(raw, dev), d, cams.to(dev))
 
     def render(self, gausssian, extrinsics, intrinsics, delta_pc=None, detach_static=False, colors_overwrite=None,
                patch_mask=None):
@@ -64,5 +76,5 @@ class GaussianRenderer:
         d = None if delta_pc is None else delta_pc[None]
         if d is not None and d.shape[-1] == 10:        # xyz/scale/rot only (gaussian_render.py:158)
             d = torch.cat([d, torch.zeros(d.shape[:-1] + (4,), device=d.device, dtype=d.dtype)], -1)
-        rgba, radii = self.render_frames(gausssian, extrinsics[None], intrinsics, d)
+        rgba, radii = self.render_frames(gausssian, extrinsics[None], intrinsics, d, detach_static=detach_static)
         return edict({"rgb": rgba[0, :3], "alpha": rgba[0, 3]})

@@ -72,6 +72,7 @@ enum gvf_raster_buf {
   GVF_RB_N_CONTRIB,      /* uint32[F*H*W] */
   GVF_RB_STATUS,         /* uint32[4]: num_rendered, overflow flag, max tile length, 0 */
   GVF_RB_SCAN_TMP,       /* uint32[...]   */
+  GVF_RB_DSPLAT,         /* float[F*P*12] backward accumulator: d(px,py,conic a,b,c,opacity',r,g,b) */
   GVF_RB_COUNT_
 };
 
@@ -101,6 +102,22 @@ GVF_API int gvf_raster_forward(const gvf_raster_params* prm, int F, int P, int a
                        int32_t* radii, void* workspace, size_t workspace_bytes, int64_t cap,
                        void* stream);
 
+
+/* Backward -- replaces GaussianRasterizer.backward (reached through autograd from reference
+ * train_vae.py:313-352) fused with the backward of GaussianModel.get_*_with_delta.  Must follow a
+ * gvf_raster_forward call with the same arguments and workspace (it reads the splat records, sorted
+ * lists, final_T and n_contrib left there).  dL_drgba: [F,4,H,W].
+ *  activated == 0: g_xyz[P,3], g_dc[P,3], g_scaling[P,3], g_rotation[P,4], g_opacity[P] receive the
+ *     gradients of the RAW canonical tensors summed over frames; g_delta [F,P,14] (or NULL) those of delta.
+ *  activated == 1: the five outputs are per-frame gradients of the activated inputs ([F,P,..]).
+ *  g_means2D: [F,P,2] or NULL, screen-space gradient in upstream's convention (d/d ndc). */
+GVF_API int gvf_raster_backward(const gvf_raster_params* prm, int F, int P, int activated,
+                                const float* xyz, const float* dc, const float* scaling,
+                                const float* rotation, const float* opacity, const float* delta,
+                                const float* cams, const float* subpixel_offset, const float* dL_drgba,
+                                void* workspace, size_t workspace_bytes, int64_t cap, float* g_xyz,
+                                float* g_dc, float* g_scaling, float* g_rotation, float* g_opacity,
+                                float* g_delta, float* g_means2D, void* stream);
 
 /* get_gaussian_tensor (reference train_vae.py:466-472): raw canonical GaussianModel tensors ->
  * activated [P,14] = [xyz3 | rgb3 | opacity1 | scale3 | rot4] (decoder queries, static_latent). */
