@@ -35,6 +35,8 @@ _SIGS = {
                                       _P, _P, _P, C.c_size_t, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_gaussian_tensor": (C.c_int, [C.POINTER(RasterParams), C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_fps": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "gvf_vox2seq_encode": (C.c_int, [_P, C.c_longlong, C.POINTER(C.c_int), C.c_int, _P, _P]),
+    "gvf_vox2seq_decode": (C.c_int, [_P, C.c_longlong, C.POINTER(C.c_int), C.c_int, _P, _P]),
     "gvf_attn_fwd_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                    C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_float, _P]),
@@ -42,6 +44,7 @@ _SIGS = {
                                _P, C.c_int, C.c_int, _P]),
     "gvf_gemm_qkv_rmsnorm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                            _P, _P, C.c_int, _P]),
+    "gvf_gemm_set_variant": (None, [C.c_int]),
     "gvf_small_linear": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "gvf_ln_mod_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gvf_rmsnorm_heads_f16": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

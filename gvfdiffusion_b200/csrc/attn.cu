@@ -410,6 +410,99 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __half* __restric
   }
 }
 
+// Same computation when the H heads of a token are contiguous (q_strides[2] == D): one CTA per batch
+// entry stages the [L x H*D] rows of q, k, v with fully coalesced 16 B loads (a row is H*D*2 = 1 KB
+// contiguous even in the strided temporal view), one warp per head, lane = query; the output goes
+// back through shared memory so stores are row-contiguous as well.
+template <int D>
+__global__ void __launch_bounds__(512) attn_small_rows_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                              const __half* __restrict__ v, __half* __restrict__ o,
+                                                              int H, int L, long long sb, long long sl,
+                                                              long long osb, long long osl, float scale) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const int HD = H * D;
+  __half* sQ = reinterpret_cast<__half*>(sm_raw);
+  __half* sK = sQ + (size_t)L * HD;
+  __half* sV = sK + (size_t)L * HD;
+  const long long nb = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int vec_per_row = HD / 8;
+  for (int idx = tid; idx < 3 * L * vec_per_row; idx += nthr) {
+    const int which = idx / (L * vec_per_row), rem = idx - which * L * vec_per_row;
+    const int l = rem / vec_per_row, c = (rem - l * vec_per_row) * 8;
+    const __half* src = (which == 0 ? q : which == 1 ? k : v) + nb * sb + (long long)l * sl + c;
+    *reinterpret_cast<uint4*>((which == 0 ? sQ : which == 1 ? sK : sV) + (size_t)l * HD + c) =
+        *reinterpret_cast<const uint4*>(src);
+  }
+  __syncthreads();
+  const int h = tid >> 5, lane = tid & 31;
+  if (h < H && lane < L) {
+    float qv[D];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      const uint4 t = *reinterpret_cast<const uint4*>(sQ + (size_t)lane * HD + h * D + i * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const float2 f = __half22float2(h2[u]); qv[i * 8 + 2 * u] = f.x; qv[i * 8 + 2 * u + 1] = f.y; }
+    }
+    float sc[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j >= L) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        const uint4 kk = *reinterpret_cast<const uint4*>(sK + (size_t)j * HD + h * D + i * 8);
+        const __half2* k2 = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 kf = __half22float2(k2[u]);
+          acc = fmaf(qv[i * 8 + 2 * u], kf.x, acc);
+          acc = fmaf(qv[i * 8 + 2 * u + 1], kf.y, acc);
+        }
+      }
+      sc[j] = acc * scale;
+      mx = fmaxf(mx, sc[j]);
+    }
+    float l = 0.f, ov[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) ov[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j >= L) break;
+      const float p = __expf(sc[j] - mx);
+      l += p;
+      const float ph = __half2float(__float2half_rn(p));
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(sV + (size_t)j * HD + h * D + i * 8);
+        const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 vf = __half22float2(v2[u]);
+          ov[i * 8 + 2 * u] = fmaf(ph, vf.x, ov[i * 8 + 2 * u]);
+          ov[i * 8 + 2 * u + 1] = fmaf(ph, vf.y, ov[i * 8 + 2 * u + 1]);
+        }
+      }
+    }
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int i = 0; i < D; i += 8) {                     // park the output row in this thread's own q slot
+      __align__(16) __half hh[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) hh[u] = __float2half_rn(ov[i + u] * inv);
+      *reinterpret_cast<uint4*>(sQ + (size_t)lane * HD + h * D + i) = *reinterpret_cast<uint4*>(hh);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < L * vec_per_row; idx += nthr) {
+    const int l = idx / vec_per_row, c = (idx - l * vec_per_row) * 8;
+    *reinterpret_cast<uint4*>(o + nb * osb + (long long)l * osl + c) =
+        *reinterpret_cast<const uint4*>(sQ + (size_t)l * HD + c);
+  }
+}
+
 template <int D>
 static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                        int Nb, cudaStream_t st) {
@@ -429,6 +522,8 @@ static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
 
 using namespace gvf;
 
+static int g_small_rows = 0;   // row-staged temporal variant: measured slower than the warp-per-(batch,head) one
+
 // q [Nb_q, Lq, H, D], k/v [Nb_kv, Lk, H, D] fp16 with element strides (batch, seq, head);
 // innermost dim contiguous.  Nb_q / Nb_kv may be 1 (tensor shared by all Nb batches).
 extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void* v, void* o, int Nb, int Lq,
@@ -447,6 +542,20 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   if (D == 32 && Lq <= 32 && Lk == Lq && !q_shared && !kv_shared && q_strides[0] == k_strides[0] &&
       q_strides[1] == k_strides[1] && q_strides[2] == k_strides[2] && q_strides[0] == v_strides[0] &&
       q_strides[1] == v_strides[1] && q_strides[2] == v_strides[2]) {
+    if (g_small_rows && q_strides[2] == D && o_strides[2] == D && H <= 16) {
+      // heads contiguous: row-staged variant (coalesced even for the strided temporal view)
+      const int smem = 3 * Lq * H * D * 2;
+      static bool configured = false;
+      if (!configured) {
+        if (cudaFuncSetAttribute(attn_small_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 3 * 32 * 16 * 32 * 2) != cudaSuccess) return GVF_ERR_CUDA;
+        configured = true;
+      }
+      attn_small_rows_kernel<32><<<Nb, 512, smem, st>>>((const __half*)q, (const __half*)k, (const __half*)v,
+                                                       (__half*)o, H, Lq, q_strides[0], q_strides[1],
+                                                       o_strides[0], o_strides[1], scale);
+      return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+    }
     const long long nbh = (long long)Nb * H;
     const unsigned blocks = (unsigned)((nbh + 7) / 8);
     attn_small_kernel<32><<<blocks, 256, 0, st>>>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o,

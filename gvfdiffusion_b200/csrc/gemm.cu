@@ -48,86 +48,18 @@ __device__ __forceinline__ float r16(float x) { return __half2float(__float2half
 constexpr int kEpiCols = 64;                 // columns per epilogue chunk
 constexpr int kStgLd = kEpiCols + 1;         // padded row of the per-warp staging tile (floats)
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 2)
-gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-            int M, int N, int K, GemmEpi ep) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[BN];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = BN * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
-  static_assert(4 * 32 * kStgLd * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline smem");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-  const int kblocks = (K + kBK - 1) / kBK;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(&accum_bar, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&mapA);
-    tma_prefetch_desc(&mapW);
-  }
-  if (warp == 2) {
-    tmem_alloc(&tmem_base_s, BN);
-    tmem_relinquish();
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {   // bias of this tile's columns -> smem (epilogue warps)
-    const int c = tile_n * BN + (threadIdx.x - 64);
-    s_bias[threadIdx.x - 64] = (ep.bias && c < N) ? __ldg(ep.bias + c) : 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        uint8_t* st = smem + s * STAGE_BYTES;
-        tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
-        tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kBM, BN, 0, 0);
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), w0 = a0 + A_BYTES;
-#pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(a0 + k * 32, 16, 1024, SWZ_128B);
-          const uint64_t wd = make_smem_desc(w0 + k * 32, 16, 1024, SWZ_128B);
-          mma_ss(tmem, ad, wd, idesc, (kb | k) != 0);
-        }
-        tc_commit(&empty_bar[s]);
-      }
-      tc_commit(&accum_bar);
-    }
-  } else {
+// Epilogue of one 128 x BN accumulator tile, executed by the four epilogue warps (q = warp % 4 owns
+// TMEM lanes 32q..32q+31).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const uint32_t tmem, float* stg,
+                                              const float* s_bias, const int q, const int lane,
+                                              const int tile_m, const int tile_n, const int M, const int N) {
     // ---------------------------------------------------------------- epilogue (warps 2..5)
     // Phase 1 (thread = row): tcgen05.ld 64 columns, bias + row-wise math (GELU / fp16 rounding /
     // per-head RMS norm), park the values in a per-warp staging tile (the pipeline smem is free
     // once accum_bar fires).  Phase 2 (lane = column pair): walk the 32 rows so that every global
     // access of the warp is one contiguous 128 B (fp16) / 256 B (fp32) row segment.
-    const int q = warp & 3;
     const int row0 = tile_m * kBM + q * 32;
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem) + q * 32 * kStgLd;
     const int mode = ep.mode;
     const int rows_here = min(32, M - row0);
     const int b_first = row0 / ep.rows_per_batch;
@@ -250,10 +182,205 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (cc + t < ep.ldo) o[(size_t)r * ep.ldo + cc + t] = stg[r * kStgLd + 2 * lane + t];
       }
     }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 2)
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+            int M, int N, int K, GemmEpi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[BN];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = BN * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  static_assert(4 * 32 * kStgLd * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline smem");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  const int kblocks = (K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_s, BN);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {   // bias of this tile's columns -> smem (epilogue warps)
+    const int c = tile_n * BN + (threadIdx.x - 64);
+    s_bias[threadIdx.x - 64] = (ep.bias && c < N) ? __ldg(ep.bias + c) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+        tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM, BN, 0, 0);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), w0 = a0 + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t ad = make_smem_desc(a0 + k * 32, 16, 1024, SWZ_128B);
+          const uint64_t wd = make_smem_desc(w0 + k * 32, 16, 1024, SWZ_128B);
+          mma_ss(tmem, ad, wd, idesc, (kb | k) != 0);
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(&accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    epilogue_tile<BN>(ep, tmem, reinterpret_cast<float*>(smem) + q * 32 * kStgLd, s_bias, q, lane, tile_m, tile_n, M, N);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, BN);
+}
+
+// ---------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks the output tiles (n fastest, so CTAs running together
+// share A rows in L2); the accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of
+// tile i overlaps the TMA / MMA main loop of tile i+1.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                       int M, int N, int K, GemmEpi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[BN];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = BN * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (K + kBK - 1) / kBK;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + kBM - 1) / kBM;
+  const int num_tiles = tiles_n * tiles_m;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_s, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+          tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM, BN, 0, 0);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tempty_bar[acc], ((lt >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), w0 = a0 + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            mma_ss(tmem + acc * BN, make_smem_desc(a0 + k * 32, 16, 1024, SWZ_128B),
+                   make_smem_desc(w0 + k * 32, 16, 1024, SWZ_128B), idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;                             // 0..127 among the epilogue threads
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+      const int acc = lt & 1;
+      asm volatile("bar.sync 1, 128;");                          // previous tile's s_bias readers are done
+      for (int c = et; c < BN; c += 128) {
+        const int col = tile_n * BN + c;
+        s_bias[c] = (ep.bias && col < N) ? __ldg(ep.bias + col) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;");
+      mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      epilogue_tile<BN>(ep, tmem + acc * BN, stg_base + q * 32 * kStgLd, s_bias, q, lane, tile_m, tile_n, M, N);
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 2 * BN);
+}
+
+template <int BN, int STAGES>
+static int launch_gemm_persistent(const CUtensorMap& mA, const CUtensorMap& mW, int M, int N, int K,
+                                  const GemmEpi& ep, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 4 * 32 * kStgLd * 4 + 1024;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM) != cudaSuccess)
+      return GVF_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int tiles = ((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_persistent_kernel<BN, STAGES><<<grid, 192, SMEM, st>>>(mA, mW, M, N, K, ep);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
 template <int BN, int STAGES>
@@ -276,6 +403,8 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mW, int M, int 
 
 using namespace gvf;
 
+static int g_gemm_variant = -1;
+
 static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue,
                      const float* bias, void* out, int ldo, const void* gate, int gate_stride,
                      int rows_per_batch, const float* gamma_q, const float* gamma_k, int norm_cols,
@@ -289,13 +418,20 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   if (gate && (gate_stride % 2)) return GVF_ERR_INVALID;
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
   if (epilogue == 2 && gate && rows_per_batch <= 0) return GVF_ERR_INVALID;
-  const bool wide = (N % 128) == 0 && N >= 1024;   // BN = 128 everywhere for now; see DESIGN.md
-  (void)wide;
-  constexpr int BN = 128;
+  // variant: 0 = one tile per CTA (v1), 1 = persistent 128x128, 2 = persistent 128x256
+  int variant = g_gemm_variant;
+  if (variant < 0) {
+    // measured on B200 (tools/gemm_bench.py, profiles/): 128x256 persistent tiles win once there are at
+    // least two full waves of them and the main loop is long (K >= 768: the VAE shapes) or N = 3C (qkv);
+    // the short-K DiT GEMMs are latency-bound and do best with two independent CTAs per SM
+    const long long tiles256 = (long long)((M + kBM - 1) / kBM) * ((N + 255) / 256);
+    variant = (N % 256 == 0 && tiles256 >= 296 && (K >= 768 || N % 768 == 0)) ? 2 : 0;
+  }
+  const int BN = (variant == 2) ? 256 : 128;
   CUtensorMap mA, mW;
   const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {1, (uint64_t)lda};
   const uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}, sW[2] = {1, (uint64_t)ldw};
-  const uint32_t bA[2] = {kBK, kBM}, bW[2] = {kBK, BN};
+  const uint32_t bA[2] = {kBK, kBM}, bW[2] = {kBK, (uint32_t)BN};
   if (!make_tmap_f16(&mA, A, 2, dA, sA, bA, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
   if (!make_tmap_f16(&mW, W, 2, dW, sW, bW, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
   GemmEpi ep;
@@ -303,8 +439,13 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   ep.gate_stride = gate_stride; ep.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   ep.ldo = ldo;
   ep.gamma_q = gamma_q; ep.gamma_k = gamma_k; ep.norm_cols = norm_cols;
-  return launch_gemm<BN, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
+  if (variant == 2) return launch_gemm_persistent<256, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
+  if (variant == 1) return launch_gemm_persistent<128, 4>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
+  return launch_gemm<128, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
 }
+
+// tuning hook for the benchmarks: -1 automatic, 0 v1 (one tile per CTA), 1 persistent 128x128, 2 persistent 128x256
+extern "C" GVF_API void gvf_gemm_set_variant(int v) { g_gemm_variant = v; }
 
 extern "C" GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N,
                                     int K, int epilogue, const float* bias, void* out, int ldo,

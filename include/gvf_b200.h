@@ -163,6 +163,10 @@ GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, 
                          int epilogue, const float* bias, void* out, int ldo, const void* gate,
                          int gate_stride, int rows_per_batch, void* stream);
 
+/* Benchmark tuning hook: tile scheduling variant of gvf_gemm_f16 (-1 automatic, 0 one 128x128 tile per
+ * CTA, 1 persistent 128x128, 2 persistent 128x256 with a double-buffered TMEM accumulator). */
+GVF_API void gvf_gemm_set_variant(int v);
+
 /* Self-attention QKV projection with MultiHeadRMSNorm fused into the epilogue (reference
  * model/attention/modules.py:113-125): out fp16 [M,N]; columns [0, norm_cols) are 32-wide heads,
  * the first half normalised with gamma_q [norm_cols/64, 32], the second half with gamma_k;
@@ -230,6 +234,18 @@ GVF_API int gvf_dpm_update(const float* x, const float* m0, const float* m1, lon
  * latent de-normalisation, inference_dpm_latent.py:250 */
 GVF_API int gvf_affine_lastdim(const float* x, long long n, int C, const float* a, const float* b, float as,
                                float bs, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 6. vox2seq -- replaces the reference's first-party extension
+ *    model/sparse_voxel_diffusion/vox2seq/src/{api,z_order,hilbert}.cu (z_order_encode/decode,
+ *    hilbert_encode/decode; called from sparse/attention/serialized_attn.py:67-74).
+ *    coords int32 [N,3], codes int32 [N] (10 bits per axis); permute = axis order fed to the curve
+ *    (vox2seq/__init__.py:17-19); hilbert 0 = Morton / z-order, 1 = Hilbert.
+ * ---------------------------------------------------------------------------------- */
+GVF_API int gvf_vox2seq_encode(const int32_t* coords, long long N, const int* permute, int hilbert,
+                               int32_t* codes, void* stream);
+GVF_API int gvf_vox2seq_decode(const int32_t* codes, long long N, const int* permute, int hilbert,
+                               int32_t* coords, void* stream);
 
 #ifdef __cplusplus
 }

@@ -245,3 +245,24 @@ def test_gemm_ragged_rows_and_multi_batch_gate():
     w16 = torch.cat([w[:14], torch.zeros(2, K, dtype=torch.float16, device=DEV)])
     ops.gemm(a, w16, torch.cat([b[:14], torch.zeros(2, device=DEV)]), ops.EPI_F32_COMPACT, out=o14)
     _close(o14, lin[:, :14], 1e-3, "compact")
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_gemm_scheduling_variants(variant):
+    from gvfdiffusion_b200 import _lib, ops
+    L = _lib.lib()
+    g = _g(100 + variant)
+    try:
+        L.gvf_gemm_set_variant(variant)
+        for (M, N, K) in [(12288, 512, 512), (1000, 1536, 512), (300, 264, 136), (12288, 2048, 512)]:
+            a = _rand((M, K), g).half()
+            w = _rand((N, K), g, 0.05).half()
+            b = _rand((N,), g, 0.1)
+            ref = a.float() @ w.float().T + b
+            _close(ops.gemm(a, w, b, ops.EPI_F16), ref, 2e-3, f"variant {variant} {M}x{N}x{K}")
+            x = _rand((M, N), g)
+            out = x.clone()
+            ops.gemm(a, w, b, ops.EPI_RESID_F32, out=out)
+            _close(out, x + ref.half().float(), 1e-3, f"variant {variant} resid {M}x{N}x{K}")
+    finally:
+        L.gvf_gemm_set_variant(-1)
