@@ -44,6 +44,8 @@ _SIGS = {
                                _P, C.c_int, C.c_int, _P]),
     "gvf_gemm_qkv_rmsnorm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                            _P, _P, C.c_int, _P]),
+    "gvf_attn_set_debug": (None, [C.c_int]),
+    "gvf_attn_set_trace": (None, [_P]),
     "gvf_gemm_set_variant": (None, [C.c_int]),
     "gvf_small_linear": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "gvf_ln_mod_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, _P]),

@@ -12,10 +12,11 @@
 //   warp 0      TMA producer: Q tiles once, then K/V tiles [128 x d] through a 4-stage
 //               mbarrier ring (SWIZZLE_64B for d=32, SWIZZLE_128B for d=64)
 //   warps 1,2   single-thread tcgen05.mma issuers, one per query tile:
-//                 S = Q K^T   (SS: A,B K-major from smem, M=128 N=128 K=d)   -> TMEM [128 cols]
-//                 O' = P V    (TS: A = P from TMEM, B = V tile MN-major, M=128 N=d K=128)
-//               S(j+1) is issued as soon as the softmax warps have pulled S(j) into registers
-//               (s_free), so the next scores are ready before the current exponentials finish
+//                 S = Q K^T   (SS: A,B K-major from smem, M=128 N=64 K=d)  -> TMEM, 2 buffers
+//                 O' = P V    (TS: A = P from TMEM, B = V rows MN-major, M=128 N=d K=64)
+//               scores are computed two 64-column blocks ahead of the softmax (double-buffered S):
+//               the MMA -> commit -> mbarrier -> tcgen05.ld hand-off latency (~1.5k cycles, measured:
+//               the loop ran at 85 % of its time with all softmax math removed) is off the critical path
 //   warps 4-7   softmax of tile A, warps 8-11 softmax of tile B: thread = one query row
 //               (TMEM lane); tcgen05.ld S -> running max / exp2 / row sum in registers ->
 //               P (fp16 pairs) to its own TMEM columns with tcgen05.st; the per-tile partial
@@ -45,9 +46,11 @@ struct AttnArgs {
   int Lq, Lk, H;
   int q_batch_mul, kv_batch_mul;                  // 0: tensor shared across the batch
   float scale_log2e;
+  long long* trace;   // optional clock64 trace of CTA (0,0,0) (tools/attn_experiments.py)
+  int dbg;   // timing experiments only (tools/attn_experiments.py): 1 no exp2, 2 no O' fold, 4 no P store, 8 no max
 };
 
-template <int D>
+template <int D, int BLK, int NSBUF>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
@@ -56,12 +59,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   constexpr uint64_t SWZ = (D == 32) ? SWZ_64B : SWZ_128B;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int S = kAttnStages;
-  // TMEM columns: S (fp32 scores) and P (fp16 probabilities, 2 per column) of both query tiles, O'
-  constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 384 + D;
-  constexpr bool kSinglePass = (D == 32);          // whole score row in registers -> S released early
+  // BLK = key/value columns per softmax block (a whole 128-row TMA tile at d=32, half of one at d=64
+  // where the 64 accumulator registers leave no room for a 128-wide score row), NSBUF score buffers.
+  // TMEM columns per query tile: NSBUF x S (fp32), P (fp16 pairs) and the partial product O'
+  constexpr int BPT = 128 / BLK;                   // blocks per TMA tile
+  constexpr uint32_t TM_STRIDE = NSBUF * BLK + BLK / 2 + D;  // 224 for (32,128,1) and (64,64,2): 2 tiles <= 512
+  constexpr uint32_t TM_P = NSBUF * BLK, TM_O = NSBUF * BLK + BLK / 2;
+  static_assert(2 * TM_STRIDE <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t q_full, kv_full[S], kv_empty[S], s_full[2], s_free[2], p_full[2], o_full[2];
+  __shared__ uint64_t q_full, kv_full[S], kv_empty[S], s_full[2][2], s_free[2][2], p_full[2], o_full[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                              // 2 tiles
@@ -71,14 +78,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   const int qblk = blockIdx.x, h = blockIdx.y, nb = blockIdx.z;
   const int q0 = qblk * 256;
   const int nq = (a.Lq - q0 > 128) ? 2 : 1;
-  const int n_kv = (a.Lk + 127) / 128;
+  const int n_kv = (a.Lk + 127) / 128;             // TMA tiles
+  const int n_blk = (a.Lk + BLK - 1) / BLK;        // softmax blocks
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], nq); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1);
-      mbar_init(&s_free[x], 128);
+      for (int b = 0; b < 2; ++b) { mbar_init(&s_full[x][b], 1); mbar_init(&s_free[x][b], 128); }
       mbar_init(&p_full[x], 128);
       mbar_init(&o_full[x], 1);
     }
@@ -96,10 +103,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  // Register re-distribution between warpgroups (setmaxnreg): warps 0-3 only issue TMA / MMA and
-  // keep 56 registers; the two softmax warpgroups (warps 4-7, 8-11) grow to 216 so that a whole
-  // 128-wide score row plus the output accumulator stay in registers without spilling.
-  // (each setmaxnreg sits at the top of the branch it governs so ptxas budgets that region only)
+  // Register re-distribution between warpgroups (setmaxnreg): warps 0-3 only issue TMA / MMA and keep
+  // 56 registers; the softmax warpgroups (warps 4-7, 8-11) grow to 216.  Each setmaxnreg sits at the top
+  // of the branch it governs so ptxas budgets that region only.
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
@@ -121,45 +127,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     // ------------------------------------------------------------------ MMA issuer of tile x
     const int x = (warp == 1) ? 0 : 1;
     if (lane == 0 && x < nq) {
-      const uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
+      const uint32_t idesc_qk = make_idesc_f16(128, BLK, 0, 0);
       const uint32_t idesc_pv = make_idesc_f16(128, D, 0, 1);
       const uint32_t qa = smem_u32(sQ) + x * TILE_BYTES, skv = smem_u32(sKV);
-      const uint32_t tS = tmem + (x ? TM_S1 : TM_S0), tP = tmem + (x ? TM_P1 : TM_P0),
-                     tO = tmem + (x ? TM_O1 : TM_O0);
-      auto issue_qk = [&](int stage) {
-        const uint32_t ka = skv + stage * 2 * TILE_BYTES;
+      const uint32_t tX = tmem + x * TM_STRIDE;
+      auto issue_qk = [&](int i) {                 // S[i % NSBUF] = Q K(block i)^T
+        const uint32_t ka = skv + ((i / BPT) % S) * 2 * TILE_BYTES + (i % BPT) * BLK * ROWB;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          mma_ss(tS, make_smem_desc(qa + k * 32, 16, SBO, SWZ), make_smem_desc(ka + k * 32, 16, SBO, SWZ),
-                 idesc_qk, k != 0);
+          mma_ss(tX + (i % NSBUF) * BLK, make_smem_desc(qa + k * 32, 16, SBO, SWZ),
+                 make_smem_desc(ka + k * 32, 16, SBO, SWZ), idesc_qk, k != 0);
       };
-      auto issue_pv = [&](int stage) {
-        const uint32_t va = skv + stage * 2 * TILE_BYTES + TILE_BYTES;
+      auto issue_pv = [&](int i) {                 // O' = P(block i) V(block i)
+        const uint32_t va = skv + ((i / BPT) % S) * 2 * TILE_BYTES + TILE_BYTES + (i % BPT) * BLK * ROWB;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          mma_ts(tO, tP + k * 8, make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv, k != 0);
+        for (int k = 0; k < BLK / 16; ++k)
+          mma_ts(tX + TM_O, tX + TM_P + k * 8, make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv, k != 0);
       };
+      const bool tr = a.trace && x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       mbar_wait(&q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_qk(0);
-      tc_commit(&s_full[x]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % S;
-        if (j + 1 < n_kv) {
-          // S(j+1) = Q K(j+1)^T as soon as the softmax warps have pulled S(j) out of TMEM
-          const int s1 = (j + 1) % S;
-          mbar_wait(&kv_full[s1], ((j + 1) / S) & 1);
-          mbar_wait(&s_free[x], j & 1);
-          tc_fence_after();
-          issue_qk(s1);
-          tc_commit(&s_full[x]);
+      int tiles_waited = 0;                        // K/V tiles whose arrival this thread has observed
+      auto need_tile = [&](int t) {
+        while (tiles_waited <= t) {
+          mbar_wait(&kv_full[tiles_waited % S], (tiles_waited / S) & 1);
+          ++tiles_waited;
         }
-        mbar_wait(&p_full[x], j & 1);              // P(j) is in TMEM
         tc_fence_after();
-        issue_pv(s);
+      };
+      for (int i = 0; i < NSBUF && i < n_blk; ++i) {
+        need_tile(i / BPT);
+        issue_qk(i);
+        tc_commit(&s_full[x][i % NSBUF]);
+      }
+      for (int i = 0; i < n_blk; ++i) {
+        if (i + NSBUF < n_blk) {
+          // next scores for this buffer as soon as the softmax warps have pulled S(i) into registers
+          need_tile((i + NSBUF) / BPT);
+          mbar_wait(&s_free[x][i % NSBUF], (i / NSBUF) & 1);
+          tc_fence_after();
+          issue_qk(i + NSBUF);
+          tc_commit(&s_full[x][i % NSBUF]);
+          if (tr && i < 16) a.trace[i * 16 + 10] = clock64();
+        }
+        mbar_wait(&p_full[x], i & 1);              // P(i) is in TMEM
+        tc_fence_after();
+        if (tr && i < 16) a.trace[i * 16 + 8] = clock64();
+        issue_pv(i);
         tc_commit(&o_full[x]);
-        tc_commit(&kv_empty[s]);
+        if (tr && i < 16) a.trace[i * 16 + 9] = clock64();
+        if ((i % BPT) == BPT - 1 || i + 1 == n_blk) tc_commit(&kv_empty[(i / BPT) % S]);   // tile fully consumed
       }
     }
   }
@@ -170,137 +186,101 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     if (x < nq) {
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;         // row inside the tile == TMEM lane
-      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-      const uint32_t tS = tmem + (x ? TM_S1 : TM_S0) + lane_addr;
-      const uint32_t tP = tmem + (x ? TM_P1 : TM_P0) + lane_addr;
-      const uint32_t tO = tmem + (x ? TM_O1 : TM_O0) + lane_addr;
+      const uint32_t tX = tmem + x * TM_STRIDE + ((uint32_t)(quarter * 32) << 16);
       const float c = a.scale_log2e;
       float O[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) O[i] = 0.f;
       float m = -INFINITY, l = 0.f;
 
-      auto fold_o = [&](float alpha) {             // O <- (O + O'(j-1)) * alpha
+      auto fold_o = [&](float alpha) {             // O <- (O + O'(i-1)) * alpha
 #pragma unroll
         for (int d0 = 0; d0 < D; d0 += 32) {
           uint32_t r[32];
-          tmem_ld_x32(tO + d0, r);
+          tmem_ld_x32(tX + TM_O + d0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) O[d0 + i] = (O[d0 + i] + __uint_as_float(r[i])) * alpha;
+          for (int k = 0; k < 32; ++k) O[d0 + k] = (O[d0 + k] + __uint_as_float(r[k])) * alpha;
         }
       };
 
-      for (int j = 0; j < n_kv; ++j) {
-        const int valid = a.Lk - j * 128;          // columns >= valid are padding (last tile)
-        const bool full = valid >= 128;
-        mbar_wait(&s_full[x], j & 1);
+      const bool tr = a.trace && warp == 4 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      for (int i = 0; i < n_blk; ++i) {
+        const int valid = a.Lk - i * BLK;          // columns >= valid are padding (last block)
+        const int b = i % NSBUF;
+        if (tr && i < 16) a.trace[i * 16 + 0] = clock64();
+        mbar_wait(&s_full[x][b], (i / NSBUF) & 1);
         tc_fence_after();
-        if constexpr (kSinglePass) {
-          // whole score row -> registers, then hand S back to the MMA warp at once
-          uint32_t sv[128];
-          tmem_ld_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-          tmem_ld_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-          tmem_ld_x32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[64]));
-          tmem_ld_x32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&sv[96]));
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&s_free[x]);
-          float mx = -INFINITY;
-          if (full) {
+        if (tr && i < 16) a.trace[i * 16 + 1] = clock64();
+        uint32_t sv[BLK];
 #pragma unroll
-            for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-          } else {
+        for (int c0 = 0; c0 < BLK; c0 += 32) tmem_ld_x32(tX + b * BLK + c0, *reinterpret_cast<uint32_t(*)[32]>(&sv[c0]));
+        tmem_ld_wait();
+        if (tr && i < 16) a.trace[i * 16 + 2] = clock64();
+        tc_fence_before();
+        mbar_arrive(&s_free[x][b]);                // the MMA warp may overwrite this score buffer
+        if (valid < BLK) {
 #pragma unroll
-            for (int i = 0; i < 128; ++i) {
-              if (i >= valid) sv[i] = 0xff800000u;   // -inf
-              mx = fmaxf(mx, __uint_as_float(sv[i]));
-            }
-          }
-          const float m_new = fmaxf(m, mx);
-          const float alpha = fast_exp2((m - m_new) * c);
-          m = m_new;
-          const float mc = m_new * c;
-          float lsum = 0.f;
-#pragma unroll
-          for (int i = 0; i < 128; i += 2) {         // packed fp16 pairs overwrite sv[0..63] in place
-            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), c, -mc));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
-            lsum += p0 + p1;
-            const __half2 hp = __floats2half2_rn(p0, p1);
-            sv[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
-          }
-          l = l * alpha + lsum;
-          if (j > 0) {                             // PV(j-1) finished long ago; P region is free again
-            mbar_wait(&o_full[x], (j - 1) & 1);
-            tc_fence_after();
-            fold_o(alpha);
-          }
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            tmem_st_x16(tP + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&sv[cc * 16]));
-        } else {
-          // two passes over S in TMEM (d = 64: 64 accumulator registers leave no room for the row)
-          float mx = -INFINITY;
-          {
-            uint32_t ra[32], rb[32];
-            tmem_ld_x32(tS, ra);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              tmem_ld_wait();
-              uint32_t(&cur)[32] = (cc & 1) ? rb : ra;
-              uint32_t(&nxt)[32] = (cc & 1) ? ra : rb;
-              if (cc < 3) tmem_ld_x32(tS + (cc + 1) * 32, nxt);
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                mx = fmaxf(mx, (full || cc * 32 + i < valid) ? __uint_as_float(cur[i]) : -INFINITY);
-            }
-          }
-          const float m_new = fmaxf(m, mx);
-          const float alpha = fast_exp2((m - m_new) * c);
-          m = m_new;
-          const float mc = m_new * c;
-          if (j > 0) {
-            mbar_wait(&o_full[x], (j - 1) & 1);
-            tc_fence_after();
-            fold_o(alpha);
-          }
-          float lsum = 0.f;
-          {
-            uint32_t ra[32], rb[32];
-            tmem_ld_x32(tS, ra);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              tmem_ld_wait();
-              uint32_t(&cur)[32] = (cc & 1) ? rb : ra;
-              uint32_t(&nxt)[32] = (cc & 1) ? ra : rb;
-              if (cc < 3) tmem_ld_x32(tS + (cc + 1) * 32, nxt);
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                float p0 = fast_exp2(fmaf(__uint_as_float(cur[i]), c, -mc));
-                float p1 = fast_exp2(fmaf(__uint_as_float(cur[i + 1]), c, -mc));
-                if (!full) {
-                  if (cc * 32 + i >= valid) p0 = 0.f;
-                  if (cc * 32 + i + 1 >= valid) p1 = 0.f;
-                }
-                lsum += p0 + p1;
-                const __half2 hp = __floats2half2_rn(p0, p1);
-                pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
-              }
-              tmem_st_x16(tP + cc * 16, pk);
-            }
-          }
-          l = l * alpha + lsum;
-          tc_fence_before();
-          mbar_arrive(&s_free[x]);
+          for (int k = 0; k < BLK; ++k)
+            if (k >= valid) sv[k] = 0xff800000u;     // -inf
         }
+        // row max with 8 independent chains (a single fmax chain costs 64 x 6 cycles of pure latency)
+        float m8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m8[k] = __uint_as_float(sv[k]);
+#pragma unroll
+        for (int k = 8; k < BLK; ++k) m8[k & 7] = fmaxf(m8[k & 7], __uint_as_float(sv[k]));
+        const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                               fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+        const float m_new = fmaxf(m, mx);
+        const float alpha = fast_exp2((m - m_new) * c);
+        m = m_new;
+        const float mc = m_new * c;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        // first half of the exponentials; packed fp16 pairs overwrite sv[0..BLK/2) in place
+#pragma unroll
+        for (int k = 0; k < BLK / 2; k += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[k]), c, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[k + 1]), c, -mc));
+          ls[(k >> 1) & 3] += p0 + p1;
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          sv[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        if (tr && i < 16) a.trace[i * 16 + 3] = clock64();
+        // PV(i-1) has had half a block to finish: start pulling its product O' while the second half
+        // of the exponentials is computed
+        uint32_t ro[D];
+        if (i > 0) {
+          mbar_wait(&o_full[x], (i - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int d0 = 0; d0 < D; d0 += 32) tmem_ld_x32(tX + TM_O + d0, *reinterpret_cast<uint32_t(*)[32]>(&ro[d0]));
+        }
+        if (tr && i < 16) a.trace[i * 16 + 4] = clock64();
+#pragma unroll
+        for (int k = BLK / 2; k < BLK; k += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[k]), c, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[k + 1]), c, -mc));
+          ls[(k >> 1) & 3] += p0 + p1;
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          sv[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        l = l * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
+        if (i > 0) {                               // O <- (O + O'(i-1)) * alpha ; the P region is free again
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < D; ++k) O[k] = (O[k] + __uint_as_float(ro[k])) * alpha;
+        }
+        if (tr && i < 16) a.trace[i * 16 + 5] = clock64();
+#pragma unroll
+        for (int c0 = 0; c0 < BLK / 2; c0 += 16) tmem_st_x16(tX + TM_P + c0, *reinterpret_cast<uint32_t(*)[16]>(&sv[c0]));
         tmem_st_wait();
+        if (tr && i < 16) a.trace[i * 16 + 6] = clock64();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
       }
       // last partial product
-      mbar_wait(&o_full[x], (n_kv - 1) & 1);
+      mbar_wait(&o_full[x], (n_blk - 1) & 1);
       tc_fence_after();
       fold_o(1.0f);
       const int qi = q0 + x * 128 + row;
@@ -308,11 +288,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         const float inv = 1.0f / l;
         __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h;
 #pragma unroll
-        for (int i = 0; i < D; i += 8) {
+        for (int k = 0; k < D; k += 8) {
           __align__(16) __half hh[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(O[i + t] * inv);
-          *reinterpret_cast<uint4*>(op + i) = *reinterpret_cast<uint4*>(hh);
+          for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(O[k + t] * inv);
+          *reinterpret_cast<uint4*>(op + k) = *reinterpret_cast<uint4*>(hh);
         }
       }
     }
@@ -507,14 +487,16 @@ template <int D>
 static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                        int Nb, cudaStream_t st) {
   constexpr int SMEM = (2 + 2 * kAttnStages) * 128 * D * 2 + 1024;
+  constexpr int BLK = (D == 32) ? 128 : 64, NSBUF = (D == 32) ? 1 : 2;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd_kernel<D, BLK, NSBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+        cudaSuccess)
       return GVF_ERR_CUDA;
     configured = true;
   }
   dim3 grid((a.Lq + 255) / 256, a.H, Nb);
-  attn_fwd_kernel<D><<<grid, 384, SMEM, st>>>(mq, mk, mv, a);
+  attn_fwd_kernel<D, BLK, NSBUF><<<grid, 384, SMEM, st>>>(mq, mk, mv, a);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -522,6 +504,10 @@ static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
 
 using namespace gvf;
 
+static int g_attn_dbg = 0;
+static long long* g_attn_trace = nullptr;
+extern "C" GVF_API void gvf_attn_set_trace(void* p) { g_attn_trace = (long long*)p; }
+extern "C" GVF_API void gvf_attn_set_debug(int v) { g_attn_dbg = v; }
 static int g_small_rows = 0;   // row-staged temporal variant: measured slower than the warp-per-(batch,head) one
 
 // q [Nb_q, Lq, H, D], k/v [Nb_kv, Lk, H, D] fp16 with element strides (batch, seq, head);
@@ -583,5 +569,7 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   a.q_batch_mul = q_shared ? 0 : 1;
   a.kv_batch_mul = kv_shared ? 0 : 1;
   a.scale_log2e = scale * 1.4426950408889634f;
+  a.dbg = g_attn_dbg;
+  a.trace = g_attn_trace;
   return D == 32 ? launch_attn<32>(mq, mk, mv, a, Nb, st) : launch_attn<64>(mq, mk, mv, a, Nb, st);
 }

@@ -91,8 +91,8 @@ static bool perm_ok(const int* p) {
 
 extern "C" GVF_API int gvf_vox2seq_encode(const int32_t* coords, long long N, const int* permute, int hilbert,
                                           int32_t* codes, void* stream) {
+  if (N == 0 && perm_ok(permute)) return GVF_OK;
   if (!coords || !codes || N < 0 || !perm_ok(permute)) return GVF_ERR_INVALID;
-  if (N == 0) return GVF_OK;
   gvf::vox_encode_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       coords, N, permute[0], permute[1], permute[2], hilbert, codes);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
@@ -100,8 +100,8 @@ extern "C" GVF_API int gvf_vox2seq_encode(const int32_t* coords, long long N, co
 
 extern "C" GVF_API int gvf_vox2seq_decode(const int32_t* codes, long long N, const int* permute, int hilbert,
                                           int32_t* coords, void* stream) {
+  if (N == 0 && perm_ok(permute)) return GVF_OK;
   if (!coords || !codes || N < 0 || !perm_ok(permute)) return GVF_ERR_INVALID;
-  if (N == 0) return GVF_OK;
   gvf::vox_decode_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       codes, N, permute[0], permute[1], permute[2], hilbert, coords);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;

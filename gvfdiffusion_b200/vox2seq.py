@@ -21,6 +21,8 @@ def encode(coords, permute=(0, 1, 2), mode="z_order"):
         raise ValueError(f"Unknown encoding mode: {mode}")
     c = coords.to(torch.int32).contiguous()
     out = torch.empty(c.shape[0], dtype=torch.int32, device=c.device)
+    if c.shape[0] == 0:
+        return out
     _lib.check(_lib.lib().gvf_vox2seq_encode(_lib.ptr(c), c.shape[0], _perm(permute), int(mode == "hilbert"),
                                              _lib.ptr(out), _lib.current_stream()), "gvf_vox2seq_encode")
     return out
@@ -34,6 +36,8 @@ def decode(code, permute=(0, 1, 2), mode="z_order"):
         raise ValueError(f"Unknown decoding mode: {mode}")
     c = code.to(torch.int32).contiguous()
     out = torch.empty((c.shape[0], 3), dtype=torch.int32, device=c.device)
+    if c.shape[0] == 0:
+        return out
     _lib.check(_lib.lib().gvf_vox2seq_decode(_lib.ptr(c), c.shape[0], _perm(permute), int(mode == "hilbert"),
                                              _lib.ptr(out), _lib.current_stream()), "gvf_vox2seq_decode")
     return out

@@ -148,6 +148,12 @@ GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void* v, void* 
                              const long long* o_strides, int q_shared, int kv_shared, float scale,
                              void* stream);
 
+/* Timing-experiment hook (tools/attn_experiments.py): disables parts of the softmax loop; results are
+ * numerically meaningless when non-zero.  0 = normal operation. */
+GVF_API void gvf_attn_set_debug(int v);
+/* Optional device buffer (256 int64) receiving clock64 stamps of CTA (0,0,0)'s first 16 blocks; NULL = off. */
+GVF_API void gvf_attn_set_trace(void* device_buffer);
+
 /* ------------------------------------------------------------------------------------
  * 3. Linear layers -- replace nn.Linear (cuBLAS under fp16 autocast) plus the elementwise
  *    kernels around it (reference model/dit.py:128-138,240-277, model/attention/modules.py:
