@@ -45,12 +45,12 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
 
-constexpr int kEpiCols = 64;                 // columns per epilogue chunk
+constexpr int kEpiCols = 64;                 // columns per epilogue chunk (default)
 constexpr int kStgLd = kEpiCols + 1;         // padded row of the per-warp staging tile (floats)
 
 // Epilogue of one 128 x BN accumulator tile, executed by the four epilogue warps (q = warp % 4 owns
 // TMEM lanes 32q..32q+31).
-template <int BN>
+template <int BN, int EC = kEpiCols>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const uint32_t tmem, float* stg,
                                               const float* s_bias, const int q, const int lane,
                                               const int tile_m, const int tile_n, const int M, const int N) {
@@ -65,29 +65,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const uint32_t 
     const int b_first = row0 / ep.rows_per_batch;
     const bool one_batch = rows_here <= 0 || (row0 + rows_here - 1) / ep.rows_per_batch == b_first;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += kEpiCols) {
+    for (int c0 = 0; c0 < BN; c0 += EC) {
       const int col0 = tile_n * BN + c0;
-      float v[kEpiCols];
+      float v[EC];
       __syncwarp();
       {
-        uint32_t r0[32], r1[32];
-        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + c0, r0);
-        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + c0 + 32, r1);
+        uint32_t rr[EC];
+#pragma unroll
+        for (int j0 = 0; j0 < EC; j0 += 32)
+          tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + c0 + j0, *reinterpret_cast<uint32_t(*)[32]>(&rr[j0]));
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(r0[j]) + s_bias[c0 + j];
-          v[32 + j] = __uint_as_float(r1[j]) + s_bias[c0 + 32 + j];
-        }
+        for (int j = 0; j < EC; ++j) v[j] = __uint_as_float(rr[j]) + s_bias[c0 + j];
       }
       if (col0 >= N || rows_here <= 0) continue;       // warp-uniform
       if (mode == 1) {
 #pragma unroll
-        for (int j = 0; j < kEpiCols; ++j) v[j] = gelu_tanh(r16(v[j]));
+        for (int j = 0; j < EC; ++j) v[j] = gelu_tanh(r16(v[j]));
       } else if (mode == 6) {
         // MultiHeadRMSNorm on the fp16-rounded Linear output, one head = 32 columns
 #pragma unroll
-        for (int hh = 0; hh < kEpiCols / 32; ++hh) {
+        for (int hh = 0; hh < EC / 32; ++hh) {
           const int hc = col0 + hh * 32;
           if (hc < ep.norm_cols) {
             float ss = 0.f;
@@ -102,21 +100,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const uint32_t 
         }
       } else if (mode == 2 || mode == 3 || mode == 5) {
 #pragma unroll
-        for (int j = 0; j < kEpiCols; ++j) v[j] = r16(v[j]);
+        for (int j = 0; j < EC; ++j) v[j] = r16(v[j]);
       }
 #pragma unroll
-      for (int j = 0; j < kEpiCols; ++j) stg[lane * kStgLd + j] = v[j];
+      for (int j = 0; j < EC; ++j) stg[lane * (EC + 1) + j] = v[j];
       __syncwarp();
       // ---- phase 2: lane owns columns (2*lane, 2*lane+1) of the chunk
-      const int cc = col0 + 2 * lane;
+      // lane -> (column pair lc, row phase ro_): EC == 64 one row per pass, EC == 32 two rows per pass
+      constexpr int RS = 64 / EC;
+      const int lc = (2 * lane) % EC, ro_ = (2 * lane) / EC;
+      const int cc = col0 + lc;
       const bool col_ok = cc < N;                       // N % 8 == 0, so the pair is in or out together
       if (mode == 0 || mode == 1 || mode == 6) {
         __half* o = reinterpret_cast<__half*>(ep.out) + (size_t)row0 * ep.ldo + cc;
         if (col_ok)
 #pragma unroll 8
-          for (int r = 0; r < rows_here; ++r)
+          for (int r = ro_; r < rows_here; r += RS)
             *reinterpret_cast<__half2*>(o + (size_t)r * ep.ldo) =
-                __floats2half2_rn(stg[r * kStgLd + 2 * lane], stg[r * kStgLd + 2 * lane + 1]);
+                __floats2half2_rn(stg[r * (EC + 1) + lc], stg[r * (EC + 1) + lc + 1]);
       } else if (mode == 2) {
         // fp32 residual read-modify-write; loads of 16 rows are issued before their stores so the
         // DRAM latency is paid once per batch, not once per row
@@ -127,21 +128,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const uint32_t 
             const __half2 gg = *reinterpret_cast<const __half2*>(ep.gate + (size_t)b_first * ep.gate_stride + cc);
             g0 = __low2float(gg); g1 = __high2float(gg);
           }
-          for (int rb = 0; rb < rows_here; rb += 16) {
+          for (int rb = 0; rb < rows_here; rb += 16 * RS) {
             float2 x[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-              if (rb + k < rows_here) x[k] = *reinterpret_cast<const float2*>(o + (size_t)(rb + k) * ep.ldo);
+              if (rb + k * RS + ro_ < rows_here)
+                x[k] = *reinterpret_cast<const float2*>(o + (size_t)(rb + k * RS + ro_) * ep.ldo);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-              const int r = rb + k;
+              const int r = rb + k * RS + ro_;
               if (r < rows_here) {
                 if (ep.gate && !one_batch) {
                   const __half2 gg = *reinterpret_cast<const __half2*>(
                       ep.gate + (size_t)((row0 + r) / ep.rows_per_batch) * ep.gate_stride + cc);
                   g0 = __low2float(gg); g1 = __high2float(gg);
                 }
-                float h0 = stg[r * kStgLd + 2 * lane], h1 = stg[r * kStgLd + 2 * lane + 1];
+                float h0 = stg[r * (EC + 1) + lc], h1 = stg[r * (EC + 1) + lc + 1];
                 if (ep.gate) { h0 = r16(h0 * g0); h1 = r16(h1 * g1); }
                 x[k].x += h0; x[k].y += h1;
                 *reinterpret_cast<float2*>(o + (size_t)r * ep.ldo) = x[k];
@@ -152,40 +154,41 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const uint32_t 
       } else if (mode == 3) {
         __half* o = reinterpret_cast<__half*>(ep.out) + (size_t)row0 * ep.ldo + cc;
         if (col_ok)
-          for (int rb = 0; rb < rows_here; rb += 8) {
+          for (int rb = 0; rb < rows_here; rb += 8 * RS) {
             __half2 old[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (rb + k < rows_here) old[k] = *reinterpret_cast<const __half2*>(o + (size_t)(rb + k) * ep.ldo);
+              if (rb + k * RS + ro_ < rows_here)
+                old[k] = *reinterpret_cast<const __half2*>(o + (size_t)(rb + k * RS + ro_) * ep.ldo);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const int r = rb + k;
+              const int r = rb + k * RS + ro_;
               if (r < rows_here)
                 *reinterpret_cast<__half2*>(o + (size_t)r * ep.ldo) =
-                    __floats2half2_rn(stg[r * kStgLd + 2 * lane] + __low2float(old[k]),
-                                      stg[r * kStgLd + 2 * lane + 1] + __high2float(old[k]));
+                    __floats2half2_rn(stg[r * (EC + 1) + lc] + __low2float(old[k]),
+                                      stg[r * (EC + 1) + lc + 1] + __high2float(old[k]));
             }
           }
       } else if (mode == 4) {
         float* o = reinterpret_cast<float*>(ep.out) + (size_t)row0 * ep.ldo + cc;
         if (col_ok)
 #pragma unroll 8
-          for (int r = 0; r < rows_here; ++r)
+          for (int r = ro_; r < rows_here; r += RS)
             *reinterpret_cast<float2*>(o + (size_t)r * ep.ldo) =
-                make_float2(stg[r * kStgLd + 2 * lane], stg[r * kStgLd + 2 * lane + 1]);
+                make_float2(stg[r * (EC + 1) + lc], stg[r * (EC + 1) + lc + 1]);
       } else {
         // mode 5: compact fp32 rows of ldo (<= N) columns, e.g. Linear(768 -> 14)
         float* o = reinterpret_cast<float*>(ep.out) + (size_t)row0 * ep.ldo;
-        for (int r = 0; r < rows_here; ++r)
+        for (int r = ro_; r < rows_here; r += RS)
 #pragma unroll
           for (int t = 0; t < 2; ++t)
-            if (cc + t < ep.ldo) o[(size_t)r * ep.ldo + cc + t] = stg[r * kStgLd + 2 * lane + t];
+            if (cc + t < ep.ldo) o[(size_t)r * ep.ldo + cc + t] = stg[r * (EC + 1) + lc + t];
       }
     }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 2)
+template <int BN, int STAGES, int EC = kEpiCols, int MINB = 2>
+__global__ void __launch_bounds__(192, MINB)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
             int M, int N, int K, GemmEpi ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -194,7 +197,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   __shared__ float s_bias[BN];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = BN * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
-  static_assert(4 * 32 * kStgLd * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline smem");
+  static_assert(4 * 32 * (EC + 1) * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline smem");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x, tile_m = blockIdx.y;
   const int kblocks = (K + kBK - 1) / kBK;
@@ -257,7 +260,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int q = warp & 3;
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    epilogue_tile<BN>(ep, tmem, reinterpret_cast<float*>(smem) + q * 32 * kStgLd, s_bias, q, lane, tile_m, tile_n, M, N);
+    epilogue_tile<BN, EC>(ep, tmem, reinterpret_cast<float*>(smem) + q * 32 * (EC + 1), s_bias, q, lane, tile_m, tile_n, M, N);
   }
   tc_fence_before();
   __syncthreads();
@@ -383,19 +386,19 @@ static int launch_gemm_persistent(const CUtensorMap& mA, const CUtensorMap& mW, 
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EC = kEpiCols, int MINB = 2>
 static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mW, int M, int N, int K,
                        const GemmEpi& ep, cudaStream_t st) {
   constexpr int SMEM = STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM) != cudaSuccess)
       return GVF_ERR_CUDA;
     configured = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM);
-  gemm_kernel<BN, STAGES><<<grid, 192, SMEM, st>>>(mA, mW, M, N, K, ep);
+  gemm_kernel<BN, STAGES, EC, MINB><<<grid, 192, SMEM, st>>>(mA, mW, M, N, K, ep);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -441,6 +444,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   ep.gamma_q = gamma_q; ep.gamma_k = gamma_k; ep.norm_cols = norm_cols;
   if (variant == 2) return launch_gemm_persistent<256, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
   if (variant == 1) return launch_gemm_persistent<128, 4>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
+  if (variant == 3) return launch_gemm<128, 2, 32, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);   // 3 CTAs / SM
   return launch_gemm<128, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
 }
 

@@ -247,7 +247,7 @@ def test_gemm_ragged_rows_and_multi_batch_gate():
     _close(o14, lin[:, :14], 1e-3, "compact")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_gemm_scheduling_variants(variant):
     from gvfdiffusion_b200 import _lib, ops
     L = _lib.lib()
