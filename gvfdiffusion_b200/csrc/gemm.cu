@@ -421,14 +421,17 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   if (gate && (gate_stride % 2)) return GVF_ERR_INVALID;
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
   if (epilogue == 2 && gate && rows_per_batch <= 0) return GVF_ERR_INVALID;
-  // variant: 0 = one tile per CTA (v1), 1 = persistent 128x128, 2 = persistent 128x256
+  // variant: 0 = one tile per CTA, 2 CTAs / SM, 3 stages; 1 = persistent 128x128; 2 = persistent 128x256;
+  //          3 = one tile per CTA, 3 CTAs / SM, 2 stages, 32-column epilogue chunks
   int variant = g_gemm_variant;
   if (variant < 0) {
     // measured on B200 (tools/gemm_bench.py, profiles/): 128x256 persistent tiles win once there are at
     // least two full waves of them and the main loop is long (K >= 768: the VAE shapes) or N = 3C (qkv);
-    // the short-K DiT GEMMs are latency-bound and do best with two independent CTAs per SM
+    // the short-K DiT GEMMs are latency-bound and do best with independent CTAs sharing an SM -- three
+    // of them (variant 3) whenever the epilogue is the light one (no per-head RMS norm)
     const long long tiles256 = (long long)((M + kBM - 1) / kBM) * ((N + 255) / 256);
-    variant = (N % 256 == 0 && tiles256 >= 296 && (K >= 768 || N % 768 == 0)) ? 2 : 0;
+    variant = (N % 256 == 0 && tiles256 >= 296 && (K >= 768 || N % 768 == 0)) ? 2
+              : (N <= 2048 && K <= 2048) ? 3 : 0;
   }
   const int BN = (variant == 2) ? 256 : 128;
   CUtensorMap mA, mW;
