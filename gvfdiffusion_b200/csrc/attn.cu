@@ -34,6 +34,24 @@ using namespace tc;
 
 constexpr int kAttnStages = 4;
 
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2, new on sm_100): one issue slot for two lanes of work.
+// The softmax loop is issue- as much as MUFU-bound, so halving its FMA-pipe instruction count matters.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "mul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; exp2(-inf) = 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -76,6 +94,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, h = blockIdx.y, nb = blockIdx.z;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (a.trace && threadIdx.x == 0 && cta_lin < 1024) {   // per-CTA (smid, start ns) for schedule studies
+    unsigned long long t; unsigned sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    a.trace[256 + 3 * cta_lin] = sm; a.trace[256 + 3 * cta_lin + 1] = (long long)t;
+  }
   const int q0 = qblk * 256;
   const int nq = (a.Lq - q0 > 128) ? 2 : 1;
   const int n_kv = (a.Lk + 127) / 128;             // TMA tiles
@@ -208,7 +233,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       for (int i = 0; i < n_blk; ++i) {
         const int valid = a.Lk - i * BLK;          // columns >= valid are padding (last block)
         const int b = i % NSBUF;
-        if (tr && i < 16) a.trace[i * 16 + 0] = clock64();
+        if (tr && i < 32) a.trace[(i & 15) * 16 + (i < 16 ? 0 : 12)] = clock64();
         mbar_wait(&s_full[x][b], (i / NSBUF) & 1);
         tc_fence_after();
         if (tr && i < 16) a.trace[i * 16 + 1] = clock64();
@@ -236,16 +261,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         const float alpha = fast_exp2((m - m_new) * c);
         m = m_new;
         const float mc = m_new * c;
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        // first half of the exponentials; packed fp16 pairs overwrite sv[0..BLK/2) in place
-#pragma unroll
-        for (int k = 0; k < BLK / 2; k += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[k]), c, -mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[k + 1]), c, -mc));
-          ls[(k >> 1) & 3] += p0 + p1;
+        float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // four packed (even, odd column) partial sums
+        const float nmc = -mc;
+        auto exp_pair = [&](int k) {               // columns k, k+1 -> fp16 pair in sv[k / 2]
+          float x0, x1;
+          ffma2(x0, x1, __uint_as_float(sv[k]), __uint_as_float(sv[k + 1]), c, c, nmc, nmc);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          const int j = (k >> 1) & 3;
+          fadd2(ls[2 * j], ls[2 * j + 1], ls[2 * j], ls[2 * j + 1], p0, p1);
           const __half2 hp = __floats2half2_rn(p0, p1);
           sv[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
-        }
+        };
+        // first half of the exponentials; packed fp16 pairs overwrite sv[0..BLK/2) in place
+#pragma unroll
+        for (int k = 0; k < BLK / 2; k += 2) exp_pair(k);
         if (tr && i < 16) a.trace[i * 16 + 3] = clock64();
         // PV(i-1) has had half a block to finish: start pulling its product O' while the second half
         // of the exponentials is computed
@@ -258,18 +287,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         }
         if (tr && i < 16) a.trace[i * 16 + 4] = clock64();
 #pragma unroll
-        for (int k = BLK / 2; k < BLK; k += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[k]), c, -mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[k + 1]), c, -mc));
-          ls[(k >> 1) & 3] += p0 + p1;
-          const __half2 hp = __floats2half2_rn(p0, p1);
-          sv[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
-        }
-        l = l * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
+        for (int k = BLK / 2; k < BLK; k += 2) exp_pair(k);
+        l = l * alpha + (((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7])));
         if (i > 0) {                               // O <- (O + O'(i-1)) * alpha ; the P region is free again
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < D; ++k) O[k] = (O[k] + __uint_as_float(ro[k])) * alpha;
+          for (int k = 0; k < D; k += 2) {
+            fadd2(O[k], O[k + 1], O[k], O[k + 1], __uint_as_float(ro[k]), __uint_as_float(ro[k + 1]));
+            fmul2(O[k], O[k + 1], O[k], O[k + 1], alpha, alpha);
+          }
         }
         if (tr && i < 16) a.trace[i * 16 + 5] = clock64();
 #pragma unroll
@@ -279,6 +305,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         tc_fence_before();
         mbar_arrive(&p_full[x]);
       }
+      if (tr) a.trace[13] = clock64();
       // last partial product
       mbar_wait(&o_full[x], (n_blk - 1) & 1);
       tc_fence_after();
@@ -300,6 +327,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 3) tmem_dealloc(tmem, 512);
+  if (a.trace && threadIdx.x == 0 && cta_lin < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.trace[256 + 3 * cta_lin + 2] = (long long)t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -311,6 +311,58 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ pts
   }
 }
 
+// Fast path for clouds that fit shared memory (P <= 16384): coordinates live in smem as SoA, each
+// thread keeps the running minimum distances of its PER points in registers, and a sample costs one
+// __syncthreads: warp arg-max by redux.sync (distances are >= +0, so their bit patterns order like
+// the floats), double-buffered per-warp results, every warp re-reduces the 32 partials redundantly.
+// Same arithmetic, same tie rule (lowest index) as fps_kernel: identical indices.
+template <int PER>
+__global__ void __launch_bounds__(1024, 1) fps_smem_kernel(const float* __restrict__ pts, int ld, int P, int K,
+                                                            int start, int* __restrict__ out_idx) {
+  extern __shared__ float sxyz[];                  // x[0..Pp) | y | z, Pp = PER * 1024
+  __shared__ unsigned sd[2][32];
+  __shared__ unsigned si[2][32];
+  constexpr int Pp = PER * 1024;
+  float* sx = sxyz; float* sy = sxyz + Pp; float* sz = sxyz + 2 * Pp;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float md[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid + 1024 * j;
+    const bool ok = i < P;
+    sx[i] = ok ? pts[(size_t)i * ld] : 0.f;
+    sy[i] = ok ? pts[(size_t)i * ld + 1] : 0.f;
+    sz[i] = ok ? pts[(size_t)i * ld + 2] : 0.f;
+    md[j] = ok ? 3.0e38f : -1.0f;                  // padding never wins: min(-1, d) = -1 < any distance
+  }
+  unsigned cur = (unsigned)start;
+  if (tid == 0) out_idx[0] = start;
+  __syncthreads();
+  for (int k = 1; k < K; ++k) {
+    const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+    float best = -1.0f;
+    unsigned bi = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = tid + 1024 * j;
+      const float dx = sx[i] - cx, dy = sy[i] - cy, dz = sz[i] - cz;
+      const float d = fminf(md[j], dx * dx + dy * dy + dz * dz);
+      md[j] = d;
+      if (d > best) { best = d; bi = (unsigned)i; }   // ascending i per thread: first max kept
+    }
+    unsigned ub = best < 0.f ? 0u : __float_as_uint(best);
+    unsigned wm = __reduce_max_sync(0xffffffffu, ub);
+    unsigned wi = __reduce_min_sync(0xffffffffu, ub == wm ? bi : 0xffffffffu);
+    if (lane == 0) { sd[k & 1][w] = wm; si[k & 1][w] = wi; }
+    __syncthreads();
+    ub = sd[k & 1][lane];
+    bi = si[k & 1][lane];
+    wm = __reduce_max_sync(0xffffffffu, ub);
+    cur = __reduce_min_sync(0xffffffffu, ub == wm ? bi : 0xffffffffu);
+    if (tid == 0) out_idx[k] = (int)cur;
+  }
+}
+
 }  // namespace gvf
 
 extern "C" GVF_API int gvf_gaussian_tensor(const gvf_raster_params* prm, int P, const float* xyz,
@@ -326,6 +378,16 @@ extern "C" GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start
                                int32_t* out_idx, void* stream) {
   if (!pts || !workspace || !out_idx || P <= 0 || K <= 0 || K > P || start < 0 || start >= P || ld < 3)
     return GVF_ERR_INVALID;
-  gvf::fps_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pts, ld, P, K, start, workspace, out_idx);
-  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+  auto launch_smem = [&](auto kern, int per) {
+    const int bytes = per * 1024 * 3 * (int)sizeof(float);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    kern<<<1, 1024, bytes, (cudaStream_t)stream>>>(pts, ld, P, K, start, out_idx);
+    return true;
+  };
+  bool ok = true;
+  if (P <= 4096) ok = launch_smem(gvf::fps_smem_kernel<4>, 4);
+  else if (P <= 8192) ok = launch_smem(gvf::fps_smem_kernel<8>, 8);
+  else if (P <= 16384) ok = launch_smem(gvf::fps_smem_kernel<16>, 16);
+  else gvf::fps_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pts, ld, P, K, start, workspace, out_idx);
+  return (ok && cudaGetLastError() == cudaSuccess) ? GVF_OK : GVF_ERR_CUDA;
 }

@@ -39,8 +39,11 @@ class GVFPipeline:
         o.arrays = R.canon_arrays(canon, self.dev)
         o.static_gs = ops.gaussian_tensor(self._gprm, o.arrays)
         P = o.static_gs.shape[0]
-        i512 = ops.fps(o.static_gs, min(self.num_latents, P)).long()
-        i4096 = ops.fps(o.static_gs, min(self.num_static, P)).long()
+        # farthest point sampling is greedy: from one start point the K-sample is a prefix of any longer
+        # sample, so the two sample_gs calls of the reference share one run
+        n1, n2 = min(self.num_latents, P), min(self.num_static, P)
+        idx = ops.fps(o.static_gs, max(n1, n2)).long()
+        i512, i4096 = idx[:n1], idx[:n2]
         o.fps512 = o.static_gs.index_select(0, i512)
         o.fps4096 = o.static_gs.index_select(0, i4096)
         return o

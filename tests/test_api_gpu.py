@@ -103,3 +103,27 @@ def test_gaussian_tensor_and_fps():
         ref_idx.append(cur)
     assert np.array_equal(idx, np.array(ref_idx, np.int32))
     assert len(set(idx.tolist())) == K
+    # greedy sampling: a shorter sample is a prefix of a longer one (the pipeline relies on it)
+    assert np.array_equal(ops.fps(gt, 50).cpu().numpy(), idx[:50])
+
+
+@pytest.mark.parametrize("P", [1000, 5000, 16384, 20000])
+def test_fps_sizes(P):
+    """every kernel variant of gvf_fps (smem-resident 4/8/16 points per thread, global fallback),
+    with duplicated points so that the lowest-index tie rule is exercised"""
+    from gvfdiffusion_b200 import ops
+    g = torch.Generator().manual_seed(P)
+    p = torch.rand(P, 3, generator=g)
+    p[P // 2:P // 2 + 100] = p[:100]
+    K = 48
+    idx = ops.fps(p.cuda(), K, start=7).cpu().numpy()
+    pn = p.numpy()
+    mind = np.full(P, 3.0e38, np.float32)
+    cur, ref_idx = 7, [7]
+    for _ in range(1, K):
+        d = pn - pn[cur]
+        dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        mind = np.minimum(mind, dist.astype(np.float32))
+        cur = int(np.argmax(mind))
+        ref_idx.append(cur)
+    assert np.array_equal(idx, np.array(ref_idx, np.int32))
