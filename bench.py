@@ -351,7 +351,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launch_estimate() * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel<32> (static cross-attention, kv 4096)",
+        "roofline": {"bound": "tensor", "kernel": "attn_fwd6_kernel (d=32, static cross-attention, kv 4096)",
                      "achieved": dom.get("tflops"), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": dom.get("frac_of_sustained"), "traffic": None, "peak_source": pk["source"] + " sustained bf16"},
         "roofline_detail": roof_detail,

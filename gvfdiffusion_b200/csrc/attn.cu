@@ -65,10 +65,14 @@ struct AttnArgs {
   int q_batch_mul, kv_batch_mul;                  // 0: tensor shared across the batch
   float scale_log2e;
   long long* trace;   // optional clock64 trace of CTA (0,0,0) (tools/attn_experiments.py)
-  int dbg;   // timing experiments only (tools/attn_experiments.py): 1 no exp2, 2 no O' fold, 4 no P store, 8 no max
+  int stagger;        // clocks tile B's softmax warpgroup starts late (see the softmax branch)
+  int dbg;            // bit 0x20: MUFU ping-pong between the two softmax warpgroups (v4)
 };
 
-template <int D, int BLK, int NSBUF>
+// POLY = n > 0: every n-th pair of exponentials is evaluated on the FMA pipe (Cody-Waite split plus a
+// degree-3 polynomial, relative error 7.5e-5 -- a sixth of the fp16 rounding P gets anyway) instead of
+// MUFU.EX2, which at 16 results / clk / SM is the unit that bounds this kernel at d = 32.
+template <int D, int BLK, int NSBUF, int POLY>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
@@ -217,6 +221,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < D; ++i) O[i] = 0.f;
       float m = -INFINITY, l = 0.f;
+      // The two softmax warpgroups share each SM sub-partition's MUFU unit.  Started together they stay in
+      // lock-step: both in the exponential phase (MUFU oversubscribed), then both in the load / max / fold
+      // phase (MUFU idle).  Delaying tile B by about half a block period interleaves the phases.
+      if (x == 1 && a.stagger > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < a.stagger) {}
+      }
+      const bool pingpong = (a.dbg & 0x20) && nq == 2;
+      if (pingpong && x == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");   // tile A goes first
 
       auto fold_o = [&](float alpha) {             // O <- (O + O'(i-1)) * alpha
 #pragma unroll
@@ -234,6 +247,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         const int valid = a.Lk - i * BLK;          // columns >= valid are padding (last block)
         const int b = i % NSBUF;
         if (tr && i < 32) a.trace[(i & 15) * 16 + (i < 16 ? 0 : 12)] = clock64();
+        if (a.trace && warp == 8 && lane == 0 && cta_lin == 0 && i < 16) a.trace[i * 16 + 14] = clock64();
         mbar_wait(&s_full[x][b], (i / NSBUF) & 1);
         tc_fence_after();
         if (tr && i < 16) a.trace[i * 16 + 1] = clock64();
@@ -262,23 +276,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         m = m_new;
         const float mc = m_new * c;
         float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // four packed (even, odd column) partial sums
-        const float nmc = -mc;
+        float nmc = -mc;
         auto exp_pair = [&](int k) {               // columns k, k+1 -> fp16 pair in sv[k / 2]
           float x0, x1;
           ffma2(x0, x1, __uint_as_float(sv[k]), __uint_as_float(sv[k + 1]), c, c, nmc, nmc);
-          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          float p0, p1;
+          if (POLY > 0 && ((k >> 1) % POLY) == POLY - 1) {
+            // 2^x = 2^n * 2^f, n = round(x), f = x - n in [-0.5, 0.5]; n sits in the low mantissa bits of
+            // t = x + 1.5 * 2^23 and is added straight into the exponent field of the polynomial's value
+            x0 = fmaxf(x0, -120.f); x1 = fmaxf(x1, -120.f);
+            float t0, t1, n0, n1, f0, f1;
+            fadd2(t0, t1, x0, x1, 12582912.f, 12582912.f);
+            fadd2(n0, n1, t0, t1, -12582912.f, -12582912.f);
+            fadd2(f0, f1, x0, x1, -n0, -n1);
+            ffma2(p0, p1, f0, f1, 0.05517164617776871f, 0.05517164617776871f, 0.2426111251115799f, 0.2426111251115799f);
+            ffma2(p0, p1, p0, p1, f0, f1, 0.6932609677314758f, 0.6932609677314758f);
+            ffma2(p0, p1, p0, p1, f0, f1, 0.9999280571937561f, 0.9999280571937561f);
+            p0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+            p1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+          } else {
+            p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+          }
           const int j = (k >> 1) & 3;
           fadd2(ls[2 * j], ls[2 * j + 1], ls[2 * j], ls[2 * j + 1], p0, p1);
           const __half2 hp = __floats2half2_rn(p0, p1);
           sv[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
         };
+        uint32_t ro[D];
+        if (pingpong) {
+          // MUFU ping-pong: the two warpgroups take turns in the exponential phase (named barriers 1 / 2),
+          // so one runs its loads / max / fold / stores while the other owns the MUFU unit
+          if (i > 0) {
+            mbar_wait(&o_full[x], (i - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int d0 = 0; d0 < D; d0 += 32) tmem_ld_x32(tX + TM_O + d0, *reinterpret_cast<uint32_t(*)[32]>(&ro[d0]));
+          }
+          asm volatile("bar.sync %1, 256;" : "+f"(nmc) : "r"(1 + x) : "memory");
+          if (tr && i < 16) a.trace[i * 16 + 3] = clock64();
+#pragma unroll
+          for (int k = 0; k < BLK; k += 2) exp_pair(k);
+          float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+          if (i + 1 < n_blk || x == 0) asm volatile("bar.arrive %1, 256;" : "+f"(lsum) : "r"(2 - x) : "memory");
+          if (tr && i < 16) a.trace[i * 16 + 4] = clock64();
+          l = l * alpha + lsum;
+        } else {
         // first half of the exponentials; packed fp16 pairs overwrite sv[0..BLK/2) in place
 #pragma unroll
         for (int k = 0; k < BLK / 2; k += 2) exp_pair(k);
         if (tr && i < 16) a.trace[i * 16 + 3] = clock64();
         // PV(i-1) has had half a block to finish: start pulling its product O' while the second half
         // of the exponentials is computed
-        uint32_t ro[D];
         if (i > 0) {
           mbar_wait(&o_full[x], (i - 1) & 1);
           tc_fence_after();
@@ -289,6 +337,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 #pragma unroll
         for (int k = BLK / 2; k < BLK; k += 2) exp_pair(k);
         l = l * alpha + (((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7])));
+        }
         if (i > 0) {                               // O <- (O + O'(i-1)) * alpha ; the P region is free again
           tmem_ld_wait();
 #pragma unroll
@@ -327,6 +376,282 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 3) tmem_dealloc(tmem, 512);
+  if (a.trace && threadIdx.x == 0 && cta_lin < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.trace[256 + 3 * cta_lin + 2] = (long long)t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// v6 (d = 32): FOUR query tiles and four softmax warpgroups per CTA.  Measurements behind it
+// (tools/attn_experiments.py, tools/probe/mufu_probe3.cu): the MUFU pipe sustains one exp2 warp
+// instruction per 8.2 clocks with two or more warps feeding it, but a softmax thread's block is a
+// serial chain (barrier wait -> tcgen05.ld -> max -> exponentials -> P store -> arrive) and with only
+// two softmax warps per SM sub-partition their stalls coincide more often than not (v4: 2850 clocks
+// per 2 x 128 x 128 scores against 2112 of MUFU work; staggering or ping-ponging the two recovers a few
+// per cent).  Four warps per sub-partition keep the pipe fed.  To fit four tiles in 512 TMEM columns
+// and 104 registers per softmax thread: 64-key blocks, single S and P buffers per tile, O accumulated
+// in TMEM by the tensor core itself, and lazy rescaling (the reference maximum only moves when a block
+// exceeds it by more than 2^8 -- softmax is shift invariant -- so O is read-modified-written rarely).
+//   20 warps: warp t < 4 = tcgen05.mma issuer of tile t (warp 0 also drives the K/V TMA ring, warp 1
+//   owns the TMEM allocation), warps 4-19 = softmax warpgroups (thread = query row = TMEM lane).
+//   TMEM columns per tile: S (64 fp32) | P (32 = 64 fp16 keys) | O (32).
+template <int POLY>
+__global__ void __launch_bounds__(640, 1)
+attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  constexpr int D = 32, BLK = 64, NT = 4;
+  constexpr int ROWB = D * 2;
+  constexpr int TILE_BYTES = 128 * ROWB;
+  constexpr uint64_t SWZ = SWZ_64B;
+  constexpr uint32_t SBO = 8 * ROWB;
+  constexpr int S = kAttnStages;
+  constexpr uint32_t TM_P = 64, TM_O = 96, TM_STRIDE = 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, kv_full[S], kv_empty[S], s_full[NT], s_free[NT], p_full[NT], o_full[NT];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                              // NT tiles
+  uint8_t* sKV = smem + NT * TILE_BYTES;           // S x (K tile, V tile)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qblk = blockIdx.x, h = blockIdx.y, nb = blockIdx.z;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (a.trace && threadIdx.x == 0 && cta_lin < 1024) {
+    unsigned long long t; unsigned sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    a.trace[256 + 3 * cta_lin] = sm; a.trace[256 + 3 * cta_lin + 1] = (long long)t;
+  }
+  const int q0 = qblk * (128 * NT);
+  const int nq = min(NT, (a.Lq - q0 + 127) / 128);
+  const int n_kv = (a.Lk + 127) / 128;
+  const int n_blk = (a.Lk + BLK - 1) / BLK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < S; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], nq); }
+    for (int x = 0; x < NT; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&s_free[x], 128);
+      mbar_init(&p_full[x], 128);
+      mbar_init(&o_full[x], 1);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const int x = warp;
+    if (lane == 0 && x < nq) {
+      const uint32_t idesc_qk = make_idesc_f16(128, BLK, 0, 0);
+      const uint32_t idesc_pv = make_idesc_f16(128, D, 0, 1);
+      const uint32_t qa = smem_u32(sQ) + x * TILE_BYTES, skv = smem_u32(sKV);
+      const uint32_t tX = tmem + x * TM_STRIDE;
+      // K/V ring, driven by tile 0's issuer between its MMA batches
+      int loaded = 0;
+      auto load_kv = [&](int j) {
+        const int s = j % S;
+        mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+        tma_load_4d(sKV + s * 2 * TILE_BYTES, &mapK, &kv_full[s], 0, h, j * 128, nb * a.kv_batch_mul);
+        tma_load_4d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &mapV, &kv_full[s], 0, h, j * 128, nb * a.kv_batch_mul);
+      };
+      auto pump = [&]() {                          // issue every load whose stage is already free
+        while (loaded < n_kv && mbar_test_wait(&kv_empty[loaded % S], ((loaded / S) & 1) ^ 1)) load_kv(loaded++);
+      };
+      if (x == 0) {
+        mbar_arrive_expect_tx(&q_full, nq * TILE_BYTES);
+        for (int t = 0; t < nq; ++t)
+          tma_load_4d(sQ + t * TILE_BYTES, &mapQ, &q_full, 0, h, q0 + t * 128, nb * a.q_batch_mul);
+        pump();
+      }
+      auto issue_qk = [&](int i) {                 // S = Q K(block i)^T
+        const uint32_t ka = skv + ((i >> 1) % S) * 2 * TILE_BYTES + (i & 1) * BLK * ROWB;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          mma_ss(tX, make_smem_desc(qa + k * 32, 16, SBO, SWZ), make_smem_desc(ka + k * 32, 16, SBO, SWZ),
+                 idesc_qk, k != 0);
+      };
+      auto issue_pv = [&](int i) {                 // O += P(block i) V(block i)
+        const uint32_t va = skv + ((i >> 1) % S) * 2 * TILE_BYTES + TILE_BYTES + (i & 1) * BLK * ROWB;
+#pragma unroll
+        for (int k = 0; k < BLK / 16; ++k)
+          mma_ts(tX + TM_O, tX + TM_P + k * 8, make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv,
+                 (i > 0 || k > 0) ? 1u : 0u);
+      };
+      int tiles_waited = 0;
+      auto need_tile = [&](int t) {
+        while (tiles_waited <= t) {
+          if (x == 0)
+            while (loaded <= tiles_waited) {       // this thread owes the load it is about to wait for
+              mbar_wait(&kv_empty[loaded % S], ((loaded / S) & 1) ^ 1);
+              load_kv(loaded++);
+            }
+          mbar_wait(&kv_full[tiles_waited % S], (tiles_waited / S) & 1);
+          ++tiles_waited;
+        }
+        tc_fence_after();
+      };
+      mbar_wait(&q_full, 0);
+      need_tile(0);
+      issue_qk(0);
+      tc_commit(&s_full[x]);
+      for (int i = 0; i < n_blk; ++i) {
+        if (i + 1 < n_blk) {
+          need_tile((i + 1) >> 1);
+          mbar_wait(&s_free[x], i & 1);            // the softmax warpgroup holds S(i) in registers
+          tc_fence_after();
+          issue_qk(i + 1);
+          tc_commit(&s_full[x]);
+        }
+        if (x == 0) pump();
+        mbar_wait(&p_full[x], i & 1);
+        tc_fence_after();
+        issue_pv(i);
+        tc_commit(&o_full[x]);
+        if ((i & 1) || i + 1 == n_blk) tc_commit(&kv_empty[(i >> 1) % S]);
+        if (x == 0) pump();
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int x = (warp - 4) >> 2;
+    if (x < nq) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t tX = tmem + x * TM_STRIDE + ((uint32_t)(quarter * 32) << 16);
+      const float c = a.scale_log2e;
+      float m = -INFINITY, l = 0.f;
+      const bool tr = a.trace && lane == 0 && cta_lin == 0 && quarter == 0;
+      if (a.stagger > 0 && x > 0) {                // de-phase the warpgroups (see header)
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)a.stagger * x) {}
+      }
+      for (int i = 0; i < n_blk; ++i) {
+        if (tr && i < 16) a.trace[i * 16 + x] = clock64();
+        uint32_t cur[BLK];
+        mbar_wait(&s_full[x], i & 1);
+        tc_fence_after();
+        tmem_ld_x32(tX, *reinterpret_cast<uint32_t(*)[32]>(&cur[0]));
+        tmem_ld_x32(tX + 32, *reinterpret_cast<uint32_t(*)[32]>(&cur[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[x]);
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 4] = clock64();
+        const int valid = a.Lk - i * BLK;
+        if (valid < BLK) {
+#pragma unroll
+          for (int k = 0; k < BLK; ++k)
+            if (k >= valid) cur[k] = 0xff800000u;   // -inf
+        }
+        float m4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m4[k] = fmaxf(__uint_as_float(cur[k]), __uint_as_float(cur[k + 4]));
+#pragma unroll
+        for (int k = 8; k < BLK; k += 8) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            m4[t] = fmaxf(m4[t], fmaxf(__uint_as_float(cur[k + t]), __uint_as_float(cur[k + t + 4])));
+        }
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        bool o_ready = false;                      // has this thread already observed P V(i - 1)?
+        if (__any_sync(0xffffffffu, (mx - m) * c > 8.0f)) {
+          const float m_new = fmaxf(m, mx);
+          const float alpha = fast_exp2((m - m_new) * c);      // first block: exp2(-inf) = 0
+          m = m_new;
+          l *= alpha;
+          if (i > 0) {                             // O <- O * alpha in TMEM
+            mbar_wait(&o_full[x], (i - 1) & 1);
+            tc_fence_after();
+            o_ready = true;
+#pragma unroll
+            for (int d0 = 0; d0 < D; d0 += 16) {
+              uint32_t r[16];
+              tmem_ld_x16(tX + TM_O + d0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 16; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
+              tmem_st_x16(tX + TM_O + d0, r);
+            }
+          }
+        }
+        const float nmc = -m * c;
+        float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < BLK; k += 2) {
+          float x0, x1, p0, p1;
+          ffma2(x0, x1, __uint_as_float(cur[k]), __uint_as_float(cur[k + 1]), c, c, nmc, nmc);
+          if (POLY > 0 && ((k >> 1) % POLY) == POLY - 1) {
+            x0 = fmaxf(x0, -120.f); x1 = fmaxf(x1, -120.f);
+            float t0, t1, n0, n1, f0, f1;
+            fadd2(t0, t1, x0, x1, 12582912.f, 12582912.f);
+            fadd2(n0, n1, t0, t1, -12582912.f, -12582912.f);
+            fadd2(f0, f1, x0, x1, -n0, -n1);
+            ffma2(p0, p1, f0, f1, 0.05517164617776871f, 0.05517164617776871f, 0.2426111251115799f, 0.2426111251115799f);
+            ffma2(p0, p1, p0, p1, f0, f1, 0.6932609677314758f, 0.6932609677314758f);
+            ffma2(p0, p1, p0, p1, f0, f1, 0.9999280571937561f, 0.9999280571937561f);
+            p0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+            p1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+          } else {
+            p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+          }
+          const int j = (k >> 1) & 3;
+          fadd2(ls[2 * j], ls[2 * j + 1], ls[2 * j], ls[2 * j + 1], p0, p1);
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          cur[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 5] = clock64();
+        if (i > 0 && !o_ready) {                   // the P columns were last read by P V(i - 1)
+          mbar_wait(&o_full[x], (i - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_x16(tX + TM_P, *reinterpret_cast<uint32_t(*)[16]>(&cur[0]));
+        tmem_st_x16(tX + TM_P + 16, *reinterpret_cast<uint32_t(*)[16]>(&cur[16]));
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 6] = clock64();
+      }
+      if (tr && x == 0) a.trace[13] = clock64();
+      mbar_wait(&o_full[x], (n_blk - 1) & 1);
+      tc_fence_after();
+      const int qi = q0 + x * 128 + row;
+      const float inv = 1.0f / l;
+      __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h;
+#pragma unroll
+      for (int d0 = 0; d0 < D; d0 += 16) {
+        uint32_t r[16];
+        tmem_ld_x16(tX + TM_O + d0, r);
+        tmem_ld_wait();
+        if (qi < a.Lq) {
+#pragma unroll
+          for (int k = 0; k < 16; k += 8) {
+            __align__(16) __half hh[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(__uint_as_float(r[k + t]) * inv);
+            *reinterpret_cast<uint4*>(op + d0 + k) = *reinterpret_cast<uint4*>(hh);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
   if (a.trace && threadIdx.x == 0 && cta_lin < 1024) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -515,20 +840,36 @@ __global__ void __launch_bounds__(512) attn_small_rows_kernel(const __half* __re
   }
 }
 
-template <int D>
+template <int D, int POLY>
 static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                        int Nb, cudaStream_t st) {
   constexpr int SMEM = (2 + 2 * kAttnStages) * 128 * D * 2 + 1024;
   constexpr int BLK = (D == 32) ? 128 : 64, NSBUF = (D == 32) ? 1 : 2;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel<D, BLK, NSBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd_kernel<D, BLK, NSBUF, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM) != cudaSuccess)
       return GVF_ERR_CUDA;
     configured = true;
   }
   dim3 grid((a.Lq + 255) / 256, a.H, Nb);
-  attn_fwd_kernel<D, BLK, NSBUF><<<grid, 384, SMEM, st>>>(mq, mk, mv, a);
+  attn_fwd_kernel<D, BLK, NSBUF, POLY><<<grid, 384, SMEM, st>>>(mq, mk, mv, a);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+template <int POLY>
+static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
+                        int Nb, cudaStream_t st) {
+  constexpr int SMEM = (4 + 2 * kAttnStages) * 128 * 32 * 2 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_fwd6_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+        cudaSuccess)
+      return GVF_ERR_CUDA;
+    configured = true;
+  }
+  dim3 grid((a.Lq + 511) / 512, a.H, Nb);
+  attn_fwd6_kernel<POLY><<<grid, 640, SMEM, st>>>(mq, mk, mv, a);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -601,7 +942,17 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   a.q_batch_mul = q_shared ? 0 : 1;
   a.kv_batch_mul = kv_shared ? 0 : 1;
   a.scale_log2e = scale * 1.4426950408889634f;
-  a.dbg = g_attn_dbg;
+  a.dbg = g_attn_dbg & 0xff;
+  a.stagger = (g_attn_dbg >> 8) * 100;
   a.trace = g_attn_trace;
-  return D == 32 ? launch_attn<32>(mq, mk, mv, a, Nb, st) : launch_attn<64>(mq, mk, mv, a, Nb, st);
+  // Kernel choice.  d = 32 with more than two query tiles per (batch, head): v6 (four softmax warpgroups, a quarter
+  // of the exponentials on the FMA pipe); otherwise v4 with the MUFU ping-pong.  gvf_attn_set_debug overrides
+  // (tools/attn_experiments.py): 0x10 v4 plain, 0x30 v4 ping-pong, 0x80 v6 MUFU only, low nibble 4 = polynomial share.
+  const int sel = g_attn_dbg & 0xf0;
+  const bool poly = (g_attn_dbg & 0xf) == 4;
+  if (D == 32 && (sel == 0x80 || (sel == 0 && Lq > 256)))
+    return (poly || sel == 0) ? launch_attn6<4>(mq, mk, mv, a, Nb, st) : launch_attn6<0>(mq, mk, mv, a, Nb, st);
+  if (sel == 0) a.dbg |= 0x20;
+  if (D == 64) return launch_attn<64, 0>(mq, mk, mv, a, Nb, st);
+  return poly ? launch_attn<32, 4>(mq, mk, mv, a, Nb, st) : launch_attn<32, 0>(mq, mk, mv, a, Nb, st);
 }

@@ -84,6 +84,33 @@ def test_attention_matches_fp32(Nb, Lq, Lk, H, D):
     _close(o, _ref_attn(q, k, v, scale), 2e-3, "attention")
 
 
+@pytest.mark.parametrize("dbg", [0x10, 0x30, 0x14, 0x80, 0x84])
+def test_attention_kernel_generations(dbg):
+    """every d = 32 kernel variant the dispatcher can pick (v4 plain / MUFU ping-pong / polynomial share, v6
+    MUFU-only / polynomial share), on shapes with 1..4 query tiles, ragged key counts, and scores whose row
+    maximum keeps growing along the keys so that v6's lazy rescale of O in TMEM runs many times"""
+    from gvfdiffusion_b200 import _lib, ops
+    L = _lib.lib()
+    g = _g(dbg)
+    scale = 1.0 / math.sqrt(32)
+    try:
+        L.gvf_attn_set_debug(dbg)
+        for (Nb, Lq, Lk, H) in [(2, 512, 512, 3), (1, 1000, 1370, 2), (2, 300, 200, 2), (1, 130, 4096, 2), (1, 512, 70, 1)]:
+            q = _rand((Nb, Lq, H, 32), g).half()
+            k = _rand((Nb, Lk, H, 32), g).half()
+            v = _rand((Nb, Lk, H, 32), g).half()
+            _close(ops.attention(q, k, v, scale), _ref_attn(q, k, v, scale), 2e-3, f"variant {dbg:#x} {(Nb, Lq, Lk, H)}")
+        # keys whose projection on q grows with the key index: the running maximum rises block after block
+        Nb, Lq, Lk, H = 1, 512, 2048, 2
+        q = (_rand((Nb, Lq, H, 32), g).abs() + 0.5).half()
+        ramp = torch.linspace(-6, 6, Lk, device=DEV)[None, :, None, None]
+        k = (ramp.expand(Nb, Lk, H, 32) + 0.1 * _rand((Nb, Lk, H, 32), g)).half()
+        v = _rand((Nb, Lk, H, 32), g).half()
+        _close(ops.attention(q, k, v, 1.0), _ref_attn(q, k, v, 1.0), 2e-3, f"variant {dbg:#x} growing max")
+    finally:
+        L.gvf_attn_set_debug(0)
+
+
 def test_attention_packed_and_shared_views():
     from gvfdiffusion_b200 import ops
     g = _g(77)
