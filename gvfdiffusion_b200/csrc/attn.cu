@@ -397,7 +397,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 //   20 warps: warp t < 4 = tcgen05.mma issuer of tile t (warp 0 also drives the K/V TMA ring, warp 1
 //   owns the TMEM allocation), warps 4-19 = softmax warpgroups (thread = query row = TMEM lane).
 //   TMEM columns per tile: S (64 fp32) | P (32 = 64 fp16 keys) | O (32).
-template <int POLY>
+template <int POLY, bool TRACE>
 __global__ void __launch_bounds__(640, 1)
 attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
@@ -419,7 +419,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, h = blockIdx.y, nb = blockIdx.z;
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  if (a.trace && threadIdx.x == 0 && cta_lin < 1024) {
+  if (TRACE && a.trace && threadIdx.x == 0 && cta_lin < 1024) {
     unsigned long long t; unsigned sm;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
@@ -454,7 +454,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const uint32_t tmem = tmem_base_s;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     const int x = warp;
     if (lane == 0 && x < nq) {
       const uint32_t idesc_qk = make_idesc_f16(128, BLK, 0, 0);
@@ -527,7 +527,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int x = (warp - 4) >> 2;
     if (x < nq) {
       const int quarter = warp & 3;
@@ -535,21 +535,24 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       const uint32_t tX = tmem + x * TM_STRIDE + ((uint32_t)(quarter * 32) << 16);
       const float c = a.scale_log2e;
       float m = -INFINITY, l = 0.f;
-      const bool tr = a.trace && lane == 0 && cta_lin == 0 && quarter == 0;
-      if (a.stagger > 0 && x > 0) {                // de-phase the warpgroups (see header)
+      // barrier addresses live in registers: the generic->shared conversions were re-done every block
+      const uint32_t b_sfull = smem_u32(&s_full[x]), b_sfree = smem_u32(&s_free[x]);
+      const uint32_t b_pfull = smem_u32(&p_full[x]), b_ofull = smem_u32(&o_full[x]);
+      const bool tr = TRACE && a.trace && lane == 0 && cta_lin == 0 && quarter == 0;
+      if (TRACE && a.stagger > 0 && x > 0) {                // de-phase the warpgroups (see header)
         const long long t0 = clock64();
         while (clock64() - t0 < (long long)a.stagger * x) {}
       }
-      for (int i = 0; i < n_blk; ++i) {
+    for (int i = 0; i < n_blk; ++i) {
         if (tr && i < 16) a.trace[i * 16 + x] = clock64();
         uint32_t cur[BLK];
-        mbar_wait(&s_full[x], i & 1);
+        mbar_wait_u32(b_sfull, i & 1);
         tc_fence_after();
         tmem_ld_x32(tX, *reinterpret_cast<uint32_t(*)[32]>(&cur[0]));
         tmem_ld_x32(tX + 32, *reinterpret_cast<uint32_t(*)[32]>(&cur[32]));
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_free[x]);
+        mbar_arrive_u32(b_sfree);
         if (tr && i < 16 && x == 0) a.trace[i * 16 + 4] = clock64();
         const int valid = a.Lk - i * BLK;
         if (valid < BLK) {
@@ -574,7 +577,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           m = m_new;
           l *= alpha;
           if (i > 0) {                             // O <- O * alpha in TMEM
-            mbar_wait(&o_full[x], (i - 1) & 1);
+            mbar_wait_u32(b_ofull, (i - 1) & 1);
             tc_fence_after();
             o_ready = true;
 #pragma unroll
@@ -589,7 +592,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           }
         }
         const float nmc = -m * c;
-        float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float ls[8];
 #pragma unroll
         for (int k = 0; k < BLK; k += 2) {
           float x0, x1, p0, p1;
@@ -609,25 +612,26 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             p0 = fast_exp2(x0); p1 = fast_exp2(x1);
           }
           const int j = (k >> 1) & 3;
-          fadd2(ls[2 * j], ls[2 * j + 1], ls[2 * j], ls[2 * j + 1], p0, p1);
+          if (k < 8) { ls[2 * j] = p0; ls[2 * j + 1] = p1; }
+          else fadd2(ls[2 * j], ls[2 * j + 1], ls[2 * j], ls[2 * j + 1], p0, p1);
           const __half2 hp = __floats2half2_rn(p0, p1);
           cur[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
         }
         l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
         if (tr && i < 16 && x == 0) a.trace[i * 16 + 5] = clock64();
         if (i > 0 && !o_ready) {                   // the P columns were last read by P V(i - 1)
-          mbar_wait(&o_full[x], (i - 1) & 1);
+          mbar_wait_u32(b_ofull, (i - 1) & 1);
           tc_fence_after();
         }
         tmem_st_x16(tX + TM_P, *reinterpret_cast<uint32_t(*)[16]>(&cur[0]));
         tmem_st_x16(tX + TM_P + 16, *reinterpret_cast<uint32_t(*)[16]>(&cur[16]));
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[x]);
+        mbar_arrive_u32(b_pfull);
         if (tr && i < 16 && x == 0) a.trace[i * 16 + 6] = clock64();
       }
       if (tr && x == 0) a.trace[13] = clock64();
-      mbar_wait(&o_full[x], (n_blk - 1) & 1);
+      mbar_wait_u32(b_ofull, (n_blk - 1) & 1);
       tc_fence_after();
       const int qi = q0 + x * 128 + row;
       const float inv = 1.0f / l;
@@ -652,7 +656,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
-  if (a.trace && threadIdx.x == 0 && cta_lin < 1024) {
+  if (TRACE && a.trace && threadIdx.x == 0 && cta_lin < 1024) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     a.trace[256 + 3 * cta_lin + 2] = (long long)t;
@@ -857,19 +861,19 @@ static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
-template <int POLY>
+template <int POLY, bool TRACE>
 static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                         int Nb, cudaStream_t st) {
   constexpr int SMEM = (4 + 2 * kAttnStages) * 128 * 32 * 2 + 1024;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd6_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+    if (cudaFuncSetAttribute(attn_fwd6_kernel<POLY, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
         cudaSuccess)
       return GVF_ERR_CUDA;
     configured = true;
   }
   dim3 grid((a.Lq + 511) / 512, a.H, Nb);
-  attn_fwd6_kernel<POLY><<<grid, 640, SMEM, st>>>(mq, mk, mv, a);
+  attn_fwd6_kernel<POLY, TRACE><<<grid, 640, SMEM, st>>>(mq, mk, mv, a);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -951,7 +955,14 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   const int sel = g_attn_dbg & 0xf0;
   const bool poly = (g_attn_dbg & 0xf) == 4;
   if (D == 32 && (sel == 0x80 || (sel == 0 && Lq > 256)))
-    return (poly || sel == 0) ? launch_attn6<4>(mq, mk, mv, a, Nb, st) : launch_attn6<0>(mq, mk, mv, a, Nb, st);
+  {
+    if (a.trace || a.stagger > 0)   // instrumented build (tools/attn_experiments.py)
+      return (poly || sel == 0) ? launch_attn6<4, true>(mq, mk, mv, a, Nb, st) : launch_attn6<0, true>(mq, mk, mv, a, Nb, st);
+    const int share = g_attn_dbg & 0xf;   // 4 / 8: every 4th / 8th pair of exponentials on the FMA pipe
+    if (share == 4) return launch_attn6<4, false>(mq, mk, mv, a, Nb, st);
+    if (share == 8) return launch_attn6<8, false>(mq, mk, mv, a, Nb, st);
+    return launch_attn6<0, false>(mq, mk, mv, a, Nb, st);            // default: MUFU only (measured fastest)
+  }
   if (sel == 0) a.dbg |= 0x20;
   if (D == 64) return launch_attn<64, 0>(mq, mk, mv, a, Nb, st);
   return poly ? launch_attn<32, 4>(mq, mk, mv, a, Nb, st) : launch_attn<32, 0>(mq, mk, mv, a, Nb, st);

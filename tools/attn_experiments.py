@@ -15,7 +15,7 @@ def run(): ops.attention(q, kv[:, 0], kv[:, 1], 1 / math.sqrt(D), out=o, kv_shar
 # fp32 reference of the first two frames
 sc = torch.einsum("tnhd,khd->thnk", q[:2].float(), kv[:, 0].float()) / math.sqrt(D)
 ref = torch.einsum("thnk,khd->tnhd", sc.softmax(-1), kv[:, 1].float())
-for dbg, name in [(0x10, "v4 mufu"), (0x14, "v4 1/4 poly"), (0x30, "v4 pingpong"), (1, "v5 mufu"), (0x80, "v6 mufu"), (0x84, "v6 1/4 poly"), (0x80 | (4 << 8), "v6 stagger 400"), (0x84 | (4 << 8), "v6 poly stagger 400"), (0x84 | (8 << 8), "v6 poly stagger 800")]:
+for dbg, name in [(0x30, "v4 pingpong"), (0x81, "v6 mufu"), (0x84, "v6 1/4 poly"), (0x88, "v6 1/8 poly"), (0, "default")]:
     L.gvf_attn_set_debug(dbg)
     for _ in range(3): run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
