@@ -844,6 +844,145 @@ __global__ void __launch_bounds__(512) attn_small_rows_kernel(const __half* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Short-sequence attention, warp-level tensor-core variant (L <= 32, d = 32, heads contiguous): the DiT
+// temporal self-attention at the benchmark shape.  The CUDA-core kernel above spends its time on
+// half->float conversions and shared-memory reads per FMA (48 us for 50 MB of traffic); here one CTA
+// stages the q/k/v rows of HC heads of one sequence with cp.async -- whole (row, HC heads) segments of
+// HC x 64 B, so the strided (B,T,N,C) temporal view is read in 512 B pieces -- and one warp per head runs
+// S = Q K^T and O = P V as mma.sync.m16n8k16 on fragments fetched with ldmatrix (a 128-row tcgen05 tile
+// would be 81 % padding at L = 24; the warp-level MMA shape fits).  Rows are 64 B with a 16 B-chunk XOR
+// swizzle (chunk ^ (row >> 1 & 3)) that makes every ldmatrix phase conflict-free.  Same rounding points
+// as the kernel above: fp32 scores and statistics, P rounded to fp16 for P V, l summed unrounded.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int HC>
+__global__ void __launch_bounds__(HC * 32) attn_small_mma_kernel(const __half* __restrict__ q,
+                                                                 const __half* __restrict__ k,
+                                                                 const __half* __restrict__ v, __half* __restrict__ o,
+                                                                 int L, long long sb, long long sl, long long osb,
+                                                                 long long osl, float scale_log2e) {
+  extern __shared__ uint4 sm4[];                    // [HC][3 (q,k,v)][32 rows][4 chunks of 16 B]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hb = blockIdx.x * HC;
+  const long long nb = blockIdx.y;
+  const uint32_t sbase = smem_u32(sm4);
+  auto slot = [](int hs, int ts, int row, int chunk) { return ((hs * 3 + ts) * 32 + row) * 4 + (chunk ^ ((row >> 1) & 3)); };
+  // ---- stage: (tensor, row) segments of HC x 64 B contiguous in global memory
+  const int per_t = L * HC * 4;
+  for (int idx = tid; idx < 3 * per_t; idx += HC * 32) {
+    const int ts = idx / per_t, r0 = idx - ts * per_t;
+    const int t = r0 / (HC * 4), r1 = r0 - t * (HC * 4);
+    const int hs = r1 >> 2, c = r1 & 3;
+    const __half* src = (ts == 0 ? q : ts == 1 ? k : v) + nb * sb + (long long)t * sl + (hb + hs) * 32 + c * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + slot(hs, ts, t, c) * 16), "l"(src) : "memory");
+  }
+  for (int idx = tid; idx < 3 * (32 - L) * HC * 4; idx += HC * 32) {    // zero the padding rows (0 x garbage = NaN)
+    const int c = idx & 3, hs = (idx >> 2) % HC, r = (idx >> 2) / HC;
+    const int ts = r / (32 - L), t = L + r - ts * (32 - L);
+    sm4[slot(hs, ts, t, c)] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int hs = warp, g = lane >> 2, tg = lane & 3;
+  const int n_mt = (L + 15) >> 4;
+  for (int mt = 0; mt < n_mt; ++mt) {
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      ldsm_x4(qa[ks], sbase + slot(hs, 0, 16 * mt + (lane & 15), 2 * ks + (lane >> 4)) * 16);
+    float sc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t kb[4];
+      ldsm_x4(kb, sbase + slot(hs, 1, 8 * nt + (lane & 7), lane >> 3) * 16);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+      mma_16816(sc[nt], qa[0], kb[0], kb[1]);
+      mma_16816(sc[nt], qa[1], kb[2], kb[3]);
+    }
+    // rows g (e = 0,1) and g + 8 (e = 2,3) of this 16-row tile; columns 8 nt + 2 tg + (e & 1)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = 8 * nt + 2 * tg + (e & 1);
+        sc[nt][e] = (col < L) ? sc[nt][e] * scale_log2e : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], sc[nt][e]);
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float l[2] = {0.f, 0.f};
+    uint32_t pa[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float p[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        p[e] = fast_exp2(sc[nt][e] - mx[e >> 1]);
+        l[e >> 1] += p[e];
+      }
+      const __half2 lo = __floats2half2_rn(p[0], p[1]), hi = __floats2half2_rn(p[2], p[3]);
+      pa[nt >> 1][(nt & 1) * 2] = *reinterpret_cast<const uint32_t*>(&lo);        // a0 / a2: row g
+      pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);    // a1 / a3: row g + 8
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    float oc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oc[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t vb[4];
+        ldsm_x4_t(vb, sbase + slot(hs, 2, 16 * ks + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * c2 + (lane >> 4)) * 16);
+        mma_16816(oc[2 * c2], pa[ks], vb[0], vb[1]);
+        mma_16816(oc[2 * c2 + 1], pa[ks], vb[2], vb[3]);
+      }
+    // park the output rows in this head's own q slot (its fragments are already in registers)
+    __syncwarp();
+    const float inv[2] = {1.0f / l[0], 1.0f / l[1]};
+    __half* sq = reinterpret_cast<__half*>(sm4);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = 16 * mt + g + 8 * r;
+        *reinterpret_cast<__half2*>(sq + slot(hs, 0, row, nt) * 8 + 2 * tg) =
+            __floats2half2_rn(oc[nt][2 * r] * inv[r], oc[nt][2 * r + 1] * inv[r]);
+      }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < per_t; idx += HC * 32) {
+    const int t = idx / (HC * 4), r1 = idx - t * (HC * 4);
+    const int h2 = r1 >> 2, c = r1 & 3;
+    *reinterpret_cast<uint4*>(o + nb * osb + (long long)t * osl + (hb + h2) * 32 + c * 8) = sm4[slot(h2, 0, t, c)];
+  }
+}
+
 template <int D, int POLY>
 static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                        int Nb, cudaStream_t st) {
@@ -905,6 +1044,20 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   if (D == 32 && Lq <= 32 && Lk == Lq && !q_shared && !kv_shared && q_strides[0] == k_strides[0] &&
       q_strides[1] == k_strides[1] && q_strides[2] == k_strides[2] && q_strides[0] == v_strides[0] &&
       q_strides[1] == v_strides[1] && q_strides[2] == v_strides[2]) {
+    if ((g_attn_dbg & 0xf0) != 0x40 && q_strides[2] == D && o_strides[2] == D && H % 8 == 0) {
+      // heads contiguous: warp-level tensor-core variant (one CTA = 8 heads of one sequence)
+      constexpr int HC = 8, SMEM = HC * 3 * 32 * 64;
+      static bool configured_mma = false;
+      if (!configured_mma) {
+        if (cudaFuncSetAttribute(attn_small_mma_kernel<HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+            cudaSuccess) return GVF_ERR_CUDA;
+        configured_mma = true;
+      }
+      attn_small_mma_kernel<HC><<<dim3(H / HC, Nb), HC * 32, SMEM, st>>>(
+          (const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, Lq, q_strides[0], q_strides[1],
+          o_strides[0], o_strides[1], scale * 1.4426950408889634f);
+      return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+    }
     if (g_small_rows && q_strides[2] == D && o_strides[2] == D && H <= 16) {
       // heads contiguous: row-staged variant (coalesced even for the strided temporal view)
       const int smem = 3 * Lq * H * D * 2;

@@ -141,6 +141,32 @@ def test_attention_packed_and_shared_views():
     _close(out.permute(1, 0, 2, 3), _ref_attn(qt, kt, vt, scale), 2e-3, "temporal view")
 
 
+@pytest.mark.parametrize("T,H", [(24, 16), (32, 8), (5, 8), (17, 16), (16, 8)])
+def test_attention_short_sequences_mma(T, H):
+    """L <= 32 with contiguous heads, H % 8 == 0: the warp-level mma.sync kernel (DiT temporal attention),
+    on the strided (T, N, 3, H, d) -> (N, T, ...) view and on a plain contiguous batch; the CUDA-core kernel
+    (debug switch 0x40) must agree with it."""
+    from gvfdiffusion_b200 import _lib, ops
+    g = _g(1000 + T + H)
+    D, Nt = 32, 37
+    scale = 1.0 / math.sqrt(D)
+    x = (_rand((T, Nt, 3, H, D), g) * 1.5).half()
+    qt, kt, vt = x.permute(1, 0, 2, 3, 4).unbind(2)
+    out = torch.empty((T, Nt, H, D), dtype=torch.float16, device=DEV)
+    ops.attention(qt, kt, vt, scale, out=out.permute(1, 0, 2, 3))
+    ref = _ref_attn(qt, kt, vt, scale)
+    _close(out.permute(1, 0, 2, 3), ref, 2e-3, "temporal view (mma)")
+    qc, kc, vc = (t.contiguous() for t in (qt, kt, vt))
+    _close(ops.attention(qc, kc, vc, scale), ref, 2e-3, "contiguous (mma)")
+    L = _lib.lib()
+    L.gvf_attn_set_debug(0x40)
+    try:
+        old = ops.attention(qc, kc, vc, scale)
+    finally:
+        L.gvf_attn_set_debug(0)
+    _close(old, ref, 2e-3, "contiguous (cuda cores)")
+
+
 @pytest.mark.parametrize("C,dt", [(512, torch.float32), (768, torch.float16), (64, torch.float32), (384, torch.float16)])
 def test_ln_mod(C, dt):
     from gvfdiffusion_b200 import ops
