@@ -44,6 +44,17 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + t);
 }
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
+// One MUFU instead of two: tanh.approx.f32 (relative error 2^-11, i.e. at most half an fp16 ulp of the
+// result, which is rounded to fp16 right after).  The 128 x 256 GELU tile costs 2 x 128 x 256 / 16 = 4096
+// MUFU clocks with exp + reciprocal -- as long as its whole main loop at K = 512.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float u = x * fmaf(k0k1, x * x, k0);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
 
 constexpr int kEpiCols = 64;                 // columns per epilogue chunk (default)
 constexpr int kStgLd = kEpiCols + 1;         // padded row of the per-warp staging tile (floats)
@@ -365,6 +376,289 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   if (warp == 2) tmem_dealloc(tmem, 2 * BN);
 }
 
+// ---------------------------------------------------------------------------------------
+// Persistent kernel, generation 2: the epilogue no longer bounds the short-K shapes.
+// Measured on the generation above (tools/gemm_bench.py): qkv N=1536 K=512 ran 40 us against 8 us of
+// tensor time -- four epilogue warps, one per SM sub-partition, walking every accumulator element through a
+// scalar shared-memory transpose (~2000 dependent instructions per thread and 128 x 256 tile).  Here
+//   * eight epilogue warps (two per TMEM lane quarter, each owning half of the tile's columns),
+//   * thread = row keeps its values in registers, packs them and writes 16 B pieces into a SWIZZLE_128B
+//     staging tile (32 rows x 128 B per warp, two buffers),
+//   * one lane per warp hands the tile to the TMA unit (cp.async.bulk.tensor store, bulk groups), which
+//     also clips the M / N edges,
+//   * the fp32 / fp16 residual of the read-modify-write epilogues is fetched with 16 B loads issued before
+//     the accumulator wait, so its DRAM latency overlaps the main loop of the tile.
+// Same rounding points as epilogue_tile() above.  320 threads: warp 0 TMA producer, warp 1 MMA issuer,
+// warps 2-9 epilogue; accumulators double buffered in TMEM (2 x BN columns).
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(320, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+               const __grid_constant__ CUtensorMap mapO, int M, int N, int K, GemmEpi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[2][BN];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = BN * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;              // 8 warps x 2 buffers x 4 KB, 1 KB aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (K + kBK - 1) / kBK;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + kBM - 1) / kBM;
+  const int num_tiles = tiles_n * tiles_m;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapO);
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_s, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+          tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM, BN, 0, 0);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tempty_bar[acc], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), w0 = a0 + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            mma_ss(tmem + acc * BN, make_smem_desc(a0 + k * 32, 16, 1024, SWZ_128B),
+                   make_smem_desc(w0 + k * 32, 16, 1024, SWZ_128B), idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;                       // 0..7
+    const int q = warp & 3;                        // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                      // which half of the tile's columns
+    constexpr int HALF = BN / 2;
+    const int et = threadIdx.x - 64;               // 0..255
+    constexpr int mode = MODE;
+    constexpr bool out16 = (mode == 0 || mode == 1 || mode == 3 || mode == 6);
+    uint8_t* stg = stg_base + ew * 2 * 4096;
+    const uint32_t sw = (uint32_t)(lane & 7);      // SWIZZLE_128B: 16 B piece j of row r sits at j ^ (r & 7)
+    int lt = 0, sbuf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+      const int acc = lt & 1;
+      float* sb = s_bias[acc];
+      for (int c = et; c < BN; c += 256) {
+        const int col = tile_n * BN + c;
+        sb[c] = (ep.bias && col < N) ? __ldg(ep.bias + col) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int row0 = tile_m * kBM + q * 32, row = row0 + lane;
+      const bool row_ok = row < M;
+      const int colh = tile_n * BN + half * HALF;   // first column of this warp's half
+      const uint32_t tacc = tmem + acc * BN + half * HALF + ((uint32_t)(q * 32) << 16);
+      if constexpr (out16) {
+        // ---------------- fp16 outputs: 64-column chunks (128 B rows)
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF; c0 += 64) {
+          const int col0 = colh + c0;
+          uint4 old[8];
+          if (mode == 3) {                          // residual rows first: latency overlaps the accumulator wait
+            const __half* orow = reinterpret_cast<const __half*>(ep.out) + (size_t)row * ep.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              old[j] = (row_ok && col0 + 8 * j < N) ? *reinterpret_cast<const uint4*>(orow + 8 * j)
+                                                    : make_uint4(0u, 0u, 0u, 0u);
+          }
+          if (c0 == 0) {
+            mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
+            tc_fence_after();
+          }
+          float v[64];
+          {
+            uint32_t rr[64];
+            tmem_ld_x32(tacc + c0, *reinterpret_cast<uint32_t(*)[32]>(&rr[0]));
+            tmem_ld_x32(tacc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rr[32]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(rr[j]) + sb[half * HALF + c0 + j];
+          }
+          if (mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_fast(r16(v[j]));
+          } else if (mode == 6) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int hc = col0 + hh * 32;
+              if (hc < ep.norm_cols) {
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { v[hh * 32 + j] = r16(v[hh * 32 + j]); ss += v[hh * 32 + j] * v[hh * 32 + j]; }
+                const float inv = 5.656854249492381f / fmaxf(sqrtf(ss), 1e-12f);
+                const int half_cols = ep.norm_cols >> 1;
+                const float* gm = (hc < half_cols) ? ep.gamma_q + hc : ep.gamma_k + (hc - half_cols);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[hh * 32 + j] = v[hh * 32 + j] * inv * __ldg(gm + j);
+              }
+            }
+          } else if (mode == 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __half2* o2 = reinterpret_cast<const __half2*>(&old[j]);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                v[8 * j + 2 * t] = r16(v[8 * j + 2 * t]) + __low2float(o2[t]);
+                v[8 * j + 2 * t + 1] = r16(v[8 * j + 2 * t + 1]) + __high2float(o2[t]);
+              }
+            }
+          }
+          if (lane == 0) tma_store_wait_read<1>();   // the buffer written two chunks ago has been read out
+          __syncwarp();
+          uint8_t* buf = stg + sbuf * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const __half2 h2 = __floats2half2_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
+              pw[t] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(buf + ((j ^ sw) << 4)) = pk;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && col0 < N && row0 < M) {
+            tma_store_2d(&mapO, stg + sbuf * 4096, col0, row0);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        }
+      } else {
+        // ---------------- fp32 outputs: 32-column chunks (128 B rows)
+        float g[32];
+        bool have_gate = false;
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
+          const int col0 = colh + c0;
+          float4 x[8];
+          if (mode == 2) {
+            const float* orow = reinterpret_cast<const float*>(ep.out) + (size_t)row * ep.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              x[j] = (row_ok && col0 + 4 * j < N) ? *reinterpret_cast<const float4*>(orow + 4 * j)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            have_gate = ep.gate != nullptr;
+            if (have_gate) {
+              const __half* gp = ep.gate + (size_t)((row_ok ? row : 0) / ep.rows_per_batch) * ep.gate_stride + col0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 gg = make_uint4(0u, 0u, 0u, 0u);
+                if (col0 + 8 * j < N) gg = *reinterpret_cast<const uint4*>(gp + 8 * j);
+                const __half2* g2 = reinterpret_cast<const __half2*>(&gg);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { g[8 * j + 2 * t] = __low2float(g2[t]); g[8 * j + 2 * t + 1] = __high2float(g2[t]); }
+              }
+            }
+          }
+          if (c0 == 0) {
+            mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
+            tc_fence_after();
+          }
+          float v[32];
+          {
+            uint32_t rr[32];
+            tmem_ld_x32(tacc + c0, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + sb[half * HALF + c0 + j];
+          }
+          if (mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float* xf = reinterpret_cast<float*>(&x[j]);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float h = r16(v[4 * j + t]);
+                if (have_gate) h = r16(h * g[4 * j + t]);
+                v[4 * j + t] = xf[t] + h;
+              }
+            }
+          }
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* buf = stg + sbuf * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(buf + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && col0 < N && row0 < M) {
+            tma_store_2d(&mapO, stg + sbuf * 4096, col0, row0);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 2 * BN);
+}
+
+template <int BN, int STAGES, int MODE>
+static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CUtensorMap& mO, int M, int N, int K,
+                          const GemmEpi& ep, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 8 * 2 * 4096 + 1024;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+        cudaSuccess)
+      return GVF_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int tiles = ((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_ws_kernel<BN, STAGES, MODE><<<grid, 320, SMEM, st>>>(mA, mW, mO, M, N, K, ep);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
 template <int BN, int STAGES>
 static int launch_gemm_persistent(const CUtensorMap& mA, const CUtensorMap& mW, int M, int N, int K,
                                   const GemmEpi& ep, cudaStream_t st) {
@@ -425,15 +719,17 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   //          3 = one tile per CTA, 3 CTAs / SM, 2 stages, 32-column epilogue chunks
   int variant = g_gemm_variant;
   if (variant < 0) {
-    // measured on B200 (tools/gemm_bench.py, profiles/): 128x256 persistent tiles win once there are at
-    // least two full waves of them and the main loop is long (K >= 768: the VAE shapes) or N = 3C (qkv);
-    // the short-K DiT GEMMs are latency-bound and do best with independent CTAs sharing an SM -- three
-    // of them (variant 3) whenever the epilogue is the light one (no per-head RMS norm)
-    const long long tiles256 = (long long)((M + kBM - 1) / kBM) * ((N + 255) / 256);
-    variant = (N % 256 == 0 && tiles256 >= 296 && (K >= 768 || N % 768 == 0)) ? 2
-              : (N <= 2048 && K <= 2048) ? 3 : 0;
+    // measured on B200 (tools/gemm_bench.py, profiles/r01_gemm_variants.txt): the generation-2 kernels win on
+    // every shape of the path; 128 x 256 tiles whenever N allows them and there is more than one column of
+    // tiles per row block to amortise the wider epilogue (N >= 768), or the epilogue is a plain fp16 store
+    variant = (N % 256 == 0 && (N >= 768 || epilogue == 0 || epilogue == 1)) ? 5 : 4;
   }
-  const int BN = (variant == 2) ? 256 : 128;
+  // generation-2 kernels need a TMA-storable output (16 B aligned rows) and do not do the compact mode 5
+  if ((variant == 4 || variant == 5) &&
+      (epilogue == 5 || (ldo * ((epilogue == 2 || epilogue == 4) ? 4 : 2)) % 16 != 0 ||
+       (gate && ((gate_stride % 8) || ((uintptr_t)gate & 15)))))
+    variant = 0;
+  const int BN = (variant == 2 || variant == 5) ? 256 : 128;
   CUtensorMap mA, mW;
   const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {1, (uint64_t)lda};
   const uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}, sW[2] = {1, (uint64_t)ldw};
@@ -445,6 +741,22 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   ep.gate_stride = gate_stride; ep.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   ep.ldo = ldo;
   ep.gamma_q = gamma_q; ep.gamma_k = gamma_k; ep.norm_cols = norm_cols;
+  if (variant == 4 || variant == 5) {
+    const bool out16 = (epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6);
+    CUtensorMap mO;
+    if (!make_tmap_2d(&mO, out, out16 ? 2 : 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, out16 ? 64 : 32, 32))
+      return GVF_ERR_CUDA;
+    cudaStream_t cs = (cudaStream_t)stream;
+#define GVF_WS(MODE)                                                                    \
+    case MODE:                                                                          \
+      return variant == 5 ? launch_gemm_ws<256, 3, MODE>(mA, mW, mO, M, N, K, ep, cs)   \
+                          : launch_gemm_ws<128, 4, MODE>(mA, mW, mO, M, N, K, ep, cs);
+    switch (epilogue) {
+      GVF_WS(0) GVF_WS(1) GVF_WS(2) GVF_WS(3) GVF_WS(4) GVF_WS(6)
+      default: return GVF_ERR_INVALID;
+    }
+#undef GVF_WS
+  }
   if (variant == 2) return launch_gemm_persistent<256, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
   if (variant == 1) return launch_gemm_persistent<128, 4>(mA, mW, M, N, K, ep, (cudaStream_t)stream);
   if (variant == 3) return launch_gemm<128, 2, 32, 3>(mA, mW, M, N, K, ep, (cudaStream_t)stream);   // 3 CTAs / SM

@@ -49,4 +49,16 @@ inline bool make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// row-major 2-D tensor of 2-byte (fp16) or 4-byte (fp32) elements, SWIZZLE_128B boxes (epilogue TMA stores)
+inline bool make_tmap_2d(CUtensorMap* m, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                         uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t d[2] = {cols, rows}, s[1] = {ld_elems * (uint64_t)elem_bytes};
+  cuuint32_t b[2] = {box_cols, box_rows}, e[2] = {1, 1};
+  return fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+            const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace gvf

@@ -300,6 +300,55 @@ def test_gemm_ragged_rows_and_multi_batch_gate():
     _close(o14, lin[:, :14], 1e-3, "compact")
 
 
+@pytest.mark.parametrize("variant", [4, 5])
+def test_gemm_tma_epilogue_all_modes(variant):
+    """Generation-2 kernels (eight epilogue warps, TMA stores): every fused epilogue, ragged M / N / K,
+    gates spanning several batches inside one tile."""
+    from gvfdiffusion_b200 import _lib, ops
+    L = _lib.lib()
+    g = _g(200 + variant)
+    try:
+        L.gvf_gemm_set_variant(variant)
+        for (M, N, K, rpb) in [(12288, 512, 512, 12288), (1000, 1536, 512, 250), (300, 264, 136, 50), (640, 768, 3072, 640)]:
+            a = _rand((M, K), g).half()
+            w = _rand((N, K), g, 0.05).half()
+            b = _rand((N,), g, 0.1)
+            lin = a.float() @ w.float().T + b
+            lin16 = lin.half().float()
+            tag = f"variant {variant} {M}x{N}x{K}"
+            _close(ops.gemm(a, w, b, ops.EPI_F16), lin, 2e-3, tag + " f16")
+            _close(ops.gemm(a, w, b, ops.EPI_F32), lin, 1e-3, tag + " f32")
+            _close(ops.gemm(a, w, b, ops.EPI_GELU_F16), F.gelu(lin16, approximate="tanh"), 2e-3, tag + " gelu")
+            x = _rand((M, N), g)
+            out = x.clone()
+            ops.gemm(a, w, b, ops.EPI_RESID_F32, out=out)
+            _close(out, x + lin16, 1e-3, tag + " resid")
+            nb = (M + rpb - 1) // rpb
+            gate = _rand((nb, N), g).half()
+            out = x.clone()
+            ops.gemm(a, w, b, ops.EPI_RESID_F32, out=out, gate=gate, gate_stride=N, rows_per_batch=rpb)
+            _close(out, x + (lin16 * gate.float().repeat_interleave(rpb, 0)[:M]).half().float(), 1e-3, tag + " gate")
+            x16 = _rand((M, N), g).half()
+            out16 = x16.clone()
+            ops.gemm(a, w, b, ops.EPI_RESID_F16, out=out16)
+            _close(out16, x16.float() + lin16, 2e-3, tag + " resid16")
+        # fused q/k RMS norm (DiT head layout)
+        M, C, H, D = 700, 256, 8, 32
+        a = _rand((M, C), g).half()
+        w = _rand((3 * C, C), g, 0.05).half()
+        b = _rand((3 * C,), g, 0.1)
+        gq, gk = _rand((H, D), g) + 1, _rand((H, D), g) + 1
+        out = torch.empty((M, 3 * C), dtype=torch.float16, device=DEV)
+        ops.gemm_qkv_rmsnorm(a, w, b, gq, gk, out)
+        lin = (a.float() @ w.float().T + b).half().float().reshape(M, 3, H, D)
+        o = out.float().reshape(M, 3, H, D)
+        _close(o[:, 0], F.normalize(lin[:, 0], dim=-1) * gq * D ** 0.5, 2e-3, "q")
+        _close(o[:, 1], F.normalize(lin[:, 1], dim=-1) * gk * D ** 0.5, 2e-3, "k")
+        _close(o[:, 2], lin[:, 2], 1e-3, "v")
+    finally:
+        L.gvf_gemm_set_variant(-1)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_gemm_scheduling_variants(variant):
     from gvfdiffusion_b200 import _lib, ops

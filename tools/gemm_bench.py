@@ -20,7 +20,7 @@ for name, N, K, kind in shapes:
     o16 = torch.empty(M, N, dtype=torch.float16, device=dev)
     gq = torch.ones(N // 96, 32, device=dev) if kind == "qkv" else None
     res = []
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4, 5):
         L.gvf_gemm_set_variant(variant)
         def run():
             if kind == "qkv": ops.gemm_qkv_rmsnorm(a, w, b, gq, gq, o16)
@@ -42,6 +42,14 @@ for name, N, K, kind in shapes:
         for _ in range(20): run()
         e1.record(); torch.cuda.synchronize()
         res.append((ts[len(ts) // 2] * 1e3, e0.elapsed_time(e1) / 20 * 1e3))
+    # cuBLAS reference point (library GEMM + bias only, no fused epilogue): what a stock fp16 nn.Linear costs
+    bh = b.half()
+    for _ in range(3): torch.nn.functional.linear(a, w, bh)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): torch.nn.functional.linear(a, w, bh)
+    e1.record(); torch.cuda.synchronize()
+    cublas_us = e0.elapsed_time(e1) / 20 * 1e3
     fl = 2 * M * N * K
-    print(f"{name:12s} N={N:5d} K={K:5d} " + "  ".join(f"v{v}: cold {c:6.1f}us warm {wm:6.1f}us ({fl / wm / 1e6:6.0f} TF/s)" for v, (c, wm) in enumerate(res)))
+    print(f"{name:12s} N={N:5d} K={K:5d} " + "  ".join(f"v{v}: cold {c:6.1f}us warm {wm:6.1f}us ({fl / wm / 1e6:6.0f} TF/s)" for v, (c, wm) in enumerate(res)) + f"  cuBLAS linear warm {cublas_us:6.1f}us ({fl / cublas_us / 1e6:6.0f} TF/s)")
 L.gvf_gemm_set_variant(-1)
