@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pdl", action="store_true", help="launch with the programmatic-dependent-launch attribute (A/B; default off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -222,8 +223,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    from gvfdiffusion_b200 import ops
+    from gvfdiffusion_b200 import _lib, ops
     from gvfdiffusion_b200.pipeline import GVFPipeline
+    if args.pdl:
+        _lib.lib().gvf_set_pdl(1)
 
     dit, vae = build_models(dev, seed=0)                      # replicated weights
     pipe = GVFPipeline(dit, vae, reference_betas(), device=dev, resolution=RES)

@@ -47,6 +47,7 @@ _SIGS = {
     "gvf_attn_set_debug": (None, [C.c_int]),
     "gvf_attn_set_trace": (None, [_P]),
     "gvf_gemm_set_variant": (None, [C.c_int]),
+    "gvf_set_pdl": (None, [C.c_int]),
     "gvf_small_linear": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "gvf_ln_mod_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gvf_rmsnorm_heads_f16": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -28,6 +28,7 @@
 #include "../../include/gvf_b200.h"
 #include "tc_common.cuh"
 #include "tma_host.h"
+#include "launch.h"
 
 namespace gvf {
 using namespace tc;
@@ -451,6 +452,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = tmem_base_s;
 
   if (warp < 4) {
@@ -653,6 +655,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       }
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
@@ -879,6 +882,7 @@ __global__ void __launch_bounds__(HC * 32) attn_small_mma_kernel(const __half* _
   const int hb = blockIdx.x * HC;
   const long long nb = blockIdx.y;
   const uint32_t sbase = smem_u32(sm4);
+  pdl_wait();
   auto slot = [](int hs, int ts, int row, int chunk) { return ((hs * 3 + ts) * 32 + row) * 4 + (chunk ^ ((row >> 1) & 3)); };
   // ---- stage: (tensor, row) segments of HC x 64 B contiguous in global memory
   const int per_t = L * HC * 4;
@@ -975,6 +979,7 @@ __global__ void __launch_bounds__(HC * 32) attn_small_mma_kernel(const __half* _
             __floats2half2_rn(oc[nt][2 * r] * inv[r], oc[nt][2 * r + 1] * inv[r]);
       }
   }
+  pdl_launch_dependents();
   __syncthreads();
   for (int idx = tid; idx < per_t; idx += HC * 32) {
     const int t = idx / (HC * 4), r1 = idx - t * (HC * 4);
@@ -1012,8 +1017,8 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
     configured = true;
   }
   dim3 grid((a.Lq + 511) / 512, a.H, Nb);
-  attn_fwd6_kernel<POLY, TRACE><<<grid, 640, SMEM, st>>>(mq, mk, mv, a);
-  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+  return launch_pdl(attn_fwd6_kernel<POLY, TRACE>, grid, dim3(640), SMEM, st, mq, mk, mv, a) == cudaSuccess ? GVF_OK
+                                                                                                   : GVF_ERR_CUDA;
 }
 
 }  // namespace gvf
@@ -1053,10 +1058,10 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
             cudaSuccess) return GVF_ERR_CUDA;
         configured_mma = true;
       }
-      attn_small_mma_kernel<HC><<<dim3(H / HC, Nb), HC * 32, SMEM, st>>>(
-          (const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, Lq, q_strides[0], q_strides[1],
-          o_strides[0], o_strides[1], scale * 1.4426950408889634f);
-      return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+      return launch_pdl(attn_small_mma_kernel<HC>, dim3(H / HC, Nb), dim3(HC * 32), SMEM, st, (const __half*)q,
+                        (const __half*)k, (const __half*)v, (__half*)o, Lq, (long long)q_strides[0],
+                        (long long)q_strides[1], (long long)o_strides[0], (long long)o_strides[1],
+                        scale * 1.4426950408889634f) == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
     }
     if (g_small_rows && q_strides[2] == D && o_strides[2] == D && H <= 16) {
       // heads contiguous: row-staged variant (coalesced even for the strided temporal view)

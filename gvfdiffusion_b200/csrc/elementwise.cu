@@ -11,6 +11,8 @@
 #include <stdint.h>
 
 #include "../../include/gvf_b200.h"
+#include "launch.h"
+#include "tc_common.cuh"
 
 namespace gvf {
 
@@ -36,6 +38,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const TIn* __restrict__ x, 
   constexpr int PER = C / 32;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  tc::pdl_wait();
   if (row >= M) return;
   float v[PER];
   const TIn* xr = x + (size_t)row * C;
@@ -475,9 +478,8 @@ GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C,
   const int rpb = rows_per_batch > 0 ? rows_per_batch : M;
   const dim3 grid((M + 7) / 8);
 #define LN_CASE(T, CC, V)                                                                          \
-  ln_mod_kernel<T, CC, V><<<grid, 256, 0, ST(stream)>>>((const T*)x, (__half*)out, M, eps, w, b,    \
-                                                        (const __half*)shift, (const __half*)scale, \
-                                                        mod_stride, rpb)
+  launch_pdl(ln_mod_kernel<T, CC, V>, grid, dim3(256), 0, ST(stream), (const T*)x, (__half*)out, M, eps, w, b, \
+             (const __half*)shift, (const __half*)scale, mod_stride, rpb)
 #define LN_BOTH(CC, V)                       \
   if (C == CC) {                             \
     if (x_is_f16) LN_CASE(__half, CC, V);    \

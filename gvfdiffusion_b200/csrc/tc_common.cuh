@@ -18,6 +18,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel on the stream (if it was launched with the programmatic-serialization
+// attribute) may be scheduled once every CTA of this grid has got here or exited; wait: returns when all
+// prerequisite grids have completed and their writes are visible (a no-op for a normally launched kernel).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -173,6 +173,11 @@ GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, 
  * CTA, 1 persistent 128x128, 2 persistent 128x256 with a double-buffered TMEM accumulator). */
 GVF_API void gvf_gemm_set_variant(int v);
 
+/* Programmatic dependent launch for the GEMM / attention / LayerNorm kernels (default OFF: measured slower
+ * under CUDA-graph replay, see csrc/launch.h): the next kernel's prologue overlaps the previous grid's drain;
+ * data dependences are unchanged (griddepcontrol.wait before the first global access). */
+GVF_API void gvf_set_pdl(int on);
+
 /* Self-attention QKV projection with MultiHeadRMSNorm fused into the epilogue (reference
  * model/attention/modules.py:113-125): out fp16 [M,N]; columns [0, norm_cols) are 32-wide heads,
  * the first half normalised with gamma_q [norm_cols/64, 32], the second half with gamma_k;
