@@ -117,7 +117,22 @@ cudaError_t launch_scan(int n, const RasterWs& ws, cudaStream_t st) {
 }
 
 // Scatter: one thread per (frame, Gaussian); slots inside a tile's segment are claimed by
-// counting tile_count back down to zero (which also leaves tile_count cleared).
+// counting tile_count back down to zero (which also leaves tile_count cleared).  Each claim is an
+// atomic round trip (~700 clocks), so a splat covering hundreds of tiles used to keep one lane -- and its
+// warp -- busy for hundreds of round trips (447 us at the benchmark scene, most of it that tail): rectangles
+// of more than kScatterSmall tiles are now spread over the 32 lanes of the warp, one after the other.
+constexpr int kScatterSmall = 8;
+
+__device__ __forceinline__ void scatter_one(size_t t, unsigned long long key, uint32_t* __restrict__ tile_count,
+                                            const uint32_t* __restrict__ tile_start,
+                                            unsigned long long* __restrict__ keys, long long cap,
+                                            uint32_t* __restrict__ status) {
+  const uint32_t slot = atomicSub(tile_count + t, 1u) - 1u;
+  const long long pos = (long long)tile_start[t] + slot;
+  if (pos < cap) keys[pos] = key;
+  else status[1] = 1u;
+}
+
 __global__ void __launch_bounds__(256) scatter_kernel(int F, int P, int gx, int gy,
                                                       const float4* __restrict__ splat,
                                                       const ushort4* __restrict__ rect,
@@ -126,22 +141,37 @@ __global__ void __launch_bounds__(256) scatter_kernel(int F, int P, int gx, int 
                                                       unsigned long long* __restrict__ keys,
                                                       long long cap, uint32_t* __restrict__ status) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)F * P) return;
-  const ushort4 r = rect[gid];
-  if (r.x >= r.z || r.y >= r.w) return;
-  const int f = (int)(gid / P);
-  const uint32_t i = (uint32_t)(gid - (long long)f * P);
-  const float depth = splat[gid * 3 + 2].y;
-  const unsigned long long key = ((unsigned long long)__float_as_uint(depth) << 32) | i;
-  const size_t tb = (size_t)f * gx * gy;
-  for (int y = r.y; y < r.w; ++y)
-    for (int x = r.x; x < r.z; ++x) {
-      const size_t t = tb + (size_t)y * gx + x;
-      const uint32_t slot = atomicSub(tile_count + t, 1u) - 1u;
-      const long long pos = (long long)tile_start[t] + slot;
-      if (pos < cap) keys[pos] = key;
-      else status[1] = 1u;
+  const int lane = threadIdx.x & 31;
+  int rx = 0, ry = 0, w = 0, n = 0;
+  unsigned long long key = 0;
+  size_t tb = 0;
+  if (gid < (long long)F * P) {
+    const ushort4 r = rect[gid];
+    if (r.x < r.z && r.y < r.w) {
+      const int f = (int)(gid / P);
+      const uint32_t i = (uint32_t)(gid - (long long)f * P);
+      const float depth = splat[gid * 3 + 2].y;
+      key = ((unsigned long long)__float_as_uint(depth) << 32) | i;
+      tb = (size_t)f * gx * gy;
+      rx = r.x; ry = r.y; w = r.z - r.x; n = w * (r.w - r.y);
     }
+  }
+  if (n > 0 && n <= kScatterSmall) {
+#pragma unroll 4
+    for (int t = 0; t < n; ++t)
+      scatter_one(tb + (size_t)(ry + t / w) * gx + rx + t % w, key, tile_count, tile_start, keys, cap, status);
+  }
+  unsigned big = __ballot_sync(0xffffffffu, n > kScatterSmall);
+  while (big) {
+    const int j = __ffs(big) - 1;
+    big &= big - 1;
+    const int jrx = __shfl_sync(0xffffffffu, rx, j), jry = __shfl_sync(0xffffffffu, ry, j);
+    const int jw = __shfl_sync(0xffffffffu, w, j), jn = __shfl_sync(0xffffffffu, n, j);
+    const unsigned long long jkey = __shfl_sync(0xffffffffu, key, j);
+    const size_t jtb = __shfl_sync(0xffffffffu, (unsigned long long)tb, j);
+    for (int t = lane; t < jn; t += 32)
+      scatter_one(jtb + (size_t)(jry + t / jw) * gx + jrx + t % jw, jkey, tile_count, tile_start, keys, cap, status);
+  }
 }
 
 cudaError_t launch_scatter(const gvf_raster_params& prm, int F, int P, const RasterWs& ws,

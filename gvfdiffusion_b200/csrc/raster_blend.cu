@@ -70,8 +70,8 @@ struct BlendArgs {
 __global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArgs a) {
   __shared__ unsigned long long skeys[kSortCap];
   __shared__ float4 sA[GVF_TILE_PIX];   // px, py, conic a, conic b
-  __shared__ float4 sB[GVF_TILE_PIX];   // conic c, opacity', r, g
-  __shared__ float sC[GVF_TILE_PIX];    // b
+  __shared__ float2 sT[GVF_TILE_PIX];   // conic c, rejection threshold on `power` (see below)
+  __shared__ float4 sC[GVF_TILE_PIX];   // opacity', r, g, b  (read only by pixels the splat reaches)
 
   const int T = a.gx * a.gy;
   const int tile = blockIdx.x;
@@ -127,26 +127,32 @@ __global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArg
     if (j < n) {
       const uint32_t id = in_smem ? (uint32_t)skeys[j] : (uint32_t)gk[j];
       const float4* r = sp + (size_t)id * 3;
+      const float4 r1 = __ldg(r + 1);
       sA[tid] = __ldg(r);
-      sB[tid] = __ldg(r + 1);
-      sC[tid] = __ldg(reinterpret_cast<const float*>(r + 2));
+      // 9 of 10 (pixel, splat) pairs of a tile end at "alpha < 1/255".  op * exp(power) < 1/255 is decided on
+      // `power` alone against log(1 / (255 op)); the 0.01 margin (1 % in alpha, __expf is good to 1e-6) keeps
+      // the pre-test strictly conservative, so the exact test below takes the same decisions as before
+      sT[tid] = make_float2(r1.x, -__logf(255.0f * r1.y) - 0.01f);
+      sC[tid] = make_float4(r1.y, r1.z, r1.w, __ldg(reinterpret_cast<const float*>(r + 2)));
     }
     __syncthreads();
     const int m = min(GVF_TILE_PIX, n - base);
     for (int k = 0; !done && k < m; ++k) {
       ++contributor;
-      const float4 A = sA[k], B = sB[k];
+      const float4 A = sA[k];
+      const float2 ct = sT[k];
       const float dx = A.x - pfx, dy = A.y - pfy;
-      const float power = -0.5f * (A.z * dx * dx + B.x * dy * dy) - A.w * dx * dy;
-      if (power > 0.0f) continue;
-      const float alpha = fminf(0.99f, B.y * __expf(power));
+      const float power = -0.5f * (A.z * dx * dx + ct.x * dy * dy) - A.w * dx * dy;
+      if (power > 0.0f || power < ct.y) continue;
+      const float4 B = sC[k];
+      const float alpha = fminf(0.99f, B.x * __expf(power));
       if (alpha < 1.0f / 255.0f) continue;
       const float test_T = Tr * (1.0f - alpha);
       if (test_T < 0.0001f) { done = true; continue; }
       const float w = alpha * Tr;
-      C0 += B.z * w;
-      C1 += B.w * w;
-      C2 += sC[k] * w;
+      C0 += B.y * w;
+      C1 += B.z * w;
+      C2 += B.w * w;
       Tr = test_T;
       last = contributor;
     }
