@@ -664,6 +664,261 @@ static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CU
              ? GVF_OK : GVF_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------
+// Residual GEMM fused with the LayerNorm (+ adaLN modulate / affine) that consumes its result:
+//     X[M,512] += gate * fp16(A W^T + b)          (fp32 residual stream, as mode 2 above)
+//     Y[M,512]  = fp16( LN(X) * (1 + scale) + shift )   or   fp16( LN(X) * w + b )
+// reference model/dit.py:246-277: every attention out-projection / MLP fc2 is followed by the norm of the
+// next sub-block.  As two kernels that was 21 us + 10 us of mostly launch, ramp and a second pass over X.
+// One CTA owns complete rows (a 128 x 512 tile: the whole TMEM as one fp32 accumulator, two N = 256 MMAs
+// per k-step), so the row statistics never leave the CTA:
+//   pass 1  (thread = row, each of the two warps of a row quarter owns 256 columns) accumulator + bias ->
+//           fp16 rounding -> gate -> + residual; the new X goes to global memory through the TMA staging
+//           tiles and back into TMEM; shifted sums give (mean, M2) of the warp's half row, Chan's formula
+//           merges the two halves through shared memory
+//   pass 2  X re-read from TMEM -> normalise -> modulate -> fp16 -> TMA store of Y.
+// 96 CTAs for M = 12288: not a full wave, but these are latency-bound launches and one of them disappears.
+struct LnEpi {
+  const float* bias;                // [512] or null
+  const __half* gate;               // [batches, gate_stride] or null
+  int gate_stride, rows_per_batch;
+  float* x;                         // [M, ldx] fp32 in / out
+  int ldx;
+  const float* ln_w;                // affine LayerNorm ([512], [512]) or null
+  const float* ln_b;
+  const __half* shift;              // adaLN modulation ([batches, mod_stride]) or null
+  const __half* scale;
+  int mod_stride;
+  float eps;
+};
+
+constexpr int kLnBN = 512, kLnStages = 2;
+
+__global__ void __launch_bounds__(320, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+               const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int M, int K,
+               LnEpi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kLnStages], empty_bar[kLnStages], tfull_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = kLnBN * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  uint8_t* stg_base = smem + kLnStages * STAGE_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (K + kBK - 1) / kBK;
+  const int tile_m = blockIdx.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kLnStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapY);
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % kLnStages;
+        mbar_wait(&empty_bar[s], ((kb / kLnStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+        tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, 0);              // W rows 0..255
+        tma_load_2d(st + A_BYTES + W_BYTES / 2, &mapW, &full_bar[s], kb * kBK, 256);   // W rows 256..511
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM, 256, 0, 0);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % kLnStages;
+        mbar_wait(&full_bar[s], (kb / kLnStages) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), w0 = a0 + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t ad = make_smem_desc(a0 + k * 32, 16, 1024, SWZ_128B);
+          mma_ss(tmem, ad, make_smem_desc(w0 + k * 32, 16, 1024, SWZ_128B), idesc, (kb | k) != 0);
+          mma_ss(tmem + 256, ad, make_smem_desc(w0 + W_BYTES / 2 + k * 32, 16, 1024, SWZ_128B), idesc, (kb | k) != 0);
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(&tfull_bar);
+    }
+  } else {
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    uint8_t* stg = stg_base + ew * 2 * 4096;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const int row0 = tile_m * kBM + q * 32, row = row0 + lane;
+    const bool row_ok = row < M;
+    const int colh = half * 256;
+    const uint32_t tacc = tmem + colh + ((uint32_t)(q * 32) << 16);
+    const int rsafe = row_ok ? row : 0;
+    const float* xrow = ep.x + (size_t)rsafe * ep.ldx + colh;
+    const __half* grow = ep.gate ? ep.gate + (size_t)(rsafe / ep.rows_per_batch) * ep.gate_stride + colh : nullptr;
+    int sbuf = 0;
+    float x0 = 0.f, s1 = 0.f, s2 = 0.f;
+    // residual rows of the first chunk travel while the main loop runs
+    float4 xr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xr[j] = row_ok ? *reinterpret_cast<const float4*>(xrow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+    // ---------------- pass 1: new X (global + TMEM) and the half-row statistics
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+      float v[32];
+      {
+        uint32_t rr[32];
+        tmem_ld_x32(tacc + c0, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+      }
+      if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + colh + c0) + j);
+          v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = r16(v[j]);
+      if (grow) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 gg = *reinterpret_cast<const uint4*>(grow + c0 + 8 * j);
+          const __half2* g2 = reinterpret_cast<const __half2*>(&gg);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            v[8 * j + 2 * t] = r16(v[8 * j + 2 * t] * __low2float(g2[t]));
+            v[8 * j + 2 * t + 1] = r16(v[8 * j + 2 * t + 1] * __high2float(g2[t]));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[4 * j] += xr[j].x; v[4 * j + 1] += xr[j].y; v[4 * j + 2] += xr[j].z; v[4 * j + 3] += xr[j].w;
+      }
+      if (c0 + 32 < 256) {                          // next chunk's residual
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          xr[j] = row_ok ? *reinterpret_cast<const float4*>(xrow + c0 + 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (c0 == 0) x0 = v[0];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - x0; s1 += d; s2 = fmaf(d, d, s2); }
+      {
+        uint32_t rr[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rr[j] = __float_as_uint(v[j]);
+        tmem_st_x32(tacc + c0, rr);
+      }
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+      uint8_t* buf = stg + sbuf * 4096 + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(buf + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && row0 < M) {
+        tma_store_2d(&mapX, stg + sbuf * 4096, colh + c0, row0);
+        tma_store_commit();
+      }
+      sbuf ^= 1;
+    }
+    tmem_st_wait();
+    // ---------------- merge the two half rows (Chan et al.): n_a = n_b = 256
+    const float mean_h = x0 + s1 * (1.0f / 256.0f);
+    const float m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 256.0f), 0.f);
+    float2* s_stat = reinterpret_cast<float2*>(smem);   // the pipeline stages are idle once tfull_bar has fired
+    s_stat[half * kBM + q * 32 + lane] = make_float2(mean_h, m2_h);
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const float2 other = s_stat[(half ^ 1) * kBM + q * 32 + lane];
+    const float dm = mean_h - other.x;
+    const float mean = 0.5f * (mean_h + other.x);
+    const float var = (m2_h + other.y + dm * dm * 128.0f) * (1.0f / 512.0f);
+    const float rstd = rsqrtf(var + ep.eps);
+    const __half* shrow = ep.shift ? ep.shift + (size_t)(rsafe / ep.rows_per_batch) * ep.mod_stride + colh : nullptr;
+    const __half* scrow = ep.scale ? ep.scale + (size_t)(rsafe / ep.rows_per_batch) * ep.mod_stride + colh : nullptr;
+    // ---------------- pass 2: normalise + modulate -> fp16
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 64) {
+      float v[64];
+      {
+        uint32_t rr[64];
+        tmem_ld_x32(tacc + c0, *reinterpret_cast<uint32_t(*)[32]>(&rr[0]));
+        tmem_ld_x32(tacc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rr[32]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = (__uint_as_float(rr[j]) - mean) * rstd;
+      }
+      if (ep.ln_w) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(ep.ln_w + colh + c0) + j);
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.ln_b + colh + c0) + j);
+          v[4 * j] = v[4 * j] * ww.x + bb.x; v[4 * j + 1] = v[4 * j + 1] * ww.y + bb.y;
+          v[4 * j + 2] = v[4 * j + 2] * ww.z + bb.z; v[4 * j + 3] = v[4 * j + 3] * ww.w + bb.w;
+        }
+      }
+      if (scrow) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 sc = *reinterpret_cast<const uint4*>(scrow + c0 + 8 * j);
+          const uint4 sh = *reinterpret_cast<const uint4*>(shrow + c0 + 8 * j);
+          const __half2* sc2 = reinterpret_cast<const __half2*>(&sc);
+          const __half2* sh2 = reinterpret_cast<const __half2*>(&sh);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            v[8 * j + 2 * t] = v[8 * j + 2 * t] * (1.0f + __low2float(sc2[t])) + __low2float(sh2[t]);
+            v[8 * j + 2 * t + 1] = v[8 * j + 2 * t + 1] * (1.0f + __high2float(sc2[t])) + __high2float(sh2[t]);
+          }
+        }
+      }
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+      uint8_t* buf = stg + sbuf * 4096 + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 pk;
+        uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const __half2 h2 = __floats2half2_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
+          pw[t] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(buf + ((j ^ sw) << 4)) = pk;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && row0 < M) {
+        tma_store_2d(&mapY, stg + sbuf * 4096, colh + c0, row0);
+        tma_store_commit();
+      }
+      sbuf ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
 template <int BN, int STAGES>
 static int launch_gemm_persistent(const CUtensorMap& mA, const CUtensorMap& mW, int M, int N, int K,
                                   const GemmEpi& ep, cudaStream_t st) {
@@ -790,4 +1045,45 @@ extern "C" GVF_API int gvf_gemm_qkv_rmsnorm_f16(const void* A, int lda, const vo
                                                 int norm_cols, void* stream) {
   return gemm_impl(A, lda, W, ldw, M, N, K, 6, bias, out, ldo, nullptr, 0, 0, gamma_q, gamma_k, norm_cols,
                    stream);
+}
+
+// Residual Linear + the LayerNorm of the next sub-block in one kernel (see gemm_ln_kernel): N is fixed to
+// 512 (one CTA owns whole rows).  x fp32 [M, ldx] in/out; y fp16 [M, ldy] = LN(x_new) * (1 + scale) + shift
+// (shift/scale fp16 [batches, mod_stride], batch = row / rows_per_batch) or * ln_w + ln_b (fp32 [512]) or plain.
+extern "C" GVF_API int gvf_gemm_resid_ln_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                                             const float* bias, float* x, int ldx, const void* gate,
+                                             int gate_stride, int rows_per_batch, const float* ln_w,
+                                             const float* ln_b, const void* shift, const void* scale,
+                                             int mod_stride, float eps, void* y, int ldy, void* stream) {
+  if (!A || !W || !x || !y || M <= 0 || K <= 0) return GVF_ERR_INVALID;
+  if (N != kLnBN) return GVF_ERR_UNSUPPORTED;
+  if ((K % 8) || (lda % 8) || (ldw % 8) || (ldx % 4) || (ldy % 8)) return GVF_ERR_INVALID;
+  if ((ln_w == nullptr) != (ln_b == nullptr) || (shift == nullptr) != (scale == nullptr)) return GVF_ERR_INVALID;
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)x | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)ln_w |
+       (uintptr_t)ln_b | (uintptr_t)gate | (uintptr_t)shift | (uintptr_t)scale) & 15)
+    return GVF_ERR_INVALID;
+  if ((gate && (gate_stride % 8)) || (shift && (mod_stride % 8))) return GVF_ERR_INVALID;
+  if ((gate || shift) && rows_per_batch <= 0) return GVF_ERR_INVALID;
+  CUtensorMap mA, mW, mX, mY;
+  const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {1, (uint64_t)lda};
+  const uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}, sW[2] = {1, (uint64_t)ldw};
+  const uint32_t bA[2] = {kBK, kBM}, bW[2] = {kBK, 256};
+  if (!make_tmap_f16(&mA, A, 2, dA, sA, bA, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
+  if (!make_tmap_f16(&mW, W, 2, dW, sW, bW, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
+  if (!make_tmap_2d(&mX, x, 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldx, 32, 32)) return GVF_ERR_CUDA;
+  if (!make_tmap_2d(&mY, y, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldy, 64, 32)) return GVF_ERR_CUDA;
+  LnEpi ep;
+  ep.bias = bias; ep.gate = (const __half*)gate; ep.gate_stride = gate_stride;
+  ep.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : M;
+  ep.x = x; ep.ldx = ldx; ep.ln_w = ln_w; ep.ln_b = ln_b;
+  ep.shift = (const __half*)shift; ep.scale = (const __half*)scale; ep.mod_stride = mod_stride; ep.eps = eps;
+  constexpr int SMEM = kLnStages * (kBM * kBK * 2 + kLnBN * kBK * 2) + 8 * 2 * 4096 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+      return GVF_ERR_CUDA;
+    configured = true;
+  }
+  return launch_pdl(gemm_ln_kernel, dim3((M + kBM - 1) / kBM), dim3(320), SMEM, (cudaStream_t)stream, mA, mW, mX, mY,
+                    M, K, ep) == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }

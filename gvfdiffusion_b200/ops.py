@@ -53,6 +53,23 @@ def gemm_qkv_rmsnorm(a, w, bias, gamma_q, gamma_k, out):
     return out
 
 
+def gemm_resid_ln(a, w, bias, x, y, gate=None, gate_stride=0, rows_per_batch=0, ln_w=None, ln_b=None, shift=None,
+                  scale=None, mod_stride=0, eps=1e-6):
+    """x[M,512] += gate * fp16(a @ w^T + bias) in place (fp32), y = fp16(LN(x) modulated) -- one kernel."""
+    _req(a, F16, "a")
+    _req(w, F16, "w")
+    _req(x, F32, "x")
+    _req(y, F16, "y")
+    M, K = a.shape
+    N = w.shape[0]
+    st = _lib.lib().gvf_gemm_resid_ln_f16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, ptr(bias), ptr(x),
+                                          x.stride(0), ptr(gate), gate_stride, rows_per_batch, ptr(ln_w), ptr(ln_b),
+                                          ptr(shift), ptr(scale), mod_stride, eps, ptr(y), y.stride(0),
+                                          current_stream())
+    check(st, "gvf_gemm_resid_ln_f16")
+    return y
+
+
 def attention(q, k, v, scale, out=None, q_shared=False, kv_shared=False):
     """q [Nb,Lq,H,D] (or [Lq,H,D] if q_shared), k/v [Nb,Lk,H,D] (or [Lk,H,D] if kv_shared): fp16
     views with contiguous last dim (any strides that are multiples of 8).  -> [Nb,Lq,H,D] fp16."""

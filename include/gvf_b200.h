@@ -186,6 +186,16 @@ GVF_API int gvf_gemm_qkv_rmsnorm_f16(const void* A, int lda, const void* W, int 
                                      const float* bias, void* out, int ldo, const float* gamma_q,
                                      const float* gamma_k, int norm_cols, void* stream);
 
+/* Residual Linear fused with the LayerNorm (+ adaLN modulate or affine) of the next sub-block (reference
+ * model/dit.py:246-277: `x = x + gate * attn_out_proj(...)` then `h = norm(x) * (1 + scale) + shift`):
+ *   x[M,512] += gate * fp16(A W^T + b)   (fp32, in place);   y[M,512] = fp16(LN(x) * (1 + scale) + shift)
+ * or y = fp16(LN(x) * ln_w + ln_b), or plain LN when all four are NULL.  N must be 512 (one CTA owns whole
+ * rows); other widths return GVF_ERR_UNSUPPORTED and the caller uses gvf_gemm_f16 + gvf_ln_mod_f16. */
+GVF_API int gvf_gemm_resid_ln_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                                  const float* bias, float* x, int ldx, const void* gate, int gate_stride,
+                                  int rows_per_batch, const float* ln_w, const float* ln_b, const void* shift,
+                                  const void* scale, int mod_stride, float eps, void* y, int ldy, void* stream);
+
 /* y = fp16(x[M,K] W[N,K]^T + b) (+ add[m % add_rows, n], fp32) for K <= 32 on CUDA cores:
  * input_layer + APE (model/dit.py:457,470-472), static_cond_proj (:465), VAE proj
  * (model/autoencoder.py:585), gs_embedding (:389).  x fp32, W fp16, out fp32 or fp16. */

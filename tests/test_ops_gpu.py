@@ -300,6 +300,55 @@ def test_gemm_ragged_rows_and_multi_batch_gate():
     _close(o14, lin[:, :14], 1e-3, "compact")
 
 
+@pytest.mark.parametrize("M,K,rpb,kind", [(12288, 512, 12288, "mod"), (300, 2048, 100, "affine"), (1000, 136, 250, "mod"),
+                                          (257, 512, 257, "plain")])
+def test_gemm_resid_ln_fused(M, K, rpb, kind):
+    """Residual Linear + LayerNorm(+modulate / affine) in one kernel against the two-kernel path and torch."""
+    from gvfdiffusion_b200 import ops
+    g = _g(300 + M + K)
+    N = 512
+    a = _rand((M, K), g).half()
+    w = _rand((N, K), g, 0.05).half()
+    b = _rand((N,), g, 0.1)
+    nb = (M + rpb - 1) // rpb
+    gate = _rand((nb, N), g).half() if kind != "plain" else None
+    x0 = _rand((M, N), g) * 2 + 0.3
+    mod = _rand((nb, 2 * N), g, 0.3).half()
+    lw, lb = _rand((N,), g) + 1, _rand((N,), g)
+    kw = {}
+    if kind == "mod":
+        kw = dict(shift=mod[:, :N], scale=mod[:, N:], mod_stride=2 * N)
+    elif kind == "affine":
+        kw = dict(ln_w=lw, ln_b=lb)
+    # fused
+    x1 = x0.clone()
+    y1 = torch.empty((M, N), dtype=torch.float16, device=DEV)
+    ops.gemm_resid_ln(a, w, b, x1, y1, gate=gate, gate_stride=N, rows_per_batch=rpb, **kw)
+    # two kernels
+    x2 = x0.clone()
+    ops.gemm(a, w, b, ops.EPI_RESID_F32, out=x2, gate=gate, gate_stride=N, rows_per_batch=rpb)
+    if kind == "mod":
+        y2 = ops.ln_mod(x2, shift=mod[:, :N], scale=mod[:, N:], mod_stride=2 * N, rows_per_batch=rpb)
+    elif kind == "affine":
+        y2 = ops.ln_mod(x2, w=lw, b=lb)
+    else:
+        y2 = ops.ln_mod(x2)
+    assert torch.equal(x1, x2), f"residual stream differs: max {float((x1 - x2).abs().max())}"
+    _close(y1, y2.float(), 1e-3, "fused LN vs ln_mod kernel")
+    # torch
+    lin = (a.float() @ w.float().T + b).half().float()
+    if gate is not None:
+        lin = (lin * gate.float().repeat_interleave(rpb, 0)[:M]).half().float()
+    xr = x0 + lin
+    ln = F.layer_norm(xr, (N,), None, None, 1e-6)
+    if kind == "mod":
+        ln = ln * (1 + mod[:, N:].float().repeat_interleave(rpb, 0)[:M]) + mod[:, :N].float().repeat_interleave(rpb, 0)[:M]
+    elif kind == "affine":
+        ln = ln * lw + lb
+    _close(x1, xr, 1e-3, "x vs torch")
+    _close(y1, ln, 2e-3, "y vs torch")
+
+
 @pytest.mark.parametrize("variant", [4, 5])
 def test_gemm_tma_epilogue_all_modes(variant):
     """Generation-2 kernels (eight epilogue warps, TMA stores): every fused epilogue, ragged M / N / K,
