@@ -46,6 +46,7 @@ _SIGS = {
                                            _P, _P, C.c_int, _P]),
     "gvf_gemm_resid_ln_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int,
                                         C.c_int, _P, _P, _P, _P, C.c_int, C.c_float, _P, C.c_int, _P]),
+    "gvf_sparse_window_attn_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "gvf_attn_set_debug": (None, [C.c_int]),
     "gvf_attn_set_trace": (None, [_P]),
     "gvf_gemm_set_variant": (None, [C.c_int]),

@@ -1,0 +1,216 @@
+// sparse_attn.cu -- windowed self-attention over sparse voxels with the window gather and the inverse
+// permutation fused into the kernel's own staging loads and stores.
+//
+// Replaces `sparse_windowed_scaled_dot_product_self_attention` of the reference
+// (sparse/attention/windowed_attn.py:61-135), as reached from `SparseMultiHeadAttention.forward`
+// (sparse/attention/modules.py:193-196) in the swin blocks of the static VAE:
+//     qkv_feats = qkv.feats[fwd_indices]                      # gather copy   [M, 3, H, C]
+//     out = flash_attn_varlen_qkvpacked_func(qkv_feats, cu_seqlens, max(seq_lens))
+//     out = out[bwd_indices]                                  # scatter copy  [T, H, C]
+// Here the rows of a window are fetched straight from qkv.feats through `fwd_idx` by the cp.async that
+// stages them into shared memory (whole 128 B head rows, so the gather costs nothing over a dense load),
+// and every output row is written to out[fwd_idx[i]] -- which IS out[bwd_indices] -- so neither copy exists.
+//
+// Windows are short and ragged (1..512 voxels of an 8^3 window, typically tens): a 128-row tcgen05 tile
+// would be mostly padding, so this is a warp-level kernel: one CTA = (window, head, 64 query rows), four
+// warps x 16 rows, S = Q K^T and O = P V as mma.sync.m16n8k16 on ldmatrix fragments, flash-style running
+// maximum over 64-key chunks, K/V chunks double buffered with cp.async.  Head dim 64 (768 / 12 heads).
+// fp16 in / out, fp32 scores, statistics and accumulators; P rounded to fp16 for P V.
+#include "../../include/gvf_b200.h"
+#include "tc_common.cuh"
+
+namespace gvf {
+using namespace tc;
+
+namespace {
+
+constexpr int kD = 64, kQB = 64, kKB = 64;     // head dim, query rows per CTA, keys per chunk
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 16 B piece `chunk` (0..7) of 128 B row `row`: XOR swizzle, conflict-free for ldmatrix and the row copies
+__device__ __forceinline__ uint32_t slot(int row, int chunk) { return (uint32_t)(row * 8 + (chunk ^ (row & 7))) * 16u; }
+
+// rows [r0, r0 + 64) of the window (clipped to `len`) of tensor `which` (0 q, 1 k, 2 v), head h -> smem tile
+__device__ __forceinline__ void stage_rows(uint32_t dst, const __half* __restrict__ qkv, const int* __restrict__ idx,
+                                           int r0, int len, int which, int h, int H, int tid) {
+  const long long row_elems = 3LL * H * kD;
+#pragma unroll
+  for (int it = 0; it < (64 * 8) / 128; ++it) {
+    const int e = it * 128 + tid, r = e >> 3, c = e & 7;
+    const bool ok = r0 + r < len;
+    const long long g = ok ? (long long)__ldg(idx + r0 + r) : 0;
+    const __half* src = qkv + g * row_elems + ((long long)which * H + h) * kD + c * 8;
+    const int bytes = ok ? 16 : 0;                 // src-size 0: the 16 B are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + slot(r, c)), "l"(src), "r"(bytes) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
+                                                                const int* __restrict__ fwd_idx,
+                                                                const int* __restrict__ cu_seqlens, int H,
+                                                                float scale_log2e) {
+  __shared__ __align__(128) uint8_t sm[(1 + 4) * 64 * 128];     // Q | K0 V0 | K1 V1   (40 KB)
+  const int w = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQB;
+  const int beg = __ldg(cu_seqlens + w), len = __ldg(cu_seqlens + w + 1) - beg;
+  if (q0 >= len) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const int* idx = fwd_idx + beg;
+  const uint32_t sQ = smem_u32(sm), sKV = sQ + 64 * 128;
+  const int nchunks = (len + kKB - 1) / kKB;
+
+  stage_rows(sQ, qkv, idx, q0, len, 0, h, H, tid);
+  stage_rows(sKV, qkv, idx, 0, len, 1, h, H, tid);
+  stage_rows(sKV + 64 * 128, qkv, idx, 0, len, 2, h, H, tid);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  uint32_t qa[4][4];
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+
+  for (int j = 0; j < nchunks; ++j) {
+    const uint32_t bK = sKV + (uint32_t)(j & 1) * 2 * 64 * 128, bV = bK + 64 * 128;
+    if (j + 1 < nchunks) {
+      const uint32_t nK = sKV + (uint32_t)((j + 1) & 1) * 2 * 64 * 128;
+      stage_rows(nK, qkv, idx, (j + 1) * kKB, len, 1, h, H, tid);
+      stage_rows(nK + 64 * 128, qkv, idx, (j + 1) * kKB, len, 2, h, H, tid);
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (j == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldsm4(qa[ks], sQ + slot(16 * warp + (lane & 15), 2 * ks + (lane >> 4)));
+    }
+    // ---- S = Q K^T for this warp's 16 rows x 64 keys
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t kb[4];
+        ldsm4(kb, bK + slot(8 * nt + (lane & 7), 4 * hf + (lane >> 3)));
+        mma16816(s[nt], qa[2 * hf], kb[0], kb[1]);
+        mma16816(s[nt], qa[2 * hf + 1], kb[2], kb[3]);
+      }
+    }
+    // ---- running softmax; rows g (e = 0,1) and g + 8 (e = 2,3), key = j*64 + 8 nt + 2 tg + (e & 1)
+    const int kvalid = len - j * kKB;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = 8 * nt + 2 * tg + (e & 1);
+        s[nt][e] = (col < kvalid) ? s[nt][e] * scale_log2e : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+      }
+    float alpha[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float mn = fmaxf(mrow[r], mx[r]);       // finite: every chunk holds at least one valid key
+      alpha[r] = ex2f(mrow[r] - mn);
+      mrow[r] = mn;
+      lrow[r] *= alpha[r];
+    }
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float p[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        p[e] = ex2f(s[nt][e] - mrow[e >> 1]);
+        lrow[e >> 1] += p[e];
+      }
+      const __half2 lo = __floats2half2_rn(p[0], p[1]), hi = __floats2half2_rn(p[2], p[3]);
+      pa[nt >> 1][(nt & 1) * 2] = *reinterpret_cast<const uint32_t*>(&lo);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
+      o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) {
+        uint32_t vb[4];
+        ldsm4t(vb, bV + slot(16 * ks + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * c2 + (lane >> 4)));
+        mma16816(o[2 * c2], pa[ks], vb[0], vb[1]);
+        mma16816(o[2 * c2 + 1], pa[ks], vb[2], vb[3]);
+      }
+    __syncthreads();                               // everyone is done with this buffer before it is refilled
+  }
+  // ---- normalise, park the 16 rows in this warp's slice of the Q tile, write whole rows to out[fwd_idx[i]]
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+  const float inv[2] = {1.0f / lrow[0], 1.0f / lrow[1]};
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = 16 * warp + g + 8 * r;
+      *reinterpret_cast<__half2*>(sm + slot(row, nt) + 4 * tg) =
+          __floats2half2_rn(o[nt][2 * r] * inv[r], o[nt][2 * r + 1] * inv[r]);
+    }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int e = it * 32 + lane, r = 16 * warp + (e >> 3), c = e & 7;
+    if (q0 + r < len) {
+      const long long grow = __ldg(idx + q0 + r);
+      *reinterpret_cast<uint4*>(out + (grow * H + h) * kD + c * 8) = *reinterpret_cast<const uint4*>(sm + slot(r, c));
+    }
+  }
+}
+
+}  // namespace
+}  // namespace gvf
+
+// qkv [T, 3, H, 64] fp16 (the to_qkv output layout, modules.py:165-166), out [T, H, 64] fp16.
+// fwd_idx [M] int32: voxel rows ordered by window; cu_seqlens [W + 1] int32: window w owns
+// fwd_idx[cu_seqlens[w] .. cu_seqlens[w + 1]); max_seqlen bounds the grid.  Rows outside every window are
+// left untouched.
+extern "C" GVF_API int gvf_sparse_window_attn_f16(const void* qkv, void* out, const int* fwd_idx,
+                                                  const int* cu_seqlens, int num_windows, int max_seqlen,
+                                                  int H, int D, float scale, void* stream) {
+  if (!qkv || !out || !fwd_idx || !cu_seqlens || num_windows < 0 || H <= 0 || max_seqlen < 0) return GVF_ERR_INVALID;
+  if (D != gvf::kD) return GVF_ERR_UNSUPPORTED;
+  if (((uintptr_t)qkv | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
+  if (num_windows == 0 || max_seqlen == 0) return GVF_OK;
+  if (num_windows > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
+  const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_windows);
+  gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __half*)qkv, (__half*)out, fwd_idx, cu_seqlens, H, scale * 1.4426950408889634f);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}

@@ -268,6 +268,16 @@ GVF_API int gvf_vox2seq_encode(const int32_t* coords, long long N, const int* pe
 GVF_API int gvf_vox2seq_decode(const int32_t* codes, long long N, const int* permute, int hilbert,
                                int32_t* coords, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Windowed self-attention over sparse voxels (static-VAE swin blocks).
+ * Replaces sparse_windowed_scaled_dot_product_self_attention (sparse/attention/windowed_attn.py:61-135):
+ * `qkv.feats[fwd_indices]` -> flash_attn_varlen_qkvpacked_func -> `out[bwd_indices]`.  The gather through
+ * fwd_idx is done by the kernel's staging loads and every result row is stored at out[fwd_idx[i]], so
+ * neither permutation copy exists.  qkv [T,3,H,64] fp16, out [T,H,64] fp16, fwd_idx [M] int32 (rows ordered
+ * by window), cu_seqlens [W+1] int32, max_seqlen >= the longest window.  Head dim 64 only. */
+GVF_API int gvf_sparse_window_attn_f16(const void* qkv, void* out, const int* fwd_idx, const int* cu_seqlens,
+                                       int num_windows, int max_seqlen, int H, int D, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

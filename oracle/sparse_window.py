@@ -1,0 +1,40 @@
+"""ORACLE (test infrastructure, never on the product path): CPU restatement of the reference's windowed
+sparse self-attention -- calc_window_partition (sparse/attention/windowed_attn.py:20-58) and the
+gather -> per-window softmax attention -> scatter of :92-129 (flash_attn_varlen_qkvpacked_func is plain
+scaled-dot-product attention inside each cu_seqlens segment).  Pinned by tests/golden/window_partition.pt,
+produced by the reference's own calc_window_partition (tests/golden/make_golden.py)."""
+import math
+
+import torch
+
+
+def calc_window_partition(coords, window_size, shift_window=0):
+    """coords [T, 1+DIM] int; returns (window id per voxel [T] int64, seq_lens list, seq_batch_indices list)
+    -- the quantities of :39-56 that do not depend on argsort's tie order."""
+    DIM = coords.shape[1] - 1
+    shift = (shift_window,) * DIM if isinstance(shift_window, int) else tuple(shift_window)
+    win = (window_size,) * DIM if isinstance(window_size, int) else tuple(window_size)
+    sc = coords.clone().long()
+    sc[:, 1:] += torch.tensor(shift)[None]
+    max_coords = sc[:, 1:].max(dim=0).values.tolist()
+    nwin = [math.ceil((mc + 1) / ws) for mc, ws in zip(max_coords, win)]
+    offset = torch.cumprod(torch.tensor([1] + nwin[::-1]), dim=0).tolist()[::-1]
+    sc[:, 1:] //= torch.tensor(win)[None]
+    ids = (sc * torch.tensor(offset)[None]).sum(dim=1)
+    counts = torch.bincount(ids)
+    batch = torch.arange(counts.shape[0]) // offset[0]
+    mask = counts != 0
+    return ids, counts[mask].tolist(), batch[mask].tolist()
+
+
+def windowed_attention(qkv_feats, coords, window_size, shift_window=0):
+    """qkv_feats [T,3,H,C] -> [T,H,C] fp32: softmax(q k^T / sqrt(C)) v inside every window."""
+    ids, _, _ = calc_window_partition(coords, window_size, shift_window)
+    q, k, v = qkv_feats.float().unbind(1)
+    out = torch.zeros_like(q)
+    scale = 1.0 / math.sqrt(q.shape[-1])
+    for wid in torch.unique(ids).tolist():
+        sel = (ids == wid).nonzero().squeeze(1)
+        s = torch.einsum("qhc,khc->hqk", q[sel], k[sel]) * scale
+        out[sel] = torch.einsum("hqk,khc->qhc", s.softmax(-1), v[sel])
+    return out

@@ -169,13 +169,43 @@ def gen_gaussian():
     return out
 
 
+def gen_window_partition():
+    """The reference's own calc_window_partition (sparse/attention/windowed_attn.py:20-58) on seeded sparse
+    voxel sets: two batch entries of a 64^3 grid, window 8, unshifted and shifted by half a window (the two
+    settings the swin blocks alternate, sparse_transformer.py).  Stored: the inputs, the window id of every
+    voxel in the reference's forward order (sorted ids -- independent of argsort's tie order), seq_lens and
+    seq_batch_indices."""
+    import types
+    from sparse.attention.windowed_attn import calc_window_partition
+    g = torch.Generator().manual_seed(11)
+    cases = []
+    for (n_vox, res, window, shift) in [(1500, 64, 8, (0, 0, 0)), (1500, 64, 8, (4, 4, 4)), (300, 16, 4, (2, 2, 2)),
+                                        (64, 8, 8, (0, 0, 0))]:
+        coords = []
+        for b in range(2):
+            lin = torch.randperm(res ** 3, generator=g)[:n_vox]
+            xyz = torch.stack([lin // (res * res), (lin // res) % res, lin % res], 1)
+            coords.append(torch.cat([torch.full((n_vox, 1), b), xyz], 1))
+        coords = torch.cat(coords).int()
+        t = types.SimpleNamespace(coords=coords, device=coords.device)
+        fwd, bwd, seq_lens, seq_batch = calc_window_partition(t, window, shift)
+        assert torch.equal(bwd[fwd], torch.arange(fwd.shape[0]))
+        cases.append({"coords": coords, "window": window, "shift": shift, "fwd": fwd, "bwd": bwd,
+                      "seq_lens": seq_lens, "seq_batch_indices": seq_batch})
+    return cases
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "window":
+        torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
+        return
     sched, diffusion, ns = gen_schedule()
     torch.save(sched, os.path.join(HERE, "schedule.pt"))
     torch.save(gen_dit(ns), os.path.join(HERE, "dit_tiny.pt"))
     torch.save(gen_vae(), os.path.join(HERE, "vae_tiny.pt"))
     torch.save(gen_p_sample(diffusion), os.path.join(HERE, "p_sample.pt"))
     torch.save(gen_gaussian(), os.path.join(HERE, "gaussian.pt"))
+    torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

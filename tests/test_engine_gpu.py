@@ -110,11 +110,19 @@ def test_dit_full_width_one_block_vs_oracle():
     ci = torch.randn(B, T, 1370, 1024, generator=gen)
     sl = torch.randn(B, 4096, 14, generator=gen)
     xyz = torch.rand(B, N, 3, generator=gen) - 0.5
-    y = m.to(DEV)(x.to(DEV), t.to(DEV), ci.to(DEV), sl.to(DEV), xyz.to(DEV))
+    y = m.to(DEV)(x.to(DEV), t.to(DEV), ci.to(DEV), sl.to(DEV), xyz.to(DEV)).clone()
     y16 = ODIT.dit_forward(sd, x, t, ci, sl, xyz, 16, "fp16")
     y32 = ODIT.dit_forward(sd, x, t, ci, sl, xyz, 16, "fp32")
     assert rel(y, y16) < 1e-3, rel(y, y16)
     assert rel(y, y32) < 3e-3, rel(y, y32)
+    # the optional fused residual-Linear + LayerNorm kernels take the same rounding points
+    m.engine().fuse_resid_ln = True
+    try:
+        yf = m(x.to(DEV), t.to(DEV), ci.to(DEV), sl.to(DEV), xyz.to(DEV)).clone()
+    finally:
+        m.engine().fuse_resid_ln = False
+    assert rel(yf, y16) < 1e-3, rel(yf, y16)
+    assert rel(yf, y) < 5e-4, rel(yf, y)
 
 
 def test_vae_decode_golden_fixture_and_full_width():

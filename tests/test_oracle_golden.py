@@ -132,3 +132,30 @@ def test_gaussian_activations_match_reference():
     t = [x.reshape(x.shape[0], -1).numpy() for x in g["with_delta"]]
     for a, b in zip(c, t):
         np.testing.assert_allclose(a, b, rtol=3e-6, atol=1e-7)
+
+
+def test_window_partition_matches_reference():
+    """oracle/sparse_window.py and the product's host-side partition against the reference's own
+    calc_window_partition (sparse/attention/windowed_attn.py:20-58): same window id per voxel, same sorted
+    id sequence in forward order, same seq_lens / seq_batch_indices."""
+    from oracle import sparse_window as OSW
+    from gvfdiffusion_b200.sparse.attention.windowed_attn import calc_window_partition
+    cases = torch.load(os.path.join(G, "window_partition.pt"), weights_only=False)
+    assert len(cases) == 4
+    for c in cases:
+        ids, seq_lens, seq_batch = OSW.calc_window_partition(c["coords"], c["window"], c["shift"])
+        assert seq_lens == c["seq_lens"] and seq_batch == c["seq_batch_indices"]
+        assert torch.equal(ids[c["fwd"]], torch.sort(ids).values)          # the reference's order sorts our ids
+        fwd, bwd, lens, batch = calc_window_partition(c["coords"], c["window"], c["shift"])     # product host code (CPU tensors)
+        assert lens.tolist() == c["seq_lens"] and batch.tolist() == c["seq_batch_indices"]
+        assert torch.equal(ids[fwd], ids[c["fwd"]])
+        assert torch.equal(bwd[fwd], torch.arange(fwd.shape[0]))
+        # the reference's DEBUG assertions (:98-106): one batch index and < window extent per segment
+        start = 0
+        sh = torch.tensor(c["shift"])
+        for n, b in zip(seq_lens, seq_batch):
+            seg = c["coords"][fwd[start:start + n]].long()
+            assert (seg[:, 0] == b).all()
+            w = (seg[:, 1:] + sh) // c["window"]
+            assert (w == w[0]).all()
+            start += n
