@@ -356,7 +356,11 @@ def main():
         "gpu_launches": launch_estimate() * args.steps,
         "roofline": {"bound": "tensor", "kernel": "attn_fwd6_kernel (d=32, static cross-attention, kv 4096)",
                      "achieved": dom.get("tflops"), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": dom.get("frac_of_sustained"), "traffic": None, "peak_source": pk["source"] + " sustained bf16"},
+                     "frac": dom.get("frac_of_sustained"), "traffic": ncu_traffic("attn_fwd6_kernel"),
+                     "peak_source": pk["source"] + " sustained bf16",
+                     "note": ("head dim 32: one MUFU exp2 per score caps this kernel at 25 % of the tensor pipe "
+                              "(1024 MUFU clocks vs 256 MMA clocks per 128x128 tile); ncu: XU pipe 79 % active, "
+                              "tensor pipe 17 % (profiles/r01_attn6_full_extract.csv)")},
         "roofline_detail": roof_detail,
         "stage_ms_eager": {"prepare_fps": stage_ms[3], "sample_32nfe": stage_ms[0], "vae_decode": stage_ms[1],
                            "raster_24f": stage_ms[2]},
@@ -364,7 +368,9 @@ def main():
                             "achieved": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6,
                             "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6 / pk["hbm_gbs"],
-                            "ms": raster_ms, "traffic": None},
+                            "ms": raster_ms, "traffic": None,
+                            "note": ("not HBM-bound at this depth complexity: ~0.5 G pixel-splat evaluations per 24 "
+                                     "frames, sort_blend runs at 77 % SM issue throughput (profiles/r01_raster_full_extract.csv)")},
     }
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -401,13 +407,27 @@ def _tagged_attention(fn, timer):
     return call
 
 
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        for k, v in json.load(open(p)).items():
+            if k.startswith(kernel_prefix):
+                return v.get("dram_bytes")
+    except Exception:
+        pass
+    return None
+
+
 def launch_estimate():
-    """Kernel launches of ours per object: counted from the engine structure (dit_engine.py,
-    vae_engine.py, raster_api.cu): per NFE 2 (modulation) + 1 (input) + 12 x 21 + 1 (final) + 2 (DPM)."""
-    per_nfe = 2 + 1 + 12 * 21 + 1 + 2
+    """Kernel launches of ours per object, counted from the engine structure and checked against the committed
+    ncu launch list (profiles/r01_nfe_launch_list.csv: 471 launches for 2 NFE incl. 4 torch copies, 117 for
+    decode + render): per NFE 2 (modulation) + 1 (input) + 12 blocks x 19 (5 LayerNorm, 2 qkv, 4 attention,
+    4 out-proj, 2 q-proj, fc1, fc2) + 1 (final) + 2 (DPM)."""
+    per_nfe = 2 + 1 + 12 * 19 + 1 + 2
     hoist = 2 + 12 + 1 + 12 + 1 + 3
-    vae = 1 + 12 * 7 + 2 + 2 * (2 + 1 + 1 + 1 + 1)
-    return NFE * per_nfe + hoist + vae + 4
+    decode_render = 112 + 5
+    return NFE * per_nfe + hoist + decode_render
 
 
 if __name__ == "__main__":
