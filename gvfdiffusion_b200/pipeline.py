@@ -10,6 +10,28 @@ from . import synthetic as S
 from .model import dpmsolver as D
 
 
+def pad_static_gs(static_gs):
+    """List of per-object activated Gaussian tensors [P_i, 14] -> ([B, max P, 14], [P_i]); padding rows are
+    zeros with a unit quaternion (column 10 = 1) -- reference train_vae.py:475-483."""
+    max_len = max(g.shape[0] for g in static_gs)
+    pad = torch.zeros((1, static_gs[0].shape[1]), dtype=static_gs[0].dtype, device=static_gs[0].device)
+    pad[0, 10] = 1.0
+    out = torch.stack([torch.cat([g, pad.expand(max_len - g.shape[0], -1)], 0) for g in static_gs], 0)
+    return out, [g.shape[0] for g in static_gs]
+
+
+def sample_gs(static_gs_list, num_latents):
+    """Farthest point sample of every object's Gaussians to `num_latents` rows -> [B, num_latents, 14]
+    (reference utils/inference_utils.py:180-198, where torch_cluster.fps runs over the ragged batch with
+    ratio num_latents / P_i and a random start; here one gvf_fps launch per object from start index 0)."""
+    out = []
+    for g in static_gs_list:
+        g = g.contiguous()
+        idx = ops.fps(g, min(num_latents, g.shape[0])).long()
+        out.append(g.index_select(0, idx))
+    return torch.stack(out, 0)
+
+
 class ObjectState:
     """Per-object tensors derived from the canonical Gaussians (inference_dpm_latent.py:205-222)."""
 

@@ -127,3 +127,26 @@ def test_fps_sizes(P):
         cur = int(np.argmax(mind))
         ref_idx.append(cur)
     assert np.array_equal(idx, np.array(ref_idx, np.int32))
+
+
+def test_pad_static_gs_and_sample_gs_ragged_batch():
+    """train_vae.py:475-483 / utils/inference_utils.py:180-198 on a ragged batch of two objects."""
+    from gvfdiffusion_b200.pipeline import pad_static_gs, sample_gs
+    g = torch.Generator().manual_seed(5)
+    a, b = torch.randn(700, 14, generator=g).cuda(), torch.randn(1000, 14, generator=g).cuda()
+    padded, idx = pad_static_gs([a, b])
+    assert padded.shape == (2, 1000, 14) and idx == [700, 1000]
+    assert torch.equal(padded[0, :700], a) and torch.equal(padded[1], b)
+    tail = padded[0, 700:]
+    assert (tail[:, 10] == 1).all() and (tail[:, :10] == 0).all() and (tail[:, 11:] == 0).all()
+    s = sample_gs([a, b], 256)
+    assert s.shape == (2, 256, 14)
+    # greedy farthest point sampling from index 0, re-derived on the host for object 0
+    pts = a[:, :3].cpu()
+    d = ((pts - pts[0]) ** 2).sum(1)
+    sel = [0]
+    for _ in range(255):
+        j = int(torch.argmax(d))
+        sel.append(j)
+        d = torch.minimum(d, ((pts - pts[j]) ** 2).sum(1))
+    assert torch.equal(s[0].cpu(), a.cpu()[sel])
