@@ -358,9 +358,12 @@ def main():
                      "achieved": dom.get("tflops"), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": dom.get("frac_of_sustained"), "traffic": ncu_traffic("attn_fwd6_kernel"),
                      "peak_source": pk["source"] + " sustained bf16",
-                     "note": ("head dim 32: one MUFU exp2 per score caps this kernel at 25 % of the tensor pipe "
-                              "(1024 MUFU clocks vs 256 MMA clocks per 128x128 tile); ncu: XU pipe 79 % active, "
-                              "tensor pipe 17 % (profiles/r01_attn6_full_extract.csv)")},
+                     "mufu_ceiling_tflops": 148 * 16 * 128 * (sampler.summary()["sm_mhz"] or 1965) * 1e6 / 1e12,
+                     "note": ("head dim 32: every score costs one MUFU exp2 (16 / clk / SM) against 128 tensor flops, so "
+                              "the kernel's ceiling is mufu_ceiling_tflops (596 at 1965 MHz = 25 % of the nominal tensor "
+                              "rate at that clock, 43 % of the measured cuBLAS peak); ncu: XU pipe 79 % busy while the "
+                              "grid is resident, tensor pipe 17 %, third of three CTA waves 59 % full "
+                              "(profiles/r01_attn6_full_extract.csv)")},
         "roofline_detail": roof_detail,
         "stage_ms_eager": {"prepare_fps": stage_ms[3], "sample_32nfe": stage_ms[0], "vae_decode": stage_ms[1],
                            "raster_24f": stage_ms[2]},
