@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn-dbg", type=lambda v: int(v, 0), default=0, help="gvf_attn_set_debug value (kernel-variant A/B)")
     ap.add_argument("--pdl", action="store_true", help="launch with the programmatic-dependent-launch attribute (A/B; default off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -227,6 +228,8 @@ def main():
     from gvfdiffusion_b200.pipeline import GVFPipeline
     if args.pdl:
         _lib.lib().gvf_set_pdl(1)
+    if args.attn_dbg:
+        _lib.lib().gvf_attn_set_debug(args.attn_dbg)
 
     dit, vae = build_models(dev, seed=0)                      # replicated weights
     pipe = GVFPipeline(dit, vae, reference_betas(), device=dev, resolution=RES)

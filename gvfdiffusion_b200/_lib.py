@@ -48,6 +48,7 @@ _SIGS = {
                                         C.c_int, _P, _P, _P, _P, C.c_int, C.c_float, _P, C.c_int, _P]),
     "gvf_sparse_window_attn_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "gvf_attn_set_debug": (None, [C.c_int]),
+    "gvf_attn_set_workspace": (None, [_P, C.c_size_t]),
     "gvf_attn_set_trace": (None, [_P]),
     "gvf_gemm_set_variant": (None, [C.c_int]),
     "gvf_set_pdl": (None, [C.c_int]),

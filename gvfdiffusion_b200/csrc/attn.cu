@@ -68,6 +68,12 @@ struct AttnArgs {
   long long* trace;   // optional clock64 trace of CTA (0,0,0) (tools/attn_experiments.py)
   int stagger;        // clocks tile B's softmax warpgroup starts late (see the softmax branch)
   int dbg;            // bit 0x20: MUFU ping-pong between the two softmax warpgroups (v4)
+  // v6 work list: items [0, split_from) are whole (query block, head, batch) units; every unit from
+  // split_from on is cut into `nsplit` key ranges whose partial (O, m, l) go to ws_o / ws_ml (see
+  // attn_merge_kernel).  gx = query blocks per (head, batch).
+  int split_from, nsplit, gx;
+  float* ws_o;        // [split units][nsplit][512 rows][32]
+  float* ws_ml;       // [split units][nsplit][512 rows][2]
 };
 
 // POLY = n > 0: every n-th pair of exponentials is evaluated on the FMA pipe (Cody-Waite split plus a
@@ -418,8 +424,15 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   uint8_t* sKV = smem + NT * TILE_BYTES;           // S x (K tile, V tile)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qblk = blockIdx.x, h = blockIdx.y, nb = blockIdx.z;
-  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  // work item -> (unit, key range); units keep the (query block fastest, head, batch) order of the old 3-D grid
+  const int item = blockIdx.x;
+  int unit = item, part = -1;
+  if (item >= a.split_from) {
+    unit = a.split_from + (item - a.split_from) / a.nsplit;
+    part = (item - a.split_from) % a.nsplit;
+  }
+  const int qblk = unit % a.gx, h = (unit / a.gx) % a.H, nb = unit / (a.gx * a.H);
+  const int cta_lin = item;
   if (TRACE && a.trace && threadIdx.x == 0 && cta_lin < 1024) {
     unsigned long long t; unsigned sm;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -428,8 +441,12 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   }
   const int q0 = qblk * (128 * NT);
   const int nq = min(NT, (a.Lq - q0 + 127) / 128);
-  const int n_kv = (a.Lk + 127) / 128;
-  const int n_blk = (a.Lk + BLK - 1) / BLK;
+  const int n_kv_all = (a.Lk + 127) / 128;
+  const int t0 = part < 0 ? 0 : (part * n_kv_all) / a.nsplit;              // first / past-the-last 128-key TMA tile
+  const int t1 = part < 0 ? n_kv_all : ((part + 1) * n_kv_all) / a.nsplit;
+  const int n_kv = t1 - t0;
+  const int b0 = 2 * t0;                                                    // first 64-key softmax block (global)
+  const int n_blk = min((a.Lk + BLK - 1) / BLK, 2 * t1) - b0;               // blocks of this CTA (local index i)
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
@@ -468,8 +485,8 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       auto load_kv = [&](int j) {
         const int s = j % S;
         mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tma_load_4d(sKV + s * 2 * TILE_BYTES, &mapK, &kv_full[s], 0, h, j * 128, nb * a.kv_batch_mul);
-        tma_load_4d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &mapV, &kv_full[s], 0, h, j * 128, nb * a.kv_batch_mul);
+        tma_load_4d(sKV + s * 2 * TILE_BYTES, &mapK, &kv_full[s], 0, h, (t0 + j) * 128, nb * a.kv_batch_mul);
+        tma_load_4d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &mapV, &kv_full[s], 0, h, (t0 + j) * 128, nb * a.kv_batch_mul);
       };
       auto pump = [&]() {                          // issue every load whose stage is already free
         while (loaded < n_kv && mbar_test_wait(&kv_empty[loaded % S], ((loaded / S) & 1) ^ 1)) load_kv(loaded++);
@@ -556,7 +573,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         tc_fence_before();
         mbar_arrive_u32(b_sfree);
         if (tr && i < 16 && x == 0) a.trace[i * 16 + 4] = clock64();
-        const int valid = a.Lk - i * BLK;
+        const int valid = a.Lk - (b0 + i) * BLK;
         if (valid < BLK) {
 #pragma unroll
           for (int k = 0; k < BLK; ++k)
@@ -636,6 +653,20 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_wait_u32(b_ofull, (n_blk - 1) & 1);
       tc_fence_after();
       const int qi = q0 + x * 128 + row;
+      if (part >= 0) {                             // partial result of one key range: unnormalised O, m, l
+        const size_t pr = ((size_t)(unit - a.split_from) * a.nsplit + part) * (NT * 128) + x * 128 + row;
+        float* wo = a.ws_o + pr * D;
+#pragma unroll
+        for (int d0 = 0; d0 < D; d0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tX + TM_O + d0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; k += 4)
+            *reinterpret_cast<uint4*>(wo + d0 + k) = make_uint4(r[k], r[k + 1], r[k + 2], r[k + 3]);
+        }
+        *reinterpret_cast<float2*>(a.ws_ml + pr * 2) = make_float2(m, l);
+      } else {
       const float inv = 1.0f / l;
       __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h;
 #pragma unroll
@@ -652,6 +683,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             *reinterpret_cast<uint4*>(op + d0 + k) = *reinterpret_cast<uint4*>(hh);
           }
         }
+      }
       }
     }
   }
@@ -1005,6 +1037,51 @@ static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
+// Merge of the key-range partials written by attn_fwd6_kernel for the split units: with m the lazily updated
+// reference maximum of each part, O = sum_p 2^((m_p - M) c) O_p, l likewise, M = max_p m_p.  One thread per
+// query row.  The split exists because 384 (batch, head) units on 148 SMs are 2.6 waves: the 88 units of the
+// third wave are cut into three key ranges each (264 items = two rounds of one third), which ends the wave
+// at 2/3 of its length; the merge costs ~5 us.
+__global__ void __launch_bounds__(256) attn_merge_kernel(const AttnArgs a, int n_split_units) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n_split_units * 512) return;
+  const int su = idx >> 9, r = idx & 511;
+  const int unit = a.split_from + su;
+  const int qblk = unit % a.gx, h = (unit / a.gx) % a.H, nb = unit / (a.gx * a.H);
+  const int qi = qblk * 512 + r;
+  if (qi >= a.Lq) return;
+  float M = -INFINITY;
+  for (int p = 0; p < a.nsplit; ++p) M = fmaxf(M, a.ws_ml[(((size_t)su * a.nsplit + p) * 512 + r) * 2]);
+  float o[32], l = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) o[k] = 0.f;
+  for (int p = 0; p < a.nsplit; ++p) {
+    const size_t pr = ((size_t)su * a.nsplit + p) * 512 + r;
+    const float2 ml = *reinterpret_cast<const float2*>(a.ws_ml + pr * 2);
+    const float w = fast_exp2((ml.x - M) * a.scale_log2e);
+    l = fmaf(w, ml.y, l);
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(a.ws_o + pr * 32 + k);
+      o[k] = fmaf(w, v.x, o[k]); o[k + 1] = fmaf(w, v.y, o[k + 1]);
+      o[k + 2] = fmaf(w, v.z, o[k + 2]); o[k + 3] = fmaf(w, v.w, o[k + 3]);
+    }
+  }
+  const float inv = 1.0f / l;
+  __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    __align__(16) __half hh[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(o[k + t] * inv);
+    *reinterpret_cast<uint4*>(op + k) = *reinterpret_cast<uint4*>(hh);
+  }
+}
+
+// caller-owned scratch for the split units (gvf_attn_set_workspace); no allocation happens in here
+static float* g_attn_ws = nullptr;
+static size_t g_attn_ws_bytes = 0;
+
 template <int POLY, bool TRACE>
 static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                         int Nb, cudaStream_t st) {
@@ -1016,9 +1093,42 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
       return GVF_ERR_CUDA;
     configured = true;
   }
-  dim3 grid((a.Lq + 511) / 512, a.H, Nb);
-  return launch_pdl(attn_fwd6_kernel<POLY, TRACE>, grid, dim3(640), SMEM, st, mq, mk, mv, a) == cudaSuccess ? GVF_OK
-                                                                                                   : GVF_ERR_CUDA;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  AttnArgs b = a;
+  b.gx = (a.Lq + 511) / 512;
+  const int units = b.gx * a.H * Nb;
+  b.split_from = units;
+  b.nsplit = 1;
+  b.ws_o = nullptr;
+  b.ws_ml = nullptr;
+  // tail of the last wave: cut its units into three key ranges when that shortens it (see attn_merge_kernel)
+  const int rem = units % num_sms, n_kv = (a.Lk + 127) / 128;
+  constexpr int NSPLIT = 3;
+  int n_split_units = 0;
+  // measured: pays for the 4096-key static cross-attention (280 -> 261 us), not for 1370 keys (110 -> 120 us:
+  // three prologues and the merge cost more than the shorter wave saves)
+  if (!TRACE && g_attn_ws && units > num_sms && rem > 0 && rem * NSPLIT <= 2 * num_sms && n_kv >= 16) {
+    const size_t rows = (size_t)rem * NSPLIT * 512;
+    if (rows * (32 + 2) * sizeof(float) <= g_attn_ws_bytes) {
+      n_split_units = rem;
+      b.split_from = units - rem;
+      b.nsplit = NSPLIT;
+      b.ws_o = g_attn_ws;
+      b.ws_ml = g_attn_ws + rows * 32;
+    }
+  }
+  const dim3 grid(b.split_from + n_split_units * b.nsplit);
+  if (launch_pdl(attn_fwd6_kernel<POLY, TRACE>, grid, dim3(640), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
+  if (n_split_units) {
+    attn_merge_kernel<<<(n_split_units * 512 + 255) / 256, 256, 0, st>>>(b, n_split_units);
+    if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
+  }
+  return GVF_OK;
 }
 
 }  // namespace gvf
@@ -1029,6 +1139,10 @@ static int g_attn_dbg = 0;
 static long long* g_attn_trace = nullptr;
 extern "C" GVF_API void gvf_attn_set_trace(void* p) { g_attn_trace = (long long*)p; }
 extern "C" GVF_API void gvf_attn_set_debug(int v) { g_attn_dbg = v; }
+extern "C" GVF_API void gvf_attn_set_workspace(void* ws, size_t bytes) {
+  gvf::g_attn_ws = (float*)ws;
+  gvf::g_attn_ws_bytes = ws ? bytes : 0;
+}
 static int g_small_rows = 0;   // row-staged temporal variant: measured slower than the warp-per-(batch,head) one
 
 // q [Nb_q, Lq, H, D], k/v [Nb_kv, Lk, H, D] fp16 with element strides (batch, seq, head);
@@ -1116,10 +1230,13 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   {
     if (a.trace || a.stagger > 0)   // instrumented build (tools/attn_experiments.py)
       return (poly || sel == 0) ? launch_attn6<4, true>(mq, mk, mv, a, Nb, st) : launch_attn6<0, true>(mq, mk, mv, a, Nb, st);
-    const int share = g_attn_dbg & 0xf;   // 4 / 8: every 4th / 8th pair of exponentials on the FMA pipe
+    const int share = g_attn_dbg & 0xf;
+    // default: every 8th pair of exponentials on the FMA pipe (bench: 282.0 ms / object; MUFU only 285.6; every
+    // 4th pair 285.6).  Low nibble of the debug word: 1 MUFU only, 4 every 4th pair.
+    // Short key ranges (spatial self-attention, 512 keys) stay MUFU only: 49.5 vs 53.5 us.
     if (share == 4) return launch_attn6<4, false>(mq, mk, mv, a, Nb, st);
-    if (share == 8) return launch_attn6<8, false>(mq, mk, mv, a, Nb, st);
-    return launch_attn6<0, false>(mq, mk, mv, a, Nb, st);            // default: MUFU only (measured fastest)
+    if (share == 1 || (share == 0 && Lk < 1024)) return launch_attn6<0, false>(mq, mk, mv, a, Nb, st);
+    return launch_attn6<8, false>(mq, mk, mv, a, Nb, st);
   }
   if (sel == 0) a.dbg |= 0x20;
   if (D == 64) return launch_attn<64, 0>(mq, mk, mv, a, Nb, st);

@@ -70,6 +70,17 @@ def gemm_resid_ln(a, w, bias, x, y, gate=None, gate_stride=0, rows_per_batch=0, 
     return y
 
 
+_attn_ws = None
+
+
+def _ensure_attn_ws(device):
+    """Scratch for the key-range split of the last attention wave (gvf_attn_set_workspace), once per process."""
+    global _attn_ws
+    if _attn_ws is None:
+        _attn_ws = torch.empty(147 * 3 * 512 * 34, dtype=F32, device=device)
+        _lib.lib().gvf_attn_set_workspace(ptr(_attn_ws), _attn_ws.numel() * 4)
+
+
 def attention(q, k, v, scale, out=None, q_shared=False, kv_shared=False):
     """q [Nb,Lq,H,D] (or [Lq,H,D] if q_shared), k/v [Nb,Lk,H,D] (or [Lk,H,D] if kv_shared): fp16
     views with contiguous last dim (any strides that are multiples of 8).  -> [Nb,Lq,H,D] fp16."""
@@ -92,6 +103,7 @@ def attention(q, k, v, scale, out=None, q_shared=False, kv_shared=False):
     if out is None:
         out = torch.empty((Nb, Lq, H, D), dtype=F16, device=q.device)
     os_ = (out.stride(0), out.stride(1), out.stride(2))
+    _ensure_attn_ws(q.device)
     st = _lib.lib().gvf_attn_fwd_f16(ptr(q), ptr(k), ptr(v), ptr(out), Nb, Lq, Lk, H, D, _ll(qs), _ll(ks),
                                      _ll(vs), _ll(os_), int(q_shared), int(kv_shared), float(scale),
                                      current_stream())

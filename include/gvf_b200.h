@@ -169,6 +169,13 @@ GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, 
                          int epilogue, const float* bias, void* out, int ldo, const void* gate,
                          int gate_stride, int rows_per_batch, void* stream);
 
+/* Caller-owned scratch for the dense attention kernel (optional): with it, the (batch, head) units of the last,
+ * partially filled CTA wave are cut into three key ranges whose partial results are merged by a second small
+ * kernel (csrc/attn.cu: attn_merge_kernel).  Needs 3 * 512 * 34 * 4 bytes per unit of the last wave (< 148
+ * units); without it (or with too small a buffer) every unit runs whole.  The buffer must stay valid while
+ * attention launches are in flight; pass NULL to unregister. */
+GVF_API void gvf_attn_set_workspace(void* ws, size_t bytes);
+
 /* Benchmark tuning hook: tile scheduling variant of gvf_gemm_f16 (-1 automatic, 0 one 128x128 tile per
  * CTA, 1 persistent 128x128, 2 persistent 128x256 with a double-buffered TMEM accumulator). */
 GVF_API void gvf_gemm_set_variant(int v);

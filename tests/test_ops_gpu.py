@@ -84,7 +84,7 @@ def test_attention_matches_fp32(Nb, Lq, Lk, H, D):
     _close(o, _ref_attn(q, k, v, scale), 2e-3, "attention")
 
 
-@pytest.mark.parametrize("dbg", [0x10, 0x30, 0x14, 0x80, 0x84])
+@pytest.mark.parametrize("dbg", [0x10, 0x30, 0x14, 0x81, 0x84, 0x88])
 def test_attention_kernel_generations(dbg):
     """every d = 32 kernel variant the dispatcher can pick (v4 plain / MUFU ping-pong / polynomial share, v6
     MUFU-only / polynomial share), on shapes with 1..4 query tiles, ragged key counts, and scores whose row
@@ -139,6 +139,40 @@ def test_attention_packed_and_shared_views():
     out = torch.empty((T, Nt, H, D), dtype=torch.float16, device=DEV)
     ops.attention(qt, kt, vt, scale, out=out.permute(1, 0, 2, 3))
     _close(out.permute(1, 0, 2, 3), _ref_attn(qt, kt, vt, scale), 2e-3, "temporal view")
+
+
+@pytest.mark.parametrize("Lk,shared", [(4096, True), (2100, False), (1370, False)])
+def test_attention_last_wave_key_split(Lk, shared):
+    """384 (batch, head) units on 148 SMs: the units of the third wave are cut into three key ranges and merged
+    (attn_merge_kernel).  Checked on the first and the last batch entries (whole / split units) against torch,
+    and against the same launch with the scratch buffer unregistered (no split)."""
+    from gvfdiffusion_b200 import _lib, ops
+    g = _g(500 + Lk)
+    Nb, Lq, H, D = 24, 512, 16, 32
+    scale = 1.0 / math.sqrt(D)
+    q = (_rand((Nb, Lq, H, D), g) * 1.5).half()
+    if shared:
+        k, v = (_rand((Lk, H, D), g) * 1.5).half(), _rand((Lk, H, D), g).half()
+    else:
+        k, v = (_rand((Nb, Lk, H, D), g) * 1.5).half(), _rand((Nb, Lk, H, D), g).half()
+    out = ops.attention(q, k, v, scale, kv_shared=shared)
+    for sl in (slice(0, 2), slice(Nb - 2, Nb)):
+        kk = k[None].expand(2, -1, -1, -1) if shared else k[sl]
+        vv = v[None].expand(2, -1, -1, -1) if shared else v[sl]
+        _close(out[sl], _ref_attn(q[sl], kk, vv, scale), 2e-3, f"Lk {Lk} batches {sl}")
+    L = _lib.lib()
+    L.gvf_attn_set_workspace(None, 0)
+    try:
+        whole = ops.attention.__wrapped__(q, k, v, scale, kv_shared=shared) if hasattr(ops.attention, "__wrapped__") else None
+        if whole is None:
+            saved, ops._attn_ws = ops._attn_ws, torch.empty(1, device=DEV)     # keep _ensure_attn_ws from re-registering
+            try:
+                whole = ops.attention(q, k, v, scale, kv_shared=shared)
+            finally:
+                ops._attn_ws = saved
+    finally:
+        L.gvf_attn_set_workspace(_lib.ptr(ops._attn_ws), ops._attn_ws.numel() * 4)
+    _close(out, whole.float(), 1e-3, f"split vs whole Lk {Lk}")
 
 
 @pytest.mark.parametrize("T,H", [(24, 16), (32, 8), (5, 8), (17, 16), (16, 8)])

@@ -15,7 +15,7 @@ def run(): ops.attention(q, kv[:, 0], kv[:, 1], 1 / math.sqrt(D), out=o, kv_shar
 # fp32 reference of the first two frames
 sc = torch.einsum("tnhd,khd->thnk", q[:2].float(), kv[:, 0].float()) / math.sqrt(D)
 ref = torch.einsum("thnk,khd->tnhd", sc.softmax(-1), kv[:, 1].float())
-for dbg, name in [(0x30, "v4 pingpong"), (0x81, "v6 mufu"), (0x84, "v6 1/4 poly"), (0x88, "v6 1/8 poly"), (0, "default")]:
+for dbg, name in [(0x30, "v4 pingpong"), (0x81, "v6 mufu"), (0x84, "v6 1/4 poly"), (0x88, "v6 1/8 poly"), (0, "default (1/8 poly)")]:
     L.gvf_attn_set_debug(dbg)
     for _ in range(3): run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
