@@ -38,3 +38,28 @@ def windowed_attention(qkv_feats, coords, window_size, shift_window=0):
         s = torch.einsum("qhc,khc->hqk", q[sel], k[sel]) * scale
         out[sel] = torch.einsum("hqk,khc->qhc", s.softmax(-1), v[sel])
     return out
+
+
+def transformer_blocks(sd, prefix, num_blocks, num_heads, feats, coords, window_size, precision="fp32"):
+    """Stack of un-modulated SparseTransformerBlock (reference model/sparse_voxel_diffusion/sparse_transformer.py
+    :126-192 with modulated=False, attn_mode "swin": block i uses shift_window = window_size // 2 * (i % 2),
+    :24-25) over a reference-keyed state dict: `{prefix}{i}.attn.to_qkv|to_out`, `{prefix}{i}.mlp.mlp.0|2`.
+    feats [T, C] fp32, coords [T, 4] int -> [T, C] fp32.  precision="fp16" emulates the autocast regime
+    (Linear / attention in fp16, LayerNorm and the residual stream in fp32), as oracle/dit.py does."""
+    import torch.nn.functional as F
+    from .dit import _P
+    P = _P(precision)
+    x = feats.float()
+    C = x.shape[1]
+    for i in range(num_blocks):
+        p = f"{prefix}{i}."
+        shift = window_size // 2 * (i % 2)
+        h = F.layer_norm(x, (C,), None, None, 1e-6)
+        qkv = P.linear(h, sd[p + "attn.to_qkv.weight"], sd[p + "attn.to_qkv.bias"]).reshape(-1, 3, num_heads, C // num_heads)
+        a = P.r(windowed_attention(qkv, coords, window_size, shift)).reshape(-1, C)
+        x = x + P.linear(a, sd[p + "attn.to_out.weight"], sd[p + "attn.to_out.bias"])
+        h = F.layer_norm(x, (C,), None, None, 1e-6)
+        h = P.linear(h, sd[p + "mlp.mlp.0.weight"], sd[p + "mlp.mlp.0.bias"])
+        h = P.r(F.gelu(h, approximate="tanh"))
+        x = x + P.linear(h, sd[p + "mlp.mlp.2.weight"], sd[p + "mlp.mlp.2.bias"])
+    return x

@@ -60,3 +60,26 @@ def test_windowed_attention_on_reference_partition_fixture():
                                                     max(c["seq_lens"]), H, 64, 1.0 / math.sqrt(64), current_stream()),
               "gvf_sparse_window_attn_f16")
         assert (out.float() - ours.float()).abs().max().item() < 2e-3
+
+
+def test_sparse_transformer_blocks_match_oracle():
+    """Two swin blocks (unshifted + shifted windows) at the static-VAE width (768 = 12 heads x 64) on ~2 x 700
+    voxels: device engine against the torch restatement of SparseTransformerBlock (fp16-emulating and fp32)."""
+    from gvfdiffusion_b200.sparse.transformer import SparseTransformerBlocks
+    from oracle import sparse_window as OSW
+    g = torch.Generator().manual_seed(21)
+    C, H, NB = 768, 12, 2
+    sd = {}
+    for i in range(NB):
+        for name, (o, k) in {"attn.to_qkv": (3 * C, C), "attn.to_out": (C, C), "mlp.mlp.0": (4 * C, C), "mlp.mlp.2": (C, 4 * C)}.items():
+            sd[f"blocks.{i}.{name}.weight"] = torch.randn(o, k, generator=g) * 0.03
+            sd[f"blocks.{i}.{name}.bias"] = torch.randn(o, generator=g) * 0.05
+    coords = _voxels(700, 32, 2, seed=3)
+    feats = torch.randn(coords.shape[0], C, generator=g)
+    eng = SparseTransformerBlocks(sd, "blocks.", NB, H, 8, device=DEV)
+    y = eng.forward(feats.to(DEV), coords.to(DEV)).cpu()
+    y16 = OSW.transformer_blocks(sd, "blocks.", NB, H, feats, coords, 8, "fp16")
+    y32 = OSW.transformer_blocks(sd, "blocks.", NB, H, feats, coords, 8, "fp32")
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(y, y16) < 1e-3, rel(y, y16)
+    assert rel(y, y32) < 3e-3, rel(y, y32)
