@@ -40,7 +40,8 @@ def windowed_attention(qkv_feats, coords, window_size, shift_window=0):
     return out
 
 
-def transformer_blocks(sd, prefix, num_blocks, num_heads, feats, coords, window_size, precision="fp32"):
+def transformer_blocks(sd, prefix, num_blocks, num_heads, feats, coords, window_size, precision="fp32",
+                       fp16_residual=False):
     """Stack of un-modulated SparseTransformerBlock (reference model/sparse_voxel_diffusion/sparse_transformer.py
     :126-192 with modulated=False, attn_mode "swin": block i uses shift_window = window_size // 2 * (i % 2),
     :24-25) over a reference-keyed state dict: `{prefix}{i}.attn.to_qkv|to_out`, `{prefix}{i}.mlp.mlp.0|2`.
@@ -49,7 +50,8 @@ def transformer_blocks(sd, prefix, num_blocks, num_heads, feats, coords, window_
     import torch.nn.functional as F
     from .dit import _P
     P = _P(precision)
-    x = feats.float()
+    rr = (lambda t: t.half().float()) if fp16_residual else (lambda t: t)     # x.type(fp16) residual stream
+    x = rr(feats.float())
     C = x.shape[1]
     for i in range(num_blocks):
         p = f"{prefix}{i}."
@@ -57,9 +59,25 @@ def transformer_blocks(sd, prefix, num_blocks, num_heads, feats, coords, window_
         h = F.layer_norm(x, (C,), None, None, 1e-6)
         qkv = P.linear(h, sd[p + "attn.to_qkv.weight"], sd[p + "attn.to_qkv.bias"]).reshape(-1, 3, num_heads, C // num_heads)
         a = P.r(windowed_attention(qkv, coords, window_size, shift)).reshape(-1, C)
-        x = x + P.linear(a, sd[p + "attn.to_out.weight"], sd[p + "attn.to_out.bias"])
+        x = rr(x + P.linear(a, sd[p + "attn.to_out.weight"], sd[p + "attn.to_out.bias"]))
         h = F.layer_norm(x, (C,), None, None, 1e-6)
         h = P.linear(h, sd[p + "mlp.mlp.0.weight"], sd[p + "mlp.mlp.0.bias"])
         h = P.r(F.gelu(h, approximate="tanh"))
-        x = x + P.linear(h, sd[p + "mlp.mlp.2.weight"], sd[p + "mlp.mlp.2.bias"])
+        x = rr(x + P.linear(h, sd[p + "mlp.mlp.2.weight"], sd[p + "mlp.mlp.2.bias"]))
     return x
+
+
+def vae_decode(sd, num_blocks, num_heads, latent, coords, window_size=8, precision="fp16", use_fp16=True,
+               norm_output=False):
+    """SparseTransformerVAE.decode (sparse_transformer_vae.py:178-188): from_latent + APE of the voxel
+    coordinates (sparse_transformer.py:62-109) -> decoder blocks -> optional layer_norm (eps 1e-5) -> out_layer."""
+    import torch.nn.functional as F
+    from .dit import _P, absolute_position_embedding
+    P = _P(precision)
+    C = sd["from_latent.weight"].shape[0]
+    h = P.linear(latent.float(), sd["from_latent.weight"], sd["from_latent.bias"])
+    h = h + absolute_position_embedding(coords[:, 1:].float()[None], C)[0]
+    h = transformer_blocks(sd, "decoder.", num_blocks, num_heads, h, coords, window_size, precision, fp16_residual=use_fp16)
+    if norm_output:
+        h = F.layer_norm(h, (C,))
+    return P.linear(h, sd["out_layer.weight"], sd["out_layer.bias"])

@@ -83,3 +83,25 @@ def test_sparse_transformer_blocks_match_oracle():
     rel = lambda a, b: float((a - b).norm() / b.norm())
     assert rel(y, y16) < 1e-3, rel(y, y16)
     assert rel(y, y32) < 3e-3, rel(y, y32)
+
+
+def test_sparse_vae_decode_matches_oracle():
+    """SparseTransformerVAE.decode at the shipped widths (latent 8 -> 768, 12 heads, out 112, norm_output, fp16
+    residual stream), 2 blocks, against the torch restatement."""
+    from gvfdiffusion_b200.sparse.transformer import SparseTransformerVAE
+    from oracle import sparse_window as OSW
+    g = torch.Generator().manual_seed(33)
+    C, H, NB = 768, 12, 2
+    sd = {"from_latent.weight": torch.randn(C, 8, generator=g) * 0.3, "from_latent.bias": torch.randn(C, generator=g) * 0.1,
+          "out_layer.weight": torch.randn(112, C, generator=g) * 0.03, "out_layer.bias": torch.randn(112, generator=g) * 0.1}
+    for i in range(NB):
+        for name, (o, k) in {"attn.to_qkv": (3 * C, C), "attn.to_out": (C, C), "mlp.mlp.0": (4 * C, C), "mlp.mlp.2": (C, 4 * C)}.items():
+            sd[f"decoder.{i}.{name}.weight"] = torch.randn(o, k, generator=g) * 0.03
+            sd[f"decoder.{i}.{name}.bias"] = torch.randn(o, generator=g) * 0.05
+    coords = _voxels(600, 64, 2, seed=9)
+    latent = torch.randn(coords.shape[0], 8, generator=g)
+    vae = SparseTransformerVAE(sd, NB, H, 8, use_fp16=True, norm_output=True, device=DEV)
+    y = vae.decode(latent.to(DEV), coords.to(DEV)).cpu()
+    ref = OSW.vae_decode(sd, NB, H, latent, coords, 8, "fp16", use_fp16=True, norm_output=True)
+    rel = float((y - ref).norm() / ref.norm())
+    assert y.shape == (coords.shape[0], 112) and rel < 2e-3, rel
