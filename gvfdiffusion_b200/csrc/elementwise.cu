@@ -36,10 +36,11 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const TIn* __restrict__ x, 
                                                      const __half* __restrict__ scale, int mod_stride,
                                                      int rows_per_batch) {
   constexpr int PER = C / 32;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   tc::pdl_wait();
-  if (row >= M) return;
+  // grid-stride over rows: the grid is at most one resident wave (148 SMs x 8 CTAs), so there is no
+  // partially filled second wave (12288 rows = 1536 CTAs of 8 rows were 1.3 waves)
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += gridDim.x * 8) {
   float v[PER];
   const TIn* xr = x + (size_t)row * C;
   if constexpr (!VEC) {
@@ -88,14 +89,29 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const TIn* __restrict__ x, 
     const int c = (i * 32 + lane) * 4;
     __align__(8) __half h[4];
 #pragma unroll
+    float wv[4] = {1.f, 1.f, 1.f, 1.f}, bv[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+    if (w) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c)), b4 = __ldg(reinterpret_cast<const float4*>(bvec + c));
+      wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+      bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w;
+    }
+    if (scale) {                                     // mod_stride and the modulation offsets are multiples of 4
+      const uint2 s2 = *reinterpret_cast<const uint2*>(scale + (size_t)b * mod_stride + c);
+      const uint2 h2 = *reinterpret_cast<const uint2*>(shift + (size_t)b * mod_stride + c);
+      const __half* sp = reinterpret_cast<const __half*>(&s2);
+      const __half* hp = reinterpret_cast<const __half*>(&h2);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { sc[t] = __half2float(sp[t]); sh[t] = __half2float(hp[t]); }
+    }
+#pragma unroll
     for (int t = 0; t < 4; ++t) {
       float y = (v[i * 4 + t] - mean) * rstd;
-      if (w) y = y * w[c + t] + bvec[c + t];
-      if (scale) y = y * (1.0f + __half2float(scale[(size_t)b * mod_stride + c + t])) +
-                     __half2float(shift[(size_t)b * mod_stride + c + t]);
+      if (w) y = y * wv[t] + bv[t];
+      if (scale) y = y * (1.0f + sc[t]) + sh[t];
       h[t] = __float2half_rn(y);
     }
     *reinterpret_cast<uint2*>(orow + c) = *reinterpret_cast<uint2*>(h);
+  }
   }
 }
 
@@ -488,7 +504,17 @@ GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C,
   if (!x || !out || M <= 0) return GVF_ERR_INVALID;
   if ((w == nullptr) != (b == nullptr) || (shift == nullptr) != (scale == nullptr)) return GVF_ERR_INVALID;
   const int rpb = rows_per_batch > 0 ? rows_per_batch : M;
-  const dim3 grid((M + 7) / 8);
+  // the vector path reads 4 modulation / affine values at a time
+  if (shift && ((mod_stride % 4) || ((uintptr_t)shift & 7) || ((uintptr_t)scale & 7))) return GVF_ERR_INVALID;
+  if (w && (((uintptr_t)w | (uintptr_t)b) & 15)) return GVF_ERR_INVALID;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int want = (M + 7) / 8, cap = num_sms * 8;
+  const dim3 grid(want < cap ? want : cap);
 #define LN_CASE(T, CC, V)                                                                          \
   launch_pdl(ln_mod_kernel<T, CC, V>, grid, dim3(256), 0, ST(stream), (const T*)x, (__half*)out, M, eps, w, b, \
              (const __half*)shift, (const __half*)scale, mod_stride, rpb)
