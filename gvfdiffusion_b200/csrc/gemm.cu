@@ -393,7 +393,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 //     the accumulator wait, so its DRAM latency overlaps the main loop of the tile.
 // Same rounding points as epilogue_tile() above.  320 threads: warp 0 TMA producer, warp 1 MMA issuer,
 // warps 2-9 epilogue; accumulators double buffered in TMEM (2 x BN columns).
-template <int BN, int STAGES, int MODE>
+template <int BN, int STAGES, int MODE, int NCTA>
 __global__ void __launch_bounds__(320, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ CUtensorMap mapO, int M, int N, int K, GemmEpi ep) {
@@ -402,27 +402,34 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[2][BN];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = BN * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  // NCTA = 2: a CTA pair computes a 256 x BN tile with tcgen05.mma.cta_group::2 -- this CTA stages its own 128
+  // rows of A and BN / 2 rows of W (the operand bytes entering each SM drop by a third at BN = 256), the leader
+  // (cluster rank 0) issues the MMAs for both, each CTA runs the epilogue of its own 128 accumulator rows.
+  constexpr int WROWS = BN / NCTA;
+  constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = WROWS * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
   uint8_t* stg_base = smem + STAGES * STAGE_BYTES;              // 8 warps x 2 buffers x 4 KB, 1 KB aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = (K + kBK - 1) / kBK;
-  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + kBM - 1) / kBM;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + NCTA * kBM - 1) / (NCTA * kBM);   // pair tiles for NCTA = 2
   const int num_tiles = tiles_n * tiles_m;
+  const int first_tile = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8 * NCTA); }
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapW);
     tma_prefetch_desc(&mapO);
   }
   if (warp == 2) {
-    tmem_alloc(&tmem_base_s, 2 * BN);
-    tmem_relinquish();
+    if constexpr (NCTA == 2) { tmem_alloc_2cta(&tmem_base_s, 2 * BN); tmem_relinquish_2cta(); }
+    else { tmem_alloc(&tmem_base_s, 2 * BN); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();      // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   pdl_wait();                       // everything above is independent of the previous kernel's output
   const uint32_t tmem = tmem_base_s;
@@ -430,23 +437,30 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
           uint8_t* st = smem + s * STAGE_BYTES;
-          tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
-          tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
+          if constexpr (NCTA == 2) {
+            // both CTAs' bytes are credited to the leader's full barrier, which expects the sum
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            tma_load_2d_2cta(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+            tma_load_2d_2cta(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN + (int)rank * WROWS);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+            tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kBM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM * NCTA, BN, 0, 0);
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++lt) {
         const int acc = lt & 1;
         mbar_wait(&tempty_bar[acc], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -456,12 +470,15 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tc_fence_after();
           const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), w0 = a0 + A_BYTES;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            mma_ss(tmem + acc * BN, make_smem_desc(a0 + k * 32, 16, 1024, SWZ_128B),
-                   make_smem_desc(w0 + k * 32, 16, 1024, SWZ_128B), idesc, (kb | k) != 0);
-          tc_commit(&empty_bar[s]);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a0 + k * 32, 16, 1024, SWZ_128B);
+            const uint64_t wd = make_smem_desc(w0 + k * 32, 16, 1024, SWZ_128B);
+            if constexpr (NCTA == 2) mma_ss_2cta(tmem + acc * BN, ad, wd, idesc, (kb | k) != 0);
+            else mma_ss(tmem + acc * BN, ad, wd, idesc, (kb | k) != 0);
+          }
+          if constexpr (NCTA == 2) tc_commit_2cta(&empty_bar[s]); else tc_commit(&empty_bar[s]);
         }
-        tc_commit(&tfull_bar[acc]);
+        if constexpr (NCTA == 2) tc_commit_2cta(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
       }
     }
   } else {
@@ -475,8 +492,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint8_t* stg = stg_base + ew * 2 * 4096;
     const uint32_t sw = (uint32_t)(lane & 7);      // SWIZZLE_128B: 16 B piece j of row r sits at j ^ (r & 7)
     int lt = 0, sbuf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++lt) {
+      const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
       const int acc = lt & 1;
       float* sb = s_bias[acc];
       for (int c = et; c < BN; c += 256) {
@@ -633,24 +650,29 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (NCTA == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if (lane == 0) tma_store_wait_all();
   }
   pdl_launch_dependents();          // this CTA only has its teardown left
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 2 * BN);
+  if constexpr (NCTA == 2) cluster_sync_all();      // nobody signals the peer's shared memory after this point
+  else __syncthreads();
+  if (warp == 2) {
+    if constexpr (NCTA == 2) tmem_dealloc_2cta(tmem, 2 * BN); else tmem_dealloc(tmem, 2 * BN);
+  }
 }
 
-template <int BN, int STAGES, int MODE>
+template <int BN, int STAGES, int MODE, int NCTA = 1>
 static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CUtensorMap& mO, int M, int N, int K,
                           const GemmEpi& ep, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 8 * 2 * 4096 + 1024;
+  constexpr int SMEM = STAGES * (kBM * kBK * 2 + (BN / NCTA) * kBK * 2) + 8 * 2 * 4096 + 1024;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
         cudaSuccess)
       return GVF_ERR_CUDA;
     int dev = 0;
@@ -658,10 +680,28 @@ static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CU
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  const int tiles = ((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep) == cudaSuccess
-             ? GVF_OK : GVF_ERR_CUDA;
+  const int tiles = ((N + BN - 1) / BN) * ((M + NCTA * kBM - 1) / (NCTA * kBM));
+  const int slots = num_sms / NCTA;
+  const int grid = (tiles < slots ? tiles : slots) * NCTA;
+  if constexpr (NCTA == 1) {
+    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep) == cudaSuccess
+               ? GVF_OK : GVF_ERR_CUDA;
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_ws_kernel<BN, STAGES, MODE, 2>, mA, mW, mO, M, N, K, ep) == cudaSuccess ? GVF_OK
+                                                                                                            : GVF_ERR_CUDA;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -976,24 +1016,31 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
   if (epilogue == 2 && gate && rows_per_batch <= 0) return GVF_ERR_INVALID;
   // variant: 0 = one tile per CTA, 2 CTAs / SM, 3 stages; 1 = persistent 128x128; 2 = persistent 128x256;
-  //          3 = one tile per CTA, 3 CTAs / SM, 2 stages, 32-column epilogue chunks
+  //          3 = one tile per CTA, 3 CTAs / SM, 2 stages, 32-column epilogue chunks;
+  //          4 / 5 = generation 2 (8 epilogue warps, TMA stores) 128x128 / 128x256; 6 / 7 = generation 2 on CTA pairs,
+  //          256x128 / 256x256 pair tiles
   int variant = g_gemm_variant;
   if (variant < 0) {
     // measured on B200 (tools/gemm_bench.py, profiles/r01_gemm_variants.txt): the generation-2 kernels win on
     // every shape of the path; 128 x 256 tiles whenever N allows them and there is more than one column of
     // tiles per row block to amortise the wider epilogue (N >= 768), or the epilogue is a plain fp16 store
     variant = (N % 256 == 0 && (N >= 768 || epilogue == 0 || epilogue == 1)) ? 5 : 4;
+    // CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA stages half of W): -6..-11 % on the long-K
+    // motion-VAE shapes (ff1 101.9 -> 91.0 us, cuBLAS 92.1), nothing on the K = 512 DiT shapes, which are bound by
+    // ramp-up and epilogue latency rather than by L2 -> SM operand traffic
+    if (variant == 5 && K >= 768 && M >= 2 * kBM * 74) variant = 7;
   }
   // generation-2 kernels need a TMA-storable output (16 B aligned rows) and do not do the compact mode 5
-  if ((variant == 4 || variant == 5) &&
+  if (variant >= 4 && variant <= 7 &&
       (epilogue == 5 || (ldo * ((epilogue == 2 || epilogue == 4) ? 4 : 2)) % 16 != 0 ||
        (gate && ((gate_stride % 8) || ((uintptr_t)gate & 15)))))
     variant = 0;
-  const int BN = (variant == 2 || variant == 5) ? 256 : 128;
+  const int BN = (variant == 2 || variant == 5 || variant == 7) ? 256 : 128;
+  const int wbox = (variant == 6 || variant == 7) ? BN / 2 : BN;      // W rows one CTA stages per k-block
   CUtensorMap mA, mW;
   const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {1, (uint64_t)lda};
   const uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}, sW[2] = {1, (uint64_t)ldw};
-  const uint32_t bA[2] = {kBK, kBM}, bW[2] = {kBK, (uint32_t)BN};
+  const uint32_t bA[2] = {kBK, kBM}, bW[2] = {kBK, (uint32_t)wbox};
   if (!make_tmap_f16(&mA, A, 2, dA, sA, bA, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
   if (!make_tmap_f16(&mW, W, 2, dW, sW, bW, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
   GemmEpi ep;
@@ -1001,16 +1048,18 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   ep.gate_stride = gate_stride; ep.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   ep.ldo = ldo;
   ep.gamma_q = gamma_q; ep.gamma_k = gamma_k; ep.norm_cols = norm_cols;
-  if (variant == 4 || variant == 5) {
+  if (variant >= 4 && variant <= 7) {
     const bool out16 = (epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6);
     CUtensorMap mO;
     if (!make_tmap_2d(&mO, out, out16 ? 2 : 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, out16 ? 64 : 32, 32))
       return GVF_ERR_CUDA;
     cudaStream_t cs = (cudaStream_t)stream;
-#define GVF_WS(MODE)                                                                    \
-    case MODE:                                                                          \
-      return variant == 5 ? launch_gemm_ws<256, 3, MODE>(mA, mW, mO, M, N, K, ep, cs)   \
-                          : launch_gemm_ws<128, 4, MODE>(mA, mW, mO, M, N, K, ep, cs);
+#define GVF_WS(MODE)                                                                      \
+    case MODE:                                                                            \
+      return variant == 7   ? launch_gemm_ws<256, 4, MODE, 2>(mA, mW, mO, M, N, K, ep, cs) \
+             : variant == 6 ? launch_gemm_ws<128, 5, MODE, 2>(mA, mW, mO, M, N, K, ep, cs) \
+             : variant == 5 ? launch_gemm_ws<256, 3, MODE>(mA, mW, mO, M, N, K, ep, cs)    \
+                            : launch_gemm_ws<128, 4, MODE>(mA, mW, mO, M, N, K, ep, cs);
     switch (epilogue) {
       GVF_WS(0) GVF_WS(1) GVF_WS(2) GVF_WS(3) GVF_WS(4) GVF_WS(6)
       default: return GVF_ERR_INVALID;

@@ -176,8 +176,9 @@ GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, 
  * attention launches are in flight; pass NULL to unregister. */
 GVF_API void gvf_attn_set_workspace(void* ws, size_t bytes);
 
-/* Benchmark tuning hook: tile scheduling variant of gvf_gemm_f16 (-1 automatic, 0 one 128x128 tile per
- * CTA, 1 persistent 128x128, 2 persistent 128x256 with a double-buffered TMEM accumulator). */
+/* Benchmark tuning hook: tile scheduling variant of gvf_gemm_f16 (-1 automatic; 0 one 128x128 tile per CTA,
+ * 1 / 2 persistent 128x128 / 128x256, 3 three CTAs per SM, 4 / 5 generation 2 (eight epilogue warps, TMA stores)
+ * 128x128 / 128x256, 6 / 7 generation 2 on CTA pairs (cta_group::2) 256x128 / 256x256). */
 GVF_API void gvf_gemm_set_variant(int v);
 
 /* Programmatic dependent launch for the GEMM / attention / LayerNorm kernels (default OFF: measured slower

@@ -383,7 +383,7 @@ def test_gemm_resid_ln_fused(M, K, rpb, kind):
     _close(y1, ln, 2e-3, "y vs torch")
 
 
-@pytest.mark.parametrize("variant", [4, 5])
+@pytest.mark.parametrize("variant", [4, 5, 6, 7])
 def test_gemm_tma_epilogue_all_modes(variant):
     """Generation-2 kernels (eight epilogue warps, TMA stores): every fused epilogue, ragged M / N / K,
     gates spanning several batches inside one tile."""

@@ -20,7 +20,7 @@ for name, N, K, kind in shapes:
     o16 = torch.empty(M, N, dtype=torch.float16, device=dev)
     gq = torch.ones(N // 96, 32, device=dev) if kind == "qkv" else None
     res = []
-    for variant in (0, 1, 2, 3, 4, 5):
+    for variant in (0, 1, 2, 3, 4, 5, 6, 7):
         L.gvf_gemm_set_variant(variant)
         def run():
             if kind == "qkv": ops.gemm_qkv_rmsnorm(a, w, b, gq, gq, o16)
