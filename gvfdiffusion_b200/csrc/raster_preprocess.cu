@@ -14,6 +14,8 @@
 //
 // HBM-bound: reads 56 B canonical + 56 B delta per (frame, Gaussian), writes a 48 B splat
 // record + 8 B rect (+4 B radius); one global atomic per touched tile (1-4 typical).
+#include <stdlib.h>
+#include <cooperative_groups.h>
 #include "../../include/gvf_math.h"
 #include "raster_common.h"
 
@@ -363,6 +365,92 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(const float* __restri
   }
 }
 
+// Cluster variant: the cloud is spread over the 8 CTAs of one thread-block cluster, 512 threads each, every
+// thread keeps the coordinates and running minimum distances of its PER points in REGISTERS (the single-CTA
+// kernel above re-reads all 196 KB of coordinates from shared memory for every sample: 1536 clocks of
+// shared-memory bandwidth out of the 2770 a sample took).  Per sample: register-only distance update, warp
+// arg-max by redux, one __syncthreads, the CTA's candidate (distance, index, x, y, z) written to its own
+// shared memory, one cluster barrier, and every CTA reads the 8 candidates through distributed shared memory.
+// Same arithmetic and tie rule (lowest index) as fps_kernel: identical indices.
+namespace cg = cooperative_groups;
+constexpr int kFpsCluster = 8, kFpsThreads = 512;
+
+template <int PER>
+__global__ void __launch_bounds__(kFpsThreads, 1) fps_cluster_kernel(const float* __restrict__ pts, int ld, int P,
+                                                                     int K, int start, int* __restrict__ out_idx) {
+  __shared__ float wslot[2][16][5];                // per warp: (distance bits, index bits, x, y, z)
+  __shared__ float cand[2][8];                     // this CTA's best, same five fields
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float px[PER], py[PER], pz[PER], md[PER];
+  int gi[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    // global point index: interleaved so that every CTA owns the same share of any prefix of the cloud
+    const int i = (j * kFpsThreads + tid) * kFpsCluster + (int)rank;
+    gi[j] = i;
+    const bool ok = i < P;
+    px[j] = ok ? pts[(size_t)i * ld] : 0.f;
+    py[j] = ok ? pts[(size_t)i * ld + 1] : 0.f;
+    pz[j] = ok ? pts[(size_t)i * ld + 2] : 0.f;
+    md[j] = ok ? 3.0e38f : -1.0f;
+  }
+  float cx = pts[(size_t)start * ld], cy = pts[(size_t)start * ld + 1], cz = pts[(size_t)start * ld + 2];
+  if (rank == 0 && tid == 0) out_idx[0] = start;
+  // arg-max over the 32 lanes of (distance bits, then lowest index); returns the winning lane
+  auto warp_best = [&](unsigned ub, unsigned bi, unsigned& wm, unsigned& wi) {
+    wm = __reduce_max_sync(0xffffffffu, ub);
+    wi = __reduce_min_sync(0xffffffffu, ub == wm ? bi : 0xffffffffu);
+    return __ffs(__ballot_sync(0xffffffffu, ub == wm && bi == wi)) - 1;
+  };
+  for (int k = 1; k < K; ++k) {
+    float best = -1.0f, bx = 0.f, by = 0.f, bz = 0.f;
+    unsigned bi = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const float dx = px[j] - cx, dy = py[j] - cy, dz = pz[j] - cz;
+      const float d = fminf(md[j], dx * dx + dy * dy + dz * dz);
+      md[j] = d;
+      if (d > best) { best = d; bi = (unsigned)gi[j]; bx = px[j]; by = py[j]; bz = pz[j]; }   // first max kept
+    }
+    const int b = k & 1;
+    unsigned wm, wi;
+    int src = warp_best(best < 0.f ? 0u : __float_as_uint(best), bi, wm, wi);
+    if (lane == src) {
+      wslot[b][w][0] = __uint_as_float(wm); wslot[b][w][1] = __uint_as_float(wi);
+      wslot[b][w][2] = bx; wslot[b][w][3] = by; wslot[b][w][4] = bz;
+    }
+    __syncthreads();
+    if (w == 0) {
+      const int l = lane & 15;
+      const unsigned ub = lane < 16 ? __float_as_uint(wslot[b][l][0]) : 0u;
+      const unsigned ui = lane < 16 ? __float_as_uint(wslot[b][l][1]) : 0xffffffffu;
+      src = warp_best(ub, ui, wm, wi);
+      if (lane == src) {
+        cand[b][0] = __uint_as_float(wm); cand[b][1] = __uint_as_float(wi);
+        cand[b][2] = wslot[b][l][2]; cand[b][3] = wslot[b][l][3]; cand[b][4] = wslot[b][l][4];
+      }
+    }
+    cluster.sync();
+    // every warp reduces the 8 CTA candidates itself (lane r reads CTA r's slot through distributed smem)
+    unsigned cm = 0u, ci = 0xffffffffu;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (lane < kFpsCluster) {
+      const float* rc = cluster.map_shared_rank(&cand[b][0], lane);
+      cm = __float_as_uint(rc[0]);
+      ci = __float_as_uint(rc[1]);
+      nx = rc[2]; ny = rc[3]; nz = rc[4];
+    }
+    src = warp_best(cm, ci, wm, wi);
+    cx = __shfl_sync(0xffffffffu, nx, src);
+    cy = __shfl_sync(0xffffffffu, ny, src);
+    cz = __shfl_sync(0xffffffffu, nz, src);
+    if (rank == 0 && tid == 0) out_idx[k] = (int)wi;
+  }
+  cluster.sync();                                  // nobody reads a peer's shared memory after it has exited
+}
+
 }  // namespace gvf
 
 extern "C" GVF_API int gvf_gaussian_tensor(const gvf_raster_params* prm, int P, const float* xyz,
@@ -385,6 +473,35 @@ extern "C" GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start
     return true;
   };
   bool ok = true;
+  // MEASURED (tools/fps_bench.py, 16384 -> 4096): cluster kernel 7.2 ms, single-CTA shared-memory kernel 5.7 ms --
+  // the cluster barrier costs more per sample (~1.7 us) than the shared-memory re-read it removes, so the
+  // single-CTA kernels stay the default; GVF_FPS=cluster selects the cluster kernel (identical indices).
+  static int fps_mode = -1;
+  if (fps_mode < 0) {
+    const char* e = getenv("GVF_FPS");
+    fps_mode = (e && e[0] == 'c') ? 0 : 1;
+  }
+  auto launch_cluster = [&](auto kern) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gvf::kFpsCluster);
+    cfg.blockDim = dim3(gvf::kFpsThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = gvf::kFpsCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, pts, ld, P, K, start, (int*)out_idx) == cudaSuccess;
+  };
+  if (fps_mode == 0 && P > 1024 && P <= 16384) {
+    const int per = (P + gvf::kFpsCluster * gvf::kFpsThreads - 1) / (gvf::kFpsCluster * gvf::kFpsThreads);
+    ok = per <= 1 ? launch_cluster(gvf::fps_cluster_kernel<1>) : per <= 2 ? launch_cluster(gvf::fps_cluster_kernel<2>)
+                                                                           : launch_cluster(gvf::fps_cluster_kernel<4>);
+    return (ok && cudaGetLastError() == cudaSuccess) ? GVF_OK : GVF_ERR_CUDA;
+  }
   if (P <= 4096) ok = launch_smem(gvf::fps_smem_kernel<4>, 4);
   else if (P <= 8192) ok = launch_smem(gvf::fps_smem_kernel<8>, 8);
   else if (P <= 16384) ok = launch_smem(gvf::fps_smem_kernel<16>, 16);
