@@ -1043,39 +1043,36 @@ static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
 // third wave are cut into three key ranges each (264 items = two rounds of one third), which ends the wave
 // at 2/3 of its length; the merge costs ~5 us.
 __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnArgs a, int n_split_units) {
+  // eight threads per query row, four output columns each: every partial row is read as one 128 B segment
   const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= n_split_units * 512) return;
-  const int su = idx >> 9, r = idx & 511;
+  const int rr = idx >> 3, c4 = (idx & 7) * 4;
+  if (rr >= n_split_units * 512) return;
+  const int su = rr >> 9, r = rr & 511;
   const int unit = a.split_from + su;
   const int qblk = unit % a.gx, h = (unit / a.gx) % a.H, nb = unit / (a.gx * a.H);
   const int qi = qblk * 512 + r;
   if (qi >= a.Lq) return;
+  float2 ml[4];
   float M = -INFINITY;
-  for (int p = 0; p < a.nsplit; ++p) M = fmaxf(M, a.ws_ml[(((size_t)su * a.nsplit + p) * 512 + r) * 2]);
-  float o[32], l = 0.f;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) o[k] = 0.f;
+  for (int p = 0; p < a.nsplit; ++p) {
+    ml[p] = *reinterpret_cast<const float2*>(a.ws_ml + (((size_t)su * a.nsplit + p) * 512 + r) * 2);
+    M = fmaxf(M, ml[p].x);
+  }
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, l = 0.f;
   for (int p = 0; p < a.nsplit; ++p) {
     const size_t pr = ((size_t)su * a.nsplit + p) * 512 + r;
-    const float2 ml = *reinterpret_cast<const float2*>(a.ws_ml + pr * 2);
-    const float w = fast_exp2((ml.x - M) * a.scale_log2e);
-    l = fmaf(w, ml.y, l);
-#pragma unroll
-    for (int k = 0; k < 32; k += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(a.ws_o + pr * 32 + k);
-      o[k] = fmaf(w, v.x, o[k]); o[k + 1] = fmaf(w, v.y, o[k + 1]);
-      o[k + 2] = fmaf(w, v.z, o[k + 2]); o[k + 3] = fmaf(w, v.w, o[k + 3]);
-    }
+    const float w = fast_exp2((ml[p].x - M) * a.scale_log2e);
+    l = fmaf(w, ml[p].y, l);
+    const float4 v = *reinterpret_cast<const float4*>(a.ws_o + pr * 32 + c4);
+    o0 = fmaf(w, v.x, o0); o1 = fmaf(w, v.y, o1); o2 = fmaf(w, v.z, o2); o3 = fmaf(w, v.w, o3);
   }
   const float inv = 1.0f / l;
-  __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h;
-#pragma unroll
-  for (int k = 0; k < 32; k += 8) {
-    __align__(16) __half hh[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(o[k + t] * inv);
-    *reinterpret_cast<uint4*>(op + k) = *reinterpret_cast<uint4*>(hh);
-  }
+  __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h + c4;
+  const __half2 lo = __floats2half2_rn(o0 * inv, o1 * inv), hi = __floats2half2_rn(o2 * inv, o3 * inv);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(op) = pk;
 }
 
 // caller-owned scratch for the split units (gvf_attn_set_workspace); no allocation happens in here
@@ -1125,7 +1122,8 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
   const dim3 grid(b.split_from + n_split_units * b.nsplit);
   if (launch_pdl(attn_fwd6_kernel<POLY, TRACE>, grid, dim3(640), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
   if (n_split_units) {
-    attn_merge_kernel<<<(n_split_units * 512 + 255) / 256, 256, 0, st>>>(b, n_split_units);
+    static_assert(NSPLIT <= 4, "attn_merge_kernel keeps the (m, l) pairs of at most four parts in registers");
+    attn_merge_kernel<<<(n_split_units * 512 * 8 + 255) / 256, 256, 0, st>>>(b, n_split_units);
     if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
   }
   return GVF_OK;

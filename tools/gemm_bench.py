@@ -10,9 +10,11 @@ rn = lambda *s: torch.randn(*s, generator=g).to(dev).half()
 M = 12288
 shapes = [("qkv(rms)", 1536, 512, "qkv"), ("out(resid)", 512, 512, "resid"), ("q(f16)", 512, 512, "f16"),
           ("fc1(gelu)", 2048, 512, "gelu"), ("fc2(resid)", 512, 2048, "resid"), ("vae ff1", 6144, 768, "f16"),
-          ("vae ff2", 768, 3072, "r16"), ("vae qkv", 2304, 768, "f16")]
+          ("vae ff2", 768, 3072, "r16"), ("vae qkv", 2304, 768, "f16"), ("img proj", 512, 1024, "f16", 32880),
+          ("img kv", 1024, 512, "f16", 32880)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for name, N, K, kind in shapes:
+for name, N, K, kind, *mm in shapes:
+    M = mm[0] if mm else 12288
     a, w = rn(M, K), rn(N, K)
     b = torch.randn(N, generator=g).to(dev)
     x = torch.randn(M, N, generator=g).to(dev)
