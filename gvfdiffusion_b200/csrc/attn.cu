@@ -458,9 +458,17 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_init(&o_full[x], 1);
     }
     fence_barrier_init();
-    tma_prefetch_desc(&mapQ);
-    tma_prefetch_desc(&mapK);
-    tma_prefetch_desc(&mapV);
+    // the Q tiles and the first K/V stages are requested right here, by the thread that has just created the
+    // barriers: their L2 / HBM latency overlaps the TMEM allocation and the CTA-wide barrier below
+    pdl_wait();
+    mbar_arrive_expect_tx(&q_full, nq * TILE_BYTES);
+    for (int t = 0; t < nq; ++t)
+      tma_load_4d(sQ + t * TILE_BYTES, &mapQ, &q_full, 0, h, q0 + t * 128, nb * a.q_batch_mul);
+    for (int j = 0; j < min(S, n_kv); ++j) {
+      mbar_arrive_expect_tx(&kv_full[j], 2 * TILE_BYTES);
+      tma_load_4d(sKV + j * 2 * TILE_BYTES, &mapK, &kv_full[j], 0, h, (t0 + j) * 128, nb * a.kv_batch_mul);
+      tma_load_4d(sKV + j * 2 * TILE_BYTES + TILE_BYTES, &mapV, &kv_full[j], 0, h, (t0 + j) * 128, nb * a.kv_batch_mul);
+    }
   }
   if (warp == 1) {
     tmem_alloc(&tmem_base_s, 512);
@@ -481,7 +489,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       const uint32_t qa = smem_u32(sQ) + x * TILE_BYTES, skv = smem_u32(sKV);
       const uint32_t tX = tmem + x * TM_STRIDE;
       // K/V ring, driven by tile 0's issuer between its MMA batches
-      int loaded = 0;
+      int loaded = min(S, n_kv);                   // the first stages were requested in the prologue
       auto load_kv = [&](int j) {
         const int s = j % S;
         mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
@@ -491,12 +499,6 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       auto pump = [&]() {                          // issue every load whose stage is already free
         while (loaded < n_kv && mbar_test_wait(&kv_empty[loaded % S], ((loaded / S) & 1) ^ 1)) load_kv(loaded++);
       };
-      if (x == 0) {
-        mbar_arrive_expect_tx(&q_full, nq * TILE_BYTES);
-        for (int t = 0; t < nq; ++t)
-          tma_load_4d(sQ + t * TILE_BYTES, &mapQ, &q_full, 0, h, q0 + t * 128, nb * a.q_batch_mul);
-        pump();
-      }
       auto issue_qk = [&](int i) {                 // S = Q K(block i)^T
         const uint32_t ka = skv + ((i >> 1) % S) * 2 * TILE_BYTES + (i & 1) * BLK * ROWB;
 #pragma unroll

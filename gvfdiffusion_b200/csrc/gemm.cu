@@ -419,9 +419,24 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8 * NCTA); }
     fence_barrier_init();
-    tma_prefetch_desc(&mapA);
-    tma_prefetch_desc(&mapW);
     tma_prefetch_desc(&mapO);
+    if constexpr (NCTA == 1) {
+      // first stages of the first tile: requested by the thread that has just created the barriers, so their
+      // latency overlaps the TMEM allocation and the CTA barrier (pairs must wait for the cluster barrier first)
+      pdl_wait();
+      if (first_tile < num_tiles) {
+        const int tile_m = first_tile / tiles_n, tile_n = first_tile % tiles_n;
+        for (int kb = 0; kb < (kblocks < STAGES ? kblocks : STAGES); ++kb) {
+          mbar_arrive_expect_tx(&full_bar[kb], STAGE_BYTES);
+          uint8_t* st = smem + kb * STAGE_BYTES;
+          tma_load_2d(st, &mapA, &full_bar[kb], kb * kBK, tile_m * kBM);
+          tma_load_2d(st + A_BYTES, &mapW, &full_bar[kb], kb * kBK, tile_n * BN);
+        }
+      }
+    } else {
+      tma_prefetch_desc(&mapA);
+      tma_prefetch_desc(&mapW);
+    }
   }
   if (warp == 2) {
     if constexpr (NCTA == 2) { tmem_alloc_2cta(&tmem_base_s, 2 * BN); tmem_relinquish_2cta(); }
@@ -437,9 +452,11 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
+      int skip = (NCTA == 1) ? (kblocks < STAGES ? kblocks : STAGES) : 0;     // requested in the prologue
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          if (skip > 0) { --skip; continue; }
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;

@@ -175,6 +175,19 @@ def test_attention_last_wave_key_split(Lk, shared):
     _close(out, whole.float(), 1e-3, f"split vs whole Lk {Lk}")
 
 
+def test_attention_key_split_ragged_query_blocks():
+    """Two query blocks per (batch, head), the second one partial (Lq = 1000), 320 units -> 24 split units."""
+    from gvfdiffusion_b200 import ops
+    g = _g(612)
+    Nb, Lq, Lk, H, D = 10, 1000, 2100, 16, 32
+    scale = 1.0 / math.sqrt(D)
+    q = (_rand((Nb, Lq, H, D), g) * 1.5).half()
+    k, v = (_rand((Nb, Lk, H, D), g) * 1.5).half(), _rand((Nb, Lk, H, D), g).half()
+    out = ops.attention(q, k, v, scale)
+    for sl in (slice(0, 1), slice(Nb - 1, Nb)):
+        _close(out[sl], _ref_attn(q[sl], k[sl], v[sl], scale), 2e-3, f"batches {sl}")
+
+
 @pytest.mark.parametrize("T,H", [(24, 16), (32, 8), (5, 8), (17, 16), (16, 8)])
 def test_attention_short_sequences_mma(T, H):
     """L <= 32 with contiguous heads, H % 8 == 0: the warp-level mma.sync kernel (DiT temporal attention),
