@@ -275,15 +275,53 @@ def main():
         torch.cuda.synchronize()
         return [ev[i].elapsed_time(ev[i + 1]) for i in range(3)] + [ev[4].elapsed_time(ev[0])]
 
+    # End to end: every step uploads its inputs from pinned host memory and reads its RGBA back.  The copies run
+    # on a second stream, double buffered: the upload of step k+1 and the read-back of step k-1 overlap the
+    # compute of step k (what a serving loop does); both still happen once per step inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = []
+    for _ in range(2):
+        slots.append({
+            "canon": {k: torch.empty_like(v, device=dev) for k, v in hin["canon"].items()},
+            "noise": torch.empty_like(hin["noise"], device=dev), "cond": torch.empty_like(hin["cond_images"], device=dev),
+            "out_dev": torch.empty((T_FRAMES, 4, RES, RES), dtype=torch.float32, device=dev),
+            "out_host": torch.empty((T_FRAMES, 4, RES, RES), dtype=torch.float32).pin_memory(),
+            "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "rendered": torch.cuda.Event()})
+    e2e_state = {"k": 0, "primed": False}
+
+    def upload(slot):
+        st = slots[slot]
+        copy_stream.wait_event(st["free"])                     # the compute that last read these buffers is done
+        with torch.cuda.stream(copy_stream):
+            for k, v in hin["canon"].items():
+                st["canon"][k].copy_(v, non_blocking=True)
+            st["noise"].copy_(hin["noise"], non_blocking=True)
+            st["cond"].copy_(hin["cond_images"], non_blocking=True)
+            st["ready"].record(copy_stream)
+
     def step_e2e():
+        cur = torch.cuda.current_stream()
+        if not e2e_state["primed"]:                            # very first call: nothing has been prefetched yet
+            for st in slots:
+                st["free"].record(cur)
+            upload(0)
+            e2e_state["primed"] = True
+        slot = e2e_state["k"] & 1
+        e2e_state["k"] += 1
+        st = slots[slot]
+        cur.wait_event(st["ready"])
+        upload(slot ^ 1)                                       # inputs of the NEXT step travel during this one
         dit.reset_conditioning()
-        c = {k: v.to(dev, non_blocking=True) for k, v in hin["canon"].items()}
-        n, ci = hin["noise"].to(dev, non_blocking=True), hin["cond_images"].to(dev, non_blocking=True)
-        o = pipe.prepare_object(c)
-        lat = pipe.sample(o, ci, n, steps=NFE)
+        o = pipe.prepare_object(st["canon"])
+        lat = pipe.sample(o, st["cond"], st["noise"], steps=NFE)
         delta = pipe.decode(lat, o)
-        pipe.render(o, delta, hin["ext"], hin["intr"], out=out_dev)
-        out_host.copy_(out_dev, non_blocking=True)
+        pipe.render(o, delta, hin["ext"], hin["intr"], out=st["out_dev"])
+        st["free"].record(cur)
+        st["rendered"].record(cur)
+        copy_stream.wait_event(st["rendered"])
+        with torch.cuda.stream(copy_stream):
+            st["out_host"].copy_(st["out_dev"], non_blocking=True)
+            st["free"].record(copy_stream)                     # out_dev may be overwritten once it has been read back
 
     def barrier():
         if world > 1:
@@ -317,6 +355,9 @@ def main():
         raise SystemExit("rasteriser tile-instance capacity overflowed: result invalid")
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    # the frames that reached the host through the overlapped path are the frames of the resident run
+    last = slots[(e2e_state["k"] - 1) & 1]["out_host"]
+    e2e_max_diff = float((last - out_dev.cpu()).abs().max())
     stage_ms = step_profiled()
     # rasteriser alone (24 frames), graph-free, for the HBM-side roofline
     torch.cuda.synchronize()
@@ -355,7 +396,9 @@ def main():
                    "num_rendered": Rn},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": out_host.numel() * 4},
+                "d2h_bytes_per_step": out_host.numel() * 4,
+                "max_abs_diff_vs_resident_rgba": e2e_max_diff,
+                "note": "copies on a second stream, double buffered: upload of step k+1 / read-back of step k-1 overlap step k"},
         "gpu_launches": launch_estimate() * args.steps,
         "roofline": {"bound": "tensor", "kernel": "attn_fwd6_kernel (d=32, static cross-attention, kv 4096)",
                      "achieved": dom.get("tflops"), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
