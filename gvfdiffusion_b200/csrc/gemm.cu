@@ -1045,7 +1045,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
     // CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA stages half of W): -6..-11 % on the long-K
     // motion-VAE shapes (ff1 101.9 -> 91.0 us, cuBLAS 92.1), nothing on the K = 512 DiT shapes, which are bound by
     // ramp-up and epilogue latency rather than by L2 -> SM operand traffic
-    if (variant == 5 && K >= 768 && M >= 2 * kBM * 74) variant = 7;
+    if (variant == 5 && K >= 768 && (long long)((M + 2 * kBM - 1) / (2 * kBM)) * (N / 256) >= 74) variant = 7;
   }
   // generation-2 kernels need a TMA-storable output (16 B aligned rows) and do not do the compact mode 5
   if (variant >= 4 && variant <= 7 &&
