@@ -1039,6 +1039,330 @@ static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------
+// v7 = v6 made persistent: one CTA per SM walks the work list (item = blockIdx.x, + gridDim.x, ...).  A
+// (batch, head) unit is only 8 .. 64 softmax blocks long, and every v6 CTA paid ~5 us of launch, barrier /
+// TMEM set-up, first-load latency, pipeline fill and drain around them (a third of the 16 us a spatial
+// self-attention CTA lasts).  Here the barriers and the TMEM allocation are made once, the K/V ring simply
+// continues into the next item's tiles, the next item's Q tiles are fetched into the other half of a double
+// buffer while the current item still runs, and a softmax warpgroup goes from its epilogue straight to block 0
+// of the next item, whose scores are already waiting in TMEM.  All mbarrier parities come from running
+// counters (K/V tiles / softmax blocks consumed so far) instead of the item-local indices of v6.
+// Requires Lq % 512 == 0 (all four query tiles of every item live, the barrier arrival counts are fixed).
+struct AttnItem {
+  int unit, part, h, nb, q0, t0, n_kv, b0, n_blk;
+};
+__device__ __forceinline__ AttnItem attn_item(const AttnArgs& a, int item) {
+  AttnItem it;
+  it.unit = item; it.part = -1;
+  if (item >= a.split_from) {
+    it.unit = a.split_from + (item - a.split_from) / a.nsplit;
+    it.part = (item - a.split_from) % a.nsplit;
+  }
+  const int qblk = it.unit % a.gx;
+  it.h = (it.unit / a.gx) % a.H;
+  it.nb = it.unit / (a.gx * a.H);
+  it.q0 = qblk * 512;
+  const int n_kv_all = (a.Lk + 127) / 128;
+  it.t0 = it.part < 0 ? 0 : (it.part * n_kv_all) / a.nsplit;
+  const int t1 = it.part < 0 ? n_kv_all : ((it.part + 1) * n_kv_all) / a.nsplit;
+  it.n_kv = t1 - it.t0;
+  it.b0 = 2 * it.t0;
+  it.n_blk = min((a.Lk + 63) / 64, 2 * t1) - it.b0;
+  return it;
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(640, 1)
+attn_fwd7_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a, const int n_items) {
+  constexpr int D = 32, BLK = 64, NT = 4;
+  constexpr int ROWB = D * 2;
+  constexpr int TILE_BYTES = 128 * ROWB;
+  constexpr uint64_t SWZ = SWZ_64B;
+  constexpr uint32_t SBO = 8 * ROWB;
+  constexpr int S = kAttnStages;
+  constexpr uint32_t TM_P = 64, TM_O = 96, TM_STRIDE = 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full[2], kv_full[S], kv_empty[S], s_full[NT], s_free[NT], p_full[NT], o_full[NT];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                              // 2 buffers x NT tiles
+  uint8_t* sKV = smem + 2 * NT * TILE_BYTES;       // S x (K tile, V tile)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first = blockIdx.x, step = gridDim.x;
+
+  auto load_q = [&](const AttnItem& it, int buf) {
+    mbar_arrive_expect_tx(&q_full[buf], NT * TILE_BYTES);
+    for (int t = 0; t < NT; ++t)
+      tma_load_4d(sQ + (buf * NT + t) * TILE_BYTES, &mapQ, &q_full[buf], 0, it.h, it.q0 + t * 128, it.nb * a.q_batch_mul);
+  };
+  auto load_kv = [&](const AttnItem& it, int j, int g) {      // local tile j of the item = running tile g of the ring
+    const int s = g % S;
+    mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+    tma_load_4d(sKV + s * 2 * TILE_BYTES, &mapK, &kv_full[s], 0, it.h, (it.t0 + j) * 128, it.nb * a.kv_batch_mul);
+    tma_load_4d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &mapV, &kv_full[s], 0, it.h, (it.t0 + j) * 128, it.nb * a.kv_batch_mul);
+  };
+
+  int pre = 0;                                     // K/V tiles requested in the prologue
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    for (int i = 0; i < S; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], NT); }
+    for (int x = 0; x < NT; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&s_free[x], 128);
+      mbar_init(&p_full[x], 128);
+      mbar_init(&o_full[x], 1);
+    }
+    fence_barrier_init();
+    pdl_wait();
+    const AttnItem it0 = attn_item(a, first);
+    load_q(it0, 0);
+    pre = min(S, it0.n_kv);
+    for (int j = 0; j < pre; ++j) load_kv(it0, j, j);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");   // the issuers carry the work-list state: 32 spilled it
+    const int x = warp;
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc_f16(128, BLK, 0, 0);
+      const uint32_t idesc_pv = make_idesc_f16(128, D, 0, 1);
+      const uint32_t skv = smem_u32(sKV);
+      const uint32_t tX = tmem + x * TM_STRIDE;
+      // ---- producer state (tile 0's issuer): the next K/V tile to request, possibly of a later item
+      int p_item = first, p_u = 0, p_j = pre, loaded = pre;          // loaded = running count of requested tiles
+      AttnItem p_it = attn_item(a, first);
+      auto p_advance = [&]() {                     // -> true while there is a tile left to request
+        while (p_item < n_items && p_j >= p_it.n_kv) {
+          p_item += step; ++p_u; p_j = 0;
+          if (p_item < n_items) p_it = attn_item(a, p_item);
+        }
+        return p_item < n_items;
+      };
+      auto p_load_next = [&]() {                   // caller has made sure the stage is free
+        if (p_j == 0 && p_u > 0) load_q(p_it, p_u & 1);   // first tile of a later item: its Q tiles travel with it
+        load_kv(p_it, p_j, loaded);
+        ++p_j; ++loaded;
+      };
+      auto pump = [&]() {                          // request every tile whose stage is already free
+        while (p_advance() && mbar_test_wait(&kv_empty[loaded % S], ((loaded / S) & 1) ^ 1)) p_load_next();
+      };
+      int tiles_waited = 0;                        // running count of K/V tiles this issuer has waited for
+      auto need_tile = [&](int g) {
+        while (tiles_waited <= g) {
+          if (x == 0)
+            while (loaded <= tiles_waited) {       // this thread owes the load it is about to wait for
+              p_advance();
+              mbar_wait(&kv_empty[loaded % S], ((loaded / S) & 1) ^ 1);
+              p_load_next();
+            }
+          mbar_wait(&kv_full[tiles_waited % S], (tiles_waited / S) & 1);
+          ++tiles_waited;
+        }
+        tc_fence_after();
+      };
+      int kvbase = 0, gblk = 0, u = 0;             // running K/V tiles / softmax blocks / items before this one
+      for (int item = first; item < n_items; item += step, ++u) {
+        const AttnItem it = attn_item(a, item);
+        const uint32_t qa = smem_u32(sQ) + ((u & 1) * NT + x) * TILE_BYTES;
+        auto issue_qk = [&](int i) {               // S = Q K(block i)^T
+          const uint32_t ka = skv + ((kvbase + (i >> 1)) % S) * 2 * TILE_BYTES + (i & 1) * BLK * ROWB;
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            mma_ss(tX, make_smem_desc(qa + k * 32, 16, SBO, SWZ), make_smem_desc(ka + k * 32, 16, SBO, SWZ),
+                   idesc_qk, k != 0);
+        };
+        auto issue_pv = [&](int i) {               // O (+)= P(block i) V(block i)
+          const uint32_t va = skv + ((kvbase + (i >> 1)) % S) * 2 * TILE_BYTES + TILE_BYTES + (i & 1) * BLK * ROWB;
+#pragma unroll
+          for (int k = 0; k < BLK / 16; ++k)
+            mma_ts(tX + TM_O, tX + TM_P + k * 8, make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv,
+                   (i > 0 || k > 0) ? 1u : 0u);
+        };
+        mbar_wait(&q_full[u & 1], (u >> 1) & 1);
+        need_tile(kvbase);
+        if (gblk > 0) {                            // S still holds the last block of the previous item
+          mbar_wait(&s_free[x], (gblk - 1) & 1);
+          tc_fence_after();
+        }
+        issue_qk(0);
+        tc_commit(&s_full[x]);
+        for (int i = 0; i < it.n_blk; ++i) {
+          const int gi = gblk + i;
+          if (i + 1 < it.n_blk) {
+            need_tile(kvbase + ((i + 1) >> 1));
+            mbar_wait(&s_free[x], gi & 1);         // the softmax warpgroup holds S(i) in registers
+            tc_fence_after();
+            issue_qk(i + 1);
+            tc_commit(&s_full[x]);
+          }
+          if (x == 0) pump();
+          mbar_wait(&p_full[x], gi & 1);
+          tc_fence_after();
+          issue_pv(i);
+          tc_commit(&o_full[x]);
+          if ((i & 1) || i + 1 == it.n_blk) tc_commit(&kv_empty[(kvbase + (i >> 1)) % S]);
+          if (x == 0) pump();
+        }
+        kvbase += it.n_kv;
+        gblk += it.n_blk;
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int x = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t tX = tmem + x * TM_STRIDE + ((uint32_t)(quarter * 32) << 16);
+    const float c = a.scale_log2e;
+    const uint32_t b_sfull = smem_u32(&s_full[x]), b_sfree = smem_u32(&s_free[x]);
+    const uint32_t b_pfull = smem_u32(&p_full[x]), b_ofull = smem_u32(&o_full[x]);
+    int gblk = 0;
+    for (int item = first; item < n_items; item += step) {
+      const AttnItem it = attn_item(a, item);
+      float m = -INFINITY, l = 0.f;
+      for (int i = 0; i < it.n_blk; ++i) {
+        const int gi = gblk + i;
+        uint32_t cur[BLK];
+        mbar_wait_u32(b_sfull, gi & 1);
+        tc_fence_after();
+        tmem_ld_x32(tX, *reinterpret_cast<uint32_t(*)[32]>(&cur[0]));
+        tmem_ld_x32(tX + 32, *reinterpret_cast<uint32_t(*)[32]>(&cur[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_u32(b_sfree);
+        const int valid = a.Lk - (it.b0 + i) * BLK;
+        if (valid < BLK) {
+#pragma unroll
+          for (int k = 0; k < BLK; ++k)
+            if (k >= valid) cur[k] = 0xff800000u;   // -inf
+        }
+        float m4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m4[k] = fmaxf(__uint_as_float(cur[k]), __uint_as_float(cur[k + 4]));
+#pragma unroll
+        for (int k = 8; k < BLK; k += 8) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            m4[t] = fmaxf(m4[t], fmaxf(__uint_as_float(cur[k + t]), __uint_as_float(cur[k + t + 4])));
+        }
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        bool o_ready = false;
+        if (__any_sync(0xffffffffu, (mx - m) * c > 8.0f)) {
+          const float m_new = fmaxf(m, mx);
+          const float alpha = fast_exp2((m - m_new) * c);      // first block: exp2(-inf) = 0
+          m = m_new;
+          l *= alpha;
+          if (i > 0) {                             // O <- O * alpha in TMEM
+            mbar_wait_u32(b_ofull, (gi - 1) & 1);
+            tc_fence_after();
+            o_ready = true;
+#pragma unroll
+            for (int d0 = 0; d0 < D; d0 += 16) {
+              uint32_t r[16];
+              tmem_ld_x16(tX + TM_O + d0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 16; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
+              tmem_st_x16(tX + TM_O + d0, r);
+            }
+          }
+        }
+        const float nmc = -m * c;
+        float ls[8];
+#pragma unroll
+        for (int k = 0; k < BLK; k += 2) {
+          float x0, x1, p0, p1;
+          ffma2(x0, x1, __uint_as_float(cur[k]), __uint_as_float(cur[k + 1]), c, c, nmc, nmc);
+          if (POLY > 0 && ((k >> 1) % POLY) == POLY - 1) {
+            x0 = fmaxf(x0, -120.f); x1 = fmaxf(x1, -120.f);
+            float t0, t1, n0, n1, f0, f1;
+            fadd2(t0, t1, x0, x1, 12582912.f, 12582912.f);
+            fadd2(n0, n1, t0, t1, -12582912.f, -12582912.f);
+            fadd2(f0, f1, x0, x1, -n0, -n1);
+            ffma2(p0, p1, f0, f1, 0.05517164617776871f, 0.05517164617776871f, 0.2426111251115799f, 0.2426111251115799f);
+            ffma2(p0, p1, p0, p1, f0, f1, 0.6932609677314758f, 0.6932609677314758f);
+            ffma2(p0, p1, p0, p1, f0, f1, 0.9999280571937561f, 0.9999280571937561f);
+            p0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+            p1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+          } else {
+            p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+          }
+          const int j = (k >> 1) & 3;
+          if (k < 8) { ls[2 * j] = p0; ls[2 * j + 1] = p1; }
+          else fadd2(ls[2 * j], ls[2 * j + 1], ls[2 * j], ls[2 * j + 1], p0, p1);
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          cur[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+        if (i > 0 && !o_ready) {                   // the P columns were last read by P V(i - 1)
+          mbar_wait_u32(b_ofull, (gi - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_x16(tX + TM_P, *reinterpret_cast<uint32_t(*)[16]>(&cur[0]));
+        tmem_st_x16(tX + TM_P + 16, *reinterpret_cast<uint32_t(*)[16]>(&cur[16]));
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_u32(b_pfull);
+      }
+      gblk += it.n_blk;
+      mbar_wait_u32(b_ofull, (gblk - 1) & 1);
+      tc_fence_after();
+      const int qi = it.q0 + x * 128 + row;
+      if (it.part >= 0) {                          // partial result of one key range: unnormalised O, m, l
+        const size_t pr = ((size_t)(it.unit - a.split_from) * a.nsplit + it.part) * (NT * 128) + x * 128 + row;
+        float* wo = a.ws_o + pr * D;
+#pragma unroll
+        for (int d0 = 0; d0 < D; d0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tX + TM_O + d0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; k += 4)
+            *reinterpret_cast<uint4*>(wo + d0 + k) = make_uint4(r[k], r[k + 1], r[k + 2], r[k + 3]);
+        }
+        *reinterpret_cast<float2*>(a.ws_ml + pr * 2) = make_float2(m, l);
+      } else {
+        const float inv = 1.0f / l;
+        __half* op = a.o + (long long)it.nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)it.h * a.o_stride_h;
+#pragma unroll
+        for (int d0 = 0; d0 < D; d0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tX + TM_O + d0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; k += 8) {
+            __align__(16) __half hh[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(__uint_as_float(r[k + t]) * inv);
+            *reinterpret_cast<uint4*>(op + d0 + k) = *reinterpret_cast<uint4*>(hh);
+          }
+        }
+      }
+      // The first P V of the next item overwrites O: it is issued only after this warpgroup's next p_full
+      // arrival, which follows these reads in program order -- tcgen05.wait::ld above has retired them.
+      tc_fence_before();
+    }
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 // Merge of the key-range partials written by attn_fwd6_kernel for the split units: with m the lazily updated
 // reference maximum of each part, O = sum_p 2^((m_p - M) c) O_p, l likewise, M = max_p m_p.  One thread per
 // query row.  The split exists because 384 (batch, head) units on 148 SMs are 2.6 waves: the 88 units of the
@@ -1081,15 +1405,16 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnArgs a, int n
 static float* g_attn_ws = nullptr;
 static size_t g_attn_ws_bytes = 0;
 
-template <int POLY, bool TRACE>
+template <int POLY, bool TRACE, bool PERSIST = false>
 static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                         int Nb, cudaStream_t st) {
-  constexpr int SMEM = (4 + 2 * kAttnStages) * 128 * 32 * 2 + 1024;
+  constexpr int SMEM = ((PERSIST ? 8 : 4) + 2 * kAttnStages) * 128 * 32 * 2 + 1024;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd6_kernel<POLY, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
-        cudaSuccess)
-      return GVF_ERR_CUDA;
+    cudaError_t e;
+    if constexpr (PERSIST) e = cudaFuncSetAttribute(attn_fwd7_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    else e = cudaFuncSetAttribute(attn_fwd6_kernel<POLY, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return GVF_ERR_CUDA;
     configured = true;
   }
   static int num_sms = 0;
@@ -1121,8 +1446,14 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
       b.ws_ml = g_attn_ws + rows * 32;
     }
   }
-  const dim3 grid(b.split_from + n_split_units * b.nsplit);
-  if (launch_pdl(attn_fwd6_kernel<POLY, TRACE>, grid, dim3(640), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
+  const int n_items = b.split_from + n_split_units * b.nsplit;
+  if constexpr (PERSIST) {
+    const dim3 grid(n_items < num_sms ? n_items : num_sms);
+    if (launch_pdl(attn_fwd7_kernel<POLY>, grid, dim3(640), SMEM, st, mq, mk, mv, b, n_items) != cudaSuccess) return GVF_ERR_CUDA;
+  } else {
+    const dim3 grid(n_items);
+    if (launch_pdl(attn_fwd6_kernel<POLY, TRACE>, grid, dim3(640), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
+  }
   if (n_split_units) {
     static_assert(NSPLIT <= 4, "attn_merge_kernel keeps the (m, l) pairs of at most four parts in registers");
     attn_merge_kernel<<<(n_split_units * 512 * 8 + 255) / 256, 256, 0, st>>>(b, n_split_units);
@@ -1226,7 +1557,7 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   // (tools/attn_experiments.py): 0x10 v4 plain, 0x30 v4 ping-pong, 0x80 v6 MUFU only, low nibble 4 = polynomial share.
   const int sel = g_attn_dbg & 0xf0;
   const bool poly = (g_attn_dbg & 0xf) == 4;
-  if (D == 32 && (sel == 0x80 || (sel == 0 && Lq > 256)))
+  if (D == 32 && (sel == 0x80 || sel == 0x90 || (sel == 0 && Lq > 256)))
   {
     if (a.trace || a.stagger > 0)   // instrumented build (tools/attn_experiments.py)
       return (poly || sel == 0) ? launch_attn6<4, true>(mq, mk, mv, a, Nb, st) : launch_attn6<0, true>(mq, mk, mv, a, Nb, st);
@@ -1234,6 +1565,16 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
     // default: every 8th pair of exponentials on the FMA pipe (bench: 282.0 ms / object; MUFU only 285.6; every
     // 4th pair 285.6).  Low nibble of the debug word: 1 MUFU only, 4 every 4th pair.
     // Short key ranges (spatial self-attention, 512 keys) stay MUFU only: 49.5 vs 53.5 us.
+    // Persistent form (v7): only on request (debug selector 0x90).  MEASURED on B200 (bench.py): spatial 49.8 us
+    // (v6 49.4), image 112.3 (104.8), static 281.7 (254.8) -- the work-list state costs the issuer warps registers
+    // (64 instead of 32, so the softmax warps drop to 104) and the per-item fill / drain of the score pipeline,
+    // not the CTA launch, turned out to be what a short item pays for.
+    const bool persist = sel == 0x90 && (Lq % 512) == 0 && Lk >= 128 * kAttnStages;
+    if (persist) {
+      if (share == 4) return launch_attn6<4, false, true>(mq, mk, mv, a, Nb, st);
+      if (share == 1 || (share == 0 && Lk < 1024)) return launch_attn6<0, false, true>(mq, mk, mv, a, Nb, st);
+      return launch_attn6<8, false, true>(mq, mk, mv, a, Nb, st);
+    }
     if (share == 4) return launch_attn6<4, false>(mq, mk, mv, a, Nb, st);
     if (share == 1 || (share == 0 && Lk < 1024)) return launch_attn6<0, false>(mq, mk, mv, a, Nb, st);
     return launch_attn6<8, false>(mq, mk, mv, a, Nb, st);

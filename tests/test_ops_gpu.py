@@ -84,7 +84,7 @@ def test_attention_matches_fp32(Nb, Lq, Lk, H, D):
     _close(o, _ref_attn(q, k, v, scale), 2e-3, "attention")
 
 
-@pytest.mark.parametrize("dbg", [0x10, 0x30, 0x14, 0x81, 0x84, 0x88])
+@pytest.mark.parametrize("dbg", [0x10, 0x30, 0x14, 0x81, 0x84, 0x88, 0x90])
 def test_attention_kernel_generations(dbg):
     """every d = 32 kernel variant the dispatcher can pick (v4 plain / MUFU ping-pong / polynomial share, v6
     MUFU-only / polynomial share), on shapes with 1..4 query tiles, ragged key counts, and scores whose row
