@@ -65,6 +65,12 @@ _SIGS = {
                              _P, _P]),
     "gvf_dpm_error_sq": (C.c_int, [_P, _P, _P, C.c_int, C.c_longlong, C.c_float, C.c_float, _P, _P]),
     "gvf_dpm_update": (C.c_int, [_P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_int, _P, _P]),
+    "gvf_ssim_l1_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gvf_ssim_l1_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P]),
+    "gvf_ssim_l1_bwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "gvf_knn": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    "gvf_knn_interp_deltas": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_float, _P, _P]),
     "gvf_affine_lastdim": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, C.c_float, C.c_float, _P, _P]),
 }
 

@@ -39,8 +39,20 @@ def _deps_mtime():
     return max(m, os.path.getmtime(__file__))
 
 
-def _compile(src, verbose):
+def _headers_mtime():
+    m = os.path.getmtime(__file__)
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in os.listdir(root):
+            if f.endswith((".h", ".cuh")):
+                m = max(m, os.path.getmtime(os.path.join(root, f)))
+    return m
+
+
+def _compile(src, verbose, force=False):
     obj = os.path.join(OBJ, src[:-3] + ".o")
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(
+            os.path.getmtime(os.path.join(CSRC, src)), _headers_mtime()):
+        return obj                              # object newer than its source and every header
     cmd = [NVCC, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
@@ -60,7 +72,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     srcs = sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
+        objs = list(ex.map(lambda s: _compile(s, verbose, force), srcs))
     cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcublasLt", "-lcublas", "-lcuda"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

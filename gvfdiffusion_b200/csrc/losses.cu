@@ -1,0 +1,365 @@
+// losses.cu -- render-loss and point-cloud kernels of the training step.
+//
+//   * gvf_ssim_l1_fwd / gvf_ssim_l1_bwd: the pixel losses of reference train_vae.py:328-330
+//       L1 = |pred - gt|.mean()            (nn.L1Loss)
+//       SSIM(pred, gt)                     (utils/loss_util.py:33-63: 11x11 Gaussian window, sigma 1.5,
+//                                           zero padding, C1 = 0.01^2, C2 = 0.03^2)
+//     The reference runs five depthwise cuDNN convolutions plus ~20 elementwise launches over
+//     (B*cams, 3, 512, 512) and autograd replays them backwards.  Here one kernel per direction:
+//     a 32x32 pixel tile with its 5-pixel halo is staged in shared memory once, the window is applied
+//     separably (rows, then columns) to the five moments at the same time, the SSIM map is reduced to
+//     per-CTA partial sums (fixed-order second pass: deterministic), and the three per-pixel partial
+//     derivatives the backward pass needs are written out.  Backward convolves those three maps with the
+//     same window and adds the L1 sign term.  HBM class: forward reads 8 B and writes 12 B per pixel-channel,
+//     backward reads 20 B and writes 4 B.
+//   * gvf_knn: exact K-nearest-neighbour search (K <= 16), replaces pytorch3d.ops.knn_points as called
+//     at reference train_vae.py:525-530 (and model/autoencoder.py's encode path).  One thread per query,
+//     reference cloud staged through shared memory, sorted insertion in registers; squared distances
+//     ((dx*dx + dy*dy) + dz*dz, no FMA contraction: bit-exact against the numpy oracle), ascending, ties ->
+//     lowest index; rows beyond lengths1 / columns beyond lengths2 are zero like pytorch3d's.
+//   * gvf_knn_interp_deltas: the RBF-weighted neighbour-motion estimate of
+//     compute_interpolation_loss_delta_interp (train_vae.py:532-563) in one pass.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gvf_b200.h"
+
+namespace gvf {
+
+constexpr int kWin = 11, kHalo = 5, kTile = 32, kReg = kTile + 2 * kHalo;   // 42
+constexpr int kRegLd = kReg + 1;
+
+struct SsimWindow { float g[kWin]; };
+
+static SsimWindow make_window() {                 // utils/loss_util.py:24-26 (fp32 tensor of python doubles)
+  SsimWindow w;
+  float s = 0.f;
+  for (int i = 0; i < kWin; ++i) {
+    w.g[i] = (float)exp(-(double)((i - kWin / 2) * (i - kWin / 2)) / (2.0 * 1.5 * 1.5));
+    s += w.g[i];
+  }
+  for (int i = 0; i < kWin; ++i) w.g[i] /= s;
+  return w;
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 8) t = red[threadIdx.x];
+  if (w == 0) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;                                       // valid in thread 0
+}
+
+// grid (ceil(W/32), ceil(H/32), planes), 256 threads.  partials [planes][gy*gx][2] = (sum ssim_map, sum |a-b|)
+__global__ void __launch_bounds__(256) ssim_l1_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
+                                                          int H, int W, const SsimWindow win,
+                                                          float* __restrict__ partials, float* __restrict__ dmaps,
+                                                          long long plane_count) {
+  __shared__ float sa[kReg][kRegLd], sb[kReg][kRegLd];
+  __shared__ float hz[5][kReg][kTile];
+  __shared__ float red[8];
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  const size_t HW = (size_t)H * W;
+  const float* a = img1 + (size_t)blockIdx.z * HW;
+  const float* b = img2 + (size_t)blockIdx.z * HW;
+  for (int i = threadIdx.x; i < kReg * kReg; i += 256) {
+    const int r = i / kReg, c = i - r * kReg;
+    const int y = y0 + r - kHalo, x = x0 + c - kHalo;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    sa[r][c] = in ? __ldg(a + (size_t)y * W + x) : 0.f;
+    sb[r][c] = in ? __ldg(b + (size_t)y * W + x) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kReg * kTile; i += 256) {
+    const int r = i / kTile, c = i - r * kTile;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) {
+      const float g = win.g[k], u = sa[r][c + k], v = sb[r][c + k];
+      m1 += g * u; m2 += g * v;
+      s11 += g * (u * u); s22 += g * (v * v); s12 += g * (u * v);
+    }
+    hz[0][r][c] = m1; hz[1][r][c] = m2; hz[2][r][c] = s11; hz[3][r][c] = s22; hz[4][r][c] = s12;
+  }
+  __syncthreads();
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  float acc_s = 0.f, acc_l = 0.f;
+  const int tx = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ty = (threadIdx.x >> 5) + 8 * j;
+    const int y = y0 + ty, x = x0 + tx;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) {
+      const float g = win.g[k];
+      m1 += g * hz[0][ty + k][tx]; m2 += g * hz[1][ty + k][tx];
+      s11 += g * hz[2][ty + k][tx]; s22 += g * hz[3][ty + k][tx]; s12 += g * hz[4][ty + k][tx];
+    }
+    if (y < H && x < W) {
+      const float mu1_sq = m1 * m1, mu2_sq = m2 * m2, mu12 = m1 * m2;
+      const float sig1 = s11 - mu1_sq, sig2 = s22 - mu2_sq, sig12 = s12 - mu12;
+      const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2;
+      const float B1 = mu1_sq + mu2_sq + C1, B2 = sig1 + sig2 + C2;
+      const float inv = 1.f / (B1 * B2);
+      const float s = A1 * A2 * inv;
+      acc_s += s;
+      acc_l += fabsf(sa[ty + kHalo][tx + kHalo] - sb[ty + kHalo][tx + kHalo]);
+      if (dmaps) {
+        // d s / d sigma12, d s / d sigma1^2, and the total derivative with respect to mu1 (sigma1^2 and
+        // sigma12 contain -mu1^2 and -mu1 mu2)
+        const float d12 = 2.f * A1 * inv;
+        const float d11 = -s / B2;
+        const float dmu = 2.f * m2 * A2 * inv - 2.f * m1 * s / B1 - 2.f * m1 * d11 - m2 * d12;
+        const size_t o = (size_t)blockIdx.z * HW + (size_t)y * W + x;
+        dmaps[o] = dmu;
+        dmaps[o + plane_count * HW] = d11;
+        dmaps[o + 2 * plane_count * HW] = d12;
+      }
+    }
+  }
+  const float ts = block_sum_256(acc_s, red);
+  const float tl = block_sum_256(acc_l, red);
+  if (threadIdx.x == 0) {
+    const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    partials[2 * cta] = ts;
+    partials[2 * cta + 1] = tl;
+  }
+}
+
+// one CTA per plane: fixed-order sum of that plane's partials in double -> sums [planes][2]
+__global__ void __launch_bounds__(256) ssim_l1_finalize_kernel(const float* __restrict__ partials, int per_plane,
+                                                               float* __restrict__ sums) {
+  __shared__ double rs[256], rl[256];
+  const float* p = partials + (size_t)blockIdx.x * per_plane * 2;
+  double s = 0.0, l = 0.0;
+  for (int i = threadIdx.x; i < per_plane; i += 256) { s += p[2 * i]; l += p[2 * i + 1]; }
+  rs[threadIdx.x] = s; rl[threadIdx.x] = l;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rl[threadIdx.x] += rl[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sums[2 * blockIdx.x] = (float)rs[0]; sums[2 * blockIdx.x + 1] = (float)rl[0]; }
+}
+
+// grad_img1 = coef_l1[plane] * sign(a - b) + coef_ssim[plane] * (w * dmu + 2 a (w * d11) + b (w * d12))
+__global__ void __launch_bounds__(256) ssim_l1_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
+                                                          const float* __restrict__ dmaps, int H, int W,
+                                                          const SsimWindow win, const float* __restrict__ coef_ssim,
+                                                          const float* __restrict__ coef_l1,
+                                                          float* __restrict__ grad, long long plane_count) {
+  __shared__ float sm[3][kReg][kRegLd];
+  __shared__ float hz[3][kReg][kTile];
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  const size_t HW = (size_t)H * W;
+  const size_t pl = (size_t)blockIdx.z * HW;
+  for (int i = threadIdx.x; i < kReg * kReg; i += 256) {
+    const int r = i / kReg, c = i - r * kReg;
+    const int y = y0 + r - kHalo, x = x0 + c - kHalo;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    const size_t o = pl + (size_t)y * W + x;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) sm[m][r][c] = in ? __ldg(dmaps + o + (size_t)m * plane_count * HW) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kReg * kTile; i += 256) {
+    const int r = i / kTile, c = i - r * kTile;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) {
+      const float g = win.g[k];
+      t0 += g * sm[0][r][c + k]; t1 += g * sm[1][r][c + k]; t2 += g * sm[2][r][c + k];
+    }
+    hz[0][r][c] = t0; hz[1][r][c] = t1; hz[2][r][c] = t2;
+  }
+  __syncthreads();
+  const float cs = coef_ssim[blockIdx.z], cl = coef_l1[blockIdx.z];
+  const int tx = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ty = (threadIdx.x >> 5) + 8 * j;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= H || x >= W) continue;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) {
+      const float g = win.g[k];
+      t0 += g * hz[0][ty + k][tx]; t1 += g * hz[1][ty + k][tx]; t2 += g * hz[2][ty + k][tx];
+    }
+    const size_t o = pl + (size_t)y * W + x;
+    const float u = __ldg(img1 + o), v = __ldg(img2 + o);
+    const float d = u - v;
+    const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    grad[o] = cl * sg + cs * (t0 + 2.f * u * t1 + v * t2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kKnnMax = 16, kKnnChunk = 1024;
+
+template <int K>
+__global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ q, const float* __restrict__ r, int P1, int P2,
+                                                  const long long* __restrict__ len1, const long long* __restrict__ len2,
+                                                  int k_used, float* __restrict__ out_d, long long* __restrict__ out_i) {
+  __shared__ float sx[kKnnChunk], sy[kKnnChunk], sz[kKnnChunk];
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int n1 = len1 ? (int)len1[b] : P1, n2 = len2 ? (int)len2[b] : P2;
+  const bool live = i < n1 && i < P1;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (live) {
+    const float* p = q + ((size_t)b * P1 + i) * 3;
+    qx = p[0]; qy = p[1]; qz = p[2];
+  }
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { bd[k] = 3.4e38f; bi[k] = -1; }
+  const float* rb = r + (size_t)b * P2 * 3;
+  for (int base = 0; base < n2; base += kKnnChunk) {
+    const int m = min(kKnnChunk, n2 - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += 256) {
+      const float* p = rb + (size_t)(base + j) * 3;
+      sx[j] = p[0]; sy[j] = p[1]; sz[j] = p[2];
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int j = 0; j < m; ++j) {
+      const float dx = __fsub_rn(qx, sx[j]), dy = __fsub_rn(qy, sy[j]), dz = __fsub_rn(qz, sz[j]);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d < bd[K - 1]) {                         // strict: among equal distances the earlier index stays in front
+        bd[K - 1] = d; bi[K - 1] = base + j;
+#pragma unroll
+        for (int k = K - 1; k > 0; --k) {
+          if (bd[k] < bd[k - 1]) {
+            const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+            const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+          }
+        }
+      }
+    }
+  }
+  if (i < P1) {
+    float* od = out_d + ((size_t)b * P1 + i) * k_used;
+    long long* oi = out_i + ((size_t)b * P1 + i) * k_used;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (k < k_used) {
+        const bool ok = live && bi[k] >= 0;
+        od[k] = ok ? bd[k] : 0.f;
+        oi[k] = ok ? bi[k] : 0;
+      }
+    }
+  }
+}
+
+// est[b, t, i, :] = sum_k w_k (moving[b, t, idx_k] - static[b, idx_k]); weights as train_vae.py:532-548
+__global__ void __launch_bounds__(256) knn_interp_kernel(const float* __restrict__ dists, const long long* __restrict__ idx,
+                                                         const float* __restrict__ stat, const float* __restrict__ mov,
+                                                         const long long* __restrict__ len1, int P1, int P2, int T, int K,
+                                                         int adaptive, float beta, float* __restrict__ est) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= P1) return;
+  const float* d = dists + ((size_t)b * P1 + i) * K;
+  const long long* id = idx + ((size_t)b * P1 + i) * K;
+  float w[kKnnMax];
+  int nb[kKnnMax];
+  float mean = 0.f;
+  for (int k = 0; k < K; ++k) mean += d[k];
+  mean /= (float)K;
+  const float rad = sqrtf(mean) + 1e-6f;
+  const float r2 = rad * rad;
+  const bool valid = len1 ? i < (int)len1[b] : true;
+  float ws = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float wk;
+    if (adaptive) wk = d[k] <= r2 ? expf(-beta * d[k] / r2) : 0.f;
+    else wk = expf(-beta * d[k]);
+    if (!valid) wk = 0.f;
+    w[k] = wk;
+    ws += wk;
+    nb[k] = (int)id[k];
+  }
+  const float inv = 1.f / (ws + 1e-8f);
+  const float* sb = stat + (size_t)b * P2 * 3;
+  for (int t = 0; t < T; ++t) {
+    const float* mb = mov + ((size_t)b * T + t) * P2 * 3;
+    float ex = 0.f, ey = 0.f, ez = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float wk = w[k] * inv;
+      const size_t o = (size_t)nb[k] * 3;
+      ex += wk * (mb[o] - sb[o]);
+      ey += wk * (mb[o + 1] - sb[o + 1]);
+      ez += wk * (mb[o + 2] - sb[o + 2]);
+    }
+    float* e = est + (((size_t)b * T + t) * P1 + i) * 3;
+    e[0] = ex; e[1] = ey; e[2] = ez;
+  }
+}
+
+}  // namespace gvf
+
+extern "C" GVF_API size_t gvf_ssim_l1_workspace_bytes(int planes, int H, int W) {
+  if (planes <= 0 || H <= 0 || W <= 0) return 0;
+  const size_t gx = (W + gvf::kTile - 1) / gvf::kTile, gy = (H + gvf::kTile - 1) / gvf::kTile;
+  return (size_t)planes * gx * gy * 2 * sizeof(float);
+}
+
+extern "C" GVF_API int gvf_ssim_l1_fwd(const float* img1, const float* img2, int planes, int H, int W, float* workspace,
+                                       size_t workspace_bytes, float* sums, float* dmaps, void* stream) {
+  if (!img1 || !img2 || !workspace || !sums || planes <= 0 || H <= 0 || W <= 0 || planes > 65535) return GVF_ERR_INVALID;
+  if (workspace_bytes < gvf_ssim_l1_workspace_bytes(planes, H, W)) return GVF_ERR_WORKSPACE;
+  static const gvf::SsimWindow win = gvf::make_window();
+  const dim3 grid((W + gvf::kTile - 1) / gvf::kTile, (H + gvf::kTile - 1) / gvf::kTile, planes);
+  cudaStream_t st = (cudaStream_t)stream;
+  gvf::ssim_l1_fwd_kernel<<<grid, 256, 0, st>>>(img1, img2, H, W, win, workspace, dmaps, planes);
+  gvf::ssim_l1_finalize_kernel<<<planes, 256, 0, st>>>(workspace, (int)(grid.x * grid.y), sums);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+extern "C" GVF_API int gvf_ssim_l1_bwd(const float* img1, const float* img2, const float* dmaps, int planes, int H, int W,
+                                       const float* coef_ssim, const float* coef_l1, float* grad_img1, void* stream) {
+  if (!img1 || !img2 || !dmaps || !coef_ssim || !coef_l1 || !grad_img1 || planes <= 0 || H <= 0 || W <= 0 ||
+      planes > 65535)
+    return GVF_ERR_INVALID;
+  static const gvf::SsimWindow win = gvf::make_window();
+  const dim3 grid((W + gvf::kTile - 1) / gvf::kTile, (H + gvf::kTile - 1) / gvf::kTile, planes);
+  gvf::ssim_l1_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img1, img2, dmaps, H, W, win, coef_ssim, coef_l1,
+                                                                  grad_img1, planes);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+extern "C" GVF_API int gvf_knn(const float* queries, const float* refs, int B, int P1, int P2, const long long* lengths1,
+                               const long long* lengths2, int K, float* dists, long long* idx, void* stream) {
+  if (!queries || !refs || !dists || !idx || B <= 0 || P1 <= 0 || P2 <= 0 || K <= 0) return GVF_ERR_INVALID;
+  if (K > gvf::kKnnMax || B > 65535) return GVF_ERR_UNSUPPORTED;
+  const dim3 grid((P1 + 255) / 256, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K <= 4) gvf::knn_kernel<4><<<grid, 256, 0, st>>>(queries, refs, P1, P2, lengths1, lengths2, K, dists, idx);
+  else if (K <= 8) gvf::knn_kernel<8><<<grid, 256, 0, st>>>(queries, refs, P1, P2, lengths1, lengths2, K, dists, idx);
+  else gvf::knn_kernel<16><<<grid, 256, 0, st>>>(queries, refs, P1, P2, lengths1, lengths2, K, dists, idx);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+extern "C" GVF_API int gvf_knn_interp_deltas(const float* dists, const long long* idx, const float* static_pc,
+                                             const float* moving_pc, const long long* lengths1, int B, int P1, int P2,
+                                             int T, int K, int adaptive_radius, float beta, float* est, void* stream) {
+  if (!dists || !idx || !static_pc || !moving_pc || !est || B <= 0 || P1 <= 0 || P2 <= 0 || T <= 0 || K <= 0)
+    return GVF_ERR_INVALID;
+  if (K > gvf::kKnnMax || B > 65535) return GVF_ERR_UNSUPPORTED;
+  const dim3 grid((P1 + 255) / 256, B);
+  gvf::knn_interp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dists, idx, static_pc, moving_pc, lengths1, P1, P2, T,
+                                                                 K, adaptive_radius, beta, est);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}

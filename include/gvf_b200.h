@@ -286,6 +286,36 @@ GVF_API int gvf_vox2seq_decode(const int32_t* codes, long long N, const int* per
 GVF_API int gvf_sparse_window_attn_f16(const void* qkv, void* out, const int* fwd_idx, const int* cu_seqlens,
                                        int num_windows, int max_seqlen, int H, int D, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * 7. Training-step losses (BASELINE configs[4]).
+ *    gvf_ssim_l1_*: nn.L1Loss + utils/loss_util.py:33-63 `ssim` as used at train_vae.py:328-330
+ *    (11x11 Gaussian window sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2) in one kernel per
+ *    direction instead of five depthwise convolutions + ~20 elementwise launches and their autograd.
+ *    img1 (prediction) / img2 (target): fp32 [planes, H, W] (planes = B * C).  Forward writes
+ *    sums [planes][2] = (sum of the SSIM map, sum of |img1 - img2|) -- the caller divides by the
+ *    element counts (size_average True / False are both host-side reductions of these) -- and, when
+ *    dmaps != NULL, the three per-pixel partial derivatives [3][planes][H][W] backward needs.
+ *    Backward: grad_img1 = coef_l1[plane] sign(img1 - img2) + coef_ssim[plane] dSSIMsum/dimg1,
+ *    coef_* fp32 [planes] on the device (upstream gradient / element count).
+ * ---------------------------------------------------------------------------------- */
+GVF_API size_t gvf_ssim_l1_workspace_bytes(int planes, int H, int W);
+GVF_API int gvf_ssim_l1_fwd(const float* img1, const float* img2, int planes, int H, int W, float* workspace,
+                            size_t workspace_bytes, float* sums, float* dmaps, void* stream);
+GVF_API int gvf_ssim_l1_bwd(const float* img1, const float* img2, const float* dmaps, int planes, int H, int W,
+                            const float* coef_ssim, const float* coef_l1, float* grad_img1, void* stream);
+/* Exact K nearest neighbours (K <= 16): replaces pytorch3d.ops.knn_points(p1, p2, lengths1, lengths2, K)
+ * as called at train_vae.py:525-530.  queries [B,P1,3], refs [B,P2,3] fp32; lengths int64 [B] or NULL;
+ * dists [B,P1,K] squared distances ascending ((dx*dx + dy*dy) + dz*dz, every operation rounded: no FMA),
+ * idx [B,P1,K] int64, ties -> lowest index; rows >= lengths1 and columns >= lengths2 are zero. */
+GVF_API int gvf_knn(const float* queries, const float* refs, int B, int P1, int P2, const long long* lengths1,
+                    const long long* lengths2, int K, float* dists, long long* idx, void* stream);
+/* compute_interpolation_loss_delta_interp's neighbour-motion estimate (train_vae.py:532-563):
+ * radius = sqrt(mean_k dists) + 1e-6; w_k = exp(-beta d_k / radius^2) [d_k <= radius^2] (or exp(-beta d_k)),
+ * zero for padded rows, normalised by (sum + 1e-8); est [B,T,P1,3] = sum_k w_k (moving[b,t,idx_k] - static[b,idx_k]). */
+GVF_API int gvf_knn_interp_deltas(const float* dists, const long long* idx, const float* static_pc,
+                                  const float* moving_pc, const long long* lengths1, int B, int P1, int P2, int T,
+                                  int K, int adaptive_radius, float beta, float* est, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

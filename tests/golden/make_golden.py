@@ -195,7 +195,73 @@ def gen_window_partition():
     return cases
 
 
+def _bruteforce_knn_points(p1, p2, lengths1=None, lengths2=None, K=1):
+    """Stand-in for pytorch3d.ops.knn_points (absent here) with its documented semantics: exact squared
+    distances ((dx*dx + dy*dy) + dz*dz in fp32), ascending, ties -> lowest index, padded rows zero."""
+    B, P1, _ = p1.shape
+    d = p1[:, :, None, :] - p2[:, None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    if lengths2 is not None:
+        d2 = d2.masked_fill(torch.arange(p2.shape[1])[None, None, :] >= lengths2[:, None, None], float("inf"))
+    order = torch.sort(d2, dim=-1, stable=True)
+    dists, idx = order.values[..., :K].clone(), order.indices[..., :K].clone()
+    if lengths1 is not None:
+        pad = torch.arange(P1)[None, :] >= lengths1[:, None]
+        dists[pad] = 0
+        idx[pad] = 0
+    return dists, idx, None
+
+
+def gen_losses():
+    """Pixel and interpolation losses of the training step, from the reference's own code:
+    utils.loss_util.ssim (imported; `lpips` stubbed, unused) with autograd gradients, and
+    train_vae.compute_interpolation_loss_delta_interp -- the function's source is read from
+    /root/reference/train_vae.py and executed as is (the module itself needs accelerate / imageio /
+    pytorch3d); only pytorch3d.ops.knn_points is replaced by the brute-force stand-in above."""
+    import ast
+    import types
+    import torch.nn.functional as F
+    _ref_import._stub("lpips", LPIPS=None)
+    from utils.loss_util import ssim
+    g = torch.Generator().manual_seed(5)
+    out = {"ssim": [], "interp": []}
+    for shape in [(2, 3, 40, 52), (1, 3, 70, 33), (3, 1, 16, 16)]:
+        gt = torch.rand(shape, generator=g)
+        pred = (gt + 0.15 * torch.randn(shape, generator=g)).clamp(0, 1).requires_grad_(True)
+        val = ssim(pred, gt)
+        l1 = torch.abs(pred - gt).mean()
+        (gs,) = torch.autograd.grad(val, pred, retain_graph=True)
+        (gl,) = torch.autograd.grad(l1, pred)
+        per = ssim(pred, gt, size_average=False)
+        out["ssim"].append({"pred": pred.detach(), "gt": gt, "ssim": val.detach(), "l1": l1.detach(),
+                            "grad_ssim": gs, "grad_l1": gl, "ssim_per_batch": per.detach()})
+    src = open(os.path.join(_ref_import.REF, "train_vae.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef)
+          and n.name == "compute_interpolation_loss_delta_interp"][0]
+    ns = {"th": torch, "F": F, "pytorch3d": types.SimpleNamespace(ops=types.SimpleNamespace(knn_points=_bruteforce_knn_points))}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "train_vae.py", "exec"), ns)
+    ref_fn = ns["compute_interpolation_loss_delta_interp"]
+    for (B, T, sizes, n_pts, k, adaptive) in [(2, 3, (150, 97), 64, 4, True), (1, 4, (200,), 33, 8, True),
+                                              (2, 2, (50, 50), 40, 4, False)]:
+        static_gs = [torch.cat([torch.rand(n, 3, generator=g) - 0.5, torch.rand(n, 11, generator=g)], 1) for n in sizes]
+        micro_static = torch.rand(B, n_pts, 3, generator=g) - 0.5
+        micro_moving = micro_static[:, None] + 0.05 * torch.randn(B, T, n_pts, 3, generator=g)
+        output = 0.05 * torch.randn(B, T, max(sizes), 14, generator=g)
+        output.requires_grad_(True)
+        loss, _, est = ref_fn(static_gs, micro_static, micro_moving, output, B, knn_k=k, adaptive_radius=adaptive)
+        (go,) = torch.autograd.grad(loss, output)
+        padded = torch.stack([F.pad(s[:, :3], (0, 0, 0, max(sizes) - s.shape[0])) for s in static_gs])
+        kd, ki, _ = _bruteforce_knn_points(padded, micro_static, lengths1=torch.tensor(sizes), K=k)
+        out["interp"].append({"static_gs": static_gs, "micro_static": micro_static, "micro_moving": micro_moving,
+                              "output": output.detach(), "knn_k": k, "adaptive": adaptive, "loss": loss.detach(),
+                              "estimated": est, "grad_output": go, "knn_dists": kd, "knn_idx": ki})
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":
+        torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "window":
         torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
         return
@@ -206,6 +272,7 @@ def main():
     torch.save(gen_p_sample(diffusion), os.path.join(HERE, "p_sample.pt"))
     torch.save(gen_gaussian(), os.path.join(HERE, "gaussian.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
+    torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -159,3 +159,27 @@ def test_window_partition_matches_reference():
             w = (seg[:, 1:] + sh) // c["window"]
             assert (w == w[0]).all()
             start += n
+
+
+# ------------------------------------------------------------------ training-step losses (row a17)
+def test_loss_oracle_matches_reference():
+    from oracle import losses as OL
+    g = load("losses.pt")
+    for c in g["ssim"]:
+        pred = c["pred"].clone().requires_grad_(True)
+        v = OL.ssim(pred, c["gt"])
+        assert abs(float(v.detach()) - float(c["ssim"])) < 1e-6
+        (gs,) = torch.autograd.grad(v, pred)
+        assert rel(gs, c["grad_ssim"]) < 1e-5
+        assert torch.allclose(OL.ssim(c["pred"], c["gt"], size_average=False), c["ssim_per_batch"], atol=1e-6)
+        assert abs(float(OL.l1_loss(c["pred"], c["gt"])) - float(c["l1"])) < 1e-7
+    for c in g["interp"]:
+        out = c["output"].clone().requires_grad_(True)
+        loss, est, kd, ki = OL.interpolation_loss(c["static_gs"], c["micro_static"], c["micro_moving"], out,
+                                                  c["knn_k"], c["adaptive"])
+        assert np.array_equal(ki, c["knn_idx"].numpy())
+        assert np.array_equal(kd, c["knn_dists"].numpy())
+        assert torch.allclose(est, c["estimated"], atol=1e-6)
+        assert abs(float(loss) - float(c["loss"])) < 1e-7
+        (go,) = torch.autograd.grad(loss, out)
+        assert torch.allclose(go, c["grad_output"], atol=1e-9)
