@@ -27,7 +27,10 @@
 namespace gvf {
 
 constexpr int kWin = 11, kHalo = 5, kTile = 32, kReg = kTile + 2 * kHalo;   // 42
-constexpr int kRegLd = kReg + 1;
+constexpr int kRegLd = 44;       // staged rows: 16 B aligned 8-column groups, conflict-free LDS.128
+constexpr int kHzLd = kTile + 1; // row-filtered rows: conflict-free column-group stores
+constexpr int kGrp = 8;          // output columns per thread in the row pass (18 staged values -> 8 outputs)
+constexpr int kRows = 4;         // output rows per thread in the column pass (14 row-filtered values -> 4 outputs)
 
 struct SsimWindow { float g[kWin]; };
 
@@ -63,47 +66,84 @@ __global__ void __launch_bounds__(256) ssim_l1_fwd_kernel(const float* __restric
                                                           int H, int W, const SsimWindow win,
                                                           float* __restrict__ partials, float* __restrict__ dmaps,
                                                           long long plane_count) {
-  __shared__ float sa[kReg][kRegLd], sb[kReg][kRegLd];
-  __shared__ float hz[5][kReg][kTile];
+  __shared__ __align__(16) float sa[kReg][kRegLd], sb[kReg][kRegLd];
+  __shared__ float hz[5][kReg][kHzLd];
   __shared__ float red[8];
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
   const size_t HW = (size_t)H * W;
   const float* a = img1 + (size_t)blockIdx.z * HW;
   const float* b = img2 + (size_t)blockIdx.z * HW;
-  for (int i = threadIdx.x; i < kReg * kReg; i += 256) {
-    const int r = i / kReg, c = i - r * kReg;
+  for (int i = threadIdx.x; i < kReg * kRegLd; i += 256) {
+    const int r = i / kRegLd, c = i - r * kRegLd;
     const int y = y0 + r - kHalo, x = x0 + c - kHalo;
-    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    const bool in = c < kReg && y >= 0 && y < H && x >= 0 && x < W;
     sa[r][c] = in ? __ldg(a + (size_t)y * W + x) : 0.f;
     sb[r][c] = in ? __ldg(b + (size_t)y * W + x) : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kReg * kTile; i += 256) {
-    const int r = i / kTile, c = i - r * kTile;
-    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+  // row pass: one thread = one staged row x 8 output columns; the 18 staged values it needs are read once
+  // (4 x LDS.128 + LDS.64 per image) and the three products formed once per value, not once per tap
+  if (threadIdx.x < kReg * (kTile / kGrp)) {
+    const int r = threadIdx.x / (kTile / kGrp), c0 = (threadIdx.x % (kTile / kGrp)) * kGrp;
+    float u[kGrp + kWin - 1], v[kGrp + kWin - 1];
 #pragma unroll
-    for (int k = 0; k < kWin; ++k) {
-      const float g = win.g[k], u = sa[r][c + k], v = sb[r][c + k];
-      m1 += g * u; m2 += g * v;
-      s11 += g * (u * u); s22 += g * (v * v); s12 += g * (u * v);
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(&sa[r][c0 + 4 * q]);
+      const float4 w = *reinterpret_cast<const float4*>(&sb[r][c0 + 4 * q]);
+      u[4 * q] = t.x; u[4 * q + 1] = t.y; u[4 * q + 2] = t.z; u[4 * q + 3] = t.w;
+      v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
     }
-    hz[0][r][c] = m1; hz[1][r][c] = m2; hz[2][r][c] = s11; hz[3][r][c] = s22; hz[4][r][c] = s12;
+    {
+      const float2 t = *reinterpret_cast<const float2*>(&sa[r][c0 + 16]);
+      const float2 w = *reinterpret_cast<const float2*>(&sb[r][c0 + 16]);
+      u[16] = t.x; u[17] = t.y; v[16] = w.x; v[17] = w.y;
+    }
+    float m1[kGrp], m2[kGrp], s11[kGrp], s22[kGrp], s12[kGrp];
+#pragma unroll
+    for (int j = 0; j < kGrp; ++j) m1[j] = m2[j] = s11[j] = s22[j] = s12[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kGrp + kWin - 1; ++i) {
+      const float uu = u[i] * u[i], vv = v[i] * v[i], uv = u[i] * v[i];
+#pragma unroll
+      for (int j = 0; j < kGrp; ++j) {
+        const int k = i - j;                       // tap index of value i for output j
+        if (k >= 0 && k < kWin) {
+          const float g = win.g[k];
+          m1[j] += g * u[i]; m2[j] += g * v[i]; s11[j] += g * uu; s22[j] += g * vv; s12[j] += g * uv;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kGrp; ++j) {
+      hz[0][r][c0 + j] = m1[j]; hz[1][r][c0 + j] = m2[j]; hz[2][r][c0 + j] = s11[j];
+      hz[3][r][c0 + j] = s22[j]; hz[4][r][c0 + j] = s12[j];
+    }
   }
   __syncthreads();
+  // column pass: one thread = one column x 4 output rows (14 row-filtered values per moment, read once)
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
   float acc_s = 0.f, acc_l = 0.f;
-  const int tx = threadIdx.x & 31;
+  const int tx = threadIdx.x & 31, ty0 = (threadIdx.x >> 5) * kRows;
+  float o[5][kRows];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int ty = (threadIdx.x >> 5) + 8 * j;
-    const int y = y0 + ty, x = x0 + tx;
-    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+  for (int m = 0; m < 5; ++m) {
 #pragma unroll
-    for (int k = 0; k < kWin; ++k) {
-      const float g = win.g[k];
-      m1 += g * hz[0][ty + k][tx]; m2 += g * hz[1][ty + k][tx];
-      s11 += g * hz[2][ty + k][tx]; s22 += g * hz[3][ty + k][tx]; s12 += g * hz[4][ty + k][tx];
+    for (int j = 0; j < kRows; ++j) o[m][j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRows + kWin - 1; ++i) {
+      const float h = hz[m][ty0 + i][tx];
+#pragma unroll
+      for (int j = 0; j < kRows; ++j) {
+        const int k = i - j;
+        if (k >= 0 && k < kWin) o[m][j] += win.g[k] * h;
+      }
     }
+  }
+#pragma unroll
+  for (int j = 0; j < kRows; ++j) {
+    const int ty = ty0 + j;
+    const int y = y0 + ty, x = x0 + tx;
+    const float m1 = o[0][j], m2 = o[1][j], s11 = o[2][j], s22 = o[3][j], s12 = o[4][j];
     if (y < H && x < W) {
       const float mu1_sq = m1 * m1, mu2_sq = m2 * m2, mu12 = m1 * m2;
       const float sig1 = s11 - mu1_sq, sig2 = s22 - mu2_sq, sig12 = s12 - mu12;
@@ -119,10 +159,10 @@ __global__ void __launch_bounds__(256) ssim_l1_fwd_kernel(const float* __restric
         const float d12 = 2.f * A1 * inv;
         const float d11 = -s / B2;
         const float dmu = 2.f * m2 * A2 * inv - 2.f * m1 * s / B1 - 2.f * m1 * d11 - m2 * d12;
-        const size_t o = (size_t)blockIdx.z * HW + (size_t)y * W + x;
-        dmaps[o] = dmu;
-        dmaps[o + plane_count * HW] = d11;
-        dmaps[o + 2 * plane_count * HW] = d12;
+        const size_t oo = (size_t)blockIdx.z * HW + (size_t)y * W + x;
+        dmaps[oo] = dmu;
+        dmaps[oo + plane_count * HW] = d11;
+        dmaps[oo + 2 * plane_count * HW] = d12;
       }
     }
   }
@@ -157,49 +197,74 @@ __global__ void __launch_bounds__(256) ssim_l1_bwd_kernel(const float* __restric
                                                           const SsimWindow win, const float* __restrict__ coef_ssim,
                                                           const float* __restrict__ coef_l1,
                                                           float* __restrict__ grad, long long plane_count) {
-  __shared__ float sm[3][kReg][kRegLd];
-  __shared__ float hz[3][kReg][kTile];
+  __shared__ __align__(16) float sm[3][kReg][kRegLd];
+  __shared__ float hz[3][kReg][kHzLd];
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
   const size_t HW = (size_t)H * W;
   const size_t pl = (size_t)blockIdx.z * HW;
-  for (int i = threadIdx.x; i < kReg * kReg; i += 256) {
-    const int r = i / kReg, c = i - r * kReg;
+  for (int i = threadIdx.x; i < kReg * kRegLd; i += 256) {
+    const int r = i / kRegLd, c = i - r * kRegLd;
     const int y = y0 + r - kHalo, x = x0 + c - kHalo;
-    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    const bool in = c < kReg && y >= 0 && y < H && x >= 0 && x < W;
     const size_t o = pl + (size_t)y * W + x;
 #pragma unroll
     for (int m = 0; m < 3; ++m) sm[m][r][c] = in ? __ldg(dmaps + o + (size_t)m * plane_count * HW) : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kReg * kTile; i += 256) {
-    const int r = i / kTile, c = i - r * kTile;
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  if (threadIdx.x < kReg * (kTile / kGrp)) {
+    const int r = threadIdx.x / (kTile / kGrp), c0 = (threadIdx.x % (kTile / kGrp)) * kGrp;
 #pragma unroll
-    for (int k = 0; k < kWin; ++k) {
-      const float g = win.g[k];
-      t0 += g * sm[0][r][c + k]; t1 += g * sm[1][r][c + k]; t2 += g * sm[2][r][c + k];
+    for (int m = 0; m < 3; ++m) {
+      float u[kGrp + kWin - 1];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(&sm[m][r][c0 + 4 * q]);
+        u[4 * q] = t.x; u[4 * q + 1] = t.y; u[4 * q + 2] = t.z; u[4 * q + 3] = t.w;
+      }
+      const float2 t2 = *reinterpret_cast<const float2*>(&sm[m][r][c0 + 16]);
+      u[16] = t2.x; u[17] = t2.y;
+      float acc[kGrp];
+#pragma unroll
+      for (int j = 0; j < kGrp; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kGrp + kWin - 1; ++i) {
+#pragma unroll
+        for (int j = 0; j < kGrp; ++j) {
+          const int k = i - j;
+          if (k >= 0 && k < kWin) acc[j] += win.g[k] * u[i];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kGrp; ++j) hz[m][r][c0 + j] = acc[j];
     }
-    hz[0][r][c] = t0; hz[1][r][c] = t1; hz[2][r][c] = t2;
   }
   __syncthreads();
   const float cs = coef_ssim[blockIdx.z], cl = coef_l1[blockIdx.z];
-  const int tx = threadIdx.x & 31;
+  const int tx = threadIdx.x & 31, ty0 = (threadIdx.x >> 5) * kRows;
+  float o[3][kRows];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int ty = (threadIdx.x >> 5) + 8 * j;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y >= H || x >= W) continue;
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  for (int m = 0; m < 3; ++m) {
 #pragma unroll
-    for (int k = 0; k < kWin; ++k) {
-      const float g = win.g[k];
-      t0 += g * hz[0][ty + k][tx]; t1 += g * hz[1][ty + k][tx]; t2 += g * hz[2][ty + k][tx];
+    for (int j = 0; j < kRows; ++j) o[m][j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRows + kWin - 1; ++i) {
+      const float h = hz[m][ty0 + i][tx];
+#pragma unroll
+      for (int j = 0; j < kRows; ++j) {
+        const int k = i - j;
+        if (k >= 0 && k < kWin) o[m][j] += win.g[k] * h;
+      }
     }
-    const size_t o = pl + (size_t)y * W + x;
-    const float u = __ldg(img1 + o), v = __ldg(img2 + o);
+  }
+#pragma unroll
+  for (int j = 0; j < kRows; ++j) {
+    const int y = y0 + ty0 + j, x = x0 + tx;
+    if (y >= H || x >= W) continue;
+    const size_t oo = pl + (size_t)y * W + x;
+    const float u = __ldg(img1 + oo), v = __ldg(img2 + oo);
     const float d = u - v;
     const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-    grad[o] = cl * sg + cs * (t0 + 2.f * u * t1 + v * t2);
+    grad[oo] = cl * sg + cs * (o[0][j] + 2.f * u * o[1][j] + v * o[2][j]);
   }
 }
 

@@ -6,8 +6,9 @@ reference uses it at renderers/gaussian_render.py:105-125,143,198-206:
                                              sh_degree, campos, prefiltered, debug)
     color, radii = GaussianRasterizer(settings)(means3D, means2D, shs=..., opacities=..., scales=..., rotations=...)
 
-Forward only in this round (inference); the tensors are the ACTIVATED rasteriser inputs and go
-through gvf_raster_forward(activated=1)."""
+The tensors are the ACTIVATED rasteriser inputs and go through gvf_raster_forward / gvf_raster_backward
+(activated=1); like upstream's autograd Function the call is differentiable with respect to means3D, shs or
+colors_precomp, opacities, scales and rotations, and `means2D.grad` receives the screen-space gradient."""
 from typing import NamedTuple
 
 import torch
@@ -53,13 +54,8 @@ class GaussianRasterizer(nn.Module):
             raise NotImplementedError("cov3D_precomp is not used by the reference call site")
         if rs.sh_degree != 0:
             raise NotImplementedError("sh_degree 0 only")
-        if any(t is not None and t.requires_grad and torch.is_grad_enabled() for t in (means3D, opacities, scales, rotations, shs)):
-            raise NotImplementedError("rasteriser backward lands with the VAE train step (next scope row)")
         dev = means3D.device
         P = means3D.shape[0]
-        f = lambda t, n: t.detach().to(dev, torch.float32).reshape(1, P, n).contiguous()
-        dc = f(shs, 3) if shs is not None else (f(colors_precomp, 3) - 0.5) / SH_C0
-        arrays = (f(means3D, 3), dc, f(scales, 3), f(rotations, 4), f(opacities, 1).reshape(1, P))
         cams = torch.cat([rs.viewmatrix.reshape(1, 16), rs.projmatrix.reshape(1, 16)], 1).to(dev, torch.float32).contiguous()
         prm = R.make_params(rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, None, rs.kernel_size,
                             rs.scale_modifier, tuple(float(b) for b in rs.bg.tolist()))
@@ -67,5 +63,15 @@ class GaussianRasterizer(nn.Module):
             self._rz = R.Rasterizer(dev)
         sub = rs.subpixel_offset
         sub = None if sub is None else sub.detach().to(dev, torch.float32).contiguous()
+        # colours: sh_degree 0 evaluates clamp_min(SH_C0 * dc + 0.5, 0) (renderers/sh_utils.py:57-113);
+        # colors_precomp is mapped onto the same input (identical for colours >= 0)
+        dc = shs if shs is not None else (colors_precomp - 0.5) / SH_C0
+        diff = torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                               for t in (means3D, means2D, dc, opacities, scales, rotations))
+        if diff:
+            return R.RasterizeActivated.apply(self._rz, prm, cams, sub, means3D, means2D, dc, opacities, scales,
+                                              rotations)
+        f = lambda t, n: t.detach().to(dev, torch.float32).reshape(1, P, n).contiguous()
+        arrays = (f(means3D, 3), f(dc, 3), f(scales, 3), f(rotations, 4), f(opacities, 1).reshape(1, P))
         rgba, radii = self._rz.forward(prm, arrays, None, cams, activated=True, subpixel_offset=sub)
         return rgba[0, :3], radii[0]

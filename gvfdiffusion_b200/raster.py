@@ -75,9 +75,20 @@ class Rasterizer:
         self._key = None
         self._ws = None
         self.cap = 0
+        self.hint = 0               # capacity learned by an earlier rasteriser of the same scene (see node())
+
+    def node(self):
+        """A rasteriser with its OWN workspace for one autograd node: backward reads the splat records, sorted
+        lists, final_T and n_contrib its forward left in the workspace (upstream returns them as the geom /
+        binning / img buffers saved for backward), so a forward that will be differentiated must not share a
+        workspace with the renders that follow it before `loss.backward()` (train_vae.py:313-334 renders every
+        camera first)."""
+        n = Rasterizer(self.device, self.tpg)
+        n.hint = max(self.hint, self.cap)
+        return n
 
     def _ensure(self, F, P, H, W, cap=None):
-        cap = int(cap or max(self.cap if self._key == (F, P, H, W) else 0, self.tpg * F * P, 1024))
+        cap = int(cap or max(self.cap if self._key == (F, P, H, W) else 0, self.hint, self.tpg * F * P, 1024))
         if self._key != (F, P, H, W) or cap != self.cap:
             nbytes = _lib.lib().gvf_raster_workspace_bytes(F, P, H, W, cap)
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -155,7 +166,9 @@ class RasterizeFrames(torch.autograd.Function):
     def forward(ctx, rz, prm, cams, xyz, dc, scaling, rotation, opacity, delta):
         arrays = tuple(t.detach().contiguous() for t in (xyz, dc, scaling, rotation, opacity))
         d = None if delta is None else delta.detach().contiguous()
+        parent, rz = rz, rz.node()                 # per-node workspace, kept alive by ctx until backward
         rgba, radii = rz.forward(prm, arrays, d, cams)
+        parent.hint = max(parent.hint, rz.cap)
         ctx.rz, ctx.prm, ctx.cams, ctx.arrays, ctx.delta = rz, prm, cams, arrays, d
         ctx.shapes = [t.shape for t in (xyz, dc, scaling, rotation, opacity)]
         ctx.mark_non_differentiable(radii)
@@ -167,6 +180,44 @@ class RasterizeFrames(torch.autograd.Function):
                                           want_delta_grad=ctx.delta is not None)
         outs = [o.reshape(s) for o, s in zip(outs, ctx.shapes)]
         return (None, None, None, *outs, gdelta)
+
+
+class RasterizeActivated(torch.autograd.Function):
+    """autograd node of the diff_gaussian_rasterization calling convention (one frame, ACTIVATED inputs):
+    (means3D, means2D, dc, opacities, scales, rotations) -> (color [3,H,W], radii [P]).  means2D only receives
+    the screen-space gradient (renderers/gaussian_render.py:96-100 reads `.grad` of a zero tensor)."""
+
+    @staticmethod
+    def forward(ctx, rz, prm, cams, sub, means3D, means2D, dc, opacities, scales, rotations):
+        P = means3D.shape[0]
+        f = lambda t, n: t.detach().to(torch.float32).reshape(1, P, n).contiguous()
+        arrays = (f(means3D, 3), f(dc, 3), f(scales, 3), f(rotations, 4), f(opacities, 1).reshape(1, P))
+        parent, rz = rz, rz.node()
+        rgba, radii = rz.forward(prm, arrays, None, cams, activated=True, subpixel_offset=sub)
+        parent.hint = max(parent.hint, rz.cap)
+        ctx.rz, ctx.prm, ctx.cams, ctx.sub, ctx.arrays = rz, prm, cams, sub, arrays
+        ctx.shapes = [t.shape for t in (means3D, dc, opacities, scales, rotations)]
+        ctx.m2_shape = None if means2D is None else means2D.shape
+        color, radii = rgba[0, :3], radii[0]
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, g_color, _g_radii):
+        H, W = ctx.prm.H, ctx.prm.W
+        g = torch.zeros((1, 4, H, W), dtype=torch.float32, device=g_color.device)
+        g[0, :3] = g_color
+        want_m2 = ctx.m2_shape is not None and ctx.needs_input_grad[5]
+        outs, _, gm2 = ctx.rz.backward(ctx.prm, ctx.arrays, None, ctx.cams, g, activated=True,
+                                       subpixel_offset=ctx.sub, want_means2D=want_m2)
+        g_m3, g_dc, g_sc, g_rot, g_op = (o[0] for o in outs)
+        s = ctx.shapes
+        g_m2 = None
+        if want_m2:
+            g_m2 = torch.zeros(ctx.m2_shape, dtype=torch.float32, device=g_color.device)
+            g_m2[:, :2] = gm2[0]
+        return (None, None, None, None, g_m3.reshape(s[0]), g_m2, g_dc.reshape(s[1]), g_op.reshape(s[2]),
+                g_sc.reshape(s[3]), g_rot.reshape(s[4]))
 
 
 def canon_arrays(canon, device):

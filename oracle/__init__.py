@@ -11,6 +11,8 @@ plain C) of the reference's algorithm for the path SURVEY.md section 8 scopes:
     vae.py      GSKLTemporalVariationalAutoEncoder.decode      (model/autoencoder.py)
     gaussian.py GaussianModel activations / get_*_with_delta, camera set-up
                 (representations/gaussian/gaussian_model.py, renderers/gaussian_render.py)
+    losses.py   ssim / L1 / KNN / interpolation loss of the training step (utils/loss_util.py,
+                train_vae.py:486-586; pytorch3d.knn_points restated from its documented semantics)
     raster.c    tile rasteriser forward + backward restatement (third-party
                 diff_gaussian_rasterization, mip-splatting fork -- NOT in /root/reference,
                 un-pinned git HEAD in setup.sh:220-224: "parity unpinned", see raster.c)
@@ -18,7 +20,7 @@ plain C) of the reference's algorithm for the path SURVEY.md section 8 scopes:
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import it.  The product package (gvfdiffusion_b200) never does.
 
-Pinning: dpm.py / dit.py / vae.py / gaussian.py are checked against the reference's
+Pinning: dpm.py / dit.py / vae.py / gaussian.py / losses.py are checked against the reference's
 own Python imported from /root/reference in the build container
 (tests/golden/make_golden.py writes the fixtures, tests/test_oracle_golden.py
 checks them everywhere).  raster.c has no reference-side golden: parity unpinned.

@@ -32,8 +32,10 @@ def activate(canon, delta, const):
 
 
 def project(means3D, scales, rots, shs, opac, view_t, proj_t, H, W, tanfovx, tanfovy, kernel_size=0.1,
-            scale_modifier=1.0):
-    """preprocess stage; view_t / proj_t are the transposed matrices handed to the rasteriser."""
+            scale_modifier=1.0, means2D=None):
+    """preprocess stage; view_t / proj_t are the transposed matrices handed to the rasteriser.
+    means2D: optional zero tensor [P,>=2] in NDC units added to the projected centre, so that its autograd
+    gradient is upstream's `dL_dmean2D` (blend-stage gradient of the screen position, d pix / d ndc = W/2, H/2)."""
     V, Pm = view_t.T, proj_t.T                      # V p = view-space point
     p = means3D
     t = p @ V[:3, :3].T + V[:3, 3]
@@ -41,6 +43,8 @@ def project(means3D, scales, rots, shs, opac, view_t, proj_t, H, W, tanfovx, tan
     pw = 1.0 / (hom[:, 3] + 1e-7)
     ndc = hom[:, :2] * pw[:, None]
     pix = torch.stack([((ndc[:, 0] + 1) * W - 1) * 0.5, ((ndc[:, 1] + 1) * H - 1) * 0.5], 1)
+    if means2D is not None:
+        pix = pix + means2D[:, :2] * torch.tensor([0.5 * W, 0.5 * H])
     s = scale_modifier * scales
     r, x, y, z = rots.unbind(1)
     R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),

@@ -73,3 +73,72 @@ def test_renderer_autograd_path_and_detach_static():
     res = r.render(gm, ext[0].to(DEV), intr.to(DEV), delta_pc=d, detach_static=False)
     (res["rgb"].sum() + res["alpha"].sum()).backward()
     assert gm._xyz.grad is not None and gm._scaling.grad.abs().sum() > 0
+
+
+def test_rasterizer_shim_backward_matches_autograd():
+    """The diff_gaussian_rasterization calling convention (activated inputs, one frame) is differentiable like
+    upstream's autograd Function; `means2D.grad` receives the screen-space gradient the reference reads at
+    renderers/gaussian_render.py:96-100."""
+    from gvfdiffusion_b200.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    H = W = 64
+    canon, delta, ext, intr, const = _scenes.scene(20, 1, H, W, seed=7)
+    m3, sc, rt, sh, op = [t.detach() for t in RT.activate(canon, delta[0], const)]
+    vt, pt, campos, tfx, tfy = OG.camera_matrices(ext[0], intr, 0.8, 1.6)
+    gen = torch.Generator().manual_seed(2)
+    wts = torch.randn(3, H, W, generator=gen)
+    # ---- oracle
+    o = [t.clone().requires_grad_(True) for t in (m3, sc, rt, sh, op)]
+    m2o = torch.zeros_like(m3).requires_grad_(True)
+    sp = RT.project(o[0], o[1], o[2], o[3], o[4], vt, pt, H, W, tfx, tfy, means2D=m2o)
+    img = RT.blend(sp, H, W, (1.0, 1.0, 1.0))
+    (img[:3] * wts).sum().backward()
+    # ---- ours, through the shim
+    st = GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=tfx, tanfovy=tfy, kernel_size=0.1,
+                                       subpixel_offset=torch.zeros(H, W, 2, device=DEV), bg=torch.ones(3, device=DEV),
+                                       scale_modifier=1.0, viewmatrix=vt.to(DEV), projmatrix=pt.to(DEV), sh_degree=0,
+                                       campos=campos.to(DEV), prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=st)
+    g = [t.to(DEV).clone().requires_grad_(True) for t in (m3, sc, rt, sh.reshape(-1, 1, 3), op.reshape(-1, 1))]
+    m2 = torch.zeros_like(g[0], requires_grad=True)
+    color, radii = rast(means3D=g[0], means2D=m2, shs=g[3], colors_precomp=None, opacities=g[4], scales=g[1],
+                        rotations=g[2], cov3D_precomp=None)
+    assert not radii.requires_grad
+    assert (color.detach().cpu() - img[:3].detach()).abs().max() < 1e-3
+    (color * wts.to(DEV)).sum().backward()
+    for name, a, b in (("means3D", g[0], o[0]), ("scales", g[1], o[1]), ("rotations", g[2], o[2]), ("shs", g[3], o[3]),
+                       ("opacities", g[4], o[4])):
+        assert _rel(a.grad.reshape(b.shape), b.grad) < 3e-3, (name, _rel(a.grad.reshape(b.shape), b.grad))
+    assert _rel(m2.grad[:, :2], m2o.grad[:, :2]) < 3e-3 and float(m2.grad[:, 2].abs().max()) == 0.0
+    # colors_precomp form: gradient reaches the colours through the same kernel
+    cp = (0.28209479177387814 * sh + 0.5).clamp_min(0.01).to(DEV).requires_grad_(True)
+    color2, _ = rast(means3D=g[0].detach(), means2D=None, shs=None, colors_precomp=cp, opacities=g[4].detach(),
+                     scales=g[1].detach(), rotations=g[2].detach())
+    color2.sum().backward()
+    assert cp.grad is not None and float(cp.grad.abs().sum()) > 0
+
+
+def test_several_renders_before_one_backward():
+    """train_vae.py:313-334 renders every camera, sums the losses and calls backward once: each autograd node
+    keeps its own workspace (upstream: the geom / binning / img buffers saved for backward), so the gradients
+    equal those of rendering and differentiating the views one at a time."""
+    from gvfdiffusion_b200.renderers import GaussianRenderer
+    from tests.test_api_gpu import _model
+    canon, delta, ext, intr, const = _scenes.scene(24, 3, 64, 64, seed=11)
+    r = GaussianRenderer({"near": 0.8, "far": 1.6, "bg_color": (1.0, 1.0, 1.0)})
+    r.pipe.use_mip_gaussian = True
+    r.rendering_options.resolution = 64
+    gm = _model(canon)
+
+    def grads(together):
+        d = delta.to(DEV).clone().requires_grad_(True)
+        if together:
+            imgs = [r.render(gm, ext[f].to(DEV), intr.to(DEV), delta_pc=d[f], detach_static=True)["rgb"] for f in range(3)]
+            sum((im * (f + 1)).sum() for f, im in enumerate(imgs)).backward()
+        else:
+            for f in range(3):
+                (r.render(gm, ext[f].to(DEV), intr.to(DEV), delta_pc=d[f], detach_static=True)["rgb"] * (f + 1)).sum().backward()
+        return d.grad.clone()
+
+    a, b = grads(True), grads(False)
+    assert float(b.abs().sum()) > 0
+    assert _rel(a, b) < 1e-5, _rel(a, b)
