@@ -370,6 +370,17 @@ def main():
     r1.record()
     torch.cuda.synchronize()
     raster_ms = r0.elapsed_time(r1) / 5
+    # the reference's visualisation loop (utils/inference_utils.py:243-283): every timestep from 128 orbit
+    # cameras, clamped and converted to uint8 on the device (24 x 128 renders, one rasteriser call per timestep)
+    from gvfdiffusion_b200 import synthetic as S
+    views_ext = S.orbit_extrinsics(128)
+    u8 = pipe.render_views(obj, delta, views_ext, hin["intr"])
+    r0.record()
+    pipe.render_views(obj, delta, views_ext, hin["intr"], out=u8)
+    r1.record()
+    torch.cuda.synchronize()
+    views_ms = r0.elapsed_time(r1)
+    del u8
 
     if rank != 0:
         return
@@ -412,7 +423,7 @@ def main():
                               "(profiles/r01_attn6_full_extract.csv)")},
         "roofline_detail": roof_detail,
         "stage_ms_eager": {"prepare_fps": stage_ms[3], "sample_32nfe": stage_ms[0], "vae_decode": stage_ms[1],
-                           "raster_24f": stage_ms[2]},
+                           "raster_24f": stage_ms[2], "raster_24x128_views_u8": views_ms},
         "roofline_raster": {"bound": "hbm", "kernel": "gvf_raster_forward (4 kernels, 24 frames)",
                             "achieved": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6,
                             "peak": pk["hbm_gbs"], "unit": "GB/s",

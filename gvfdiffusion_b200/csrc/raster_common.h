@@ -63,7 +63,7 @@ cudaError_t launch_preprocess(const gvf_raster_params& prm, int F, int P, int ac
                               const float* xyz, const float* dc, const float* scaling,
                               const float* rotation, const float* opacity, const float* delta,
                               const float* cams, const RasterWs& ws, int32_t* radii,
-                              cudaStream_t st);
+                              cudaStream_t st, int views = 1);
 cudaError_t launch_scan(int n_tiles_total, const RasterWs& ws, cudaStream_t st);
 cudaError_t launch_scatter(const gvf_raster_params& prm, int F, int P, const RasterWs& ws,
                            int64_t cap, cudaStream_t st);

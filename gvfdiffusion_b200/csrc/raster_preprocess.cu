@@ -29,6 +29,7 @@ __device__ __forceinline__ int f2i_clamped(float v) {
 struct PreArgs {
   gvf_raster_params prm;
   int F, P, activated;
+  int views;           // consecutive frames that share one delta row (cameras per timestep), >= 1
   const float *xyz, *dc, *scaling, *rotation, *opacity, *delta, *cams;
   float4* splat;
   ushort4* rect;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
     float d[14];
     if (a.delta) {
       // [F,P,14] rows are 56 B: 8-byte aligned -> seven float2 loads
-      const float2* dp = reinterpret_cast<const float2*>(a.delta + (size_t)gid * 14);
+      const float2* dp = reinterpret_cast<const float2*>(a.delta + ((size_t)(f / a.views) * a.P + i) * 14);
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
         const float2 v = __ldg(dp + k);
@@ -212,9 +213,9 @@ cudaError_t launch_preprocess(const gvf_raster_params& prm, int F, int P, int ac
                               const float* xyz, const float* dc, const float* scaling,
                               const float* rotation, const float* opacity, const float* delta,
                               const float* cams, const RasterWs& ws, int32_t* radii,
-                              cudaStream_t st) {
+                              cudaStream_t st, int views) {
   PreArgs a;
-  a.prm = prm; a.F = F; a.P = P; a.activated = activated;
+  a.prm = prm; a.F = F; a.P = P; a.activated = activated; a.views = views < 1 ? 1 : views;
   a.xyz = xyz; a.dc = dc; a.scaling = scaling; a.rotation = rotation; a.opacity = opacity;
   a.delta = delta; a.cams = cams;
   a.splat = ws.splat; a.rect = ws.rect; a.tile_count = ws.tile_count; a.radii = radii;

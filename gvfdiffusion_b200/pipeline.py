@@ -108,6 +108,29 @@ class GVFPipeline:
                                   out=out, check_overflow=False)
         return rgba
 
+    def render_views(self, obj, delta, extrinsics, intrinsics, timesteps_per_call=1, out=None):
+        """The reference's visualisation loop (utils/inference_utils.py:243-283): every timestep of `delta`
+        [T,P,14] from every camera of `extrinsics` [V,4,4] (128 orbit views there), clamped and converted to
+        uint8 like `(rgb.clamp(0, 1) * 255).astype('uint8')` -> [T,V,H,W,3] uint8 on the device.  One rasteriser
+        call per `timesteps_per_call` timesteps (V frames each share a delta row: gvf_raster_forward_views);
+        the fp32 frames of a call are converted in place of being kept (PNG / ffmpeg writing stays with the caller)."""
+        T, V = delta.shape[0], extrinsics.shape[0]
+        cams, tfx, tfy = R.pack_cameras(extrinsics, intrinsics, self.near, self.far)
+        prm = R.make_params(self.res, self.res, tfx, tfy, self.const, self.kernel_size, 1.0, self.bg)
+        cams = cams.to(self.dev)
+        if out is None:
+            out = torch.empty((T, V, self.res, self.res, 3), dtype=torch.uint8, device=self.dev)
+        if not hasattr(self, "_rz_views"):
+            self._rz_views = R.Rasterizer(self.dev)
+        n = max(1, int(timesteps_per_call))
+        delta = delta.contiguous()
+        for t0 in range(0, T, n):
+            t1 = min(T, t0 + n)
+            rgba, _ = self._rz_views.forward(prm, obj.arrays, delta[t0:t1], cams.repeat(t1 - t0, 1), want_radii=False,
+                                             views_per_delta=V)
+            R.rgba_to_u8(rgba, out[t0:t1].view(-1, self.res, self.res, 3))
+        return out
+
     def __call__(self, obj, cond_images, noise, extrinsics, intrinsics, steps=32, **kw):
         lat = self.sample(obj, cond_images, noise, steps=steps, **kw)
         delta = self.decode(lat, obj)

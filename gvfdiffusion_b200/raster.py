@@ -111,9 +111,10 @@ class Rasterizer:
         return int(s[0]) & 0xffffffff, bool(s[1]), int(s[2])
 
     def forward(self, prm, arrays, delta, cams, activated=False, subpixel_offset=None,
-                want_radii=True, out=None, check_overflow=True):
+                want_radii=True, out=None, check_overflow=True, views_per_delta=1):
         """arrays = (xyz, dc, scaling, rotation, opacity) fp32 contiguous device tensors.
-        Returns rgba (F,4,H,W) fp32 and radii (F,P) int32 (or None)."""
+        Returns rgba (F,4,H,W) fp32 and radii (F,P) int32 (or None).  views_per_delta = V > 1: the F frames
+        are (timestep, camera) pairs ordered timestep-major and delta is [F / V, P, 14] (gvf_raster_forward_views)."""
         L = _lib.lib()
         F = cams.shape[0]
         P = arrays[0].shape[-2] if arrays[0].dim() >= 2 else arrays[0].shape[0]
@@ -125,10 +126,18 @@ class Rasterizer:
             ws = self._ensure(F, P, H, W)
             rgba = out if out is not None else torch.empty((F, 4, H, W), dtype=torch.float32, device=self.device)
             radii = torch.empty((F, P), dtype=torch.int32, device=self.device) if want_radii else None
-            st = L.gvf_raster_forward(C.byref(prm), F, P, int(activated), *[_lib.ptr(a) for a in arrays],
-                                      _lib.ptr(delta), _lib.ptr(cams), _lib.ptr(subpixel_offset),
-                                      _lib.ptr(rgba), _lib.ptr(radii), _lib.ptr(ws), ws.numel(),
-                                      self.cap, _lib.current_stream())
+            if views_per_delta > 1:
+                if delta is None or delta.shape[0] * views_per_delta != F or activated:
+                    raise ValueError("views_per_delta: delta must be [F / views, P, 14] and inputs raw")
+                st = L.gvf_raster_forward_views(C.byref(prm), F, P, int(views_per_delta), *[_lib.ptr(a) for a in arrays],
+                                                _lib.ptr(delta), _lib.ptr(cams), _lib.ptr(subpixel_offset),
+                                                _lib.ptr(rgba), _lib.ptr(radii), _lib.ptr(ws), ws.numel(),
+                                                self.cap, _lib.current_stream())
+            else:
+                st = L.gvf_raster_forward(C.byref(prm), F, P, int(activated), *[_lib.ptr(a) for a in arrays],
+                                          _lib.ptr(delta), _lib.ptr(cams), _lib.ptr(subpixel_offset),
+                                          _lib.ptr(rgba), _lib.ptr(radii), _lib.ptr(ws), ws.numel(),
+                                          self.cap, _lib.current_stream())
             _lib.check(st, "gvf_raster_forward")
             if not check_overflow:
                 return rgba, radii
@@ -157,6 +166,18 @@ class Rasterizer:
                                    _lib.ptr(gdelta), _lib.ptr(gm2), _lib.current_stream())
         _lib.check(st, "gvf_raster_backward")
         return outs, gdelta, gm2
+
+
+def rgba_to_u8(rgba, out=None):
+    """(clamp(rgb, 0, 1) * 255).astype(uint8): planar fp32 [F,4,H,W] -> [F,H,W,3] uint8 on the device
+    (utils/inference_utils.py:278-283)."""
+    if not (rgba.is_cuda and rgba.dtype == torch.float32 and rgba.is_contiguous() and rgba.dim() == 4 and rgba.shape[1] == 4):
+        raise ValueError("rgba_to_u8: expected a contiguous CUDA fp32 [F,4,H,W] tensor")
+    F, _, H, W = rgba.shape
+    if out is None:
+        out = torch.empty((F, H, W, 3), dtype=torch.uint8, device=rgba.device)
+    _lib.check(_lib.lib().gvf_rgba_to_u8(_lib.ptr(rgba), F, H, W, _lib.ptr(out), _lib.current_stream()), "gvf_rgba_to_u8")
+    return out
 
 
 class RasterizeFrames(torch.autograd.Function):

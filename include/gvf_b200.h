@@ -102,6 +102,20 @@ GVF_API int gvf_raster_forward(const gvf_raster_params* prm, int F, int P, int a
                        int32_t* radii, void* workspace, size_t workspace_bytes, int64_t cap,
                        void* stream);
 
+/* The reference's visualisation loop renders every timestep from 128 orbit cameras
+ * (utils/inference_utils.py:243-269: 32 x 128 calls of renderer.render per object).  Same as
+ * gvf_raster_forward(activated = 0) for F = timesteps x views_per_delta frames ordered timestep-major,
+ * with delta [F / views_per_delta, P, 14]: the views of one timestep read the same delta rows (no
+ * replicated copies), cams stays per frame [F,32]. */
+GVF_API int gvf_raster_forward_views(const gvf_raster_params* prm, int F, int P, int views_per_delta,
+                       const float* xyz, const float* dc, const float* scaling,
+                       const float* rotation, const float* opacity, const float* delta,
+                       const float* cams, const float* subpixel_offset, float* out_rgba,
+                       int32_t* radii, void* workspace, size_t workspace_bytes, int64_t cap,
+                       void* stream);
+/* Output stage of the same loop (utils/inference_utils.py:278-283): (clamp(rgb, 0, 1) * 255).astype(uint8),
+ * planar fp32 rgba [F,4,H,W] -> interleaved uint8 [F,H,W,3] on the device (a quarter of the bytes to copy back). */
+GVF_API int gvf_rgba_to_u8(const float* rgba, int F, int H, int W, uint8_t* out, void* stream);
 
 /* Backward -- replaces GaussianRasterizer.backward (reached through autograd from reference
  * train_vae.py:313-352) fused with the backward of GaussianModel.get_*_with_delta.  Must follow a

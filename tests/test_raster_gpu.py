@@ -101,3 +101,42 @@ def test_raster_empty_and_culled():
     rz, rgba, radii = _run_cuda(canon, None, ext, intr, const, 64, 64)
     assert (radii == 0).all() and outs[0]["num_rendered"] == 0
     assert np.allclose(rgba[0, :3], 1.0) and np.allclose(rgba[0, 3], 0.0)
+
+
+def test_views_per_delta_matches_replicated_delta_and_oracle():
+    """The reference's visualisation loop renders each timestep from many cameras
+    (utils/inference_utils.py:243-269).  gvf_raster_forward_views lets the V views of a timestep read one delta
+    row: bit-identical to rasterising with the delta replicated per frame, and frame (t, v) matches the oracle's
+    render of delta[t] from camera v (indices bit-exact)."""
+    from gvfdiffusion_b200 import raster as R
+    T, V, H, W = 2, 3, 96, 96
+    canon, delta, _, intr, const = _scenes.scene(96, T, H, W)
+    from gvfdiffusion_b200 import synthetic as S
+    ext = S.orbit_extrinsics(V)
+    cams, tfx, tfy = R.pack_cameras(ext, intr, 0.8, 1.6)
+    prm = R.make_params(H, W, tfx, tfy, const)
+    arrays = R.canon_arrays(canon, "cuda")
+    cams_tv = cams.repeat(T, 1).cuda()
+    rz = R.Rasterizer("cuda")
+    a, ra = rz.forward(prm, arrays, delta.cuda().contiguous(), cams_tv, views_per_delta=V)
+    rz2 = R.Rasterizer("cuda")
+    b, rb = rz2.forward(prm, arrays, delta.repeat_interleave(V, 0).cuda().contiguous(), cams_tv)
+    assert torch.equal(a, b) and torch.equal(ra, rb)
+    for t in range(T):
+        outs = _scenes.oracle_frames(canon, delta[t:t + 1].expand(V, -1, -1), ext, intr, const, H, W)
+        for v in range(V):
+            assert np.array_equal(ra[t * V + v].cpu().numpy(), outs[v]["radii"])
+            assert np.abs(a[t * V + v].cpu().numpy() - outs[v]["rgba"]).max() <= 1e-2
+    with pytest.raises(ValueError):
+        rz.forward(prm, arrays, delta.cuda().contiguous(), cams_tv[:5], views_per_delta=V)
+
+
+def test_rgba_to_u8_is_the_reference_conversion():
+    """(rgb.clamp(0, 1) * 255).astype('uint8') of utils/inference_utils.py:278-283, bit-exact, HWC."""
+    from gvfdiffusion_b200 import raster as R
+    g = torch.Generator().manual_seed(0)
+    rgba = (torch.rand(3, 4, 40, 56, generator=g) * 1.4 - 0.2)
+    rgba[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 0.999999, 1.0 / 255.0])
+    got = R.rgba_to_u8(rgba.cuda().contiguous()).cpu().numpy()
+    want = (rgba[:, :3].clamp(0.0, 1.0).permute(0, 2, 3, 1).numpy() * 255).astype("uint8")
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
