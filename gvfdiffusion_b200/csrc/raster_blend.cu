@@ -23,25 +23,26 @@ constexpr int kSortCap = 2048;
 
 template <typename KeyPtr>
 __device__ __forceinline__ void bitonic_sort_any_n(KeyPtr keys, int n) {
-  // all-ascending bitonic network ("flip" then "disperse"), valid for arbitrary n
-  int np2 = 1;
-  while (np2 < n) np2 <<= 1;
-  const int ncmp = np2 >> 1;
-  for (int k = 2; k <= np2; k <<= 1) {
-    const int h = k >> 1;
+  // all-ascending bitonic network ("flip" then "disperse"), valid for arbitrary n.  Block sizes are powers of
+  // two: comparator -> element indices by shifts and masks (lk = log2 k), no integer division.
+  int lnp2 = 0;
+  while ((1 << lnp2) < n) ++lnp2;
+  const int ncmp = (1 << lnp2) >> 1;
+  for (int lk = 1; lk <= lnp2; ++lk) {
+    const int lh = lk - 1, hmask = (1 << lh) - 1, kfull = (1 << lk) - 1;
     for (int c = threadIdx.x; c < ncmp; c += blockDim.x) {
-      const int blk = c / h, r = c - blk * h;
-      const int i = blk * k + r, p = blk * k + (k - 1 - r);
+      const int blk = c >> lh, r = c & hmask;
+      const int i = (blk << lk) + r, p = (blk << lk) + (kfull - r);
       if (p < n) {
         const unsigned long long a = keys[i], b = keys[p];
         if (a > b) { keys[i] = b; keys[p] = a; }
       }
     }
     __syncthreads();
-    for (int j = h >> 1; j >= 1; j >>= 1) {
+    for (int lj = lh - 1; lj >= 0; --lj) {
+      const int jmask = (1 << lj) - 1;
       for (int c = threadIdx.x; c < ncmp; c += blockDim.x) {
-        const int blk = c / j, r = c - blk * j;
-        const int i = blk * 2 * j + r, p = i + j;
+        const int i = ((c >> lj) << (lj + 1)) + (c & jmask), p = i + (1 << lj);
         if (p < n) {
           const unsigned long long a = keys[i], b = keys[p];
           if (a > b) { keys[i] = b; keys[p] = a; }
@@ -50,6 +51,12 @@ __device__ __forceinline__ void bitonic_sort_any_n(KeyPtr keys, int n) {
       __syncthreads();
     }
   }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2; flushes denormal results to zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 struct BlendArgs {
@@ -72,6 +79,7 @@ __global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArg
   __shared__ float4 sA[GVF_TILE_PIX];   // px, py, conic a, conic b
   __shared__ float2 sT[GVF_TILE_PIX];   // conic c, rejection threshold on `power` (see below)
   __shared__ float4 sC[GVF_TILE_PIX];   // opacity', r, g, b  (read only by pixels the splat reaches)
+  __shared__ uint32_t sM[GVF_TILE_PIX]; // bit w: the splat's alpha >= 1/255 ellipse may reach warp w's 8 x 4 block
 
   const int T = a.gx * a.gy;
   const int tile = blockIdx.x;
@@ -105,8 +113,11 @@ __global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArg
     }
   }
 
-  const int px = txi * GVF_TILE + (tid & (GVF_TILE - 1));
-  const int py = tyi * GVF_TILE + (tid >> 4);
+  // a warp covers an 8 x 4 pixel block (not a 16 x 2 strip): the more compact footprint lets whole warps
+  // leave the loop body at the rejection test more often
+  const int wq = tid >> 5, ln = tid & 31;
+  const int px = txi * GVF_TILE + (ln & 7) + 8 * (wq & 1);
+  const int py = tyi * GVF_TILE + (ln >> 3) + 4 * (wq >> 1);
   const bool inside = px < a.W && py < a.H;
   const size_t HW = (size_t)a.H * a.W;
   const size_t pid = (size_t)py * a.W + px;
@@ -116,10 +127,12 @@ __global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArg
     pfx += o.x;
     pfy += o.y;
   }
-  float Tr = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-  uint32_t contributor = 0, last = 0;
+  float Tr = 1.0f, Tfin = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  uint32_t last = 0;
   bool done = !inside;
   const float4* sp = a.splat + (size_t)f * a.P * 3;
+  const float tile_x0 = (float)(txi * GVF_TILE), tile_y0 = (float)(tyi * GVF_TILE);
+  const float slack = a.subpixel_offset ? 1.01f : 0.01f;      // pixel centres move by the sub-pixel offset
 
   for (int base = 0; base < n; base += GVF_TILE_PIX) {
     if (__syncthreads_count(done) == GVF_TILE_PIX) break;
@@ -127,36 +140,76 @@ __global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArg
     if (j < n) {
       const uint32_t id = in_smem ? (uint32_t)skeys[j] : (uint32_t)gk[j];
       const float4* r = sp + (size_t)id * 3;
-      const float4 r1 = __ldg(r + 1);
-      sA[tid] = __ldg(r);
-      // 9 of 10 (pixel, splat) pairs of a tile end at "alpha < 1/255".  op * exp(power) < 1/255 is decided on
-      // `power` alone against log(1 / (255 op)); the 0.01 margin (1 % in alpha, __expf is good to 1e-6) keeps
-      // the pre-test strictly conservative, so the exact test below takes the same decisions as before
-      sT[tid] = make_float2(r1.x, -__logf(255.0f * r1.y) - 0.01f);
+      const float4 r0 = __ldg(r), r1 = __ldg(r + 1);
+      // The conic is staged pre-multiplied by -0.5 log2(e) (a, c) and -log2(e) (b): the loop evaluates
+      // log2 of the Gaussian with five FMUL / FFMA and feeds MUFU.EX2 directly.
+      // 9 of 10 (pixel, splat) pairs of a tile end at "alpha < 1/255".  op * 2^p < 1/255 is decided on p alone
+      // against -log2(255 op); the 0.0145 margin (1 % in alpha, ex2.approx is good to 2^-22) keeps the pre-test
+      // strictly conservative, so the exact test below takes the same decisions as without it
+      constexpr float kLog2e = 1.4426950408889634f;
+      const float qa = 0.5f * kLog2e * r0.z, qb = kLog2e * r0.w, qc = 0.5f * kLog2e * r1.x;
+      const float tau = __log2f(255.0f * r1.y) + 0.0145f;      // the pair survives iff qa dx^2 + qb dx dy + qc dy^2 <= tau
+      sA[tid] = make_float4(r0.x, r0.y, -qa, -qb);
+      sT[tid] = make_float2(-qc, -tau);
       sC[tid] = make_float4(r1.y, r1.z, r1.w, __ldg(reinterpret_cast<const float*>(r + 2)));
+      // Sub-tile culling.  ncu: 86 % of the (warp, splat) pairs of the list were rejected by all 32 lanes, each
+      // at the price of the full rejection test.  The thread that stages a splat intersects the axis-aligned
+      // bounding box of its {alpha >= 1/255} ellipse (half extents sqrt(tau qc / det), sqrt(tau qa / det),
+      // inflated against rounding) with the eight 8 x 4 pixel blocks of the tile, one per warp; a warp then
+      // walks only the splats whose bit is set.  Skipped pairs are pairs the exact test rejects: same image.
+      uint32_t mask = 0;
+      if (tau > 0.0f) {
+        const float det = qa * qc - 0.25f * qb * qb;
+        mask = 0xffu;
+        if (det > 0.0f) {
+          const float k = tau / det;
+          const float hx = sqrtf(k * qc) * 1.001f + slack, hy = sqrtf(k * qa) * 1.001f + slack;
+          const float cx = r0.x - tile_x0, cy = r0.y - tile_y0;
+          const float xl = cx - hx, xh = cx + hx, yl = cy - hy, yh = cy + hy;
+          const uint32_t cols = (xl <= 7.0f && xh >= 0.0f ? 1u : 0u) | (xl <= 15.0f && xh >= 8.0f ? 2u : 0u);
+          mask = 0;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+            if (yl <= (float)(4 * rr + 3) && yh >= (float)(4 * rr)) mask |= cols << (2 * rr);
+        }
+      }
+      sM[tid] = mask;
     }
     __syncthreads();
     const int m = min(GVF_TILE_PIX, n - base);
-    for (int k = 0; !done && k < m; ++k) {
-      ++contributor;
-      const float4 A = sA[k];
-      const float2 ct = sT[k];
-      const float dx = A.x - pfx, dy = A.y - pfy;
-      const float power = -0.5f * (A.z * dx * dx + ct.x * dy * dy) - A.w * dx * dy;
-      if (power > 0.0f || power < ct.y) continue;
-      const float4 B = sC[k];
-      const float alpha = fminf(0.99f, B.x * __expf(power));
-      if (alpha < 1.0f / 255.0f) continue;
-      const float test_T = Tr * (1.0f - alpha);
-      if (test_T < 0.0001f) { done = true; continue; }
-      const float w = alpha * Tr;
-      C0 += B.y * w;
-      C1 += B.z * w;
-      C2 += B.w * w;
-      Tr = test_T;
-      last = contributor;
+    for (int g = 0; g < m; g += 32) {
+      if (__all_sync(0xffffffffu, done)) break;
+      const uint32_t mk = (g + ln < m) ? sM[g + ln] : 0u;
+      uint32_t bits = __ballot_sync(0xffffffffu, (mk >> wq) & 1u);
+      while (bits) {
+        const int k = g + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const float4 A = sA[k];
+        const float2 ct = sT[k];
+        const float dx = A.x - pfx, dy = A.y - pfy;
+        const float t = fmaf(A.z, dx, A.w * dy);
+        const float p2 = fmaf(dx, t, (ct.x * dy) * dy);       // log2 of exp(power)
+        if (p2 > 0.0f || p2 < ct.y) continue;
+        const float4 B = sC[k];
+        const float alpha = fminf(0.99f, B.x * ex2_approx(p2));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = Tr * (1.0f - alpha);
+        if (test_T < 0.0001f) {
+          // saturated: this pixel is finished.  Its lane stays in the warp's loop (the ballots need it) with a
+          // live transmittance of zero, which sends every later candidate to this branch again.
+          if (!done) { Tfin = Tr; done = true; Tr = 0.0f; }
+          continue;
+        }
+        const float w = alpha * Tr;
+        C0 += B.y * w;
+        C1 += B.z * w;
+        C2 += B.w * w;
+        Tr = test_T;
+        last = (uint32_t)(base + k + 1);                      // entries of the tile list seen up to this one
+      }
     }
   }
+  if (done) Tr = Tfin;
   if (inside) {
     float* o = a.out_rgba + (size_t)f * 4 * HW + pid;
     o[0] = C0 + Tr * a.bg0;
