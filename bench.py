@@ -429,8 +429,10 @@ def main():
                             "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6 / pk["hbm_gbs"],
                             "ms": raster_ms, "traffic": None,
-                            "note": ("not HBM-bound at this depth complexity: ~0.5 G pixel-splat evaluations per 24 "
-                                     "frames, sort_blend runs at 77 % SM issue throughput (profiles/r01_raster_full_extract.csv)")},
+                            "note": ("not HBM-bound at this depth complexity: 17.7 M (warp, splat) pairs per 24 frames; with "
+                                     "sub-tile culling sort_blend executes 310 M warp instructions (671 M before) at 75 % issue "
+                                     "utilisation, about half of them in the per-tile depth sort "
+                                     "(profiles/r01_raster_full_extract.csv)")},
     }
     if not args.no_cpu_baseline and world == 1:
         try:
