@@ -9,7 +9,7 @@ Out of scope here and therefore replaced by inputs (TRELLIS
 CLIP alignment, dataset loading, PNG/ffmpeg output): the canonical Gaussians and the DINOv2
 conditioning come from `--data_dir/<name>.pt` files ({"gaussian": dict of raw GaussianModel tensors,
 "cond_images": (T,1370,1024)}) or, when absent, from the seeded synthetic generator; frames are
-written as one uint8 tensor per object (`rgba_<id>.pt`) instead of 4096 PNGs.
+written as one uint8 tensor per object (`rgb_<id>.pt`, (T, cameras, H, W, 3)) instead of 4096 PNGs.
 
 Multi-GPU: launch with torchrun; objects are sharded round-robin across ranks (the reference runs
 every object on every rank)."""
@@ -21,6 +21,7 @@ import torch
 import yaml
 
 from gvfdiffusion_b200 import parallel, synthetic
+from gvfdiffusion_b200 import raster as R
 from gvfdiffusion_b200.model.autoencoder import GSKLTemporalVariationalAutoEncoder
 from gvfdiffusion_b200.model.dit import DiT
 from gvfdiffusion_b200.pipeline import GVFPipeline
@@ -89,8 +90,8 @@ def create_argparser():
     return p
 
 
-def main():
-    args = create_argparser().parse_args()
+def main(argv=None):
+    args = create_argparser().parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -144,13 +145,14 @@ def main():
         lat = pipe.sample(obj, cond.to(dev), noise, steps=args.rescale_timesteps, guidance_scale=args.guidance_scale,
                           guidance_scale2=args.guidance_scale2, adaptive=args.adaptive)
         delta = pipe.decode(lat, obj, d_mean, d_std)
-        frames = []
-        for c in range(args.num_cameras):
-            ext = synthetic.orbit_extrinsics(args.num_cameras)[c][None].expand(T, 4, 4) if args.num_cameras > 1 \
-                else synthetic.orbit_extrinsics(T)
-            frames.append(pipe.render(obj, delta, ext, intr).clamp(0, 1))
-        rgba = torch.stack(frames, 0)                      # (cams, T, 4, H, W)
-        torch.save((rgba * 255).to(torch.uint8).cpu(), os.path.join(args.exp_name, f"rank_{rank:02d}_rgba_{i:06d}.pt"))
+        if args.num_cameras > 1:
+            # the reference's visualisation loop (utils/inference_utils.py:243-283): every timestep from every orbit
+            # camera, clamp * 255 -> uint8 on the device -> (T, cams, H, W, 3)
+            out = pipe.render_views(obj, delta, synthetic.orbit_extrinsics(args.num_cameras), intr)
+        else:
+            out = R.rgba_to_u8(pipe.render(obj, delta, synthetic.orbit_extrinsics(T), intr))[:, None]
+        torch.save(out.cpu(), os.path.join(args.exp_name, f"rank_{rank:02d}_rgb_{i:06d}.pt"))
+        rgba = out
         print(f"[rank {rank}] object {i}: {tuple(rgba.shape)} frames written")
 
 
