@@ -366,6 +366,81 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(const float* __restri
   }
 }
 
+// Second generation of the single-CTA kernel.  Per sample the first one re-read all three coordinate arrays
+// from shared memory (196 KB = 1536 clocks of the SM's 128 B / clk) and spent as long again issuing twelve
+// instructions per point.  Here every thread keeps the x coordinates of its PER points in registers next to
+// their running minimum distances (y and z still come from shared memory: the register file cannot hold all
+// three at 1024 threads), and the arithmetic runs on packed pairs of points (sub / mul / add .f32x2: the same
+// individually rounded operations in the same order, half the instructions).  Identical indices.
+__device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, float b) {
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %4};\nsub.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n}" : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1) {      // (a0*a0, a1*a1)
+  asm("{\n.reg .b64 ra, rd;\nmov.b64 ra, {%2, %3};\nmul.rn.f32x2 rd, ra, ra;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nadd.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n}" : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+template <int PER>
+__global__ void __launch_bounds__(1024, 1) fps_smem2_kernel(const float* __restrict__ pts, int ld, int P, int K,
+                                                             int start, int* __restrict__ out_idx) {
+  extern __shared__ float sxyz[];                  // x[0..Pp) | y | z, Pp = PER * 1024
+  __shared__ unsigned sd[2][32];
+  __shared__ unsigned si[2][32];
+  constexpr int Pp = PER * 1024;
+  float* sx = sxyz; float* sy = sxyz + Pp; float* sz = sxyz + 2 * Pp;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float md[PER], px[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid + 1024 * j;
+    const bool ok = i < P;
+    px[j] = ok ? pts[(size_t)i * ld] : 0.f;
+    sx[i] = px[j];
+    sy[i] = ok ? pts[(size_t)i * ld + 1] : 0.f;
+    sz[i] = ok ? pts[(size_t)i * ld + 2] : 0.f;
+    md[j] = ok ? 3.0e38f : -1.0f;                  // padding never wins: min(-1, d) = -1 < any distance
+  }
+  unsigned cur = (unsigned)start;
+  if (tid == 0) out_idx[0] = start;
+  __syncthreads();
+  for (int k = 1; k < K; ++k) {
+    const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+    float best = -1.0f;
+    unsigned bi = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < PER; j += 2) {
+      const int i0 = tid + 1024 * j, i1 = i0 + 1024;
+      float dx0, dx1, dy0, dy1, dz0, dz1, s0, s1;
+      sub2(dx0, dx1, px[j], px[j + 1], cx);
+      sub2(dy0, dy1, sy[i0], sy[i1], cy);
+      sub2(dz0, dz1, sz[i0], sz[i1], cz);
+      mul2(dx0, dx1, dx0, dx1);
+      mul2(dy0, dy1, dy0, dy1);
+      mul2(dz0, dz1, dz0, dz1);
+      add2(s0, s1, dx0, dx1, dy0, dy1);
+      add2(s0, s1, s0, s1, dz0, dz1);               // (dx*dx + dy*dy) + dz*dz, every operation rounded
+      const float d0 = fminf(md[j], s0), d1 = fminf(md[j + 1], s1);
+      md[j] = d0; md[j + 1] = d1;
+      if (d0 > best) { best = d0; bi = (unsigned)i0; }   // ascending i per thread: first max kept
+      if (d1 > best) { best = d1; bi = (unsigned)i1; }
+    }
+    unsigned ub = best < 0.f ? 0u : __float_as_uint(best);
+    unsigned wm = __reduce_max_sync(0xffffffffu, ub);
+    unsigned wi = __reduce_min_sync(0xffffffffu, ub == wm ? bi : 0xffffffffu);
+    if (lane == 0) { sd[k & 1][w] = wm; si[k & 1][w] = wi; }
+    __syncthreads();
+    ub = sd[k & 1][lane];
+    bi = si[k & 1][lane];
+    wm = __reduce_max_sync(0xffffffffu, ub);
+    cur = __reduce_min_sync(0xffffffffu, ub == wm ? bi : 0xffffffffu);
+    if (tid == 0) out_idx[k] = (int)cur;
+  }
+}
+
 // Cluster variant: the cloud is spread over the 8 CTAs of one thread-block cluster, 512 threads each, every
 // thread keeps the coordinates and running minimum distances of its PER points in REGISTERS (the single-CTA
 // kernel above re-reads all 196 KB of coordinates from shared memory for every sample: 1536 clocks of
@@ -474,13 +549,14 @@ extern "C" GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start
     return true;
   };
   bool ok = true;
-  // MEASURED (tools/fps_bench.py, 16384 -> 4096): cluster kernel 7.2 ms, single-CTA shared-memory kernel 5.7 ms --
+  // MEASURED (tools/fps_bench.py, 16384 -> 4096): cluster kernel 7.2 - 9.2 ms, single-CTA shared-memory kernel 5.66 ms,
+  // its second generation (x in registers, packed f32x2 arithmetic) 5.02 ms = the default --
   // the cluster barrier costs more per sample (~1.7 us) than the shared-memory re-read it removes, so the
   // single-CTA kernels stay the default; GVF_FPS=cluster selects the cluster kernel (identical indices).
   static int fps_mode = -1;
   if (fps_mode < 0) {
     const char* e = getenv("GVF_FPS");
-    fps_mode = (e && e[0] == 'c') ? 0 : 1;
+    fps_mode = (e && e[0] == 'c') ? 0 : (e && e[0] == 's') ? 1 : 2;     // "cluster" / "smem" (generation 1) / default
   }
   auto launch_cluster = [&](auto kern) {
     cudaLaunchConfig_t cfg = {};
@@ -501,6 +577,12 @@ extern "C" GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start
     const int per = (P + gvf::kFpsCluster * gvf::kFpsThreads - 1) / (gvf::kFpsCluster * gvf::kFpsThreads);
     ok = per <= 1 ? launch_cluster(gvf::fps_cluster_kernel<1>) : per <= 2 ? launch_cluster(gvf::fps_cluster_kernel<2>)
                                                                            : launch_cluster(gvf::fps_cluster_kernel<4>);
+    return (ok && cudaGetLastError() == cudaSuccess) ? GVF_OK : GVF_ERR_CUDA;
+  }
+  if (fps_mode == 2 && P <= 16384) {
+    if (P <= 4096) ok = launch_smem(gvf::fps_smem2_kernel<4>, 4);
+    else if (P <= 8192) ok = launch_smem(gvf::fps_smem2_kernel<8>, 8);
+    else ok = launch_smem(gvf::fps_smem2_kernel<16>, 16);
     return (ok && cudaGetLastError() == cudaSuccess) ? GVF_OK : GVF_ERR_CUDA;
   }
   if (P <= 4096) ok = launch_smem(gvf::fps_smem_kernel<4>, 4);

@@ -16,5 +16,5 @@ if len(sys.argv) > 1:
         e1.record(); torch.cuda.synchronize()
         print(f"{sys.argv[1]:8s} P={P:6d} K={K}: {e0.elapsed_time(e1) / 5:7.3f} ms  checksum {int(idx.long().sum())} first {idx[:6].tolist()}")
 else:
-    for mode in ("cluster", "smem"):
+    for mode in ("cluster", "smem", "v2"):   # v2 = default
         subprocess.run([sys.executable, __file__, mode], env=dict(os.environ, GVF_FPS=mode))
