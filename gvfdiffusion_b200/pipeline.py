@@ -70,6 +70,30 @@ class GVFPipeline:
         o.fps4096 = o.static_gs.index_select(0, i4096)
         return o
 
+    def prepare_object_async(self, canon, after=None):
+        """`prepare_object` for the NEXT object on a high-priority side stream, so that its farthest point
+        sampling (one CTA, ~5 ms: 4096 dependent arg-max steps) runs next to the sampling of the current
+        object instead of in front of its own.  `after`: event the inputs become valid at (an upload on a
+        copy stream).  The caller passes the result to `wait_object` before using it on its own stream."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.dev, priority=-1)
+        main = torch.cuda.current_stream()
+        if after is not None:
+            self._side.wait_event(after)
+        with torch.cuda.stream(self._side):
+            o = self.prepare_object(canon)
+            o.ready = torch.cuda.Event()
+            o.ready.record(self._side)
+        for t in (*o.arrays, o.static_gs, o.fps512, o.fps4096):
+            t.record_stream(main)                 # allocated on the side stream, consumed on the caller's
+        return o
+
+    def wait_object(self, o):
+        ev = getattr(o, "ready", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        return o
+
     # ------------------------------------------------------------------ stages
     def sample(self, obj, cond_images, noise, steps=32, guidance_scale=1.0, guidance_scale2=1.0, adaptive=False,
                static_mean=0.0, static_std=1.0):

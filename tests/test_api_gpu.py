@@ -169,3 +169,18 @@ def test_inference_script_flag_surface_runs(tmp_path):
     mod.main(["--exp_name", str(tmp_path), "--num_samples", "1", "--rescale_timesteps", "2", "--num_timesteps", "4",
               "--config", "none", "--data_dir", str(tmp_path), "--adaptive"])
     assert torch.load(os.path.join(str(tmp_path), "rank_00_rgb_000000.pt")).shape == (4, 1, 512, 512, 3)
+
+
+def test_prepare_object_async_equals_sync():
+    """The side-stream preparation used by the steady-state object loop returns the tensors of prepare_object."""
+    from gvfdiffusion_b200.pipeline import GVFPipeline
+    from gvfdiffusion_b200 import synthetic as S
+    canon = {k: v.to(DEV) for k, v in S.canonical_gaussians(num_voxels=300, seed=4).items()}
+    pipe = GVFPipeline(None, None, torch.linspace(1e-4, 2e-2, 1000, dtype=torch.float64), device=DEV, resolution=64,
+                       num_latents=128, num_static=512)
+    a = pipe.prepare_object(canon)
+    b = pipe.wait_object(pipe.prepare_object_async(canon))
+    c = pipe.wait_object(pipe.prepare_object_async(canon, after=torch.cuda.current_stream().record_event()))
+    torch.cuda.synchronize()
+    for o in (b, c):
+        assert torch.equal(a.static_gs, o.static_gs) and torch.equal(a.fps512, o.fps512) and torch.equal(a.fps4096, o.fps4096)
