@@ -1,0 +1,189 @@
+// sparse_vae.cu -- the voxel-side operators around the static (canonical Gaussian) VAE:
+//
+//  (1) gvf_to_representation: SparseVAE.to_representation (reference
+//      model/sparse_voxel_diffusion/sparse_vae.py:114-180) -- the decoder's [Nvox, 14 G] feature rows
+//      become the raw GaussianModel tensors (_xyz, _features_dc, _scaling, _rotation, _opacity) of
+//      P = Nvox * G Gaussians in one launch (the reference runs ~25 slicing / elementwise launches per
+//      batch entry and builds one python object per entry).
+//  (2) submanifold sparse 3-D convolution (reference sparse/conv/conv_spconv.py:6-15 ->
+//      spconv.SubMConv3d, used by trellis/models/structured_latent_flow.py:34-35 and
+//      structured_latent_vae/decoder_mesh.py:43-52): neighbour map through a dense voxel -> row
+//      index grid (180 GB of HBM make the [B, D, D, D] int32 grid the cheapest exact "hash"), an
+//      im2col gather into the fp16 [N, k^3 Cin] operand of the tcgen05 GEMM (gvf_gemm_f16, which
+//      applies bias / residual epilogues), and nothing else: out[i] = sum_k W[:, k, :] x[nbr(i, k)].
+//
+// HBM-bound byte movers: coalesced 16 B accesses, one pass over the data, no tensor cores here.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gvf_b200.h"
+
+namespace gvf {
+
+// one thread per (voxel, gaussian); a warp covers 32 / G voxels whose 14 G-float rows it reads whole
+__global__ void __launch_bounds__(256) to_representation_kernel(
+    const float* __restrict__ feats, int ldf, const int* __restrict__ coords, int nvox, int G,
+    const float* __restrict__ perturb, float lr_xyz, float lr_dc, float lr_scaling, float lr_rotation,
+    float lr_opacity, float resolution, int reg_mode, float soft_scale, float* __restrict__ xyz,
+    float* __restrict__ dc, float* __restrict__ scaling, float* __restrict__ rotation,
+    float* __restrict__ opacity) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)nvox * G) return;
+  const int v = (int)(p / G), g = (int)(p % G);
+  const float* row = feats + (size_t)v * ldf;
+  const int* c = coords + (size_t)v * 4;
+  // layout of a row (sparse_vae.py:211-227): _xyz (G,3) | _features_dc (G,1,3) | _scaling (G,3) |
+  // _rotation (G,4) | _opacity (G,1)
+  const float* fx = row + 3 * g;
+  const float* fd = row + 3 * G + 3 * g;
+  const float* fs = row + 6 * G + 3 * g;
+  const float* fr = row + 9 * G + 4 * g;
+  const float* fo = row + 13 * G + g;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    // xyz = (coords + 0.5) / resolution (:143); offset = feats * lr (+ perturbation) (:146-149)
+    const float centre = __fdiv_rn(__fadd_rn((float)c[1 + a], 0.5f), resolution);
+    float off = __fmul_rn(fx[a], lr_xyz);
+    if (perturb) off = __fadd_rn(off, perturb[3 * g + a]);
+    if (reg_mode == 1) off = __fdiv_rn(tanhf(off), resolution);                       // invoxel (:150-151)
+    else if (reg_mode == 2)                                                           // soft_invoxel (:152-153)
+      off = __fmul_rn(__fmul_rn(__fdiv_rn(tanhf(off), resolution), 0.5f), soft_scale);
+    xyz[p * 3 + a] = __fadd_rn(centre, off);
+    dc[p * 3 + a] = __fmul_rn(fd[a], lr_dc);
+    scaling[p * 3 + a] = __fmul_rn(fs[a], lr_scaling);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) rotation[p * 4 + a] = __fmul_rn(fr[a], lr_rotation);
+  opacity[p] = __fmul_rn(fo[0], lr_opacity);
+}
+
+// ------------------------------------------------------------------------------------------------
+// submanifold convolution: neighbour map
+__global__ void __launch_bounds__(256) voxel_grid_fill_kernel(const int* __restrict__ coords, int n, int B, int D,
+                                                              int* __restrict__ grid, int* __restrict__ err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = reinterpret_cast<const int4*>(coords)[i];
+  if ((unsigned)c.x >= (unsigned)B || (unsigned)c.y >= (unsigned)D || (unsigned)c.z >= (unsigned)D ||
+      (unsigned)c.w >= (unsigned)D) {
+    atomicOr(err, 1);
+    return;
+  }
+  const size_t cell = (((size_t)c.x * D + c.y) * D + c.z) * D + c.w;
+  // duplicate coordinates: the highest row index wins deterministically (spconv requires unique
+  // coordinates; the flag lets the host mirror raise)
+  const int prev = atomicMax(&grid[cell], i);
+  if (prev >= 0) atomicOr(err, 2);
+}
+
+// nbr[i, k] = row index of the voxel at coords[i] + dilation * (k_xyz - ks/2), or -1; k = (kx * ks + ky) * ks + kz
+__global__ void __launch_bounds__(256) neighbor_map_kernel(const int* __restrict__ coords, int n, int B, int D, int ks,
+                                                           int dilation, const int* __restrict__ grid,
+                                                           int* __restrict__ nbr) {
+  const int K3 = ks * ks * ks;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * K3) return;
+  const int i = (int)(t / K3), k = (int)(t % K3);
+  const int4 c = reinterpret_cast<const int4*>(coords)[i];
+  const int half = ks / 2;
+  const int x = c.y + dilation * (k / (ks * ks) - half);
+  const int y = c.z + dilation * ((k / ks) % ks - half);
+  const int z = c.w + dilation * (k % ks - half);
+  int r = -1;
+  if ((unsigned)c.x < (unsigned)B && (unsigned)x < (unsigned)D && (unsigned)y < (unsigned)D && (unsigned)z < (unsigned)D)
+    r = grid[(((size_t)c.x * D + x) * D + y) * D + z];
+  nbr[t] = r;
+}
+
+// im2col: out[i, k * Cin + c] = x[nbr[i, k], c] (0 where nbr < 0).  One thread moves 8 channels (16 B store);
+// consecutive threads walk the channels of one (i, k) pair, so loads and stores are whole 128 B lines.
+template <typename TIn>
+__global__ void __launch_bounds__(256) sparse_im2col_kernel(const TIn* __restrict__ x, int ldx, const int* __restrict__ nbr,
+                                                            long long pairs, int cin8, __half* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pairs * cin8) return;
+  const long long pr = t / cin8;
+  const int c8 = (int)(t % cin8);
+  const int src = nbr[pr];
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (src >= 0) {
+    if constexpr (sizeof(TIn) == 2) {
+      o = *reinterpret_cast<const uint4*>(x + (size_t)src * ldx + c8 * 8);
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(x + (size_t)src * ldx + c8 * 8);
+      const float4 b = *reinterpret_cast<const float4*>(x + (size_t)src * ldx + c8 * 8 + 4);
+      __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+      __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+      o.x = *reinterpret_cast<uint32_t*>(&h0);
+      o.y = *reinterpret_cast<uint32_t*>(&h1);
+      o.z = *reinterpret_cast<uint32_t*>(&h2);
+      o.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+  }
+  reinterpret_cast<uint4*>(out)[t] = o;
+}
+
+}  // namespace gvf
+
+using namespace gvf;
+#define ST(s) ((cudaStream_t)(s))
+#define RET() return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA
+
+extern "C" {
+
+GVF_API int gvf_to_representation(const float* feats, int ldf, const int* coords, int nvox, int G,
+                                  const float* perturbation, const float* lr, float resolution, int reg_mode,
+                                  float voxel_size, float* xyz, float* features_dc, float* scaling,
+                                  float* rotation, float* opacity, void* stream) {
+  if (!feats || !coords || !lr || !xyz || !features_dc || !scaling || !rotation || !opacity) return GVF_ERR_INVALID;
+  if (nvox <= 0 || G <= 0 || ldf < 14 * G || resolution <= 0.0f || reg_mode < 0 || reg_mode > 2) return GVF_ERR_INVALID;
+  const long long n = (long long)nvox * G;
+  to_representation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(
+      feats, ldf, coords, nvox, G, perturbation, lr[0], lr[1], lr[2], lr[3], lr[4], resolution, reg_mode, voxel_size,
+      xyz, features_dc, scaling, rotation, opacity);
+  RET();
+}
+
+GVF_API size_t gvf_sparse_conv_workspace_bytes(int B, int D) {
+  if (B <= 0 || D <= 0) return 0;
+  return ((size_t)B * D * D * D + 4) * sizeof(int);       // grid + status word (+ padding)
+}
+
+GVF_API int gvf_sparse_neighbor_map(const int* coords, int N, int B, int D, int ksize, int dilation, void* workspace,
+                                    size_t workspace_bytes, int* nbr, int* status, void* stream) {
+  if (!coords || !workspace || !nbr || N <= 0 || B <= 0 || D <= 0 || dilation <= 0) return GVF_ERR_INVALID;
+  if (ksize != 1 && ksize != 3 && ksize != 5) return GVF_ERR_UNSUPPORTED;
+  if ((uintptr_t)coords & 15) return GVF_ERR_INVALID;
+  if (workspace_bytes < gvf_sparse_conv_workspace_bytes(B, D)) return GVF_ERR_WORKSPACE;
+  const size_t cells = (size_t)B * D * D * D;
+  int* grid = (int*)workspace;
+  int* err = grid + cells;
+  if (cudaMemsetAsync(grid, 0xFF, cells * sizeof(int), ST(stream)) != cudaSuccess) return GVF_ERR_CUDA;
+  if (cudaMemsetAsync(err, 0, sizeof(int), ST(stream)) != cudaSuccess) return GVF_ERR_CUDA;
+  voxel_grid_fill_kernel<<<(N + 255) / 256, 256, 0, ST(stream)>>>(coords, N, B, D, grid, err);
+  if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
+  const long long t = (long long)N * ksize * ksize * ksize;
+  neighbor_map_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>(coords, N, B, D, ksize, dilation, grid, nbr);
+  if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
+  if (status && cudaMemcpyAsync(status, err, sizeof(int), cudaMemcpyDeviceToDevice, ST(stream)) != cudaSuccess)
+    return GVF_ERR_CUDA;
+  return GVF_OK;
+}
+
+GVF_API int gvf_sparse_im2col_f16(const void* x, int x_is_f16, int ldx, const int* nbr, int N, int K3, int Cin,
+                                  void* out, void* stream) {
+  if (!x || !nbr || !out || N <= 0 || K3 <= 0 || Cin <= 0) return GVF_ERR_INVALID;
+  if ((Cin % 8) || (ldx % 8) || (((uintptr_t)x | (uintptr_t)out) & 15)) return GVF_ERR_INVALID;
+  const long long pairs = (long long)N * K3;
+  const int cin8 = Cin / 8;
+  const long long t = pairs * cin8;
+  const unsigned blocks = (unsigned)((t + 255) / 256);
+  if (x_is_f16)
+    sparse_im2col_kernel<__half><<<blocks, 256, 0, ST(stream)>>>((const __half*)x, ldx, nbr, pairs, cin8, (__half*)out);
+  else
+    sparse_im2col_kernel<float><<<blocks, 256, 0, ST(stream)>>>((const float*)x, ldx, nbr, pairs, cin8, (__half*)out);
+  RET();
+}
+
+}  // extern "C"

@@ -265,3 +265,54 @@ class LaunchTimer:
     def summary(self):
         torch.cuda.synchronize()
         return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.records.items()}
+
+
+# ---- voxel-side operators (include/gvf_b200.h section 7) ----
+def to_representation(feats, coords, num_gaussians, lr, resolution, reg_mode=0, voxel_size=1.0, perturbation=None):
+    """SparseVAE.to_representation in one launch: feats fp32 [Nvox, 14 G], coords int32 [Nvox, 4] ->
+    (_xyz [P,3], _features_dc [P,1,3], _scaling [P,3], _rotation [P,4], _opacity [P,1]), P = Nvox * G."""
+    _req(feats, F32, "feats")
+    _req(coords, torch.int32, "coords")
+    assert feats.stride(1) == 1 and coords.is_contiguous() and coords.shape[1] == 4
+    nvox, G = feats.shape[0], int(num_gaussians)
+    assert feats.shape[1] >= 14 * G and coords.shape[0] == nvox
+    P = nvox * G
+    e = lambda *s: torch.empty(s, dtype=F32, device=feats.device)
+    xyz, dc, sc, rot, op = e(P, 3), e(P, 1, 3), e(P, 3), e(P, 4), e(P, 1)
+    if perturbation is not None:
+        _req(perturbation, F32, "perturbation")
+        assert perturbation.is_contiguous() and tuple(perturbation.shape) == (G, 3)
+    lr5 = (C.c_float * 5)(*[float(v) for v in lr])
+    check(_lib.lib().gvf_to_representation(ptr(feats), feats.stride(0), ptr(coords), nvox, G, ptr(perturbation), lr5,
+                                           float(resolution), int(reg_mode), float(voxel_size), ptr(xyz), ptr(dc),
+                                           ptr(sc), ptr(rot), ptr(op), current_stream()), "gvf_to_representation")
+    return xyz, dc, sc, rot, op
+
+
+def sparse_neighbor_map(coords, batch_size, grid_size, ksize=3, dilation=1, workspace=None, status=None):
+    """coords int32 [N,4] (batch, x, y, z) -> nbr int32 [N, ksize^3] (-1 = no voxel there)."""
+    _req(coords, torch.int32, "coords")
+    assert coords.is_contiguous() and coords.shape[1] == 4
+    N = coords.shape[0]
+    need = _lib.lib().gvf_sparse_conv_workspace_bytes(int(batch_size), int(grid_size))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=coords.device)
+    nbr = torch.empty((N, ksize ** 3), dtype=torch.int32, device=coords.device)
+    check(_lib.lib().gvf_sparse_neighbor_map(ptr(coords), N, int(batch_size), int(grid_size), int(ksize), int(dilation),
+                                             ptr(workspace), workspace.numel() * workspace.element_size(), ptr(nbr),
+                                             ptr(status), current_stream()), "gvf_sparse_neighbor_map")
+    return nbr
+
+
+def sparse_im2col(x, nbr, out=None):
+    """x fp16 / fp32 [N, Cin], nbr int32 [N, K3] -> fp16 [N, K3 * Cin] (zero rows where nbr < 0)."""
+    assert x.is_cuda and x.dtype in (F16, F32) and x.stride(1) == 1
+    _req(nbr, torch.int32, "nbr")
+    N, K3 = nbr.shape
+    Cin = x.shape[1]
+    if out is None:
+        out = torch.empty((N, K3 * Cin), dtype=F16, device=x.device)
+    assert out.is_contiguous() and out.dtype == F16
+    check(_lib.lib().gvf_sparse_im2col_f16(ptr(x), int(x.dtype == F16), x.stride(0), ptr(nbr), N, K3, Cin, ptr(out),
+                                           current_stream()), "gvf_sparse_im2col_f16")
+    return out

@@ -330,6 +330,38 @@ GVF_API int gvf_knn_interp_deltas(const float* dists, const long long* idx, cons
                                   const float* moving_pc, const long long* lengths1, int B, int P1, int P2, int T,
                                   int K, int adaptive_radius, float beta, float* est, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * 7. Voxel-side operators of the static (canonical Gaussian) VAE and of the TRELLIS stage in front of it.
+ *
+ *    gvf_to_representation replaces SparseVAE.to_representation (reference
+ *    model/sparse_voxel_diffusion/sparse_vae.py:114-180; layout of a feature row :211-227):
+ *    feats fp32 [nvox, ldf >= 14 G] = (_xyz (G,3) | _features_dc (G,1,3) | _scaling (G,3) | _rotation (G,4) |
+ *    _opacity (G,1)), coords int32 [nvox, 4] = (batch, x, y, z), perturbation fp32 [G, 3] or NULL
+ *    (perturb_offset false), lr HOST float[5] in the order (_xyz, _features_dc, _scaling, _rotation, _opacity);
+ *    reg_mode 0 none | 1 invoxel tanh(o) / res | 2 soft_invoxel tanh(o) / res * 0.5 * voxel_size.
+ *    Outputs are the raw GaussianModel tensors of P = nvox * G Gaussians (voxel-major, Gaussian-minor, exactly
+ *    the reference's flatten(0, 1)): xyz [P,3], features_dc [P,3], scaling [P,3], rotation [P,4], opacity [P].
+ *
+ *    Submanifold sparse convolution (sparse/conv/conv_spconv.py:6-15 -> spconv.SubMConv3d, callers
+ *    trellis/models/structured_latent_flow.py:34-35, structured_latent_vae/decoder_mesh.py:43-52):
+ *    gvf_sparse_neighbor_map builds nbr int32 [N, ksize^3] (row index of the voxel at
+ *    coords[i] + dilation * (k - ksize/2) per axis, k = (kx * ksize + ky) * ksize + kz, -1 where empty) through a
+ *    dense [B, D, D, D] int32 grid in the caller's workspace (gvf_sparse_conv_workspace_bytes); *status
+ *    (device int, optional) gets bit 0 for out-of-range coordinates, bit 1 for duplicates.
+ *    gvf_sparse_im2col_f16 gathers x (fp16 or fp32 [N, ldx]) into the fp16 [N, K3 * Cin] GEMM operand
+ *    (zeros where nbr < 0); the contraction itself is gvf_gemm_f16 with W [Cout, K3 * Cin] (spconv's
+ *    [Cout, kx, ky, kz, Cin] weight, flattened) and any of its epilogues.
+ * ---------------------------------------------------------------------------------- */
+GVF_API int gvf_to_representation(const float* feats, int ldf, const int* coords, int nvox, int G,
+                                  const float* perturbation, const float* lr /* host */, float resolution,
+                                  int reg_mode, float voxel_size, float* xyz, float* features_dc, float* scaling,
+                                  float* rotation, float* opacity, void* stream);
+GVF_API size_t gvf_sparse_conv_workspace_bytes(int B, int D);
+GVF_API int gvf_sparse_neighbor_map(const int* coords, int N, int B, int D, int ksize, int dilation, void* workspace,
+                                    size_t workspace_bytes, int* nbr, int* status, void* stream);
+GVF_API int gvf_sparse_im2col_f16(const void* x, int x_is_f16, int ldx, const int* nbr, int N, int K3, int Cin,
+                                  void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -258,7 +258,71 @@ def gen_losses():
     return out
 
 
+def gen_to_representation():
+    """The reference's own SparseVAE.to_representation / _build_perturbation / _calc_layout
+    (model/sparse_voxel_diffusion/sparse_vae.py:104-180,202-227) with the MipGS block of configs/vae.yml, on a
+    seeded two-entry batch of sparse voxels.  The object is created without __init__ (which wants backbones and
+    renderers); GaussianModel is the reference's, constructed on the CPU."""
+    import functools
+    import types
+    for name in ("utils3d", "utils3d.torch", "plyfile", "easydict"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["utils3d"].torch = sys.modules["utils3d.torch"]
+    sys.modules["plyfile"].PlyData = sys.modules["plyfile"].PlyElement = object
+
+    class _EDict(dict):
+        def __init__(self, d=None):
+            super().__init__()
+            for k, v in (d or {}).items():
+                self[k] = _EDict(v) if isinstance(v, dict) else v
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    sys.modules["easydict"].EasyDict = _EDict
+    _ref_import._stub("lpips", LPIPS=None)
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        from model.sparse_voxel_diffusion import sparse_vae as SV
+        from representations.gaussian.gaussian_model import GaussianModel
+        SV.GaussianModel = functools.partial(GaussianModel, device="cpu")
+        cfg = dict(SV._DEFAULT_MIPGS_CFG)
+        cfg.update({"lr": {"_xyz": 1.0, "_features_dc": 1.0, "_opacity": 1.0, "_scaling": 1.0, "_rotation": 0.1},
+                    "perturb_offset": True, "reg_mode": "soft_invoxel", "voxel_size": 1.5, "num_gaussians": 8,
+                    "2d_filter_kernel_size": 0.1, "3d_filter_kernel_size": 0.0009, "scaling_bias": 0.004,
+                    "opacity_bias": 0.1, "scaling_activation": "softplus"})
+        sv = object.__new__(SV.SparseVAE)
+        sv.resolution = 64
+        sv.rep_config = {"MipGS": cfg}
+        sv._calc_layout(sv.rep_config)
+        bb = types.SimpleNamespace(device="cpu")
+        sv.backbones = {"vae": bb}
+        bb.MipGS_perturbation = sv._build_perturbation(8, "soft_invoxel")
+        g = torch.Generator().manual_seed(11)
+        counts = [37, 20]
+        coords = torch.cat([torch.cat([torch.full((n, 1), b), torch.randint(0, 64, (n, 3), generator=g)], dim=1)
+                            for b, n in enumerate(counts)]).int()
+        feats = torch.randn(sum(counts), 112, generator=g) * 1.5
+        x = types.SimpleNamespace(shape=torch.Size([2, 112]), coords=coords, feats=feats,
+                                  layout=[slice(0, 37), slice(37, 57)])
+        reps = sv.to_representation(x)["MipGS"]
+        names = ("_xyz", "_features_dc", "_scaling", "_rotation", "_opacity")
+        out = {"cfg": {k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()}, "resolution": 64,
+               "coords": coords, "feats": feats, "counts": counts, "perturbation": bb.MipGS_perturbation.clone(),
+               "layout": {k: tuple(v["range"]) for k, v in sv.layouts["MipGS"].items()},
+               "reps": [{n: getattr(r, n).clone() for n in names} for r in reps],
+               "activated": [{"xyz": r.get_xyz.clone(), "scaling": r.get_scaling.clone(),
+                              "opacity": r.get_opacity.clone(), "rotation": r.get_rotation.clone()} for r in reps]}
+    finally:
+        torch.Tensor.cuda = orig
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "to_representation":
+        torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
         return
@@ -273,6 +337,7 @@ def main():
     torch.save(gen_gaussian(), os.path.join(HERE, "gaussian.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
+    torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -1,0 +1,58 @@
+"""Pins oracle/sparse_vae.py: to_representation against the fixture produced by the reference's own
+SparseVAE.to_representation (tests/golden/to_representation.pt), the neighbour map / submanifold convolution
+restatement against each other (gather form == dense conv3d form), and the host-side layout mirror."""
+import os
+
+import torch
+
+from oracle import sparse_vae as OSV
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = ("_xyz", "_features_dc", "_scaling", "_rotation", "_opacity")
+
+
+def test_to_representation_oracle_matches_reference_fixture():
+    g = torch.load(os.path.join(G, "to_representation.pt"), weights_only=False)
+    cfg = g["cfg"]
+    pert = OSV.build_perturbation(cfg["num_gaussians"], cfg["reg_mode"], cfg["voxel_size"])
+    assert torch.equal(pert, g["perturbation"])
+    out = OSV.to_representation(g["feats"], g["coords"], cfg, g["resolution"], pert)
+    off = 0
+    for n, rep in zip(g["counts"], g["reps"]):
+        for name in NAMES:
+            assert torch.equal(out[name][off * 8:(off + n) * 8], rep[name]), name      # same torch ops: bit-exact
+        off += n
+    # layout table of _calc_layout
+    start = 0
+    for name, w in OSV.ORDER:
+        assert g["layout"][name] == (start, start + 8 * w)
+        start += 8 * w
+
+
+def test_host_mirror_layout_and_perturbation_match_fixture():
+    from gvfdiffusion_b200.model.sparse_voxel_diffusion.sparse_vae import SparseVAE
+    g = torch.load(os.path.join(G, "to_representation.pt"), weights_only=False)
+    sv = SparseVAE(resolution=64, representation_config={"MipGS": g["cfg"]}, device="cpu")
+    assert sv.out_channels == 112
+    assert {k: tuple(v["range"]) for k, v in sv.layouts["MipGS"].items()} == g["layout"]
+    assert torch.equal(sv.perturbation["MipGS"], g["perturbation"])
+
+
+def test_subm_conv_gather_form_equals_dense_form():
+    g = torch.Generator().manual_seed(3)
+    res, n, cin, cout = 10, 120, 8, 16
+    coords = []
+    for b in range(2):
+        lin = torch.randperm(res ** 3, generator=g)[:n]
+        coords.append(torch.stack([torch.full((n,), b), lin // (res * res), (lin // res) % res, lin % res], 1))
+    coords = torch.cat(coords).int()
+    x = torch.randn(2 * n, cin, generator=g)
+    w = torch.randn(cout, 3, 3, 3, cin, generator=g) * 0.1
+    bias = torch.randn(cout, generator=g)
+    ref = OSV.subm_conv3d(x, coords, w, bias, 2, res)
+    nbr = OSV.neighbor_map(coords, 3)
+    xz = torch.cat([x, torch.zeros(1, cin)])
+    cols = xz[nbr.clamp_min(-1)].reshape(2 * n, 27 * cin)          # index -1 = the appended zero row
+    out = cols @ w.reshape(cout, -1).t() + bias
+    assert (out - ref).abs().max() < 1e-4
+    assert int((nbr[:, 13] == torch.arange(2 * n)).all()) == 1      # centre tap is the voxel itself
