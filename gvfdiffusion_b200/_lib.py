@@ -79,6 +79,7 @@ _SIGS = {
     "gvf_sparse_conv_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "gvf_sparse_neighbor_map": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P]),
     "gvf_sparse_im2col_f16": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "gvf_raster_set_sort": (None, [C.c_int]),
     "gvf_affine_lastdim": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, C.c_float, C.c_float, _P, _P]),
 }
 

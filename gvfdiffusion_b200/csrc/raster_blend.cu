@@ -15,11 +15,16 @@
 //
 // No tensor cores on this path.  Blend math: alpha = min(.99, op * exp(power)), skip
 // alpha < 1/255, stop when T(1-alpha) < 1e-4, out = C + T * bg, A = 1 - T.
+#include <stdlib.h>
+
 #include "raster_common.h"
 
 namespace gvf {
 
 constexpr int kSortCap = 2048;
+#ifndef GVF_BLEND_MIN_CTAS
+#define GVF_BLEND_MIN_CTAS 6
+#endif
 
 template <bool PADDED, typename KeyPtr>
 __device__ __forceinline__ void bitonic_sort_any_n(KeyPtr keys, int n) {
@@ -64,6 +69,121 @@ __device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2; flushes de
   return y;
 }
 
+// Generation 2 of the per-tile depth sort (opt-in: GVF_RASTER_SORT=bucket): one-pass distribution sort.
+// A tile list holds a few hundred keys whose depth bits are spread over a narrow range, so a monotone map
+// of the depth bits onto kBuckets buckets leaves 0..3 keys per bucket.  thread t keeps keys t, t + 256, ..
+// in registers: (A) min / max of the depth bits, (B) bucket + arrival rank by a shared-memory atomic,
+// (C) exclusive scan of the bucket counts, (D) keys stored bucket-major, (E) every key counts the smaller
+// keys of its own bucket = its final place.  bucket() is monotone in the key and keys are unique, so the
+// result is the ascending order the bitonic network produces (bit-identical point lists).  ~8 barriers
+// instead of 55 for 1024 keys.  Returns false (list left permuted, caller runs the network) when a bucket
+// holds more than kBucketMax keys (near-constant depth): correctness never depends on the distribution.
+constexpr int kBuckets = 1024;
+constexpr int kBucketMax = 24;
+constexpr int kKeysPerThread = kSortCap / GVF_TILE_PIX;
+constexpr int kBucketMin = 128;          // shorter lists: the network's few steps are cheaper than the fixed cost
+
+__device__ __forceinline__ bool bucket_sort_tile(const unsigned long long* __restrict__ gk, int n,
+                                                 unsigned long long* skeys, uint32_t* cnt, uint32_t* red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long key[kKeysPerThread];
+  uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int i = 0; i < kKeysPerThread; ++i) {
+    const int j = tid + i * GVF_TILE_PIX;
+    key[i] = j < n ? gk[j] : ~0ull;
+    if (j < n) {
+      const uint32_t d = (uint32_t)(key[i] >> 32);
+      lo = min(lo, d);
+      hi = max(hi, d);
+    }
+  }
+#pragma unroll
+  for (int c = tid; c < kBuckets; c += GVF_TILE_PIX) cnt[c] = 0;
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lane == 0) { red[warp] = lo; red[8 + warp] = hi; }
+  __syncthreads();
+  lo = red[lane & 7];
+  hi = red[8 + (lane & 7)];
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  const float scale = (float)kBuckets / (__uint2float_rz(hi - lo) + 1.0f);
+  uint32_t bk[kKeysPerThread];          // bucket << 16 | arrival rank
+#pragma unroll
+  for (int i = 0; i < kKeysPerThread; ++i) {
+    const int j = tid + i * GVF_TILE_PIX;
+    if (j < n) {
+      const uint32_t d = (uint32_t)(key[i] >> 32) - lo;
+      const int b = min(kBuckets - 1, (int)(__uint2float_rz(d) * scale));
+      bk[i] = ((uint32_t)b << 16) | atomicAdd(&cnt[b], 1u);
+    }
+  }
+  __syncthreads();
+  // exclusive scan of cnt: thread t owns buckets 4t .. 4t + 3
+  uint32_t c4[4], tot = 0, big = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    c4[q] = cnt[4 * tid + q];
+    big |= c4[q] > (uint32_t)kBucketMax;
+    tot += c4[q];
+  }
+  uint32_t inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) red[16 + warp] = inc;
+  const int any_big = __syncthreads_or((int)big);
+  uint32_t base = inc - tot;
+#pragma unroll
+  for (int w = 0; w < 7; ++w)
+    if (w < warp) base += red[16 + w];
+  // cnt becomes (start << 8 | count): start < 2048 and count <= kBucketMax fit comfortably
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cnt[4 * tid + q] = (base << 8) | min(c4[q], 255u);
+    base += c4[q];
+  }
+  __syncthreads();
+  if (any_big) {                       // degenerate depth distribution: hand the keys back unsorted
+#pragma unroll
+    for (int i = 0; i < kKeysPerThread; ++i) {
+      const int j = tid + i * GVF_TILE_PIX;
+      if (j < n) skeys[j] = key[i];
+    }
+    __syncthreads();
+    return false;
+  }
+#pragma unroll
+  for (int i = 0; i < kKeysPerThread; ++i) {
+    const int j = tid + i * GVF_TILE_PIX;
+    if (j < n) skeys[(cnt[bk[i] >> 16] >> 8) + (bk[i] & 0xffffu)] = key[i];
+  }
+  __syncthreads();
+  uint32_t fin[kKeysPerThread];
+#pragma unroll
+  for (int i = 0; i < kKeysPerThread; ++i) {
+    const int j = tid + i * GVF_TILE_PIX;
+    if (j < n) {
+      const uint32_t sc = cnt[bk[i] >> 16];
+      const uint32_t st = sc >> 8, c = sc & 0xffu;
+      uint32_t r = 0;
+      for (uint32_t q = 0; q < c; ++q) r += skeys[st + q] < key[i] ? 1u : 0u;
+      fin[i] = st + r;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kKeysPerThread; ++i) {
+    const int j = tid + i * GVF_TILE_PIX;
+    if (j < n) skeys[fin[i]] = key[i];
+  }
+  __syncthreads();
+  return true;
+}
+
 struct BlendArgs {
   int F, P, H, W, gx, gy;
   float bg0, bg1, bg2;
@@ -77,13 +197,17 @@ struct BlendArgs {
   float* final_T;
   uint32_t* n_contrib;
   uint32_t* status;
+  int sort_mode;              // 0 bitonic network, 1 bucket sort for lists of more than kBucketMin keys
 };
 
-__global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArgs a) {
+__global__ void __launch_bounds__(GVF_TILE_PIX, GVF_BLEND_MIN_CTAS) sort_blend_kernel(const BlendArgs a) {
   __shared__ unsigned long long skeys[kSortCap];
   __shared__ float4 sA[GVF_TILE_PIX];   // px, py, conic a, conic b
   __shared__ float2 sT[GVF_TILE_PIX];   // conic c, rejection threshold on `power` (see below)
   __shared__ float4 sC[GVF_TILE_PIX];   // opacity', r, g, b  (read only by pixels the splat reaches)
+  __shared__ uint32_t sRed[24];
+  uint32_t* sCnt = reinterpret_cast<uint32_t*>(sA);   // bucket sort scratch (kBuckets words): dead before sA is staged
+  static_assert(sizeof(float4) * GVF_TILE_PIX >= sizeof(uint32_t) * kBuckets, "sCnt aliases sA");
   __shared__ uint32_t sM[GVF_TILE_PIX]; // bit w: the splat's alpha >= 1/255 ellipse may reach warp w's 8 x 4 block
 
   const int T = a.gx * a.gy;
@@ -103,9 +227,18 @@ __global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArg
     if (in_smem) {
       int np2 = 1;
       while (np2 < n) np2 <<= 1;
-      for (int j = tid; j < np2; j += GVF_TILE_PIX) skeys[j] = j < n ? gk[j] : ~0ull;
-      __syncthreads();
-      bitonic_sort_any_n<true>(skeys, n);
+      bool sorted = false;
+      if (a.sort_mode == 1 && n > kBucketMin) {
+        sorted = bucket_sort_tile(gk, n, skeys, sCnt, sRed);
+        if (!sorted) {
+          for (int j = n + tid; j < np2; j += GVF_TILE_PIX) skeys[j] = ~0ull;
+          __syncthreads();
+        }
+      } else {
+        for (int j = tid; j < np2; j += GVF_TILE_PIX) skeys[j] = j < n ? gk[j] : ~0ull;
+        __syncthreads();
+      }
+      if (!sorted) bitonic_sort_any_n<true>(skeys, n);
       for (int j = tid; j < n; j += GVF_TILE_PIX) {
         const unsigned long long k = skeys[j];
         gk[j] = k;
@@ -228,6 +361,8 @@ __global__ void __launch_bounds__(GVF_TILE_PIX) sort_blend_kernel(const BlendArg
   }
 }
 
+int g_raster_sort_mode = -1;
+
 cudaError_t launch_sort_blend(const gvf_raster_params& prm, int F, int P, const RasterWs& ws,
                               int64_t cap, const float* subpixel_offset, float* out_rgba,
                               cudaStream_t st) {
@@ -241,9 +376,27 @@ cudaError_t launch_sort_blend(const gvf_raster_params& prm, int F, int P, const 
   a.subpixel_offset = reinterpret_cast<const float2*>(subpixel_offset);
   a.out_rgba = out_rgba; a.final_T = ws.final_T; a.n_contrib = ws.n_contrib;
   a.status = ws.status;
+  // GVF_RASTER_SORT=bucket selects generation 2 of the per-tile sort (identical point lists);
+  // gvf_raster_set_sort overrides the environment
+  static int env_mode = -1;
+  if (env_mode < 0) {
+    const char* e = getenv("GVF_RASTER_SORT");
+    env_mode = (e && e[0] == 'b' && e[1] == 'u') ? 1 : 0;
+  }
+  a.sort_mode = g_raster_sort_mode >= 0 ? g_raster_sort_mode : env_mode;
+  // 27.7 KB of shared memory and 40 registers per thread: six CTAs per SM once the carve-out leaves room
+  // (ncu: four CTAs, limited by both, left the barrier stalls of the sort and staging phases exposed)
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(sort_blend_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
   const unsigned grid = (unsigned)((size_t)F * a.gx * a.gy);
   sort_blend_kernel<<<grid, GVF_TILE_PIX, 0, st>>>(a);
   return cudaGetLastError();
 }
 
 }  // namespace gvf
+
+// tuning hook: -1 environment (GVF_RASTER_SORT), 0 bitonic network, 1 bucket sort
+extern "C" GVF_API void gvf_raster_set_sort(int mode) { gvf::g_raster_sort_mode = mode; }

@@ -140,3 +140,57 @@ def test_rgba_to_u8_is_the_reference_conversion():
     got = R.rgba_to_u8(rgba.cuda().contiguous()).cpu().numpy()
     want = (rgba[:, :3].clamp(0.0, 1.0).permute(0, 2, 3, 1).numpy() * 255).astype("uint8")
     assert got.dtype == np.uint8 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("num_voxels,F,H,W", [(256, 3, 128, 128), (2048, 4, 512, 512), (2048, 2, 64, 64)])
+def test_raster_bucket_sort_same_point_lists(num_voxels, F, H, W):
+    """Generation 2 of the per-tile sort (gvf_raster_set_sort(1)): point lists, keys and images identical to the
+    bitonic network's and bit-exact against the oracle; (2048, 2, 64, 64) puts > 2048 keys in a tile (global
+    fallback) and dense lists in the others."""
+    from gvfdiffusion_b200 import _lib
+    canon, delta, ext, intr, const = _scenes.scene(num_voxels, F, H, W)
+    outs = _scenes.oracle_frames(canon, delta, ext, intr, const, H, W)
+    L = _lib.lib()
+    try:
+        L.gvf_raster_set_sort(1)
+        rz1, rgba1, radii1 = _run_cuda(canon, delta, ext, intr, const, H, W)
+        _compare(rz1, rgba1, radii1, outs, F, canon["_xyz"].shape[0], H, W)
+        n = rz1.status()[0]
+        pl1 = rz1.buffer("point_list", torch.int32, n).clone()
+        L.gvf_raster_set_sort(0)
+        rz0, rgba0, radii0 = _run_cuda(canon, delta, ext, intr, const, H, W)
+        assert torch.equal(pl1, rz0.buffer("point_list", torch.int32, n))
+        assert np.array_equal(rgba0, rgba1)
+    finally:
+        L.gvf_raster_set_sort(-1)
+
+
+def test_raster_bucket_sort_degenerate_depths():
+    """All Gaussians at one depth (coplanar, camera on the axis): the bucket map collapses, the kernel falls back
+    to the network; order = ascending id inside equal depths either way."""
+    from gvfdiffusion_b200 import _lib, raster as R
+    L = _lib.lib()
+    P, H, W = 3000, 64, 64
+    g = torch.Generator().manual_seed(2)
+    xyz = torch.cat([torch.rand(P, 2, generator=g) * 0.2 - 0.1, torch.zeros(P, 1)], 1)
+    arrays = (xyz, torch.rand(P, 3, generator=g), torch.full((P, 1), 0.3), torch.full((P, 3), 0.01),
+              torch.tensor([[1.0, 0, 0, 0]]).repeat(P, 1))
+    ext = torch.eye(4)[None].clone()
+    ext[0, 2, 3] = 1.2                                  # camera looks down +z, every centre at depth 1.2
+    from gvfdiffusion_b200 import synthetic as S
+    cams, tfx, tfy = R.pack_cameras(ext, S.intrinsics(), 0.8, 1.6)
+    prm = R.make_params(H, W, tfx, tfy, S.gaussian_constants())
+    res = []
+    try:
+        for mode in (1, 0):
+            L.gvf_raster_set_sort(mode)
+            rz = R.Rasterizer("cuda")
+            rgba, radii = rz.forward(prm, tuple(a.cuda().contiguous() for a in (arrays[0], arrays[1], arrays[3], arrays[4], arrays[2])),
+                                     None, cams.cuda(), activated=True)
+            torch.cuda.synchronize()
+            n = rz.status()[0]
+            res.append((rgba.clone(), rz.buffer("point_list", torch.int32, n).clone(), n))
+    finally:
+        L.gvf_raster_set_sort(-1)
+    assert res[0][2] == res[1][2] and res[0][2] > 0
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][0], res[1][0])

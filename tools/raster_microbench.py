@@ -9,8 +9,11 @@ ap.add_argument("--frames", type=int, default=24)
 ap.add_argument("--voxels", type=int, default=2048)
 ap.add_argument("--res", type=int, default=512)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--sort", type=int, default=-1, help="-1 env, 0 bitonic network, 1 bucket sort")
 a = ap.parse_args()
 dev = "cuda"
+from gvfdiffusion_b200 import _lib
+_lib.lib().gvf_raster_set_sort(a.sort)
 canon = S.canonical_gaussians(num_voxels=a.voxels)
 P = canon["_xyz"].shape[0]
 delta = S.raster_delta(a.frames, P).to(dev)
@@ -36,6 +39,6 @@ for _ in range(a.iters):
 ts.sort()
 ms = ts[len(ts) // 2]
 alg = a.frames * (112 * P + 16 * a.res * a.res) + 64 * Rn
-print(json.dumps({"frames": a.frames, "P": P, "res": a.res, "num_rendered": Rn, "overflow": ovf,
+print(json.dumps({"sort": a.sort, "frames": a.frames, "P": P, "res": a.res, "num_rendered": Rn, "overflow": ovf,
                   "ms_median": ms, "ms_min": ts[0], "alg_bytes": alg, "GBps": alg / ms / 1e6,
                   "frames_per_s": a.frames / ms * 1e3}))
