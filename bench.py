@@ -448,11 +448,12 @@ def main():
                             "achieved": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6,
                             "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6 / pk["hbm_gbs"],
-                            "ms": raster_ms, "traffic": None,
-                            "note": ("not HBM-bound at this depth complexity: 17.7 M (warp, splat) pairs per 24 frames; with "
-                                     "sub-tile culling sort_blend executes 310 M warp instructions (671 M before) at 75 % issue "
-                                     "utilisation, about half of them in the per-tile depth sort "
-                                     "(profiles/r01_raster_full_extract.csv)")},
+                            "ms": raster_ms, "traffic": ncu_traffic("gvf_raster_forward 24 frames"),
+                            "note": ("not HBM-bound at this depth complexity: the tile lists hold 460-790 splats in the scene's "
+                                     "central tiles; sort_blend (75 % of the call) executes 237 M warp instructions (bitonic sort: "
+                                     "310 M, before sub-tile culling: 671 M) at 64 % issue utilisation, two thirds of them in the "
+                                     "blend loop, a fifth in the bucket sort; DRAM traffic is below the algorithmic bytes because "
+                                     "key lists and splat records are re-read from L2 (profiles/r01_raster_bucket_full_extract.csv)")},
     }
     if not args.no_cpu_baseline and world == 1:
         try:

@@ -362,8 +362,8 @@ GVF_API int gvf_sparse_neighbor_map(const int* coords, int N, int B, int D, int 
 GVF_API int gvf_sparse_im2col_f16(const void* x, int x_is_f16, int ldx, const int* nbr, int N, int K3, int Cin,
                                   void* out, void* stream);
 
-/* Tuning hook of the rasteriser's per-tile depth sort: -1 environment (GVF_RASTER_SORT=bucket|bitonic),
- * 0 bitonic network, 1 one-pass bucket sort (identical point lists). */
+/* Tuning hook of the rasteriser's per-tile depth sort: -1 environment (GVF_RASTER_SORT=bucket|bitonic,
+ * default bucket), 0 bitonic network, 1 one-pass bucket sort (identical point lists). */
 GVF_API void gvf_raster_set_sort(int mode);
 
 #ifdef __cplusplus
