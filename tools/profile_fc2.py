@@ -11,7 +11,7 @@ h1, w2 = rn(M, 2048), rn(512, 2048)
 b = torch.randn(512, generator=g).cuda()
 x = torch.randn(M, 512, generator=g).cuda()
 gate = rn(1, 512)
-for v in (4, 5, 6, 7):
+for v in (4, 5, 7):
     L.gvf_gemm_set_variant(v)
     for _ in range(3):
         ops.gemm(h1, w2, b, ops.EPI_RESID_F32, out=x, gate=gate, gate_stride=512, rows_per_batch=M)

@@ -9,6 +9,7 @@ ap.add_argument("--frames", type=int, default=24)
 ap.add_argument("--voxels", type=int, default=2048)
 ap.add_argument("--res", type=int, default=512)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--backward", action="store_true", help="also time gvf_raster_backward (gradients to raw parameters and delta)")
 ap.add_argument("--sort", type=int, default=-1, help="-1 env, 0 bitonic network, 1 bucket sort")
 a = ap.parse_args()
 dev = "cuda"
@@ -39,6 +40,25 @@ for _ in range(a.iters):
 ts.sort()
 ms = ts[len(ts) // 2]
 alg = a.frames * (112 * P + 16 * a.res * a.res) + 64 * Rn
-print(json.dumps({"sort": a.sort, "frames": a.frames, "P": P, "res": a.res, "num_rendered": Rn, "overflow": ovf,
+bw = {}
+if a.backward:
+    g = torch.randn(a.frames, 4, a.res, a.res, device=dev)
+    rz.forward(prm, arrays, delta, cams, out=out, want_radii=False, check_overflow=False)
+    for _ in range(2):
+        rz.backward(prm, arrays, delta, cams, g)
+    tb = []
+    for _ in range(a.iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rz.backward(prm, arrays, delta, cams, g)
+        e1.record()
+        torch.cuda.synchronize()
+        tb.append(e0.elapsed_time(e1))
+    tb.sort()
+    alg_b = alg + a.frames * (16 * a.res * a.res + 112 * P) + 40 * Rn      # A_bwd
+    bw = {"bwd_ms_median": tb[len(tb) // 2], "bwd_ms_min": tb[0], "bwd_alg_bytes": alg_b,
+          "bwd_GBps": alg_b / tb[len(tb) // 2] / 1e6}
+print(json.dumps({**bw, "sort": a.sort, "frames": a.frames, "P": P, "res": a.res, "num_rendered": Rn, "overflow": ovf,
                   "ms_median": ms, "ms_min": ts[0], "alg_bytes": alg, "GBps": alg / ms / 1e6,
                   "frames_per_s": a.frames / ms * 1e3}))
