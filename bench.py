@@ -388,6 +388,23 @@ def main():
     r1.record()
     torch.cuda.synchronize()
     raster_ms = r0.elapsed_time(r1) / 5
+    # BASELINE.json configs[2] (render forward + backward): gradients of the 24 frames to the raw Gaussian
+    # parameters and delta (gvf_raster_backward: blend backward + preprocess backward)
+    from gvfdiffusion_b200 import raster as R
+    cams_b, tfx_b, tfy_b = R.pack_cameras(hin["ext"], hin["intr"], pipe.near, pipe.far)
+    prm_b = R.make_params(pipe.res, pipe.res, tfx_b, tfy_b, pipe.const, pipe.kernel_size, 1.0, pipe.bg)
+    cams_b, delta_b = cams_b.to(dev), delta.contiguous()
+    rz_b = R.Rasterizer(dev)
+    rz_b.forward(prm_b, obj.arrays, delta_b, cams_b, want_radii=False)
+    grad_b = torch.randn(out_dev.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    rz_b.backward(prm_b, obj.arrays, delta_b, cams_b, grad_b)
+    r0.record()
+    for _ in range(5):
+        rz_b.backward(prm_b, obj.arrays, delta_b, cams_b, grad_b)
+    r1.record()
+    torch.cuda.synchronize()
+    raster_bwd_ms = r0.elapsed_time(r1) / 5
+    del rz_b, grad_b
     # the reference's visualisation loop (utils/inference_utils.py:243-283): every timestep from 128 orbit
     # cameras, clamped and converted to uint8 on the device (24 x 128 renders, one rasteriser call per timestep)
     from gvfdiffusion_b200 import synthetic as S
@@ -443,7 +460,8 @@ def main():
                               "(profiles/r01_attn6_full_extract.csv)")},
         "roofline_detail": roof_detail,
         "stage_ms_eager": {"prepare_fps": stage_ms[3], "sample_32nfe": stage_ms[0], "vae_decode": stage_ms[1],
-                           "raster_24f": stage_ms[2], "raster_24x128_views_u8": views_ms},
+                           "raster_24f": stage_ms[2], "raster_24f_backward": raster_bwd_ms,
+                           "raster_24x128_views_u8": views_ms},
         "roofline_raster": {"bound": "hbm", "kernel": "gvf_raster_forward (4 kernels, 24 frames)",
                             "achieved": (T_FRAMES * (112 * VOXELS * 8 + 16 * RES * RES) + 64 * Rn) / raster_ms / 1e6,
                             "peak": pk["hbm_gbs"], "unit": "GB/s",
