@@ -399,6 +399,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapO, int M, int N, int K, GemmEpi ep) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t xres_bar[8][2];     // mode 2, BN = 128: residual chunks arriving by TMA (one per warp and buffer)
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[2][BN];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -418,6 +419,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8 * NCTA); }
+    for (int i = 0; i < 16; ++i) mbar_init(&xres_bar[i >> 1][i & 1], 1);
     fence_barrier_init();
     tma_prefetch_desc(&mapO);
     if constexpr (NCTA == 1) {
@@ -509,6 +511,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint8_t* stg = stg_base + ew * 2 * 4096;
     const uint32_t sw = (uint32_t)(lane & 7);      // SWIZZLE_128B: 16 B piece j of row r sits at j ^ (r & 7)
     int lt = 0, sbuf = 0;
+    uint32_t xph = 0;                              // phase bits of this warp's two residual barriers
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++lt) {
       const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
       const int acc = lt & 1;
@@ -601,6 +604,30 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       } else {
         // ---------------- fp32 outputs: 32-column chunks (128 B rows)
+        // Residual by TMA (mode 2, BN = 128: a warp's half tile is exactly two chunks = its two staging buffers).
+        // The thread = row loads of the first version touched 32 different lines per instruction, half of every
+        // 32 B sector unused (L1 is ~30 KB next to 193 KB of shared memory), and only the first chunk's latency
+        // overlapped the main loop: the fp32 residual epilogue cost 8 us per launch over a plain fp16 store
+        // (tools/gemm_depth_probe.py: out-proj 21.3 vs 13 us, fc2 39.9 vs 30).  Now lane 0 requests both
+        // 32 x 32 fp32 boxes of the tile at tile start through the output's own tensor map; they land, swizzled
+        // like the store wants them, while the main loop of the tile runs; the thread adds into its row in place.
+        // BN = 256 (four chunks per warp): chunks 2 and 3 are requested as soon as the stores of chunks 0 and 1 have
+        // been read out of their buffers.
+        constexpr bool kTmaResid = (mode == 2);
+        if constexpr (kTmaResid) {
+          if (lane == 0) {
+            tma_store_wait_read<0>();             // the previous tile's stores have left both buffers
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              if (colh + 32 * b < N && row0 < M) {
+                mbar_arrive_expect_tx(&xres_bar[ew][b], 4096);
+                tma_load_2d(stg + b * 4096, &mapO, &xres_bar[ew][b], colh + 32 * b, row0);
+              }
+            }
+          }
+          __syncwarp();
+          sbuf = 0;
+        }
         float g[32];
         bool have_gate = false;
 #pragma unroll 1
@@ -608,11 +635,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int col0 = colh + c0;
           float4 x[8];
           if (mode == 2) {
-            const float* orow = reinterpret_cast<const float*>(ep.out) + (size_t)row * ep.ldo + col0;
+            if constexpr (!kTmaResid) {
+              const float* orow = reinterpret_cast<const float*>(ep.out) + (size_t)row * ep.ldo + col0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              x[j] = (row_ok && col0 + 4 * j < N) ? *reinterpret_cast<const float4*>(orow + 4 * j)
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int j = 0; j < 8; ++j)
+                x[j] = (row_ok && col0 + 4 * j < N) ? *reinterpret_cast<const float4*>(orow + 4 * j)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             have_gate = ep.gate != nullptr;
             if (have_gate) {
               const __half* gp = ep.gate + (size_t)((row_ok ? row : 0) / ep.rows_per_batch) * ep.gate_stride + col0;
@@ -638,6 +667,18 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + sb[half * HALF + c0 + j];
           }
+          if constexpr (kTmaResid) {
+            if (col0 < N && row0 < M) {
+              mbar_wait(&xres_bar[ew][sbuf], (xph >> sbuf) & 1u);   // own phase bits: ragged tiles skip boxes
+              xph ^= 1u << sbuf;
+              const uint8_t* xb = stg + sbuf * 4096 + lane * 128;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4*>(xb + ((j ^ sw) << 4));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
           if (mode == 2) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -650,8 +691,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               }
             }
           }
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
+          if constexpr (!kTmaResid) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
           uint8_t* buf = stg + sbuf * 4096 + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -661,6 +704,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (lane == 0 && col0 < N && row0 < M) {
             tma_store_2d(&mapO, stg + sbuf * 4096, col0, row0);
             tma_store_commit();
+          }
+          if constexpr (kTmaResid && HALF > 64) {
+            if (lane == 0 && c0 + 64 < HALF && col0 + 64 < N && row0 < M) {
+              tma_store_wait_read<0>();           // this chunk's store has left the buffer
+              mbar_arrive_expect_tx(&xres_bar[ew][sbuf], 4096);
+              tma_load_2d(stg + sbuf * 4096, &mapO, &xres_bar[ew][sbuf], col0 + 64, row0);
+            }
           }
           sbuf ^= 1;
         }
@@ -1042,18 +1092,22 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
     // every shape of the path; 128 x 256 tiles whenever N allows them and there is more than one column of
     // tiles per row block to amortise the wider epilogue (N >= 768), or the epilogue is a plain fp16 store
     variant = (N % 256 == 0 && (N >= 768 || epilogue == 0 || epilogue == 1)) ? 5 : 4;
+    // long-K residual shapes (fc2: N = 512, K = 2048): with the residual arriving by TMA the wide tiles are no longer
+    // held back by their epilogue, and 128 x 128 tiles sit on the L2 -> SM cap (38.6 vs 29 us, tools/gemm_depth_probe.py)
+    if (variant == 4 && epilogue == 2 && N % 256 == 0 && K >= 1024) variant = 5;
     // CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA stages half of W): -6..-11 % on the long-K
     // motion-VAE shapes (ff1 101.9 -> 91.0 us, cuBLAS 92.1), nothing on the K = 512 DiT shapes, which are bound by
     // ramp-up and epilogue latency rather than by L2 -> SM operand traffic
     if (variant == 5 && K >= 768 && (long long)((M + 2 * kBM - 1) / (2 * kBM)) * (N / 256) >= 74) variant = 7;
   }
   // generation-2 kernels need a TMA-storable output (16 B aligned rows) and do not do the compact mode 5
-  if (variant >= 4 && variant <= 7 &&
+  if (variant >= 4 && variant <= 9 &&
       (epilogue == 5 || (ldo * ((epilogue == 2 || epilogue == 4) ? 4 : 2)) % 16 != 0 ||
        (gate && ((gate_stride % 8) || ((uintptr_t)gate & 15)))))
     variant = 0;
+  // 8 / 9: pipeline-depth experiments (128x128 with 5 stages, 256x128 pair tiles with 6 stages)
   const int BN = (variant == 2 || variant == 5 || variant == 7) ? 256 : 128;
-  const int wbox = (variant == 6 || variant == 7) ? BN / 2 : BN;      // W rows one CTA stages per k-block
+  const int wbox = (variant == 6 || variant == 7 || variant == 9) ? BN / 2 : BN;      // W rows one CTA stages per k-block
   CUtensorMap mA, mW;
   const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {1, (uint64_t)lda};
   const uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}, sW[2] = {1, (uint64_t)ldw};
@@ -1065,7 +1119,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   ep.gate_stride = gate_stride; ep.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   ep.ldo = ldo;
   ep.gamma_q = gamma_q; ep.gamma_k = gamma_k; ep.norm_cols = norm_cols;
-  if (variant >= 4 && variant <= 7) {
+  if (variant >= 4 && variant <= 9) {
     const bool out16 = (epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6);
     CUtensorMap mO;
     if (!make_tmap_2d(&mO, out, out16 ? 2 : 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, out16 ? 64 : 32, 32))
@@ -1073,7 +1127,9 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
     cudaStream_t cs = (cudaStream_t)stream;
 #define GVF_WS(MODE)                                                                      \
     case MODE:                                                                            \
-      return variant == 7   ? launch_gemm_ws<256, 4, MODE, 2>(mA, mW, mO, M, N, K, ep, cs) \
+      return variant == 9   ? launch_gemm_ws<128, 6, MODE, 2>(mA, mW, mO, M, N, K, ep, cs) \
+             : variant == 8 ? launch_gemm_ws<128, 5, MODE, 1>(mA, mW, mO, M, N, K, ep, cs)   \
+             : variant == 7 ? launch_gemm_ws<256, 4, MODE, 2>(mA, mW, mO, M, N, K, ep, cs) \
              : variant == 6 ? launch_gemm_ws<128, 5, MODE, 2>(mA, mW, mO, M, N, K, ep, cs) \
              : variant == 5 ? launch_gemm_ws<256, 3, MODE>(mA, mW, mO, M, N, K, ep, cs)    \
                             : launch_gemm_ws<128, 4, MODE>(mA, mW, mO, M, N, K, ep, cs);
