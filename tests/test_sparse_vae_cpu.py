@@ -56,3 +56,30 @@ def test_subm_conv_gather_form_equals_dense_form():
     out = cols @ w.reshape(cout, -1).t() + bias
     assert (out - ref).abs().max() < 1e-4
     assert int((nbr[:, 13] == torch.arange(2 * n)).all()) == 1      # centre tap is the voxel itself
+
+
+def test_sparse_tensor_container_layout_and_cache():
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    coords = torch.tensor([[0, 1, 2, 3], [0, 4, 5, 6], [1, 0, 0, 0], [2, 7, 7, 7], [2, 1, 1, 1]])
+    x = SparseTensor(torch.arange(10.0).reshape(5, 2), coords)
+    assert x.shape == torch.Size([3, 2]) and x.coords.dtype == torch.int32
+    assert [(s.start, s.stop) for s in x.layout] == [(0, 2), (2, 3), (3, 5)]
+    y = x.replace(torch.zeros(5, 7))
+    assert y.shape == torch.Size([3, 7]) and y.layout == x.layout and y.coords is x.coords
+    x.register_spatial_cache("k", 5)
+    assert y.get_spatial_cache("k") == 5            # the cache is shared by tensors over the same coordinates
+
+
+def test_sparse_conv_mirror_rejects_what_is_not_on_the_path():
+    import pytest
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from gvfdiffusion_b200.sparse.conv import SparseConv3d
+    with pytest.raises(NotImplementedError):
+        SparseConv3d(8, 8, 3, stride=2, device="cpu")
+    with pytest.raises(ValueError):
+        SparseConv3d(6, 8, 3, device="cpu")
+    conv = SparseConv3d(8, 16, 3, device="cpu").load_state_dict(
+        {"p.conv.weight": torch.randn(16, 3, 3, 3, 8), "p.conv.bias": torch.randn(16)}, prefix="p.")
+    assert conv.weight.shape == (16, 27 * 8) and conv.weight.dtype == torch.float16
+    with pytest.raises(RuntimeError, match="device only"):
+        conv(SparseTensor(torch.zeros(2, 8), torch.tensor([[0, 0, 0, 0], [0, 1, 1, 1]])))
