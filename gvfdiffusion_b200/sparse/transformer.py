@@ -16,10 +16,27 @@ from .attention import sparse_windowed_scaled_dot_product_self_attention
 F16, F32 = torch.float16, torch.float32
 
 
+def qkv_rows_from_old_attn_impl(weight, bias, num_heads):
+    """`use_old_attn_impl=True` (the class default of SparseTransformerVAE; the shipped configs/vae.yml:30 and
+    configs/diffusion.yml:57 set it to false) lays the to_qkv output channels out as [H][3][d]
+    (sparse/attention/modules.py:161-164: reshape to (H, 3 d), chunk 3) instead of [3][H][d].  The kernels consume
+    [3][H][d]; permuting the ROWS of to_qkv once at load time gives exactly the same q, k, v."""
+    c3 = weight.shape[0]
+    d = c3 // (3 * num_heads)
+    idx = torch.arange(c3, device=weight.device).reshape(num_heads, 3, d).permute(1, 0, 2).reshape(-1)
+    return weight[idx], bias[idx]
+
+
 class SparseTransformerBlocks:
-    def __init__(self, state_dict, prefix, num_blocks, num_heads, window_size, device="cuda", fp16_residual=False):
+    def __init__(self, state_dict, prefix, num_blocks, num_heads, window_size, device="cuda", fp16_residual=False,
+                 use_old_attn_impl=False):
         """fp16_residual: the residual stream is fp16 (`h.type(self.dtype)` with use_fp16=True,
-        sparse_transformer_vae.py:155,181) instead of fp32."""
+        sparse_transformer_vae.py:155,181) instead of fp32.  use_old_attn_impl: see qkv_rows_from_old_attn_impl."""
+        if use_old_attn_impl:
+            state_dict = dict(state_dict)
+            for i in range(num_blocks):
+                kw, kb = f"{prefix}{i}.attn.to_qkv.weight", f"{prefix}{i}.attn.to_qkv.bias"
+                state_dict[kw], state_dict[kb] = qkv_rows_from_old_attn_impl(state_dict[kw], state_dict[kb], num_heads)
         dev = torch.device(device)
         self.fp16_residual = fp16_residual
         h = lambda t: t.detach().to(device=dev, dtype=F16).contiguous()
@@ -67,7 +84,8 @@ class SparseTransformerVAE:
     affine-free LayerNorm (norm_output, eps 1e-5) -> to_latent / out_layer.  `to_representation`
     (sparse_vae.py:114-180) stays host-side torch (gvfdiffusion_b200/synthetic.py builds the same tensors)."""
 
-    def __init__(self, state_dict, num_blocks, num_heads, window_size=8, use_fp16=True, norm_output=False, device="cuda"):
+    def __init__(self, state_dict, num_blocks, num_heads, window_size=8, use_fp16=True, norm_output=False, device="cuda",
+                 use_old_attn_impl=False):
         dev = torch.device(device)
         self.dev, self.norm_output, self.use_fp16 = dev, norm_output, use_fp16
         h = lambda t: t.detach().to(device=dev, dtype=F16).contiguous()
@@ -76,7 +94,8 @@ class SparseTransformerVAE:
         self.lin = {n: (h(sd[n + ".weight"]), b(sd[n + ".bias"])) for n in ("input_layer", "to_latent", "from_latent", "out_layer")
                     if n + ".weight" in sd}
         self.C = sd["from_latent.weight"].shape[0] if "from_latent.weight" in sd else sd["input_layer.weight"].shape[0]
-        mk = lambda prefix: SparseTransformerBlocks(sd, prefix, num_blocks, num_heads, window_size, dev, fp16_residual=use_fp16)
+        mk = lambda prefix: SparseTransformerBlocks(sd, prefix, num_blocks, num_heads, window_size, dev, fp16_residual=use_fp16,
+                                                    use_old_attn_impl=use_old_attn_impl)
         self.encoder = mk("encoder.") if "encoder.0.attn.to_qkv.weight" in sd else None
         self.decoder = mk("decoder.") if "decoder.0.attn.to_qkv.weight" in sd else None
 

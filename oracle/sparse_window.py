@@ -2,7 +2,9 @@
 sparse self-attention -- calc_window_partition (sparse/attention/windowed_attn.py:20-58) and the
 gather -> per-window softmax attention -> scatter of :92-129 (flash_attn_varlen_qkvpacked_func is plain
 scaled-dot-product attention inside each cu_seqlens segment).  Pinned by tests/golden/window_partition.pt,
-produced by the reference's own calc_window_partition (tests/golden/make_golden.py)."""
+produced by the reference's own calc_window_partition, and -- blocks, encode and decode trunks, both qkv channel
+layouts -- by tests/golden/sparse_vae_tiny.pt, produced by the reference's own SparseTransformerVAE on the CPU
+(tests/golden/make_golden.py gen_sparse_vae; tests/test_sparse_vae_cpu.py)."""
 import math
 
 import torch
@@ -41,7 +43,7 @@ def windowed_attention(qkv_feats, coords, window_size, shift_window=0):
 
 
 def transformer_blocks(sd, prefix, num_blocks, num_heads, feats, coords, window_size, precision="fp32",
-                       fp16_residual=False):
+                       fp16_residual=False, old_attn_impl=False):
     """Stack of un-modulated SparseTransformerBlock (reference model/sparse_voxel_diffusion/sparse_transformer.py
     :126-192 with modulated=False, attn_mode "swin": block i uses shift_window = window_size // 2 * (i % 2),
     :24-25) over a reference-keyed state dict: `{prefix}{i}.attn.to_qkv|to_out`, `{prefix}{i}.mlp.mlp.0|2`.
@@ -57,7 +59,11 @@ def transformer_blocks(sd, prefix, num_blocks, num_heads, feats, coords, window_
         p = f"{prefix}{i}."
         shift = window_size // 2 * (i % 2)
         h = F.layer_norm(x, (C,), None, None, 1e-6)
-        qkv = P.linear(h, sd[p + "attn.to_qkv.weight"], sd[p + "attn.to_qkv.bias"]).reshape(-1, 3, num_heads, C // num_heads)
+        qkv = P.linear(h, sd[p + "attn.to_qkv.weight"], sd[p + "attn.to_qkv.bias"])
+        if old_attn_impl:     # sparse/attention/modules.py:161-164: channels [H][3][d] (use_old_attn_impl=True)
+            qkv = qkv.reshape(-1, num_heads, 3, C // num_heads).permute(0, 2, 1, 3)
+        else:                 # :166: channels [3][H][d] (the shipped configs)
+            qkv = qkv.reshape(-1, 3, num_heads, C // num_heads)
         a = P.r(windowed_attention(qkv, coords, window_size, shift)).reshape(-1, C)
         x = rr(x + P.linear(a, sd[p + "attn.to_out.weight"], sd[p + "attn.to_out.bias"]))
         h = F.layer_norm(x, (C,), None, None, 1e-6)
@@ -68,7 +74,7 @@ def transformer_blocks(sd, prefix, num_blocks, num_heads, feats, coords, window_
 
 
 def vae_decode(sd, num_blocks, num_heads, latent, coords, window_size=8, precision="fp16", use_fp16=True,
-               norm_output=False):
+               norm_output=False, old_attn_impl=False):
     """SparseTransformerVAE.decode (sparse_transformer_vae.py:178-188): from_latent + APE of the voxel
     coordinates (sparse_transformer.py:62-109) -> decoder blocks -> optional layer_norm (eps 1e-5) -> out_layer."""
     import torch.nn.functional as F
@@ -77,7 +83,8 @@ def vae_decode(sd, num_blocks, num_heads, latent, coords, window_size=8, precisi
     C = sd["from_latent.weight"].shape[0]
     h = P.linear(latent.float(), sd["from_latent.weight"], sd["from_latent.bias"])
     h = h + absolute_position_embedding(coords[:, 1:].float()[None], C)[0]
-    h = transformer_blocks(sd, "decoder.", num_blocks, num_heads, h, coords, window_size, precision, fp16_residual=use_fp16)
+    h = transformer_blocks(sd, "decoder.", num_blocks, num_heads, h, coords, window_size, precision, fp16_residual=use_fp16,
+                           old_attn_impl=old_attn_impl)
     if norm_output:
         h = F.layer_norm(h, (C,))
     return P.linear(h, sd["out_layer.weight"], sd["out_layer.bias"])

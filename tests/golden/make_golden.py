@@ -258,6 +258,82 @@ def gen_losses():
     return out
 
 
+def gen_sparse_vae():
+    """The reference's own SparseTransformerVAE (model/sparse_voxel_diffusion/sparse_transformer_vae.py) -- swin
+    SparseTransformerBlocks over sparse.SparseTensor -- run on the CPU in fp32 on a seeded two-entry batch.
+    Stand-ins needed for that: a container for spconv.pytorch.SparseConvTensor (the reference only stores tensors in
+    it) and flash_attn's two packed-QKV entry points restated as plain scaled-dot-product attention inside each
+    cu_seqlens segment (flash-attn's documented semantics; the CUDA wheel cannot run on the CPU)."""
+    import types
+
+    class _SCT:
+        def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None, **kw):
+            self._features, self.indices, self.spatial_shape, self.batch_size = features, indices, spatial_shape, batch_size
+            self.grid, self.voxel_num, self.indice_dict = grid, voxel_num, indice_dict
+            self.benchmark = self.benchmark_record = self.thrust_allocator = self._timer = None
+            self.force_algo = self.int8_scale = None
+
+        @property
+        def features(self):
+            return self._features
+
+        def replace_feature(self, f):
+            return _SCT(f, self.indices, self.spatial_shape, self.batch_size)
+
+    sys.modules["spconv.pytorch"].SparseConvTensor = _SCT
+    sdpa = torch.nn.functional.scaled_dot_product_attention
+
+    def varlen(qkv, cu, maxlen):
+        out = torch.empty_like(qkv[:, 0])
+        for i in range(len(cu) - 1):
+            s, e = int(cu[i]), int(cu[i + 1])
+            q, k, v = (t.transpose(0, 1).float() for t in qkv[s:e].unbind(1))
+            out[s:e] = sdpa(q, k, v).transpose(0, 1).to(qkv.dtype)
+        return out
+
+    def packed(qkv):
+        q, k, v = (t.transpose(1, 2).float() for t in qkv.unbind(2))
+        return sdpa(q, k, v).transpose(1, 2).to(qkv.dtype)
+
+    fa = types.ModuleType("flash_attn")
+    fa.flash_attn_varlen_qkvpacked_func, fa.flash_attn_qkvpacked_func = varlen, packed
+    saved = sys.modules.get("flash_attn")
+    sys.modules["flash_attn"] = fa
+    try:
+        from model.sparse_voxel_diffusion.sparse_transformer_vae import SparseTransformerVAE
+        import sparse as sp
+        # use_old_attn_impl: false is what configs/vae.yml:30 and configs/diffusion.yml:57 ship ([3][H][d] qkv channels);
+        # the class default True ([H][3][d], sparse/attention/modules.py:161-164) is run on the same weights as well
+        cfg = dict(resolution=16, in_channels=16, model_channels=128, out_channels=24, latent_channels=8, num_blocks=2,
+                   window_size=8, num_head_channels=64, attn_mode="swin", pe_mode="ape", use_fp16=False, norm_output=True,
+                   use_old_attn_impl=False)
+        torch.manual_seed(0)
+        m = SparseTransformerVAE(**cfg).eval()
+        rerandomise_zero_layers(m)
+        m_old = SparseTransformerVAE(**dict(cfg, use_old_attn_impl=True)).eval()
+        m_old.load_state_dict(m.state_dict())
+        g = torch.Generator().manual_seed(1)
+        coords = []
+        for b, n in enumerate((150, 90)):
+            lin = torch.randperm(16 ** 3, generator=g)[:n].sort().values
+            coords.append(torch.stack([torch.full((n,), b), lin // 256, (lin // 16) % 16, lin % 16], 1))
+        coords = torch.cat(coords).int()
+        latent = torch.randn(coords.shape[0], 8, generator=g)
+        feats = torch.randn(coords.shape[0], 16, generator=g)
+        with torch.no_grad():
+            dec = m.decode(sp.SparseTensor(latent, coords)).feats
+            _, mean, logvar = m.encode(sp.SparseTensor(feats, coords), sample_posterior=False, return_raw=True)
+            dec_old = m_old.decode(sp.SparseTensor(latent, coords)).feats
+        return {"cfg": cfg, "state_dict": {k: v.clone() for k, v in m.state_dict().items()}, "coords": coords,
+                "latent": latent, "feats": feats, "decode": dec, "mean": mean, "logvar": logvar,
+                "decode_old_attn_impl": dec_old}
+    finally:
+        if saved is not None:
+            sys.modules["flash_attn"] = saved
+        else:
+            sys.modules.pop("flash_attn", None)
+
+
 def gen_to_representation():
     """The reference's own SparseVAE.to_representation / _build_perturbation / _calc_layout
     (model/sparse_voxel_diffusion/sparse_vae.py:104-180,202-227) with the MipGS block of configs/vae.yml, on a
@@ -320,6 +396,9 @@ def gen_to_representation():
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sparse_vae":
+        torch.save(gen_sparse_vae(), os.path.join(HERE, "sparse_vae_tiny.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "to_representation":
         torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
         return
@@ -338,6 +417,7 @@ def main():
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
+    torch.save(gen_sparse_vae(), os.path.join(HERE, "sparse_vae_tiny.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

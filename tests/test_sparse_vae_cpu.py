@@ -83,3 +83,60 @@ def test_sparse_conv_mirror_rejects_what_is_not_on_the_path():
     assert conv.weight.shape == (16, 27 * 8) and conv.weight.dtype == torch.float16
     with pytest.raises(RuntimeError, match="device only"):
         conv(SparseTensor(torch.zeros(2, 8), torch.tensor([[0, 0, 0, 0], [0, 1, 1, 1]])))
+
+
+def test_sparse_transformer_vae_oracle_matches_reference_fixture():
+    """oracle/sparse_window.py (window partition + per-window attention + swin blocks + SparseTransformerVAE
+    encode / decode) against the reference's own SparseTransformerVAE run on the CPU in fp32
+    (tests/golden/sparse_vae_tiny.pt, tests/golden/make_golden.py gen_sparse_vae)."""
+    import torch.nn.functional as F
+    from oracle import sparse_window as OSW
+    from oracle.dit import absolute_position_embedding
+    g = torch.load(os.path.join(G, "sparse_vae_tiny.pt"), weights_only=False)
+    cfg, sd, coords = g["cfg"], g["state_dict"], g["coords"]
+    H = cfg["model_channels"] // cfg["num_head_channels"]
+    dec = OSW.vae_decode(sd, cfg["num_blocks"], H, g["latent"], coords, cfg["window_size"], precision="fp32",
+                         use_fp16=False, norm_output=True)
+    assert dec.shape == g["decode"].shape
+    assert float((dec - g["decode"]).norm() / g["decode"].norm()) < 2e-5
+    # encode (:151-176): input_layer + APE -> encoder blocks -> layer_norm -> to_latent -> (mean, logvar)
+    C = cfg["model_channels"]
+    h = F.linear(g["feats"], sd["input_layer.weight"], sd["input_layer.bias"])
+    h = h + absolute_position_embedding(coords[:, 1:].float()[None], C)[0]
+    h = OSW.transformer_blocks(sd, "encoder.", cfg["num_blocks"], H, h, coords, cfg["window_size"], "fp32")
+    h = F.linear(F.layer_norm(h, (C,)), sd["to_latent.weight"], sd["to_latent.bias"])
+    mean, logvar = h.chunk(2, dim=-1)
+    assert float((mean - g["mean"]).norm() / g["mean"].norm()) < 2e-5
+    assert float((logvar - g["logvar"]).norm() / g["logvar"].norm()) < 2e-5
+
+
+def test_old_attn_impl_layout_oracle_and_weight_permutation():
+    """use_old_attn_impl=True ([H][3][d] qkv channels, the class default; the shipped configs use false): the oracle
+    restates it, and the device mirror's load-time row permutation of to_qkv yields the same q, k, v."""
+    import torch.nn.functional as F
+    from gvfdiffusion_b200.sparse.transformer import qkv_rows_from_old_attn_impl
+    from oracle import sparse_window as OSW
+    g = torch.load(os.path.join(G, "sparse_vae_tiny.pt"), weights_only=False)
+    cfg, sd, coords = g["cfg"], g["state_dict"], g["coords"]
+    H = cfg["model_channels"] // cfg["num_head_channels"]
+    dec = OSW.vae_decode(sd, cfg["num_blocks"], H, g["latent"], coords, cfg["window_size"], precision="fp32",
+                         use_fp16=False, norm_output=True, old_attn_impl=True)
+    ref = g["decode_old_attn_impl"]
+    assert float((dec - ref).norm() / ref.norm()) < 2e-5
+    assert float((g["decode"] - ref).norm() / ref.norm()) > 0.1          # the two layouts are different functions
+    # permuted rows + the [3][H][d] reading == original rows + the [H][3][d] reading, bit for bit
+    w, b = sd["decoder.0.attn.to_qkv.weight"], sd["decoder.0.attn.to_qkv.bias"]
+    wp, bp = qkv_rows_from_old_attn_impl(w, b, H)
+    x = torch.randn(37, w.shape[1], generator=torch.Generator().manual_seed(4))
+    d = w.shape[0] // (3 * H)
+    old = F.linear(x, w, b).reshape(-1, H, 3, d).permute(0, 2, 1, 3)
+    new = F.linear(x, wp, bp).reshape(-1, 3, H, d)
+    assert torch.equal(old, new)
+    # and through the whole oracle trunk: permuted state dict in the default layout == old layout on the original
+    sd2 = dict(sd)
+    for i in range(cfg["num_blocks"]):
+        k = f"decoder.{i}.attn.to_qkv."
+        sd2[k + "weight"], sd2[k + "bias"] = qkv_rows_from_old_attn_impl(sd[k + "weight"], sd[k + "bias"], H)
+    dec2 = OSW.vae_decode(sd2, cfg["num_blocks"], H, g["latent"], coords, cfg["window_size"], precision="fp32",
+                          use_fp16=False, norm_output=True)
+    assert float((dec2 - ref).norm() / ref.norm()) < 2e-5
