@@ -334,6 +334,96 @@ def gen_sparse_vae():
             sys.modules.pop("flash_attn", None)
 
 
+def gen_render_call():
+    """What the reference hands to the third-party rasteriser: the reference's own GaussianRenderer.render
+    (renderers/gaussian_render.py:269-369 -> render() :85-238) is run on the CPU with a RECORDING stand-in for
+    diff_gaussian_rasterization (the module is absent here and on the GPU box); the fixture holds the
+    GaussianRasterizationSettings fields and the tensors of the GaussianRasterizer call for a seeded GaussianModel,
+    delta and orbit camera.  `device="cuda"` literals of the two functions are dropped through a proxy of the torch
+    module inside that one reference module."""
+    import types
+    for name in ("utils3d", "plyfile", "easydict"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["plyfile"].PlyData = sys.modules["plyfile"].PlyElement = object
+
+    class _EDict(dict):
+        def __init__(self, d=None, **kw):
+            super().__init__()
+            for k, v in dict(d or {}, **kw).items():
+                self[k] = v
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    sys.modules["easydict"].EasyDict = _EDict
+    rec = {}
+
+    class Settings:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    class Rasterizer:
+        def __init__(self, raster_settings):
+            rec["settings"] = raster_settings
+
+        def __call__(self, **kw):
+            rec["call"] = kw
+            s = rec["settings"]
+            return torch.zeros(3, s.image_height, s.image_width), torch.ones(kw["means3D"].shape[0], dtype=torch.int32)
+
+    sys.modules["diff_gaussian_rasterization"] = types.SimpleNamespace(GaussianRasterizationSettings=Settings,
+                                                                       GaussianRasterizer=Rasterizer)
+
+    class _TorchProxy:
+        def __getattr__(self, name):
+            f = getattr(torch, name)
+            if name in ("zeros", "tensor", "zeros_like", "ones"):
+                def g(*a, **k):
+                    k.pop("device", None)
+                    return f(*a, **k)
+                return g
+            return f
+
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        from representations.gaussian.gaussian_model import GaussianModel
+        import renderers.gaussian_render as GR
+        GR.torch = _TorchProxy()
+        gm = GaussianModel(sh_degree=0, aabb=[-0.5, -0.5, -0.5, 1.0, 1.0, 1.0], mininum_kernel_size=0.0009,
+                           scaling_bias=0.004, opacity_bias=0.1, scaling_activation="softplus", device="cpu")
+        g = torch.Generator().manual_seed(21)
+        P = 96
+        gm._xyz = torch.rand(P, 3, generator=g)
+        gm._features_dc = torch.randn(P, 1, 3, generator=g)
+        gm._scaling = torch.randn(P, 3, generator=g)
+        gm._rotation = torch.randn(P, 4, generator=g) * 0.1
+        gm._opacity = torch.randn(P, 1, generator=g)
+        delta = torch.randn(P, 14, generator=g) * 0.05
+        sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+        from gvfdiffusion_b200 import synthetic as S
+        ext = S.orbit_extrinsics(24)[5]
+        intr = S.intrinsics()
+        r = GR.GaussianRenderer({"resolution": 64, "near": 0.8, "far": 1.6, "ssaa": 1, "bg_color": (1.0, 1.0, 1.0)})
+        r.pipe.use_mip_gaussian = True
+        r.pipe.kernel_size = 0.1
+        out = {"raw": {k: getattr(gm, k).clone() for k in ("_xyz", "_features_dc", "_scaling", "_rotation", "_opacity")},
+               "delta": delta, "extrinsics": ext, "intrinsics": intr, "near": 0.8, "far": 1.6, "resolution": 64}
+        for tag, d in (("with_delta", delta), ("no_delta", None)):
+            rec.clear()
+            ret = r.render(gm, ext, intr, delta_pc=d)
+            assert set(ret.keys()) == {"rgb"}
+            s_, c_ = rec["settings"], rec["call"]
+            out[tag] = {"settings": {k: (v.clone() if torch.is_tensor(v) else v) for k, v in s_.__dict__.items()},
+                        "call": {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in c_.items()}}
+            out[tag]["settings"]["tanfovx"] = float(s_.tanfovx)
+            out[tag]["settings"]["tanfovy"] = float(s_.tanfovy)
+    finally:
+        torch.Tensor.cuda = orig
+        sys.modules.pop("diff_gaussian_rasterization", None)
+    return out
+
+
 def gen_to_representation():
     """The reference's own SparseVAE.to_representation / _build_perturbation / _calc_layout
     (model/sparse_voxel_diffusion/sparse_vae.py:104-180,202-227) with the MipGS block of configs/vae.yml, on a
@@ -396,6 +486,9 @@ def gen_to_representation():
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "render_call":
+        torch.save(gen_render_call(), os.path.join(HERE, "render_call.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "sparse_vae":
         torch.save(gen_sparse_vae(), os.path.join(HERE, "sparse_vae_tiny.pt"))
         return
@@ -418,6 +511,7 @@ def main():
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
     torch.save(gen_sparse_vae(), os.path.join(HERE, "sparse_vae_tiny.pt"))
+    torch.save(gen_render_call(), os.path.join(HERE, "render_call.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
