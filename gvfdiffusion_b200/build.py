@@ -59,8 +59,8 @@ def _compile(src, verbose, force=False):
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}")
-    with open(obj + ".ptxas.txt", "w") as f:
-        f.write(r.stderr)
+    with open(obj + ".ptxas.txt", "w") as f:      # registers / spills / shared memory per kernel; compile times dropped (noise)
+        f.write("".join(l for l in r.stderr.splitlines(True) if "Compile time" not in l))
     return obj
 
 
