@@ -93,7 +93,9 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if os.environ.get("GVF_NO_AUTOBUILD") != "1":
+    # under torchrun several ranks import at once: never rebuild concurrently when a library is already there
+    multi_rank = int(os.environ.get("WORLD_SIZE", "1") or 1) > 1 and os.path.exists(LIB_PATH)
+    if os.environ.get("GVF_NO_AUTOBUILD") != "1" and not multi_rank:
         try:
             from . import build as _b
             _b.build()
