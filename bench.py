@@ -473,6 +473,10 @@ def main():
                                      "blend loop, a fifth in the bucket sort; DRAM traffic is below the algorithmic bytes because "
                                      "key lists and splat records are re-read from L2 (profiles/r01_raster_bucket_full_extract.csv)")},
     }
+    try:        # derived figure only: never allowed to break the line
+        line["roofline_dit"] = dit_roofline(ms_step, line["stage_ms_eager"], pk["tf_sustained"], NFE)
+    except Exception as e:
+        line["roofline_dit"] = {"error": str(e)}
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline()
@@ -507,6 +511,18 @@ def _tagged_attention(fn, timer):
         return r
     return call
 
+
+
+def dit_roofline(ms_step, stage_ms_eager, peak_tflops, nfe=32):
+    """Tensor roofline of the whole sampler: algorithmic F_NFE = 3.394 TFLOP per NFE + F_once =
+    0.465 TFLOP per object (time- and frame-invariant projections hoisted) over the sampler's share of the timed
+    step = ms_step minus the eagerly timed non-sampler stages (FPS, VAE decode, render)."""
+    other = sum(float(stage_ms_eager.get(k, 0.0)) for k in ("prepare_fps", "vae_decode", "raster_24f"))
+    t_ms = max(float(ms_step) - other, 1e-6)
+    flop = 3.394e12 * nfe + 0.465e12
+    ach = flop / (t_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "DiT sampler (32 NFE, graph replay)", "achieved": ach, "peak": peak_tflops,
+            "unit": "TFLOP/s", "frac": ach / peak_tflops, "ms": t_ms, "algorithmic_tflop": flop / 1e12}
 
 def ncu_traffic(kernel_prefix):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""

@@ -34,3 +34,15 @@ def test_reference_arm_runs_on_cpu_and_prints_the_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "frames/s"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_dit_roofline_helper_on_the_snapshot():
+    """bench.dit_roofline: algorithmic sampler FLOPs over the sampler's share of the step."""
+    import bench
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json")).read().strip().splitlines()[-1])
+    r = bench.dit_roofline(line["ms_per_step"], line["stage_ms_eager"], 1392.3, 32)
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s"
+    assert abs(r["algorithmic_tflop"] - (3.394 * 32 + 0.465)) < 1e-9
+    assert 0.0 < r["frac"] < 1.0 and abs(r["frac"] - r["achieved"] / 1392.3) < 1e-12
+    assert r["ms"] < line["ms_per_step"]
+    assert bench.dit_roofline(1.0, {}, 1000.0)["achieved"] > 0          # degenerate inputs do not raise
