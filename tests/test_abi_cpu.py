@@ -79,3 +79,18 @@ def test_schedule_host_mirror_matches_oracle_on_cpu():
     fn = D.model_wrapper(lambda *a, **k: None, ns, model_type="v", guidance_type="classifier-free",
                          condition={"static_latent": torch.zeros(1)}, unconditional_condition=None)
     assert abs(float(fn.t_input(1.0)) - (1.0 - 1 / 996) * 1000) < 1e-3 and abs(float(fn.t_input(1e-3)) + 0.004) < 1e-3
+
+
+def test_header_is_plain_c_and_cpp():
+    """include/gvf_b200.h is the drop-in boundary: it must compile as C99 and as C++17 without torch or CUDA headers."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "gvf_b200.h")
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    txt = open(hdr).read()
+    assert "#include <torch" not in txt and "#include <cuda" not in txt and "at::Tensor" not in txt
