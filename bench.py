@@ -548,12 +548,4 @@ def launch_estimate():
 
 
 if __name__ == "__main__":
-    try:
-        main()
-    finally:
-        try:
-            import torch.distributed as _dist
-            if _dist.is_available() and _dist.is_initialized():
-                _dist.destroy_process_group()
-        except Exception:
-            pass
+    main()      # no destroy_process_group(): ranks leave at different times (rank 0 prints), process exit tears NCCL down
