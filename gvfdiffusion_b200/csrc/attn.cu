@@ -701,6 +701,344 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------
+// v8 (d = 32) = v6 with the MMA issue path made warp-uniform.  Finding behind it (tools/attn_trace.py, round 2):
+// with ALL softmax arithmetic removed the v6 kernel still took 222 of its 255 us -- the single thread per tile
+// that issues tcgen05.mma / commit / TMA was the bottleneck, not the MUFU pipe.  Inside `if (lane == 0)` every
+// operand lives in per-thread registers, so ptxas wraps each tcgen05.mma, commit and TMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" loop and recomputes descriptors with dependent integer chains:
+// ~2 200 clocks per (QK, PV) pair of batches on a warp that shares its scheduler with four busy softmax warps.
+// Here the issuer warps run their loop with all 32 lanes (every value provably warp-uniform: blockIdx, kernel
+// arguments, a shuffled warp index), descriptors are built once and advanced by adding to their address field,
+// only the tcgen05 / TMA instructions themselves sit behind elect.sync, and the softmax warps arrive on their barriers once per warp instead of once
+// per thread (4 arrivals instead of 128 shared-memory atomics per hand-off).
+//   20 warps: 0-3 MMA issuers (tile = warp; warp 0 also keeps the K/V ring going), 4-19 softmax (thread = query
+//   row = TMEM lane).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int PMASK, int DROP>
+__global__ void __launch_bounds__(640, 1)
+attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  constexpr int D = 32, BLK = 64, NT = 4;
+  constexpr int ROWB = D * 2;
+  constexpr int TILE_BYTES = 128 * ROWB;
+  constexpr uint64_t SWZ = SWZ_64B;
+  constexpr uint32_t SBO = 8 * ROWB;
+  constexpr int S = kAttnStages;
+  constexpr uint32_t TM_P = 64, TM_O = 96, TM_STRIDE = 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, kv_full[S], kv_empty[S], s_full[NT], s_free[NT], p_full[NT], o_full[NT];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                              // NT tiles
+  uint8_t* sKV = smem + NT * TILE_BYTES;           // S x (K tile, V tile)
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x;
+  int unit = item, part = -1;
+  if (item >= a.split_from) {
+    unit = a.split_from + (item - a.split_from) / a.nsplit;
+    part = (item - a.split_from) % a.nsplit;
+  }
+  const int qblk = unit % a.gx, h = (unit / a.gx) % a.H, nb = unit / (a.gx * a.H);
+  const int q0 = qblk * (128 * NT);
+  const int nq = min(NT, (a.Lq - q0 + 127) / 128);
+  const int n_kv_all = (a.Lk + 127) / 128;
+  const int t0 = part < 0 ? 0 : (part * n_kv_all) / a.nsplit;
+  const int t1 = part < 0 ? n_kv_all : ((part + 1) * n_kv_all) / a.nsplit;
+  const int n_kv = t1 - t0;
+  const int b0 = 2 * t0;
+  const int n_blk = min((a.Lk + BLK - 1) / BLK, 2 * t1) - b0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < S; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], nq); }
+    for (int x = 0; x < NT; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&s_free[x], 4);                    // one arrival per softmax warp of the tile
+      mbar_init(&p_full[x], 4);
+      mbar_init(&o_full[x], 1);
+    }
+    fence_barrier_init();
+    pdl_wait();
+    mbar_arrive_expect_tx(&q_full, nq * TILE_BYTES);
+    for (int t = 0; t < nq; ++t)
+      tma_load_4d(sQ + t * TILE_BYTES, &mapQ, &q_full, 0, h, q0 + t * 128, nb * a.q_batch_mul);
+    for (int j = 0; j < min(S, n_kv); ++j) {
+      mbar_arrive_expect_tx(&kv_full[j], 2 * TILE_BYTES);
+      tma_load_4d(sKV + j * 2 * TILE_BYTES, &mapK, &kv_full[j], 0, h, (t0 + j) * 128, nb * a.kv_batch_mul);
+      tma_load_4d(sKV + j * 2 * TILE_BYTES + TILE_BYTES, &mapV, &kv_full[j], 0, h, (t0 + j) * 128, nb * a.kv_batch_mul);
+    }
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ MMA issuer of tile x (all lanes, uniform)
+    // (a 21st warp for the K/V ring does not fit: the register file is per SM sub-partition, and one issuer
+    // at 32 plus four softmax warps at 112 registers already fill its 16 K entries -- tile 0's issuer keeps
+    // the ring going between its MMA batches, with warp-uniform polling)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    const int x = warp;
+    if (x < nq) {
+      const uint32_t idesc_qk = make_idesc_f16(128, BLK, 0, 0);
+      const uint32_t idesc_pv = make_idesc_f16(128, D, 0, 1);
+      const uint32_t tX = tmem + x * TM_STRIDE;
+      // descriptors: high words are constants, low words = (address >> 4) | (LBO >> 4) << 16; a block further
+      // on in shared memory is reached by adding (bytes >> 4) to the low word (addresses stay below 2^18)
+      const uint32_t hi = (uint32_t)((make_smem_desc(0, 0, SBO, SWZ)) >> 32);
+      const uint32_t q_lo = (uint32_t)make_smem_desc(smem_u32(sQ) + x * TILE_BYTES, 16, SBO, SWZ);
+      const uint32_t k_lo0 = (uint32_t)make_smem_desc(smem_u32(sKV), 16, SBO, SWZ);                  // stage 0, first half
+      const uint32_t v_lo0 = (uint32_t)make_smem_desc(smem_u32(sKV) + TILE_BYTES, SBO, SBO, SWZ);
+      constexpr uint32_t STAGE16 = (2 * TILE_BYTES) >> 4, HALF16 = (BLK * ROWB) >> 4;
+      auto desc = [&](uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+      uint32_t qk_off = 0, pv_off = 0;             // (stage, half) offsets of the next QK / PV block, in 16 B units
+      int qk_stage = 0, pv_stage = 0, qk_half = 0, pv_half = 0;
+      uint32_t kv_par = 0;                         // parity of kv_full[qk_stage] for the tile about to be used
+      const uint32_t b_kvfull = smem_u32(&kv_full[0]), b_kvempty = smem_u32(&kv_empty[0]);
+      const uint32_t b_sfull = smem_u32(&s_full[x]), b_sfree = smem_u32(&s_free[x]);
+      const uint32_t b_pfull = smem_u32(&p_full[x]), b_ofull = smem_u32(&o_full[x]);
+      auto issue_qk = [&]() {                      // S = Q K(next block)^T, then advance
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            mma_ss(tX, desc(q_lo + 2 * k), desc(k_lo0 + qk_off + 2 * k), idesc_qk, k != 0);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_sfull) : "memory");
+        }
+        __syncwarp();
+        qk_half ^= 1;
+        qk_off += HALF16;
+        if (qk_half == 0) {
+          qk_off += STAGE16 - 2 * HALF16;
+          if (++qk_stage == S) { qk_stage = 0; qk_off = 0; kv_par ^= 1; }
+        }
+      };
+      // K/V ring (tile 0's issuer): tiles [0, min(S, n_kv)) were requested in the prologue
+      int loaded = min(S, n_kv), ld_stage = 0;
+      uint32_t ld_par = 0;                         // parity to wait for on kv_empty[ld_stage]: first re-use waits for phase 0
+      auto load_next = [&]() {                     // caller has made sure stage ld_stage is free
+        if (elect_one()) {
+          const uint32_t dst = smem_u32(sKV) + ld_stage * 2 * TILE_BYTES;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_kvfull + 8 * ld_stage), "r"(2 * TILE_BYTES) : "memory");
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(dst), "l"(&mapK), "r"(b_kvfull + 8 * ld_stage), "r"(0), "r"(h), "r"((t0 + loaded) * 128), "r"(nb * a.kv_batch_mul) : "memory");
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(dst + TILE_BYTES), "l"(&mapV), "r"(b_kvfull + 8 * ld_stage), "r"(0), "r"(h), "r"((t0 + loaded) * 128), "r"(nb * a.kv_batch_mul) : "memory");
+        }
+        __syncwarp();
+        ++loaded;
+        if (++ld_stage == S) { ld_stage = 0; ld_par ^= 1; }
+      };
+      auto pump = [&]() {                          // request every tile whose stage is already free
+        while (loaded < n_kv) {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(b_kvempty + 8 * ld_stage), "r"(ld_par) : "memory");
+          if (!__shfl_sync(0xffffffffu, ok, 0)) break;
+          load_next();
+        }
+      };
+      int tiles_used = 1;                          // K/V tiles this issuer has started to consume
+      auto need_tile = [&]() {                     // before the first block of K/V tile number `tiles_used`
+        if (x == 0)
+          while (loaded <= tiles_used) {           // this warp owes the load it is about to wait for
+            mbar_wait_u32(b_kvempty + 8 * ld_stage, ld_par);
+            load_next();
+          }
+        mbar_wait_u32(b_kvfull + 8 * qk_stage, kv_par);
+        ++tiles_used;
+      };
+      mbar_wait(&q_full, 0);
+      mbar_wait_u32(b_kvfull, 0);
+      tc_fence_after();
+      issue_qk();
+      for (int i = 0; i < n_blk; ++i) {
+        if (i + 1 < n_blk) {
+          if (qk_half == 0) need_tile();           // first block of a new K/V tile
+          mbar_wait_u32(b_sfree, i & 1);           // the softmax warpgroup holds S(i) in registers
+          tc_fence_after();
+          issue_qk();
+        }
+        if (x == 0) pump();
+        mbar_wait_u32(b_pfull, i & 1);
+        tc_fence_after();
+        const bool last_of_tile = pv_half == 1 || i + 1 == n_blk;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BLK / 16; ++k)
+            mma_ts(tX + TM_O, tX + TM_P + k * 8, desc(v_lo0 + pv_off + k * ((16 * ROWB) >> 4)), idesc_pv,
+                   (i > 0 || k > 0) ? 1u : 0u);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_ofull) : "memory");
+          if (last_of_tile)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_kvempty + 8 * pv_stage) : "memory");
+        }
+        __syncwarp();
+        pv_half ^= 1;
+        pv_off += HALF16;
+        if (pv_half == 0) {
+          pv_off += STAGE16 - 2 * HALF16;
+          if (++pv_stage == S) { pv_stage = 0; pv_off = 0; }
+        }
+        if (x == 0) pump();
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int x = (warp - 4) >> 2;
+    if (x < nq) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t tX = tmem + x * TM_STRIDE + ((uint32_t)(quarter * 32) << 16);
+      const float c = a.scale_log2e;
+      float m = -INFINITY, l = 0.f;
+      const uint32_t b_sfull = smem_u32(&s_full[x]), b_sfree = smem_u32(&s_free[x]);
+      const uint32_t b_pfull = smem_u32(&p_full[x]), b_ofull = smem_u32(&o_full[x]);
+      for (int i = 0; i < n_blk; ++i) {
+        uint32_t cur[BLK];
+        mbar_wait_u32(b_sfull, i & 1);
+        tc_fence_after();
+        tmem_ld_x32(tX, *reinterpret_cast<uint32_t(*)[32]>(&cur[0]));
+        tmem_ld_x32(tX + 32, *reinterpret_cast<uint32_t(*)[32]>(&cur[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_u32(b_sfree);   // tcgen05.wait::ld is warp-wide: every lane's scores are in registers
+        const int valid = a.Lk - (b0 + i) * BLK;
+        if (valid < BLK) {
+#pragma unroll
+          for (int k = 0; k < BLK; ++k)
+            if (k >= valid) cur[k] = 0xff800000u;   // -inf
+        }
+        float m4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m4[k] = fmaxf(__uint_as_float(cur[k]), __uint_as_float(cur[k + 4]));
+        if (!(DROP & 4)) {
+#pragma unroll
+        for (int k = 8; k < BLK; k += 8) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            m4[t] = fmaxf(m4[t], fmaxf(__uint_as_float(cur[k + t]), __uint_as_float(cur[k + t + 4])));
+        }
+        }
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        bool o_ready = false;                      // has this thread already observed P V(i - 1)?
+        if (__any_sync(0xffffffffu, (mx - m) * c > 8.0f)) {
+          const float m_new = fmaxf(m, mx);
+          const float alpha = fast_exp2((m - m_new) * c);      // first block: exp2(-inf) = 0
+          m = m_new;
+          l *= alpha;
+          if (i > 0) {                             // O <- O * alpha in TMEM
+            mbar_wait_u32(b_ofull, (i - 1) & 1);
+            tc_fence_after();
+            o_ready = true;
+#pragma unroll
+            for (int d0 = 0; d0 < D; d0 += 16) {
+              uint32_t r[16];
+              tmem_ld_x16(tX + TM_O + d0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 16; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
+              tmem_st_x16(tX + TM_O + d0, r);
+            }
+          }
+        }
+        const float nmc = -m * c;
+        float ls[8];
+#pragma unroll
+        for (int k = 0; k < BLK; k += 2) {
+          float x0, x1, p0, p1;
+          if (DROP & 1) { x0 = __uint_as_float(cur[k]); x1 = __uint_as_float(cur[k + 1]); }
+          else ffma2(x0, x1, __uint_as_float(cur[k]), __uint_as_float(cur[k + 1]), c, c, nmc, nmc);
+          if (DROP & 16) { p0 = x0; p1 = x1; } else
+          if ((PMASK >> ((k >> 1) & 15)) & 1) {
+            x0 = fmaxf(x0, -120.f); x1 = fmaxf(x1, -120.f);
+            float t0_, t1_, n0, n1, f0, f1;
+            fadd2(t0_, t1_, x0, x1, 12582912.f, 12582912.f);
+            fadd2(n0, n1, t0_, t1_, -12582912.f, -12582912.f);
+            fadd2(f0, f1, x0, x1, -n0, -n1);
+            ffma2(p0, p1, f0, f1, 0.05517164617776871f, 0.05517164617776871f, 0.2426111251115799f, 0.2426111251115799f);
+            ffma2(p0, p1, p0, p1, f0, f1, 0.6932609677314758f, 0.6932609677314758f);
+            ffma2(p0, p1, p0, p1, f0, f1, 0.9999280571937561f, 0.9999280571937561f);
+            p0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0_) << 23));
+            p1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1_) << 23));
+          } else {
+            p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+          }
+          const int j = (k >> 1) & 3;
+          if (k < 8) { ls[2 * j] = p0; ls[2 * j + 1] = p1; }
+          else if (!(DROP & 2)) fadd2(ls[2 * j], ls[2 * j + 1], ls[2 * j], ls[2 * j + 1], p0, p1);
+          if (DROP & 8) { cur[k >> 1] = __float_as_uint(p0) ^ __float_as_uint(p1); } else {
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          cur[k >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+          }
+        }
+        l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+        if (i > 0 && !o_ready) {                   // the P columns were last read by P V(i - 1)
+          mbar_wait_u32(b_ofull, (i - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_x16(tX + TM_P, *reinterpret_cast<uint32_t(*)[16]>(&cur[0]));
+        tmem_st_x16(tX + TM_P + 16, *reinterpret_cast<uint32_t(*)[16]>(&cur[16]));
+        tmem_st_wait();
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_u32(b_pfull);   // tcgen05.wait::st is warp-wide
+      }
+      mbar_wait_u32(b_ofull, (n_blk - 1) & 1);
+      tc_fence_after();
+      const int qi = q0 + x * 128 + row;
+      if (part >= 0) {                             // partial result of one key range: unnormalised O, m, l
+        const size_t pr = ((size_t)(unit - a.split_from) * a.nsplit + part) * (NT * 128) + x * 128 + row;
+        float* wo = a.ws_o + pr * D;
+#pragma unroll
+        for (int d0 = 0; d0 < D; d0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tX + TM_O + d0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; k += 4)
+            *reinterpret_cast<uint4*>(wo + d0 + k) = make_uint4(r[k], r[k + 1], r[k + 2], r[k + 3]);
+        }
+        *reinterpret_cast<float2*>(a.ws_ml + pr * 2) = make_float2(m, l);
+      } else {
+        const float inv = 1.0f / l;
+        __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h;
+#pragma unroll
+        for (int d0 = 0; d0 < D; d0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tX + TM_O + d0, r);
+          tmem_ld_wait();
+          if (qi < a.Lq) {
+#pragma unroll
+            for (int k = 0; k < 16; k += 8) {
+              __align__(16) __half hh[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) hh[t] = __float2half_rn(__uint_as_float(r[k + t]) * inv);
+              *reinterpret_cast<uint4*>(op + d0 + k) = *reinterpret_cast<uint4*>(hh);
+            }
+          }
+        }
+      }
+    }
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------
 // Short-sequence attention on CUDA cores (L <= 32): the DiT temporal self-attention
 // (reference model/dit.py:254-260: sequences of T = 24 frames per latent token, d = 32).
 // 0.6 GFLOP per block -- latency-, not tensor-bound; a 128-row MMA tile would be 81 % padding.
@@ -1405,7 +1743,7 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnArgs a, int n
 static float* g_attn_ws = nullptr;
 static size_t g_attn_ws_bytes = 0;
 
-template <int POLY, bool TRACE, bool PERSIST = false>
+template <int POLY, bool TRACE, bool PERSIST = false, int V8 = 0, int DROP = 0>
 static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                         int Nb, cudaStream_t st) {
   constexpr int SMEM = ((PERSIST ? 8 : 4) + 2 * kAttnStages) * 128 * 32 * 2 + 1024;
@@ -1413,6 +1751,7 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
   if (!configured) {
     cudaError_t e;
     if constexpr (PERSIST) e = cudaFuncSetAttribute(attn_fwd7_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    else if constexpr (V8 != 0) e = cudaFuncSetAttribute(attn_fwd8_kernel<V8, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     else e = cudaFuncSetAttribute(attn_fwd6_kernel<POLY, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return GVF_ERR_CUDA;
     configured = true;
@@ -1450,6 +1789,9 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
   if constexpr (PERSIST) {
     const dim3 grid(n_items < num_sms ? n_items : num_sms);
     if (launch_pdl(attn_fwd7_kernel<POLY>, grid, dim3(640), SMEM, st, mq, mk, mv, b, n_items) != cudaSuccess) return GVF_ERR_CUDA;
+  } else if constexpr (V8 != 0) {
+    const dim3 grid(n_items);
+    if (launch_pdl(attn_fwd8_kernel<V8, DROP>, grid, dim3(640), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
   } else {
     const dim3 grid(n_items);
     if (launch_pdl(attn_fwd6_kernel<POLY, TRACE>, grid, dim3(640), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
@@ -1550,18 +1892,41 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   a.kv_batch_mul = kv_shared ? 0 : 1;
   a.scale_log2e = scale * 1.4426950408889634f;
   a.dbg = g_attn_dbg & 0xff;
-  a.stagger = (g_attn_dbg >> 8) * 100;
+  a.stagger = ((g_attn_dbg >> 8) & 0xff) * 100;
   a.trace = g_attn_trace;
   // Kernel choice.  d = 32 with more than two query tiles per (batch, head): v6 (four softmax warpgroups, a quarter
   // of the exponentials on the FMA pipe); otherwise v4 with the MUFU ping-pong.  gvf_attn_set_debug overrides
   // (tools/attn_experiments.py): 0x10 v4 plain, 0x30 v4 ping-pong, 0x80 v6 MUFU only, low nibble 4 = polynomial share.
   const int sel = g_attn_dbg & 0xf0;
   const bool poly = (g_attn_dbg & 0xf) == 4;
-  if (D == 32 && (sel == 0x80 || sel == 0x90 || (sel == 0 && Lq > 256)))
+  if (D == 32 && (sel == 0x80 || sel == 0x90 || sel == 0xa0 || (sel == 0 && Lq > 256)))
   {
     if (a.trace || a.stagger > 0)   // instrumented build (tools/attn_experiments.py)
       return (poly || sel == 0) ? launch_attn6<4, true>(mq, mk, mv, a, Nb, st) : launch_attn6<0, true>(mq, mk, mv, a, Nb, st);
     const int share = g_attn_dbg & 0xf;
+    // v8 (warp-uniform MMA issuers) is the default; 0x80 selects v6, 0x90 the persistent v7 (A/B runs).  Low nibble =
+    // share of the exponentials evaluated on the FMA pipe.  MEASURED on B200 (tools/attn_variants.py, static / image /
+    // spatial us): MUFU only 259 / 107 / 49.6, 1/8 238 / 101 / 47.6, 3/16 226.7 / 96.7 / 45.5, 1/4 227.7 / 96.5 / 45.5,
+    // 5/16 231.9 / 98.5, 3/8 239 / 100.8, 1/2 253 / 105 (v6 at its best mix: 252 / 103 / 49.6).
+    if (sel == 0 || sel == 0xa0) {
+      const int drop = (g_attn_dbg >> 16) & 0xff;    // timing-only ablation builds (tools/attn_variants.py; WRONG results)
+#define GVF_V8(M) return launch_attn6<0, false, false, 0x10000 | (M)>(mq, mk, mv, a, Nb, st)
+#define GVF_V8D(DR) if (drop == DR) return launch_attn6<0, false, false, 0x18888, DR>(mq, mk, mv, a, Nb, st)
+      if (drop == 31) return launch_attn6<0, false, false, 0x10000, 31>(mq, mk, mv, a, Nb, st);
+      if (drop == 16) return launch_attn6<0, false, false, 0x10000, 16>(mq, mk, mv, a, Nb, st);
+      GVF_V8D(1); GVF_V8D(2); GVF_V8D(3); GVF_V8D(4); GVF_V8D(7); GVF_V8D(8);
+      switch (share) {
+        case 1: GVF_V8(0x0000);
+        case 2: GVF_V8(0xaaaa);     // 1/2
+        case 3: GVF_V8(0xa8a8);     // 3/8
+        case 5: GVF_V8(0xa888);     // 5/16
+        case 6: GVF_V8(0x8880);     // 3/16
+        case 8: GVF_V8(0x8080);     // 1/8
+        default: GVF_V8(0x8888);    // 1/4
+      }
+#undef GVF_V8
+#undef GVF_V8D
+    }
     // default: every 8th pair of exponentials on the FMA pipe (bench: 282.0 ms / object; MUFU only 285.6; every
     // 4th pair 285.6).  Low nibble of the debug word: 1 MUFU only, 4 every 4th pair.
     // Short key ranges (spatial self-attention, 512 keys) stay MUFU only: 49.5 vs 53.5 us.

@@ -90,7 +90,7 @@ class DiTEngine:
         self.b_mod = _b(torch.cat([b.detach().float().cpu() for b in mods_b], 0), dev)
         self.R = self.w_mod.shape[0]          # nblk * 9C + 2C
         assert self.R == self.nblk * 9 * C + 2 * C
-        self._ws_key = None
+        self._ws = {}             # (Bx, T, N) -> activation buffers; never freed while graphs may point at them
         self._pools = {}          # (kind, slot, shape) -> persistent buffers (stable pointers for CUDA graphs)
         self._graphs = {}
         self.use_graphs = True
@@ -176,21 +176,26 @@ class DiTEngine:
 
     # ------------------------------------------------------------------ forward
     def _workspace(self, Bx, T, N):
+        """One set of activation buffers PER shape key, kept for the engine's lifetime: a captured CUDA graph
+        (forward_graphed) holds raw pointers into the workspace it was captured with, so a shape change must
+        never free or re-use another shape's buffers (1-branch <-> 3-branch CFG alternation on one engine)."""
         key = (Bx, T, N)
-        if self._ws_key != key:
+        ws = self._ws.get(key)
+        if ws is None:
             M, C, dev = Bx * T * N, self.C, self.dev
-            self.X = torch.empty((M, C), dtype=F32, device=dev)
-            self.A16 = torch.empty((M, C), dtype=F16, device=dev)
-            self.QKV = torch.empty((M, 3 * C), dtype=F16, device=dev)
-            self.Q = torch.empty((M, C), dtype=F16, device=dev)
-            self.AO = torch.empty((M, C), dtype=F16, device=dev)
-            self.H1 = torch.empty((M, self.blocks[0]["w1"].shape[0]), dtype=F16, device=dev)
-            self.temb = torch.empty((Bx, C), dtype=F16, device=dev)
-            self.stemb = torch.empty((Bx, C), dtype=F16, device=dev)
-            self.mod = torch.empty((Bx, self.R), dtype=F16, device=dev)
-            self.vout = torch.empty((M, self.Cout), dtype=F32, device=dev)
-            self._ws_key = key
-        return self.X
+            ws = dict(
+                X=torch.empty((M, C), dtype=F32, device=dev),
+                A16=torch.empty((M, C), dtype=F16, device=dev),
+                QKV=torch.empty((M, 3 * C), dtype=F16, device=dev),
+                Q=torch.empty((M, C), dtype=F16, device=dev),
+                AO=torch.empty((M, C), dtype=F16, device=dev),
+                H1=torch.empty((M, self.blocks[0]["w1"].shape[0]), dtype=F16, device=dev),
+                temb=torch.empty((Bx, C), dtype=F16, device=dev),
+                stemb=torch.empty((Bx, C), dtype=F16, device=dev),
+                mod=torch.empty((Bx, self.R), dtype=F16, device=dev),
+                vout=torch.empty((M, self.Cout), dtype=F32, device=dev))
+            self._ws[key] = ws
+        return ws
 
     def _qkv(self, A16, p, QKV):
         """to_qkv + q/k MultiHeadRMSNorm (model/attention/modules.py:113-125)."""
@@ -208,10 +213,10 @@ class DiTEngine:
         C, H, d, R = self.C, self.H, self.d, self.R
         M, TN = Bx * T * N, T * N
         scale = 1.0 / math.sqrt(d)
-        X = self._workspace(Bx, T, N)
-        A16, QKV, Q, AO, H1, mod = self.A16, self.QKV, self.Q, self.AO, self.H1, self.mod
+        ws = self._workspace(Bx, T, N)
+        X, A16, QKV, Q, AO, H1, mod = ws["X"], ws["A16"], ws["QKV"], ws["Q"], ws["AO"], ws["H1"], ws["mod"]
         ops.dit_modulation(t, self.t_w0, self.t_b0, self.t_w2, self.t_b2, self.w_mod, self.b_mod,
-                           self.temb, self.stemb, mod)
+                           ws["temb"], ws["stemb"], mod)
         xf = x.reshape(M, Cin)
         for b in range(Bx):
             ops.small_linear(xf[b * TN:(b + 1) * TN], self.w_in, self.b_in, out_f16=False, add=pos[b],
@@ -285,5 +290,5 @@ class DiTEngine:
                            rows_per_batch=TN)
         fb = self.nblk * 9 * C
         ops.dit_final_layer(X, mod[:, fb:fb + C], mod[:, fb + C:fb + 2 * C], R, TN, self.w_fin, self.b_fin,
-                            out=self.vout)
-        return self.vout.view(Bx, T, N, self.Cout)
+                            out=ws["vout"])
+        return ws["vout"].view(Bx, T, N, self.Cout)

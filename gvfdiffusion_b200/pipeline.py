@@ -123,14 +123,26 @@ class GVFPipeline:
             z = ops.affine_lastdim(latents.contiguous(), a=deformation_std, b=deformation_mean)
         return self.vae.decode(z.reshape(B * T, N, C), obj.static_gs[None])[0]
 
-    def render(self, obj, delta, extrinsics, intrinsics, out=None):
+    def render(self, obj, delta, extrinsics, intrinsics, out=None, check_overflow=True):
         """delta [F,P,14], extrinsics [F,4,4] -> rgba [F,4,H,W] fp32 (utils/inference_utils.py:256-269
-        with one camera per frame)."""
+        with one camera per frame).  The reference rasteriser sizes its binning buffers from the actual
+        tile-instance count; ours works in a caller-owned workspace, so the count is checked: True = one
+        host sync per call and a transparent re-run with a larger workspace; "defer" = no sync here, the
+        caller must call `confirm_render()` after its own synchronisation (raises if splats were dropped)."""
         cams, tfx, tfy = R.pack_cameras(extrinsics, intrinsics, self.near, self.far)
         prm = R.make_params(self.res, self.res, tfx, tfy, self.const, self.kernel_size, 1.0, self.bg)
         rgba, _ = self.rz.forward(prm, obj.arrays, delta.contiguous(), cams.to(self.dev), want_radii=False,
-                                  out=out, check_overflow=False)
+                                  out=out, check_overflow=check_overflow)
         return rgba
+
+    def confirm_render(self):
+        """Verdict on the last `render(check_overflow="defer")`: raises if the workspace capacity was exceeded
+        (that image is missing splats); the workspace of the next render is already enlarged."""
+        st = self.rz.deferred_status()
+        if st is not None and st[1]:
+            raise RuntimeError(f"rasteriser workspace overflow: {st[0]} tile instances > capacity; the frames of "
+                               "that render dropped splats -- render again (the workspace has been enlarged)")
+        return st
 
     def render_views(self, obj, delta, extrinsics, intrinsics, timesteps_per_call=1, out=None):
         """The reference's visualisation loop (utils/inference_utils.py:243-283): every timestep of `delta`
@@ -151,7 +163,7 @@ class GVFPipeline:
         for t0 in range(0, T, n):
             t1 = min(T, t0 + n)
             rgba, _ = self._rz_views.forward(prm, obj.arrays, delta[t0:t1], cams.repeat(t1 - t0, 1), want_radii=False,
-                                             views_per_delta=V)
+                                             views_per_delta=V, check_overflow=True)
             R.rgba_to_u8(rgba, out[t0:t1].view(-1, self.res, self.res, 3))
         return out
 

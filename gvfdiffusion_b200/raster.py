@@ -76,6 +76,7 @@ class Rasterizer:
         self._ws = None
         self.cap = 0
         self.hint = 0               # capacity learned by an earlier rasteriser of the same scene (see node())
+        self._deferred = None       # (event, pinned int32[4]) of a forward(check_overflow="defer")
 
     def node(self):
         """A rasteriser with its OWN workspace for one autograd node: backward reads the splat records, sorted
@@ -110,11 +111,29 @@ class Rasterizer:
         s = self.buffer("status", torch.int32, 4).cpu()
         return int(s[0]) & 0xffffffff, bool(s[1]), int(s[2])
 
+    def deferred_status(self):
+        """(num_rendered, overflow) of the last forward(check_overflow="defer"), or None.  Waits for that
+        forward's status copy only (an event), not for the stream."""
+        if self._deferred is None:
+            return None
+        ev, host = self._deferred
+        ev.synchronize()
+        self._deferred = None
+        R, overflow = int(host[0]) & 0xffffffff, bool(host[1])
+        if overflow:                            # the NEXT forward gets a workspace that fits
+            self.hint = max(self.hint, int(R * 1.25) + 1024)
+        return R, overflow
+
     def forward(self, prm, arrays, delta, cams, activated=False, subpixel_offset=None,
                 want_radii=True, out=None, check_overflow=True, views_per_delta=1):
         """arrays = (xyz, dc, scaling, rotation, opacity) fp32 contiguous device tensors.
         Returns rgba (F,4,H,W) fp32 and radii (F,P) int32 (or None).  views_per_delta = V > 1: the F frames
-        are (timestep, camera) pairs ordered timestep-major and delta is [F / V, P, 14] (gvf_raster_forward_views)."""
+        are (timestep, camera) pairs ordered timestep-major and delta is [F / V, P, 14] (gvf_raster_forward_views).
+        check_overflow: True = read the status word back (one host sync) and re-run with a larger workspace
+        when the tile-instance capacity was exceeded (upstream sizes its buffers from the count, so it never
+        drops a splat); "defer" = copy the status to pinned memory behind the kernels and let the caller ask
+        `deferred_status()` after its own synchronisation point; False = unchecked (benchmarks of the kernels
+        alone; the kernels clamp to `cap`, so memory stays safe but splats may be dropped)."""
         L = _lib.lib()
         F = cams.shape[0]
         P = arrays[0].shape[-2] if arrays[0].dim() >= 2 else arrays[0].shape[0]
@@ -140,6 +159,13 @@ class Rasterizer:
                                           self.cap, _lib.current_stream())
             _lib.check(st, "gvf_raster_forward")
             if not check_overflow:
+                return rgba, radii
+            if check_overflow == "defer":
+                host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+                host.copy_(self.buffer("status", torch.int32, 4), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._deferred = (ev, host)
                 return rgba, radii
             R, overflow, _ = self.status()
             if not overflow:
