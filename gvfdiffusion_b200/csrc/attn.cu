@@ -713,12 +713,6 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 // per thread (4 arrivals instead of 128 shared-memory atomics per hand-off).
 //   20 warps: 0-3 MMA issuers (tile = warp; warp 0 also keeps the K/V ring going), 4-19 softmax (thread = query
 //   row = TMEM lane).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
 template <int PMASK, int DROP>
 __global__ void __launch_bounds__(640, 1)
 attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -738,7 +732,7 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   uint8_t* sQ = smem;                              // NT tiles
   uint8_t* sKV = smem + NT * TILE_BYTES;           // S x (K tile, V tile)
 
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const int item = blockIdx.x;
   int unit = item, part = -1;

@@ -410,7 +410,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int A_BYTES = kBM * kBK * 2, W_BYTES = WROWS * kBK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
   const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
   uint8_t* stg_base = smem + STAGES * STAGE_BYTES;              // 8 warps x 2 buffers x 4 KB, 1 KB aligned
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int kblocks = (K + kBK - 1) / kBK;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + NCTA * kBM - 1) / (NCTA * kBM);   // pair tiles for NCTA = 2
   const int num_tiles = tiles_n * tiles_m;
@@ -452,52 +452,72 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int it = 0;
-      int skip = (NCTA == 1) ? (kblocks < STAGES ? kblocks : STAGES) : 0;     // requested in the prologue
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-        const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          if (skip > 0) { --skip; continue; }
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          uint8_t* st = smem + s * STAGE_BYTES;
-          if constexpr (NCTA == 2) {
-            // both CTAs' bytes are credited to the leader's full barrier, which expects the sum
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
-            tma_load_2d_2cta(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
-            tma_load_2d_2cta(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN + (int)rank * WROWS);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-            tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
-            tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
+    // TMA producer: all 32 lanes run the (warp-uniform) loop, one elected lane issues -- see elect_one()
+    int s = 0;
+    uint32_t ph = 0;                               // parity of full / empty for the current pass over the ring
+    int skip = (NCTA == 1) ? (kblocks < STAGES ? kblocks : STAGES) : 0;     // requested in the prologue
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if (skip > 0) --skip;
+        else {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (elect_one()) {
+            uint8_t* st = smem + s * STAGE_BYTES;
+            if constexpr (NCTA == 2) {
+              // both CTAs' bytes are credited to the leader's full barrier, which expects the sum
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+              tma_load_2d_2cta(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+              tma_load_2d_2cta(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN + (int)rank * WROWS);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+              tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+              tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
+            }
           }
+          __syncwarp();
         }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    // MMA issuer (leader CTA of a pair): warp-uniform loop; the descriptors' high words are constants, the low
+    // words (address >> 4 | LBO field) advance by adds; only tcgen05.mma / commit sit behind elect.sync
+    if (rank == 0) {
       const uint32_t idesc = make_idesc_f16(kBM * NCTA, BN, 0, 0);
-      int it = 0, lt = 0;
+      const uint32_t d_hi = (uint32_t)(make_smem_desc(0, 16, 1024, SWZ_128B) >> 32);
+      const uint32_t a_lo0 = (uint32_t)make_smem_desc(smem_u32(smem), 16, 1024, SWZ_128B);
+      constexpr uint32_t STAGE16 = STAGE_BYTES >> 4, A16 = A_BYTES >> 4;
+      const uint32_t b_full = smem_u32(&full_bar[0]), b_empty = smem_u32(&empty_bar[0]);
+      int s = 0, lt = 0;
+      uint32_t ph = 0, s_lo = a_lo0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++lt) {
         const int acc = lt & 1;
         mbar_wait(&tempty_bar[acc], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        const uint32_t d_tmem = tmem + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait_u32(b_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), w0 = a0 + A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a0 + k * 32, 16, 1024, SWZ_128B);
-            const uint64_t wd = make_smem_desc(w0 + k * 32, 16, 1024, SWZ_128B);
-            if constexpr (NCTA == 2) mma_ss_2cta(tmem + acc * BN, ad, wd, idesc, (kb | k) != 0);
-            else mma_ss(tmem + acc * BN, ad, wd, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t ad = ((uint64_t)d_hi << 32) | (s_lo + 2 * k);
+              const uint64_t wd = ((uint64_t)d_hi << 32) | (s_lo + A16 + 2 * k);
+              if constexpr (NCTA == 2) mma_ss_2cta(d_tmem, ad, wd, idesc, (kb | k) != 0);
+              else mma_ss(d_tmem, ad, wd, idesc, (kb | k) != 0);
+            }
+            if constexpr (NCTA == 2) tc_commit_2cta(&empty_bar[s]);
+            else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_empty + 8 * s) : "memory");
           }
-          if constexpr (NCTA == 2) tc_commit_2cta(&empty_bar[s]); else tc_commit(&empty_bar[s]);
+          __syncwarp();
+          s_lo += STAGE16;
+          if (++s == STAGES) { s = 0; ph ^= 1; s_lo = a_lo0; }
         }
-        if constexpr (NCTA == 2) tc_commit_2cta(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if constexpr (NCTA == 2) tc_commit_2cta(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -25,6 +25,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// One lane of a converged warp (elect.sync).  The tcgen05.mma / commit / TMA issue loops run with all 32
+// lanes on warp-uniform values and put only the instruction itself behind this predicate: inside
+// `if (lane == 0) { ... }` ptxas holds every operand in per-thread registers and wraps each tcgen05 / TMA
+// instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~12 dependent instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_id() {      // warp index the compiler can prove warp-uniform
+  return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
