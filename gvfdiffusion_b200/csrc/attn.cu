@@ -713,11 +713,11 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 // per thread (4 arrivals instead of 128 shared-memory atomics per hand-off).
 //   20 warps: 0-3 MMA issuers (tile = warp; warp 0 also keeps the K/V ring going), 4-19 softmax (thread = query
 //   row = TMEM lane).
-template <int PMASK, int DROP>
-__global__ void __launch_bounds__(640, 1)
+template <int PMASK, int DROP, bool TRACE, int NT>
+__global__ void __launch_bounds__(NT * 160, NT == 2 ? 2 : 1)
 attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
-  constexpr int D = 32, BLK = 64, NT = 4;
+  constexpr int D = 32, BLK = 64;
   constexpr int ROWB = D * 2;
   constexpr int TILE_BYTES = 128 * ROWB;
   constexpr uint64_t SWZ = SWZ_64B;
@@ -750,6 +750,7 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const int b0 = 2 * t0;
   const int n_blk = min((a.Lk + BLK - 1) / BLK, 2 * t1) - b0;
 
+  if (TRACE && a.trace && threadIdx.x == 0 && item == 0) a.trace[240] = clock64();
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
     for (int i = 0; i < S; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], nq); }
@@ -771,7 +772,7 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     }
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_s, 512);
+    tmem_alloc(&tmem_base_s, NT * 128);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -779,13 +780,17 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   tc_fence_after();
   pdl_wait();
   const uint32_t tmem = tmem_base_s;
+  if (TRACE && a.trace && threadIdx.x == 0 && item == 0) a.trace[241] = clock64();
 
-  if (warp < 4) {
+  if (warp < NT) {
     // ------------------------------------------------------------------ MMA issuer of tile x (all lanes, uniform)
     // (a 21st warp for the K/V ring does not fit: the register file is per SM sub-partition, and one issuer
     // at 32 plus four softmax warps at 112 registers already fill its 16 K entries -- tile 0's issuer keeps
     // the ring going between its MMA batches, with warp-uniform polling)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    // NT = 2 (two CTAs per SM): no register re-distribution -- a CTA's ten warps put three warps on two of the SM
+    // sub-partitions and two on the others, and the per-sub-partition register pool of the pair without an
+    // issuer warp has nothing to hand to its softmax warps (setmaxnreg.inc never returns); 96 registers for all.
+    if constexpr (NT == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     const int x = warp;
     if (x < nq) {
       const uint32_t idesc_qk = make_idesc_f16(128, BLK, 0, 0);
@@ -858,17 +863,22 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_wait(&q_full, 0);
       mbar_wait_u32(b_kvfull, 0);
       tc_fence_after();
+      if (TRACE && a.trace && item == 0 && x == 0 && lane == 0) a.trace[242] = clock64();
       issue_qk();
+      const bool tri = TRACE && a.trace && item == 0 && x == 0 && lane == 0;
       for (int i = 0; i < n_blk; ++i) {
         if (i + 1 < n_blk) {
           if (qk_half == 0) need_tile();           // first block of a new K/V tile
+          if (tri && i < 16) a.trace[i * 16 + 9] = clock64();
           mbar_wait_u32(b_sfree, i & 1);           // the softmax warpgroup holds S(i) in registers
           tc_fence_after();
+          if (tri && i < 16) a.trace[i * 16 + 7] = clock64();
           issue_qk();
         }
         if (x == 0) pump();
         mbar_wait_u32(b_pfull, i & 1);
         tc_fence_after();
+        if (tri && i < 16) a.trace[i * 16 + 8] = clock64();
         const bool last_of_tile = pv_half == 1 || i + 1 == n_blk;
         if (elect_one()) {
 #pragma unroll
@@ -890,8 +900,8 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    const int x = (warp - 4) >> 2;
+    if constexpr (NT == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int x = (warp - NT) >> 2;               // NT = 2: warps 2-5 / 6-9 = tiles 0 / 1, TMEM lane quarter = warp & 3
     if (x < nq) {
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;
@@ -900,15 +910,19 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       float m = -INFINITY, l = 0.f;
       const uint32_t b_sfull = smem_u32(&s_full[x]), b_sfree = smem_u32(&s_free[x]);
       const uint32_t b_pfull = smem_u32(&p_full[x]), b_ofull = smem_u32(&o_full[x]);
+      const bool tr = TRACE && a.trace && lane == 0 && item == 0 && quarter == 0;
       for (int i = 0; i < n_blk; ++i) {
         uint32_t cur[BLK];
+        if (tr && i < 16) a.trace[i * 16 + x] = clock64();
         mbar_wait_u32(b_sfull, i & 1);
         tc_fence_after();
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 10] = clock64();
         tmem_ld_x32(tX, *reinterpret_cast<uint32_t(*)[32]>(&cur[0]));
         tmem_ld_x32(tX + 32, *reinterpret_cast<uint32_t(*)[32]>(&cur[32]));
         tmem_ld_wait();
         tc_fence_before();
         if (lane == 0) mbar_arrive_u32(b_sfree);   // tcgen05.wait::ld is warp-wide: every lane's scores are in registers
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 4] = clock64();
         const int valid = a.Lk - (b0 + i) * BLK;
         if (valid < BLK) {
 #pragma unroll
@@ -949,6 +963,7 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           }
         }
         const float nmc = -m * c;
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 12] = clock64();
         float ls[8];
 #pragma unroll
         for (int k = 0; k < BLK; k += 2) {
@@ -979,16 +994,20 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           }
         }
         l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 5] = clock64();
         if (i > 0 && !o_ready) {                   // the P columns were last read by P V(i - 1)
           mbar_wait_u32(b_ofull, (i - 1) & 1);
           tc_fence_after();
         }
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 11] = clock64();
         tmem_st_x16(tX + TM_P, *reinterpret_cast<uint32_t(*)[16]>(&cur[0]));
         tmem_st_x16(tX + TM_P + 16, *reinterpret_cast<uint32_t(*)[16]>(&cur[16]));
         tmem_st_wait();
         tc_fence_before();
         if (lane == 0) mbar_arrive_u32(b_pfull);   // tcgen05.wait::st is warp-wide
+        if (tr && i < 16 && x == 0) a.trace[i * 16 + 6] = clock64();
       }
+      if (tr && x == 0) a.trace[13] = clock64();
       mbar_wait_u32(b_ofull, (n_blk - 1) & 1);
       tc_fence_after();
       const int qi = q0 + x * 128 + row;
@@ -1026,10 +1045,12 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       }
     }
   }
+  if (TRACE && a.trace && threadIdx.x == 128 && item == 0) a.trace[243] = clock64();   // tile 0's first softmax thread: output stored
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, NT * 128);
+  if (TRACE && a.trace && threadIdx.x == 0 && item == 0) a.trace[244] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1737,15 +1758,15 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnArgs a, int n
 static float* g_attn_ws = nullptr;
 static size_t g_attn_ws_bytes = 0;
 
-template <int POLY, bool TRACE, bool PERSIST = false, int V8 = 0, int DROP = 0>
+template <int POLY, bool TRACE, bool PERSIST = false, int V8 = 0, int DROP = 0, int NT = 4>
 static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                         int Nb, cudaStream_t st) {
-  constexpr int SMEM = ((PERSIST ? 8 : 4) + 2 * kAttnStages) * 128 * 32 * 2 + 1024;
+  constexpr int SMEM = ((PERSIST ? 8 : NT) + 2 * kAttnStages) * 128 * 32 * 2 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e;
     if constexpr (PERSIST) e = cudaFuncSetAttribute(attn_fwd7_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    else if constexpr (V8 != 0) e = cudaFuncSetAttribute(attn_fwd8_kernel<V8, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    else if constexpr (V8 != 0) e = cudaFuncSetAttribute(attn_fwd8_kernel<V8, DROP, TRACE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     else e = cudaFuncSetAttribute(attn_fwd6_kernel<POLY, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return GVF_ERR_CUDA;
     configured = true;
@@ -1757,7 +1778,7 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   AttnArgs b = a;
-  b.gx = (a.Lq + 511) / 512;
+  b.gx = (a.Lq + 128 * NT - 1) / (128 * NT);
   const int units = b.gx * a.H * Nb;
   b.split_from = units;
   b.nsplit = 1;
@@ -1769,7 +1790,7 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
   int n_split_units = 0;
   // measured: pays for the 4096-key static cross-attention (280 -> 261 us), not for 1370 keys (110 -> 120 us:
   // three prologues and the merge cost more than the shorter wave saves)
-  if (!TRACE && g_attn_ws && units > num_sms && rem > 0 && rem * NSPLIT <= 2 * num_sms && n_kv >= 16) {
+  if (!TRACE && NT == 4 && g_attn_ws && units > num_sms && rem > 0 && rem * NSPLIT <= 2 * num_sms && n_kv >= 16) {
     const size_t rows = (size_t)rem * NSPLIT * 512;
     if (rows * (32 + 2) * sizeof(float) <= g_attn_ws_bytes) {
       n_split_units = rem;
@@ -1785,7 +1806,7 @@ static int launch_attn6(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
     if (launch_pdl(attn_fwd7_kernel<POLY>, grid, dim3(640), SMEM, st, mq, mk, mv, b, n_items) != cudaSuccess) return GVF_ERR_CUDA;
   } else if constexpr (V8 != 0) {
     const dim3 grid(n_items);
-    if (launch_pdl(attn_fwd8_kernel<V8, DROP>, grid, dim3(640), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
+    if (launch_pdl(attn_fwd8_kernel<V8, DROP, TRACE, NT>, grid, dim3(NT * 160), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
   } else {
     const dim3 grid(n_items);
     if (launch_pdl(attn_fwd6_kernel<POLY, TRACE>, grid, dim3(640), SMEM, st, mq, mk, mv, b) != cudaSuccess) return GVF_ERR_CUDA;
@@ -1895,7 +1916,10 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   const bool poly = (g_attn_dbg & 0xf) == 4;
   if (D == 32 && (sel == 0x80 || sel == 0x90 || sel == 0xa0 || (sel == 0 && Lq > 256)))
   {
-    if (a.trace || a.stagger > 0)   // instrumented build (tools/attn_experiments.py)
+    if (a.trace && (sel == 0 || sel == 0xa0))        // instrumented v8 (tools/attn_trace.py), no key-range split
+      return (g_attn_dbg & 0xf) == 1 ? launch_attn6<0, true, false, 0x10000>(mq, mk, mv, a, Nb, st)
+                                     : launch_attn6<0, true, false, 0x18888>(mq, mk, mv, a, Nb, st);
+    if (a.trace)   // instrumented build (tools/attn_experiments.py)
       return (poly || sel == 0) ? launch_attn6<4, true>(mq, mk, mv, a, Nb, st) : launch_attn6<0, true>(mq, mk, mv, a, Nb, st);
     const int share = g_attn_dbg & 0xf;
     // v8 (warp-uniform MMA issuers) is the default; 0x80 selects v6, 0x90 the persistent v7 (A/B runs).  Low nibble =
@@ -1906,6 +1930,9 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
       const int drop = (g_attn_dbg >> 16) & 0xff;    // timing-only ablation builds (tools/attn_variants.py; WRONG results)
 #define GVF_V8(M) return launch_attn6<0, false, false, 0x10000 | (M)>(mq, mk, mv, a, Nb, st)
 #define GVF_V8D(DR) if (drop == DR) return launch_attn6<0, false, false, 0x18888, DR>(mq, mk, mv, a, Nb, st)
+      if (g_attn_dbg & 0x10000000)                   // two-tile CTAs, two CTAs per SM
+        return share == 1 ? launch_attn6<0, false, false, 0x10000, 0, 2>(mq, mk, mv, a, Nb, st)
+                          : launch_attn6<0, false, false, 0x18888, 0, 2>(mq, mk, mv, a, Nb, st);
       if (drop == 31) return launch_attn6<0, false, false, 0x10000, 31>(mq, mk, mv, a, Nb, st);
       if (drop == 16) return launch_attn6<0, false, false, 0x10000, 16>(mq, mk, mv, a, Nb, st);
       GVF_V8D(1); GVF_V8D(2); GVF_V8D(3); GVF_V8D(4); GVF_V8D(7); GVF_V8D(8);
