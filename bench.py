@@ -106,95 +106,77 @@ def reference_betas():
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_baseline(threads=None):
-    """The oracle port of the same path on the host cores, bounded sample, extrapolated:
-    1 of 12 DiT blocks at the full shape (x12 blocks x32 NFE), 1 of 12 VAE latent layers (x12) + the
-    decoder cross-attention on 1 of 24 frames (x24), 2 of 24 raster frames (x12)."""
+def cpu_sample(threads=None):
+    """ONE measured sample of the oracle port on the host cores, nothing sliced: a full NFE (12 DiT blocks at the
+    full shape incl. the image / static projections the reference recomputes every call), the full motion-VAE
+    decode (12 latent layers, the decoder cross-attention of all 24 frames x 16 384 queries) and all 24 raster
+    frames.  Only the factor 32 over identical NFEs is extrapolated.  -> (t_nfe, t_decode, t_raster) seconds."""
     import numpy as np
     from gvfdiffusion_b200 import synthetic as S
     from oracle import dit as ODIT, gaussian as OG, raster as OR, vae as OVAE
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    g = torch.Generator().manual_seed(0)
-    C, H = 512, 16
-    rnd = lambda *s: torch.randn(*s, generator=g) * 0.02
-    sd = {}
-    p = "blocks.0."
-    for n, (o, i) in {"adaLN_modulation.1": (6 * C, C), "adaLN_modulation_temporal.1": (3 * C, C),
-                      "spatial_self_attn.to_qkv": (3 * C, C), "spatial_self_attn.to_out": (C, C),
-                      "temporal_self_attn.to_qkv": (3 * C, C), "temporal_self_attn.to_out": (C, C),
-                      "image_cross_attn.to_q": (C, C), "image_cross_attn.to_kv": (2 * C, C), "image_cross_attn.to_out": (C, C),
-                      "static_cross_attn.to_q": (C, C), "static_cross_attn.to_kv": (2 * C, C), "static_cross_attn.to_out": (C, C),
-                      "mlp.mlp.0": (4 * C, C), "mlp.mlp.2": (C, 4 * C)}.items():
-        sd[p + n + ".weight"], sd[p + n + ".bias"] = rnd(o, i), rnd(o)
-    for n in ("spatial_self_attn", "temporal_self_attn"):
-        sd[p + n + ".q_rms_norm.gamma"], sd[p + n + ".k_rms_norm.gamma"] = torch.ones(H, 32), torch.ones(H, 32)
-    for n in ("norm3", "norm4"):
-        sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.ones(C), torch.zeros(C)
-    x = torch.randn(1, T_FRAMES, N_LAT, C, generator=g)
-    img = torch.randn(1, T_FRAMES, L_IMG, C, generator=g)
-    st = torch.randn(1, N_STATIC, C, generator=g)
-    mod = torch.randn(1, C, generator=g)
-    P_ = ODIT._P("fp32")
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        ODIT.block_forward(sd, p, x, mod, img, st, H, P_)
-    t_block = time.perf_counter() - t0
-    # VAE: one latent layer + decoder cross-attention for one frame
-    D = 768
-    vsd = {"layers.0.0.fn.to_q.weight": rnd(D, D), "layers.0.0.fn.to_kv.weight": rnd(2 * D, D),
-           "layers.0.0.fn.to_out.weight": rnd(D, D), "layers.0.0.fn.to_out.bias": rnd(D),
-           "layers.0.1.fn.net.0.weight": rnd(8 * D, D), "layers.0.1.fn.net.0.bias": rnd(8 * D),
-           "layers.0.1.fn.net.2.weight": rnd(D, 4 * D), "layers.0.1.fn.net.2.bias": rnd(D),
-           "decoder_cross_attn.fn.to_q.weight": rnd(D, D), "decoder_cross_attn.fn.to_kv.weight": rnd(2 * D, D),
-           "decoder_cross_attn.fn.to_out.weight": rnd(D, D), "decoder_cross_attn.fn.to_out.bias": rnd(D),
-           "to_outputs.weight": rnd(14, D), "to_outputs.bias": rnd(14)}
-    xv = torch.randn(T_FRAMES, N_LAT, D, generator=g)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        n_ = OVAE._ln(xv, 1e-6)
-        xv2 = OVAE.attention(vsd, "layers.0.0.fn.", n_, n_, 12, P_) + xv
-        xv2 = OVAE.feed_forward(vsd, "layers.0.1.fn.", OVAE._ln(xv2, 1e-6), P_) + xv2
-    t_vlayer = time.perf_counter() - t0
-    qe = torch.randn(1, VOXELS * 8, D, generator=g)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        lat = OVAE.attention(vsd, "decoder_cross_attn.fn.", OVAE._ln(qe, 1e-6), OVAE._ln(xv[:1], 1e-6), 12, P_)
-        torch.nn.functional.linear(lat, vsd["to_outputs.weight"], vsd["to_outputs.bias"])
-    t_vdec = time.perf_counter() - t0
-    # raster: 2 frames
+    dit, vae = build_models("cpu", seed=0)
+    sd, vsd = dit.state_dict(), vae.state_dict()
+    si = S.sampler_inputs(1, T_FRAMES, N_LAT, C_LAT, L_IMG, C_IMG, seed=0)
     canon = S.canonical_gaussians(num_voxels=VOXELS, seed=0)
-    delta = S.raster_delta(2, VOXELS * 8).numpy()
-    ext, intr, const = S.orbit_extrinsics(T_FRAMES)[:2], S.intrinsics(), S.gaussian_constants()
+    g = torch.Generator().manual_seed(0)
+    static_latent = torch.randn(1, N_STATIC, 14, generator=g)
+    xyz = torch.rand(1, N_LAT, 3, generator=g) - 0.5
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ODIT.dit_forward(sd, si["noise"], torch.tensor([500.0]), si["cond_images"], static_latent, xyz,
+                         DIT_CFG["num_heads"], "fp32")
+    t_nfe = time.perf_counter() - t0
+    queries = torch.randn(1, VOXELS * 8, 14, generator=g)
+    z = torch.randn(T_FRAMES, N_LAT, C_LAT, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        OVAE.vae_decode(vsd, z, queries, VAE_CFG["heads"], T_FRAMES, "fp32")
+    t_dec = time.perf_counter() - t0
+    delta = S.raster_delta(T_FRAMES, VOXELS * 8).numpy()
+    ext, intr, const = S.orbit_extrinsics(T_FRAMES), S.intrinsics(), S.gaussian_constants()
     vt, pt = [], []
-    for f in range(2):
+    for f in range(T_FRAMES):
         v, p_, _, tfx, tfy = OG.camera_matrices(ext[f], intr, 0.8, 1.6)
         vt.append(v.numpy())
         pt.append(p_.numpy())
     prm = OR.make_params(RES, RES, tfx, tfy, const)
     t0 = time.perf_counter()
     OR.render_frames(prm, {k: v.numpy() for k, v in canon.items()}, delta, np.stack(vt), np.stack(pt))
-    t_r2 = time.perf_counter() - t0
-    total = NFE * 12 * t_block + 12 * t_vlayer + T_FRAMES * t_vdec + (T_FRAMES / 2) * t_r2
+    t_r = time.perf_counter() - t0
+    return t_nfe, t_dec, t_r
+
+
+def cpu_baseline(threads=None, samples=1):
+    """Median of `samples` cpu_sample() runs -> the cpu_baseline object of the bench line."""
+    threads = threads or os.cpu_count()
+    runs = sorted((cpu_sample(threads) for _ in range(samples)), key=lambda r: NFE * r[0] + r[1] + r[2])
+    t_nfe, t_dec, t_r = runs[len(runs) // 2]
+    total = NFE * t_nfe + t_dec + t_r
     return {"value": T_FRAMES / total, "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": (f"timed on host: 1 DiT block fwd at full shape ({t_block:.2f}s) x12 blocks x{NFE} NFE; 1 VAE latent "
-                       f"layer ({t_vlayer:.2f}s) x12; decoder cross-attn 1 frame ({t_vdec:.2f}s) x{T_FRAMES}; raster 2 "
-                       f"frames ({t_r2:.2f}s) x{T_FRAMES // 2}; extrapolated total {total:.0f}s/object; oracle port "
-                       "(torch fp32 + C raster), the reference itself has no CPU rasteriser")}
+            "extrapolated": {"nfe": NFE}, "samples": samples, "measured_s": {"one_nfe": t_nfe, "vae_decode": t_dec,
+                                                                             "raster_24f": t_r},
+            "seconds_per_object": total,
+            "sample": (f"measured on the host ({threads} threads), median of {samples}: ONE full NFE of the 12-block DiT at the "
+                       f"full shape ({t_nfe:.2f}s), the full 12-layer motion-VAE decode with all 24 x 16384 decoder queries "
+                       f"({t_dec:.2f}s), all 24 raster frames ({t_r:.2f}s); only x{NFE} over identical NFEs is extrapolated "
+                       f"-> {total:.0f}s/object; oracle port (torch fp32 + C rasteriser; the reference has no CPU rasteriser)")}
 
 
 def run_reference(args, rank):
+    """`--impl reference`: the CPU arm.  Every timed "step" is one bounded sample (cpu_sample: ~10 s of host work);
+    at most three are run whatever --steps says, the median is reported."""
     if rank != 0:
         return
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):
-        vals.append(cpu_baseline())
-    cb = vals[-1]
+    if args.warmup > 0:
+        cpu_sample()                                           # page the oracle / MKL in
+    cb = cpu_baseline(samples=max(1, min(args.steps, 3)))
     line = {"impl": "reference", "metric": "4D frames/sec (32-step DPM, 24f x 512^2, 16k Gaussians)",
             "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * T_FRAMES / cb["value"], "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * cb["seconds_per_object"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "samples_timed": cb["samples"], "extrapolated": cb["extrapolated"],
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
                                         "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -208,6 +190,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip the GPU stand-in of the reference's own execution (tools/gpu_reference.py, N = 1 only)")
+    ap.add_argument("--scatter", action="store_true",
+                    help="N > 1: measure e2e through the real data-parallel path (SURVEY 8e): rank 0 owns all objects in "
+                         "pinned host memory, uploads and sends every rank its conditioning each step and collects the frames "
+                         "(NCCL point-to-point, overlapped with compute: gvfdiffusion_b200.parallel.PipelinedExchange)")
     ap.add_argument("--prefetch", action="store_true",
                     help="A/B: issue sample_gs (farthest point sampling) of the next object on a side stream next to this "
                          "object's sampling.  MEASURED on B200: resident 272.1 vs 273.4 ms / object (+0.5 %: the persistent "
@@ -341,6 +329,36 @@ def main():
             st["out_host"].copy_(st["out_dev"], non_blocking=True)
             st["free"].record(copy_stream)                     # out_dev may be overwritten once it has been read back
 
+    # ---- N > 1 with --scatter: the e2e number goes through rank 0 (scatter of conditioning, gather of frames)
+    ex = None
+    if world > 1 and args.scatter:
+        from gvfdiffusion_b200.parallel import PipelinedExchange
+        specs = {("canon." + k): (tuple(v.shape), v.dtype) for k, v in hin["canon"].items()}
+        specs["noise"] = (tuple(hin["noise"].shape), hin["noise"].dtype)
+        specs["cond_images"] = (tuple(hin["cond_images"].shape), hin["cond_images"].dtype)
+        ex = PipelinedExchange(specs, (T_FRAMES, 4, RES, RES), dev)
+        root_objects = None
+        if rank == 0:                                          # one distinct object per rank, all owned by rank 0
+            root_objects = []
+            for r in range(world):
+                h = hin if r == 0 else host_inputs(seed=r)
+                d = {("canon." + k): v for k, v in h["canon"].items()}
+                d["noise"], d["cond_images"] = h["noise"], h["cond_images"]
+                root_objects.append(d)
+        sc_state = {"k": 0}
+
+        def step_scatter():
+            k = sc_state["k"]
+            sc_state["k"] += 1
+            ex.post(k, root_objects)
+            inp, out = ex.inputs(k), ex.output(k)
+            dit.reset_conditioning()
+            o = pipe.prepare_object({n[6:]: t for n, t in inp.items() if n.startswith("canon.")})
+            lat = pipe.sample(o, inp["cond_images"], inp["noise"], steps=NFE)
+            delta = pipe.decode(lat, o)
+            pipe.render(o, delta, hin["ext"], hin["intr"], out=out, check_overflow="defer")
+            ex.done(k)
+
     def barrier():
         if world > 1:
             import torch.distributed as dist
@@ -353,7 +371,9 @@ def main():
         e0.record()
         for _ in range(k):
             fn()
-        # the last step's read-back runs on the copy stream: it belongs inside the interval
+        # the last step's read-back runs on a side stream: it belongs inside the interval
+        if ex is not None and fn is step_scatter:
+            ex.flush(sc_state["k"])
         torch.cuda.current_stream().wait_stream(copy_stream)
         e1.record()
         barrier()
@@ -374,11 +394,40 @@ def main():
     Rn, overflow, _ = pipe.rz.status()
     if overflow:
         raise SystemExit("rasteriser tile-instance capacity overflowed: result invalid")
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    # the frames that reached the host through the overlapped path are the frames of the resident run
-    last = slots[(e2e_state["k"] - 1) & 1]["out_host"]
-    e2e_max_diff = float((last - out_dev.cpu()).abs().max())
+    scatter_info = None
+    if ex is not None:
+        ex.prime(root_objects)
+        step_scatter()                                          # untimed: fills the pipeline
+        ex.flush(sc_state["k"])
+        b0 = (ex.bytes_h2d, ex.bytes_d2h, ex.bytes_p2p)
+        ms_e2e = timed(step_scatter, args.steps)
+        per = [(b - a) / args.steps for a, b in zip(b0, (ex.bytes_h2d, ex.bytes_d2h, ex.bytes_p2p))]
+        # the exchange alone (no compute between the posts): what one step's scatter + gather costs on the side stream
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            k = sc_state["k"]
+            sc_state["k"] += 1
+            ex.post(k, root_objects)
+            ex.inputs(k)
+            ex.done(k)
+        ex.flush(sc_state["k"])
+        c1.record()
+        torch.cuda.synchronize()
+        last = ex.host_results[0] if rank == 0 else None
+        e2e_max_diff = float((last - out_dev.cpu()).abs().max()) if rank == 0 else 0.0
+        scatter_info = {"root_h2d_bytes_per_step": per[0], "root_d2h_bytes_per_step": per[1],
+                        "nccl_p2p_bytes_per_step_at_root": per[2], "exchange_alone_ms_per_step": c0.elapsed_time(c1) / 3,
+                        "path": "rank 0 pinned host -> H2D -> NCCL isend/irecv (one batched group per step, side stream) -> "
+                                "sample/decode/render -> NCCL -> rank 0 -> D2H; scatter of step k+1 and gather of step k-1 "
+                                "overlap compute of step k"}
+    else:
+        step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        # the frames that reached the host through the overlapped path are the frames of the resident run
+        last = slots[(e2e_state["k"] - 1) & 1]["out_host"]
+        e2e_max_diff = float((last - out_dev.cpu()).abs().max())
     stage_ms = step_profiled()
     # rasteriser alone (24 frames), graph-free, for the HBM-side roofline
     torch.cuda.synchronize()
@@ -446,10 +495,12 @@ def main():
                    "object_prefetch": ("sample_gs (FPS) of object k+1 on a side stream during the sampling of object k; "
                                        "one prepare_object per step" if prefetch else "off")},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": out_host.numel() * 4,
+        "e2e": {"value": e2e_val, "unit": "frames/s",
+                "h2d_bytes_per_step": scatter_info["root_h2d_bytes_per_step"] if scatter_info else h2d,
+                "d2h_bytes_per_step": scatter_info["root_d2h_bytes_per_step"] if scatter_info else out_host.numel() * 4,
                 "max_abs_diff_vs_resident_rgba": e2e_max_diff,
-                "note": "copies on a second stream, double buffered: upload of step k+1 / read-back of step k-1 overlap step k"},
+                "note": (scatter_info["path"] if scatter_info else
+                         "copies on a second stream, double buffered: upload of step k+1 / read-back of step k-1 overlap step k")},
         "gpu_launches": launch_estimate() * args.steps,
         "roofline": {"bound": "tensor", "kernel": "attn_fwd6_kernel (d=32, static cross-attention, kv 4096)",
                      "achieved": dom.get("tflops"), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
@@ -476,13 +527,32 @@ def main():
                                      "blend loop, a fifth in the bucket sort; DRAM traffic is below the algorithmic bytes because "
                                      "key lists and splat records are re-read from L2 (profiles/r01_raster_bucket_full_extract.csv)")},
     }
+    if scatter_info:
+        line["scatter_gather"] = scatter_info
+    if world == 1 and not args.no_gpu_reference:
+        try:        # the reference's own execution restated on this GPU (stand-in; see tools/gpu_reference.py)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import gpu_reference as GR
+            gr, rgba_ref, _, lat_ref = GR.measure(dit, vae, pipe, canon_d, cond_d, noise_d, hin["ext"], hin["intr"],
+                                                  steps=NFE, reps=2)
+            dit.reset_conditioning()
+            lat_p = pipe.sample(obj, cond_d, noise_d, steps=NFE)
+            rgba_p = pipe.render(obj, pipe.decode(lat_p, obj), hin["ext"], hin["intr"])
+            rel = lambda x, y: float((x - y).norm() / y.norm())
+            gr["product_vs_standin"] = {"latent_rel_l2": rel(lat_p, lat_ref), "rgba_rel_l2": rel(rgba_p, rgba_ref),
+                                        "rgba_max_abs": float((rgba_p - rgba_ref).abs().max())}
+            gr["speedup_e2e"] = e2e_val / gr["value"]
+            gr["speedup_resident"] = value / gr["value"]
+            line["gpu_reference"] = gr
+        except Exception as e:
+            line["gpu_reference"] = {"error": repr(e)}
     try:        # derived figure only: never allowed to break the line
         line["roofline_dit"] = dit_roofline(ms_step, line["stage_ms_eager"], pk["tf_sustained"], NFE)
     except Exception as e:
         line["roofline_dit"] = {"error": str(e)}
     if not args.no_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline(samples=1)
         except Exception as e:   # the oracle is a checker; never let it take the GPU number down
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line))

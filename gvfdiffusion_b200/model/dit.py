@@ -96,6 +96,7 @@ class DiT(nn.Module):
         self.initialize_weights()
         self._engine, self._engine_sig = None, None
         self._cond_cache = {}
+        self._cond_gen = 0
 
     @property
     def device(self):
@@ -133,15 +134,29 @@ class DiT(nn.Module):
             self._cond_cache.clear()
         return self._engine
 
+    _MAX_COND_ENTRIES = 24
+
     def _cached(self, kind, tensor, fn):
+        """Per-conditioning-tensor projections, LRU over engine buffer slots.  An entry keeps its source tensor
+        alive (so data_ptr stays unique) and owns one persistent engine slot of its kind; eviction hands the slot
+        to the next miss.  Entries touched by the call in flight (same `_cond_gen`) are never evicted: their
+        buffers are still referenced by the K/V lists being assembled."""
         key = (kind, tensor.data_ptr(), tuple(tensor.shape), tensor._version, str(tensor.device))
         hit = self._cond_cache.get(key)
         if hit is None:
-            if len(self._cond_cache) > 24:
-                self._cond_cache.clear()
-            slot = sum(1 for k in self._cond_cache if k[0] == kind)   # engine-side persistent buffer slot
-            hit = (fn(tensor, slot), tensor)     # keep the source alive so data_ptr stays unique
+            slot = None
+            if len(self._cond_cache) >= self._MAX_COND_ENTRIES:
+                for k, h in sorted(self._cond_cache.items(), key=lambda kv: kv[1][3]):      # oldest first
+                    if h[3] < self._cond_gen and k[0] == kind:
+                        slot = h[2]
+                        del self._cond_cache[k]
+                        break
+            if slot is None:
+                used = {h[2] for k, h in self._cond_cache.items() if k[0] == kind}
+                slot = next(i for i in range(len(used) + 1) if i not in used)
+            hit = [fn(tensor, slot), tensor, slot, self._cond_gen]
             self._cond_cache[key] = hit
+        hit[3] = self._cond_gen
         return hit[0]
 
     def reset_conditioning(self):
@@ -162,6 +177,7 @@ class DiT(nn.Module):
         assert deformation_position_xyz is not None, "Deformation position xyz is required for APE mode"
         eng = self.engine()
         dev = eng.dev
+        self._cond_gen += 1
         kv_img, kv_st, pos = self._cond_sets(eng, cond_images, static_latent, deformation_position_xyz)
         xt = x.to(dev, torch.float32).contiguous()
         tt = t.to(dev, torch.float32).reshape(-1).contiguous()
@@ -175,6 +191,7 @@ class DiT(nn.Module):
         x (B,...) is shared, conds = list of condition dicts -> (len(conds)*B, T, N, Cout)."""
         eng = self.engine()
         dev = eng.dev
+        self._cond_gen += 1
         B = x.shape[0]
         kv_img, kv_st, pos = [], [], []
         for c in conds:

@@ -262,7 +262,12 @@ class DPM_Solver:
                 s = t
                 x_prev, x_lower = x_lower, x_prev
                 lambda_s = ns.marginal_lambda(s)
-            h = f32(min(f32(theta * h * f32(E ** (-1.0 / 2))), f32(lambda_0 - lambda_s)))
+            if not math.isfinite(E):
+                raise FloatingPointError(f"adaptive DPM-Solver: error estimate is {E} (non-finite model output)")
+            # torch.float_power(E, -1/2) semantics (:1022): E == 0 gives inf, and min() then takes the remaining interval
+            with np.errstate(divide="ignore"):
+                grow = np.float_power(np.float64(E), -0.5)
+            h = f32(min(f32(theta * h * f32(grow)), f32(lambda_0 - lambda_s)))
             nfe += 2
         self.adaptive_nfe = nfe
         return x

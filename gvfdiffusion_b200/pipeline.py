@@ -98,6 +98,10 @@ class GVFPipeline:
     def sample(self, obj, cond_images, noise, steps=32, guidance_scale=1.0, guidance_scale2=1.0, adaptive=False,
                static_mean=0.0, static_std=1.0):
         """-> latents [1,T,N,C] fp32 (inference_dpm_latent.py:213-249)."""
+        # one object = one conditioning set: the previous object's hoisted projections are dead, their engine
+        # buffers (0.9 GB of image K/V per slot) are handed to this one
+        if hasattr(self.dit, "reset_conditioning"):
+            self.dit.reset_conditioning()
         static_latent = obj.fps4096[None]
         if not (static_mean == 0.0 and static_std == 1.0):
             static_latent = ops.affine_lastdim(static_latent.contiguous(), a_scalar=1.0 / static_std,

@@ -52,11 +52,14 @@ def _partition(coords, window_size, shift_window):
         fwd, bwd, seq_lens, seq_batch = calc_window_partition(coords, window_size, shift_window)
         cu = torch.zeros(seq_lens.shape[0] + 1, dtype=torch.int32, device=coords.device)
         cu[1:] = torch.cumsum(seq_lens, 0)
-        hit = (fwd.int().contiguous(), bwd, cu, int(seq_lens.max()) if seq_lens.numel() else 0)
+        # the entry holds `coords` itself: the key contains its address, which must not be recycled by another
+        # coordinate tensor while the entry lives (the reference hangs the partition on the SparseTensor's
+        # spatial cache, :79-85, which has the same lifetime)
+        hit = (fwd.int().contiguous(), bwd, cu, int(seq_lens.max()) if seq_lens.numel() else 0, coords)
         if len(_partition_cache) > 64:
             _partition_cache.clear()
         _partition_cache[key] = hit
-    return hit
+    return hit[:4]
 
 
 def sparse_windowed_scaled_dot_product_self_attention(qkv_feats, coords, window_size, shift_window=(0, 0, 0)):
