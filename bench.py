@@ -179,7 +179,8 @@ def run_reference(args, rank):
             "samples_timed": cb["samples"], "extrapolated": cb["extrapolated"],
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
                                         "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    args._out.write(json.dumps(line) + "\n")
+    args._out.flush()
 
 
 # ------------------------------------------------------------------------------------------
@@ -192,10 +193,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip the GPU stand-in of the reference's own execution (tools/gpu_reference.py, N = 1 only)")
-    ap.add_argument("--scatter", action="store_true",
-                    help="N > 1: measure e2e through the real data-parallel path (SURVEY 8e): rank 0 owns all objects in "
-                         "pinned host memory, uploads and sends every rank its conditioning each step and collects the frames "
-                         "(NCCL point-to-point, overlapped with compute: gvfdiffusion_b200.parallel.PipelinedExchange)")
+    ap.add_argument("--scatter", action="store_true", help="(default for N > 1; kept for explicit command lines)")
+    ap.add_argument("--no-scatter", action="store_true",
+                    help="N > 1: by default e2e goes through the real data-parallel path (SURVEY 8e): rank 0 owns all objects "
+                         "in pinned host memory, uploads and sends every rank its conditioning each step and collects the "
+                         "frames (NCCL point-to-point, overlapped with compute: gvfdiffusion_b200.parallel.PipelinedExchange); "
+                         "this flag makes every rank copy its own object instead (no collective on the data path)")
     ap.add_argument("--prefetch", action="store_true",
                     help="A/B: issue sample_gs (farthest point sampling) of the next object on a side stream next to this "
                          "object's sampling.  MEASURED on B200: resident 272.1 vs 273.4 ms / object (+0.5 %: the persistent "
@@ -206,6 +209,13 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    args.scatter = world > 1 and not args.no_scatter
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner there) write to fd 1,
+    # so fd 1 is pointed at stderr for the duration of the run and the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    args._out = real_stdout
     if args.impl == "reference":
         return run_reference(args, rank)
     if not torch.cuda.is_available():
@@ -502,16 +512,18 @@ def main():
                 "note": (scatter_info["path"] if scatter_info else
                          "copies on a second stream, double buffered: upload of step k+1 / read-back of step k-1 overlap step k")},
         "gpu_launches": launch_estimate() * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "attn_fwd6_kernel (d=32, static cross-attention, kv 4096)",
+        "roofline": {"bound": "tensor", "kernel": "attn_fwd8_kernel (d=32, static cross-attention, kv 4096)",
                      "achieved": dom.get("tflops"), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": dom.get("frac_of_sustained"), "traffic": ncu_traffic("attn_fwd6_kernel"),
+                     "frac": dom.get("frac_of_sustained"), "traffic": ncu_traffic("attn_fwd8_kernel static"),
                      "peak_source": pk["source"] + " sustained bf16",
                      "mufu_ceiling_tflops": 148 * 16 * 128 * (sampler.summary()["sm_mhz"] or 1965) * 1e6 / 1e12,
-                     "note": ("head dim 32: every score costs one MUFU exp2 (16 / clk / SM) against 128 tensor flops, so "
-                              "the kernel's ceiling is mufu_ceiling_tflops (596 at 1965 MHz = 25 % of the nominal tensor "
-                              "rate at that clock, 43 % of the measured cuBLAS peak); ncu: XU pipe 79 % busy while the "
-                              "grid is resident, tensor pipe 17 %, third of three CTA waves 59 % full "
-                              "(profiles/r01_attn6_full_extract.csv)")},
+                     "note": ("head dim 32: every score costs one exponential against 128 tensor flops; with MUFU alone (16 / clk / SM) "
+                              "the ceiling is mufu_ceiling_tflops (596 at 1965 MHz = 43 % of the measured cuBLAS peak).  v8 runs 1/4 "
+                              "of the exponentials on the FMA pipe (ceiling 794) and issues tcgen05.mma from warp-uniform code; the "
+                              "measured balance point of the loop is 12.3 clk per pair of scores and sub-partition "
+                              "(tools/probe/pipe_probe.cu) = 770 TFLOP/s, the kernel reaches 59 % of that -- the rest is the per-block "
+                              "TMEM load / store / mbarrier hand-off (~840 of 2130 clk per 64-key block, tools/attn_trace.py); ncu: "
+                              "XU 68 %, issue 65 %, tensor pipe 21 % (profiles/r02_attn8_full_extract.csv)")},
         "roofline_detail": roof_detail,
         "stage_ms_eager": {"prepare_fps": stage_ms[3], "sample_32nfe": stage_ms[0], "vae_decode": stage_ms[1],
                            "raster_24f": stage_ms[2], "raster_24f_backward": raster_bwd_ms,
@@ -555,7 +567,8 @@ def main():
             line["cpu_baseline"] = cpu_baseline(samples=1)
         except Exception as e:   # the oracle is a checker; never let it take the GPU number down
             line["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(line))
+    args._out.write(json.dumps(line) + "\n")
+    args._out.flush()
 
 
 # attention FLOPs per launch (4 * Nb * H * Lq * Lk * d), tagged by shape
@@ -598,8 +611,8 @@ def dit_roofline(ms_step, stage_ms_eager, peak_tflops, nfe=32):
             "unit": "TFLOP/s", "frac": ach / peak_tflops, "ms": t_ms, "algorithmic_tflop": flop / 1e12}
 
 def ncu_traffic(kernel_prefix):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r02_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         for k, v in json.load(open(p)).items():
             if k.startswith(kernel_prefix):

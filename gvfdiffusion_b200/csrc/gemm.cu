@@ -1112,9 +1112,9 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
     // every shape of the path; 128 x 256 tiles whenever N allows them and there is more than one column of
     // tiles per row block to amortise the wider epilogue (N >= 768), or the epilogue is a plain fp16 store
     variant = (N % 256 == 0 && (N >= 768 || epilogue == 0 || epilogue == 1)) ? 5 : 4;
-    // long-K residual shapes (fc2: N = 512, K = 2048): with the residual arriving by TMA the wide tiles are no longer
-    // held back by their epilogue, and 128 x 128 tiles sit on the L2 -> SM cap (38.6 vs 29 us, tools/gemm_depth_probe.py)
-    if (variant == 4 && epilogue == 2 && N % 256 == 0 && K >= 1024) variant = 5;
+    // long-K residual shapes (fc2: N = 512, K = 2048) stay on 128 x 128 tiles: since the MMA issue loop became
+    // warp-uniform (round 2) they run 30.1 us against 31.5 (128 x 256) / 31.4 (256 x 256 pairs) -- the wide tiles'
+    // 96 / 192 work items quantise badly on 148 SMs, which used to be hidden behind the slow issue loop
     // CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA stages half of W): -6..-11 % on the long-K
     // motion-VAE shapes (ff1 101.9 -> 91.0 us, cuBLAS 92.1), nothing on the K = 512 DiT shapes, which are bound by
     // ramp-up and epilogue latency rather than by L2 -> SM operand traffic
