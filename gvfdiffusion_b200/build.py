@@ -73,7 +73,7 @@ def build(force=False, verbose=False):
     srcs = sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose, force), srcs))
-    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcublasLt", "-lcublas", "-lcuda"]
+    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -133,6 +133,35 @@ def gen_p_sample(diffusion):
     return {"x": x, "W": W, "outs": outs}
 
 
+def gen_respace():
+    """space_timesteps / SpacedDiffusion of the reference (model/respace.py, utils/script_util.py) for the product-side
+    twin gvfdiffusion_b200/model/{gaussian_diffusion,respace}.py: kept-timestep sets, respaced betas / timestep maps and
+    one p_sample per prediction type on a respaced, rescaled process."""
+    from model.respace import space_timesteps
+    out = {"space": {}}
+    for n, sec in ((1000, "100"), (1000, "ddim50"), (1000, "10,15,20"), (1000, "fast27"), (300, [10, 15, 20]), (1000, [1000]),
+                   (1000, "7"), (997, "13,5")):
+        out["space"][(n, str(sec))] = sorted(space_timesteps(n, sec))
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 4, 8, 8, 8, generator=g)
+    W = torch.randn(4, 4, generator=g) * 0.5
+    model = lambda x, ts: torch.einsum("oc,bcdhw->bodhw", W, x) * torch.cos(ts / 1000.0).view(-1, 1, 1, 1, 1)
+    out["x"], out["W"], out["cases"] = x, W, []
+    for ptype, sched, resp, small in (("v", "cosine", "50", False), ("eps", "linear", "ddim25", True),
+                                      ("xstart", "cosine", "", False)):
+        cfg = dict(DIFF_CFG, predict_type=ptype, noise_schedule=sched, timestep_respacing=resp, sigma_small=small)
+        d = create_gaussian_diffusion(**cfg)
+        case = {"cfg": cfg, "betas": torch.from_numpy(d.betas), "timestep_map": list(d.timestep_map), "outs": {}}
+        for tt in (d.num_timesteps - 1, d.num_timesteps // 2, 0):
+            t = torch.tensor([tt, max(tt - 1, 0)])
+            for clip in (True, False):
+                torch.manual_seed(7 + tt)
+                o = d.p_sample(model, x, t, clip_denoised=clip)
+                case["outs"][(tt, clip)] = {"sample": o["sample"], "pred_xstart": o["pred_xstart"]}
+        out["cases"].append(case)
+    return out
+
+
 def gen_gaussian():
     """GaussianModel activations (+ delta).  The reference hard-codes .cuda() at construction:
     patch Tensor.cuda to identity for this CPU run."""
@@ -498,6 +527,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "respace":
+        torch.save(gen_respace(), os.path.join(HERE, "respace.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "window":
         torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
         return
@@ -507,6 +539,7 @@ def main():
     torch.save(gen_vae(), os.path.join(HERE, "vae_tiny.pt"))
     torch.save(gen_p_sample(diffusion), os.path.join(HERE, "p_sample.pt"))
     torch.save(gen_gaussian(), os.path.join(HERE, "gaussian.pt"))
+    torch.save(gen_respace(), os.path.join(HERE, "respace.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
