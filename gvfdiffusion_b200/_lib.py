@@ -45,6 +45,7 @@ _SIGS = {
                                    C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_float, _P]),
     "gvf_gemm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                _P, C.c_int, C.c_int, _P]),
+    "gvf_gemm_geglu_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "gvf_gemm_qkv_rmsnorm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                            _P, _P, C.c_int, _P]),
     "gvf_gemm_resid_ln_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int,

@@ -527,7 +527,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int HALF = BN / 2;
     const int et = threadIdx.x - 64;               // 0..255
     constexpr int mode = MODE;
-    constexpr bool out16 = (mode == 0 || mode == 1 || mode == 3 || mode == 6);
+    constexpr bool out16 = (mode == 0 || mode == 1 || mode == 3 || mode == 6 || mode == 7);
     uint8_t* stg = stg_base + ew * 2 * 4096;
     const uint32_t sw = (uint32_t)(lane & 7);      // SWIZZLE_128B: 16 B piece j of row r sits at j ^ (r & 7)
     int lt = 0, sbuf = 0;
@@ -547,9 +547,16 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t tacc = tmem + acc * BN + half * HALF + ((uint32_t)(q * 32) << 16);
       if constexpr (out16) {
         // ---------------- fp16 outputs: 64-column chunks (128 B rows)
+        // mode 7 (GEGLU, model/autoencoder.py:90-93): the W rows of a tile are [BN/2 value rows | BN/2 gate rows]
+        // (interleaved once at load time), so value j and gate j of an output column sit BN/2 accumulator columns
+        // apart in the same TMEM lane; the tile's output is BN/2 wide and each warp owns 64 of its columns
+        constexpr int NCOLS = (mode == 7) ? 64 : HALF;
+        const int nlim = (mode == 7) ? (N >> 1) : N;
 #pragma unroll 1
-        for (int c0 = 0; c0 < HALF; c0 += 64) {
-          const int col0 = colh + c0;
+        for (int c0 = 0; c0 < NCOLS; c0 += 64) {
+          const int col0 = (mode == 7) ? tile_n * (BN / 2) + half * 64 : colh + c0;
+          const uint32_t tsrc = (mode == 7) ? tmem + acc * BN + half * 64 + ((uint32_t)(q * 32) << 16) : tacc + c0;
+          const int sboff = (mode == 7) ? half * 64 : half * HALF + c0;
           uint4 old[8];
           if (mode == 3) {                          // residual rows first: latency overlaps the accumulator wait
             const __half* orow = reinterpret_cast<const __half*>(ep.out) + (size_t)row * ep.ldo + col0;
@@ -565,11 +572,27 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           float v[64];
           {
             uint32_t rr[64];
-            tmem_ld_x32(tacc + c0, *reinterpret_cast<uint32_t(*)[32]>(&rr[0]));
-            tmem_ld_x32(tacc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rr[32]));
+            tmem_ld_x32(tsrc, *reinterpret_cast<uint32_t(*)[32]>(&rr[0]));
+            tmem_ld_x32(tsrc + 32, *reinterpret_cast<uint32_t(*)[32]>(&rr[32]));
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(rr[j]) + sb[half * HALF + c0 + j];
+            for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(rr[j]) + sb[sboff + j];
+          }
+          if constexpr (mode == 7) {
+            // out = fp16(fp16(value) * fp16(gelu_erf(fp16(gate)))): the rounding points of the reference's autocast
+            // Linear -> chunk -> F.gelu -> multiply (and of geglu_kernel, which this epilogue replaces)
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              uint32_t gg[32];
+              tmem_ld_x32(tsrc + BN / 2 + 32 * h2, gg);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = r16(__uint_as_float(gg[j]) + sb[BN / 2 + sboff + 32 * h2 + j]);
+                const float ge = r16(0.5f * x * (1.0f + erff(x * 0.7071067811865476f)));
+                v[32 * h2 + j] = r16(v[32 * h2 + j]) * ge;
+              }
+            }
           }
           if (mode == 1) {
 #pragma unroll
@@ -616,7 +639,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && col0 < N && row0 < M) {
+          if (lane == 0 && col0 < nlim && row0 < M) {
             tma_store_2d(&mapO, stg + sbuf * 4096, col0, row0);
             tma_store_commit();
           }
@@ -1094,10 +1117,11 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
                      int rows_per_batch, const float* gamma_q, const float* gamma_k, int norm_cols,
                      void* stream) {
   if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return GVF_ERR_INVALID;
-  if ((N % 8) || (K % 8) || (lda % 8) || (ldw % 8) || epilogue < 0 || epilogue > 6) return GVF_ERR_INVALID;
+  if ((N % 8) || (K % 8) || (lda % 8) || (ldw % 8) || epilogue < 0 || epilogue > 7) return GVF_ERR_INVALID;
   if (epilogue == 6 && (!gamma_q || !gamma_k || norm_cols <= 0 || (norm_cols % 64) || norm_cols > N))
     return GVF_ERR_INVALID;
-  if ((epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6) && (ldo % 2)) return GVF_ERR_INVALID;
+  if ((epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6 || epilogue == 7) && (ldo % 2)) return GVF_ERR_INVALID;
+  if (epilogue == 7 && (N % 256)) return GVF_ERR_UNSUPPORTED;      // GEGLU: whole 256-row weight tiles [128 value | 128 gate]
   if ((epilogue == 2 || epilogue == 4) && (ldo % 2)) return GVF_ERR_INVALID;
   if (gate && (gate_stride % 2)) return GVF_ERR_INVALID;
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
@@ -1120,11 +1144,13 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
     // ramp-up and epilogue latency rather than by L2 -> SM operand traffic
     if (variant == 5 && K >= 768 && (long long)((M + 2 * kBM - 1) / (2 * kBM)) * (N / 256) >= 74) variant = 7;
   }
+  if (epilogue == 7 && variant != 5 && variant != 7) variant = 5;   // the interleaving is defined on 256-column tiles
   // generation-2 kernels need a TMA-storable output (16 B aligned rows) and do not do the compact mode 5
   if (variant >= 4 && variant <= 9 &&
       (epilogue == 5 || (ldo * ((epilogue == 2 || epilogue == 4) ? 4 : 2)) % 16 != 0 ||
        (gate && ((gate_stride % 8) || ((uintptr_t)gate & 15)))))
     variant = 0;
+  if (epilogue == 7 && variant != 5 && variant != 7) return GVF_ERR_UNSUPPORTED;
   // 8 / 9: pipeline-depth experiments (128x128 with 5 stages, 256x128 pair tiles with 6 stages)
   const int BN = (variant == 2 || variant == 5 || variant == 7) ? 256 : 128;
   const int wbox = (variant == 6 || variant == 7 || variant == 9) ? BN / 2 : BN;      // W rows one CTA stages per k-block
@@ -1140,9 +1166,10 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   ep.ldo = ldo;
   ep.gamma_q = gamma_q; ep.gamma_k = gamma_k; ep.norm_cols = norm_cols;
   if (variant >= 4 && variant <= 9) {
-    const bool out16 = (epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6);
+    const bool out16 = (epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6 || epilogue == 7);
     CUtensorMap mO;
-    if (!make_tmap_2d(&mO, out, out16 ? 2 : 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, out16 ? 64 : 32, 32))
+    if (!make_tmap_2d(&mO, out, out16 ? 2 : 4, (uint64_t)(epilogue == 7 ? N / 2 : N), (uint64_t)M, (uint64_t)ldo,
+                      out16 ? 64 : 32, 32))
       return GVF_ERR_CUDA;
     cudaStream_t cs = (cudaStream_t)stream;
 #define GVF_WS(MODE)                                                                      \
@@ -1155,6 +1182,9 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
                             : launch_gemm_ws<128, 4, MODE>(mA, mW, mO, M, N, K, ep, cs);
     switch (epilogue) {
       GVF_WS(0) GVF_WS(1) GVF_WS(2) GVF_WS(3) GVF_WS(4) GVF_WS(6)
+      case 7:
+        return variant == 7 ? launch_gemm_ws<256, 4, 7, 2>(mA, mW, mO, M, N, K, ep, cs)
+                            : launch_gemm_ws<256, 3, 7>(mA, mW, mO, M, N, K, ep, cs);
       default: return GVF_ERR_INVALID;
     }
 #undef GVF_WS
@@ -1173,9 +1203,18 @@ extern "C" GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int l
                                     int K, int epilogue, const float* bias, void* out, int ldo,
                                     const void* gate, int gate_stride, int rows_per_batch,
                                     void* stream) {
-  if (epilogue == 6) return GVF_ERR_INVALID;
+  if (epilogue == 6 || epilogue == 7) return GVF_ERR_INVALID;
   return gemm_impl(A, lda, W, ldw, M, N, K, epilogue, bias, out, ldo, gate, gate_stride, rows_per_batch,
                    nullptr, nullptr, 0, stream);
+}
+
+// FeedForward's first Linear with GEGLU in the epilogue (reference model/autoencoder.py:90-107):
+// out[M, N/2] = fp16(value * gelu_erf(gate)).  W / bias rows must be interleaved per 256-row tile:
+// rows [256 t, 256 t + 128) = value rows [128 t, 128 t + 128) of net.0, rows [256 t + 128, 256 t + 256) = gate rows
+// [N/2 + 128 t, ...) (gvfdiffusion_b200/ops.py: geglu_interleave).  N % 256 == 0.
+extern "C" GVF_API int gvf_gemm_geglu_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                                          const float* bias, void* out, int ldo, void* stream) {
+  return gemm_impl(A, lda, W, ldw, M, N, K, 7, bias, out, ldo, nullptr, 0, 0, nullptr, nullptr, 0, stream);
 }
 
 // QKV projection with MultiHeadRMSNorm fused into the epilogue (reference

@@ -70,6 +70,34 @@ def gemm_resid_ln(a, w, bias, x, y, gate=None, gate_stride=0, rows_per_batch=0, 
     return y
 
 
+def geglu_interleave(w, bias=None):
+    """Rows of FeedForward.net[0] ([2F, K]: F value rows then F gate rows, model/autoencoder.py:90-101) re-ordered for
+    `gemm_geglu`: per 256-row tile 128 value rows followed by their 128 gate rows.  F % 128 == 0."""
+    F2 = w.shape[0]
+    Fh = F2 // 2
+    if Fh % 128:
+        raise ValueError("geglu_interleave: hidden width must be a multiple of 128")
+    idx = torch.arange(Fh, device=w.device).view(-1, 128)
+    perm = torch.cat([idx, idx + Fh], dim=1).reshape(-1)
+    return w[perm].contiguous(), (None if bias is None else bias[perm].contiguous())
+
+
+def gemm_geglu(a, w_il, bias_il, out=None):
+    """out[M, F] = fp16(value * gelu_erf(gate)) of (a @ w^T + bias) with w / bias from `geglu_interleave`: the FF's
+    first Linear and GEGLU in one kernel (the [M, 2F] hidden tensor never exists)."""
+    _req(a, F16, "a")
+    _req(w_il, F16, "w")
+    M, K = a.shape
+    N = w_il.shape[0]
+    assert w_il.shape[1] == K and a.stride(1) == 1 and w_il.stride(1) == 1 and N % 256 == 0
+    if out is None:
+        out = torch.empty((M, N // 2), dtype=F16, device=a.device)
+    assert out.dtype == F16 and out.stride(1) == 1 and out.shape[1] == N // 2
+    check(_lib.lib().gvf_gemm_geglu_f16(ptr(a), a.stride(0), ptr(w_il), w_il.stride(0), M, N, K, ptr(bias_il), ptr(out),
+                                        out.stride(0), current_stream()), "gvf_gemm_geglu_f16")
+    return out
+
+
 _attn_ws = None
 
 

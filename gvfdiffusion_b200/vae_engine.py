@@ -40,6 +40,9 @@ class VAEDecodeEngine:
                 w_out=_h(sd[a + "to_out.weight"], dev), b_out=_b(sd[a + "to_out.bias"], dev),
                 w1=_h(sd[f + "net.0.weight"], dev), b1=_b(sd[f + "net.0.bias"], dev),
                 w2=_h(sd[f + "net.2.weight"], dev), b2=_b(sd[f + "net.2.bias"], dev)))
+            ly = self.layers[-1]
+            if (ly["w1"].shape[0] // 2) % 128 == 0:     # GEGLU in the ff1 epilogue needs whole [128 value | 128 gate] tiles
+                ly["w1g"], ly["b1g"] = ops.geglu_interleave(ly["w1"], ly["b1"])
         self.w_gs, self.b_gs = _h(sd["gs_embedding.0.weight"], dev), _b(sd["gs_embedding.0.bias"], dev)
         c = "decoder_cross_attn.fn."
         self.w_dq, self.w_dkv = _h(sd[c + "to_q.weight"], dev), _h(sd[c + "to_kv.weight"], dev)
@@ -68,8 +71,11 @@ class VAEDecodeEngine:
             ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale, out=AO.view(BT, L, H, d))
             ops.gemm(AO, ly["w_out"], ly["b_out"], ops.EPI_RESID_F16, out=x)
             ops.ln_mod(x, out=A, eps=1e-6)
-            ops.gemm(A, ly["w1"], ly["b1"], ops.EPI_F16, out=Hf)
-            ops.geglu(Hf, out=G)
+            if "w1g" in ly:
+                ops.gemm_geglu(A, ly["w1g"], ly["b1g"], out=G)                 # Linear + GEGLU, one kernel
+            else:
+                ops.gemm(A, ly["w1"], ly["b1"], ops.EPI_F16, out=Hf)
+                ops.geglu(Hf, out=G)
             ops.gemm(G, ly["w2"], ly["b2"], ops.EPI_RESID_F16, out=x)
         return x
 

@@ -208,6 +208,15 @@ GVF_API int gvf_gemm_qkv_rmsnorm_f16(const void* A, int lda, const void* W, int 
                                      const float* bias, void* out, int ldo, const float* gamma_q,
                                      const float* gamma_k, int norm_cols, void* stream);
 
+/* FeedForward's first Linear with GEGLU fused into the epilogue (reference model/autoencoder.py:90-107:
+ * `x, gates = net[0](x).chunk(2, -1); x * F.gelu(gates)`): out fp16 [M, N/2] = fp16(fp16(value) * fp16(gelu_erf(fp16(gate)))).
+ * W [N, K] / bias [N] are the rows of net.0 interleaved per 256-row tile -- rows [256 t, 256 t + 128) = value rows
+ * [128 t, 128 t + 128), rows [256 t + 128, 256 t + 256) = gate rows [N/2 + 128 t, N/2 + 128 t + 128) -- so that value and
+ * gate of an output column meet in one accumulator tile.  N % 256 == 0, else GVF_ERR_UNSUPPORTED (caller uses
+ * gvf_gemm_f16 + gvf_geglu_f16). */
+GVF_API int gvf_gemm_geglu_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                               const float* bias, void* out, int ldo, void* stream);
+
 /* Residual Linear fused with the LayerNorm (+ adaLN modulate or affine) of the next sub-block (reference
  * model/dit.py:246-277: `x = x + gate * attn_out_proj(...)` then `h = norm(x) * (1 + scale) + shift`):
  *   x[M,512] += gate * fp16(A W^T + b)   (fp32, in place);   y[M,512] = fp16(LN(x) * (1 + scale) + shift)

@@ -464,3 +464,22 @@ def test_gemm_scheduling_variants(variant):
             _close(out, x + ref.half().float(), 1e-3, f"variant {variant} resid {M}x{N}x{K}")
     finally:
         L.gvf_gemm_set_variant(-1)
+
+
+@pytest.mark.parametrize("M,F_,K", [(12288, 3072, 768), (1000, 384, 96), (130, 128, 64), (24576, 3072, 768)])
+def test_gemm_geglu_fused_is_bit_identical_to_the_two_kernels(M, F_, K):
+    """FeedForward.net[0] + GEGLU (reference model/autoencoder.py:90-107) in one kernel: interleaved weight rows, value
+    and gate meet in one accumulator tile.  Same rounding points as gvf_gemm_f16 + gvf_geglu_f16 -> identical bits;
+    and within fp16 rounding of the fp32 torch expression."""
+    from gvfdiffusion_b200 import ops
+    g = _g(M + F_)
+    a = _rand((M, K), g).half()
+    w = _rand((2 * F_, K), g, 0.05).half()
+    b = _rand((2 * F_,), g, 0.1)
+    two = ops.geglu(ops.gemm(a, w, b, ops.EPI_F16))
+    wi, bi = ops.geglu_interleave(w, b)
+    one = ops.gemm_geglu(a, wi, bi)
+    assert torch.equal(one, two)
+    h = (a.float() @ w.float().T + b).half().float()
+    ref = h[:, :F_] * F.gelu(h[:, F_:])
+    _close(one, ref, 2e-3, "geglu fused")
