@@ -43,6 +43,19 @@ _SIGS = {
     "gvf_attn_fwd_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                    C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_float, _P]),
+    "gvf_attn_fwd_lse_f16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                       C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_float, _P]),
+    "gvf_attn_bwd_f16": (C.c_int, [_P] * 10 + [C.c_int] * 6 + [C.POINTER(C.c_longlong)] * 8 + [C.c_int, C.c_float, _P]),
+    "gvf_transpose_f16": (C.c_int, [_P, C.c_int, C.c_int, C.c_longlong, _P, C.c_longlong, _P]),
+    "gvf_colsum_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_int, C.c_int]),
+    "gvf_colsum": (C.c_int, [_P, C.c_int, C.c_longlong, C.c_int, C.c_longlong, _P, C.c_size_t, _P, C.c_int, _P]),
+    "gvf_ln_bwd_f16": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
+    "gvf_geglu_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P, _P]),
+    "gvf_small_linear_bwd_input": (C.c_int, [_P, C.c_int, C.c_longlong, _P, C.c_longlong, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "gvf_skinny_outer": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_longlong, C.c_longlong, C.c_int, _P, C.c_size_t,
+                                   _P, C.c_int, _P]),
+    "gvf_vae_query_embed_bwd": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "gvf_gemm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                _P, C.c_int, C.c_int, _P]),
     "gvf_gemm_geglu_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]),

@@ -74,6 +74,10 @@ struct AttnArgs {
   int split_from, nsplit, gx;
   float* ws_o;        // [split units][nsplit][512 rows][32]
   float* ws_ml;       // [split units][nsplit][512 rows][2]
+  // training: LSE2[nb, h, q] = log2(sum_k exp(scale s_qk)) for the backward kernels (csrc/attn_bwd.cu); rows in
+  // [Lq, lse_ld) get +inf.  Only attn_fwd_kernel writes it (gvf_attn_fwd_lse_f16 selects that kernel).
+  float* lse = nullptr;
+  int lse_ld = 0;
 };
 
 // POLY = n > 0: every n-th pair of exponentials is evaluated on the FMA pipe (Cody-Waite split plus a
@@ -367,6 +371,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       tc_fence_after();
       fold_o(1.0f);
       const int qi = q0 + x * 128 + row;
+      if (a.lse && qi < a.lse_ld)
+        a.lse[((long long)nb * a.H + h) * a.lse_ld + qi] = qi < a.Lq ? fmaf(m, c, log2f(l)) : INFINITY;
       if (qi < a.Lq) {
         const float inv = 1.0f / l;
         __half* op = a.o + (long long)nb * a.o_stride_b + (long long)qi * a.o_stride_l + (long long)h * a.o_stride_h;
@@ -1835,12 +1841,13 @@ static int g_small_rows = 0;   // row-staged temporal variant: measured slower t
 
 // q [Nb_q, Lq, H, D], k/v [Nb_kv, Lk, H, D] fp16 with element strides (batch, seq, head);
 // innermost dim contiguous.  Nb_q / Nb_kv may be 1 (tensor shared by all Nb batches).
-extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void* v, void* o, int Nb, int Lq,
-                                        int Lk, int H, int D, const long long* q_strides,
-                                        const long long* k_strides, const long long* v_strides,
-                                        const long long* o_strides, int q_shared, int kv_shared,
-                                        float scale, void* stream) {
+static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, int Nb, int Lq,
+                         int Lk, int H, int D, const long long* q_strides,
+                         const long long* k_strides, const long long* v_strides,
+                         const long long* o_strides, int q_shared, int kv_shared,
+                         float scale, float* lse, int lse_ld, void* stream) {
   if (!q || !k || !v || !o || !q_strides || !k_strides || !v_strides || !o_strides) return GVF_ERR_INVALID;
+  if (lse && (lse_ld < ((Lq + 127) / 128) * 128 || (lse_ld % 128) || ((uintptr_t)lse & 15))) return GVF_ERR_INVALID;
   if (Nb <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return GVF_ERR_INVALID;
   if (D != 32 && D != 64) return GVF_ERR_UNSUPPORTED;
   for (int i = 0; i < 3; ++i)
@@ -1848,7 +1855,7 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15) return GVF_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
 
-  if (D == 32 && Lq <= 32 && Lk == Lq && !q_shared && !kv_shared && q_strides[0] == k_strides[0] &&
+  if (!lse && D == 32 && Lq <= 32 && Lk == Lq && !q_shared && !kv_shared && q_strides[0] == k_strides[0] &&
       q_strides[1] == k_strides[1] && q_strides[2] == k_strides[2] && q_strides[0] == v_strides[0] &&
       q_strides[1] == v_strides[1] && q_strides[2] == v_strides[2]) {
     if ((g_attn_dbg & 0xf0) != 0x40 && q_strides[2] == D && o_strides[2] == D && H % 8 == 0) {
@@ -1909,6 +1916,10 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   a.dbg = g_attn_dbg & 0xff;
   a.stagger = ((g_attn_dbg >> 8) & 0xff) * 100;
   a.trace = g_attn_trace;
+  if (lse) {                     // training forward: the generic kernel is the one that also leaves LSE2 behind
+    a.lse = lse; a.lse_ld = lse_ld; a.dbg = 0; a.stagger = 0; a.trace = nullptr;
+    return D == 64 ? launch_attn<64, 0>(mq, mk, mv, a, Nb, st) : launch_attn<32, 0>(mq, mk, mv, a, Nb, st);
+  }
   // Kernel choice.  d = 32 with more than two query tiles per (batch, head): v6 (four softmax warpgroups, a quarter
   // of the exponentials on the FMA pipe); otherwise v4 with the MUFU ping-pong.  gvf_attn_set_debug overrides
   // (tools/attn_experiments.py): 0x10 v4 plain, 0x30 v4 ping-pong, 0x80 v6 MUFU only, low nibble 4 = polynomial share.
@@ -1968,4 +1979,24 @@ extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void
   if (sel == 0) a.dbg |= 0x20;
   if (D == 64) return launch_attn<64, 0>(mq, mk, mv, a, Nb, st);
   return poly ? launch_attn<32, 4>(mq, mk, mv, a, Nb, st) : launch_attn<32, 0>(mq, mk, mv, a, Nb, st);
+}
+
+extern "C" GVF_API int gvf_attn_fwd_f16(const void* q, const void* k, const void* v, void* o, int Nb, int Lq,
+                                        int Lk, int H, int D, const long long* q_strides,
+                                        const long long* k_strides, const long long* v_strides,
+                                        const long long* o_strides, int q_shared, int kv_shared,
+                                        float scale, void* stream) {
+  return attn_fwd_impl(q, k, v, o, Nb, Lq, Lk, H, D, q_strides, k_strides, v_strides, o_strides, q_shared, kv_shared,
+                       scale, nullptr, 0, stream);
+}
+
+// Training forward: as above, and LSE2 [Nb, H, lse_ld] fp32 (lse_ld = Lq rounded up to 128) for gvf_attn_bwd_f16.
+extern "C" GVF_API int gvf_attn_fwd_lse_f16(const void* q, const void* k, const void* v, void* o, float* lse2, int lse_ld,
+                                            int Nb, int Lq, int Lk, int H, int D, const long long* q_strides,
+                                            const long long* k_strides, const long long* v_strides,
+                                            const long long* o_strides, int q_shared, int kv_shared, float scale,
+                                            void* stream) {
+  if (!lse2) return GVF_ERR_INVALID;
+  return attn_fwd_impl(q, k, v, o, Nb, Lq, Lk, H, D, q_strides, k_strides, v_strides, o_strides, q_shared, kv_shared,
+                       scale, lse2, lse_ld, stream);
 }

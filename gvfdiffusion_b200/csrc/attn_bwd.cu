@@ -197,7 +197,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       for (int i = 0; i < n_blk; ++i) {
         const int j = i >> 1, s = j % S;
         const float* st = reinterpret_cast<const float*>(sQ + s * STAGE_BYTES + 2 * TILE_BYTES) + (i & 1) * 64;
-        mbar_wait(&s_full[x], i & 1);                  // implies q_full[s] (the MMAs read that stage)
+        if ((i & 1) == 0) mbar_wait(&q_full[s], (j / S) & 1);   // LSE2 / D of the stage (bulk copies) are visible
+        mbar_wait(&s_full[x], i & 1);
         tc_fence_after();
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {

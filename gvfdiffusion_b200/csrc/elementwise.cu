@@ -528,6 +528,7 @@ GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C,
   LN_BOTH(768, true)
   LN_BOTH(64, false)
   LN_BOTH(96, false)
+  LN_BOTH(192, false)
   LN_BOTH(128, true)
   LN_BOTH(384, true)
 #undef LN_BOTH
@@ -586,6 +587,7 @@ GVF_API int gvf_vae_query_embed(const float* queries, int ldq, const void* gs, i
   if (C == 768) query_embed_kernel<768><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
   else if (C == 96) query_embed_kernel<96><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
   else if (C == 384) query_embed_kernel<384><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
+  else if (C == 192) query_embed_kernel<192><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
   else return GVF_ERR_UNSUPPORTED;
   RET();
 }

@@ -1,13 +1,34 @@
 """`GSKLTemporalVariationalAutoEncoder`: drop-in for the DECODE side of the reference's motion
 VAE (model/autoencoder.py:345-609): same constructor keywords, same state-dict names for the
 decode weights (`proj`, `layers.{i}.{0,1}.fn.*`, `gs_embedding.0`, `decoder_cross_attn.fn.*`,
-`to_outputs`), `decode(x, queries)` on the sm_100a engine.  `encode` (FPS + KNN interpolation +
+`to_outputs`), `decode(x, queries)` on the sm_100a engine -- forward only under no_grad, forward + hand-written
+backward (vae_train.py) when autograd is recording.  `encode` (FPS + KNN interpolation +
 cross-attention, training / dataset preparation only) is out of scope.
 """
 import torch
 import torch.nn as nn
 
 from ..vae_engine import VAEDecodeEngine
+from ..vae_train import VAEDecodeTrainEngine
+
+
+class _DecodeFn(torch.autograd.Function):
+    """decode() under autograd: forward with saved activations and the hand-written backward of vae_train.py (the
+    reference relies on torch autograd through model/autoencoder.py:552-609 here, train_vae.py:293-353)."""
+
+    @staticmethod
+    def forward(ctx, module, z, queries, *params):
+        eng = module.train_engine()
+        out, saved = eng.forward_train(z, queries)
+        ctx.eng, ctx.saved, ctx.names = eng, saved, module._param_names
+        ctx.z_shape, ctx.q_dtype = z.shape, queries.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads, dz, dq = ctx.eng.backward(ctx.saved, dout)
+        ctx.saved = None
+        return (None, dz.view(ctx.z_shape), dq.to(ctx.q_dtype)) + tuple(grads[n] for n in ctx.names)
 
 
 class _Fn(nn.Module):
@@ -56,6 +77,8 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         nn.init.constant_(self.to_outputs.weight, 0)
         nn.init.constant_(self.to_outputs.bias, 0)
         self._engine, self._sig = None, None
+        self._train_engine, self._train_sig = None, None
+        self._param_names = [n for n, _ in self.named_parameters()]
 
     def load_state_dict(self, state_dict, strict=False, **kw):
         # reference checkpoints also carry the encoder; only the decode weights are consumed here
@@ -76,10 +99,25 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
             self._sig = sig
         return self._engine
 
-    @torch.no_grad()
+    def train_engine(self):
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._train_engine is None or sig != self._train_sig:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("decode runs on a CUDA device only (no CPU fallback)")
+            self._train_engine = VAEDecodeTrainEngine(self.state_dict(), self.heads, self.num_timesteps, dev)
+            self._train_sig = sig
+        return self._train_engine
+
     def decode(self, x, queries):
-        """x ((B*T), L, latent_dim), queries (B, Q, 14) -> (B, T, Q, output_dim) fp32."""
-        return self.engine().decode(x, queries)
+        """x ((B*T), L, latent_dim), queries (B, Q, 14) -> (B, T, Q, output_dim) fp32.  Differentiable with respect to
+        x, queries and every decode parameter when autograd is recording (training step); otherwise the inference
+        engine runs."""
+        params = list(self.parameters())
+        if torch.is_grad_enabled() and (x.requires_grad or queries.requires_grad or any(p.requires_grad for p in params)):
+            return _DecodeFn.apply(self, x, queries, *params)
+        with torch.no_grad():
+            return self.engine().decode(x, queries)
 
     def encode(self, *a, **k):
         raise NotImplementedError("encode() is training-data preparation, outside the inference hot path")

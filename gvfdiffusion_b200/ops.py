@@ -344,3 +344,140 @@ def sparse_im2col(x, nbr, out=None):
     check(_lib.lib().gvf_sparse_im2col_f16(ptr(x), int(x.dtype == F16), x.stride(0), ptr(nbr), N, K3, Cin, ptr(out),
                                            current_stream()), "gvf_sparse_im2col_f16")
     return out
+
+
+# ---- training step of the motion VAE (include/gvf_b200.h section 8) ----
+def _st3(t, shared=False):
+    return (0, t.stride(0), t.stride(1)) if shared else (t.stride(0), t.stride(1), t.stride(2))
+
+
+def attention_fwd_lse(q, k, v, scale, out=None, q_shared=False):
+    """`attention` that also returns LSE2 [Nb, H, Lq rounded up to 128] fp32 for `attention_bwd`."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, F16, n)
+        assert t.stride(-1) == 1
+    Lq, H, D = (q.shape if q_shared else q.shape[1:])
+    Nb, Lk = k.shape[0], k.shape[1]
+    if out is None:
+        out = torch.empty((Nb, Lq, H, D), dtype=F16, device=q.device)
+    ld = (Lq + 127) // 128 * 128
+    lse = torch.empty((Nb, H, ld), dtype=F32, device=q.device)
+    st = _lib.lib().gvf_attn_fwd_lse_f16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ld, Nb, Lq, Lk, H, D,
+                                         _ll(_st3(q, q_shared)), _ll(_st3(k)), _ll(_st3(v)), _ll(_st3(out)),
+                                         int(q_shared), 0, float(scale), current_stream())
+    check(st, "gvf_attn_fwd_lse_f16")
+    return out, lse
+
+
+def attention_bwd(q, k, v, o, dout, lse, scale, dq, dk, dv, q_shared=False):
+    """dq / dk / dv (fp16 views, written in place) of softmax(scale q k^T) v; q_shared: dq [Lq,H,D] sums over the batch."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
+        _req(t, F16, n)
+        assert t.stride(-1) == 1
+    Lq, H, D = (q.shape if q_shared else q.shape[1:])
+    Nb, Lk = k.shape[0], k.shape[1]
+    dsum = torch.empty_like(lse)
+    st = _lib.lib().gvf_attn_bwd_f16(ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dsum), ptr(dq), ptr(dk),
+                                     ptr(dv), Nb, Lq, Lk, H, D, lse.shape[-1], _ll(_st3(q, q_shared)), _ll(_st3(k)),
+                                     _ll(_st3(v)), _ll(_st3(o)), _ll(_st3(dout)), _ll(_st3(dq, q_shared)), _ll(_st3(dk)),
+                                     _ll(_st3(dv)), int(q_shared), float(scale), current_stream())
+    check(st, "gvf_attn_bwd_f16")
+    return dq, dk, dv
+
+
+def transpose(x, out=None):
+    """x fp16 [R, C] (row stride any) -> [C, R8] with R8 = R rounded up to 8, pad columns zero; returns the padded
+    tensor (a legal K-major GEMM operand whose reduction length is R8)."""
+    _req(x, F16, "x")
+    R, Cc = x.shape
+    assert x.stride(1) == 1
+    R8 = (R + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((Cc, R8), dtype=F16, device=x.device)
+    assert out.shape == (Cc, R8) and out.is_contiguous()
+    check(_lib.lib().gvf_transpose_f16(ptr(x), R, Cc, x.stride(0), ptr(out), R8, current_stream()), "gvf_transpose_f16")
+    return out
+
+
+_red_ws = {}
+
+
+def _reduce_ws(device, nbytes):
+    ws = _red_ws.get(device)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty((nbytes + 3) // 4, dtype=F32, device=device)
+        _red_ws[device] = ws
+    return ws
+
+
+def colsum(x, out=None, accumulate=False):
+    """sum over rows of x [M, N] (fp16 / fp32) -> fp32 [N]: bias gradients."""
+    M, N = x.shape
+    assert x.stride(1) == 1 and x.dtype in (F16, F32)
+    need = _lib.lib().gvf_colsum_workspace_bytes(M, N, 0)
+    ws = _reduce_ws(x.device, need)
+    if out is None:
+        out = torch.empty(N, dtype=F32, device=x.device)
+        accumulate = False
+    check(_lib.lib().gvf_colsum(ptr(x), int(x.dtype == F16), M, N, x.stride(0), ptr(ws), ws.numel() * 4, ptr(out),
+                                int(accumulate), current_stream()), "gvf_colsum")
+    return out
+
+
+def ln_bwd(x, dy, dres=None, eps=1e-6, out=None):
+    M, Cc = x.shape
+    assert x.is_contiguous() and dy.is_contiguous() and dy.dtype == F16 and (dres is None or dres.is_contiguous())
+    if out is None:
+        out = torch.empty((M, Cc), dtype=F16, device=x.device)
+    check(_lib.lib().gvf_ln_bwd_f16(ptr(x), int(x.dtype == F16), ptr(dy), ptr(dres), ptr(out), M, Cc, eps,
+                                    current_stream()), "gvf_ln_bwd_f16")
+    return out
+
+
+def geglu_bwd(h, dG, out=None):
+    M, F2 = h.shape
+    assert h.is_contiguous() and dG.is_contiguous() and h.dtype == F16 and dG.dtype == F16
+    if out is None:
+        out = torch.empty_like(h)
+    check(_lib.lib().gvf_geglu_bwd_f16(ptr(h), ptr(dG), M, F2 // 2, ptr(out), current_stream()), "gvf_geglu_bwd_f16")
+    return out
+
+
+def small_linear_bwd_input(dy, w):
+    """dx fp32 [M, K] = dy [M, N] (fp16 / fp32) @ w [N, K] (fp16), K <= 32."""
+    M, N = dy.shape
+    K = w.shape[1]
+    assert dy.stride(1) == 1 and w.is_contiguous() and w.dtype == F16 and w.shape[0] == N
+    dx = torch.empty((M, K), dtype=F32, device=dy.device)
+    check(_lib.lib().gvf_small_linear_bwd_input(ptr(dy), int(dy.dtype == F16), dy.stride(0), ptr(w), M, N, K, ptr(dx), K,
+                                                current_stream()), "gvf_small_linear_bwd_input")
+    return dx
+
+
+def skinny_outer(x, y, out=None, accumulate=False):
+    """fp32 [K, N] = x[M, K]^T @ y[M, N] for K <= 16 (x fp32, y fp16 / fp32)."""
+    _req(x, F32, "x")
+    M, K = x.shape
+    N = y.shape[1]
+    assert x.stride(1) == 1 and y.stride(1) == 1 and y.shape[0] == M
+    need = _lib.lib().gvf_colsum_workspace_bytes(M, N, K)
+    ws = _reduce_ws(x.device, need)
+    if out is None:
+        out = torch.empty((K, N), dtype=F32, device=x.device)
+        accumulate = False
+    check(_lib.lib().gvf_skinny_outer(ptr(x), x.stride(0), K, ptr(y), int(y.dtype == F16), y.stride(0), M, N, ptr(ws),
+                                      ws.numel() * 4, ptr(out), int(accumulate), current_stream()), "gvf_skinny_outer")
+    return out
+
+
+def vae_query_embed_bwd(queries, gs, dout, dxyz=None, accumulate=False):
+    """-> (d gs fp16 [Q, C], d xyz): d xyz is written (or added) into the first three columns of `dxyz` (fp32 rows)."""
+    Q, Cc = gs.shape
+    dgs = torch.empty((Q, Cc), dtype=F16, device=gs.device)
+    if dxyz is None:
+        dxyz = torch.empty((Q, 3), dtype=F32, device=gs.device)
+        accumulate = False
+    assert dxyz.dtype == F32 and dxyz.stride(1) == 1 and dxyz.shape[0] == Q
+    check(_lib.lib().gvf_vae_query_embed_bwd(ptr(queries), queries.stride(0), ptr(gs), ptr(dout), Q, Cc, ptr(dgs), ptr(dxyz),
+                                             dxyz.stride(0), int(accumulate), current_stream()), "gvf_vae_query_embed_bwd")
+    return dgs, dxyz

@@ -125,7 +125,8 @@ class GVFPipeline:
         z = latents
         if deformation_mean is not None or deformation_std is not None:
             z = ops.affine_lastdim(latents.contiguous(), a=deformation_std, b=deformation_mean)
-        return self.vae.decode(z.reshape(B * T, N, C), obj.static_gs[None])[0]
+        with torch.no_grad():          # inference pipeline: the forward-only engine (training goes through vae.decode itself)
+            return self.vae.decode(z.reshape(B * T, N, C), obj.static_gs[None])[0]
 
     def render(self, obj, delta, extrinsics, intrinsics, out=None, check_overflow=True):
         """delta [F,P,14], extrinsics [F,4,4] -> rgba [F,4,H,W] fp32 (utils/inference_utils.py:256-269

@@ -371,6 +371,54 @@ GVF_API int gvf_sparse_neighbor_map(const int* coords, int N, int B, int D, int 
 GVF_API int gvf_sparse_im2col_f16(const void* x, int x_is_f16, int ldx, const int* nbr, int N, int K3, int Cin,
                                   void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * 8. Training step of the motion VAE (SURVEY.md rows g / a9 backward; BASELINE configs[2] and [4]).
+ *    What torch autograd derives for reference model/autoencoder.py:552-609 (`decode`) under train_vae.py:293-353:
+ *    attention backward on tcgen05, the element-wise / skinny backward passes, and the operand transposes that let
+ *    gvf_gemm_f16 compute dgrad (dX = dY W: A = dY, "W" = W^T) and wgrad (dW = dY^T X: A = dY^T, "W" = X^T, fp32
+ *    output, epilogue 4).
+ * ---------------------------------------------------------------------------------- */
+/* Forward attention that also leaves LSE2[Nb, H, lse_ld] = log2(sum_k exp(scale s_qk)) (fp32; lse_ld = Lq rounded up
+ * to a multiple of 128, rows >= Lq set to +inf) for gvf_attn_bwd_f16.  Otherwise identical to gvf_attn_fwd_f16. */
+GVF_API int gvf_attn_fwd_lse_f16(const void* q, const void* k, const void* v, void* o, float* lse2, int lse_ld, int Nb,
+                                 int Lq, int Lk, int H, int D, const long long* q_strides, const long long* k_strides,
+                                 const long long* v_strides, const long long* o_strides, int q_shared, int kv_shared,
+                                 float scale, void* stream);
+/* Backward of flash_attn_func (model/autoencoder.py:132-144): dq / dk / dv fp16 from q, k, v, o, dout and LSE2.
+ * q_shared: q [Lq, H, D] is shared by the Nb batch entries (the decoder's frame-independent queries) and dq is the
+ * sum over them; k / v / o / dout always carry the batch.  dsum: scratch [Nb, H, lse_ld] fp32 (row sums of dout * o).
+ * Every *_strides = element strides {batch, sequence, head}.  D in {32, 64}. */
+GVF_API int gvf_attn_bwd_f16(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                             const float* lse2, float* dsum, void* dq, void* dk, void* dv, int Nb, int Lq, int Lk, int H,
+                             int D, int lse_ld, const long long* q_strides, const long long* k_strides,
+                             const long long* v_strides, const long long* o_strides, const long long* do_strides,
+                             const long long* dq_strides, const long long* dk_strides, const long long* dv_strides,
+                             int q_shared, float scale, void* stream);
+/* out[C, ld_out] = in[R, C]^T (fp16); columns [R, ld_out) of every output row are zero (ld_out = R rounded up to 8
+ * so that the transposed tensor is a legal GEMM operand). */
+GVF_API int gvf_transpose_f16(const void* in, int R, int C, long long ld_in, void* out, long long ld_out, void* stream);
+/* Bytes of scratch for gvf_colsum (K = 0) / gvf_skinny_outer (K rows). */
+GVF_API size_t gvf_colsum_workspace_bytes(long long M, int N, int K);
+/* out[n] (+)= sum_m x[m, n]: bias gradients.  x fp16 or fp32 [M, N] with row stride ld. */
+GVF_API int gvf_colsum(const void* x, int x_is_f16, long long M, int N, long long ld, float* workspace,
+                       size_t workspace_bytes, float* out, int accumulate, void* stream);
+/* LayerNorm (no affine, PreNorm model/autoencoder.py:73-88) backward: dx = dLN(dy; x) + dres (dres optional), fp16. */
+GVF_API int gvf_ln_bwd_f16(const void* x, int x_is_f16, const void* dy, const void* dres, void* dx, int M, int C, float eps,
+                           void* stream);
+/* GEGLU backward (model/autoencoder.py:90-93): h [M, 2F], dG [M, F] -> dh [M, 2F] (all fp16). */
+GVF_API int gvf_geglu_bwd_f16(const void* h, const void* dG, long long M, int F, void* dh, void* stream);
+/* Backward of gvf_small_linear with respect to its input: dx[M, K] = dy[M, N] W[N, K] (fp32 out, K <= 32). */
+GVF_API int gvf_small_linear_bwd_input(const void* dy, int dy_is_f16, long long ld, const void* W, long long M, int N, int K,
+                                       float* dx, int ldx, void* stream);
+/* out[K, N] (+)= x[M, K]^T y[M, N] for K <= 16 (fp32 x; y fp16 or fp32): weight gradients of the K <= 16 Linears
+ * (transposed: proj / gs_embedding, x = layer input, y = dy) and of to_outputs (x = d out, y = layer input). */
+GVF_API int gvf_skinny_outer(const float* x, int ldx, int K, const void* y, int y_is_f16, long long ldy, long long M, int N,
+                             float* workspace, size_t workspace_bytes, float* out, int accumulate, void* stream);
+/* Backward of gvf_vae_query_embed: d out fp16 [Q, C] -> d gs fp16 [Q, C], d xyz fp32 (rows of ld_dxyz >= 3 floats,
+ * e.g. the first three columns of d queries [Q, 14]; accumulate != 0 adds to what is there). */
+GVF_API int gvf_vae_query_embed_bwd(const float* queries, int ldq, const void* gs, const void* dout, int Q, int C,
+                                    void* dgs, float* dxyz, int ld_dxyz, int accumulate, void* stream);
+
 /* Tuning hook of the rasteriser's per-tile depth sort: -1 environment (GVF_RASTER_SORT=bucket|bitonic,
  * default bucket), 0 bitonic network, 1 one-pass bucket sort (identical point lists). */
 GVF_API void gvf_raster_set_sort(int mode);

@@ -86,7 +86,8 @@ def test_vae_decode_16384_gaussians_chunked_vs_oracle():
     sd = {k: t_.clone() for k, t_ in v.state_dict().items()}
     z = torch.randn(T, 512, 16, generator=gen)
     q = torch.randn(1, 16384, 14, generator=gen) * 0.3
-    d = v.to(DEV).decode(z.to(DEV), q.to(DEV))
+    with torch.no_grad():
+        d = v.to(DEV).decode(z.to(DEV), q.to(DEV))
     assert d.shape == (1, T, 16384, 14)
     with torch.no_grad():
         d16 = OVAE.vae_decode(sd, z, q, 12, T, "fp16")
