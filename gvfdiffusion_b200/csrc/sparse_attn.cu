@@ -49,13 +49,13 @@ __device__ __forceinline__ uint32_t slot(int row, int chunk) { return (uint32_t)
 
 // rows [r0, r0 + 64) of the window (clipped to `len`) of tensor `which` (0 q, 1 k, 2 v), head h -> smem tile
 __device__ __forceinline__ void stage_rows(uint32_t dst, const __half* __restrict__ qkv, const int* __restrict__ idx,
-                                           int r0, int len, int which, int h, int H, int tid) {
+                                           int beg, int r0, int len, int which, int h, int H, int tid) {
   const long long row_elems = 3LL * H * kD;
 #pragma unroll
   for (int it = 0; it < (64 * 8) / 128; ++it) {
     const int e = it * 128 + tid, r = e >> 3, c = e & 7;
     const bool ok = r0 + r < len;
-    const long long g = ok ? (long long)__ldg(idx + r0 + r) : 0;
+    const long long g = ok ? (idx ? (long long)__ldg(idx + beg + r0 + r) : (long long)(beg + r0 + r)) : 0;   // no list: identity
     const __half* src = qkv + g * row_elems + ((long long)which * H + h) * kD + c * 8;
     const int bytes = ok ? 16 : 0;                 // src-size 0: the 16 B are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + slot(r, c)), "l"(src), "r"(bytes) : "memory");
@@ -64,6 +64,7 @@ __device__ __forceinline__ void stage_rows(uint32_t dst, const __half* __restric
 
 __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
                                                                 const int* __restrict__ fwd_idx,
+                                                                const int* __restrict__ out_idx,
                                                                 const int* __restrict__ cu_seqlens, int H,
                                                                 float scale_log2e) {
   __shared__ __align__(128) uint8_t sm[(1 + 4) * 64 * 128];     // Q | K0 V0 | K1 V1   (40 KB)
@@ -71,13 +72,13 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
   const int beg = __ldg(cu_seqlens + w), len = __ldg(cu_seqlens + w + 1) - beg;
   if (q0 >= len) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
-  const int* idx = fwd_idx + beg;
+  const int* idx = fwd_idx;                      // gather list (nullptr: rows beg.. of qkv itself)
   const uint32_t sQ = smem_u32(sm), sKV = sQ + 64 * 128;
   const int nchunks = (len + kKB - 1) / kKB;
 
-  stage_rows(sQ, qkv, idx, q0, len, 0, h, H, tid);
-  stage_rows(sKV, qkv, idx, 0, len, 1, h, H, tid);
-  stage_rows(sKV + 64 * 128, qkv, idx, 0, len, 2, h, H, tid);
+  stage_rows(sQ, qkv, idx, beg, q0, len, 0, h, H, tid);
+  stage_rows(sKV, qkv, idx, beg, 0, len, 1, h, H, tid);
+  stage_rows(sKV + 64 * 128, qkv, idx, beg, 0, len, 2, h, H, tid);
   asm volatile("cp.async.commit_group;" ::: "memory");
 
   uint32_t qa[4][4];
@@ -92,8 +93,8 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
     const uint32_t bK = sKV + (uint32_t)(j & 1) * 2 * 64 * 128, bV = bK + 64 * 128;
     if (j + 1 < nchunks) {
       const uint32_t nK = sKV + (uint32_t)((j + 1) & 1) * 2 * 64 * 128;
-      stage_rows(nK, qkv, idx, (j + 1) * kKB, len, 1, h, H, tid);
-      stage_rows(nK + 64 * 128, qkv, idx, (j + 1) * kKB, len, 2, h, H, tid);
+      stage_rows(nK, qkv, idx, beg, (j + 1) * kKB, len, 1, h, H, tid);
+      stage_rows(nK + 64 * 128, qkv, idx, beg, (j + 1) * kKB, len, 2, h, H, tid);
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -188,8 +189,12 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
   for (int it = 0; it < 4; ++it) {
     const int e = it * 32 + lane, r = 16 * warp + (e >> 3), c = e & 7;
     if (q0 + r < len) {
-      const long long grow = __ldg(idx + q0 + r);
-      *reinterpret_cast<uint4*>(out + (grow * H + h) * kD + c * 8) = *reinterpret_cast<const uint4*>(sm + slot(r, c));
+      // destination row: the scatter list when given (negative = this position is padding of an overlapping window,
+      // serialized attention), else the row the query came from
+      const int pos = beg + q0 + r;
+      const long long grow = out_idx ? (long long)__ldg(out_idx + pos) : (idx ? (long long)__ldg(idx + pos) : (long long)pos);
+      if (grow >= 0)
+        *reinterpret_cast<uint4*>(out + (grow * H + h) * kD + c * 8) = *reinterpret_cast<const uint4*>(sm + slot(r, c));
     }
   }
 }
@@ -211,6 +216,26 @@ extern "C" GVF_API int gvf_sparse_window_attn_f16(const void* qkv, void* out, co
   if (num_windows > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_windows);
   gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, fwd_idx, cu_seqlens, H, scale * 1.4426950408889634f);
+      (const __half*)qkv, (__half*)out, fwd_idx, nullptr, cu_seqlens, H, scale * 1.4426950408889634f);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+// General form: variable-length self-attention over rows of a packed qkv [T, 3, H, 64] tensor.
+//   gather_idx  [M] int32 or NULL: position i of the sequence list reads qkv row gather_idx[i] (NULL: row i itself --
+//               sparse full attention, sparse/attention/full_attn.py:90-215 with cu_seqlens = the batch layout);
+//   scatter_idx [M] int32 or NULL: its result goes to out row scatter_idx[i], negative = dropped (serialized attention,
+//               sparse/attention/serialized_attn.py:38-192: windows are padded to window_size with wrapped-around
+//               neighbours whose results are discarded); NULL: the row the query was read from.
+extern "C" GVF_API int gvf_sparse_varlen_attn_f16(const void* qkv, void* out, const int* gather_idx, const int* scatter_idx,
+                                                  const int* cu_seqlens, int num_seqs, int max_seqlen, int H, int D,
+                                                  float scale, void* stream) {
+  if (!qkv || !out || !cu_seqlens || num_seqs < 0 || H <= 0 || max_seqlen < 0) return GVF_ERR_INVALID;
+  if (D != gvf::kD) return GVF_ERR_UNSUPPORTED;
+  if (((uintptr_t)qkv | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
+  if (num_seqs == 0 || max_seqlen == 0) return GVF_OK;
+  if (num_seqs > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
+  const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_seqs);
+  gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, H, scale * 1.4426950408889634f);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }

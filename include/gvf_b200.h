@@ -309,6 +309,15 @@ GVF_API int gvf_vox2seq_decode(const int32_t* codes, long long N, const int* per
 GVF_API int gvf_sparse_window_attn_f16(const void* qkv, void* out, const int* fwd_idx, const int* cu_seqlens,
                                        int num_windows, int max_seqlen, int H, int D, float scale, void* stream);
 
+/* General form of the kernel above: variable-length self-attention over rows of a packed qkv [T, 3, H, 64] tensor.
+ * gather_idx [M] int32 or NULL (position i reads qkv row i: sparse full attention, sparse/attention/full_attn.py:90-215,
+ * cu_seqlens = the batch layout); scatter_idx [M] int32 or NULL: destination row of position i's result, negative =
+ * dropped (serialized attention, sparse/attention/serialized_attn.py:38-192, pads every window to window_size with
+ * wrapped-around neighbours and keeps only the valid part via bwd_indices); NULL = the row the query came from. */
+GVF_API int gvf_sparse_varlen_attn_f16(const void* qkv, void* out, const int* gather_idx, const int* scatter_idx,
+                                       const int* cu_seqlens, int num_seqs, int max_seqlen, int H, int D, float scale,
+                                       void* stream);
+
 /* ------------------------------------------------------------------------------------
  * 7. Training-step losses (BASELINE configs[4]).
  *    gvf_ssim_l1_*: nn.L1Loss + utils/loss_util.py:33-63 `ssim` as used at train_vae.py:328-330

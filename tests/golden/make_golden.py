@@ -224,6 +224,42 @@ def gen_window_partition():
     return cases
 
 
+def gen_serialization():
+    """The reference's own calc_serialization (sparse/attention/serialized_attn.py:38-119) with `vox2seq.encode`
+    provided by the reference's PyTorch twin of its extension (vox2seq/vox2seq/pytorch): forward / backward indices,
+    sequence lengths and batch indices for the four serialisation modes, shifted sequences and shifted windows."""
+    import importlib.util
+    import types
+    twin_dir = os.path.join(_ref_import.REF, "model", "sparse_voxel_diffusion", "vox2seq", "vox2seq", "pytorch")
+    spec = importlib.util.spec_from_file_location("_vox2seq_twin", os.path.join(twin_dir, "__init__.py"),
+                                                  submodule_search_locations=[twin_dir])
+    twin = importlib.util.module_from_spec(spec)
+    sys.modules["_vox2seq_twin"] = twin
+    spec.loader.exec_module(twin)
+    sys.modules["vox2seq"].encode = twin.encode
+    from sparse.attention.serialized_attn import SerializeMode, calc_serialization
+    g = torch.Generator().manual_seed(21)
+    cases = []
+    for (counts, res, window, mode, shift_seq, shift_win) in [
+            ((700, 333), 64, 256, "Z_ORDER", 0, (0, 0, 0)), ((700, 333), 64, 256, "HILBERT", 0, (0, 0, 0)),
+            ((700, 333), 64, 256, "Z_ORDER_TRANSPOSED", 128, (0, 0, 0)), ((700, 333), 64, 256, "HILBERT_TRANSPOSED", 64, (3, 5, 7)),
+            ((100, 1025, 64), 32, 64, "HILBERT", 16, (1, 0, 2)), ((50,), 16, 64, "Z_ORDER", 0, (0, 0, 0))]:
+        coords, layout, off = [], [], 0
+        for b, n_vox in enumerate(counts):
+            lin = torch.randperm(res ** 3, generator=g)[:n_vox]
+            xyz = torch.stack([lin // (res * res), (lin // res) % res, lin % res], 1)
+            coords.append(torch.cat([torch.full((n_vox, 1), b), xyz], 1))
+            layout.append(slice(off, off + n_vox))
+            off += n_vox
+        coords = torch.cat(coords).int()
+        t = types.SimpleNamespace(coords=coords, layout=layout, device=coords.device)
+        fwd, bwd, seq_lens, seq_batch = calc_serialization(t, window, SerializeMode[mode], shift_seq, shift_win)
+        cases.append({"coords": coords, "counts": counts, "window": window, "mode": mode, "shift_sequence": shift_seq,
+                      "shift_window": shift_win, "fwd": fwd, "bwd": bwd, "seq_lens": list(seq_lens),
+                      "seq_batch_indices": list(seq_batch)})
+    return cases
+
+
 def _bruteforce_knn_points(p1, p2, lengths1=None, lengths2=None, K=1):
     """Stand-in for pytorch3d.ops.knn_points (absent here) with its documented semantics: exact squared
     distances ((dx*dx + dy*dy) + dz*dz in fp32), ascending, ties -> lowest index, padded rows zero."""
@@ -527,6 +563,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "serialization":
+        torch.save(gen_serialization(), os.path.join(HERE, "serialization.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "respace":
         torch.save(gen_respace(), os.path.join(HERE, "respace.pt"))
         return
@@ -540,6 +579,7 @@ def main():
     torch.save(gen_p_sample(diffusion), os.path.join(HERE, "p_sample.pt"))
     torch.save(gen_gaussian(), os.path.join(HERE, "gaussian.pt"))
     torch.save(gen_respace(), os.path.join(HERE, "respace.pt"))
+    torch.save(gen_serialization(), os.path.join(HERE, "serialization.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
