@@ -55,6 +55,7 @@ _SIGS = {
     "gvf_small_linear_bwd_input": (C.c_int, [_P, C.c_int, C.c_longlong, _P, C.c_longlong, C.c_int, C.c_int, _P, C.c_int, _P]),
     "gvf_skinny_outer": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_longlong, C.c_longlong, C.c_int, _P, C.c_size_t,
                                    _P, C.c_int, _P]),
+    "gvf_skinny_expand": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_longlong, C.c_int, _P, C.c_int, C.c_longlong, _P]),
     "gvf_vae_query_embed_bwd": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "gvf_gemm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                _P, C.c_int, C.c_int, _P]),
@@ -69,6 +70,7 @@ _SIGS = {
     "gvf_attn_set_workspace": (None, [_P, C.c_size_t]),
     "gvf_attn_set_trace": (None, [_P]),
     "gvf_gemm_set_variant": (None, [C.c_int]),
+    "gvf_gemm_set_ksplit": (None, [C.c_int]),
     "gvf_set_pdl": (None, [C.c_int]),
     "gvf_small_linear": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "gvf_ln_mod_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, _P]),

@@ -216,6 +216,45 @@ __global__ void __launch_bounds__(256) skinny_outer_partial_kernel(const float* 
     for (int k = 0; k < K; ++k) partial[((long long)blockIdx.y * K + k) * N + n] = acc[k];
 }
 
+// out[m, n] = sum_k x[m, k] Wt[k, n]   (K <= 16, fp32 operands; out fp16 or fp32): rank-K expansion, e.g. the gradient of
+// to_outputs' input, d lat = d out [M, 14] @ W [14, 768].  Thread = two adjacent columns (weights in registers), CTA =
+// 64 rows staged in shared memory; one coalesced 4 B (8 B) store per thread and row.
+template <typename TOut>
+__global__ void __launch_bounds__(512) skinny_expand_kernel(const float* __restrict__ x, int ldx, int K,
+                                                            const float* __restrict__ Wt, long long M, int N,
+                                                            TOut* __restrict__ out, long long ldo) {
+  __shared__ float sx[64][16];
+  const long long m0 = (long long)blockIdx.x * 64;
+  for (int t = threadIdx.x; t < 64 * 16; t += blockDim.x) {
+    const int r = t >> 4, k = t & 15;
+    sx[r][k] = (m0 + r < M && k < K) ? x[(m0 + r) * ldx + k] : 0.f;
+  }
+  __syncthreads();
+  const int lim = (int)(M - m0 < 64 ? M - m0 : 64);
+  for (int n = 2 * threadIdx.x; n < N; n += 2 * blockDim.x) {
+    float w0[16], w1[16];
+    const bool two = n + 1 < N;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      w0[k] = k < K ? Wt[(size_t)k * N + n] : 0.f;
+      w1[k] = (k < K && two) ? Wt[(size_t)k * N + n + 1] : 0.f;
+    }
+    for (int r = 0; r < lim; ++r) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { a0 = fmaf(sx[r][k], w0[k], a0); a1 = fmaf(sx[r][k], w1[k], a1); }
+      TOut* o = out + (m0 + r) * ldo + n;
+      if constexpr (sizeof(TOut) == 2) {
+        if (two && ((ldo & 1) == 0)) *reinterpret_cast<__half2*>(o) = __floats2half2_rn(a0, a1);
+        else { o[0] = __float2half_rn(a0); if (two) o[1] = __float2half_rn(a1); }
+      } else {
+        o[0] = a0;
+        if (two) o[1] = a1;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ query embedding
 // Backward of gvf_vae_query_embed: out = LN_1e-6( LN_1e-5(gs) + LN_1e-5(PE(xyz)) ), PE as in query_embed_kernel
 // (fp16-rounded argument and value).  d_out fp16 [Q, C] -> d_gs fp16 [Q, C], d_xyz fp32 [Q, 3] (the derivative of the
@@ -392,6 +431,18 @@ GVF_API int gvf_skinny_outer(const float* x, int ldx, int K, const void* y, int 
     skinny_outer_partial_kernel<float><<<grid, 256, 0, ST(stream)>>>(x, ldx, K, (const float*)y, ldy, M, N, rps, workspace);
   const long long n = (long long)K * N;
   reduce_slabs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(workspace, slabs, n, out, accumulate);
+  RET();
+}
+
+GVF_API int gvf_skinny_expand(const float* x, int ldx, int K, const float* Wt, long long M, int N, void* out,
+                              int out_is_f16, long long ldo, void* stream) {
+  if (!x || !Wt || !out || M <= 0 || N <= 0 || K <= 0 || K > 16 || ldx < K || ldo < N) return GVF_ERR_INVALID;
+  if (out_is_f16 && (((uintptr_t)out & 3) != 0)) return GVF_ERR_INVALID;
+  int threads = (N + 1) / 2;
+  threads = threads > 512 ? 512 : ((threads + 31) / 32) * 32;
+  const unsigned blocks = (unsigned)((M + 63) / 64);
+  if (out_is_f16) skinny_expand_kernel<__half><<<blocks, threads, 0, ST(stream)>>>(x, ldx, K, Wt, M, N, (__half*)out, ldo);
+  else skinny_expand_kernel<float><<<blocks, threads, 0, ST(stream)>>>(x, ldx, K, Wt, M, N, (float*)out, ldo);
   RET();
 }
 

@@ -396,7 +396,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 template <int BN, int STAGES, int MODE, int NCTA>
 __global__ void __launch_bounds__(320, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-               const __grid_constant__ CUtensorMap mapO, int M, int N, int K, GemmEpi ep) {
+               const __grid_constant__ CUtensorMap mapO, int M, int N, int K, GemmEpi ep, int ksplit) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint64_t xres_bar[8][2];     // mode 2, BN = 128: residual chunks arriving by TMA (one per warp and buffer)
@@ -413,7 +413,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int kblocks = (K + kBK - 1) / kBK;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + NCTA * kBM - 1) / (NCTA * kBM);   // pair tiles for NCTA = 2
-  const int num_tiles = tiles_n * tiles_m;
+  // Split-K (wgrad shapes of the training step: few output tiles, reduction length 12288 ..): a work item is
+  // (output tile, k range); the partial tiles are summed in global memory by TMA reduce-add stores (mode 4 only, the
+  // host zeroes the output first).  ksplit = 1: one item per tile, plain stores.
+  const int out_tiles = tiles_n * tiles_m;
+  const int num_tiles = out_tiles * ksplit;           // work items
+  const int kb_per = (kblocks + ksplit - 1) / ksplit;
   const int first_tile = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
 
   if (threadIdx.x == 0) {
@@ -427,12 +432,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // latency overlaps the TMEM allocation and the CTA barrier (pairs must wait for the cluster barrier first)
       pdl_wait();
       if (first_tile < num_tiles) {
-        const int tile_m = first_tile / tiles_n, tile_n = first_tile % tiles_n;
-        for (int kb = 0; kb < (kblocks < STAGES ? kblocks : STAGES); ++kb) {
+        const int ot = first_tile % out_tiles, kb0 = (first_tile / out_tiles) * kb_per;
+        const int nkb = min(kblocks, kb0 + kb_per) - kb0;
+        const int tile_m = ot / tiles_n, tile_n = ot % tiles_n;
+        for (int kb = 0; kb < (nkb < STAGES ? nkb : STAGES); ++kb) {
           mbar_arrive_expect_tx(&full_bar[kb], STAGE_BYTES);
           uint8_t* st = smem + kb * STAGE_BYTES;
-          tma_load_2d(st, &mapA, &full_bar[kb], kb * kBK, tile_m * kBM);
-          tma_load_2d(st + A_BYTES, &mapW, &full_bar[kb], kb * kBK, tile_n * BN);
+          tma_load_2d(st, &mapA, &full_bar[kb], (kb0 + kb) * kBK, tile_m * kBM);
+          tma_load_2d(st + A_BYTES, &mapW, &full_bar[kb], (kb0 + kb) * kBK, tile_n * BN);
         }
       }
     } else {
@@ -455,10 +462,15 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // TMA producer: all 32 lanes run the (warp-uniform) loop, one elected lane issues -- see elect_one()
     int s = 0;
     uint32_t ph = 0;                               // parity of full / empty for the current pass over the ring
-    int skip = (NCTA == 1) ? (kblocks < STAGES ? kblocks : STAGES) : 0;     // requested in the prologue
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    int skip = 0;
+    if (NCTA == 1 && first_tile < num_tiles) {                               // requested in the prologue
+      const int kb0 = (first_tile / out_tiles) * kb_per, nkb = min(kblocks, kb0 + kb_per) - kb0;
+      skip = nkb < STAGES ? nkb : STAGES;
+    }
+    for (int item = first_tile; item < num_tiles; item += tile_step) {
+      const int tile = item % out_tiles, kb0 = (item / out_tiles) * kb_per, kb1 = min(kblocks, kb0 + kb_per);
       const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (skip > 0) --skip;
         else {
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -491,12 +503,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t b_full = smem_u32(&full_bar[0]), b_empty = smem_u32(&empty_bar[0]);
       int s = 0, lt = 0;
       uint32_t ph = 0, s_lo = a_lo0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++lt) {
+      for (int item = first_tile; item < num_tiles; item += tile_step, ++lt) {
+        const int kb0 = (item / out_tiles) * kb_per, kb1 = min(kblocks, kb0 + kb_per);
         const int acc = lt & 1;
         mbar_wait(&tempty_bar[acc], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_u32(b_full + 8 * s, ph);
           tc_fence_after();
           if (elect_one()) {
@@ -504,8 +517,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t ad = ((uint64_t)d_hi << 32) | (s_lo + 2 * k);
               const uint64_t wd = ((uint64_t)d_hi << 32) | (s_lo + A16 + 2 * k);
-              if constexpr (NCTA == 2) mma_ss_2cta(d_tmem, ad, wd, idesc, (kb | k) != 0);
-              else mma_ss(d_tmem, ad, wd, idesc, (kb | k) != 0);
+              if constexpr (NCTA == 2) mma_ss_2cta(d_tmem, ad, wd, idesc, ((kb - kb0) | k) != 0);
+              else mma_ss(d_tmem, ad, wd, idesc, ((kb - kb0) | k) != 0);
             }
             if constexpr (NCTA == 2) tc_commit_2cta(&empty_bar[s]);
             else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_empty + 8 * s) : "memory");
@@ -532,13 +545,15 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t sw = (uint32_t)(lane & 7);      // SWIZZLE_128B: 16 B piece j of row r sits at j ^ (r & 7)
     int lt = 0, sbuf = 0;
     uint32_t xph = 0;                              // phase bits of this warp's two residual barriers
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++lt) {
+    for (int item = first_tile; item < num_tiles; item += tile_step, ++lt) {
+      const int tile = item % out_tiles;
+      const bool first_split = item < out_tiles;     // the bias is added once
       const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
       const int acc = lt & 1;
       float* sb = s_bias[acc];
       for (int c = et; c < BN; c += 256) {
         const int col = tile_n * BN + c;
-        sb[c] = (ep.bias && col < N) ? __ldg(ep.bias + col) : 0.f;
+        sb[c] = (ep.bias && col < N && first_split) ? __ldg(ep.bias + col) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int row0 = tile_m * kBM + q * 32, row = row0 + lane;
@@ -745,7 +760,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && col0 < N && row0 < M) {
-            tma_store_2d(&mapO, stg + sbuf * 4096, col0, row0);
+            if (mode == 4 && ksplit > 1) tma_reduce_add_2d(&mapO, stg + sbuf * 4096, col0, row0);
+            else tma_store_2d(&mapO, stg + sbuf * 4096, col0, row0);
             tma_store_commit();
           }
           if constexpr (kTmaResid && HALF > 64) {
@@ -777,7 +793,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
 template <int BN, int STAGES, int MODE, int NCTA = 1>
 static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CUtensorMap& mO, int M, int N, int K,
-                          const GemmEpi& ep, cudaStream_t st) {
+                          const GemmEpi& ep, cudaStream_t st, int ksplit = 1) {
   constexpr int SMEM = STAGES * (kBM * kBK * 2 + (BN / NCTA) * kBK * 2) + 8 * 2 * 4096 + 1024;
   static bool configured = false;
   static int num_sms = 0;
@@ -790,11 +806,11 @@ static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CU
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  const int tiles = ((N + BN - 1) / BN) * ((M + NCTA * kBM - 1) / (NCTA * kBM));
+  const int tiles = ((N + BN - 1) / BN) * ((M + NCTA * kBM - 1) / (NCTA * kBM)) * ksplit;
   const int slots = num_sms / NCTA;
   const int grid = (tiles < slots ? tiles : slots) * NCTA;
   if constexpr (NCTA == 1) {
-    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep) == cudaSuccess
+    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep, ksplit) == cudaSuccess
                ? GVF_OK : GVF_ERR_CUDA;
   } else {
     cudaLaunchConfig_t cfg = {};
@@ -809,8 +825,8 @@ static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CU
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_ws_kernel<BN, STAGES, MODE, 2>, mA, mW, mO, M, N, K, ep) == cudaSuccess ? GVF_OK
-                                                                                                            : GVF_ERR_CUDA;
+    return cudaLaunchKernelEx(&cfg, gemm_ws_kernel<BN, STAGES, MODE, 2>, mA, mW, mO, M, N, K, ep, ksplit) == cudaSuccess ? GVF_OK
+                                                                                                                    : GVF_ERR_CUDA;
   }
 }
 
@@ -1111,6 +1127,7 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mW, int M, int 
 using namespace gvf;
 
 static int g_gemm_variant = -1;
+static int g_gemm_ksplit = 0;      // 0 automatic, -1 never, n > 0 forced (fp32-store epilogue only)
 
 static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue,
                      const float* bias, void* out, int ldo, const void* gate, int gate_stride,
@@ -1180,8 +1197,37 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
              : variant == 6 ? launch_gemm_ws<128, 5, MODE, 2>(mA, mW, mO, M, N, K, ep, cs) \
              : variant == 5 ? launch_gemm_ws<256, 3, MODE>(mA, mW, mO, M, N, K, ep, cs)    \
                             : launch_gemm_ws<128, 4, MODE>(mA, mW, mO, M, N, K, ep, cs);
+    if (epilogue == 4) {
+      // fp32 outputs with few tiles and a long reduction (the wgrad GEMMs of the training step: 768 x 768 outputs
+      // over K = 12288 are 18 tiles of 192 k-blocks): split K so that about one wave of work items exists; the
+      // partial tiles are summed by TMA reduce-add stores into the zeroed output
+      const int NC = (variant == 6 || variant == 7 || variant == 9) ? 2 : 1;
+      const long long tiles = (long long)((N + BN - 1) / BN) * ((M + NC * kBM - 1) / (NC * kBM));
+      const int kblocks = (K + kBK - 1) / kBK;
+      int sms = 148;
+      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      int ksplit = 1;
+      if (g_gemm_ksplit > 0) ksplit = g_gemm_ksplit;
+      else if (g_gemm_ksplit == 0 && tiles * 2 <= sms / NC && kblocks >= 32) {
+        ksplit = (int)((sms / NC) / tiles);
+        if (ksplit > kblocks / 8) ksplit = kblocks / 8;
+      }
+      if (ksplit > 1) {
+        const int per = (kblocks + ksplit - 1) / ksplit;
+        ksplit = (kblocks + per - 1) / per;           // no empty split
+      }
+      if (ksplit > 1 &&
+          cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)N * 4, (size_t)M, cs) != cudaSuccess)
+        return GVF_ERR_CUDA;
+      return variant == 9   ? launch_gemm_ws<128, 6, 4, 2>(mA, mW, mO, M, N, K, ep, cs, ksplit)
+             : variant == 8 ? launch_gemm_ws<128, 5, 4, 1>(mA, mW, mO, M, N, K, ep, cs, ksplit)
+             : variant == 7 ? launch_gemm_ws<256, 4, 4, 2>(mA, mW, mO, M, N, K, ep, cs, ksplit)
+             : variant == 6 ? launch_gemm_ws<128, 5, 4, 2>(mA, mW, mO, M, N, K, ep, cs, ksplit)
+             : variant == 5 ? launch_gemm_ws<256, 3, 4>(mA, mW, mO, M, N, K, ep, cs, ksplit)
+                            : launch_gemm_ws<128, 4, 4>(mA, mW, mO, M, N, K, ep, cs, ksplit);
+    }
     switch (epilogue) {
-      GVF_WS(0) GVF_WS(1) GVF_WS(2) GVF_WS(3) GVF_WS(4) GVF_WS(6)
+      GVF_WS(0) GVF_WS(1) GVF_WS(2) GVF_WS(3) GVF_WS(6)
       case 7:
         return variant == 7 ? launch_gemm_ws<256, 4, 7, 2>(mA, mW, mO, M, N, K, ep, cs)
                             : launch_gemm_ws<256, 3, 7>(mA, mW, mO, M, N, K, ep, cs);
@@ -1198,6 +1244,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
 // tuning hook for the benchmarks: -1 automatic, 0 v1 (one tile per CTA), 1 persistent 128x128, 2 persistent 128x256
 extern "C" GVF_API void gvf_gemm_set_variant(int v) { g_gemm_variant = v; }
 extern "C" GVF_API void gvf_set_pdl(int on) { gvf::g_pdl_enabled = on ? 1 : 0; }
+extern "C" GVF_API void gvf_gemm_set_ksplit(int k) { g_gemm_ksplit = k; }
 
 extern "C" GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N,
                                     int K, int epilogue, const float* bias, void* out, int ldo,

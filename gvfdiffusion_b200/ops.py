@@ -481,3 +481,16 @@ def vae_query_embed_bwd(queries, gs, dout, dxyz=None, accumulate=False):
     check(_lib.lib().gvf_vae_query_embed_bwd(ptr(queries), queries.stride(0), ptr(gs), ptr(dout), Q, Cc, ptr(dgs), ptr(dxyz),
                                              dxyz.stride(0), int(accumulate), current_stream()), "gvf_vae_query_embed_bwd")
     return dgs, dxyz
+
+
+def skinny_expand(x, wt, out_f16=True):
+    """x fp32 [M, K <= 16] @ wt fp32 [K, N] -> [M, N] fp16 / fp32."""
+    _req(x, F32, "x")
+    _req(wt, F32, "wt")
+    M, K = x.shape
+    N = wt.shape[1]
+    assert x.stride(1) == 1 and wt.is_contiguous() and wt.shape[0] == K
+    out = torch.empty((M, N), dtype=F16 if out_f16 else F32, device=x.device)
+    check(_lib.lib().gvf_skinny_expand(ptr(x), x.stride(0), K, ptr(wt), M, N, ptr(out), int(out_f16), N, current_stream()),
+          "gvf_skinny_expand")
+    return out

@@ -6,6 +6,7 @@ Host orchestration only; every contraction / reduction is a libgvf_b200.so kerne
   * Linear dgrad  dX = dY W          -> gvf_gemm_f16(A = dY, "W" = W^T)            (W^T made once per weight version)
   * Linear wgrad  dW = dY^T X (fp32) -> gvf_gemm_f16(A = dY^T, "W" = X^T, fp32 out) over gvf_transpose_f16 copies
   * bias grads gvf_colsum; LayerNorm / GEGLU / query-embedding backward, K <= 16 Linears: csrc/backward.cu
+  * the decoder's output side (to_out followed by to_outputs, no non-linearity) composes into rank-14 products
   * attention forward with LSE + backward (dQ, dK, dV): csrc/attn.cu / csrc/attn_bwd.cu
 Activation gradients are fp16 (as under the reference's autocast), parameter gradients fp32.  The decoder queries are
 not chunked here (the reference chunks at 8192 queries with gradient checkpointing to save memory,
@@ -98,14 +99,17 @@ class VAEDecodeTrainEngine(VAEDecodeEngine):
         kv4 = sv["KV"].view(B, T, L, 2, H, d)
         q2 = sv["queries"].view(B * Q, -1)
         do2 = dout.view(B * T * Q, self.out_dim)
-        # to_outputs (model/autoencoder.py:574)
-        dlat = ops.small_linear(do2, self.w_o_t, None, out_f16=True)
+        # to_outputs o to_out (model/autoencoder.py:562-574): out = (ao W_d^T + b_d) W_o^T + b_o with no non-linearity in
+        # between, so the backward composes into rank-14 products -- no [B*T*Q, dim] x [dim, dim] dgrad / wgrad GEMM, no
+        # d lat tensor:  d ao = d out (W_o W_d),  dW_d = W_o^T (d out^T ao),  db_d = (sum d out) W_o,  dW_o = d out^T lat
+        wo = self.w_o[:self.out_dim].float()                                        # [14, dim]
+        wc = ops.skinny_outer(self.w_o_t.float(), self.w_dout)                      # W_o W_d  [14, dim]
         g["to_outputs.weight"] = ops.skinny_outer(do2, sv["lat"])
         g["to_outputs.bias"] = ops.colsum(do2)
-        # decoder cross-attention: to_out, attention (per object: queries shared by its T frames), to_q
-        dao = ops.gemm(dlat, self.w_dout_t, None, ops.EPI_F16).view(B, T, Q, H, d)
-        g[c + "to_out.weight"] = self._wgrad(dlat, sv["ao"].view(B * T * Q, dim))
-        g[c + "to_out.bias"] = ops.colsum(dlat)
+        s1 = ops.skinny_outer(do2, sv["ao"].view(B * T * Q, dim))                   # d out^T ao  [14, dim]
+        g[c + "to_out.weight"] = ops.skinny_expand(self.w_o_t.float(), s1, out_f16=False)
+        g[c + "to_out.bias"] = ops.skinny_expand(g["to_outputs.bias"].view(1, -1), wo, out_f16=False).view(-1)
+        dao = ops.skinny_expand(do2, wc).view(B, T, Q, H, d)
         dqd = torch.empty((B * Q, dim), dtype=F16, device=dev)
         for b in range(B):
             ops.attention_bwd(sv["qd"][b * Q:(b + 1) * Q].view(Q, H, d), kv4[b, :, :, 0], kv4[b, :, :, 1], sv["ao"][b], dao[b],

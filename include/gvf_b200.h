@@ -194,6 +194,9 @@ GVF_API void gvf_attn_set_workspace(void* ws, size_t bytes);
  * 1 / 2 persistent 128x128 / 128x256, 3 three CTAs per SM, 4 / 5 generation 2 (eight epilogue warps, TMA stores)
  * 128x128 / 128x256, 6 / 7 generation 2 on CTA pairs (cta_group::2) 256x128 / 256x256). */
 GVF_API void gvf_gemm_set_variant(int v);
+/* Split-K of the fp32-store epilogue (4): 0 automatic (few output tiles and a long reduction: the wgrad shapes of the
+ * training step; partial tiles are summed by TMA reduce-add stores, summation order not fixed), -1 never, n > 0 forced. */
+GVF_API void gvf_gemm_set_ksplit(int k);
 
 /* Programmatic dependent launch for the GEMM / attention / LayerNorm kernels (default OFF: measured slower
  * under CUDA-graph replay, see csrc/launch.h): the next kernel's prologue overlaps the previous grid's drain;
@@ -423,6 +426,11 @@ GVF_API int gvf_small_linear_bwd_input(const void* dy, int dy_is_f16, long long 
  * (transposed: proj / gs_embedding, x = layer input, y = dy) and of to_outputs (x = d out, y = layer input). */
 GVF_API int gvf_skinny_outer(const float* x, int ldx, int K, const void* y, int y_is_f16, long long ldy, long long M, int N,
                              float* workspace, size_t workspace_bytes, float* out, int accumulate, void* stream);
+/* out[M, N] (fp16 or fp32, row stride ldo) = x[M, K] Wt[K, N] for K <= 16, fp32 operands: rank-K expansions of the
+ * decoder's output side (d attention-out = d out [M, 14] @ (W_to_outputs W_to_out) [14, 768]: to_outputs follows
+ * decoder_cross_attn.to_out without a non-linearity, model/autoencoder.py:562-574, so their backward composes). */
+GVF_API int gvf_skinny_expand(const float* x, int ldx, int K, const float* Wt, long long M, int N, void* out,
+                              int out_is_f16, long long ldo, void* stream);
 /* Backward of gvf_vae_query_embed: d out fp16 [Q, C] -> d gs fp16 [Q, C], d xyz fp32 (rows of ld_dxyz >= 3 floats,
  * e.g. the first three columns of d queries [Q, 14]; accumulate != 0 adds to what is there). */
 GVF_API int gvf_vae_query_embed_bwd(const float* queries, int ldq, const void* gs, const void* dout, int Q, int C,

@@ -155,3 +155,36 @@ def test_query_embed_backward(C):
     dgs, dxyz = ops.vae_query_embed_bwd(queries, gs, dout)
     assert _rel(dgs, gsf.grad) < 3e-3, _rel(dgs, gsf.grad)
     assert _rel(dxyz, xyz.grad) < 2e-2, _rel(dxyz, xyz.grad)               # sin / cos arguments are fp16-rounded in the kernel
+
+
+def test_skinny_expand():
+    from gvfdiffusion_b200 import ops
+    g = _g(13)
+    for M, K, N in ((3000, 14, 768), (1, 14, 768), (777, 16, 96), (768, 14, 768)):
+        x, wt = _rand((M, K), g), _rand((K, N), g, 0.2)
+        ref = x @ wt
+        assert _rel(ops.skinny_expand(x, wt, out_f16=False), ref) < 1e-6
+        assert _rel(ops.skinny_expand(x, wt), ref) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,force", [(768, 768, 12288, 0), (768, 768, 12288, 5), (2304, 768, 12288, 0), (768, 3072, 12296, 0),
+                                          (96, 96, 4096, 0), (1536, 768, 12288, 3), (6144, 768, 12288, 0)])
+def test_gemm_split_k_fp32_store(M, N, K, force):
+    """wgrad shapes of the training step: few output tiles, long reduction -> (tile, k range) work items whose partial
+    tiles are summed by TMA reduce-add stores.  Against the fp32 matmul of the same fp16 operands."""
+    from gvfdiffusion_b200 import _lib, ops
+    g = _g(M + N + K + force)
+    a = _rand((M, K), g, 0.5).half()
+    w = _rand((N, K), g, 0.5).half()
+    b = _rand((N,), g)
+    ref = a.float() @ w.float().T
+    try:
+        _lib.lib().gvf_gemm_set_ksplit(force)
+        out = ops.gemm(a, w, None, ops.EPI_F32)
+        outb = ops.gemm(a, w, b, ops.EPI_F32)
+        _lib.lib().gvf_gemm_set_ksplit(-1)
+        plain = ops.gemm(a, w, None, ops.EPI_F32)
+    finally:
+        _lib.lib().gvf_gemm_set_ksplit(0)
+    assert _rel(out, ref) < 1e-5 and _rel(plain, ref) < 5e-5, (_rel(out, ref), _rel(plain, ref))   # one long fp32 chain is the less exact one
+    assert _rel(outb, ref + b) < 1e-5
