@@ -205,6 +205,10 @@ def main():
                          "GEMMs lose the SM the single-CTA FPS sits on), end to end 83.1 vs 88.0 frames/s -- default off")
     ap.add_argument("--attn-dbg", type=lambda v: int(v, 0), default=0, help="gvf_attn_set_debug value (kernel-variant A/B)")
     ap.add_argument("--pdl", action="store_true", help="launch with the programmatic-dependent-launch attribute (A/B; default off)")
+    ap.add_argument("--config", default="cfg1", choices=["cfg1", "cfg3"],
+                    help="cfg1 (default): BASELINE.json configs[1], the headline inference metric.  cfg3: configs[2], one "
+                         "training step of the motion-VAE decoder + 24-frame render, forward + backward (tools/train_step_bench.py; "
+                         "N = 1), printed as its own JSON line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -220,6 +224,21 @@ def main():
         return run_reference(args, rank)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    if args.config == "cfg3":
+        if rank == 0:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+            import train_step_bench as TSB
+            mon = ClockSampler(local)
+            mon.start()
+            res = TSB.measure(steps=args.steps, warmup=max(args.warmup, 3), standin=not args.no_gpu_reference)
+            mon.stop_flag = True
+            mon.join(timeout=2)
+            res.update({"n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+                        "ms_per_step": res["ms_forward"] + res["ms_backward"], "higher_is_better": True, "scaling": "weak",
+                        "vs_baseline": None, "clocks": mon.summary()})
+            real_stdout.write(json.dumps(res) + "\n")
+            real_stdout.flush()
+        return
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

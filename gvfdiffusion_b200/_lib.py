@@ -69,6 +69,8 @@ _SIGS = {
     "gvf_attn_set_debug": (None, [C.c_int]),
     "gvf_attn_set_workspace": (None, [_P, C.c_size_t]),
     "gvf_attn_set_trace": (None, [_P]),
+    "gvf_gemm_tn_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "gvf_attn_bwd_set_serial": (None, [C.c_int]),
     "gvf_gemm_set_variant": (None, [C.c_int]),
     "gvf_gemm_set_ksplit": (None, [C.c_int]),
     "gvf_set_pdl": (None, [C.c_int]),

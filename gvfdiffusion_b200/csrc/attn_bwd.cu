@@ -50,6 +50,11 @@ struct AttnBwdArgs {
   int Lq, Lk, H, Lqp, Nb;
   int q_batch_mul, kv_batch_mul;   // 0: tensor shared across the batch
   float scale, scale_log2e;
+  // 1: the issuer waits for the TS MMAs of block i (which read the fp16 P / dS columns) before it issues the SS MMAs
+  // of block i + 1 (which overwrite them as fp32 S / dP).  0 (default): issue them back to back -- tcgen05.mma
+  // instructions of one thread execute in issue order, so the hazard is resolved inside the tensor pipe and one
+  // commit -> mbarrier -> wait hop per block disappears (gvf_attn_bwd_set_serial for A/B runs).
+  int serial;
 };
 
 // D[b,h,q] = sum_d dO O (fp32); rows q in [Lq, Lqp) are zeroed.  One thread per (b, q, h).
@@ -161,7 +166,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       for (int i = 0; i < n_blk; ++i) {
         const int j = i >> 1, s = j % S;
         if ((i & 1) == 0) { mbar_wait(&q_full[s], (j / S) & 1); tc_fence_after(); }
-        if (i > 0) { mbar_wait(&o_done[x], (i - 1) & 1); tc_fence_after(); }     // P / dS columns are free again
+        if (i > 0 && a.serial) { mbar_wait(&o_done[x], (i - 1) & 1); tc_fence_after(); }   // P / dS columns are free again
         const uint32_t qa = smem_u32(sQ) + s * STAGE_BYTES + (i & 1) * 64 * ROWB;
         const uint32_t da = qa + TILE_BYTES;
 #pragma unroll
@@ -351,7 +356,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         for (int i = 0; i < n_blk; ++i, ++g) {
           const int s = t % S;
           if ((i & 1) == 0) { mbar_wait(&kv_full[s], (t / S) & 1); tc_fence_after(); }
-          if (g > 0) { mbar_wait(&dq_done[x], (g - 1) & 1); tc_fence_after(); }   // dS columns are free again
+          if (g > 0 && a.serial) { mbar_wait(&dq_done[x], (g - 1) & 1); tc_fence_after(); }   // dS columns are free again
           const uint32_t ka = smem_u32(sKV) + s * 2 * TILE_BYTES + (i & 1) * 64 * ROWB;
           const uint32_t va = ka + TILE_BYTES;
 #pragma unroll
@@ -464,6 +469,9 @@ static int launch_attn_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const C
 
 using namespace gvf;
 
+static int g_attn_bwd_serial = 0;
+extern "C" GVF_API void gvf_attn_bwd_set_serial(int v) { g_attn_bwd_serial = v; }
+
 extern "C" GVF_API int gvf_attn_bwd_f16(const void* q, const void* k, const void* v, const void* o, const void* dout,
                                         const float* lse2, float* dsum, void* dq, void* dk, void* dv, int Nb, int Lq,
                                         int Lk, int H, int D, int lse_ld, const long long* q_strides,
@@ -519,5 +527,6 @@ extern "C" GVF_API int gvf_attn_bwd_f16(const void* q, const void* k, const void
   a.Lq = Lq; a.Lk = Lk; a.H = H; a.Lqp = lse_ld; a.Nb = Nb;
   a.q_batch_mul = q_shared ? 0 : 1; a.kv_batch_mul = 1;
   a.scale = scale; a.scale_log2e = scale * 1.4426950408889634f;
+  a.serial = g_attn_bwd_serial;
   return D == 64 ? launch_attn_bwd<64>(mq, mk, mv, mdo, a, q_shared, st) : launch_attn_bwd<32>(mq, mk, mv, mdo, a, q_shared, st);
 }

@@ -182,20 +182,21 @@ __global__ void __launch_bounds__(256) small_linear_bwd_input_kernel(const TDy* 
     }
 }
 
-// partial[slab][k][n] = sum_{m in slab} x[m, k] * y[m, n]   (k < K <= 16; thread = column n, x rows broadcast from
-// shared memory).  Serves dW^T of proj / gs_embedding (x = the layer input, y = dy fp16) and dW of to_outputs
-// (x = dOut fp32 [M, 14], y = the layer input fp16).
+// partial[slab][k][n] = sum_{m in slab} x[m, k] * y[m, n]   (k < K <= 16; thread = two adjacent columns, x rows broadcast
+// from shared memory as float4).  Serves dW^T of proj / gs_embedding (x = the layer input, y = dy fp16) and dW of
+// to_outputs (x = dOut fp32 [M, 14], y = the layer input fp16).
 template <typename TY>
 __global__ void __launch_bounds__(256) skinny_outer_partial_kernel(const float* __restrict__ x, int ldx, int K,
                                                                    const TY* __restrict__ y, long long ldy, long long M,
                                                                    int N, int rows_per_slab, float* __restrict__ partial) {
-  __shared__ float sx[64][16];
-  const int n = blockIdx.x * 256 + threadIdx.x;
+  __shared__ __align__(16) float sx[64][16];
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 2;
   const long long m0 = (long long)blockIdx.y * rows_per_slab;
   const long long m1 = m0 + rows_per_slab < M ? m0 + rows_per_slab : M;
-  float acc[16];
+  const bool vec = (sizeof(TY) == 2) && ((ldy & 1) == 0) && ((reinterpret_cast<uintptr_t>(y) & 3) == 0) && n + 1 < N;
+  float a0[16], a1[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 16; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
   for (long long mb = m0; mb < m1; mb += 64) {
     __syncthreads();
     for (int t = threadIdx.x; t < 64 * 16; t += 256) {
@@ -205,15 +206,41 @@ __global__ void __launch_bounds__(256) skinny_outer_partial_kernel(const float* 
     __syncthreads();
     if (n < N) {
       const int lim = (int)(m1 - mb < 64 ? m1 - mb : 64);
+#pragma unroll 2
       for (int r = 0; r < lim; ++r) {
-        const float yv = (float)y[(mb + r) * ldy + n];
+        float y0, y1 = 0.f;
+        if constexpr (sizeof(TY) == 2) {
+          if (vec) {
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(y + (mb + r) * ldy + n));
+            y0 = v.x; y1 = v.y;
+          } else {
+            y0 = __half2float(y[(mb + r) * ldy + n]);
+            if (n + 1 < N) y1 = __half2float(y[(mb + r) * ldy + n + 1]);
+          }
+        } else {
+          y0 = y[(mb + r) * ldy + n];
+          if (n + 1 < N) y1 = y[(mb + r) * ldy + n + 1];
+        }
+        const float4* xr = reinterpret_cast<const float4*>(sx[r]);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = fmaf(sx[r][k], yv, acc[k]);
+        for (int q = 0; q < 4; ++q) {
+          const float4 xv = xr[q];
+          a0[4 * q] = fmaf(xv.x, y0, a0[4 * q]);         a1[4 * q] = fmaf(xv.x, y1, a1[4 * q]);
+          a0[4 * q + 1] = fmaf(xv.y, y0, a0[4 * q + 1]); a1[4 * q + 1] = fmaf(xv.y, y1, a1[4 * q + 1]);
+          a0[4 * q + 2] = fmaf(xv.z, y0, a0[4 * q + 2]); a1[4 * q + 2] = fmaf(xv.z, y1, a1[4 * q + 2]);
+          a0[4 * q + 3] = fmaf(xv.w, y0, a0[4 * q + 3]); a1[4 * q + 3] = fmaf(xv.w, y1, a1[4 * q + 3]);
+        }
       }
     }
   }
-  if (n < N)
-    for (int k = 0; k < K; ++k) partial[((long long)blockIdx.y * K + k) * N + n] = acc[k];
+  if (n < N) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) {
+        partial[((long long)blockIdx.y * K + k) * N + n] = a0[k];
+        if (n + 1 < N) partial[((long long)blockIdx.y * K + k) * N + n + 1] = a1[k];
+      }
+  }
 }
 
 // out[m, n] = sum_k x[m, k] Wt[k, n]   (K <= 16, fp32 operands; out fp16 or fp32): rank-K expansion, e.g. the gradient of
@@ -424,7 +451,7 @@ GVF_API int gvf_skinny_outer(const float* x, int ldx, int K, const void* y, int 
   int slabs;
   const int rps = slab_rows(M, &slabs);
   if (workspace_bytes < (size_t)slabs * K * N * sizeof(float)) return GVF_ERR_WORKSPACE;
-  const dim3 grid((N + 255) / 256, slabs);
+  const dim3 grid((N + 511) / 512, slabs);
   if (y_is_f16)
     skinny_outer_partial_kernel<__half><<<grid, 256, 0, ST(stream)>>>(x, ldx, K, (const __half*)y, ldy, M, N, rps, workspace);
   else

@@ -393,7 +393,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 //     the accumulator wait, so its DRAM latency overlaps the main loop of the tile.
 // Same rounding points as epilogue_tile() above.  320 threads: warp 0 TMA producer, warp 1 MMA issuer,
 // warps 2-9 epilogue; accumulators double buffered in TMEM (2 x BN columns).
-template <int BN, int STAGES, int MODE, int NCTA>
+// TRANS (NCTA = 1 only): both operands are MN-major -- out[m, n] = sum_r A[r, m] W[r, n] with A [R, M] and W [R, N]
+// row-major, i.e. the weight gradient dW = dY^T X straight from the activation tensors (no transposed copies).  A
+// stage holds 64 reduction rows: 64-column boxes (128 B inner extent, SWIZZLE_128B) of 8 KB each, two for A and
+// BN / 64 for W; the shared-memory descriptors walk them with LBO = 8 KB between the 64-wide column blocks and
+// SBO = 1 KB between 8-row groups (canonical MN-major layout), 2 KB per 16-row k-step.
+template <int BN, int STAGES, int MODE, int NCTA, bool TRANS = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ CUtensorMap mapO, int M, int N, int K, GemmEpi ep, int ksplit) {
@@ -438,8 +443,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = 0; kb < (nkb < STAGES ? nkb : STAGES); ++kb) {
           mbar_arrive_expect_tx(&full_bar[kb], STAGE_BYTES);
           uint8_t* st = smem + kb * STAGE_BYTES;
-          tma_load_2d(st, &mapA, &full_bar[kb], (kb0 + kb) * kBK, tile_m * kBM);
-          tma_load_2d(st + A_BYTES, &mapW, &full_bar[kb], (kb0 + kb) * kBK, tile_n * BN);
+          if constexpr (TRANS) {
+            for (int b = 0; b < kBM / 64; ++b) tma_load_2d(st + b * 8192, &mapA, &full_bar[kb], tile_m * kBM + b * 64, (kb0 + kb) * kBK);
+            for (int b = 0; b < BN / 64; ++b) tma_load_2d(st + A_BYTES + b * 8192, &mapW, &full_bar[kb], tile_n * BN + b * 64, (kb0 + kb) * kBK);
+          } else {
+            tma_load_2d(st, &mapA, &full_bar[kb], (kb0 + kb) * kBK, tile_m * kBM);
+            tma_load_2d(st + A_BYTES, &mapW, &full_bar[kb], (kb0 + kb) * kBK, tile_n * BN);
+          }
         }
       }
     } else {
@@ -481,6 +491,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
               tma_load_2d_2cta(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
               tma_load_2d_2cta(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN + (int)rank * WROWS);
+            } else if constexpr (TRANS) {
+              mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+              for (int b = 0; b < kBM / 64; ++b) tma_load_2d(st + b * 8192, &mapA, &full_bar[s], tile_m * kBM + b * 64, kb * kBK);
+              for (int b = 0; b < BN / 64; ++b) tma_load_2d(st + A_BYTES + b * 8192, &mapW, &full_bar[s], tile_n * BN + b * 64, kb * kBK);
             } else {
               mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
               tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
@@ -496,9 +510,11 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // MMA issuer (leader CTA of a pair): warp-uniform loop; the descriptors' high words are constants, the low
     // words (address >> 4 | LBO field) advance by adds; only tcgen05.mma / commit sit behind elect.sync
     if (rank == 0) {
-      const uint32_t idesc = make_idesc_f16(kBM * NCTA, BN, 0, 0);
-      const uint32_t d_hi = (uint32_t)(make_smem_desc(0, 16, 1024, SWZ_128B) >> 32);
-      const uint32_t a_lo0 = (uint32_t)make_smem_desc(smem_u32(smem), 16, 1024, SWZ_128B);
+      const uint32_t idesc = make_idesc_f16(kBM * NCTA, BN, TRANS ? 1 : 0, TRANS ? 1 : 0);
+      constexpr uint32_t LBO = TRANS ? 8192u : 16u;          // MN-major: between 64-column blocks; K-major: unused
+      constexpr uint32_t KSTEP16 = TRANS ? 128u : 2u;        // descriptor advance per 16-deep k-step (16 B units)
+      const uint32_t d_hi = (uint32_t)(make_smem_desc(0, LBO, 1024, SWZ_128B) >> 32);
+      const uint32_t a_lo0 = (uint32_t)make_smem_desc(smem_u32(smem), LBO, 1024, SWZ_128B);
       constexpr uint32_t STAGE16 = STAGE_BYTES >> 4, A16 = A_BYTES >> 4;
       const uint32_t b_full = smem_u32(&full_bar[0]), b_empty = smem_u32(&empty_bar[0]);
       int s = 0, lt = 0;
@@ -515,8 +531,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t ad = ((uint64_t)d_hi << 32) | (s_lo + 2 * k);
-              const uint64_t wd = ((uint64_t)d_hi << 32) | (s_lo + A16 + 2 * k);
+              const uint64_t ad = ((uint64_t)d_hi << 32) | (s_lo + KSTEP16 * k);
+              const uint64_t wd = ((uint64_t)d_hi << 32) | (s_lo + A16 + KSTEP16 * k);
               if constexpr (NCTA == 2) mma_ss_2cta(d_tmem, ad, wd, idesc, ((kb - kb0) | k) != 0);
               else mma_ss(d_tmem, ad, wd, idesc, ((kb - kb0) | k) != 0);
             }
@@ -791,14 +807,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
-template <int BN, int STAGES, int MODE, int NCTA = 1>
+template <int BN, int STAGES, int MODE, int NCTA = 1, bool TRANS = false>
 static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CUtensorMap& mO, int M, int N, int K,
                           const GemmEpi& ep, cudaStream_t st, int ksplit = 1) {
   constexpr int SMEM = STAGES * (kBM * kBK * 2 + (BN / NCTA) * kBK * 2) + 8 * 2 * 4096 + 1024;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE, NCTA, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
         cudaSuccess)
       return GVF_ERR_CUDA;
     int dev = 0;
@@ -810,7 +826,7 @@ static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CU
   const int slots = num_sms / NCTA;
   const int grid = (tiles < slots ? tiles : slots) * NCTA;
   if constexpr (NCTA == 1) {
-    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep, ksplit) == cudaSuccess
+    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1, TRANS>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep, ksplit) == cudaSuccess
                ? GVF_OK : GVF_ERR_CUDA;
   } else {
     cudaLaunchConfig_t cfg = {};
@@ -1314,4 +1330,45 @@ extern "C" GVF_API int gvf_gemm_resid_ln_f16(const void* A, int lda, const void*
   }
   return launch_pdl(gemm_ln_kernel, dim3((M + kBM - 1) / kBM), dim3(320), SMEM, (cudaStream_t)stream, mA, mW, mX, mY,
                     M, K, ep) == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+// Weight gradient without transposed copies: out[M, N] fp32 (+ nothing) = A[R, M]^T W[R, N], A / W fp16 row-major
+// activations (dY and X of a Linear: dW[out, in] = dY^T X).  Both operands enter the tensor core MN-major; split-K over R
+// like the fp32-store epilogue of gvf_gemm_f16.  M, N multiples of 8 (16 B rows), any R.
+extern "C" GVF_API int gvf_gemm_tn_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int R, float* out,
+                                       int ldo, void* stream) {
+  if (!A || !W || !out || M <= 0 || N <= 0 || R <= 0) return GVF_ERR_INVALID;
+  if ((M % 8) || (N % 8) || (lda % 8) || (ldw % 8) || (ldo % 4) || lda < M || ldw < N || ldo < N) return GVF_ERR_INVALID;
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
+  CUtensorMap mA, mW, mO;
+  const uint64_t dA[2] = {(uint64_t)M, (uint64_t)R}, sA[2] = {1, (uint64_t)lda};
+  const uint64_t dW[2] = {(uint64_t)N, (uint64_t)R}, sW[2] = {1, (uint64_t)ldw};
+  const uint32_t box[2] = {64, kBK};
+  if (!make_tmap_f16(&mA, A, 2, dA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
+  if (!make_tmap_f16(&mW, W, 2, dW, sW, box, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
+  if (!make_tmap_2d(&mO, out, 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, 32, 32)) return GVF_ERR_CUDA;
+  GemmEpi ep;
+  ep.mode = 4; ep.bias = nullptr; ep.out = out; ep.gate = nullptr; ep.gate_stride = 0; ep.rows_per_batch = 1; ep.ldo = ldo;
+  ep.gamma_q = nullptr; ep.gamma_k = nullptr; ep.norm_cols = 0;
+  cudaStream_t cs = (cudaStream_t)stream;
+  const bool wide = (N % 256) == 0;
+  const int BN = wide ? 256 : 128;
+  const long long tiles = (long long)((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
+  const int kblocks = (R + kBK - 1) / kBK;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int ksplit = 1;
+  if (g_gemm_ksplit > 0) ksplit = g_gemm_ksplit;
+  else if (g_gemm_ksplit == 0 && kblocks >= 16) {
+    ksplit = (int)((2 * sms + tiles - 1) / tiles);            // about two waves of work items
+    if (ksplit > kblocks / 4) ksplit = kblocks / 4;
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (ksplit > 1) {
+    const int per = (kblocks + ksplit - 1) / ksplit;
+    ksplit = (kblocks + per - 1) / per;
+  }
+  if (ksplit > 1 && cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)N * 4, (size_t)M, cs) != cudaSuccess) return GVF_ERR_CUDA;
+  return wide ? launch_gemm_ws<256, 3, 4, 1, true>(mA, mW, mO, M, N, R, ep, cs, ksplit)
+              : launch_gemm_ws<128, 4, 4, 1, true>(mA, mW, mO, M, N, R, ep, cs, ksplit);
 }

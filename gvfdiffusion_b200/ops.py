@@ -494,3 +494,17 @@ def skinny_expand(x, wt, out_f16=True):
     check(_lib.lib().gvf_skinny_expand(ptr(x), x.stride(0), K, ptr(wt), M, N, ptr(out), int(out_f16), N, current_stream()),
           "gvf_skinny_expand")
     return out
+
+
+def gemm_tn(a, w, out=None):
+    """fp32 [M, N] = a[R, M]^T @ w[R, N] (fp16 row-major activations): the weight gradient dW = dY^T X, no transposes."""
+    _req(a, F16, "a")
+    _req(w, F16, "w")
+    R, M = a.shape
+    N = w.shape[1]
+    assert w.shape[0] == R and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=F32, device=a.device)
+    check(_lib.lib().gvf_gemm_tn_f16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, R, ptr(out), out.stride(0),
+                                     current_stream()), "gvf_gemm_tn_f16")
+    return out

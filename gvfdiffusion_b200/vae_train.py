@@ -4,7 +4,8 @@ configs[4]; reference train_vae.py:293-353 -> model/autoencoder.py:552-609 under
 
 Host orchestration only; every contraction / reduction is a libgvf_b200.so kernel:
   * Linear dgrad  dX = dY W          -> gvf_gemm_f16(A = dY, "W" = W^T)            (W^T made once per weight version)
-  * Linear wgrad  dW = dY^T X (fp32) -> gvf_gemm_f16(A = dY^T, "W" = X^T, fp32 out) over gvf_transpose_f16 copies
+  * Linear wgrad  dW = dY^T X (fp32) -> gvf_gemm_tn_f16: both operands MN-major from 64 x 64 TMA boxes, split-K with
+    TMA reduce-add (no transposed activation copies)
   * bias grads gvf_colsum; LayerNorm / GEGLU / query-embedding backward, K <= 16 Linears: csrc/backward.cu
   * the decoder's output side (to_out followed by to_outputs, no non-linearity) composes into rank-14 products
   * attention forward with LSE + backward (dQ, dK, dV): csrc/attn.cu / csrc/attn_bwd.cu
@@ -81,8 +82,9 @@ class VAEDecodeTrainEngine(VAEDecodeEngine):
     # ------------------------------------------------------------------------------------------------ backward
     @staticmethod
     def _wgrad(dy, x):
-        """dW fp32 [N_out, K_in] = dy[M, N_out]^T x[M, K_in]."""
-        return ops.gemm(ops.transpose(dy), ops.transpose(x), None, ops.EPI_F32)
+        """dW fp32 [N_out, K_in] = dy[M, N_out]^T x[M, K_in]: both activations enter the tensor core MN-major as they
+        lie in memory (gvf_gemm_tn_f16), split over the token dimension."""
+        return ops.gemm_tn(dy, x)
 
     def backward(self, sv, dout):
         """dout [B, T, Q, out_dim] fp32 -> (grads {reference parameter name: fp32 tensor}, dz, dqueries)."""

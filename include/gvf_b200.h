@@ -406,6 +406,15 @@ GVF_API int gvf_attn_bwd_f16(const void* q, const void* k, const void* v, const 
                              const long long* v_strides, const long long* o_strides, const long long* do_strides,
                              const long long* dq_strides, const long long* dk_strides, const long long* dv_strides,
                              int q_shared, float scale, void* stream);
+/* A/B hook of the attention backward kernels: 1 = the MMA issuer waits for the P / dS consumers of a block before it
+ * overwrites their TMEM columns with the next block's scores (default 0: ordered by the tensor pipe itself). */
+GVF_API void gvf_attn_bwd_set_serial(int v);
+/* Weight gradient of a Linear without transposed copies: out[M, N] fp32 = A[R, M]^T W[R, N] (A = dY, W = X, fp16
+ * row-major with row strides lda / ldw; dW[out, in] = dY^T X, reference autograd of nn.Linear under train_vae.py:352).
+ * Both operands enter tcgen05.mma MN-major straight from 64 x 64 TMA boxes; split-K over R, partial tiles summed by
+ * TMA reduce-add.  M, N multiples of 8. */
+GVF_API int gvf_gemm_tn_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int R, float* out, int ldo,
+                            void* stream);
 /* out[C, ld_out] = in[R, C]^T (fp16); columns [R, ld_out) of every output row are zero (ld_out = R rounded up to 8
  * so that the transposed tensor is a legal GEMM operand). */
 GVF_API int gvf_transpose_f16(const void* in, int R, int C, long long ld_in, void* out, long long ld_out, void* stream);
