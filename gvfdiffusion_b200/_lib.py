@@ -19,7 +19,7 @@ class RasterParams(C.Structure):
     _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("tanfovx", C.c_float), ("tanfovy", C.c_float),
                 ("kernel_size", C.c_float), ("scale_modifier", C.c_float), ("bg", C.c_float * 3),
                 ("aabb", C.c_float * 6), ("scale_bias", C.c_float), ("min_kernel", C.c_float),
-                ("opacity_bias", C.c_float), ("softplus", C.c_int32)]
+                ("opacity_bias", C.c_float), ("softplus", C.c_int32), ("mip_filter", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -98,6 +98,8 @@ _SIGS = {
     "gvf_sparse_conv_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "gvf_sparse_neighbor_map": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P]),
     "gvf_sparse_im2col_f16": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "gvf_sparse_conv_gemm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int,
+                                           C.c_int, _P]),
     "gvf_raster_set_sort": (None, [C.c_int]),
     "gvf_affine_lastdim": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, C.c_float, C.c_float, _P, _P]),
 }

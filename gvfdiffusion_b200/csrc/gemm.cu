@@ -37,6 +37,11 @@ struct GemmEpi {
   const float* gamma_q;     // mode 6: per-head RMS-norm gains [H, 32] for columns [0, norm_cols/2)
   const float* gamma_k;     //         and [norm_cols/2, norm_cols)
   int norm_cols;            // mode 6: columns below this are RMS-normalised per 32-wide head
+  // GATHER kernels (submanifold sparse convolution): row m of the A operand in k-block kb is row
+  // gather_idx[m * gather_k3 + kb / gather_cb] of the tensor behind mapA (negative = absent voxel = zeros), columns
+  // [64 (kb % gather_cb), +64)
+  const int* gather_idx = nullptr;
+  int gather_k3 = 0, gather_cb = 1;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -398,7 +403,11 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 // stage holds 64 reduction rows: 64-column boxes (128 B inner extent, SWIZZLE_128B) of 8 KB each, two for A and
 // BN / 64 for W; the shared-memory descriptors walk them with LBO = 8 KB between the 64-wide column blocks and
 // SBO = 1 KB between 8-row groups (canonical MN-major layout), 2 KB per 16-row k-step.
-template <int BN, int STAGES, int MODE, int NCTA, bool TRANS = false>
+// GATHER (NCTA = 1 only): the A operand is never materialised -- the producer warp fetches the 128 rows of a stage
+// with 32 `cp.async.bulk.tensor.2d.tile::gather4` loads (lane l: rows 4 l .. 4 l + 3 of the tile, row indices read
+// from the neighbour map, out-of-range = zero-filled), each landing as four 128 B rows exactly where the one-box load
+// of the dense kernel would have put them (TMA swizzling is a function of the shared-memory address).
+template <int BN, int STAGES, int MODE, int NCTA, bool TRANS = false, bool GATHER = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ CUtensorMap mapO, int M, int N, int K, GemmEpi ep, int ksplit) {
@@ -432,7 +441,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int i = 0; i < 16; ++i) mbar_init(&xres_bar[i >> 1][i & 1], 1);
     fence_barrier_init();
     tma_prefetch_desc(&mapO);
-    if constexpr (NCTA == 1) {
+    if constexpr (NCTA == 1 && !GATHER) {
       // first stages of the first tile: requested by the thread that has just created the barriers, so their
       // latency overlaps the TMEM allocation and the CTA barrier (pairs must wait for the cluster barrier first)
       pdl_wait();
@@ -473,7 +482,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int s = 0;
     uint32_t ph = 0;                               // parity of full / empty for the current pass over the ring
     int skip = 0;
-    if (NCTA == 1 && first_tile < num_tiles) {                               // requested in the prologue
+    if (NCTA == 1 && !GATHER && first_tile < num_tiles) {                    // requested in the prologue
       const int kb0 = (first_tile / out_tiles) * kb_per, nkb = min(kblocks, kb0 + kb_per) - kb0;
       skip = nkb < STAGES ? nkb : STAGES;
     }
@@ -482,7 +491,24 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int tile_m = (tile / tiles_n) * NCTA + (int)rank, tile_n = tile % tiles_n;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (skip > 0) --skip;
-        else {
+        else if constexpr (GATHER) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          const int kk = kb / ep.gather_cb, cc = (kb - kk * ep.gather_cb) * kBK;
+          const int lane_p = threadIdx.x & 31;
+          int ridx[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = tile_m * kBM + 4 * lane_p + j;
+            ridx[j] = r < M ? __ldg(ep.gather_idx + (size_t)r * ep.gather_k3 + kk) : -1;
+          }
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_2d(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN);
+          }
+          __syncwarp();
+          tma_gather4_2d(st + lane_p * 512, &mapA, &full_bar[s], cc, ridx[0], ridx[1], ridx[2], ridx[3]);
+        } else {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (elect_one()) {
             uint8_t* st = smem + s * STAGE_BYTES;
@@ -807,14 +833,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
-template <int BN, int STAGES, int MODE, int NCTA = 1, bool TRANS = false>
+template <int BN, int STAGES, int MODE, int NCTA = 1, bool TRANS = false, bool GATHER = false>
 static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CUtensorMap& mO, int M, int N, int K,
                           const GemmEpi& ep, cudaStream_t st, int ksplit = 1) {
   constexpr int SMEM = STAGES * (kBM * kBK * 2 + (BN / NCTA) * kBK * 2) + 8 * 2 * 4096 + 1024;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE, NCTA, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE, NCTA, TRANS, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
         cudaSuccess)
       return GVF_ERR_CUDA;
     int dev = 0;
@@ -826,7 +852,7 @@ static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CU
   const int slots = num_sms / NCTA;
   const int grid = (tiles < slots ? tiles : slots) * NCTA;
   if constexpr (NCTA == 1) {
-    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1, TRANS>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep, ksplit) == cudaSuccess
+    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1, TRANS, GATHER>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep, ksplit) == cudaSuccess
                ? GVF_OK : GVF_ERR_CUDA;
   } else {
     cudaLaunchConfig_t cfg = {};
@@ -1371,4 +1397,39 @@ extern "C" GVF_API int gvf_gemm_tn_f16(const void* A, int lda, const void* W, in
   if (ksplit > 1 && cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)N * 4, (size_t)M, cs) != cudaSuccess) return GVF_ERR_CUDA;
   return wide ? launch_gemm_ws<256, 3, 4, 1, true>(mA, mW, mO, M, N, R, ep, cs, ksplit)
               : launch_gemm_ws<128, 4, 4, 1, true>(mA, mW, mO, M, N, R, ep, cs, ksplit);
+}
+
+// Submanifold sparse convolution as ONE kernel (reference sparse/conv/conv_spconv.py:6-15 ->
+// spconv.SubMConv3d): out[n, :] = epilogue(sum_k W[:, k, :] x[nbr[n, k]] + bias).  x fp16 [N, Cin] (row stride ldx), nbr
+// int32 [N, K3] from gvf_sparse_neighbor_map (-1 = absent), W fp16 [Cout, K3 * Cin].  The im2col operand of
+// gvf_sparse_im2col_f16 + gvf_gemm_f16 is never written: the GEMM's TMA producer gathers the neighbour rows itself
+// (tile::gather4).  Cin % 64 == 0; epilogue 0 (fp16 store) or 4 (fp32 store).  Bit-identical to the two-kernel path.
+extern "C" GVF_API int gvf_sparse_conv_gemm_f16(const void* x, int ldx, const int* nbr, int N, int K3, int Cin, const void* W,
+                                                int ldw, int Cout, const float* bias, void* out, int ldo, int epilogue,
+                                                void* stream) {
+  if (!x || !nbr || !W || !out || N <= 0 || K3 <= 0 || Cin <= 0 || Cout <= 0) return GVF_ERR_INVALID;
+  if ((Cin % 64) || (Cout % 8) || (ldx % 8) || (ldw % 8) || ldx < Cin || ldw < K3 * Cin) return GVF_ERR_UNSUPPORTED;
+  if (epilogue != 0 && epilogue != 4) return GVF_ERR_UNSUPPORTED;
+  if (((uintptr_t)x | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
+  if ((ldo * (epilogue == 4 ? 4 : 2)) % 16) return GVF_ERR_INVALID;
+  const int K = K3 * Cin;
+  CUtensorMap mA, mW, mO;
+  const uint64_t dA[2] = {(uint64_t)Cin, (uint64_t)N}, sA[2] = {1, (uint64_t)ldx};
+  const uint64_t dW[2] = {(uint64_t)K, (uint64_t)Cout}, sW[2] = {1, (uint64_t)ldw};
+  const bool wide = (Cout % 256) == 0;
+  const uint32_t bA[2] = {kBK, 1}, bW[2] = {kBK, (uint32_t)(wide ? 256 : 128)};
+  if (!make_tmap_f16(&mA, x, 2, dA, sA, bA, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
+  if (!make_tmap_f16(&mW, W, 2, dW, sW, bW, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
+  if (!make_tmap_2d(&mO, out, epilogue == 4 ? 4 : 2, (uint64_t)Cout, (uint64_t)N, (uint64_t)ldo, epilogue == 4 ? 32 : 64, 32))
+    return GVF_ERR_CUDA;
+  GemmEpi ep;
+  ep.mode = epilogue; ep.bias = bias; ep.out = out; ep.gate = nullptr; ep.gate_stride = 0; ep.rows_per_batch = 1; ep.ldo = ldo;
+  ep.gamma_q = nullptr; ep.gamma_k = nullptr; ep.norm_cols = 0;
+  ep.gather_idx = nbr; ep.gather_k3 = K3; ep.gather_cb = Cin / kBK;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (epilogue == 0)
+    return wide ? launch_gemm_ws<256, 3, 0, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs)
+                : launch_gemm_ws<128, 4, 0, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs);
+  return wide ? launch_gemm_ws<256, 3, 4, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs)
+              : launch_gemm_ws<128, 4, 4, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs);
 }

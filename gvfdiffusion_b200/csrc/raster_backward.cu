@@ -423,8 +423,9 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PreBwdAr
     const float ks = prm.kernel_size;
     const float d0r = a0 * c0 - b * b, d1r = (a0 + ks) * (c0 + ks) - b * b;
     const float det0 = fmaxf(1e-6f, d0r), det1 = fmaxf(1e-6f, d1r);
-    const bool coef_zero = det0 <= 1e-6f || det1 <= 1e-6f;
-    const float coef = coef_zero ? 0.f : sqrtf(det0 / (det1 + 1e-6f) + 1e-6f);
+    const bool mip = prm.mip_filter != 0;
+    const bool coef_zero = mip && (det0 <= 1e-6f || det1 <= 1e-6f);
+    const float coef = !mip ? 1.0f : (coef_zero ? 0.f : sqrtf(det0 / (det1 + 1e-6f) + 1e-6f));
     const float ca = a0 + ks, cc = c0 + ks;
     const float det = ca * cc - b * b;
     const float di2 = 1.0f / (det * det);
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PreBwdAr
     float g_c = (gA * (-b * b) + gB * (ca * b) + gC * (-ca * ca)) * di2;
     // ---- mip opacity compensation
     g_opac = coef * g_opp;
-    if (!coef_zero) {
+    if (mip && !coef_zero) {
       const float g_coef = opac * g_opp;
       const float g_r = g_coef / (2.0f * coef);
       const float g_det0 = (d0r > 1e-6f) ? g_r / (det1 + 1e-6f) : 0.f;

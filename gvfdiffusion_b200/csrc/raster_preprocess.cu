@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
     const float det1 = fmaxf(1e-6f, (ca + ks) * (cc + ks) - cb * cb);
     float coef = sqrtf(det0 / (det1 + 1e-6f) + 1e-6f);
     if (det0 <= 1e-6f || det1 <= 1e-6f) coef = 0.0f;
+    if (!prm.mip_filter) coef = 1.0f;            // plain 3DGS dilation: no opacity compensation
     ca = ca + ks;
     cc = cc + ks;
     const float det = ca * cc - cb * cb;

@@ -117,6 +117,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-D gather: four rows (r0..r3, any order, out-of-range rows are zero-filled) x the map's box width at column c0,
+// written as four consecutive box rows at smem_dst; the tensor map's box is {columns, 1}
+__device__ __forceinline__ void tma_gather4_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int r0, int r1,
+                                               int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
 // 2-D tiled store smem -> global (bulk async group); the writers of the smem tile must have executed
 // fence.proxy.async before the issuing thread gets here
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {

@@ -508,3 +508,19 @@ def gemm_tn(a, w, out=None):
     check(_lib.lib().gvf_gemm_tn_f16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, R, ptr(out), out.stride(0),
                                      current_stream()), "gvf_gemm_tn_f16")
     return out
+
+
+def sparse_conv_gemm(x, nbr, w, bias=None, out_f32=False, out=None):
+    """Gather-fused submanifold convolution: x fp16 [N, Cin], nbr int32 [N, K3], w fp16 [Cout, K3 * Cin] -> [N, Cout]."""
+    _req(x, F16, "x")
+    _req(w, F16, "w")
+    _req(nbr, torch.int32, "nbr")
+    N, Cin = x.shape
+    K3, Cout = nbr.shape[1], w.shape[0]
+    assert x.stride(1) == 1 and w.stride(1) == 1 and nbr.is_contiguous() and w.shape[1] == K3 * Cin
+    if out is None:
+        out = torch.empty((N, Cout), dtype=F32 if out_f32 else F16, device=x.device)
+    check(_lib.lib().gvf_sparse_conv_gemm_f16(ptr(x), x.stride(0), ptr(nbr), N, K3, Cin, ptr(w), w.stride(0), Cout, ptr(bias),
+                                              ptr(out), out.stride(0), 4 if out.dtype == F32 else 0, current_stream()),
+          "gvf_sparse_conv_gemm_f16")
+    return out

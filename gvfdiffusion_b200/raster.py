@@ -54,8 +54,9 @@ def pack_cameras(extrinsics, intrinsics, near, far):
 
 
 def make_params(H, W, tanfovx, tanfovy, const=None, kernel_size=0.1, scale_modifier=1.0,
-                bg=(1.0, 1.0, 1.0)):
+                bg=(1.0, 1.0, 1.0), mip_filter=True):
     p = _lib.RasterParams()
+    p.mip_filter = int(bool(mip_filter))
     p.H, p.W, p.tanfovx, p.tanfovy = int(H), int(W), float(tanfovx), float(tanfovy)
     p.kernel_size, p.scale_modifier = float(kernel_size), float(scale_modifier)
     p.bg = (C.c_float * 3)(*[float(b) for b in bg])

@@ -5,8 +5,9 @@ callers use: trellis/models/structured_latent_flow.py:34-35, structured_latent_v
     out[i] = bias + sum_k W[:, k, :] x[row of the voxel at coords[i] + dilation (k - ks // 2)]      (absent = 0)
 
 State-dict keys and layout follow spconv 2.x: `conv.weight` [Cout, kx, ky, kz, Cin], `conv.bias` [Cout].
-Execution: neighbour map (cached per coordinate set under `indice_key`, like spconv's indice_dict) ->
-im2col gather to the fp16 [N, ks^3 Cin] operand -> one tcgen05 GEMM with the bias in its epilogue.
+Execution: neighbour map (cached per coordinate set under `indice_key`, like spconv's indice_dict) -> ONE tcgen05 GEMM
+whose TMA producer gathers the neighbour rows itself (`cp.async.bulk.tensor ... tile::gather4`, absent voxels zero-filled),
+bias in the epilogue; fp32 features or Cin % 64 != 0 go through the im2col gather + plain GEMM instead.
 Strided / padded SparseConv3d (spatial resampling) is not part of the path and raises."""
 import torch
 
@@ -25,6 +26,7 @@ class SparseConv3d:
             raise ValueError("channel counts must be multiples of 8 (16 B rows)")
         self.in_channels, self.out_channels, self.kernel_size, self.dilation = in_channels, out_channels, kernel_size, dilation
         self.indice_key = indice_key
+        self.fused_gather = True            # False: im2col + GEMM (the only path for fp32 features / Cin % 64 != 0)
         self.device = torch.device(device)
         self.weight = torch.zeros(out_channels, kernel_size ** 3 * in_channels, dtype=F16, device=self.device)
         self.bias = torch.zeros(out_channels, dtype=F32, device=self.device) if bias else None
@@ -60,6 +62,11 @@ class SparseConv3d:
         if not x.feats.is_cuda:
             raise RuntimeError("SparseConv3d runs on the device only (no CPU fallback)")
         nbr = self.neighbor_map(x, grid_size)
+        if (self.fused_gather and self.in_channels % 64 == 0 and x.feats.dtype == F16 and x.feats.stride(1) == 1
+                and epilogue in (ops.EPI_F16, ops.EPI_F32)):
+            # one kernel: the GEMM's TMA producer gathers the neighbour rows (tile::gather4), no im2col operand
+            y = ops.sparse_conv_gemm(x.feats, nbr, self.weight, self.bias, out_f32=epilogue == ops.EPI_F32, out=out)
+            return x.replace(y)
         a = ops.sparse_im2col(x.feats if x.feats.dtype in (F16, F32) else x.feats.float(), nbr)
         y = ops.gemm(a, self.weight, self.bias, epilogue, out=out)
         return x.replace(y)

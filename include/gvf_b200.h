@@ -58,6 +58,11 @@ typedef struct gvf_raster_params {
   float min_kernel;           /* mininum_kernel_size (3-D filter) */
   float opacity_bias;         /* logit(opacity_bias) */
   int32_t softplus;           /* 1 softplus, 0 exp scaling activation */
+  int32_t mip_filter;         /* 1: mip-splatting 2-D filter (cov2D += kernel_size I, opacity *= sqrt(det0 / det1)), the
+                                 `pipe.use_mip_gaussian = True` rasteriser of renderers/gaussian_render.py:103-125;
+                                 0: plain 3DGS dilation (cov2D += kernel_size I, usually 0.3, no opacity compensation) --
+                                 the `diff_gauss` rasteriser of :126-141, used by the alignment pre-step
+                                 (utils/inference_utils.py:50) */
 } gvf_raster_params;
 
 /* Names of the sub-buffers inside the rasteriser workspace (for tests / backward). */
@@ -444,6 +449,13 @@ GVF_API int gvf_skinny_expand(const float* x, int ldx, int K, const float* Wt, l
  * e.g. the first three columns of d queries [Q, 14]; accumulate != 0 adds to what is there). */
 GVF_API int gvf_vae_query_embed_bwd(const float* queries, int ldq, const void* gs, const void* dout, int Q, int C,
                                     void* dgs, float* dxyz, int ld_dxyz, int accumulate, void* stream);
+
+/* The same convolution as ONE kernel: the GEMM's TMA producer gathers the neighbour rows itself
+ * (cp.async.bulk.tensor tile::gather4 through nbr, absent neighbours zero-filled), so the [N, K3 * Cin] im2col operand is
+ * never written.  x fp16 [N, Cin] (row stride ldx), W fp16 [Cout, K3 * Cin], out fp16 (epilogue 0) or fp32 (4) [N, Cout].
+ * Cin % 64 == 0, else GVF_ERR_UNSUPPORTED (callers fall back to im2col + gvf_gemm_f16).  Bit-identical to that path. */
+GVF_API int gvf_sparse_conv_gemm_f16(const void* x, int ldx, const int* nbr, int N, int K3, int Cin, const void* W, int ldw,
+                                     int Cout, const float* bias, void* out, int ldo, int epilogue, void* stream);
 
 /* Tuning hook of the rasteriser's per-tile depth sort: -1 environment (GVF_RASTER_SORT=bucket|bitonic,
  * default bucket), 0 bitonic network, 1 one-pass bucket sort (identical point lists). */

@@ -55,6 +55,7 @@ typedef struct {
   float min_kernel;       /* 3-D filter size (mininum_kernel_size) */
   float opacity_bias;     /* logit(opacity_bias) */
   int32_t softplus;       /* 1: softplus scaling activation, 0: exp */
+  int32_t mip_filter;     /* 1: mip 2-D filter + opacity compensation; 0: plain 3DGS dilation by kernel_size */
 } gvf_oracle_params;
 
 /* ---- GaussianModel.get_*_with_delta: raw canonical params (+ delta) -> activated ---- */
@@ -168,6 +169,7 @@ static int preprocess_one(const gvf_oracle_params* prm, const float* view, const
   const float det1 = fmaxf(1e-6f, (ca + ks) * (cc + ks) - cb * cb);
   float coef = sqrtf(det0 / (det1 + 1e-6f) + 1e-6f);
   if (det0 <= 1e-6f || det1 <= 1e-6f) coef = 0.0f;
+  if (!prm->mip_filter) coef = 1.0f;
   ca = ca + ks;
   cc = cc + ks;
   const float det = ca * cc - cb * cb;

@@ -14,7 +14,7 @@ class Params(C.Structure):
     _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("tanfovx", C.c_float), ("tanfovy", C.c_float),
                 ("kernel_size", C.c_float), ("scale_modifier", C.c_float), ("bg", C.c_float * 3),
                 ("aabb", C.c_float * 6), ("scale_bias", C.c_float), ("min_kernel", C.c_float),
-                ("opacity_bias", C.c_float), ("softplus", C.c_int32)]
+                ("opacity_bias", C.c_float), ("softplus", C.c_int32), ("mip_filter", C.c_int32)]
 
 
 def build(force=False):
@@ -40,8 +40,9 @@ def lib():
     return _lib
 
 
-def make_params(H, W, tanfovx, tanfovy, const, kernel_size=0.1, scale_modifier=1.0, bg=(1.0, 1.0, 1.0)):
+def make_params(H, W, tanfovx, tanfovy, const, kernel_size=0.1, scale_modifier=1.0, bg=(1.0, 1.0, 1.0), mip_filter=True):
     p = Params()
+    p.mip_filter = int(bool(mip_filter))
     p.H, p.W, p.tanfovx, p.tanfovy = H, W, tanfovx, tanfovy
     p.kernel_size, p.scale_modifier = kernel_size, scale_modifier
     p.bg = (C.c_float * 3)(*bg)
