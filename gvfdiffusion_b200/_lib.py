@@ -101,6 +101,7 @@ _SIGS = {
     "gvf_sparse_conv_gemm_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int,
                                            C.c_int, _P]),
     "gvf_raster_set_sort": (None, [C.c_int]),
+    "gvf_flow_euler_step": (C.c_int, [_P, _P, _P, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
     "gvf_affine_lastdim": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, C.c_float, C.c_float, _P, _P]),
 }
 

@@ -490,6 +490,26 @@ __global__ void __launch_bounds__(256) affine_lastdim_kernel(const float* __rest
   out[i] = x[i] * (a ? a[c] : as) + (b ? b[c] : bs);
 }
 
+// Euler step of the TRELLIS flow samplers (trellis/pipelines/samplers/flow_euler.py:36-77 + the guidance mixins):
+//   v = (1 + s) v_cond - s v_neg (when v_neg is given);  x_prev = x - (t - t_prev) v;
+//   x0 = (1 - sigma_min) x - (sigma_min + (1 - sigma_min) t) v
+// Every product and difference is rounded on its own (no FMA contraction), in the reference's operation order, so the
+// result equals the torch expressions bit for bit.
+// The scalar coefficients arrive as floats the HOST rounded from its double expressions (1 + s, 1 - sigma_min,
+// sigma_min + (1 - sigma_min) t), exactly what torch does with a Python scalar operand.
+__global__ void __launch_bounds__(256) flow_euler_kernel(const float* __restrict__ x, const float* __restrict__ v,
+                                                         const float* __restrict__ vn, long long n, float s1, float s,
+                                                         float dt, float c0, float c1, float* __restrict__ xp,
+                                                         float* __restrict__ x0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float vv = v[i];
+  if (vn) vv = __fsub_rn(__fmul_rn(s1, vv), __fmul_rn(s, vn[i]));
+  const float xi = x[i];
+  xp[i] = __fsub_rn(xi, __fmul_rn(dt, vv));
+  if (x0) x0[i] = __fsub_rn(__fmul_rn(c0, xi), __fmul_rn(c1, vv));
+}
+
 }  // namespace gvf
 
 using namespace gvf;
@@ -630,6 +650,15 @@ GVF_API int gvf_dpm_x0(const float* x, const float* v, long long n, int branches
   if (model_type != 0 && model_type != 1) return GVF_ERR_UNSUPPORTED;
   dpm_x0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, v, n, branches, model_type, alpha, sigma,
                                                                      s1, s2, x0);
+  RET();
+}
+
+GVF_API int gvf_flow_euler_step(const float* x, const float* v, const float* v_neg, long long n, double cfg_strength,
+                                double t, double t_prev, double sigma_min, float* x_prev, float* x0, void* stream) {
+  if (!x || !v || !x_prev || n <= 0) return GVF_ERR_INVALID;
+  flow_euler_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(
+      x, v, v_neg, n, (float)(1.0 + cfg_strength), (float)cfg_strength, (float)(t - t_prev), (float)(1.0 - sigma_min),
+      (float)(sigma_min + (1.0 - sigma_min) * t), x_prev, x0);
   RET();
 }
 

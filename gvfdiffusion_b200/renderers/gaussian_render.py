@@ -38,21 +38,20 @@ class GaussianRenderer:
     def render_frames(self, gausssian, extrinsics, intrinsics, delta_pc=None, detach_static=False):
         """extrinsics (F,4,4), intrinsics (3,3)|(F,3,3), delta_pc (F,P,14)|None -> rgba (F,4,H,W), radii (F,P).
         Differentiable w.r.t. delta_pc and (unless detach_static) the GaussianModel's raw tensors."""
-        if not self.pipe.use_mip_gaussian:
-            raise NotImplementedError("only the mip-Gaussian rasteriser (pipe.use_mip_gaussian=True) is on the "
-                                      "inference path; the diff_gauss variant serves the alignment pre-step")
+        # pipe.use_mip_gaussian False = the `diff_gauss` rasteriser of the reference (renderers/gaussian_render.py:126-141,
+        # the alignment pre-step sets it at utils/inference_utils.py:50): no mip 2-D filter / opacity compensation, the
+        # plain 3DGS screen-space dilation of 0.3 px^2 instead -- same kernels, gvf_raster_params.mip_filter = 0
+        mip = bool(self.pipe.use_mip_gaussian)
         if self.pipe.convert_SHs_python or self.pipe.compute_cov3D_python:
             raise NotImplementedError("convert_SHs_python / compute_cov3D_python are not used by the reference configs")
         opt = self.rendering_options
-        if opt["ssaa"] != 1:
-            raise NotImplementedError("ssaa > 1 (bicubic downsample) is not on the inference path")
         dev = gausssian._xyz.device
-        res = int(opt["resolution"])
+        res = int(opt["resolution"]) * int(opt["ssaa"])        # ssaa > 1: rendered large, reduced by render()
         bg = self._bg()
         self.bg_color = torch.tensor(bg, dtype=torch.float32, device=dev)
         cams, tfx, tfy = R.pack_cameras(extrinsics, intrinsics, opt["near"], opt["far"])
-        prm = R.make_params(res, res, tfx, tfy, gausssian.constants(), self.pipe.kernel_size,
-                            self.pipe.scale_modifier, bg)
+        prm = R.make_params(res, res, tfx, tfy, gausssian.constants(), self.pipe.kernel_size if mip else 0.3,
+                            self.pipe.scale_modifier, bg, mip_filter=mip)
         if self._rz is None:
             self._rz = R.Rasterizer(dev)
         raw = gausssian.raw()
@@ -77,4 +76,12 @@ class GaussianRenderer:
         if d is not None and d.shape[-1] == 10:        # xyz/scale/rot only (gaussian_render.py:158)
             d = torch.cat([d, torch.zeros(d.shape[:-1] + (4,), device=d.device, dtype=d.dtype)], -1)
         rgba, radii = self.render_frames(gausssian, extrinsics[None], intrinsics, d, detach_static=detach_static)
-        return edict({"rgb": rgba[0, :3], "alpha": rgba[0, 3]})
+        rgb, alpha = rgba[0, :3], rgba[0, 3]
+        ssaa, res = int(self.rendering_options["ssaa"]), int(self.rendering_options["resolution"])
+        if ssaa > 1:
+            # renderers/gaussian_render.py:355-358: the super-sampled image is reduced with torch's antialiased bicubic
+            # filter (the same library call as the reference; alpha / depth are not resampled there either)
+            import torch.nn.functional as F
+            rgb = F.interpolate(rgb[None], size=(res, res), mode="bicubic", align_corners=False, antialias=True).squeeze()
+        # patch_mask is accepted and unused, exactly like the reference's render() (it never reads the argument)
+        return edict({"rgb": rgb, "alpha": alpha})

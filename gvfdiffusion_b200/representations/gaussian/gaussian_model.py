@@ -40,6 +40,16 @@ class GaussianModel:
         return {"_xyz": self._xyz, "_features_dc": self._features_dc, "_scaling": self._scaling,
                 "_rotation": self._rotation, "_opacity": self._opacity}
 
+    def from_xyz(self, xyz):
+        """activated positions -> raw `_xyz` (gaussian_model.py:137-138)"""
+        self._xyz = (xyz - self.aabb[None, :3]) / self.aabb[None, 3:]
+
+    def from_rotation(self, rots):
+        """activated (w-first) quaternions -> raw `_rotation` (gaussian_model.py:134-135; rots_bias = [1, 0, 0, 0])"""
+        bias = torch.zeros(4, dtype=rots.dtype, device=rots.device)
+        bias[0] = 1.0
+        self._rotation = rots - bias[None, :]
+
     def gaussian_tensor(self):
         """[P,14] = [xyz3 | rgb3 | opacity1 | scale3 | rot4] (train_vae.py:466-472)."""
         prm = R.make_params(16, 16, 1.0, 1.0, self.constants())

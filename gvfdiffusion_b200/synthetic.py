@@ -95,13 +95,13 @@ def orbit_camera(elevation, azimuth, radius=1.0):
     return T
 
 
-def orbit_extrinsics(F, elevation=0.0, radius=2.0):
+def orbit_extrinsics(F, elevation=0.0, radius=2.0, azimuths=None):
     """World->camera matrices of the reference render loop (utils/inference_utils.py:245-254),
-    azimuth 360 * f / F."""
+    azimuth 360 * f / F (or the given list of azimuths in degrees: the alignment loop of :53-62)."""
     convert = np.array([[1, 0, 0, 0], [0, 0, -1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.float32)
     out = []
     for f in range(F):
-        pose = convert @ orbit_camera(elevation, 360.0 * f / F, radius)
+        pose = convert @ orbit_camera(elevation, 360.0 * f / F if azimuths is None else float(azimuths[f]), radius)
         pose[:3, 1:3] *= -1
         out.append(np.linalg.inv(pose))
     return torch.from_numpy(np.stack(out)).float()

@@ -290,6 +290,11 @@ GVF_API int gvf_dpm_error_sq(const float* x_higher, const float* x_lower, const 
                              long long n_per_batch, float atol, float rtol, float* E2, void* stream);
 GVF_API int gvf_dpm_update(const float* x, const float* m0, const float* m1, long long n, float cx, float cm,
                            float inv_r0, int order, float* out, void* stream);
+/* Euler step of the TRELLIS flow-matching samplers (trellis/pipelines/samplers/flow_euler.py:36-77 with the guidance
+ * mixins): v = (1 + cfg) v - cfg v_neg when v_neg != NULL; x_prev = x - (t - t_prev) v; x0 (optional) =
+ * (1 - sigma_min) x - (sigma_min + (1 - sigma_min) t) v.  Bit-identical to the reference's torch expressions. */
+GVF_API int gvf_flow_euler_step(const float* x, const float* v, const float* v_neg, long long n, double cfg_strength, double t,
+                                double t_prev, double sigma_min, float* x_prev, float* x0, void* stream);
 /* out = x * a[c] + b[c] over the last dim (or scalars as/bs when a/b are NULL):
  * latent de-normalisation, inference_dpm_latent.py:250 */
 GVF_API int gvf_affine_lastdim(const float* x, long long n, int C, const float* a, const float* b, float as,

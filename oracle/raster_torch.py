@@ -32,7 +32,7 @@ def activate(canon, delta, const):
 
 
 def project(means3D, scales, rots, shs, opac, view_t, proj_t, H, W, tanfovx, tanfovy, kernel_size=0.1,
-            scale_modifier=1.0, means2D=None):
+            scale_modifier=1.0, means2D=None, mip_filter=True):
     """preprocess stage; view_t / proj_t are the transposed matrices handed to the rasteriser.
     means2D: optional zero tensor [P,>=2] in NDC units added to the projected centre, so that its autograd
     gradient is upstream's `dL_dmean2D` (blend-stage gradient of the screen position, d pix / d ndc = W/2, H/2)."""
@@ -67,6 +67,8 @@ def project(means3D, scales, rots, shs, opac, view_t, proj_t, H, W, tanfovx, tan
     det1 = torch.clamp((a0 + ks) * (c0 + ks) - b * b, min=1e-6)
     coef = torch.sqrt(det0 / (det1 + 1e-6) + 1e-6)
     coef = torch.where((det0 <= 1e-6) | (det1 <= 1e-6), torch.zeros_like(coef), coef)
+    if not mip_filter:                              # plain 3DGS dilation (diff_gauss): no opacity compensation
+        coef = torch.ones_like(coef)
     a, c = a0 + ks, c0 + ks
     det = a * c - b * b
     conic = torch.stack([c / det, -b / det, a / det], 1)
@@ -115,7 +117,7 @@ def blend(sp, H, W, bg):
     return torch.cat([C + T[None] * bgt[:, None, None], (1 - T)[None]], 0)
 
 
-def render(canon, delta, const, view_t, proj_t, H, W, tanfovx, tanfovy, bg=(1.0, 1.0, 1.0), kernel_size=0.1):
+def render(canon, delta, const, view_t, proj_t, H, W, tanfovx, tanfovy, bg=(1.0, 1.0, 1.0), kernel_size=0.1, mip_filter=True):
     m3, sc, rt, sh, op = activate(canon, delta, const)
-    sp = project(m3, sc, rt, sh, op, view_t, proj_t, H, W, tanfovx, tanfovy, kernel_size)
+    sp = project(m3, sc, rt, sh, op, view_t, proj_t, H, W, tanfovx, tanfovy, kernel_size, mip_filter=mip_filter)
     return blend(sp, H, W, bg)

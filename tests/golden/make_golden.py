@@ -260,6 +260,50 @@ def gen_serialization():
     return cases
 
 
+def gen_flow_euler():
+    """The reference's FlowEuler samplers (trellis/pipelines/samplers/flow_euler.py:11-199, TRELLIS stage in front of the
+    path) on a toy velocity model, CPU fp32: plain, classifier-free guidance and guidance interval."""
+    import importlib.util
+    import types
+    try:
+        import easydict  # noqa: F401
+    except ImportError:
+        m = types.ModuleType("easydict")
+
+        class EasyDict(dict):
+            __getattr__ = dict.get
+
+            def __setattr__(self, k, v):
+                self[k] = v
+        m.EasyDict = EasyDict
+        sys.modules["easydict"] = m
+    d = os.path.join(_ref_import.REF, "trellis", "pipelines", "samplers")
+    pkg = types.ModuleType("refsamplers")
+    pkg.__path__ = [d]
+    sys.modules["refsamplers"] = pkg
+    spec = importlib.util.spec_from_file_location("refsamplers.flow_euler", os.path.join(d, "flow_euler.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["refsamplers.flow_euler"] = mod
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(31)
+    noise = torch.randn(2, 8, 16, generator=g)
+    W = torch.randn(16, 16, generator=g) * 0.3
+    cond, neg = torch.randn(2, 1, 16, generator=g), torch.zeros(2, 1, 16)
+    model = lambda x, t, c: torch.tanh(x @ W) * torch.cos(t / 1000.0).view(-1, 1, 1) + 0.1 * c
+    out = {"noise": noise, "W": W, "cond": cond, "neg_cond": neg, "cases": {}}
+    r = mod.FlowEulerSampler(1e-5).sample(model, noise, cond, steps=12, rescale_t=1.0, verbose=False)
+    out["cases"]["plain"] = {"args": dict(steps=12, rescale_t=1.0), "samples": r.samples, "pred_x_0": r.pred_x_0[-1]}
+    r = mod.FlowEulerSampler(1e-5).sample(model, noise, cond, steps=7, rescale_t=3.0, verbose=False)
+    out["cases"]["rescaled"] = {"args": dict(steps=7, rescale_t=3.0), "samples": r.samples, "pred_x_0": r.pred_x_0[-1]}
+    r = mod.FlowEulerCfgSampler(1e-5).sample(model, noise, cond, neg, steps=9, rescale_t=1.0, cfg_strength=3.0, verbose=False)
+    out["cases"]["cfg"] = {"args": dict(steps=9, rescale_t=1.0, cfg_strength=3.0), "samples": r.samples, "pred_x_0": r.pred_x_0[-1]}
+    r = mod.FlowEulerGuidanceIntervalSampler(1e-5).sample(model, noise, cond, neg, steps=9, rescale_t=3.0, cfg_strength=7.5,
+                                                            cfg_interval=(0.5, 0.95), verbose=False)
+    out["cases"]["interval"] = {"args": dict(steps=9, rescale_t=3.0, cfg_strength=7.5, cfg_interval=(0.5, 0.95)),
+                                "samples": r.samples, "pred_x_0": r.pred_x_0[-1]}
+    return out
+
+
 def _bruteforce_knn_points(p1, p2, lengths1=None, lengths2=None, K=1):
     """Stand-in for pytorch3d.ops.knn_points (absent here) with its documented semantics: exact squared
     distances ((dx*dx + dy*dy) + dz*dz in fp32), ascending, ties -> lowest index, padded rows zero."""
@@ -563,6 +607,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "flow_euler":
+        torch.save(gen_flow_euler(), os.path.join(HERE, "flow_euler.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "serialization":
         torch.save(gen_serialization(), os.path.join(HERE, "serialization.pt"))
         return
@@ -580,6 +627,7 @@ def main():
     torch.save(gen_gaussian(), os.path.join(HERE, "gaussian.pt"))
     torch.save(gen_respace(), os.path.join(HERE, "respace.pt"))
     torch.save(gen_serialization(), os.path.join(HERE, "serialization.pt"))
+    torch.save(gen_flow_euler(), os.path.join(HERE, "flow_euler.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
