@@ -107,7 +107,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   uint8_t* sQ = smem;                              // 2 tiles
   uint8_t* sKV = smem + 2 * TILE_BYTES;            // S x (K tile, V tile)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, h = blockIdx.y, nb = blockIdx.z;
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   if (a.trace && threadIdx.x == 0 && cta_lin < 1024) {   // per-CTA (smid, start ns) for schedule studies
@@ -125,8 +125,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     mbar_init(&q_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], nq); }
     for (int x = 0; x < 2; ++x) {
-      for (int b = 0; b < 2; ++b) { mbar_init(&s_full[x][b], 1); mbar_init(&s_free[x][b], 128); }
-      mbar_init(&p_full[x], 128);
+      for (int b = 0; b < 2; ++b) { mbar_init(&s_full[x][b], 1); mbar_init(&s_free[x][b], 4); }   // one arrival per softmax warp
+      mbar_init(&p_full[x], 4);
       mbar_init(&o_full[x], 1);
     }
     fence_barrier_init();
@@ -165,26 +165,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     }
   } else if (warp == 1 || warp == 2) {
     // ------------------------------------------------------------------ MMA issuer of tile x
+    // warp-uniform issue loop, tcgen05 instructions behind elect.sync (see the v8 kernel below for the finding)
     const int x = (warp == 1) ? 0 : 1;
-    if (lane == 0 && x < nq) {
+    if (x < nq) {
       const uint32_t idesc_qk = make_idesc_f16(128, BLK, 0, 0);
       const uint32_t idesc_pv = make_idesc_f16(128, D, 0, 1);
       const uint32_t qa = smem_u32(sQ) + x * TILE_BYTES, skv = smem_u32(sKV);
       const uint32_t tX = tmem + x * TM_STRIDE;
       auto issue_qk = [&](int i) {                 // S[i % NSBUF] = Q K(block i)^T
         const uint32_t ka = skv + ((i / BPT) % S) * 2 * TILE_BYTES + (i % BPT) * BLK * ROWB;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          mma_ss(tX + (i % NSBUF) * BLK, make_smem_desc(qa + k * 32, 16, SBO, SWZ),
-                 make_smem_desc(ka + k * 32, 16, SBO, SWZ), idesc_qk, k != 0);
+          for (int k = 0; k < D / 16; ++k)
+            mma_ss(tX + (i % NSBUF) * BLK, make_smem_desc(qa + k * 32, 16, SBO, SWZ),
+                   make_smem_desc(ka + k * 32, 16, SBO, SWZ), idesc_qk, k != 0);
+          tc_commit(&s_full[x][i % NSBUF]);
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int i) {                 // O' = P(block i) V(block i)
         const uint32_t va = skv + ((i / BPT) % S) * 2 * TILE_BYTES + TILE_BYTES + (i % BPT) * BLK * ROWB;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BLK / 16; ++k)
-          mma_ts(tX + TM_O, tX + TM_P + k * 8, make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv, k != 0);
+          for (int k = 0; k < BLK / 16; ++k)
+            mma_ts(tX + TM_O, tX + TM_P + k * 8, make_smem_desc(va + k * 16 * ROWB, SBO, SBO, SWZ), idesc_pv, k != 0);
+          tc_commit(&o_full[x]);
+          if ((i % BPT) == BPT - 1 || i + 1 == n_blk) tc_commit(&kv_empty[(i / BPT) % S]);   // tile fully consumed
+        }
+        __syncwarp();
       };
-      const bool tr = a.trace && x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      const bool tr = a.trace && lane == 0 && x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       mbar_wait(&q_full, 0);
       int tiles_waited = 0;                        // K/V tiles whose arrival this thread has observed
       auto need_tile = [&](int t) {
@@ -197,7 +207,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       for (int i = 0; i < NSBUF && i < n_blk; ++i) {
         need_tile(i / BPT);
         issue_qk(i);
-        tc_commit(&s_full[x][i % NSBUF]);
       }
       for (int i = 0; i < n_blk; ++i) {
         if (i + NSBUF < n_blk) {
@@ -206,16 +215,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
           mbar_wait(&s_free[x][i % NSBUF], (i / NSBUF) & 1);
           tc_fence_after();
           issue_qk(i + NSBUF);
-          tc_commit(&s_full[x][i % NSBUF]);
           if (tr && i < 16) a.trace[i * 16 + 10] = clock64();
         }
         mbar_wait(&p_full[x], i & 1);              // P(i) is in TMEM
         tc_fence_after();
         if (tr && i < 16) a.trace[i * 16 + 8] = clock64();
         issue_pv(i);
-        tc_commit(&o_full[x]);
         if (tr && i < 16) a.trace[i * 16 + 9] = clock64();
-        if ((i % BPT) == BPT - 1 || i + 1 == n_blk) tc_commit(&kv_empty[(i / BPT) % S]);   // tile fully consumed
       }
     }
   }
@@ -268,7 +274,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         tmem_ld_wait();
         if (tr && i < 16) a.trace[i * 16 + 2] = clock64();
         tc_fence_before();
-        mbar_arrive(&s_free[x][b]);                // the MMA warp may overwrite this score buffer
+        __syncwarp();                              // tcgen05.wait::ld is warp-wide: every lane's scores are in registers
+        if (lane == 0) mbar_arrive(&s_free[x][b]); // the MMA warp may overwrite this score buffer
         if (valid < BLK) {
 #pragma unroll
           for (int k = 0; k < BLK; ++k)
@@ -363,7 +370,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         tmem_st_wait();
         if (tr && i < 16) a.trace[i * 16 + 6] = clock64();
         tc_fence_before();
-        mbar_arrive(&p_full[x]);
+        __syncwarp();                              // tcgen05.wait::st is warp-wide
+        if (lane == 0) mbar_arrive(&p_full[x]);
       }
       if (tr) a.trace[13] = clock64();
       // last partial product

@@ -114,7 +114,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   uint8_t* sV = smem + 2 * TILE_BYTES;                 // 2 tiles
   uint8_t* sQ = smem + 4 * TILE_BYTES;                 // S stages
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int kblk = blockIdx.x, h = blockIdx.y, nb = blockIdx.z;
   const int k0 = kblk * 256;
   const int nkt = (a.Lk - k0 > 128) ? 2 : 1;           // live key tiles of this CTA
@@ -123,8 +123,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 
   if (threadIdx.x == 0) {
     mbar_init(&kv_full, 1);
-    for (int s = 0; s < S; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], nkt * 129); }
-    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&o_done[x], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], nkt * 5); }     // 1 commit + 4 warps per tile
+    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 4); mbar_init(&o_done[x], 1); }
     fence_barrier_init();
     tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapDO);
   }
@@ -155,8 +155,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       }
     }
   } else if (warp == 1 || warp == 2) {
+    // MMA issuer of key tile x: the loop runs with all 32 lanes on warp-uniform values and only the tcgen05 instructions
+    // sit behind elect.sync -- inside `if (lane == 0)` ptxas wraps every tcgen05.mma / commit in an ELECT / R2UR /
+    // BRA.U.ANY loop with dependent descriptor arithmetic (the finding behind attention v8, csrc/attn.cu)
     const int x = warp - 1;
-    if (lane == 0 && x < nkt) {
+    if (x < nkt) {
       const uint32_t idesc_s = make_idesc_f16(128, 64, 0, 0);
       const uint32_t idesc_o = make_idesc_f16(128, D, 0, 1);
       const uint32_t ka = smem_u32(sK) + x * TILE_BYTES, va = smem_u32(sV) + x * TILE_BYTES;
@@ -169,27 +172,33 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         if (i > 0 && a.serial) { mbar_wait(&o_done[x], (i - 1) & 1); tc_fence_after(); }   // P / dS columns are free again
         const uint32_t qa = smem_u32(sQ) + s * STAGE_BYTES + (i & 1) * 64 * ROWB;
         const uint32_t da = qa + TILE_BYTES;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)               // S^T = K Q^T
-          mma_ss(tX + TM_S, make_smem_desc(ka + k * 32, 16, SBO, SWZ), make_smem_desc(qa + k * 32, 16, SBO, SWZ),
-                 idesc_s, k != 0);
+          for (int k = 0; k < D / 16; ++k)             // S^T = K Q^T
+            mma_ss(tX + TM_S, make_smem_desc(ka + k * 32, 16, SBO, SWZ), make_smem_desc(qa + k * 32, 16, SBO, SWZ),
+                   idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)               // dP^T = V dO^T
-          mma_ss(tX + TM_DP, make_smem_desc(va + k * 32, 16, SBO, SWZ), make_smem_desc(da + k * 32, 16, SBO, SWZ),
-                 idesc_s, k != 0);
-        tc_commit(&s_full[x]);
+          for (int k = 0; k < D / 16; ++k)             // dP^T = V dO^T
+            mma_ss(tX + TM_DP, make_smem_desc(va + k * 32, 16, SBO, SWZ), make_smem_desc(da + k * 32, 16, SBO, SWZ),
+                   idesc_s, k != 0);
+          tc_commit(&s_full[x]);
+        }
+        __syncwarp();
         mbar_wait(&p_full[x], i & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)                    // dV += P^T dO   (K = 64 queries)
-          mma_ts(tX + TM_DV, tX + TM_S + k * 8, make_smem_desc(da + k * 16 * ROWB, SBO, SBO, SWZ), idesc_o,
-                 (i | k) != 0);
+          for (int k = 0; k < 4; ++k)                  // dV += P^T dO   (K = 64 queries)
+            mma_ts(tX + TM_DV, tX + TM_S + k * 8, make_smem_desc(da + k * 16 * ROWB, SBO, SBO, SWZ), idesc_o,
+                   (i | k) != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)                    // dK += dS^T Q
-          mma_ts(tX + TM_DK, tX + TM_DP + k * 8, make_smem_desc(qa + k * 16 * ROWB, SBO, SBO, SWZ), idesc_o,
-                 (i | k) != 0);
-        tc_commit(&o_done[x]);
-        if (i & 1) tc_commit(&q_empty[s]);             // this tile's operands of the stage are consumed
+          for (int k = 0; k < 4; ++k)                  // dK += dS^T Q
+            mma_ts(tX + TM_DK, tX + TM_DP + k * 8, make_smem_desc(qa + k * 16 * ROWB, SBO, SBO, SWZ), idesc_o,
+                   (i | k) != 0);
+          tc_commit(&o_done[x]);
+          if (i & 1) tc_commit(&q_empty[s]);           // this tile's operands of the stage are consumed
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -232,10 +241,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           tmem_st_x16(tX + TM_S + 16 * hf, pp);
           tmem_st_x16(tX + TM_DP + 16 * hf, ds);
         }
-        tmem_st_wait();
+        tmem_st_wait();                                // warp-wide: every lane's P / dS columns are written
         tc_fence_before();
-        mbar_arrive(&p_full[x]);
-        if (i & 1) mbar_arrive(&q_empty[s]);           // LSE2 / D of this stage are no longer needed by this thread
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&p_full[x]);
+          if (i & 1) mbar_arrive(&q_empty[s]);         // LSE2 / D of this stage are no longer needed by this warp
+        }
       }
       mbar_wait(&o_done[x], (n_blk - 1) & 1);
       tc_fence_after();
@@ -289,7 +301,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint8_t* sDO = smem + 2 * TILE_BYTES;                // 2 stages
   uint8_t* sKV = sDO + 2 * DO_BYTES;                   // S x (K tile, V tile)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, h = blockIdx.y, nbq = blockIdx.z;
   const int q0 = qblk * 256;
   const int nq = (a.Lq - q0 > 128) ? 2 : 1;
@@ -298,9 +310,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&do_full[s], 1); mbar_init(&do_empty[s], nq * 129); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&do_full[s], 1); mbar_init(&do_empty[s], nq * 5); }
     for (int s = 0; s < S; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], nq); }
-    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&dq_done[x], 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 4); mbar_init(&dq_done[x], 1); }
     fence_barrier_init();
     tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV); tma_prefetch_desc(&mapDO);
   }
@@ -339,8 +351,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
     }
   } else if (warp == 1 || warp == 2) {
-    const int x = warp - 1;
-    if (lane == 0 && x < nq) {
+    const int x = warp - 1;                            // warp-uniform issue loop, see the dK/dV kernel
+    if (x < nq) {
       const uint32_t idesc_s = make_idesc_f16(128, 64, 0, 0);
       const uint32_t idesc_o = make_idesc_f16(128, D, 0, 1);
       const uint32_t qa = smem_u32(sQ) + x * TILE_BYTES;
@@ -359,24 +371,32 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           if (g > 0 && a.serial) { mbar_wait(&dq_done[x], (g - 1) & 1); tc_fence_after(); }   // dS columns are free again
           const uint32_t ka = smem_u32(sKV) + s * 2 * TILE_BYTES + (i & 1) * 64 * ROWB;
           const uint32_t va = ka + TILE_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k)             // S = Q K^T
-            mma_ss(tX + TM_S, make_smem_desc(qa + k * 32, 16, SBO, SWZ), make_smem_desc(ka + k * 32, 16, SBO, SWZ),
-                   idesc_s, k != 0);
+            for (int k = 0; k < D / 16; ++k)           // S = Q K^T
+              mma_ss(tX + TM_S, make_smem_desc(qa + k * 32, 16, SBO, SWZ), make_smem_desc(ka + k * 32, 16, SBO, SWZ),
+                     idesc_s, k != 0);
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k)             // dP = dO V^T
-            mma_ss(tX + TM_DP, make_smem_desc(da + k * 32, 16, SBO, SWZ), make_smem_desc(va + k * 32, 16, SBO, SWZ),
-                   idesc_s, k != 0);
-          tc_commit(&s_full[x]);
+            for (int k = 0; k < D / 16; ++k)           // dP = dO V^T
+              mma_ss(tX + TM_DP, make_smem_desc(da + k * 32, 16, SBO, SWZ), make_smem_desc(va + k * 32, 16, SBO, SWZ),
+                     idesc_s, k != 0);
+            tc_commit(&s_full[x]);
+          }
+          __syncwarp();
           mbar_wait(&p_full[x], g & 1);
           tc_fence_after();
+          const bool tile_done = (i & 1) || i + 1 == n_blk;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)                  // dQ += dS K   (K = 64 keys)
-            mma_ts(tX + TM_DQ, tX + TM_S + k * 8, make_smem_desc(ka + k * 16 * ROWB, SBO, SBO, SWZ), idesc_o,
-                   (g | k) != 0);
-          tc_commit(&dq_done[x]);
-          if ((i & 1) || i + 1 == n_blk) { tc_commit(&kv_empty[s]); ++t; }
-          if (i + 1 == n_blk) tc_commit(&do_empty[ds]);
+            for (int k = 0; k < 4; ++k)                // dQ += dS K   (K = 64 keys)
+              mma_ts(tX + TM_DQ, tX + TM_S + k * 8, make_smem_desc(ka + k * 16 * ROWB, SBO, SBO, SWZ), idesc_o,
+                     (g | k) != 0);
+            tc_commit(&dq_done[x]);
+            if (tile_done) tc_commit(&kv_empty[s]);
+            if (i + 1 == n_blk) tc_commit(&do_empty[ds]);
+          }
+          __syncwarp();
+          if (tile_done) ++t;
         }
       }
     }
@@ -393,7 +413,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         mbar_wait(&do_full[ds], (r >> 1) & 1);
         const float* st = reinterpret_cast<const float*>(sDO + ds * DO_BYTES + 2 * TILE_BYTES);
         const float lse = st[x * 128 + row], dsm = st[256 + x * 128 + row];
-        mbar_arrive(&do_empty[ds]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&do_empty[ds]);
         for (int i = 0; i < n_blk; ++i, ++g) {
           mbar_wait(&s_full[x], g & 1);
           tc_fence_after();
@@ -416,7 +437,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           }
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&p_full[x]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[x]);
         }
       }
       mbar_wait(&dq_done[x], (g - 1) & 1);

@@ -243,6 +243,71 @@ __global__ void __launch_bounds__(256) skinny_outer_partial_kernel(const float* 
   }
 }
 
+// The same for fp16 y with N % 8 == 0 (the [B*T*Q, 768] activations of the decoder's output side, 0.6 GB per pass):
+// thread = 8 adjacent columns (one 16 B load per row) x one of RG row groups, 8 x K accumulators in registers, the row
+// groups of a CTA are summed through shared memory.  FMA-bound at K = 14 (4.2 GFMA for the 393 216 x 768 pass).
+template <int RG>
+__global__ void __launch_bounds__(384) skinny_outer_vec8_kernel(const float* __restrict__ x, int ldx, int K,
+                                                                const __half* __restrict__ y, long long ldy, long long M,
+                                                                int N, int rows_per_slab, float* __restrict__ partial) {
+  extern __shared__ float sred[];                       // [RG][16][8 * CT] for the final reduction, also x staging
+  __shared__ __align__(16) float sx[64][16];
+  const int CT = N >> 3;                                // column threads per row
+  const int c = threadIdx.x % CT, rg = threadIdx.x / CT;
+  const bool active = rg < RG;
+  const long long m0 = (long long)blockIdx.x * rows_per_slab;
+  const long long m1 = m0 + rows_per_slab < M ? m0 + rows_per_slab : M;
+  float acc[16][8];
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  for (long long mb = m0; mb < m1; mb += 64) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 64 * 16; t += blockDim.x) {
+      const int r = t >> 4, k = t & 15;
+      sx[r][k] = (mb + r < m1 && k < K) ? x[(mb + r) * ldx + k] : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      const int lim = (int)(m1 - mb < 64 ? m1 - mb : 64);
+#pragma unroll 2
+      for (int r = rg; r < lim; r += RG) {
+        const uint4 v = *reinterpret_cast<const uint4*>(y + (mb + r) * ldy + 8 * c);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+        float yv[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); yv[2 * j] = f.x; yv[2 * j + 1] = f.y; }
+        const float4* xr = reinterpret_cast<const float4*>(sx[r]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 xv = xr[q];
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[4 * q + e][j] = fmaf(xs[e], yv[j], acc[4 * q + e][j]);
+        }
+      }
+    }
+  }
+  // sum the row groups: [rg][k][n] in shared memory, then thread (c, rg = 0) adds them up
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sred[((size_t)rg * K + k) * N + 8 * c + j] = acc[k][j];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < K * N; t += blockDim.x) {
+    float v = 0.f;
+    for (int g = 0; g < RG; ++g) v += sred[(size_t)g * K * N + t];
+    partial[(size_t)blockIdx.x * K * N + t] = v;
+  }
+}
+
 // out[m, n] = sum_k x[m, k] Wt[k, n]   (K <= 16, fp32 operands; out fp16 or fp32): rank-K expansion, e.g. the gradient of
 // to_outputs' input, d lat = d out [M, 14] @ W [14, 768].  Thread = two adjacent columns (weights in registers), CTA =
 // 64 rows staged in shared memory; one coalesced 4 B (8 B) store per thread and row.
@@ -380,7 +445,7 @@ GVF_API int gvf_transpose_f16(const void* in, int R, int C, long long ld_in, voi
 }
 
 GVF_API size_t gvf_colsum_workspace_bytes(long long M, int N, int K) {
-  const int slabs = 256;
+  const int slabs = 512;
   return (size_t)slabs * (size_t)(K > 0 ? K : 1) * (size_t)N * sizeof(float);
 }
 
@@ -449,6 +514,30 @@ GVF_API int gvf_skinny_outer(const float* x, int ldx, int K, const void* y, int 
                              float* workspace, size_t workspace_bytes, float* out, int accumulate, void* stream) {
   if (!x || !y || !workspace || !out || M <= 0 || N <= 0 || K <= 0 || K > 16 || ldx < K || ldy < N) return GVF_ERR_INVALID;
   int slabs;
+  if (y_is_f16 && (N % 8) == 0 && N / 8 <= 96 && M >= 4096 && (ldy % 8) == 0 && ((uintptr_t)y & 15) == 0) {
+    // big fp16 passes: 8 columns per thread, ~2 CTAs per SM
+    constexpr int RG = 4;
+    long long rps = (M + 295) / 296;
+    rps = ((rps + 63) / 64) * 64;
+    slabs = (int)((M + rps - 1) / rps);
+    if (workspace_bytes < (size_t)slabs * K * N * sizeof(float)) return GVF_ERR_WORKSPACE;
+    const int threads = (N / 8) * RG;
+    const size_t smem = (size_t)RG * K * N * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(skinny_outer_vec8_kernel<RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+          cudaSuccess)
+        return GVF_ERR_CUDA;
+      configured = true;
+    }
+    if (smem <= 200 * 1024 && threads <= 384) {
+      skinny_outer_vec8_kernel<RG><<<slabs, threads, smem, ST(stream)>>>(x, ldx, K, (const __half*)y, ldy, M, N, (int)rps,
+                                                                         workspace);
+      const long long n = (long long)K * N;
+      reduce_slabs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(workspace, slabs, n, out, accumulate);
+      RET();
+    }
+  }
   const int rps = slab_rows(M, &slabs);
   if (workspace_bytes < (size_t)slabs * K * N * sizeof(float)) return GVF_ERR_WORKSPACE;
   const dim3 grid((N + 511) / 512, slabs);

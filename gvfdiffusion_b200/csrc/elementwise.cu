@@ -297,10 +297,13 @@ __global__ void ape_kernel(const float* __restrict__ xyz, int R, int C, float* _
 // in the reference (einsum is autocast-to-fp16): coordinate, omega and their product are
 // rounded to fp16 before sin/cos, whose results are rounded to fp16 too.
 // omega_j = 10000^(-j / (E/2)), E = C/6, computed in float64 then rounded.  Warp per query.
-template <int C>
+// FINAL = false: the sum LN(gs) + LN(PE(xyz)) itself (the encoder's token embedding, model/autoencoder.py:529-533,
+// which enters a residual stream before its PreNorm); `rows_per_xyz` consecutive output rows share one xyz row
+// (the T frames of a point).
+template <int C, bool FINAL = true>
 __global__ void __launch_bounds__(256) query_embed_kernel(const float* __restrict__ queries, int ldq,
                                                           const __half* __restrict__ gs, int Q,
-                                                          __half* __restrict__ out) {
+                                                          __half* __restrict__ out, const int* __restrict__ xyz_row = nullptr) {
   constexpr int PER = C / 32, E = C / 6;
   const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (qi >= Q) return;
@@ -313,7 +316,8 @@ __global__ void __launch_bounds__(256) query_embed_kernel(const float* __restric
     const int coord = c / (2 * E), w = c - coord * 2 * E;
     const int j = w < E ? w : w - E;
     const double om = 1.0 / pow(10000.0, (double)j / ((double)E / 2.0));
-    const float x16 = r16f(queries[(size_t)qi * ldq + coord]);
+    const size_t qrow = xyz_row ? (size_t)__ldg(xyz_row + qi) : (size_t)qi;
+    const float x16 = r16f(queries[qrow * ldq + coord]);
     const float a = r16f(x16 * r16f((float)om));
     p[i] = r16f(w < E ? sinf(a) : cosf(a));
     sg += g[i];
@@ -327,6 +331,11 @@ __global__ void __launch_bounds__(256) query_embed_kernel(const float* __restric
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) { g[i] = (g[i] - mg) * rg + (p[i] - mp) * rp; s += g[i]; }
+  if constexpr (!FINAL) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) out[(size_t)qi * C + i * 32 + lane] = __float2half_rn(g[i]);
+    return;
+  }
   const float m = warp_sum(s) / C;
   float v = 0.f;
 #pragma unroll
@@ -609,6 +618,49 @@ GVF_API int gvf_vae_query_embed(const float* queries, int ldq, const void* gs, i
   else if (C == 384) query_embed_kernel<384><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
   else if (C == 192) query_embed_kernel<192><<<grid, 256, 0, ST(stream)>>>(queries, ldq, (const __half*)gs, Q, (__half*)out);
   else return GVF_ERR_UNSUPPORTED;
+  RET();
+}
+
+GVF_API int gvf_vae_embed_sum(const float* xyz, int ldq, const int* xyz_row, const void* lin, int R, int C, void* out,
+                              void* stream) {
+  if (!xyz || !lin || !out || R <= 0) return GVF_ERR_INVALID;
+  const dim3 grid((R + 7) / 8);
+  if (C == 768) query_embed_kernel<768, false><<<grid, 256, 0, ST(stream)>>>(xyz, ldq, (const __half*)lin, R, (__half*)out, xyz_row);
+  else if (C == 96) query_embed_kernel<96, false><<<grid, 256, 0, ST(stream)>>>(xyz, ldq, (const __half*)lin, R, (__half*)out, xyz_row);
+  else if (C == 384) query_embed_kernel<384, false><<<grid, 256, 0, ST(stream)>>>(xyz, ldq, (const __half*)lin, R, (__half*)out, xyz_row);
+  else if (C == 192) query_embed_kernel<192, false><<<grid, 256, 0, ST(stream)>>>(xyz, ldq, (const __half*)lin, R, (__half*)out, xyz_row);
+  else return GVF_ERR_UNSUPPORTED;
+  RET();
+}
+
+// DiagonalGaussianDistribution (model/autoencoder.py:304-326): logvar clamped to [-30, 20]; sample = mean + exp(logvar / 2)
+// * noise; kl[b] = 0.5 * mean over the entry's elements of (mean^2 + var - 1 - logvar).  One CTA per batch entry.
+__global__ void __launch_bounds__(256) diag_gaussian_kernel(const float* __restrict__ mean, const float* __restrict__ logvar,
+                                                            const float* __restrict__ noise, long long per_batch,
+                                                            float* __restrict__ sample, float* __restrict__ kl) {
+  __shared__ float red[8];
+  const long long base = (long long)blockIdx.x * per_batch;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < per_batch; i += 256) {
+    const float m = mean[base + i];
+    const float lv = fminf(fmaxf(logvar[base + i], -30.0f), 20.0f);
+    if (sample) sample[base + i] = m + expf(0.5f * lv) * (noise ? noise[base + i] : 0.f);
+    acc += m * m + expf(lv) - 1.0f - lv;
+  }
+  acc = gvf::warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    if (kl) kl[blockIdx.x] = 0.5f * s / (float)per_batch;
+  }
+}
+
+GVF_API int gvf_diag_gaussian(const float* mean, const float* logvar, const float* noise, int B, long long per_batch,
+                              float* sample, float* kl, void* stream) {
+  if (!mean || !logvar || B <= 0 || per_batch <= 0) return GVF_ERR_INVALID;
+  diag_gaussian_kernel<<<B, 256, 0, ST(stream)>>>(mean, logvar, noise, per_batch, sample, kl);
   RET();
 }
 

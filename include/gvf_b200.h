@@ -267,6 +267,16 @@ GVF_API int gvf_ape(const float* xyz, int R, int C, float* out, void* stream);
  * (model/autoencoder.py:250-301,389-391,560; PreNorm of :562). */
 GVF_API int gvf_vae_query_embed(const float* queries, int ldq, const void* gs, int Q, int C, void* out,
                                 void* stream);
+/* Token embedding of the motion-VAE ENCODER (model/autoencoder.py:529-533): out fp16 [R, C] = LN_1e-5(lin[r]) +
+ * LN_1e-5(PointEmbed(xyz[xyz_row[r]])) without the PreNorm that gvf_vae_query_embed applies on top (the sum enters a
+ * residual stream first); lin fp16 [R, C] = input_embedding's Linear(3 -> C) of the per-frame displacement; xyz_row int32
+ * [R] (or NULL: row r) lets the T frames of a point share its position row. */
+GVF_API int gvf_vae_embed_sum(const float* xyz, int ldq, const int* xyz_row, const void* lin, int R, int C, void* out,
+                              void* stream);
+/* DiagonalGaussianDistribution (model/autoencoder.py:304-326): sample = mean + exp(clamp(logvar, -30, 20) / 2) * noise,
+ * kl[b] = 0.5 * mean_b(mean^2 + var - 1 - logvar); fp32 [B, per_batch]; sample / kl / noise may be NULL. */
+GVF_API int gvf_diag_gaussian(const float* mean, const float* logvar, const float* noise, int B, long long per_batch,
+                              float* sample, float* kl, void* stream);
 /* GEGLU (model/autoencoder.py:90-93): h [M,2F] fp16 -> [M,F] */
 GVF_API int gvf_geglu_f16(const void* h, long long M, int F, void* out, void* stream);
 GVF_API int gvf_cast_f32_f16(const float* x, long long n, void* out, void* stream);

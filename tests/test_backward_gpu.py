@@ -133,6 +133,10 @@ def test_skinny_linears_backward():
     assert _rel(acc, 2 * (x.T @ dy.float())) < 1e-5
     y32 = _rand((M, 96), g)
     assert _rel(ops.skinny_outer(x, y32), x.T @ y32) < 1e-5
+    # the vectorised path (fp16, N % 8 == 0, many rows): 8 columns per thread, row groups reduced through shared memory
+    for Mb, Nb in ((20000, 768), (393216, 768), (4097, 96), (5000, 200)):
+        xb, yb = _rand((Mb, K), g), _rand((Mb, Nb), g).half()
+        assert _rel(ops.skinny_outer(xb, yb), xb.T @ yb.float()) < 2e-5, (Mb, Nb)
 
 
 @pytest.mark.parametrize("C", [96, 192, 768])
