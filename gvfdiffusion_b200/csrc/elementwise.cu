@@ -331,9 +331,10 @@ __global__ void __launch_bounds__(256) query_embed_kernel(const float* __restric
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) { g[i] = (g[i] - mg) * rg + (p[i] - mp) * rp; s += g[i]; }
-  if constexpr (!FINAL) {
+  if constexpr (!FINAL) {                          // fp32: LayerNorm outputs stay fp32 under autocast, and so does their sum
+    float* o32 = reinterpret_cast<float*>(out);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) out[(size_t)qi * C + i * 32 + lane] = __float2half_rn(g[i]);
+    for (int i = 0; i < PER; ++i) o32[(size_t)qi * C + i * 32 + lane] = g[i];
     return;
   }
   const float m = warp_sum(s) / C;

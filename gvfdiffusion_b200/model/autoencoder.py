@@ -2,12 +2,13 @@
 VAE (model/autoencoder.py:345-609): same constructor keywords, same state-dict names for the
 decode weights (`proj`, `layers.{i}.{0,1}.fn.*`, `gs_embedding.0`, `decoder_cross_attn.fn.*`,
 `to_outputs`), `decode(x, queries)` on the sm_100a engine -- forward only under no_grad, forward + hand-written
-backward (vae_train.py) when autograd is recording.  `encode` (FPS + KNN interpolation +
-cross-attention, training / dataset preparation only) is out of scope.
+backward (vae_train.py) when autograd is recording.  `encode` (FPS + KNN interpolation + cross-attention +
+DiagonalGaussian, model/autoencoder.py:502-550) runs forward on the engine of vae_encode.py.
 """
 import torch
 import torch.nn as nn
 
+from ..vae_encode import VAEEncodeEngine
 from ..vae_engine import VAEDecodeEngine
 from ..vae_train import VAEDecodeTrainEngine
 
@@ -63,7 +64,12 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         if dim_head * heads != dim or dim_head not in (32, 64):
             raise NotImplementedError("the sm_100a attention kernels cover head dims 32 and 64")
         self.depth, self.dim, self.heads, self.num_timesteps, self.chunk_size = depth, dim, heads, num_timesteps, chunk_size
-        self.num_latents, self.num_inputs = num_latents, num_inputs
+        self.num_latents, self.num_inputs, self.knn_k, self.beta = num_latents, num_inputs, knn_k, beta
+        # encoder (model/autoencoder.py:385-415): one cross-attention block + feed-forward, token embedding, heads
+        self.cross_attend_blocks = nn.ModuleList([_Fn(_Attn(dim, dim, dim)), _Fn(_FF(dim))])
+        self.input_embedding = nn.Sequential(nn.Linear(input_dim, dim), nn.LayerNorm(dim, elementwise_affine=False))
+        self.mean_fc = nn.Linear(dim, latent_dim)
+        self.logvar_fc = nn.Linear(dim, latent_dim)
         self.layers = nn.ModuleList([nn.ModuleList([_Fn(_Attn(dim, dim, dim)), _Fn(_FF(dim))]) for _ in range(depth)])
         self.gs_embedding = nn.Sequential(nn.Linear(gs_dim, dim), nn.LayerNorm(dim, elementwise_affine=False))
         self.decoder_cross_attn = _Fn(_Attn(queries_dim, dim, dim))
@@ -78,16 +84,21 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         nn.init.constant_(self.to_outputs.bias, 0)
         self._engine, self._sig = None, None
         self._train_engine, self._train_sig = None, None
-        self._param_names = [n for n, _ in self.named_parameters()]
+        self._enc_engine, self._enc_sig = None, None
+        self._encoder_loaded = True                     # False after loading a decode-only checkpoint
+        self._ENC = ("cross_attend_blocks.", "input_embedding.", "mean_fc.", "logvar_fc.")
+        # decode() is differentiable with respect to the DECODE parameters (the encoder is forward-only here)
+        self._param_names = [n for n, _ in self.named_parameters() if not n.startswith(self._ENC)]
 
     def load_state_dict(self, state_dict, strict=False, **kw):
         # reference checkpoints also carry the encoder; only the decode weights are consumed here
         own = self.state_dict()
         sub = {k: v for k, v in state_dict.items() if k in own}
         missing = [k for k in own if k not in sub]
-        if missing:
-            raise KeyError(f"decode weights missing from checkpoint: {missing[:4]}...")
-        return super().load_state_dict(sub, strict=True)
+        if any(not k.startswith(self._ENC) for k in missing):
+            raise KeyError(f"decode weights missing from checkpoint: {[k for k in missing if not k.startswith(self._ENC)][:4]}...")
+        self._encoder_loaded = not missing              # decode-only checkpoints are fine for decode()
+        return super().load_state_dict(sub, strict=False)
 
     def engine(self):
         sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -98,6 +109,19 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
             self._engine = VAEDecodeEngine(self.state_dict(), self.heads, self.num_timesteps, dev, self.chunk_size)
             self._sig = sig
         return self._engine
+
+    def encode_engine(self):
+        if not self._encoder_loaded:
+            raise RuntimeError("this checkpoint carried no encoder weights (cross_attend_blocks / input_embedding / mean_fc / "
+                               "logvar_fc)")
+        sig = tuple((p.data_ptr(), p._version) for n, p in self.named_parameters() if n.startswith(self._ENC))
+        if self._enc_engine is None or sig != self._enc_sig:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("encode runs on a CUDA device only (no CPU fallback)")
+            self._enc_engine = VAEEncodeEngine(self.state_dict(), self.heads, self.num_latents, self.knn_k, self.beta, dev)
+            self._enc_sig = sig
+        return self._enc_engine
 
     def train_engine(self):
         sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -113,11 +137,23 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         """x ((B*T), L, latent_dim), queries (B, Q, 14) -> (B, T, Q, output_dim) fp32.  Differentiable with respect to
         x, queries and every decode parameter when autograd is recording (training step); otherwise the inference
         engine runs."""
-        params = list(self.parameters())
+        named = dict(self.named_parameters())
+        params = [named[n] for n in self._param_names]                       # the decode parameters, in gradient order
         if torch.is_grad_enabled() and (x.requires_grad or queries.requires_grad or any(p.requires_grad for p in params)):
             return _DecodeFn.apply(self, x, queries, *params)
         with torch.no_grad():
             return self.engine().decode(x, queries)
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("encode() is training-data preparation, outside the inference hot path")
+    @torch.no_grad()
+    def encode(self, static_pc, delta_pc, static_gs_list, noise=None):
+        """static_pc (B, N, 3), delta_pc (B, T, N, 3), static_gs_list [P_b x 14] -> (kl, x, posterior, sampled_static_gs) like
+        the reference (model/autoencoder.py:502-550); `posterior` is a dict with mean / logvar.  Forward only."""
+        o = self.encode_engine().encode(static_pc, delta_pc, static_gs_list, noise)
+        return o["kl"], o["x"], {"mean": o["mean"], "logvar": o["logvar"]}, o["sampled_static_gs"]
+
+    def forward(self, static_gs, static_pc, delta_pc):
+        """model/autoencoder.py:620-627: encode -> pad_static_gs -> decode."""
+        from ..pipeline import pad_static_gs
+        kl, x, posterior, _ = self.encode(static_pc, delta_pc, static_gs)
+        padded, _ = pad_static_gs([g.to(x.device) for g in static_gs])
+        return {"logits": self.decode(x, padded), "kl": kl, "posterior": posterior}

@@ -267,7 +267,7 @@ GVF_API int gvf_ape(const float* xyz, int R, int C, float* out, void* stream);
  * (model/autoencoder.py:250-301,389-391,560; PreNorm of :562). */
 GVF_API int gvf_vae_query_embed(const float* queries, int ldq, const void* gs, int Q, int C, void* out,
                                 void* stream);
-/* Token embedding of the motion-VAE ENCODER (model/autoencoder.py:529-533): out fp16 [R, C] = LN_1e-5(lin[r]) +
+/* Token embedding of the motion-VAE ENCODER (model/autoencoder.py:529-533): out fp32 [R, C] = LN_1e-5(lin[r]) +
  * LN_1e-5(PointEmbed(xyz[xyz_row[r]])) without the PreNorm that gvf_vae_query_embed applies on top (the sum enters a
  * residual stream first); lin fp16 [R, C] = input_embedding's Linear(3 -> C) of the per-frame displacement; xyz_row int32
  * [R] (or NULL: row r) lets the T frames of a point share its position row. */

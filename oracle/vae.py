@@ -96,3 +96,57 @@ def vae_decode(sd, z, queries, heads, num_timesteps, precision="fp16", chunk_siz
         lat = attention(sd, "decoder_cross_attn.fn.", _ln(qe, 1e-6), ctx, heads, P)
         outs.append(P.linear(lat, sd["to_outputs.weight"], sd["to_outputs.bias"]))
     return torch.cat(outs, dim=1).reshape(B, T, Q, -1)
+
+
+# ---------------------------------------------------------------------------------------------- encode
+def fps_indices(points, K, start=0):
+    """Greedy farthest point sampling from `start`, squared distances (dx*dx + dy*dy) + dz*dz in fp32, ties -> lowest
+    index (the deterministic rule of gvf_fps; torch_cluster.fps, model/autoencoder.py:525, starts at a random point)."""
+    p = points.numpy().astype(np.float32)
+    mind = np.full(p.shape[0], 3.0e38, np.float32)
+    cur, idx = start, [start]
+    for _ in range(1, K):
+        d = p - p[cur]
+        dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        mind = np.minimum(mind, dist.astype(np.float32))
+        cur = int(np.argmax(mind))
+        idx.append(cur)
+    return torch.from_numpy(np.array(idx, dtype=np.int64))
+
+
+def token_embed(sd, disp, xyz, P):
+    """input_embedding(disp) + position_encoding(xyz): LN_1e-5(Linear(3 -> dim)(disp)) + LN_1e-5(PointEmbed(xyz)), fp32
+    (LayerNorm outputs are fp32 under autocast) -- model/autoencoder.py:386-391,529-533."""
+    dim = sd["input_embedding.0.weight"].shape[0]
+    a = _ln(P.linear(disp, sd["input_embedding.0.weight"], sd["input_embedding.0.bias"]), 1e-5)
+    return a + _ln(point_embed(xyz, dim, P), 1e-5)
+
+
+def vae_encode(sd, static_pc, delta_pc, static_gs_list, heads, num_latents, knn_k, beta, precision="fp16", noise=None):
+    """Restates GSKLTemporalVariationalAutoEncoder.encode (model/autoencoder.py:502-550) and compute_delta_interp
+    (:451-500).  -> dict(kl [(B T)], x [(B T), L, latent], mean, logvar, sampled_static_gs [B, L, 14])."""
+    from . import losses as OL
+    P = _P(precision)
+    sd = {k: v.float() for k, v in sd.items()}
+    B, N, _ = static_pc.shape
+    T = delta_pc.shape[1]
+    L = num_latents
+    sampled = torch.stack([g[fps_indices(g[:, :3], L)] for g in static_gs_list])            # [B, L, 14]
+    gs_xyz = sampled[:, :, :3].contiguous()
+    moving = delta_pc + static_pc.unsqueeze(1)
+    d, idx = OL.knn_points(gs_xyz, static_pc, K=knn_k)[:2]
+    est = OL.interp_deltas(d, idx, static_pc, moving, torch.full((B,), L, dtype=torch.int64), True, beta)   # [B, T, L, 3]
+    rep = lambda t: t.unsqueeze(1).expand(B, T, t.shape[1], t.shape[2])
+    a = token_embed(sd, est, rep(gs_xyz), P).reshape(B * T, L, -1)                            # latent tokens
+    ctx = token_embed(sd, delta_pc, rep(static_pc), P).reshape(B * T, N, -1)                  # point tokens
+    pre0, pre1 = "cross_attend_blocks.0.fn.", "cross_attend_blocks.1.fn."
+    x = attention(sd, pre0, _ln(a, 1e-6), _ln(ctx, 1e-6), heads, P) + a                       # fp32 residual stream
+    x = feed_forward(sd, pre1, _ln(x, 1e-6), P) + x
+    mean = P.linear(x, sd["mean_fc.weight"], sd["mean_fc.bias"])
+    logvar = P.linear(x, sd["logvar_fc.weight"], sd["logvar_fc.bias"]).clamp(-30.0, 20.0)
+    std, var = P.r(torch.exp(0.5 * logvar)), P.r(torch.exp(logvar))
+    if noise is None:
+        noise = torch.randn(mean.shape)
+    sample = mean + std * noise
+    kl = 0.5 * torch.mean(P.r(P.r(P.r(mean.pow(2)) + var - 1.0) - logvar), dim=[1, 2])
+    return {"kl": kl, "x": sample, "mean": mean, "logvar": logvar, "sampled_static_gs": sampled}

@@ -118,6 +118,67 @@ def gen_vae():
     return out
 
 
+def _fps_stub(x, batch, ratio):
+    """Stand-in for torch_cluster.fps (absent here): greedy farthest point sampling per batch entry from its FIRST point
+    (torch_cluster defaults to a random start), squared distances (dx*dx + dy*dy) + dz*dz in fp32, ties -> lowest index --
+    the deterministic rule of gvf_fps.  Returns global row indices, entry by entry."""
+    out = []
+    x = x.numpy().astype(np.float32)
+    for b in range(int(batch.max()) + 1):
+        rows = np.nonzero(batch.numpy() == b)[0]
+        p = x[rows]
+        K = int(round(float(ratio[b]) * len(rows)))
+        mind = np.full(len(rows), 3.0e38, np.float32)
+        cur, idx = 0, [0]
+        for _ in range(1, K):
+            d = p - p[cur]
+            dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+            mind = np.minimum(mind, dist.astype(np.float32))
+            cur = int(np.argmax(mind))
+            idx.append(cur)
+        out.append(torch.from_numpy(rows[np.array(idx)]))
+    return torch.cat(out)
+
+
+def gen_vae_encode():
+    """The reference's GSKLTemporalVariationalAutoEncoder.encode (model/autoencoder.py:502-550) on the tiny config, CPU,
+    fp32 and fp16 autocast, with torch_cluster.fps / pytorch3d.ops.knn_points replaced by deterministic stand-ins of their
+    documented semantics (both are absent third parties).  The posterior noise is drawn under a fixed seed and stored."""
+    import model.autoencoder as AE
+    import pytorch3d.ops as P3
+    AE.fps = _fps_stub
+    P3.knn_points = _bruteforce_knn_points
+    torch.manual_seed(2)
+    cfg = dict(TINY_VAE, knn_k=4, beta=7.0)
+    vae = GSKLTemporalVariationalAutoEncoder(**cfg).eval()
+    rerandomise_zero_layers(vae, std=0.05)
+    g = torch.Generator().manual_seed(17)
+    B, T, N, L = 2, cfg["num_timesteps"], cfg["num_inputs"], cfg["num_latents"]
+    static_pc = torch.rand(B, N, 3, generator=g) - 0.5
+    delta_pc = torch.randn(B, T, N, 3, generator=g) * 0.05
+    gs_list = []
+    for Pn in (100, 80):
+        gsx = torch.randn(Pn, 14, generator=g) * 0.3
+        gsx[:, :3] = torch.rand(Pn, 3, generator=g) - 0.5
+        gs_list.append(gsx)
+    keep = ("cross_attend_blocks.", "input_embedding.", "mean_fc.", "logvar_fc.")
+    out = {"cfg": cfg, "static_pc": static_pc, "delta_pc": delta_pc, "static_gs": gs_list,
+           "state_dict": {k: v.clone() for k, v in vae.state_dict().items() if k.startswith(keep)}}
+    with torch.no_grad():
+        for name, ctx in (("fp32", None), ("autocast_fp16", torch.autocast("cpu", dtype=torch.float16))):
+            torch.manual_seed(5)
+            if ctx is None:
+                kl, x, post, sgs = vae.encode(static_pc, delta_pc, gs_list)
+            else:
+                with ctx:
+                    kl, x, post, sgs = vae.encode(static_pc, delta_pc, gs_list)
+            out[name] = {"kl": kl.float(), "x": x.float(), "mean": post.mean.float(), "logvar": post.logvar.float(),
+                         "sampled_static_gs": sgs}
+        torch.manual_seed(5)
+        out["noise"] = torch.randn(out["fp32"]["mean"].shape)
+    return out
+
+
 def gen_p_sample(diffusion):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(1, 4, 8, 8, 8, generator=g)
@@ -607,6 +668,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "vae_encode":
+        torch.save(gen_vae_encode(), os.path.join(HERE, "vae_encode_tiny.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "flow_euler":
         torch.save(gen_flow_euler(), os.path.join(HERE, "flow_euler.pt"))
         return
@@ -623,6 +687,7 @@ def main():
     torch.save(sched, os.path.join(HERE, "schedule.pt"))
     torch.save(gen_dit(ns), os.path.join(HERE, "dit_tiny.pt"))
     torch.save(gen_vae(), os.path.join(HERE, "vae_tiny.pt"))
+    torch.save(gen_vae_encode(), os.path.join(HERE, "vae_encode_tiny.pt"))
     torch.save(gen_p_sample(diffusion), os.path.join(HERE, "p_sample.pt"))
     torch.save(gen_gaussian(), os.path.join(HERE, "gaussian.pt"))
     torch.save(gen_respace(), os.path.join(HERE, "respace.pt"))

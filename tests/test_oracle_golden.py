@@ -183,3 +183,17 @@ def test_loss_oracle_matches_reference():
         assert abs(float(loss) - float(c["loss"])) < 1e-7
         (go,) = torch.autograd.grad(loss, out)
         assert torch.allclose(go, c["grad_output"], atol=1e-9)
+
+
+def test_vae_encode_matches_reference():
+    """oracle/vae.py::vae_encode against the reference's own `encode` run on the CPU (fp32 and fp16 autocast) with
+    deterministic stand-ins for torch_cluster.fps / pytorch3d.knn_points (tests/golden/make_golden.py::gen_vae_encode)."""
+    g = load("vae_encode_tiny.pt")
+    c = g["cfg"]
+    for prec, key, tol in (("fp32", "fp32", 2e-5), ("fp16", "autocast_fp16", 2e-3)):
+        o = OVAE.vae_encode(g["state_dict"], g["static_pc"], g["delta_pc"], g["static_gs"], c["heads"], c["num_latents"],
+                            c["knn_k"], c["beta"], prec, noise=g["noise"])
+        assert torch.equal(o["sampled_static_gs"], g[key]["sampled_static_gs"])
+        for k in ("mean", "logvar", "x"):
+            assert rel(o[k], g[key][k]) < tol, (prec, k, rel(o[k], g[key][k]))
+        assert torch.allclose(o["kl"], g[key]["kl"], rtol=5e-3 if prec == "fp16" else 1e-5, atol=1e-6), (o["kl"], g[key]["kl"])

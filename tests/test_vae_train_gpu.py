@@ -45,7 +45,9 @@ def _check(v, sd, z, q, heads, T, tol, label):
     for prec in ("fp32", "fp16"):
         o_ref, dz, dq, gw = _oracle_grads(sd, z, q, heads, T, R, prec)
         errs = {"out": rel(out, o_ref), "dz": rel(zd.grad, dz), "dqueries": rel(qd.grad, dq)}
-        for n, p in v.named_parameters():
+        named = dict(v.named_parameters())
+        for n in v._param_names:                                  # every DECODE parameter (the encoder is forward-only)
+            p = named[n]
             assert p.grad is not None and p.grad.shape == p.shape, n
             errs[n] = rel(p.grad, gw[n])
         worst[prec] = max(errs.values())

@@ -119,7 +119,7 @@ def measure(steps=10, warmup=3, standin=True, seed=0):
                                   "canonical+delta rasteriser 24 frames + L1 + (1 - SSIM), gradients to all decoder parameters, "
                                   "latent, queries and raw canonical Gaussians"},
            "dtype": "f16 (fp32 accumulate, fp32 parameter gradients)", "data": "synthetic"}
-    grads = {n: p.grad.detach().clone() for n, p in vae.named_parameters()}
+    grads = {n: p.grad.detach().clone() for n, p in vae.named_parameters() if p.grad is not None}
     gz, gq, graw = z.grad.clone(), q.grad.clone(), [t.grad.clone() for t in S_["raw"]]
     if standin:
         sd = {k: v.detach().float().clone().requires_grad_(True) for k, v in vae.state_dict().items()}
