@@ -34,6 +34,8 @@ _SIGS = {
     "gvf_raster_forward_views": (C.c_int, [C.POINTER(RasterParams), C.c_int, C.c_int, C.c_int,
                                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
     "gvf_rgba_to_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "gvf_resample_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    "gvf_pad_crop_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gvf_raster_backward": (C.c_int, [C.POINTER(RasterParams), C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
                                       _P, _P, _P, C.c_size_t, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_gaussian_tensor": (C.c_int, [C.POINTER(RasterParams), C.c_int, _P, _P, _P, _P, _P, _P, _P]),

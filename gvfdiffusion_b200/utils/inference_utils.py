@@ -112,3 +112,69 @@ def align_gaussian_to_canonical(static_gs_model, canonical_image, canonical_alph
     qz = torch.tensor([math.cos(ang / 2), 0.0, 0.0, math.sin(ang / 2)], dtype=torch.float32, device=rot.device)
     static_gs_model.from_rotation(_quat_mul(qz.expand_as(static_gs_model.get_rotation), static_gs_model.get_rotation))
     return static_gs_model, best_scale
+
+
+# ---------------------------------------------------------------------------------------------- output stage (:276-297)
+def pil_resample_coeffs(in_size, out_size, support=3.0):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the LANCZOS filter over the whole input range:
+    -> (bounds int32 [out, 2], coeffs int32 [out, ksize], ksize).  Double arithmetic with libm's sin, like Pillow."""
+    def lanczos(x):
+        if -3.0 <= x < 3.0:
+            if x == 0.0:
+                return 1.0
+            a, b = x * math.pi, x * math.pi / 3.0
+            return (math.sin(a) / a) * (math.sin(b) / b)
+        return 0.0
+    scale = in_size / out_size
+    fscale = max(scale, 1.0)
+    sup = support * fscale
+    ksize = int(math.ceil(sup)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    ss = 1.0 / fscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - sup + 0.5), 0)
+        xmax = min(int(center + sup + 0.5), in_size) - xmin
+        w = [lanczos((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = sum(w)                                       # Pillow accumulates left to right in a double, as sum() does
+        if ww != 0.0:
+            w = [v / ww for v in w]
+        for x, v in enumerate(w):
+            kk[xx, x] = int(-0.5 + v * (1 << 22)) if v < 0 else int(0.5 + v * (1 << 22))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk, ksize
+
+
+_coef_cache = {}
+
+
+def resize_pad_frames_u8(frames, scale_factor, size=512, fill=255):
+    """frames uint8 [F, H, W, 3] on the device (gvf_rgba_to_u8 output) -> uint8 [F, size, size, 3]: PIL LANCZOS resize to
+    int(size * scale_factor) and centre pad (white) / crop, exactly the reference's per-frame host code (:284-297)."""
+    from .. import _lib
+    from .._lib import check, current_stream, ptr
+    if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3):
+        raise ValueError("frames: expected a CUDA uint8 [F, H, W, 3] tensor")
+    frames = frames.contiguous()
+    Fn, H, W, _ = frames.shape
+    t = int(size * scale_factor)
+    if t <= 0:
+        raise ValueError("scale factor too small")
+    dev = frames.device
+    key = (H, W, t, str(dev))
+    if key not in _coef_cache:
+        bh, kh, ksh = pil_resample_coeffs(W, t)
+        bv, kv, ksv = pil_resample_coeffs(H, t)
+        _coef_cache[key] = tuple(torch.from_numpy(a).to(dev) for a in (bh, kh, bv, kv)) + (ksh, ksv)
+    bh, kh, bv, kv, ksh, ksv = _coef_cache[key]
+    if t == W and t == H:
+        resized = frames                                  # Pillow returns a copy without resampling
+    else:
+        tmp = torch.empty((Fn, H, t, 3), dtype=torch.uint8, device=dev)
+        resized = torch.empty((Fn, t, t, 3), dtype=torch.uint8, device=dev)
+        check(_lib.lib().gvf_resample_u8(ptr(frames), Fn, H, W, t, t, ptr(bh), ptr(kh), ksh, ptr(bv), ptr(kv), ksv, ptr(tmp),
+                                         ptr(resized), current_stream()), "gvf_resample_u8")
+    out = torch.empty((Fn, size, size, 3), dtype=torch.uint8, device=dev)
+    check(_lib.lib().gvf_pad_crop_u8(ptr(resized), Fn, t, t, size, fill, ptr(out), current_stream()), "gvf_pad_crop_u8")
+    return out

@@ -122,6 +122,17 @@ GVF_API int gvf_raster_forward_views(const gvf_raster_params* prm, int F, int P,
  * planar fp32 rgba [F,4,H,W] -> interleaved uint8 [F,H,W,3] on the device (a quarter of the bytes to copy back). */
 GVF_API int gvf_rgba_to_u8(const float* rgba, int F, int H, int W, uint8_t* out, void* stream);
 
+/* Rest of the output stage (utils/inference_utils.py:284-297): `Image.fromarray(rgb).resize((t, t), LANCZOS)` followed by the
+ * centre pad (white) / centre crop back to 512^2, on interleaved uint8 frames [F, H, W, 3] that stay on the device.
+ * gvf_resample_u8 is Pillow's separable 8-bit resampler: bounds_* int32 [out, 2] = (first input index, tap count), coef_*
+ * int32 [out, ksize] = taps in fixed point with 22 fractional bits (gvfdiffusion_b200/utils/inference_utils.py:
+ * pil_resample_coeffs computes them in double like Pillow's precompute_coeffs); horizontal pass into tmp [F, Hin, Wout, 3],
+ * then vertical into out [F, Hout, Wout, 3].  Byte-identical to PIL. */
+GVF_API int gvf_resample_u8(const uint8_t* in, int F, int Hin, int Win, int Hout, int Wout, const int* bounds_h,
+                            const int* coef_h, int ksize_h, const int* bounds_v, const int* coef_v, int ksize_v,
+                            uint8_t* tmp, uint8_t* out, void* stream);
+GVF_API int gvf_pad_crop_u8(const uint8_t* in, int F, int Hin, int Win, int S, int fill, uint8_t* out, void* stream);
+
 /* Backward -- replaces GaussianRasterizer.backward (reached through autograd from reference
  * train_vae.py:313-352) fused with the backward of GaussianModel.get_*_with_delta.  Must follow a
  * gvf_raster_forward call with the same arguments and workspace (it reads the splat records, sorted
