@@ -84,6 +84,7 @@ _SIGS = {
     "gvf_vae_query_embed": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "gvf_vae_embed_sum": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P]),
     "gvf_diag_gaussian": (C.c_int, [_P, _P, _P, C.c_int, C.c_longlong, _P, _P, _P]),
+    "gvf_diag_gaussian_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_longlong, _P, _P, _P]),
     "gvf_geglu_f16": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P]),
     "gvf_cast_f32_f16": (C.c_int, [_P, C.c_longlong, _P, _P]),
     "gvf_dit_final_layer": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),

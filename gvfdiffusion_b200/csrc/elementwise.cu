@@ -658,6 +658,34 @@ __global__ void __launch_bounds__(256) diag_gaussian_kernel(const float* __restr
   }
 }
 
+// backward of the above: d mean = d sample + d kl[b] * mean / n,  d logvar = (d sample * noise * std / 2 + d kl[b] * (var - 1)
+// / (2 n)) inside the clamp range, 0 outside (n = elements per batch entry)
+__global__ void __launch_bounds__(256) diag_gaussian_bwd_kernel(const float* __restrict__ mean, const float* __restrict__ logvar,
+                                                                const float* __restrict__ noise,
+                                                                const float* __restrict__ dsample,
+                                                                const float* __restrict__ dkl, long long per_batch,
+                                                                long long total, float* __restrict__ dmean,
+                                                                float* __restrict__ dlogvar) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float gk = dkl ? dkl[i / per_batch] / (float)per_batch : 0.f;
+  const float gs = dsample ? dsample[i] : 0.f;
+  const float lv0 = logvar[i];
+  const bool inside = lv0 >= -30.0f && lv0 <= 20.0f;
+  const float lv = fminf(fmaxf(lv0, -30.0f), 20.0f);
+  dmean[i] = gs + gk * mean[i];
+  dlogvar[i] = inside ? gs * (noise ? noise[i] : 0.f) * 0.5f * expf(0.5f * lv) + 0.5f * gk * (expf(lv) - 1.0f) : 0.f;
+}
+
+GVF_API int gvf_diag_gaussian_bwd(const float* mean, const float* logvar, const float* noise, const float* dsample,
+                                  const float* dkl, int B, long long per_batch, float* dmean, float* dlogvar, void* stream) {
+  if (!mean || !logvar || !dmean || !dlogvar || B <= 0 || per_batch <= 0) return GVF_ERR_INVALID;
+  const long long total = (long long)B * per_batch;
+  diag_gaussian_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(mean, logvar, noise, dsample, dkl, per_batch,
+                                                                                  total, dmean, dlogvar);
+  RET();
+}
+
 GVF_API int gvf_diag_gaussian(const float* mean, const float* logvar, const float* noise, int B, long long per_batch,
                               float* sample, float* kl, void* stream) {
   if (!mean || !logvar || B <= 0 || per_batch <= 0) return GVF_ERR_INVALID;

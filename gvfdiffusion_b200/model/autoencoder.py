@@ -32,6 +32,25 @@ class _DecodeFn(torch.autograd.Function):
         return (None, dz.view(ctx.z_shape), dq.to(ctx.q_dtype)) + tuple(grads[n] for n in ctx.names)
 
 
+class _EncodeFn(torch.autograd.Function):
+    """encode() under autograd: gradients of the sampled latent and of the KL term flow to the ENCODER parameters; the
+    point clouds and Gaussians are data (the reference interpolates them under no_grad, model/autoencoder.py:470)."""
+
+    @staticmethod
+    def forward(ctx, module, static_pc, delta_pc, gs_list, noise, *params):
+        eng = module.encode_engine()
+        o, saved = eng.forward_train(static_pc, delta_pc, gs_list, noise)
+        ctx.eng, ctx.saved, ctx.names = eng, saved, module._enc_names
+        ctx.mark_non_differentiable(o["mean"], o["logvar"], o["sampled_static_gs"])
+        return o["kl"], o["x"], o["mean"], o["logvar"], o["sampled_static_gs"]
+
+    @staticmethod
+    def backward(ctx, dkl, dx, *_):
+        grads = ctx.eng.backward(ctx.saved, dx, dkl)
+        ctx.saved = None
+        return (None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
 class _Fn(nn.Module):
     def __init__(self, fn):
         super().__init__()
@@ -89,6 +108,7 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         self._ENC = ("cross_attend_blocks.", "input_embedding.", "mean_fc.", "logvar_fc.")
         # decode() is differentiable with respect to the DECODE parameters (the encoder is forward-only here)
         self._param_names = [n for n, _ in self.named_parameters() if not n.startswith(self._ENC)]
+        self._enc_names = [n for n, _ in self.named_parameters() if n.startswith(self._ENC)]
 
     def load_state_dict(self, state_dict, strict=False, **kw):
         # reference checkpoints also carry the encoder; only the decode weights are consumed here
@@ -144,11 +164,17 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         with torch.no_grad():
             return self.engine().decode(x, queries)
 
-    @torch.no_grad()
     def encode(self, static_pc, delta_pc, static_gs_list, noise=None):
         """static_pc (B, N, 3), delta_pc (B, T, N, 3), static_gs_list [P_b x 14] -> (kl, x, posterior, sampled_static_gs) like
-        the reference (model/autoencoder.py:502-550); `posterior` is a dict with mean / logvar.  Forward only."""
-        o = self.encode_engine().encode(static_pc, delta_pc, static_gs_list, noise)
+        the reference (model/autoencoder.py:502-550); `posterior` is a dict with mean / logvar.  Differentiable with respect
+        to the encoder parameters when autograd is recording."""
+        named = dict(self.named_parameters())
+        params = [named[n] for n in self._enc_names]
+        if torch.is_grad_enabled() and self._encoder_loaded and any(p.requires_grad for p in params):
+            kl, x, mean, logvar, sgs = _EncodeFn.apply(self, static_pc, delta_pc, static_gs_list, noise, *params)
+            return kl, x, {"mean": mean, "logvar": logvar}, sgs
+        with torch.no_grad():
+            o = self.encode_engine().encode(static_pc, delta_pc, static_gs_list, noise)
         return o["kl"], o["x"], {"mean": o["mean"], "logvar": o["logvar"]}, o["sampled_static_gs"]
 
     def forward(self, static_gs, static_pc, delta_pc):

@@ -51,9 +51,10 @@ class VAEEncodeEngine:
         return out
 
     @torch.no_grad()
-    def encode(self, static_pc, delta_pc, static_gs_list, noise=None):
+    def encode(self, static_pc, delta_pc, static_gs_list, noise=None, save=None):
         """static_pc [B, N, 3], delta_pc [B, T, N, 3], static_gs_list: B tensors [P_b, 14]
-        -> dict(kl [(B T)], x [(B T), L, latent], mean, logvar, sampled_static_gs [B, L, 14])."""
+        -> dict(kl [(B T)], x [(B T), L, latent], mean, logvar, sampled_static_gs [B, L, 14]).
+        save: a dict that receives the activations `backward` needs (training step)."""
         dev, L, H, d, dim = self.dev, self.L, self.H, self.d, self.dim
         static_pc = static_pc.to(dev, F32).contiguous()
         delta_pc = delta_pc.to(dev, F32).contiguous()
@@ -77,6 +78,9 @@ class VAEEncodeEngine:
         # cross_attend_blocks[0]: x = Attention(LN a, LN ctx) + a ; [1]: x = FF(LN x) + x   (:538-539)
         q = ops.gemm(ops.ln_mod(A, eps=1e-6), self.w_q, None, ops.EPI_F16)
         kv = ops.gemm(ops.ln_mod(Cx, eps=1e-6), self.w_kv, None, ops.EPI_F16).view(B * T, N, 2, H, d)
+        if save is not None:                                                   # training: the forward that also leaves LSE2
+            ao, save["lse"] = ops.attention_fwd_lse(q.view(B * T, L, H, d), kv[:, :, 0], kv[:, :, 1], d ** -0.5)
+            return self._encode_train(save, A, Cx, q, kv, ao, est, delta_pc, sampled, noise, B, T, N)
         ao = ops.attention(q.view(B * T, L, H, d), kv[:, :, 0], kv[:, :, 1], d ** -0.5)
         x = A
         ops.gemm(ao.view(B * T * L, dim), self.w_out, self.b_out, ops.EPI_RESID_F32, out=x)
@@ -86,9 +90,14 @@ class VAEEncodeEngine:
         else:
             G = ops.geglu(ops.gemm(hmid, self.w1, self.b1, ops.EPI_F16))
         ops.gemm(G, self.w2, self.b2, ops.EPI_RESID_F32, out=x)
+        return self._heads(x, sampled, noise, B, T)
+
+    def _heads(self, x, sampled, noise, B, T, save=None):
+        dev, L = self.dev, self.L
         # heads: Linear under autocast -> fp16-rounded values
         ml = torch.empty((B * T * L, self.w_ml.shape[0]), dtype=F32, device=dev)
-        ops.gemm(ops.cast_f16(x), self.w_ml, self.b_ml, ops.EPI_F32_COMPACT, out=ml)
+        x16 = ops.cast_f16(x)
+        ops.gemm(x16, self.w_ml, self.b_ml, ops.EPI_F32_COMPACT, out=ml)
         mean = ml[:, :self.latent].contiguous().view(B * T, L, self.latent)
         logvar = ml[:, self.latent:2 * self.latent].contiguous().view(B * T, L, self.latent)
         if noise is None:
@@ -97,4 +106,88 @@ class VAEEncodeEngine:
         sample, kl = torch.empty_like(mean), torch.empty(B * T, dtype=F32, device=dev)
         check(_lib.lib().gvf_diag_gaussian(ptr(mean), ptr(logvar), ptr(noise), B * T, L * self.latent, ptr(sample), ptr(kl),
                                            current_stream()), "gvf_diag_gaussian")
+        if save is not None:
+            save.update(x16=x16, mean=mean, logvar=logvar, noise=noise)
         return {"kl": kl, "x": sample, "mean": mean, "logvar": logvar.clamp(-30.0, 20.0), "sampled_static_gs": sampled}
+
+    # ------------------------------------------------------------------------------------------------ training step
+    def _encode_train(self, sv, A, Cx, q, kv, ao, est, delta_pc, sampled, noise, B, T, N):
+        """Tail of `encode` with every activation the backward needs kept (un-fused GEGLU, out-of-place residuals)."""
+        L, dim = self.L, self.dim
+        M = B * T * L
+        qn, cn = ops.ln_mod(A, eps=1e-6), ops.ln_mod(Cx, eps=1e-6)            # recomputed: cheap, keeps `encode` linear
+        x1 = A.clone()
+        ops.gemm(ao.view(M, dim), self.w_out, self.b_out, ops.EPI_RESID_F32, out=x1)
+        hmid = ops.ln_mod(x1, eps=1e-6)
+        Hf = ops.gemm(hmid, self.w1, self.b1, ops.EPI_F16)
+        G = ops.geglu(Hf)
+        x2 = x1.clone()
+        ops.gemm(G, self.w2, self.b2, ops.EPI_RESID_F32, out=x2)
+        sv.update(A=A, Cx=Cx, qn=qn, cn=cn, q=q, kv=kv, ao=ao, x1=x1, hmid=hmid, Hf=Hf, G=G, x2=x2, est=est, delta_pc=delta_pc,
+                  shape=(B, T, N))
+        return self._heads(x2, sampled, noise, B, T, save=sv)
+
+    def forward_train(self, static_pc, delta_pc, static_gs_list, noise=None):
+        sv = {}
+        return self.encode(static_pc, delta_pc, static_gs_list, noise, save=sv), sv
+
+    def backward(self, sv, dx, dkl):
+        """dx [(B T), L, latent] (gradient of the sampled latent), dkl [(B T)] or None -> {encoder parameter name: fp32 grad}.
+        static_pc / delta_pc / the Gaussians are data (the reference interpolates them under no_grad, :470)."""
+        if not hasattr(self, "w_q_t"):
+            T_ = ops.transpose
+            self.w_q_t, self.w_kv_t, self.w_out_t = T_(self.w_q), T_(self.w_kv), T_(self.w_out)
+            self.w1_t, self.w2_t, self.w_ml_t = T_(self.w1), T_(self.w2), T_(self.w_ml)
+        dev, L, H, d, dim, lat = self.dev, self.L, self.H, self.d, self.dim, self.latent
+        B, T, N = sv["shape"]
+        M = B * T * L
+        g = {}
+        a, f = "cross_attend_blocks.0.fn.", "cross_attend_blocks.1.fn."
+        wg = lambda dy, x: ops.gemm_tn(dy, x)
+        # DiagonalGaussian + heads
+        dmean, dlogvar = torch.empty_like(sv["mean"]), torch.empty_like(sv["mean"])
+        dxc = None if dx is None else dx.detach().to(dev, F32).contiguous()
+        dkc = None if dkl is None else dkl.detach().to(dev, F32).contiguous()
+        check(_lib.lib().gvf_diag_gaussian_bwd(ptr(sv["mean"]), ptr(sv["logvar"]), ptr(sv["noise"]), ptr(dxc), ptr(dkc), B * T,
+                                               L * lat, ptr(dmean), ptr(dlogvar), current_stream()), "gvf_diag_gaussian_bwd")
+        dml = torch.zeros((M, self.w_ml.shape[0]), dtype=F16, device=dev)
+        dml[:, :lat] = dmean.view(M, lat)
+        dml[:, lat:2 * lat] = dlogvar.view(M, lat)
+        wml = wg(dml, sv["x16"])                                                 # [32, dim]
+        g["mean_fc.weight"], g["logvar_fc.weight"] = wml[:lat], wml[lat:2 * lat]
+        bml = ops.colsum(dml)
+        g["mean_fc.bias"], g["logvar_fc.bias"] = bml[:lat], bml[lat:2 * lat]
+        dx2 = ops.gemm(dml, self.w_ml_t, None, ops.EPI_F16)                      # [M, dim]
+        # feed-forward block: x2 = x1 + net.2(GEGLU(net.0(LN x1)))
+        dG = ops.gemm(dx2, self.w2_t, None, ops.EPI_F16)
+        g[f + "net.2.weight"], g[f + "net.2.bias"] = wg(dx2, sv["G"]), ops.colsum(dx2)
+        dHf = ops.geglu_bwd(sv["Hf"], dG)
+        dh = ops.gemm(dHf, self.w1_t, None, ops.EPI_F16)
+        g[f + "net.0.weight"], g[f + "net.0.bias"] = wg(dHf, sv["hmid"]), ops.colsum(dHf)
+        dx1 = ops.ln_bwd(sv["x1"], dh, dx2, eps=1e-6)
+        # cross-attention block: x1 = a + to_out(attention(to_q(LN a), to_kv(LN ctx)))
+        dao = ops.gemm(dx1, self.w_out_t, None, ops.EPI_F16)
+        g[a + "to_out.weight"], g[a + "to_out.bias"] = wg(dx1, sv["ao"].view(M, dim)), ops.colsum(dx1)
+        kv = sv["kv"]
+        dq, dkv = torch.empty_like(sv["q"]), torch.empty_like(kv)
+        ops.attention_bwd(sv["q"].view(B * T, L, H, d), kv[:, :, 0], kv[:, :, 1], sv["ao"], dao.view(B * T, L, H, d), sv["lse"],
+                          d ** -0.5, dq.view(B * T, L, H, d), dkv[:, :, 0], dkv[:, :, 1])
+        dkv2 = dkv.view(B * T * N, 2 * dim)
+        g[a + "to_q.weight"] = wg(dq, sv["qn"])
+        g[a + "to_kv.weight"] = wg(dkv2, sv["cn"])
+        dqn = ops.gemm(dq, self.w_q_t, None, ops.EPI_F16)
+        dcn = ops.gemm(dkv2, self.w_kv_t, None, ops.EPI_F16)
+        dA = ops.ln_bwd(sv["A"], dqn, dx1, eps=1e-6)                              # + the residual branch
+        dC = ops.ln_bwd(sv["Cx"], dcn, None, eps=1e-6)
+        # token embeddings: LN_1e-5(Linear(3 -> dim)(disp)) + LN_1e-5(PointEmbed) -- only the Linear has parameters
+        est2, dpc2 = sv["est"].reshape(M, 3), sv["delta_pc"].reshape(B * T * N, 3)
+        lin_a = ops.small_linear(est2, self.w_in, self.b_in, out_f16=True)
+        lin_c = ops.small_linear(dpc2, self.w_in, self.b_in, out_f16=True)
+        dlin_a = ops.ln_bwd(lin_a, dA, None, eps=1e-5)
+        dlin_c = ops.ln_bwd(lin_c, dC, None, eps=1e-5)
+        wt = ops.skinny_outer(est2, dlin_a)
+        wt = ops.skinny_outer(dpc2, dlin_c, out=wt, accumulate=True)             # [3, dim] = dW^T
+        g["input_embedding.0.weight"] = wt.t().contiguous()
+        bsum = ops.colsum(dlin_a)
+        g["input_embedding.0.bias"] = ops.colsum(dlin_c, out=bsum, accumulate=True)
+        return g

@@ -288,6 +288,8 @@ GVF_API int gvf_vae_embed_sum(const float* xyz, int ldq, const int* xyz_row, con
  * kl[b] = 0.5 * mean_b(mean^2 + var - 1 - logvar); fp32 [B, per_batch]; sample / kl / noise may be NULL. */
 GVF_API int gvf_diag_gaussian(const float* mean, const float* logvar, const float* noise, int B, long long per_batch,
                               float* sample, float* kl, void* stream);
+GVF_API int gvf_diag_gaussian_bwd(const float* mean, const float* logvar, const float* noise, const float* dsample,
+                                  const float* dkl, int B, long long per_batch, float* dmean, float* dlogvar, void* stream);
 /* GEGLU (model/autoencoder.py:90-93): h [M,2F] fp16 -> [M,F] */
 GVF_API int gvf_geglu_f16(const void* h, long long M, int F, void* out, void* stream);
 GVF_API int gvf_cast_f32_f16(const float* x, long long n, void* out, void* stream);

@@ -68,3 +68,71 @@ def test_encode_shipped_width_matches_oracle():
     print("encode (dim 768) vs oracle fp16:", {k: f"{a:.2e}" for k, a in e.items()})
     assert max(e.values()) < 2e-3, e
     assert torch.allclose(kl.cpu(), o["kl"], rtol=5e-3, atol=1e-5)
+
+
+def _oracle_train(sd, g, heads, cfg, R, wkl, noise):
+    sd = {k: v.clone().float().requires_grad_(True) for k, v in sd.items()}
+    o = OVAE.vae_encode(sd, g["static_pc"], g["delta_pc"], g["static_gs"], heads, cfg["num_latents"], cfg["knn_k"], cfg["beta"],
+                        "fp16", noise=noise)                     # fp16 roundings of the forward, straight-through gradients
+    ((o["x"] * R).sum() + wkl * o["kl"].sum()).backward()
+    return {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize("attn_std", [None, 0.1])
+def test_encode_backward_matches_oracle_autograd(attn_std):
+    """Gradients of (sampled latent, KL) with respect to every encoder parameter against torch autograd of the oracle
+    restatement, tiny golden configuration (golden weights, and to_q / to_kv re-drawn with std 0.1 = logits of order one);
+    tolerance 1e-2 rel. L2 (fp16 activation gradients).  One gradient is bounded differently: d to_q.  The keys of this
+    attention are embeddings of neighbouring points, i.e. nearly parallel vectors, and every row of dS sums to zero, so
+    dQ = dS K cancels to ~0.2 % of its terms (measured: |dQ| 1e-3 for |dO| 0.5) and carries the fp16 rounding of dS
+    amplified -- 5.6e-2 relative on dQ with exactly the same kernel that gives 3e-4 on uncorrelated keys
+    (tests/test_backward_gpu.py); flash-attn rounds dS to fp16 as well.  It is bounded against the size of the sibling
+    gradient d to_kv instead."""
+    from gvfdiffusion_b200.model.autoencoder import GSKLTemporalVariationalAutoEncoder as VAE
+    g = torch.load(os.path.join(G, "vae_encode_tiny.pt"), weights_only=False)
+    dec = torch.load(os.path.join(G, "vae_tiny.pt"), weights_only=False)
+    enc_sd = {k: t.clone() for k, t in g["state_dict"].items()}
+    if attn_std is not None:
+        gen = torch.Generator().manual_seed(8)
+        for k in ("cross_attend_blocks.0.fn.to_q.weight", "cross_attend_blocks.0.fn.to_kv.weight"):
+            enc_sd[k] = torch.randn(enc_sd[k].shape, generator=gen) * attn_std
+    v = VAE(**g["cfg"])
+    v.load_state_dict({**dec["state_dict"], **enc_sd})
+    v = v.to(DEV)
+    R = torch.randn(g["noise"].shape, generator=torch.Generator().manual_seed(2))
+    kl, x, post, _ = v.encode(g["static_pc"].to(DEV), g["delta_pc"].to(DEV), [t.to(DEV) for t in g["static_gs"]], noise=g["noise"])
+    assert x.requires_grad and kl.requires_grad
+    ((x * R.to(DEV)).sum() + 3.0 * kl.sum()).backward()
+    ref = _oracle_train(enc_sd, g, g["cfg"]["heads"], g["cfg"], R, 3.0, g["noise"])
+    named = dict(v.named_parameters())
+    errs = {n: rel(named[n].grad, ref[n]) for n in v._enc_names}
+    print(f"encode backward vs oracle autograd (attn std {attn_std}):",
+          {k: f"{e:.2e}" for k, e in sorted(errs.items(), key=lambda kv: -kv[1])[:4]})
+    tq, tkv = "cross_attend_blocks.0.fn.to_q.weight", "cross_attend_blocks.0.fn.to_kv.weight"
+    cancel = float((named[tq].grad.cpu() - ref[tq]).norm() / ref[tkv].norm())
+    print(f"  |d to_q| / |d to_kv| = {float(ref[tq].norm() / ref[tkv].norm()):.2e}, d to_q error / |d to_kv| = {cancel:.2e}")
+    assert cancel < 2e-3
+    errs.pop(tq)
+    assert max(errs.values()) < 1e-2, errs
+    assert all(named[n].grad is None for n in v._param_names)                # the decoder was not involved
+
+
+def test_model_forward_is_differentiable_end_to_end():
+    """model(static_gs, static_pc, delta_pc) = encode -> pad -> decode (model/autoencoder.py:620-627): one backward reaches
+    encoder and decoder parameters (train_vae.py:293-353: `output = self.model(...)`, KL + reconstruction terms)."""
+    from gvfdiffusion_b200.model.autoencoder import GSKLTemporalVariationalAutoEncoder as VAE
+    g = torch.load(os.path.join(G, "vae_encode_tiny.pt"), weights_only=False)
+    dec = torch.load(os.path.join(G, "vae_tiny.pt"), weights_only=False)
+    v = VAE(**g["cfg"])
+    v.load_state_dict({**dec["state_dict"], **g["state_dict"]})
+    v = v.to(DEV)
+    torch.manual_seed(0)
+    out = v([t.to(DEV) for t in g["static_gs"]], g["static_pc"].to(DEV), g["delta_pc"].to(DEV))
+    # a SUM, not a mean: fp16 activation gradients need the magnitude a GradScaler would give them (with a mean over
+    # 4 200 outputs the attention's dS underflows fp16 and d to_q comes out exactly zero -- in the reference too)
+    loss = out["logits"].square().sum() + out["kl"].sum()
+    loss.backward()
+    named = dict(v.named_parameters())
+    for n in v._enc_names + v._param_names:
+        assert named[n].grad is not None and torch.isfinite(named[n].grad).all(), n
+    assert float(named["cross_attend_blocks.0.fn.to_q.weight"].grad.abs().max()) > 0
