@@ -224,27 +224,29 @@ def main():
         return run_reference(args, rank)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    if args.config == "cfg3":
-        if rank == 0:
-            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
-            import train_step_bench as TSB
-            mon = ClockSampler(local)
-            mon.start()
-            res = TSB.measure(steps=args.steps, warmup=max(args.warmup, 3), standin=not args.no_gpu_reference)
-            mon.stop_flag = True
-            mon.join(timeout=2)
-            res.update({"n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-                        "ms_per_step": res["ms_forward"] + res["ms_backward"], "higher_is_better": True, "scaling": "weak",
-                        "vs_baseline": None, "clocks": mon.summary()})
-            real_stdout.write(json.dumps(res) + "\n")
-            real_stdout.flush()
-        return
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.config == "cfg3":
+        # BASELINE configs[2] (and, for N > 1, the data-parallel half of configs[4]: every rank steps its own object and the
+        # fp32 parameter gradients are averaged with one NCCL all-reduce inside the timed step)
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        import train_step_bench as TSB
+        mon = ClockSampler(local)
+        mon.start()
+        res = TSB.measure(steps=args.steps, warmup=max(args.warmup, 3), standin=(not args.no_gpu_reference) and world == 1,
+                          seed=rank, world=world, device=dev)
+        mon.stop_flag = True
+        mon.join(timeout=2)
+        if rank == 0:
+            res.update({"n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+                        "scaling": "weak", "vs_baseline": None, "clocks": mon.summary()})
+            real_stdout.write(json.dumps(res) + "\n")
+            real_stdout.flush()
+        return
     from gvfdiffusion_b200 import _lib, ops
     from gvfdiffusion_b200.pipeline import GVFPipeline
     if args.pdl:

@@ -63,3 +63,24 @@ def test_rasteriser_has_no_tensor_core_instructions(sass_by_kernel):
         for name, body in _kernels(sass_by_kernel, needle).items():
             assert not re.search(r"UTC\w*MMA", body) and not LEGACY.search(body), name
     assert "MUFU.EX2" in next(iter(_kernels(sass_by_kernel, "sort_blend_kernel").values()))
+
+
+def test_round2_kernels_are_blackwell_native(sass_by_kernel):
+    """attention v8 and the training-step kernels: tcgen05 + TMEM + TMA; the split-K epilogue reduces through the TMA unit
+    (UTMAREDG), the sparse-convolution GEMM gathers its A rows with tile::gather4 (UTMALDG ... GATHER4 / .G4), the attention
+    backward reads its LSE / D rows with bulk copies (UBLKCP)."""
+    for needle in ("attn_fwd8_kernel", "attn_bwd_dkdv_kernel", "attn_bwd_dq_kernel"):
+        ks = _kernels(sass_by_kernel, needle)
+        assert ks, needle
+        for name, body in ks.items():
+            assert re.search(r"UTC\w*MMA", body) and "UTMALDG" in body and "LDTM" in body and "STTM" in body, name
+            assert not LEGACY.search(body), name
+    assert any("UBLKCP" in b for b in _kernels(sass_by_kernel, "attn_bwd_dq_kernel").values())
+    # fp32-store epilogue (MODE 4): TMA reduce-add for the split-K partial tiles
+    m4 = {k: b for k, b in _kernels(sass_by_kernel, "gemm_ws_kernel").items() if re.search(r"ELi4ELi[12]ELb", k)}
+    assert m4 and all("UTMAREDG" in b for b in m4.values()), list(m4)[:2]
+    # MN-major (TRANS) and gather instantiations exist and are tcgen05 kernels
+    trans = [k for k in _kernels(sass_by_kernel, "gemm_ws_kernel") if k.endswith("ELb1ELb0EEEv14CUtensorMap_stS1_S1_iiiNS_7GemmEpiEi")]
+    gath = {k: b for k, b in _kernels(sass_by_kernel, "gemm_ws_kernel").items() if "ELb0ELb1EEEv" in k}
+    assert trans and gath
+    assert all(re.search(r"UTMALDG\S*(GATHER4|G4)", b) or "GATHER" in b for b in gath.values()), "no gather4 TMA load in the sparse-conv GEMM"

@@ -54,7 +54,20 @@ def loss_of(S_, delta):
     return (l1 + (1.0 - ssim)) * LOSS_SCALE
 
 
-def step_ours(S_):
+def _allreduce_grads(S_, world):
+    """DDP's gradient averaging (train_vae.py runs under accelerate's DDP): one flat NCCL all-reduce of the fp32 parameter
+    gradients inside the step."""
+    import torch.distributed as dist
+    grads = [p.grad for p in S_["vae"].parameters() if p.grad is not None]
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat)
+    flat.div_(world)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+    return flat.numel() * 4
+
+
+def step_ours(S_, world=1):
     vae, z = S_["vae"], S_["z"]
     z = z.detach().requires_grad_(True)
     q = S_["obj"].static_gs[None].detach().requires_grad_(True)
@@ -68,6 +81,8 @@ def step_ours(S_):
     loss = loss_of(S_, delta)
     e[1].record()
     loss.backward()
+    if world > 1:
+        S_["allreduce_bytes"] = _allreduce_grads(S_, world)
     e[2].record()
     return loss, e, z, q
 
@@ -91,8 +106,8 @@ def step_standin(S_, sd):
     return loss, e, z, q
 
 
-def measure(steps=10, warmup=3, standin=True, seed=0):
-    dev = torch.device("cuda", 0)
+def measure(steps=10, warmup=3, standin=True, seed=0, world=1, device=None):
+    dev = device if device is not None else torch.device("cuda", 0)
     S_ = build(dev, seed)
     vae = S_["vae"]
     vae.train()
@@ -111,14 +126,23 @@ def measure(steps=10, warmup=3, standin=True, seed=0):
         med = lambda v: sorted(v)[len(v) // 2]
         return med(fw), med(bw), loss, z, q
 
-    fw, bw, loss, z, q = run(lambda: step_ours(S_))
+    fw, bw, loss, z, q = run(lambda: step_ours(S_, world))
     T = S_["T"]
+    step_ms = fw + bw
+    if world > 1:                                         # max over ranks, like the headline bench
+        import torch.distributed as dist
+        t = torch.tensor([step_ms, fw, bw], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, fw, bw = (float(v) for v in t.tolist())
     res = {"metric": "train-step frames/s (VAE decode + 24f x 512^2 render, fwd+bwd, 16k Gaussians)",
-           "value": T / ((fw + bw) / 1e3), "unit": "frames/s", "ms_forward": fw, "ms_backward": bw, "loss": float(loss.detach()) / LOSS_SCALE, "loss_scale": LOSS_SCALE,
+           "value": world * T / (step_ms / 1e3), "unit": "frames/s", "ms_per_step": step_ms, "ms_forward": fw, "ms_backward": bw, "loss": float(loss.detach()) / LOSS_SCALE, "loss_scale": LOSS_SCALE,
            "config": {"workload": "BASELINE.json configs[2]: decode (12 layers, dim 768, 24 x 512 latents, 16384 queries) + "
                                   "canonical+delta rasteriser 24 frames + L1 + (1 - SSIM), gradients to all decoder parameters, "
                                   "latent, queries and raw canonical Gaussians"},
            "dtype": "f16 (fp32 accumulate, fp32 parameter gradients)", "data": "synthetic"}
+    if world > 1:
+        res["ddp"] = {"allreduce_bytes_per_step": S_.get("allreduce_bytes"), "where": "inside the backward time",
+                      "objects_per_step": world}
     grads = {n: p.grad.detach().clone() for n, p in vae.named_parameters() if p.grad is not None}
     gz, gq, graw = z.grad.clone(), q.grad.clone(), [t.grad.clone() for t in S_["raw"]]
     if standin:
