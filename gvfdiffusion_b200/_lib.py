@@ -68,6 +68,9 @@ _SIGS = {
                                         C.c_int, _P, _P, _P, _P, C.c_int, C.c_float, _P, C.c_int, _P]),
     "gvf_sparse_window_attn_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "gvf_sparse_varlen_attn_f16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "gvf_sparse_varlen_attn_lse_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "gvf_sparse_varlen_attn_bwd_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_longlong, C.c_int,
+                                                 C.c_int, C.c_float, _P]),
     "gvf_attn_set_debug": (None, [C.c_int]),
     "gvf_attn_set_workspace": (None, [_P, C.c_size_t]),
     "gvf_attn_set_trace": (None, [_P]),

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
                                                                 const int* __restrict__ fwd_idx,
                                                                 const int* __restrict__ out_idx,
                                                                 const int* __restrict__ cu_seqlens, int H,
-                                                                float scale_log2e) {
+                                                                float scale_log2e, float* __restrict__ lse2) {
   __shared__ __align__(128) uint8_t sm[(1 + 4) * 64 * 128];     // Q | K0 V0 | K1 V1   (40 KB)
   const int w = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQB;
   const int beg = __ldg(cu_seqlens + w), len = __ldg(cu_seqlens + w + 1) - beg;
@@ -176,6 +176,17 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
     lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
   }
   const float inv[2] = {1.0f / lrow[0], 1.0f / lrow[1]};
+  if (lse2 && tg == 0) {                           // training: LSE2[row, h] = log2 sum_k exp(scale s) for the backward kernels
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = q0 + 16 * warp + g + 8 * r;
+      if (row < len) {
+        const int pos = beg + row;
+        const long long grow = out_idx ? (long long)__ldg(out_idx + pos) : (idx ? (long long)__ldg(idx + pos) : (long long)pos);
+        if (grow >= 0) lse2[grow * H + h] = mrow[r] + log2f(lrow[r]);
+      }
+    }
+  }
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -216,7 +227,7 @@ extern "C" GVF_API int gvf_sparse_window_attn_f16(const void* qkv, void* out, co
   if (num_windows > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_windows);
   gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, fwd_idx, nullptr, cu_seqlens, H, scale * 1.4426950408889634f);
+      (const __half*)qkv, (__half*)out, fwd_idx, nullptr, cu_seqlens, H, scale * 1.4426950408889634f, nullptr);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -236,6 +247,21 @@ extern "C" GVF_API int gvf_sparse_varlen_attn_f16(const void* qkv, void* out, co
   if (num_seqs > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_seqs);
   gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, H, scale * 1.4426950408889634f);
+      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, H, scale * 1.4426950408889634f, nullptr);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+// Training forward: as above, plus LSE2 [T, H] fp32 (per voxel row) for gvf_sparse_varlen_attn_bwd_f16.
+extern "C" GVF_API int gvf_sparse_varlen_attn_lse_f16(const void* qkv, void* out, float* lse2, const int* gather_idx,
+                                                      const int* scatter_idx, const int* cu_seqlens, int num_seqs,
+                                                      int max_seqlen, int H, int D, float scale, void* stream) {
+  if (!qkv || !out || !lse2 || !cu_seqlens || num_seqs < 0 || H <= 0 || max_seqlen < 0) return GVF_ERR_INVALID;
+  if (D != gvf::kD) return GVF_ERR_UNSUPPORTED;
+  if (((uintptr_t)qkv | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
+  if (num_seqs == 0 || max_seqlen == 0) return GVF_OK;
+  if (num_seqs > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
+  const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_seqs);
+  gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, H, scale * 1.4426950408889634f, lse2);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }

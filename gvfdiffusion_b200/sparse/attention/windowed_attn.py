@@ -76,3 +76,40 @@ def sparse_windowed_scaled_dot_product_self_attention(qkv_feats, coords, window_
                                                1.0 / math.sqrt(C), current_stream())
     check(st, "gvf_sparse_window_attn_f16")
     return out
+
+
+class _WindowedAttnFn(torch.autograd.Function):
+    """Windowed attention under autograd (training step of the static VAE): forward that also leaves
+    LSE2, backward on csrc/sparse_attn_bwd.cu."""
+
+    @staticmethod
+    def forward(ctx, qkv_feats, coords, window_size, shift_window):
+        T, _, H, C = qkv_feats.shape
+        fwd, _bwd, cu, max_len = _partition(coords, window_size, shift_window)
+        q = qkv_feats.detach().contiguous()
+        out = torch.empty((T, H, C), dtype=torch.float16, device=q.device)
+        lse = torch.empty((T, H), dtype=torch.float32, device=q.device)
+        check(_lib.lib().gvf_sparse_varlen_attn_lse_f16(ptr(q), ptr(out), ptr(lse), ptr(fwd), None, ptr(cu), cu.shape[0] - 1,
+                                                        max_len, H, C, 1.0 / math.sqrt(C), current_stream()),
+              "gvf_sparse_varlen_attn_lse_f16")
+        ctx.save_for_backward(q, out, lse, fwd, cu)
+        ctx.max_len = max_len
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, out, lse, fwd, cu = ctx.saved_tensors
+        T, _, H, C = q.shape
+        dout = dout.to(torch.float16).contiguous()
+        dqkv = torch.zeros_like(q)                       # rows outside every window (none for a partition) stay zero
+        dsum = torch.empty_like(lse)
+        check(_lib.lib().gvf_sparse_varlen_attn_bwd_f16(ptr(q), ptr(out), ptr(dout), ptr(lse), ptr(dsum), ptr(dqkv), ptr(fwd),
+                                                        ptr(cu), cu.shape[0] - 1, ctx.max_len, T, H, C, 1.0 / math.sqrt(C),
+                                                        current_stream()), "gvf_sparse_varlen_attn_bwd_f16")
+        return dqkv, None, None, None
+
+
+def sparse_windowed_attention_autograd(qkv_feats, coords, window_size, shift_window=(0, 0, 0)):
+    """Differentiable form of `sparse_windowed_scaled_dot_product_self_attention` (gradient with respect to qkv_feats)."""
+    shift = tuple(shift_window) if not isinstance(shift_window, int) else (shift_window,) * (coords.shape[1] - 1)
+    return _WindowedAttnFn.apply(qkv_feats, coords, window_size, shift)

@@ -354,6 +354,17 @@ GVF_API int gvf_sparse_varlen_attn_f16(const void* qkv, void* out, const int* ga
                                        const int* cu_seqlens, int num_seqs, int max_seqlen, int H, int D, float scale,
                                        void* stream);
 
+/* Training forward of the kernel above (also leaves LSE2 [T, H] fp32 per voxel row) and its backward for bijective lists
+ * (windowed / full attention; the padded windows of serialized attention are forward-only): o [T, H, 64] the forward
+ * output, dout its gradient, dsum [T, H] scratch, dqkv [T, 3, H, 64] receives dq | dk | dv in voxel order.  Replaces the
+ * backward of flash_attn_varlen_qkvpacked_func (sparse/attention/windowed_attn.py:125-127 under autograd, cfg 5). */
+GVF_API int gvf_sparse_varlen_attn_lse_f16(const void* qkv, void* out, float* lse2, const int* gather_idx,
+                                           const int* scatter_idx, const int* cu_seqlens, int num_seqs, int max_seqlen, int H,
+                                           int D, float scale, void* stream);
+GVF_API int gvf_sparse_varlen_attn_bwd_f16(const void* qkv, const void* o, const void* dout, const float* lse2, float* dsum,
+                                           void* dqkv, const int* gather_idx, const int* cu_seqlens, int num_seqs,
+                                           int max_seqlen, long long T, int H, int D, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * 7. Training-step losses (BASELINE configs[4]).
  *    gvf_ssim_l1_*: nn.L1Loss + utils/loss_util.py:33-63 `ssim` as used at train_vae.py:328-330
