@@ -54,6 +54,10 @@ _SIGS = {
     "gvf_colsum": (C.c_int, [_P, C.c_int, C.c_longlong, C.c_int, C.c_longlong, _P, C.c_size_t, _P, C.c_int, _P]),
     "gvf_ln_bwd_f16": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
     "gvf_geglu_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P, _P]),
+    "gvf_gelu_tanh_f16": (C.c_int, [_P, C.c_longlong, _P, _P]),
+    "gvf_gelu_tanh_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),
+    "gvf_to_representation_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_float), C.c_float, C.c_int,
+                                            C.c_float, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_small_linear_bwd_input": (C.c_int, [_P, C.c_int, C.c_longlong, _P, C.c_longlong, C.c_int, C.c_int, _P, C.c_int, _P]),
     "gvf_skinny_outer": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_longlong, C.c_longlong, C.c_int, _P, C.c_size_t,
                                    _P, C.c_int, _P]),

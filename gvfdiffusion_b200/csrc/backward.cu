@@ -155,6 +155,49 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __half* __restrict
   *reinterpret_cast<uint4*>(dh + row * 2 * F + F + c) = *reinterpret_cast<uint4*>(og);
 }
 
+// ------------------------------------------------------------------------------------------------ GELU (tanh)
+// The sparse trunk's MLP (sparse_transformer.py: nn.GELU(approximate="tanh")).  Inference fuses it into the fc1 epilogue;
+// the training forward keeps the pre-activation and applies the same tanh.approx form here.
+__device__ __forceinline__ float bw_tanh(float u) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return t;
+}
+__global__ void __launch_bounds__(256) gelu_tanh_kernel(const __half* __restrict__ h, long long n8, __half* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = reinterpret_cast<const uint4*>(h)[i];
+  const __half* hv = reinterpret_cast<const __half*>(&v);
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x = __half2float(hv[j]);
+    const float u = x * fmaf(0.7978845608028654f * 0.044715f, x * x, 0.7978845608028654f);
+    const float hx = 0.5f * x;
+    o[j] = __float2half_rn(fmaf(hx, bw_tanh(u), hx));
+  }
+  reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<uint4*>(o);
+}
+// d/dx [0.5 x (1 + tanh u)], u = k0 (x + k1 x^3):  0.5 (1 + t) + 0.5 x (1 - t^2) k0 (1 + 3 k1 x^2)
+__global__ void __launch_bounds__(256) gelu_tanh_bwd_kernel(const __half* __restrict__ h, const __half* __restrict__ dy,
+                                                            long long n8, __half* __restrict__ dh) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = reinterpret_cast<const uint4*>(h)[i], g = reinterpret_cast<const uint4*>(dy)[i];
+  const __half* hv = reinterpret_cast<const __half*>(&v);
+  const __half* gv = reinterpret_cast<const __half*>(&g);
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x = __half2float(hv[j]);
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float t = bw_tanh(k0 * (x + k1 * x * x * x));
+    const float d = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
+    o[j] = __float2half_rn(__half2float(gv[j]) * d);
+  }
+  reinterpret_cast<uint4*>(dh)[i] = *reinterpret_cast<uint4*>(o);
+}
+
 // ------------------------------------------------------------------------------------------------ K <= 32 Linears
 // dx[m, k] = sum_n dy[m, n] W[n, k]   (y = x W^T + b with K <= 32 inputs).  Warp per row; W fp16 [N, K].
 template <typename TDy>
@@ -494,6 +537,18 @@ GVF_API int gvf_geglu_bwd_f16(const void* h, const void* dG, long long M, int F,
   const long long n8 = M * (F / 8);
   geglu_bwd_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)h, (const __half*)dG, M, F,
                                                                         (__half*)dh);
+  RET();
+}
+
+GVF_API int gvf_gelu_tanh_f16(const void* h, long long n, void* out, void* stream) {
+  if (!h || !out || n <= 0 || (n % 8)) return GVF_ERR_INVALID;
+  gelu_tanh_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)h, n / 8, (__half*)out);
+  RET();
+}
+GVF_API int gvf_gelu_tanh_bwd_f16(const void* h, const void* dy, long long n, void* dh, void* stream) {
+  if (!h || !dy || !dh || n <= 0 || (n % 8)) return GVF_ERR_INVALID;
+  gelu_tanh_bwd_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)h, (const __half*)dy, n / 8,
+                                                                              (__half*)dh);
   RET();
 }
 

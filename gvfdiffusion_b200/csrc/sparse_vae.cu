@@ -58,6 +58,38 @@ __global__ void __launch_bounds__(256) to_representation_kernel(
   opacity[p] = __fmul_rn(fo[0], lr_opacity);
 }
 
+// backward of the above: gradients of the raw GaussianModel tensors -> gradient of the feature rows [nvox, ldf]
+// (columns >= 14 G are zeroed).  d offset / d feat = lr_xyz (1 - tanh^2) * {1, 1/res, 0.5 soft_scale / res}.
+__global__ void __launch_bounds__(256) to_representation_bwd_kernel(
+    const float* __restrict__ feats, int ldf, int nvox, int G, const float* __restrict__ perturb, float lr_xyz,
+    float lr_dc, float lr_scaling, float lr_rotation, float lr_opacity, float resolution, int reg_mode, float soft_scale,
+    const float* __restrict__ g_xyz, const float* __restrict__ g_dc, const float* __restrict__ g_scaling,
+    const float* __restrict__ g_rotation, const float* __restrict__ g_opacity, float* __restrict__ g_feats) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)nvox * G) return;
+  const int v = (int)(p / G), g = (int)(p % G);
+  const float* row = feats + (size_t)v * ldf;
+  float* out = g_feats + (size_t)v * ldf;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float off = row[3 * g + a] * lr_xyz;
+    if (perturb) off += perturb[3 * g + a];
+    float d = lr_xyz;
+    if (reg_mode != 0) {
+      const float t = tanhf(off);
+      d *= (1.0f - t * t) / resolution * (reg_mode == 2 ? 0.5f * soft_scale : 1.0f);
+    }
+    out[3 * g + a] = g_xyz ? g_xyz[p * 3 + a] * d : 0.f;
+    out[3 * G + 3 * g + a] = g_dc ? g_dc[p * 3 + a] * lr_dc : 0.f;
+    out[6 * G + 3 * g + a] = g_scaling ? g_scaling[p * 3 + a] * lr_scaling : 0.f;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) out[9 * G + 4 * g + a] = g_rotation ? g_rotation[p * 4 + a] * lr_rotation : 0.f;
+  out[13 * G + g] = g_opacity ? g_opacity[p] * lr_opacity : 0.f;
+  if (g == 0)
+    for (int c = 14 * G; c < ldf; ++c) out[c] = 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------
 // submanifold convolution: neighbour map
 __global__ void __launch_bounds__(256) voxel_grid_fill_kernel(const int* __restrict__ coords, int n, int B, int D,
@@ -142,6 +174,19 @@ GVF_API int gvf_to_representation(const float* feats, int ldf, const int* coords
   to_representation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(
       feats, ldf, coords, nvox, G, perturbation, lr[0], lr[1], lr[2], lr[3], lr[4], resolution, reg_mode, voxel_size,
       xyz, features_dc, scaling, rotation, opacity);
+  RET();
+}
+
+GVF_API int gvf_to_representation_bwd(const float* feats, int ldf, int nvox, int G, const float* perturbation,
+                                      const float* lr /* host */, float resolution, int reg_mode, float voxel_size,
+                                      const float* g_xyz, const float* g_dc, const float* g_scaling, const float* g_rotation,
+                                      const float* g_opacity, float* g_feats, void* stream) {
+  if (!feats || !lr || !g_feats || nvox <= 0 || G <= 0 || ldf < 14 * G || resolution <= 0.0f || reg_mode < 0 || reg_mode > 2)
+    return GVF_ERR_INVALID;
+  const long long n = (long long)nvox * G;
+  to_representation_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(
+      feats, ldf, nvox, G, perturbation, lr[0], lr[1], lr[2], lr[3], lr[4], resolution, reg_mode, voxel_size, g_xyz, g_dc,
+      g_scaling, g_rotation, g_opacity, g_feats);
   RET();
 }
 

@@ -36,6 +36,26 @@ def hammersley_sequence(dim, n, num_samples):
     return [n / num_samples] + [_radical_inverse(_PRIMES[d], n) for d in range(dim - 1)]
 
 
+class _ToRepresentationFn(torch.autograd.Function):
+    """to_representation under autograd (training_losses, reference sparse_vae.py:303-362, backpropagates the render loss
+    through it into the decoder trunk): forward gvf_to_representation, backward gvf_to_representation_bwd."""
+
+    @staticmethod
+    def forward(ctx, feats, coords, G, lr, resolution, reg_mode, voxel_size, perturbation):
+        f = feats.detach()
+        ctx.save_for_backward(f, perturbation)
+        ctx.cfg = (G, lr, resolution, reg_mode, voxel_size)
+        return ops.to_representation(f, coords, G, lr, resolution, reg_mode, voxel_size, perturbation)
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_dc, g_scaling, g_rotation, g_opacity):
+        f, perturbation = ctx.saved_tensors
+        G, lr, resolution, reg_mode, voxel_size = ctx.cfg
+        d = ops.to_representation_bwd(f, G, lr, resolution, reg_mode, voxel_size, perturbation, g_xyz, g_dc, g_scaling,
+                                      g_rotation, g_opacity)
+        return d, None, None, None, None, None, None, None
+
+
 class SparseVAE:
     def __init__(self, backbones=None, resolution=64, representation_config=None, device="cuda"):
         self.backbones = backbones or {}
@@ -83,8 +103,8 @@ class SparseVAE:
             lo = self.layouts[k]["_xyz"]["range"][0]
             # the GS branch hard-codes 1.25 where MipGS uses its voxel_size (:153 / :175)
             vs = 1.25 if k == "GS" else cfg["voxel_size"]
-            raw = ops.to_representation(feats[:, lo:lo + 14 * G], coords, G, [cfg["lr"][n] for n in _ORDER], self.resolution,
-                                        _REG[cfg["reg_mode"]], vs, self.perturbation.get(k))
+            raw = _ToRepresentationFn.apply(feats[:, lo:lo + 14 * G], coords, G, tuple(cfg["lr"][n] for n in _ORDER),
+                                            self.resolution, _REG[cfg["reg_mode"]], vs, self.perturbation.get(k))
             ret[k] = []
             for i in range(x.shape[0]):
                 sl = x.layout[i]

@@ -317,6 +317,28 @@ def to_representation(feats, coords, num_gaussians, lr, resolution, reg_mode=0, 
     return xyz, dc, sc, rot, op
 
 
+def to_representation_bwd(feats, num_gaussians, lr, resolution, reg_mode=0, voxel_size=1.0, perturbation=None,
+                          g_xyz=None, g_dc=None, g_scaling=None, g_rotation=None, g_opacity=None):
+    """Backward of `to_representation`: gradients of the raw GaussianModel tensors (fp32, any may be None) -> d feats
+    fp32 [Nvox, feats.shape[1]]."""
+    _req(feats, F32, "feats")
+    feats = feats.contiguous()                           # one row stride for feats and d feats
+    nvox, G = feats.shape[0], int(num_gaussians)
+    P = nvox * G
+    gs = []
+    for t, w in ((g_xyz, 3), (g_dc, 3), (g_scaling, 3), (g_rotation, 4), (g_opacity, 1)):
+        if t is not None:
+            t = t.to(F32).contiguous()
+            assert t.is_cuda and t.numel() == P * w
+        gs.append(t)
+    out = torch.empty((nvox, feats.shape[1]), dtype=F32, device=feats.device)
+    lr5 = (C.c_float * 5)(*[float(v) for v in lr])
+    check(_lib.lib().gvf_to_representation_bwd(ptr(feats), feats.stride(0), nvox, G, ptr(perturbation), lr5, float(resolution),
+                                               int(reg_mode), float(voxel_size), *[ptr(t) for t in gs], ptr(out),
+                                               current_stream()), "gvf_to_representation_bwd")
+    return out
+
+
 def sparse_neighbor_map(coords, batch_size, grid_size, ksize=3, dilation=1, workspace=None, status=None):
     """coords int32 [N,4] (batch, x, y, z) -> nbr int32 [N, ksize^3] (-1 = no voxel there)."""
     _req(coords, torch.int32, "coords")
@@ -440,6 +462,26 @@ def geglu_bwd(h, dG, out=None):
     if out is None:
         out = torch.empty_like(h)
     check(_lib.lib().gvf_geglu_bwd_f16(ptr(h), ptr(dG), M, F2 // 2, ptr(out), current_stream()), "gvf_geglu_bwd_f16")
+    return out
+
+
+def gelu_tanh(h, out=None):
+    """GELU(approximate="tanh") of an fp16 pre-activation (training forward of the sparse trunk's MLP)."""
+    _req(h, F16, "h")
+    assert h.is_contiguous()
+    if out is None:
+        out = torch.empty_like(h)
+    check(_lib.lib().gvf_gelu_tanh_f16(ptr(h), h.numel(), ptr(out), current_stream()), "gvf_gelu_tanh_f16")
+    return out
+
+
+def gelu_tanh_bwd(h, dy, out=None):
+    _req(h, F16, "h")
+    _req(dy, F16, "dy")
+    assert h.is_contiguous() and dy.is_contiguous() and dy.shape == h.shape
+    if out is None:
+        out = torch.empty_like(h)
+    check(_lib.lib().gvf_gelu_tanh_bwd_f16(ptr(h), ptr(dy), h.numel(), ptr(out), current_stream()), "gvf_gelu_tanh_bwd_f16")
     return out
 
 

@@ -78,20 +78,42 @@ def sparse_windowed_scaled_dot_product_self_attention(qkv_feats, coords, window_
     return out
 
 
+def windowed_attention_fwd_lse(qkv_feats, coords, window_size, shift_window):
+    """Forward that also leaves LSE2 [T, H] (log2-domain log-sum-exp of the scaled scores) for the backward.
+    -> (out [T, H, C] fp16, lse2, partition = (fwd_indices, cu_seqlens, max_len))."""
+    T, _, H, C = qkv_feats.shape
+    fwd, _bwd, cu, max_len = _partition(coords, window_size, shift_window)
+    q = qkv_feats.contiguous()
+    out = torch.empty((T, H, C), dtype=torch.float16, device=q.device)
+    lse = torch.empty((T, H), dtype=torch.float32, device=q.device)
+    check(_lib.lib().gvf_sparse_varlen_attn_lse_f16(ptr(q), ptr(out), ptr(lse), ptr(fwd), None, ptr(cu), cu.shape[0] - 1,
+                                                    max_len, H, C, 1.0 / math.sqrt(C), current_stream()),
+          "gvf_sparse_varlen_attn_lse_f16")
+    return out, lse, (fwd, cu, max_len)
+
+
+def windowed_attention_bwd(qkv_feats, out, dout, lse, partition, dqkv=None):
+    """dqkv [T, 3, H, C] fp16 of the windowed attention (csrc/sparse_attn_bwd.cu, window gather fused)."""
+    fwd, cu, max_len = partition
+    T, _, H, C = qkv_feats.shape
+    dout = dout.to(torch.float16).contiguous()
+    if dqkv is None:
+        dqkv = torch.zeros_like(qkv_feats)               # rows outside every window (none for a partition) stay zero
+    dsum = torch.empty_like(lse)
+    check(_lib.lib().gvf_sparse_varlen_attn_bwd_f16(ptr(qkv_feats), ptr(out), ptr(dout), ptr(lse), ptr(dsum), ptr(dqkv), ptr(fwd),
+                                                    ptr(cu), cu.shape[0] - 1, max_len, T, H, C, 1.0 / math.sqrt(C),
+                                                    current_stream()), "gvf_sparse_varlen_attn_bwd_f16")
+    return dqkv
+
+
 class _WindowedAttnFn(torch.autograd.Function):
     """Windowed attention under autograd (training step of the static VAE): forward that also leaves
     LSE2, backward on csrc/sparse_attn_bwd.cu."""
 
     @staticmethod
     def forward(ctx, qkv_feats, coords, window_size, shift_window):
-        T, _, H, C = qkv_feats.shape
-        fwd, _bwd, cu, max_len = _partition(coords, window_size, shift_window)
         q = qkv_feats.detach().contiguous()
-        out = torch.empty((T, H, C), dtype=torch.float16, device=q.device)
-        lse = torch.empty((T, H), dtype=torch.float32, device=q.device)
-        check(_lib.lib().gvf_sparse_varlen_attn_lse_f16(ptr(q), ptr(out), ptr(lse), ptr(fwd), None, ptr(cu), cu.shape[0] - 1,
-                                                        max_len, H, C, 1.0 / math.sqrt(C), current_stream()),
-              "gvf_sparse_varlen_attn_lse_f16")
+        out, lse, (fwd, cu, max_len) = windowed_attention_fwd_lse(q, coords, window_size, shift_window)
         ctx.save_for_backward(q, out, lse, fwd, cu)
         ctx.max_len = max_len
         return out
@@ -99,14 +121,7 @@ class _WindowedAttnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, out, lse, fwd, cu = ctx.saved_tensors
-        T, _, H, C = q.shape
-        dout = dout.to(torch.float16).contiguous()
-        dqkv = torch.zeros_like(q)                       # rows outside every window (none for a partition) stay zero
-        dsum = torch.empty_like(lse)
-        check(_lib.lib().gvf_sparse_varlen_attn_bwd_f16(ptr(q), ptr(out), ptr(dout), ptr(lse), ptr(dsum), ptr(dqkv), ptr(fwd),
-                                                        ptr(cu), cu.shape[0] - 1, ctx.max_len, T, H, C, 1.0 / math.sqrt(C),
-                                                        current_stream()), "gvf_sparse_varlen_attn_bwd_f16")
-        return dqkv, None, None, None
+        return windowed_attention_bwd(q, out, dout, lse, (fwd, cu, ctx.max_len)), None, None, None
 
 
 def sparse_windowed_attention_autograd(qkv_feats, coords, window_size, shift_window=(0, 0, 0)):

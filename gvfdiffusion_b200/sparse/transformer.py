@@ -12,6 +12,7 @@ import torch
 
 from .. import ops
 from .attention import sparse_windowed_scaled_dot_product_self_attention
+from .attention.windowed_attn import windowed_attention_bwd, windowed_attention_fwd_lse
 
 F16, F32 = torch.float16, torch.float32
 
@@ -32,7 +33,10 @@ class SparseTransformerBlocks:
                  use_old_attn_impl=False):
         """fp16_residual: the residual stream is fp16 (`h.type(self.dtype)` with use_fp16=True,
         sparse_transformer_vae.py:155,181) instead of fp32.  use_old_attn_impl: see qkv_rows_from_old_attn_impl."""
+        self.prefix, self.qkv_perm = prefix, None
         if use_old_attn_impl:
+            c3 = state_dict[f"{prefix}0.attn.to_qkv.weight"].shape[0]
+            self.qkv_perm = torch.arange(c3).reshape(num_heads, 3, c3 // (3 * num_heads)).permute(1, 0, 2).reshape(-1)
             state_dict = dict(state_dict)
             for i in range(num_blocks):
                 kw, kb = f"{prefix}{i}.attn.to_qkv.weight", f"{prefix}{i}.attn.to_qkv.bias"
@@ -76,6 +80,76 @@ class SparseTransformerBlocks:
             ops.gemm(H1, blk["w2"], blk["b2"], epi, out=X)
         return X
 
+    # ---------------------------------------------------------------------------------------- training (cfg 5)
+    def forward_train(self, feats, coords):
+        """Same blocks, keeping what the backward needs (block inputs, LayerNorm outputs, QKV, attention output + LSE,
+        the MLP pre-activation).  The MLP runs fc1 -> fp16 -> GELU as two launches (autocast's order: the Linear result
+        is rounded to fp16 before the activation), the inference path fuses GELU into the fc1 epilogue.
+        -> (X [T, C], saved)"""
+        if not (feats.is_cuda and coords.is_cuda):
+            raise ValueError("SparseTransformerBlocks runs on CUDA tensors only (no CPU fallback)")
+        T, C, H = feats.shape[0], self.C, self.H
+        X = feats.detach().to(F16 if self.fp16_residual else F32).contiguous()
+        epi = ops.EPI_RESID_F16 if self.fp16_residual else ops.EPI_RESID_F32
+        coords = coords.int().contiguous()
+        saved = {"coords": coords, "blocks": []}
+        for i, blk in enumerate(self.blocks):
+            shift = (self.window // 2 * (i % 2),) * 3
+            A = ops.ln_mod(X)
+            QKV = ops.gemm(A, blk["w_qkv"], blk["b_qkv"], ops.EPI_F16)
+            AO, lse, part = windowed_attention_fwd_lse(QKV.view(T, 3, H, 64), coords, self.window, shift)
+            x1 = X.clone()
+            ops.gemm(AO.view(T, C), blk["w_out"], blk["b_out"], epi, out=x1)
+            A2 = ops.ln_mod(x1)
+            H0 = ops.gemm(A2, blk["w1"], blk["b1"], ops.EPI_F16)
+            Hg = ops.gelu_tanh(H0)
+            x2 = x1.clone()
+            ops.gemm(Hg, blk["w2"], blk["b2"], epi, out=x2)
+            saved["blocks"].append(dict(x0=X, A=A, QKV=QKV, AO=AO, lse=lse, part=part, x1=x1, A2=A2, H0=H0, Hg=Hg))
+            X = x2
+        return X, saved
+
+    def _transposed(self):
+        if "w_qkv_t" not in self.blocks[0]:
+            for blk in self.blocks:
+                for n in ("w_qkv", "w_out", "w1", "w2"):
+                    blk[n + "_t"] = ops.transpose(blk[n])
+        return self.blocks
+
+    def backward(self, saved, dX):
+        """dX [T, C] (gradient of forward_train's output) -> ({reference parameter name: fp32 gradient}, d feats fp16).
+        Per block, in reverse: fc2 dgrad / wgrad -> GELU' -> fc1 dgrad / wgrad -> LayerNorm backward (+ residual) ->
+        to_out dgrad / wgrad -> window attention backward -> to_qkv dgrad / wgrad -> LayerNorm backward (+ residual).
+        Activation gradients are fp16 (fp32 accumulation inside every kernel), parameter gradients fp32."""
+        T, C, H = dX.shape[0], self.C, self.H
+        dx = dX.detach().to(F16).contiguous()
+        g = {}
+        blocks = self._transposed()
+        for i in reversed(range(len(blocks))):
+            blk, s = blocks[i], saved["blocks"][i]
+            p = f"{self.prefix}{i}."
+            dHg = ops.gemm(dx, blk["w2_t"], None, ops.EPI_F16)
+            g[p + "mlp.mlp.2.weight"] = ops.gemm_tn(dx, s["Hg"])
+            g[p + "mlp.mlp.2.bias"] = ops.colsum(dx)
+            dH0 = ops.gelu_tanh_bwd(s["H0"], dHg)
+            dA2 = ops.gemm(dH0, blk["w1_t"], None, ops.EPI_F16)
+            g[p + "mlp.mlp.0.weight"] = ops.gemm_tn(dH0, s["A2"])
+            g[p + "mlp.mlp.0.bias"] = ops.colsum(dH0)
+            dx1 = ops.ln_bwd(s["x1"], dA2, dx)
+            dAO = ops.gemm(dx1, blk["w_out_t"], None, ops.EPI_F16)
+            g[p + "attn.to_out.weight"] = ops.gemm_tn(dx1, s["AO"].view(T, C))
+            g[p + "attn.to_out.bias"] = ops.colsum(dx1)
+            dQKV = windowed_attention_bwd(s["QKV"].view(T, 3, H, 64), s["AO"], dAO.view(T, H, 64), s["lse"], s["part"]).view(T, 3 * C)
+            dA = ops.gemm(dQKV, blk["w_qkv_t"], None, ops.EPI_F16)
+            gw, gb = ops.gemm_tn(dQKV, s["A"]), ops.colsum(dQKV)
+            if self.qkv_perm is not None:                 # rows were permuted at load time: hand the gradient back in
+                inv = torch.empty_like(self.qkv_perm)     # the checkpoint's [H][3][d] order
+                inv[self.qkv_perm] = torch.arange(inv.numel())
+                gw, gb = gw[inv.to(gw.device)], gb[inv.to(gb.device)]
+            g[p + "attn.to_qkv.weight"], g[p + "attn.to_qkv.bias"] = gw, gb
+            dx = ops.ln_bwd(s["x0"], dA, dx1)
+        return g, dx
+
 
 class SparseTransformerVAE:
     """encode / decode trunks of the static SparseTransformerVAE (reference
@@ -116,6 +190,48 @@ class SparseTransformerVAE:
         if self.norm_output:
             hcur = ops.ln_mod(hcur.contiguous(), eps=1e-5).float()
         return self._linear(last, hcur)
+
+    # ---------------------------------------------------------------------------------------- training (cfg 5)
+    def _trunk_train(self, blocks, first, feats, coords):
+        coords = coords.int().contiguous()
+        feats = feats.detach().to(self.dev, F32).contiguous()
+        pos = ops.ape(coords[:, 1:].float().contiguous(), self.C)
+        w, bias = self.lin[first]
+        if w.shape[1] > 32:
+            raise NotImplementedError("training path of the first Linear is built for <= 32 input channels (from_latent)")
+        h0 = ops.small_linear(feats, w, bias, out_f16=False, add=pos, add_rows=feats.shape[0])
+        X, saved = blocks.forward_train(h0, coords)
+        saved["first_in"] = feats
+        return X, saved
+
+    def decode_train(self, latent_feats, coords):
+        """decode keeping the activations: -> (out [T, out_channels] fp32, saved)."""
+        X, saved = self._trunk_train(self.decoder, "from_latent", latent_feats, coords)
+        saved["x_last"] = X
+        hn = ops.ln_mod(X, eps=1e-5) if self.norm_output else (X if X.dtype == F16 else ops.cast_f16(X))
+        saved["hn"] = hn
+        w, bias = self.lin["out_layer"]
+        return ops.gemm(hn, w, bias, ops.EPI_F16).float(), saved
+
+    def decode_backward(self, saved, dout):
+        """dout [T, out_channels] -> ({parameter name: fp32 gradient}, d latent fp32 [T, latent_channels])."""
+        w, _ = self.lin["out_layer"]
+        N, T = w.shape[0], dout.shape[0]
+        N8 = (N + 7) // 8 * 8
+        d16 = torch.zeros((T, N8), dtype=F16, device=self.dev)
+        d16[:, :N] = dout.detach()
+        if "out_layer_t" not in self.lin:
+            self.lin["out_layer_t"] = ops.transpose(w)                        # [C, N8]
+        g = {"out_layer.weight": ops.gemm_tn(d16, saved["hn"])[:N], "out_layer.bias": ops.colsum(d16)[:N]}
+        dh = ops.gemm(d16, self.lin["out_layer_t"], None, ops.EPI_F16)
+        if self.norm_output:
+            dh = ops.ln_bwd(saved["x_last"], dh, None, eps=1e-5)
+        gb, dx = self.decoder.backward(saved, dh)
+        g.update(gb)
+        wf, _ = self.lin["from_latent"]
+        g["from_latent.weight"] = ops.skinny_outer(saved["first_in"], dx).t().contiguous()
+        g["from_latent.bias"] = ops.colsum(dx)
+        return g, ops.small_linear_bwd_input(dx, wf)
 
     def decode(self, latent_feats, coords):
         """latent [T, latent_channels] fp32, coords [T, 4] int32 -> [T, out_channels] fp32 (:178-188)."""

@@ -421,6 +421,11 @@ GVF_API int gvf_to_representation(const float* feats, int ldf, const int* coords
                                   const float* perturbation, const float* lr /* host */, float resolution,
                                   int reg_mode, float voxel_size, float* xyz, float* features_dc, float* scaling,
                                   float* rotation, float* opacity, void* stream);
+/* Backward of gvf_to_representation: gradients of the raw GaussianModel tensors (any may be NULL) -> g_feats [nvox, ldf]. */
+GVF_API int gvf_to_representation_bwd(const float* feats, int ldf, int nvox, int G, const float* perturbation,
+                                      const float* lr /* host */, float resolution, int reg_mode, float voxel_size,
+                                      const float* g_xyz, const float* g_dc, const float* g_scaling, const float* g_rotation,
+                                      const float* g_opacity, float* g_feats, void* stream);
 GVF_API size_t gvf_sparse_conv_workspace_bytes(int B, int D);
 GVF_API int gvf_sparse_neighbor_map(const int* coords, int N, int B, int D, int ksize, int dilation, void* workspace,
                                     size_t workspace_bytes, int* nbr, int* status, void* stream);
@@ -472,6 +477,9 @@ GVF_API int gvf_ln_bwd_f16(const void* x, int x_is_f16, const void* dy, const vo
                            void* stream);
 /* GEGLU backward (model/autoencoder.py:90-93): h [M, 2F], dG [M, F] -> dh [M, 2F] (all fp16). */
 GVF_API int gvf_geglu_bwd_f16(const void* h, const void* dG, long long M, int F, void* dh, void* stream);
+/* GELU(tanh) of the sparse trunk's MLP as its own pass (training keeps the pre-activation) and its backward; n % 8 == 0. */
+GVF_API int gvf_gelu_tanh_f16(const void* h, long long n, void* out, void* stream);
+GVF_API int gvf_gelu_tanh_bwd_f16(const void* h, const void* dy, long long n, void* dh, void* stream);
 /* Backward of gvf_small_linear with respect to its input: dx[M, K] = dy[M, N] W[N, K] (fp32 out, K <= 32). */
 GVF_API int gvf_small_linear_bwd_input(const void* dy, int dy_is_f16, long long ld, const void* W, long long M, int N, int K,
                                        float* dx, int ldx, void* stream);

@@ -139,3 +139,53 @@ def test_windowed_attention_backward_matches_autograd(n_vox, res, window, shift)
     e_o, e_g = rel(out, ref), [rel(qkv.grad[:, i], qf.grad[:, i]) for i in range(3)]
     print(f"windowed attn bwd T={T} windows={len(seq_lens)} max={int(seq_lens.max())}: out {e_o:.2e} dq {e_g[0]:.2e} dk {e_g[1]:.2e} dv {e_g[2]:.2e}")
     assert e_o < 2e-3 and max(e_g) < 5e-3, (e_o, e_g)
+
+
+@pytest.mark.parametrize("use_fp16,norm_output,old_impl", [(True, True, False), (False, False, False), (True, False, True)])
+def test_sparse_vae_decode_backward_matches_autograd(use_fp16, norm_output, old_impl):
+    """SparseTransformerVAE.decode_train / decode_backward (from_latent + APE -> swin blocks -> LayerNorm -> out_layer, all
+    gradients on the library's kernels) against torch autograd of the oracle restatement in its fp16-emulating regime, at
+    the shipped widths (768 channels, 12 heads, window 8, out 112), 2 blocks.  fp16 activation gradients: 1e-2 rel. L2."""
+    from gvfdiffusion_b200 import ops
+    from gvfdiffusion_b200.sparse.transformer import SparseTransformerVAE
+    from oracle import sparse_window as OSW
+    g = torch.Generator().manual_seed(35)
+    C, H, NB = 768, 12, 2
+    sd = {"from_latent.weight": torch.randn(C, 8, generator=g) * 0.3, "from_latent.bias": torch.randn(C, generator=g) * 0.1,
+          "out_layer.weight": torch.randn(112, C, generator=g) * 0.03, "out_layer.bias": torch.randn(112, generator=g) * 0.1}
+    for i in range(NB):
+        for name, (o, k) in {"attn.to_qkv": (3 * C, C), "attn.to_out": (C, C), "mlp.mlp.0": (4 * C, C), "mlp.mlp.2": (C, 4 * C)}.items():
+            sd[f"decoder.{i}.{name}.weight"] = torch.randn(o, k, generator=g) * 0.03
+            sd[f"decoder.{i}.{name}.bias"] = torch.randn(o, generator=g) * 0.05
+    sd = {k: v.half().float() for k, v in sd.items()}
+    coords = _voxels(700, 64, 2, seed=11)
+    T = coords.shape[0]
+    latent = torch.randn(T, 8, generator=g)
+    dout = torch.randn(T, 112, generator=g)
+    vae = SparseTransformerVAE(sd, NB, H, 8, use_fp16=use_fp16, norm_output=norm_output, device=DEV, use_old_attn_impl=old_impl)
+    y, saved = vae.decode_train(latent.to(DEV), coords.to(DEV))
+    y_inf = vae.decode(latent.to(DEV), coords.to(DEV))
+    grads, dlat = vae.decode_backward(saved, dout.to(DEV))
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lr = latent.clone().requires_grad_(True)
+    ref = OSW.vae_decode(sdr, NB, H, lr, coords, 8, "fp16", use_fp16=use_fp16, norm_output=norm_output, old_attn_impl=old_impl)
+    (ref * dout).sum().backward()
+    rel = lambda a, b: float((a.float().cpu() - b).norm() / b.norm().clamp_min(1e-20))
+    assert rel(y, ref.detach()) < 2e-3 and rel(y, y_inf.cpu()) < 2e-3
+    assert set(grads) == set(sd)
+    errs = {k: rel(grads[k], sdr[k].grad) for k in sd}
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    assert worst[1] < 1e-2, worst
+    assert rel(dlat, lr.grad) < 1e-2, rel(dlat, lr.grad)
+
+
+def test_gelu_tanh_forward_backward():
+    from gvfdiffusion_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    h = (torch.randn(1000, 512, generator=g) * 2.5).half().to(DEV)
+    dy = torch.randn(1000, 512, generator=g).half().to(DEV)
+    hr = h.float().requires_grad_(True)
+    ref = torch.nn.functional.gelu(hr, approximate="tanh")
+    ref.backward(dy.float())
+    assert (ops.gelu_tanh(h).float() - ref.detach()).abs().max() < 4e-3          # tanh.approx + fp16 rounding
+    assert (ops.gelu_tanh_bwd(h, dy).float() - hr.grad).abs().max() < 8e-3

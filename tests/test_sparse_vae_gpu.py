@@ -148,3 +148,39 @@ def test_subm_conv_gather_fused_is_bit_identical_to_im2col(n, res, cin, cout):
     f32 = ops.sparse_conv_gemm(xs.feats, conv.neighbor_map(xs), conv.weight, conv.bias, out_f32=True)
     ref = OSV.subm_conv3d(x.float(), coords, w.half().float(), bias, 2, res)
     assert float((f32.cpu() - ref).norm() / ref.norm()) < 1e-4
+
+
+@pytest.mark.parametrize("kind,reg,perturb", [("MipGS", "soft_invoxel", True), ("GS", "invoxel", False), ("GS", "none", False)])
+def test_to_representation_backward_matches_autograd(kind, reg, perturb):
+    """gvf_to_representation_bwd (through SparseVAE.to_representation under autograd) against torch autograd of the oracle
+    restatement: fp32, 1e-5 relative."""
+    from gvfdiffusion_b200.model.sparse_voxel_diffusion import SparseVAE
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from oracle import sparse_vae as OSV
+    cfg = {"lr": {"_xyz": 1.0, "_features_dc": 0.5, "_opacity": 0.05, "_scaling": 0.25, "_rotation": 0.1},
+           "perturb_offset": perturb, "reg_mode": reg, "voxel_size": 1.5, "num_gaussians": 8}
+    rc = {kind: cfg} if kind == "MipGS" else {kind: cfg, "MipGS": dict(cfg)}
+    sv = SparseVAE(resolution=64, representation_config=rc, device=DEV)
+    coords = _voxels(700, 64, 2, seed=6)
+    gen = torch.Generator().manual_seed(10)
+    feats = torch.randn(coords.shape[0], sv.out_channels, generator=gen)
+    fd = feats.to(DEV).requires_grad_(True)
+    reps = sv.to_representation(SparseTensor(fd, coords.to(DEV)))[kind]
+    P = coords.shape[0] * 8
+    w = {n: torch.randn(P, k, generator=gen) for n, k in (("_xyz", 3), ("_features_dc", 3), ("_scaling", 3), ("_rotation", 4), ("_opacity", 1))}
+    loss = 0
+    for b, rep in enumerate(reps):
+        sl = slice(b * 700 * 8, (b + 1) * 700 * 8)
+        for n in NAMES:
+            loss = loss + (getattr(rep, n).reshape(700 * 8, -1) * w[n][sl].to(DEV)).sum()
+    loss.backward()
+    fr = feats.clone().requires_grad_(True)
+    full = dict(sv.rep_config[kind])
+    pert = OSV.build_perturbation(8, reg, 1.5) if perturb else None
+    lo = sv.layouts[kind]["_xyz"]["range"][0]
+    ref = OSV.to_representation(fr, coords, full, 64, pert, kind=kind, start=lo)
+    sum((ref[n].reshape(P, -1) * w[n]).sum() for n in NAMES).backward()
+    got = fd.grad.cpu()
+    assert (got[:, :lo] == 0).all() and (got[:, lo + 112:] == 0).all()
+    err = (got - fr.grad).abs().max() / fr.grad.abs().max()
+    assert err < 1e-5, float(err)
