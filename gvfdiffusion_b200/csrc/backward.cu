@@ -527,7 +527,7 @@ GVF_API int gvf_ln_bwd_f16(const void* x, int x_is_f16, const void* dy, const vo
                                                              (const __half*)dres, (__half*)dx, M, eps);           \
     RET();                                                                                                        \
   }
-  GVF_LNB(768) GVF_LNB(96) GVF_LNB(192) GVF_LNB(384) GVF_LNB(512) GVF_LNB(1024)
+  GVF_LNB(768) GVF_LNB(128) GVF_LNB(96) GVF_LNB(192) GVF_LNB(384) GVF_LNB(512) GVF_LNB(1024)
 #undef GVF_LNB
   return GVF_ERR_UNSUPPORTED;
 }

@@ -10,7 +10,8 @@ LayerNorm, fc1 + GELU, fc2 + residual -- seven launches per block.  Same precisi
 """
 import torch
 
-from .. import ops
+from .. import _lib, ops
+from .._lib import check, current_stream, ptr
 from .attention import sparse_windowed_scaled_dot_product_self_attention
 from .attention.windowed_attn import windowed_attention_bwd, windowed_attention_fwd_lse
 
@@ -197,41 +198,108 @@ class SparseTransformerVAE:
         feats = feats.detach().to(self.dev, F32).contiguous()
         pos = ops.ape(coords[:, 1:].float().contiguous(), self.C)
         w, bias = self.lin[first]
-        if w.shape[1] > 32:
-            raise NotImplementedError("training path of the first Linear is built for <= 32 input channels (from_latent)")
-        h0 = ops.small_linear(feats, w, bias, out_f16=False, add=pos, add_rows=feats.shape[0])
+        if w.shape[1] <= 16:
+            h0 = ops.small_linear(feats, w, bias, out_f16=False, add=pos, add_rows=feats.shape[0])
+        else:
+            feats = ops.cast_f16(feats)
+            h0 = ops.gemm(feats, w, bias, ops.EPI_F16).float() + pos
         X, saved = blocks.forward_train(h0, coords)
         saved["first_in"] = feats
         return X, saved
 
-    def decode_train(self, latent_feats, coords):
-        """decode keeping the activations: -> (out [T, out_channels] fp32, saved)."""
-        X, saved = self._trunk_train(self.decoder, "from_latent", latent_feats, coords)
-        saved["x_last"] = X
-        hn = ops.ln_mod(X, eps=1e-5) if self.norm_output else (X if X.dtype == F16 else ops.cast_f16(X))
-        saved["hn"] = hn
-        w, bias = self.lin["out_layer"]
-        return ops.gemm(hn, w, bias, ops.EPI_F16).float(), saved
+    def _first_backward(self, first, saved, dx, g, need_input_grad):
+        """gradients of the trunk's first Linear (from_latent: K <= 32 on the skinny kernels; input_layer: GEMMs)."""
+        w, _ = self.lin[first]
+        x = saved["first_in"]
+        g[first + ".bias"] = ops.colsum(dx)
+        if w.shape[1] <= 16:
+            g[first + ".weight"] = ops.skinny_outer(x, dx).t().contiguous()
+            return ops.small_linear_bwd_input(dx, w) if need_input_grad else None
+        g[first + ".weight"] = ops.gemm_tn(dx, x)
+        if not need_input_grad:
+            return None
+        if first + "_t" not in self.lin:
+            self.lin[first + "_t"] = ops.transpose(w)
+        return ops.gemm(dx, self.lin[first + "_t"], None, ops.EPI_F32)
 
-    def decode_backward(self, saved, dout):
-        """dout [T, out_channels] -> ({parameter name: fp32 gradient}, d latent fp32 [T, latent_channels])."""
-        w, _ = self.lin["out_layer"]
+    def _last_backward(self, last, saved, dout, g):
+        """gradients of the trunk's last Linear (+ the affine-free LayerNorm in front of it) -> d block output fp16."""
+        w, _ = self.lin[last]
         N, T = w.shape[0], dout.shape[0]
         N8 = (N + 7) // 8 * 8
         d16 = torch.zeros((T, N8), dtype=F16, device=self.dev)
         d16[:, :N] = dout.detach()
-        if "out_layer_t" not in self.lin:
-            self.lin["out_layer_t"] = ops.transpose(w)                        # [C, N8]
-        g = {"out_layer.weight": ops.gemm_tn(d16, saved["hn"])[:N], "out_layer.bias": ops.colsum(d16)[:N]}
-        dh = ops.gemm(d16, self.lin["out_layer_t"], None, ops.EPI_F16)
+        if last + "_t" not in self.lin:
+            self.lin[last + "_t"] = ops.transpose(w)                          # [C, N8]
+        g[last + ".weight"] = ops.gemm_tn(d16, saved["hn"])[:N]
+        g[last + ".bias"] = ops.colsum(d16)[:N]
+        dh = ops.gemm(d16, self.lin[last + "_t"], None, ops.EPI_F16)
         if self.norm_output:
             dh = ops.ln_bwd(saved["x_last"], dh, None, eps=1e-5)
+        return dh
+
+    def _last_forward(self, last, X, saved):
+        saved["x_last"] = X
+        hn = ops.ln_mod(X, eps=1e-5) if self.norm_output else (X if X.dtype == F16 else ops.cast_f16(X))
+        saved["hn"] = hn
+        w, bias = self.lin[last]
+        return ops.gemm(hn, w, bias, ops.EPI_F16).float()
+
+    def encode_train(self, feats, coords, noise=None, sample_posterior=True):
+        """encode keeping the activations (:151-176): -> (z, mean, logvar, kl, saved); kl = 0.5 mean(mean^2 + var - logvar
+        - 1) over all voxels (sparse_vae.py:351).  noise: the randn_like draw of :165 ([T, latent]; host RNG when None)."""
+        X, saved = self._trunk_train(self.encoder, "input_layer", feats, coords)
+        ml = self._last_forward("to_latent", X, saved)
+        lat = ml.shape[1] // 2
+        mean, logvar = ml[:, :lat].contiguous(), ml[:, lat:].contiguous()
+        if sample_posterior and noise is None:
+            noise = torch.randn(mean.shape)
+        noise = noise.to(self.dev, F32).contiguous() if sample_posterior else None
+        z, kl = torch.empty_like(mean), torch.empty(1, dtype=F32, device=self.dev)
+        check(_lib.lib().gvf_diag_gaussian(ptr(mean), ptr(logvar), ptr(noise), 1, mean.numel(), ptr(z), ptr(kl), current_stream()),
+              "gvf_diag_gaussian")
+        saved.update(mean=mean, logvar=logvar, noise=noise)
+        return z, mean, logvar, kl[0], saved
+
+    def encode_backward(self, saved, dz=None, dkl=None, need_input_grad=False):
+        """-> ({parameter name: fp32 gradient}, d feats or None)."""
+        mean, logvar = saved["mean"], saved["logvar"]
+        dmean, dlogvar = torch.empty_like(mean), torch.empty_like(mean)
+        dzc = None if dz is None else dz.detach().to(self.dev, F32).contiguous()
+        dkc = None if dkl is None else dkl.detach().to(self.dev, F32).reshape(1).contiguous()
+        check(_lib.lib().gvf_diag_gaussian_bwd(ptr(mean), ptr(logvar), ptr(saved["noise"]), ptr(dzc), ptr(dkc), 1, mean.numel(),
+                                               ptr(dmean), ptr(dlogvar), current_stream()), "gvf_diag_gaussian_bwd")
+        g = {}
+        dh = self._last_backward("to_latent", saved, torch.cat([dmean, dlogvar], 1), g)
+        gb, dx = self.encoder.backward(saved, dh)
+        g.update(gb)
+        return g, self._first_backward("input_layer", saved, dx, g, need_input_grad)
+
+    def forward_train(self, feats, coords, noise=None):
+        """SparseTransformerVAE.forward with sample_posterior=True (:206-210): -> (out, mean, logvar, kl, saved)."""
+        z, mean, logvar, kl, se = self.encode_train(feats, coords, noise)
+        out, sd_ = self.decode_train(z, coords)
+        return out, mean, logvar, kl, {"enc": se, "dec": sd_}
+
+    def backward(self, saved, dout, dkl=None):
+        """gradients of every parameter of the VAE from d out [T, out_channels] and d kl (scalar tensor)."""
+        g, dz = self.decode_backward(saved["dec"], dout)
+        ge, _ = self.encode_backward(saved["enc"], dz, dkl)
+        g.update(ge)
+        return g
+
+    def decode_train(self, latent_feats, coords):
+        """decode keeping the activations: -> (out [T, out_channels] fp32, saved)."""
+        X, saved = self._trunk_train(self.decoder, "from_latent", latent_feats, coords)
+        return self._last_forward("out_layer", X, saved), saved
+
+    def decode_backward(self, saved, dout):
+        """dout [T, out_channels] -> ({parameter name: fp32 gradient}, d latent fp32 [T, latent_channels])."""
+        g = {}
+        dh = self._last_backward("out_layer", saved, dout, g)
         gb, dx = self.decoder.backward(saved, dh)
         g.update(gb)
-        wf, _ = self.lin["from_latent"]
-        g["from_latent.weight"] = ops.skinny_outer(saved["first_in"], dx).t().contiguous()
-        g["from_latent.bias"] = ops.colsum(dx)
-        return g, ops.small_linear_bwd_input(dx, wf)
+        return g, self._first_backward("from_latent", saved, dx, g, True)
 
     def decode(self, latent_feats, coords):
         """latent [T, latent_channels] fp32, coords [T, 4] int32 -> [T, out_channels] fp32 (:178-188)."""
@@ -241,3 +309,30 @@ class SparseTransformerVAE:
         """feats [T, in_channels] -> (mean, logvar) [T, latent_channels] each (:151-176, sample_posterior=False)."""
         out = self._trunk(self.encoder, "input_layer", "to_latent", feats, coords)
         return out.chunk(2, dim=-1)
+
+
+class _SparseVAETrainFn(torch.autograd.Function):
+    """The whole static VAE (encode -> posterior sample -> decode) as one autograd node: forward_train / backward of the
+    engine above.  Parameter gradients are left on `engine.grads` ({reference parameter name: fp32 tensor}); `anchor` is any
+    tensor that requires grad, so that autograd calls the node."""
+
+    @staticmethod
+    def forward(ctx, engine, feats, coords, noise, anchor):
+        out, mean, logvar, kl, saved = engine.forward_train(feats, coords, noise)
+        ctx.engine, ctx.saved = engine, saved
+        ctx.mark_non_differentiable(mean, logvar)
+        return out, kl.reshape(()), mean, logvar
+
+    @staticmethod
+    def backward(ctx, dout, dkl, _dm, _dl):
+        ctx.engine.grads = ctx.engine.backward(ctx.saved, dout, dkl)
+        ctx.saved = None
+        return None, None, None, None, None
+
+
+def sparse_vae_forward_autograd(engine, feats, coords, noise=None, anchor=None):
+    """(out [T, out_channels], kl, mean, logvar) with `out` and `kl` attached to the autograd graph (what
+    `SparseVAE.training_losses`, reference sparse_vae.py:318, consumes)."""
+    if anchor is None:
+        anchor = torch.zeros((), device=engine.dev, requires_grad=True)
+    return _SparseVAETrainFn.apply(engine, feats, coords, noise, anchor)
