@@ -1,9 +1,11 @@
 """`SparseVAE.to_representation` on the device: the canonical-Gaussian end of the static VAE, mirroring the
 reference's model/sparse_voxel_diffusion/sparse_vae.py:60-112 (configuration, Hammersley perturbation),
 :114-180 (to_representation) and :202-227 (feature-row layout).  The trunk that produces the feature rows is
-`gvfdiffusion_b200.sparse.transformer.SparseTransformerVAE.decode`; training (losses, regularisers, optimiser
-phases) is out of scope.  One kernel launch per representation type covers the whole batch; the per-entry
-`GaussianModel`s returned are views into its outputs."""
+`gvfdiffusion_b200.sparse.transformer.SparseTransformerVAE`.  One kernel launch per representation type covers the whole
+batch; the per-entry `GaussianModel`s returned are views into its outputs.  `training_losses` (:303-362) is the static-VAE
+half of the reference's train step (BASELINE configs[4]): backbone forward / backward on the library's kernels as one
+autograd node, to_representation, one render per sample, L1 + lambda_ssim (1 - SSIM) [+ lambda_lpips LPIPS through a
+caller-supplied module: the VGG16 weights are a network download] + lamda_kl KL + volume / opacity regularisers."""
 import copy
 
 import torch
@@ -57,9 +59,14 @@ class _ToRepresentationFn(torch.autograd.Function):
 
 
 class SparseVAE:
-    def __init__(self, backbones=None, resolution=64, representation_config=None, device="cuda"):
+    def __init__(self, backbones=None, resolution=64, representation_config=None, device="cuda", loss_type="l1",
+                 lambda_ssim=0.2, lambda_lpips=0.0, lamda_kl=1e-6, regularizations=None, mem_ratio=1.0, lpips=None):
         self.backbones = backbones or {}
         self.resolution = resolution
+        self.loss_type, self.lambda_ssim, self.lambda_lpips, self.lamda_kl = loss_type, lambda_ssim, lambda_lpips, lamda_kl
+        self.regularizations = regularizations or {}
+        self.mem_ratio = mem_ratio        # accepted; every activation is kept (180 GB of HBM: no checkpointing needed)
+        self.lpips = lpips
         self.device = torch.device(device)
         self.rep_config = {}
         for k, v in (representation_config or {}).items():
@@ -68,8 +75,109 @@ class SparseVAE:
             self.rep_config[k] = copy.deepcopy(_DEFAULT_CONFIG[k])
             self.rep_config[k].update(v)
         self._calc_layout(self.rep_config)
+        self._init_renderer()
         self.perturbation = {k: self._build_perturbation(v["num_gaussians"], v["reg_mode"])
                              for k, v in self.rep_config.items() if v["perturb_offset"]}
+
+    def get_renderer(self, type, rendering_options):
+        """:184-194"""
+        from ...renderers.gaussian_render import GaussianRenderer
+        renderer = GaussianRenderer(rendering_options)
+        if type == "MipGS":
+            renderer.pipe.use_mip_gaussian = True
+            renderer.pipe.kernel_size = self.rep_config["MipGS"]["2d_filter_kernel_size"]
+        elif type != "GS":
+            raise ValueError(f"Invalid representation type: {type}")
+        return renderer
+
+    def _init_renderer(self):
+        """:196-200"""
+        opts = {"near": 0.8, "far": 1.6, "bg_color": (1.0, 1.0, 1.0)}
+        self.renderers = {k: self.get_renderer(k, opts) for k in self.rep_config.keys()}
+
+    def render_batch(self, reps, extrinsics, intrinsics):
+        """One render per (representation type, batch entry) (:281-301) -> {type: {'rgb' [N,3,H,W], 'alpha' [N,H,W],
+        'bg_color' [N,3]}}."""
+        ret = {}
+        for k, v in reps.items():
+            packs = [self.renderers[k].render(rep, extrinsics[i], intrinsics[i]) for i, rep in enumerate(v)]
+            ret[k] = {kk: torch.stack([p[kk] for p in packs], 0) for kk in packs[0].keys()}
+            ret[k]["bg_color"] = torch.stack([self.renderers[k].bg_color] * len(packs), 0)
+        return ret
+
+    def get_regularization_loss(self, x, reps):
+        """Volume and opacity regularisers (:228-248).  The activated scales / opacities are re-derived from the raw
+        tensors with torch expressions here so that autograd reaches to_representation's backward: two elementwise
+        maps over [P, 3] / [P, 1], not part of the rendered path."""
+        import torch.nn.functional as F
+        loss, terms = 0.0, {}
+        for k, v in reps.items():
+            reg = self.regularizations.get(k)
+            if not reg:
+                continue
+            if "lambda_vol" in reg:
+                sc = []
+                for g in v:
+                    s = g._scaling + g.scale_bias
+                    s = F.softplus(s) if g.scaling_activation_type == "softplus" else torch.exp(s)
+                    sc.append(torch.sqrt(torch.square(s) + g.mininum_kernel_size ** 2))
+                terms[f"reg_{k}_vol"] = torch.prod(torch.cat(sc, 0), dim=1).mean()
+                loss = loss + reg["lambda_vol"] * terms[f"reg_{k}_vol"]
+            if "lambda_opacity" in reg:
+                op = torch.cat([torch.sigmoid(g._opacity + g.opacity_logit_bias) for g in v], 0)
+                terms[f"reg_{k}_opacity"] = (op - 1).pow(2).mean()
+                loss = loss + reg["lambda_opacity"] * terms[f"reg_{k}_opacity"]
+        return loss, terms
+
+    def _backbone_forward(self, feats, noise=None):
+        """`self.backbones['vae'](feats)` of :318 -> (out [Nvox, out_channels], kl, mean, logvar), out and kl on the graph."""
+        from ...sparse.transformer import sparse_vae_forward_autograd
+        return sparse_vae_forward_autograd(self.backbones["vae"], feats.feats, feats.coords, noise)
+
+    def training_losses(self, feats, image, extrinsics, intrinsics, return_aux=False, noise=None, **kwargs):
+        """feats: SparseTensor [Nvox, in_channels]; image [N,3,H,W]; extrinsics [N,4,4]; intrinsics [N,3,3] ->
+        (terms, reps) with terms['loss'] a scalar attached to the autograd graph (:303-362).  After
+        `terms['loss'].backward()` the backbone's parameter gradients are on `backbones['vae'].grads`.
+        noise: the posterior's randn_like draw (host RNG when None)."""
+        from ...utils.loss_util import l2_loss, ssim, ssim_l1
+        out, kl, mean, logvar = self._backbone_forward(feats, noise)
+        x = feats.replace(out)
+        reps = self.to_representation(x)
+        for v in self.renderers.values():
+            v.rendering_options.resolution = image.shape[-1]
+        render_results = self.render_batch(reps, extrinsics, intrinsics)
+        terms = {"loss": 0.0, "rec": 0.0}
+        for k, rr in render_results.items():
+            rec = rr["rgb"]
+            if self.loss_type == "l1":
+                s, l1 = ssim_l1(rec, image)                    # one kernel for both terms
+                terms[k + "_l1"] = l1
+                terms["rec"] = terms["rec"] + l1
+            elif self.loss_type == "l2":
+                terms[k + "_l2"] = l2_loss(rec, image)
+                terms["rec"] = terms["rec"] + terms[k + "_l2"]
+                s = ssim(rec, image) if self.lambda_ssim > 0 else None
+            else:
+                raise ValueError(f"Invalid loss type: {self.loss_type}")
+            if self.lambda_ssim > 0:
+                terms[k + "_ssim"] = 1 - s
+                terms["rec"] = terms["rec"] + self.lambda_ssim * terms[k + "_ssim"]
+            if self.lambda_lpips > 0:
+                if self.lpips is None:
+                    raise RuntimeError("lambda_lpips > 0 needs an LPIPS module (SparseVAE(lpips=...)): its VGG16 weights are a "
+                                       "network download in the reference (utils/lpips)")
+                terms[k + "_lpips"] = self.lpips(rec, image)
+                terms["rec"] = terms["rec"] + self.lambda_lpips * terms[k + "_lpips"]
+            terms["loss"] = terms["loss"] + terms["rec"]
+        terms["kl"] = kl
+        terms["loss"] = terms["loss"] + self.lamda_kl * kl
+        reg_loss, reg_terms = self.get_regularization_loss(x, reps)
+        terms.update(reg_terms)
+        terms["loss"] = terms["loss"] + reg_loss
+        if return_aux:
+            rec_image = torch.cat([v["rgb"] for v in render_results.values()])
+            return terms, reps, {"rec_image": rec_image, "gt_image": torch.cat([image for _ in render_results])}
+        return terms, reps
 
     def _build_perturbation(self, num_gaussians, reg_mode):
         offsets = torch.tensor([hammersley_sequence(3, i, num_gaussians) for i in range(num_gaussians)]).float() - 0.5

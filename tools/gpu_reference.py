@@ -214,6 +214,62 @@ def vae_decode(sd, z, queries, heads, T, depth, chunk=8192):
     return out.float()
 
 
+# ------------------------------------------------------------------------------------------ static VAE (cfg 5)
+def sparse_vae_forward(sd, sd16, feats, coords, noise, H, nblk, parts, norm_output=True):
+    """SparseTransformerVAE.forward with use_fp16=True (sparse_transformer_vae.py:151-210): fp16 block weights (sd16: the
+    reference converts the blocks with convert_module_to_f16 once) and an fp16 residual stream, LayerNorm32 in fp32,
+    window attention as sparse/attention/windowed_attn.py:92-129 runs it -- gather by fwd_indices, flash_attn varlen,
+    scatter by bwd_indices -- with the partition cached (parts[shifted] = (fwd, bwd, cu_seqlens, max_len)).
+    -> (out, mean, logvar) under torch autograd."""
+    fa = _flash()
+    C = sd["input_layer.weight"].shape[0]
+    pos = _ape(coords[:, 1:].float()[None], C)[0]
+
+    def trunk(prefix, h):
+        h = h.half()
+        for i in range(nblk):
+            p = f"{prefix}{i}."
+            fwd, bwd, cu, maxlen = parts[i % 2]
+            n = F.layer_norm(h.float(), (C,), eps=1e-6).half()
+            qkv = F.linear(n, sd16[p + "attn.to_qkv.weight"], sd16[p + "attn.to_qkv.bias"]).reshape(-1, 3, H, C // H)
+            o = fa.flash_attn_varlen_qkvpacked_func(qkv[fwd], cu, maxlen)[bwd].reshape(-1, C)
+            h = h + F.linear(o, sd16[p + "attn.to_out.weight"], sd16[p + "attn.to_out.bias"])
+            n = F.layer_norm(h.float(), (C,), eps=1e-6).half()
+            m = F.gelu(F.linear(n, sd16[p + "mlp.mlp.0.weight"], sd16[p + "mlp.mlp.0.bias"]), approximate="tanh")
+            h = h + F.linear(m, sd16[p + "mlp.mlp.2.weight"], sd16[p + "mlp.mlp.2.bias"])
+        h = h.float()
+        return F.layer_norm(h, (C,)) if norm_output else h
+
+    lin = lambda x, n: F.linear(x, sd[n + ".weight"], sd[n + ".bias"])
+    with torch.autocast("cuda", dtype=torch.float16):
+        h = lin(feats, "input_layer").float() + pos
+    h = trunk("encoder.", h)
+    with torch.autocast("cuda", dtype=torch.float16):
+        ml = lin(h, "to_latent").float()
+    mean, logvar = ml.chunk(2, dim=-1)
+    z = mean + torch.exp(0.5 * logvar) * noise
+    with torch.autocast("cuda", dtype=torch.float16):
+        h = lin(z, "from_latent").float() + pos
+    h = trunk("decoder.", h)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = lin(h, "out_layer").float()
+    return out, mean, logvar
+
+
+def to_representation_torch(feats, coords, G, lr, resolution, voxel_size, perturbation):
+    """SparseVAE.to_representation, MipGS / soft_invoxel branch (sparse_vae.py:165-180), as the torch expressions the
+    reference evaluates -> raw (_xyz, _features_dc, _scaling, _rotation, _opacity) for all voxels."""
+    xyz = (coords[:, 1:].float() + 0.5) / resolution
+    off = feats[:, :3 * G].reshape(-1, G, 3) * lr[0] + perturbation
+    off = torch.tanh(off) / resolution * 0.5 * voxel_size
+    out = [(xyz.unsqueeze(1) + off).flatten(0, 1)]
+    s = 3 * G
+    for w, l, shape in ((3, lr[1], (G, 1, 3)), (3, lr[2], (G, 3)), (4, lr[3], (G, 4)), (1, lr[4], (G, 1))):
+        out.append(feats[:, s:s + G * w].reshape(-1, *shape).flatten(0, 1) * l)
+        s += G * w
+    return out
+
+
 # ------------------------------------------------------------------------------------------ whole object
 class GpuReference:
     """One object end to end the way the reference drives it; weights = the product models' state dicts."""
