@@ -23,6 +23,17 @@ class RasterParams(C.Structure):
 
 
 _P = C.c_void_p
+
+
+class SparseBlock(C.Structure):
+    """gvf_sparse_block (include/gvf_b200.h): weights, transposes and gradient outputs of one SparseTransformerBlock."""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "w_qkv", "w_out", "w1", "w2", "b_qkv", "b_out", "b1", "b2", "w_qkv_t", "w_out_t", "w1_t", "w2_t",
+        "g_w_qkv", "g_b_qkv", "g_w_out", "g_b_out", "g_w1", "g_b1", "g_w2", "g_b2")]
+
+
+class WindowPartition(C.Structure):
+    _fields_ = [("fwd_idx", C.c_void_p), ("cu_seqlens", C.c_void_p), ("num_windows", C.c_int), ("max_seqlen", C.c_int)]
 _SIGS = {
     # name: (restype, argtypes)
     "gvf_status_string": (C.c_char_p, [C.c_int]),
@@ -54,6 +65,12 @@ _SIGS = {
     "gvf_colsum": (C.c_int, [_P, C.c_int, C.c_longlong, C.c_int, C.c_longlong, _P, C.c_size_t, _P, C.c_int, _P]),
     "gvf_ln_bwd_f16": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
     "gvf_geglu_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P, _P]),
+    "gvf_sparse_trunk_arena_bytes": (C.c_size_t, [C.c_int] * 6),
+    "gvf_sparse_trunk_scratch_bytes": (C.c_size_t, [C.c_int] * 4),
+    "gvf_sparse_trunk_forward": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t,
+                                           _P, C.c_size_t, _P, _P]),
+    "gvf_sparse_trunk_backward": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P,
+                                            _P, C.c_size_t, _P, C.c_size_t, _P, _P]),
     "gvf_gelu_tanh_f16": (C.c_int, [_P, C.c_longlong, _P, _P]),
     "gvf_gelu_tanh_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),
     "gvf_to_representation_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_float), C.c_float, C.c_int,

@@ -90,6 +90,60 @@ __global__ void __launch_bounds__(256) reduce_slabs_kernel(const float* __restri
   out[i] = accumulate ? out[i] + s : s;
 }
 
+// fp16, N % 8 == 0: one launch.  CTA = 256 columns (32 x 16 B vectors) x 8 row lanes over a slab of rows; the slab
+// partials go to the workspace and the LAST CTA of a column block to finish (ticket counter, self-resetting) adds them
+// in slab order -- the same deterministic sum as the two-launch form without its second launch (~7 us each, 150 bias
+// gradients per static-VAE step).  Not re-entrant across streams (neither is the shared workspace).
+__device__ unsigned int g_colsum_tickets[256];
+__global__ void __launch_bounds__(256) colsum_f16_fused_kernel(const __half* __restrict__ x, long long M, int N,
+                                                               long long ld, int rows_per_slab,
+                                                               float* __restrict__ partial, float* __restrict__ out,
+                                                               int accumulate) {
+  __shared__ float red[8][256 + 8];
+  __shared__ unsigned int s_ticket;
+  const int vc = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * 256 + vc * 8;
+  const long long m0 = (long long)blockIdx.y * rows_per_slab;
+  const long long m1 = m0 + rows_per_slab < M ? m0 + rows_per_slab : M;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (n0 < N) {
+#pragma unroll 4
+    for (long long m = m0 + rl; m < m1; m += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + m * ld + n0));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[2 * j] += __low2float(h[j]);
+        s[2 * j + 1] += __high2float(h[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][vc * 8 + j] = s[j];
+  __syncthreads();
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+    partial[(long long)blockIdx.y * N + n] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&g_colsum_tickets[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  __threadfence();
+  if (n < N) {
+    float t = 0.f;
+    for (unsigned k = 0; k < gridDim.y; ++k) t += __ldcg(partial + (long long)k * N + n);
+    out[n] = accumulate ? out[n] + t : t;
+  }
+  if (threadIdx.x == 0) g_colsum_tickets[blockIdx.x] = 0u;
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 // y = (x - mean) * rstd (no affine, PreNorm):  dx = rstd * (dy - mean(dy) - yhat * mean(dy * yhat)) (+ dres).
 // x fp16 or fp32 [M, C]; dy, dres, dx fp16.  One warp per row, row in registers.
@@ -506,6 +560,10 @@ GVF_API int gvf_colsum(const void* x, int x_is_f16, long long M, int N, long lon
   const int rps = slab_rows(M, &slabs);
   if (workspace_bytes < (size_t)slabs * N * sizeof(float)) return GVF_ERR_WORKSPACE;
   const dim3 grid((N + 255) / 256, slabs);
+  if (x_is_f16 && (N % 8) == 0 && (ld % 8) == 0 && ((uintptr_t)x & 15) == 0 && grid.x <= 256) {
+    colsum_f16_fused_kernel<<<grid, 256, 0, ST(stream)>>>((const __half*)x, M, N, ld, rps, workspace, out, accumulate);
+    RET();
+  }
   if (x_is_f16) colsum_partial_kernel<__half><<<grid, 256, 0, ST(stream)>>>((const __half*)x, M, N, ld, rps, workspace);
   else colsum_partial_kernel<float><<<grid, 256, 0, ST(stream)>>>((const float*)x, M, N, ld, rps, workspace);
   reduce_slabs_kernel<<<(N + 255) / 256, 256, 0, ST(stream)>>>(workspace, slabs, N, out, accumulate);

@@ -64,6 +64,15 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return fmaf(h, t, h);
 }
 
+// d/dx of the above with the same tanh.approx: 0.5 (1 + t) + 0.5 x (1 - t^2) k0 (1 + 3 k1 x^2)
+__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * fmaf(k0 * k1, x2, k0)));
+  return fmaf(0.5f * x * (1.0f - t * t), k0 * fmaf(3.0f * k1, x2, 1.0f), 0.5f * (1.0f + t));
+}
+
 constexpr int kEpiCols = 64;                 // columns per epilogue chunk (default)
 constexpr int kStgLd = kEpiCols + 1;         // padded row of the per-warp staging tile (floats)
 
@@ -582,7 +591,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int HALF = BN / 2;
     const int et = threadIdx.x - 64;               // 0..255
     constexpr int mode = MODE;
-    constexpr bool out16 = (mode == 0 || mode == 1 || mode == 3 || mode == 6 || mode == 7);
+    constexpr bool out16 = (mode == 0 || mode == 1 || mode == 3 || mode == 6 || mode == 7 || mode == 8);
     uint8_t* stg = stg_base + ew * 2 * 4096;
     const uint32_t sw = (uint32_t)(lane & 7);      // SWIZZLE_128B: 16 B piece j of row r sits at j ^ (r & 7)
     int lt = 0, sbuf = 0;
@@ -622,6 +631,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               old[j] = (row_ok && col0 + 8 * j < N) ? *reinterpret_cast<const uint4*>(orow + 8 * j)
                                                     : make_uint4(0u, 0u, 0u, 0u);
           }
+          if (mode == 8) {                          // GELU backward: the saved pre-activation rows, same overlap
+            const __half* hrow = ep.gate + (size_t)row * ep.gate_stride + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              old[j] = (row_ok && col0 + 8 * j < N) ? __ldg(reinterpret_cast<const uint4*>(hrow + 8 * j))
+                                                    : make_uint4(0u, 0u, 0u, 0u);
+          }
           if (c0 == 0) {
             mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
             tc_fence_after();
@@ -652,8 +668,34 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
           }
           if (mode == 1) {
+            if (ep.gate) {
+              // training forward: the fp16 pre-activation is kept for GELU' (rows are 128 B per thread and chunk)
+              __half* hrow = const_cast<__half*>(ep.gate) + (size_t)row * ep.gate_stride + col0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint4 pk;
+                uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const __half2 h2 = __floats2half2_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
+                  pw[t] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                if (row_ok && col0 + 8 * j < N) *reinterpret_cast<uint4*>(hrow + 8 * j) = pk;
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_fast(r16(v[j]));
+          } else if (mode == 8) {
+            // out = fp16(fp16(acc) * gelu'(h0)): the dgrad of the MLP's second Linear with the activation's backward
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __half2* o2 = reinterpret_cast<const __half2*>(&old[j]);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                v[8 * j + 2 * t] = r16(v[8 * j + 2 * t]) * gelu_tanh_grad_fast(__low2float(o2[t]));
+                v[8 * j + 2 * t + 1] = r16(v[8 * j + 2 * t + 1]) * gelu_tanh_grad_fast(__high2float(o2[t]));
+              }
+            }
           } else if (mode == 6) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -1171,15 +1213,56 @@ using namespace gvf;
 static int g_gemm_variant = -1;
 static int g_gemm_ksplit = 0;      // 0 automatic, -1 never, n > 0 forced (fp32-store epilogue only)
 
+// Split-K factor of the fp32-store GEMMs (weight gradients).  Work items = tiles x ksplit run in waves of one item per
+// SM, so what matters is the wave count: 18 tiles x 8 = 144 items are one wave, x 10 = 180 are two with the second 78 %
+// empty (768 x 768 x 393216: 407 us at 8, 623 us at 10, 409 us at 16 -- tools/gemm_tn_ksplit_sweep.py,
+// profiles/r02_gemm_tn_ksplit.txt).  Cost model fitted to that sweep, in us: waves x (k-blocks per item x 0.5 + 3.7
+// epilogue incl. the TMA reduce-add) + 3 for the zero fill when split; an un-split kernel on at most half the SMs sees
+// 0.42 us per k-block (the operand stream L2 -> SM is the limit, fewer CTAs get more of it).  It picks the measured optimum on
+// every shape of the two training steps.
+static int sm_count() {             // one device kind per process: queried once (the attribute call costs microseconds)
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms = n;
+  }
+  return sms;
+}
+static int pick_ksplit(long long tiles, int kblocks, int sms) {
+  if (kblocks < 8) return 1;
+  const int kmax = kblocks / 4 < 32 ? kblocks / 4 : 32;
+  double cost[33];
+  double best = 1e30;
+  for (int ks = 1; ks <= 32; ++ks) {
+    cost[ks] = 1e30;
+    if (ks > (kmax > 1 ? kmax : 1)) continue;
+    const int per = (kblocks + ks - 1) / ks;
+    if (ks > 1 && (kblocks + per - 1) / per != ks) continue;        // would leave an empty split
+    const long long waves = (tiles * ks + sms - 1) / sms;
+    const double a = (ks == 1 && tiles * 2 <= sms) ? 0.42 : 0.5;
+    cost[ks] = waves * (per * a + 3.7) + (ks > 1 ? 3.0 : 0.0);
+    if (cost[ks] < best) best = cost[ks];
+  }
+  // within 2.5 % of the optimum prefer the finest split: shorter fp32 accumulation chains in the tensor core (which
+  // truncates), e.g. 24 x 16384 instead of 8 x 49152 products for the decoder's 393216-row weight gradients
+  for (int ks = 32; ks >= 1; --ks)
+    if (cost[ks] <= best * 1.025) return ks;
+  return 1;
+}
+
 static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue,
                      const float* bias, void* out, int ldo, const void* gate, int gate_stride,
                      int rows_per_batch, const float* gamma_q, const float* gamma_k, int norm_cols,
                      void* stream) {
   if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return GVF_ERR_INVALID;
-  if ((N % 8) || (K % 8) || (lda % 8) || (ldw % 8) || epilogue < 0 || epilogue > 7) return GVF_ERR_INVALID;
+  if ((N % 8) || (K % 8) || (lda % 8) || (ldw % 8) || epilogue < 0 || epilogue > 8) return GVF_ERR_INVALID;
+  if (epilogue == 8 && !gate) return GVF_ERR_INVALID;
   if (epilogue == 6 && (!gamma_q || !gamma_k || norm_cols <= 0 || (norm_cols % 64) || norm_cols > N))
     return GVF_ERR_INVALID;
-  if ((epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6 || epilogue == 7) && (ldo % 2)) return GVF_ERR_INVALID;
+  if ((epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6 || epilogue == 7 || epilogue == 8) && (ldo % 2))
+    return GVF_ERR_INVALID;
   if (epilogue == 7 && (N % 256)) return GVF_ERR_UNSUPPORTED;      // GEGLU: whole 256-row weight tiles [128 value | 128 gate]
   if ((epilogue == 2 || epilogue == 4) && (ldo % 2)) return GVF_ERR_INVALID;
   if (gate && (gate_stride % 2)) return GVF_ERR_INVALID;
@@ -1210,6 +1293,8 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
        (gate && ((gate_stride % 8) || ((uintptr_t)gate & 15)))))
     variant = 0;
   if (epilogue == 7 && variant != 5 && variant != 7) return GVF_ERR_UNSUPPORTED;
+  // the pre-activation side output of mode 1 and the GELU' epilogue exist in the generation-2 kernels only
+  if ((epilogue == 8 || (epilogue == 1 && gate)) && !(variant >= 4 && variant <= 9)) return GVF_ERR_UNSUPPORTED;
   // 8 / 9: pipeline-depth experiments (128x128 with 5 stages, 256x128 pair tiles with 6 stages)
   const int BN = (variant == 2 || variant == 5 || variant == 7) ? 256 : 128;
   const int wbox = (variant == 6 || variant == 7 || variant == 9) ? BN / 2 : BN;      // W rows one CTA stages per k-block
@@ -1225,7 +1310,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
   ep.ldo = ldo;
   ep.gamma_q = gamma_q; ep.gamma_k = gamma_k; ep.norm_cols = norm_cols;
   if (variant >= 4 && variant <= 9) {
-    const bool out16 = (epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6 || epilogue == 7);
+    const bool out16 = (epilogue == 0 || epilogue == 1 || epilogue == 3 || epilogue == 6 || epilogue == 7 || epilogue == 8);
     CUtensorMap mO;
     if (!make_tmap_2d(&mO, out, out16 ? 2 : 4, (uint64_t)(epilogue == 7 ? N / 2 : N), (uint64_t)M, (uint64_t)ldo,
                       out16 ? 64 : 32, 32))
@@ -1246,14 +1331,10 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
       const int NC = (variant == 6 || variant == 7 || variant == 9) ? 2 : 1;
       const long long tiles = (long long)((N + BN - 1) / BN) * ((M + NC * kBM - 1) / (NC * kBM));
       const int kblocks = (K + kBK - 1) / kBK;
-      int sms = 148;
-      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int sms = sm_count();
       int ksplit = 1;
       if (g_gemm_ksplit > 0) ksplit = g_gemm_ksplit;
-      else if (g_gemm_ksplit == 0 && tiles * 2 <= sms / NC && kblocks >= 32) {
-        ksplit = (int)((sms / NC) / tiles);
-        if (ksplit > kblocks / 8) ksplit = kblocks / 8;
-      }
+      else if (g_gemm_ksplit == 0 && tiles * 2 <= sms / NC && kblocks >= 32) ksplit = pick_ksplit(tiles, kblocks, sms / NC);
       if (ksplit > 1) {
         const int per = (kblocks + ksplit - 1) / ksplit;
         ksplit = (kblocks + per - 1) / per;           // no empty split
@@ -1273,6 +1354,11 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, int M, int 
       case 7:
         return variant == 7 ? launch_gemm_ws<256, 4, 7, 2>(mA, mW, mO, M, N, K, ep, cs)
                             : launch_gemm_ws<256, 3, 7>(mA, mW, mO, M, N, K, ep, cs);
+      case 8:
+        return variant == 7   ? launch_gemm_ws<256, 4, 8, 2>(mA, mW, mO, M, N, K, ep, cs)
+               : variant == 5 ? launch_gemm_ws<256, 3, 8>(mA, mW, mO, M, N, K, ep, cs)
+               : variant == 4 ? launch_gemm_ws<128, 4, 8>(mA, mW, mO, M, N, K, ep, cs)
+                              : GVF_ERR_UNSUPPORTED;
       default: return GVF_ERR_INVALID;
     }
 #undef GVF_WS
@@ -1381,15 +1467,10 @@ extern "C" GVF_API int gvf_gemm_tn_f16(const void* A, int lda, const void* W, in
   const int BN = wide ? 256 : 128;
   const long long tiles = (long long)((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
   const int kblocks = (R + kBK - 1) / kBK;
-  int sms = 148;
-  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = sm_count();
   int ksplit = 1;
   if (g_gemm_ksplit > 0) ksplit = g_gemm_ksplit;
-  else if (g_gemm_ksplit == 0 && kblocks >= 16) {
-    ksplit = (int)((2 * sms + tiles - 1) / tiles);            // about two waves of work items
-    if (ksplit > kblocks / 4) ksplit = kblocks / 4;
-    if (ksplit < 1) ksplit = 1;
-  }
+  else if (g_gemm_ksplit == 0) ksplit = pick_ksplit(tiles, kblocks, sms);
   if (ksplit > 1) {
     const int per = (kblocks + ksplit - 1) / ksplit;
     ksplit = (kblocks + per - 1) / per;

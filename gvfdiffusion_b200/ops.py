@@ -12,6 +12,7 @@ from ._lib import check, current_stream, ptr
 
 F16, F32 = torch.float16, torch.float32
 EPI_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_RESID_F16, EPI_F32, EPI_F32_COMPACT = 0, 1, 2, 3, 4, 5
+EPI_GELU_BWD_F16 = 8          # out = fp16(acc) * gelu_tanh'(gate): gate = the saved fp16 pre-activation [M, N]
 
 
 def _ll(vals):
@@ -31,9 +32,14 @@ def gemm(a, w, bias=None, epilogue=EPI_F16, out=None, gate=None, gate_stride=0, 
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
     if out is None:
-        assert epilogue in (EPI_F16, EPI_GELU_F16, EPI_F32)
+        assert epilogue in (EPI_F16, EPI_GELU_F16, EPI_F32, EPI_GELU_BWD_F16)
         out = torch.empty((M, N), dtype=F32 if epilogue == EPI_F32 else F16, device=a.device)
     assert out.stride(1) == 1 and out.dtype == (F32 if epilogue in (EPI_RESID_F32, EPI_F32, EPI_F32_COMPACT) else F16)
+    if epilogue in (EPI_GELU_F16, EPI_GELU_BWD_F16) and gate is not None:
+        # GELU forward: `gate` RECEIVES the fp16 pre-activation; GELU backward: `gate` IS the saved pre-activation
+        _req(gate, F16, "gate")
+        assert gate.shape == (M, N) and gate.stride(1) == 1
+        gate_stride = gate.stride(0)
     st = _lib.lib().gvf_gemm_f16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
                                  ptr(out), out.stride(0), ptr(gate), gate_stride, rows_per_batch,
                                  current_stream())

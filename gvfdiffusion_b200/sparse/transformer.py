@@ -56,59 +56,74 @@ class SparseTransformerBlocks:
                 w1=h(state_dict[p + "mlp.mlp.0.weight"]), b1=b(state_dict[p + "mlp.mlp.0.bias"]),
                 w2=h(state_dict[p + "mlp.mlp.2.weight"]), b2=b(state_dict[p + "mlp.mlp.2.bias"])))
         self.C = self.blocks[0]["w_out"].shape[0]
+        self.F = self.blocks[0]["w1"].shape[0]
+        self._scr = None
         if self.C // num_heads != 64:
             raise NotImplementedError("windowed sparse attention is built for head dim 64 (768 / 12 on the shipped config)")
 
+    # ---------------------------------------------------------------------------------------- native driver
+    def _parts(self, coords):
+        """gvf_window_partition[2]: the un-shifted and the shifted window partition of `coords` (cached per tensor)."""
+        from .attention.windowed_attn import _partition
+        arr = (_lib.WindowPartition * 2)()
+        keep = []
+        for k, sh in enumerate((0, self.window // 2)):
+            fwd, _bwd, cu, max_len = _partition(coords, self.window, (sh,) * 3)
+            arr[k] = _lib.WindowPartition(ptr(fwd), ptr(cu), cu.shape[0] - 1, max_len)
+            keep += [fwd, cu]
+        return arr, keep
+
+    def _block_structs(self, grads=None):
+        """gvf_sparse_block[num_blocks] over the engine's weights (+ transposes and gradient views for the backward)."""
+        arr = (_lib.SparseBlock * len(self.blocks))()
+        for i, blk in enumerate(self.blocks):
+            vals = {n: ptr(blk[n]) for n in ("w_qkv", "w_out", "w1", "w2", "b_qkv", "b_out", "b1", "b2")}
+            if grads is not None:
+                vals.update({n + "_t": ptr(blk[n + "_t"]) for n in ("w_qkv", "w_out", "w1", "w2")})
+                vals.update({"g_" + n: ptr(t) for n, t in grads[i].items()})
+            arr[i] = _lib.SparseBlock(**vals)
+        return arr
+
+    def _scratch(self, T):
+        need = _lib.lib().gvf_sparse_trunk_scratch_bytes(T, self.C, self.H, self.F)
+        if self._scr is None or self._scr.numel() < need:
+            self._scr = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        return self._scr
+
     def forward(self, feats, coords):
-        """feats [T, C] fp32 CUDA, coords [T, 4] int32 CUDA (batch, x, y, z) -> [T, C] fp32 (fp16 with fp16_residual)."""
+        """feats [T, C] fp32 CUDA, coords [T, 4] int32 CUDA (batch, x, y, z) -> [T, C] fp32 (fp16 with fp16_residual).
+        One call into the native trunk driver (csrc/sparse_trunk.cu: seven launches per block)."""
         if not (feats.is_cuda and coords.is_cuda):
             raise ValueError("SparseTransformerBlocks runs on CUDA tensors only (no CPU fallback)")
-        T, C, H = feats.shape[0], self.C, self.H
+        T = feats.shape[0]
         X = feats.to(F16 if self.fp16_residual else F32).contiguous().clone()
-        epi = ops.EPI_RESID_F16 if self.fp16_residual else ops.EPI_RESID_F32
-        A16 = torch.empty((T, C), dtype=F16, device=self.dev)
-        QKV = torch.empty((T, 3 * C), dtype=F16, device=self.dev)
-        H1 = torch.empty((T, self.blocks[0]["w1"].shape[0]), dtype=F16, device=self.dev)
         coords = coords.int().contiguous()
-        for i, blk in enumerate(self.blocks):
-            shift = (self.window // 2 * (i % 2),) * 3
-            ops.ln_mod(X, out=A16)
-            ops.gemm(A16, blk["w_qkv"], blk["b_qkv"], ops.EPI_F16, out=QKV)
-            ao = sparse_windowed_scaled_dot_product_self_attention(QKV.view(T, 3, H, 64), coords, self.window, shift)
-            ops.gemm(ao.view(T, C), blk["w_out"], blk["b_out"], epi, out=X)
-            ops.ln_mod(X, out=A16)
-            ops.gemm(A16, blk["w1"], blk["b1"], ops.EPI_GELU_F16, out=H1)
-            ops.gemm(H1, blk["w2"], blk["b2"], epi, out=X)
+        parts, _keep = self._parts(coords)
+        scr = self._scratch(T)
+        check(_lib.lib().gvf_sparse_trunk_forward(self._block_structs(), len(self.blocks), T, self.C, self.H, self.F,
+                                                  int(self.fp16_residual), parts, ptr(X), None, 0, ptr(scr), scr.numel(), ptr(X),
+                                                  current_stream()), "gvf_sparse_trunk_forward")
         return X
 
     # ---------------------------------------------------------------------------------------- training (cfg 5)
     def forward_train(self, feats, coords):
-        """Same blocks, keeping what the backward needs (block inputs, LayerNorm outputs, QKV, attention output + LSE,
-        the MLP pre-activation).  The MLP runs fc1 -> fp16 -> GELU as two launches (autocast's order: the Linear result
-        is rounded to fp16 before the activation), the inference path fuses GELU into the fc1 epilogue.
+        """Same blocks, keeping what the backward needs (block inputs, LayerNorm outputs, QKV, attention output + LSE, the
+        MLP pre-activation and activation) in one arena (gvf_sparse_trunk_arena_bytes: ~25 KB per token and block).  GELU
+        stays in the fc1 epilogue, which also stores the fp16 pre-activation (autocast's rounding order).
         -> (X [T, C], saved)"""
         if not (feats.is_cuda and coords.is_cuda):
             raise ValueError("SparseTransformerBlocks runs on CUDA tensors only (no CPU fallback)")
-        T, C, H = feats.shape[0], self.C, self.H
-        X = feats.detach().to(F16 if self.fp16_residual else F32).contiguous()
-        epi = ops.EPI_RESID_F16 if self.fp16_residual else ops.EPI_RESID_F32
+        T, nb = feats.shape[0], len(self.blocks)
+        x_in = feats.detach().to(F16 if self.fp16_residual else F32).contiguous()
         coords = coords.int().contiguous()
-        saved = {"coords": coords, "blocks": []}
-        for i, blk in enumerate(self.blocks):
-            shift = (self.window // 2 * (i % 2),) * 3
-            A = ops.ln_mod(X)
-            QKV = ops.gemm(A, blk["w_qkv"], blk["b_qkv"], ops.EPI_F16)
-            AO, lse, part = windowed_attention_fwd_lse(QKV.view(T, 3, H, 64), coords, self.window, shift)
-            x1 = X.clone()
-            ops.gemm(AO.view(T, C), blk["w_out"], blk["b_out"], epi, out=x1)
-            A2 = ops.ln_mod(x1)
-            H0 = ops.gemm(A2, blk["w1"], blk["b1"], ops.EPI_F16)
-            Hg = ops.gelu_tanh(H0)
-            x2 = x1.clone()
-            ops.gemm(Hg, blk["w2"], blk["b2"], epi, out=x2)
-            saved["blocks"].append(dict(x0=X, A=A, QKV=QKV, AO=AO, lse=lse, part=part, x1=x1, A2=A2, H0=H0, Hg=Hg))
-            X = x2
-        return X, saved
+        parts, keep = self._parts(coords)
+        nbytes = _lib.lib().gvf_sparse_trunk_arena_bytes(T, self.C, self.H, self.F, nb, int(self.fp16_residual))
+        arena = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        X = torch.empty_like(x_in)
+        check(_lib.lib().gvf_sparse_trunk_forward(self._block_structs(), nb, T, self.C, self.H, self.F, int(self.fp16_residual),
+                                                  parts, ptr(x_in), ptr(arena), nbytes, None, 0, ptr(X), current_stream()),
+              "gvf_sparse_trunk_forward")
+        return X, {"coords": coords, "arena": arena, "parts": parts, "keep": keep, "T": T}
 
     def _transposed(self):
         if "w_qkv_t" not in self.blocks[0]:
@@ -119,37 +134,44 @@ class SparseTransformerBlocks:
 
     def backward(self, saved, dX):
         """dX [T, C] (gradient of forward_train's output) -> ({reference parameter name: fp32 gradient}, d feats fp16).
-        Per block, in reverse: fc2 dgrad / wgrad -> GELU' -> fc1 dgrad / wgrad -> LayerNorm backward (+ residual) ->
-        to_out dgrad / wgrad -> window attention backward -> to_qkv dgrad / wgrad -> LayerNorm backward (+ residual).
-        Activation gradients are fp16 (fp32 accumulation inside every kernel), parameter gradients fp32."""
-        T, C, H = dX.shape[0], self.C, self.H
+        Per block, in reverse (csrc/sparse_trunk.cu): fc2 dgrad with GELU' in its epilogue / wgrad -> fc1 dgrad / wgrad ->
+        LayerNorm backward (+ residual) -> to_out dgrad / wgrad -> window attention backward -> to_qkv dgrad / wgrad ->
+        LayerNorm backward (+ residual); bias gradients = one-launch column sums.  Activation gradients are fp16 (fp32
+        accumulation inside every kernel), parameter gradients fp32 views of one flat buffer."""
+        T, C, F_, nb = saved["T"], self.C, self.F, len(self.blocks)
         dx = dX.detach().to(F16).contiguous()
+        self._transposed()
+        shapes = (("w_qkv", (3 * C, C)), ("b_qkv", (3 * C,)), ("w_out", (C, C)), ("b_out", (C,)), ("w1", (F_, C)), ("b1", (F_,)),
+                  ("w2", (C, F_)), ("b2", (C,)))
+        per = sum(int(torch.Size(s).numel()) for _, s in shapes)
+        flat = torch.empty(nb * per, dtype=F32, device=self.dev)
+        grads, off = [], 0
+        for _ in range(nb):
+            d = {}
+            for n, s in shapes:
+                k = int(torch.Size(s).numel())
+                d[n] = flat[off:off + k].view(s)
+                off += k
+            grads.append(d)
+        scr = self._scratch(T)
+        ws = ops._reduce_ws(self.dev, _lib.lib().gvf_colsum_workspace_bytes(T, max(3 * C, F_), 0))
+        d_in = torch.empty((T, C), dtype=F16, device=self.dev)
+        arena = saved["arena"]
+        check(_lib.lib().gvf_sparse_trunk_backward(self._block_structs(grads), nb, T, C, self.H, F_, int(self.fp16_residual),
+                                                   saved["parts"], ptr(arena), arena.numel(), ptr(dx), ptr(scr), scr.numel(), ptr(ws),
+                                                   ws.numel() * 4, ptr(d_in), current_stream()), "gvf_sparse_trunk_backward")
+        names = {"w_qkv": "attn.to_qkv.weight", "b_qkv": "attn.to_qkv.bias", "w_out": "attn.to_out.weight", "b_out": "attn.to_out.bias",
+                 "w1": "mlp.mlp.0.weight", "b1": "mlp.mlp.0.bias", "w2": "mlp.mlp.2.weight", "b2": "mlp.mlp.2.bias"}
         g = {}
-        blocks = self._transposed()
-        for i in reversed(range(len(blocks))):
-            blk, s = blocks[i], saved["blocks"][i]
-            p = f"{self.prefix}{i}."
-            dHg = ops.gemm(dx, blk["w2_t"], None, ops.EPI_F16)
-            g[p + "mlp.mlp.2.weight"] = ops.gemm_tn(dx, s["Hg"])
-            g[p + "mlp.mlp.2.bias"] = ops.colsum(dx)
-            dH0 = ops.gelu_tanh_bwd(s["H0"], dHg)
-            dA2 = ops.gemm(dH0, blk["w1_t"], None, ops.EPI_F16)
-            g[p + "mlp.mlp.0.weight"] = ops.gemm_tn(dH0, s["A2"])
-            g[p + "mlp.mlp.0.bias"] = ops.colsum(dH0)
-            dx1 = ops.ln_bwd(s["x1"], dA2, dx)
-            dAO = ops.gemm(dx1, blk["w_out_t"], None, ops.EPI_F16)
-            g[p + "attn.to_out.weight"] = ops.gemm_tn(dx1, s["AO"].view(T, C))
-            g[p + "attn.to_out.bias"] = ops.colsum(dx1)
-            dQKV = windowed_attention_bwd(s["QKV"].view(T, 3, H, 64), s["AO"], dAO.view(T, H, 64), s["lse"], s["part"]).view(T, 3 * C)
-            dA = ops.gemm(dQKV, blk["w_qkv_t"], None, ops.EPI_F16)
-            gw, gb = ops.gemm_tn(dQKV, s["A"]), ops.colsum(dQKV)
+        for i, d in enumerate(grads):
             if self.qkv_perm is not None:                 # rows were permuted at load time: hand the gradient back in
                 inv = torch.empty_like(self.qkv_perm)     # the checkpoint's [H][3][d] order
                 inv[self.qkv_perm] = torch.arange(inv.numel())
-                gw, gb = gw[inv.to(gw.device)], gb[inv.to(gb.device)]
-            g[p + "attn.to_qkv.weight"], g[p + "attn.to_qkv.bias"] = gw, gb
-            dx = ops.ln_bwd(s["x0"], dA, dx1)
-        return g, dx
+                inv = inv.to(self.dev)
+                d["w_qkv"], d["b_qkv"] = d["w_qkv"][inv], d["b_qkv"][inv]
+            for n, t in d.items():
+                g[f"{self.prefix}{i}.{names[n]}"] = t
+        return g, d_in
 
 
 class SparseTransformerVAE:

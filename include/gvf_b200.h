@@ -193,7 +193,10 @@ GVF_API void gvf_attn_set_trace(void* device_buffer);
  *    out[m,n] += fp16(gate[m / rows_per_batch, n] * fp16(acc + bias)) (gate optional, fp16)
  *    | 3 fp16 residual: out = fp16(fp16(acc + bias) + out) | 4 fp32 store
  *    | 5 fp32 store of the fp16-rounded result into compact rows of ldo <= N columns (W rows
- *    padded to a multiple of 8, e.g. the VAE's Linear(768 -> 14)).
+ *    padded to a multiple of 8, e.g. the VAE's Linear(768 -> 14))
+ *    | 8 GELU(tanh) backward: out = fp16(fp16(acc) * gelu'(gate[m, n])), gate = the saved fp16 pre-activation
+ *    [M, gate_stride] (the dgrad of an MLP's second Linear with the activation's derivative applied in place).
+ *    Epilogue 1 with gate != NULL additionally stores the fp16 pre-activation there (training forward).
  * ---------------------------------------------------------------------------------- */
 GVF_API int gvf_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                          int epilogue, const float* bias, void* out, int ldo, const void* gate,
@@ -364,6 +367,36 @@ GVF_API int gvf_sparse_varlen_attn_lse_f16(const void* qkv, void* out, float* ls
 GVF_API int gvf_sparse_varlen_attn_bwd_f16(const void* qkv, const void* o, const void* dout, const float* lse2, float* dsum,
                                            void* dqkv, const int* gather_idx, const int* cu_seqlens, int num_seqs,
                                            int max_seqlen, long long T, int H, int D, float scale, void* stream);
+
+/* Native driver of a stack of un-modulated SparseTransformerBlocks (reference sparse_transformer.py:126-192 stacked at
+ * sparse_transformer_vae.py:55-91; block i uses partition parts[i % 2] = un-shifted / shifted windows): the whole launch
+ * sequence of the static VAE's encoder or decoder trunk behind one call (csrc/sparse_trunk.cu), so that a 4096-token training
+ * step is not bound by per-launch host overhead.  T tokens, C = 64 H channels, F = MLP width; residual stream fp16
+ * (use_fp16) or fp32.  All pointers are device pointers except `blocks` and `parts` (host arrays). */
+typedef struct gvf_sparse_block {
+  const void *w_qkv, *w_out, *w1, *w2;             /* fp16 [3C,C] ([3][H][d] rows), [C,C], [F,C], [C,F] */
+  const float *b_qkv, *b_out, *b1, *b2;            /* fp32 */
+  const void *w_qkv_t, *w_out_t, *w1_t, *w2_t;     /* fp16 transposes [C,3C], [C,C], [C,F], [F,C] (backward only) */
+  float *g_w_qkv, *g_b_qkv, *g_w_out, *g_b_out, *g_w1, *g_b1, *g_w2, *g_b2;   /* fp32 gradient outputs (backward only) */
+} gvf_sparse_block;
+typedef struct gvf_window_partition {
+  const int* fwd_idx;                              /* [T] token rows ordered by window */
+  const int* cu_seqlens;                           /* [num_windows + 1] */
+  int num_windows, max_seqlen;
+} gvf_window_partition;
+GVF_API size_t gvf_sparse_trunk_arena_bytes(int T, int C, int H, int F, int num_blocks, int fp16_residual);
+GVF_API size_t gvf_sparse_trunk_scratch_bytes(int T, int C, int H, int F);
+/* x_out = blocks(x_in) ([T, C] in the residual dtype).  arena != NULL: training forward, every activation the backward
+ * needs is kept there (gvf_sparse_trunk_arena_bytes); arena == NULL: inference, `scratch` holds the temporaries. */
+GVF_API int gvf_sparse_trunk_forward(const gvf_sparse_block* blocks, int num_blocks, int T, int C, int H, int F,
+                                     int fp16_residual, const gvf_window_partition* parts, const void* x_in, void* arena,
+                                     size_t arena_bytes, void* scratch, size_t scratch_bytes, void* x_out, void* stream);
+/* d_out fp16 [T, C] (gradient of x_out) -> d_in fp16 [T, C] and every g_* of `blocks`; reduce_ws: gvf_colsum scratch
+ * for [T, 3C]. */
+GVF_API int gvf_sparse_trunk_backward(const gvf_sparse_block* blocks, int num_blocks, int T, int C, int H, int F,
+                                      int fp16_residual, const gvf_window_partition* parts, const void* arena,
+                                      size_t arena_bytes, const void* d_out, void* scratch, size_t scratch_bytes,
+                                      float* reduce_ws, size_t reduce_ws_bytes, void* d_in, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * 7. Training-step losses (BASELINE configs[4]).

@@ -204,7 +204,40 @@ def test_gemm_tn_weight_gradient(R, M, N):
     dy = _rand((R, M), g, 0.5).half()
     x = _rand((R, N), g, 0.5).half()
     ref = dy.float().T @ x.float()
-    assert _rel(ops.gemm_tn(dy, x), ref) < 5e-5
+    err = _rel(ops.gemm_tn(dy, x), ref)
+    assert err < 5e-5, err
     if M >= 16:
         sub = dy[:, M // 2:]
         assert _rel(ops.gemm_tn(sub, x), sub.float().T @ x.float()) < 5e-5
+
+
+def test_colsum_single_launch_form_and_gelu_epilogues():
+    """The one-launch fp16 column sum (ticketed last-CTA reduction, N % 8 == 0) repeated on the same buffers, and the GELU
+    epilogues of the MLP: forward with the pre-activation kept (epilogue 1 + side output), backward fused into the dgrad GEMM
+    (epilogue 8) against the two-pass kernels and torch."""
+    from gvfdiffusion_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    for M, N in ((4096, 768), (5000, 2304), (257, 3072), (12288, 8)):
+        x = _rand((M, N), g).half()
+        ref = x.double().sum(0)
+        for _ in range(3):                                        # the ticket counters reset themselves
+            got = ops.colsum(x)
+            assert torch.allclose(got.double(), ref, rtol=1e-5, atol=2e-3)
+        assert torch.equal(ops.colsum(x), got)                    # deterministic
+    xs = _rand((3000, 2304), g).half()[:, 768:1536]
+    assert torch.allclose(ops.colsum(xs).double(), xs.double().sum(0), rtol=1e-5, atol=2e-3)
+    M, K, N = 1000, 768, 3072
+    a, w = (_rand((M, K), g) * 0.5).half(), (_rand((N, K), g) * 0.05).half()
+    b = _rand((N,), g).half().float()
+    h0 = torch.empty((M, N), dtype=torch.float16, device=DEV)
+    hg = ops.gemm(a, w, b, ops.EPI_GELU_F16, gate=h0)
+    assert torch.equal(h0, ops.gemm(a, w, b, ops.EPI_F16))
+    assert torch.equal(hg, ops.gemm(a, w, b, ops.EPI_GELU_F16)) and torch.equal(hg, ops.gelu_tanh(h0))
+    dy = _rand((M, K), g).half()
+    # w [N, K] in the role of fc2's transposed weight: d hg [M, N] = dy [M, K] @ w^T, then GELU'(h0)
+    fused = ops.gemm(dy, w, None, ops.EPI_GELU_BWD_F16, gate=h0)
+    two = ops.gelu_tanh_bwd(h0, ops.gemm(dy, w, None, ops.EPI_F16))
+    assert _rel(fused, two) < 1e-3
+    hr = h0.float().requires_grad_(True)
+    F.gelu(hr, approximate="tanh").backward(dy.float() @ w.float().t())
+    assert _rel(fused, hr.grad) < 2e-3
