@@ -53,6 +53,14 @@ def pack_cameras(extrinsics, intrinsics, near, far):
     return cams.contiguous(), tanfovx, tanfovy
 
 
+def to_device_async(t, device):
+    """Host tensor -> device through pinned memory without synchronising the stream (torch's blocking H2D copy waits for
+    everything enqueued before it).  Device tensors pass through."""
+    if t.is_cuda:
+        return t
+    return t.contiguous().pin_memory().to(device, non_blocking=True)
+
+
 def make_params(H, W, tanfovx, tanfovy, const=None, kernel_size=0.1, scale_modifier=1.0,
                 bg=(1.0, 1.0, 1.0), mip_filter=True):
     p = _lib.RasterParams()
@@ -208,14 +216,21 @@ def rgba_to_u8(rgba, out=None):
 
 
 class RasterizeFrames(torch.autograd.Function):
-    """autograd node: (raw canonical tensors, delta) -> RGBA for F frames (train_vae.py:313-334)."""
+    """autograd node: (raw canonical tensors, delta) -> RGBA for F frames (train_vae.py:313-334).
+
+    The tile-instance overflow check of the forward is DEFERRED to the backward (one event wait there instead of a blocking
+    status read-back per render, which would stop the host from enqueueing the rest of the step): if the forward did
+    overflow its workspace, the backward re-renders into a workspace that fits -- its gradients are those of the complete
+    image -- and warns that the image handed to the loss in this step was missing splats; the next forward starts from the
+    grown capacity."""
 
     @staticmethod
     def forward(ctx, rz, prm, cams, xyz, dc, scaling, rotation, opacity, delta):
         arrays = tuple(t.detach().contiguous() for t in (xyz, dc, scaling, rotation, opacity))
         d = None if delta is None else delta.detach().contiguous()
         parent, rz = rz, rz.node()                 # per-node workspace, kept alive by ctx until backward
-        rgba, radii = rz.forward(prm, arrays, d, cams)
+        rgba, radii = rz.forward(prm, arrays, d, cams, check_overflow="defer")
+        ctx.parent = parent
         parent.hint = max(parent.hint, rz.cap)
         ctx.rz, ctx.prm, ctx.cams, ctx.arrays, ctx.delta = rz, prm, cams, arrays, d
         ctx.shapes = [t.shape for t in (xyz, dc, scaling, rotation, opacity)]
@@ -224,6 +239,13 @@ class RasterizeFrames(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rgba, _g_radii):
+        st = ctx.rz.deferred_status()
+        if st is not None and st[1]:
+            import warnings
+            warnings.warn(f"rasteriser workspace overflow in the forward of this step ({st[0]} tile instances > capacity "
+                          f"{ctx.rz.cap}): re-rendered for the backward; the loss saw an image with splats missing")
+            ctx.rz.forward(ctx.prm, ctx.arrays, ctx.delta, ctx.cams, check_overflow=True)
+            ctx.parent.hint = max(ctx.parent.hint, ctx.rz.cap)
         outs, gdelta, _ = ctx.rz.backward(ctx.prm, ctx.arrays, ctx.delta, ctx.cams, g_rgba,
                                           want_delta_grad=ctx.delta is not None)
         outs = [o.reshape(s) for o, s in zip(outs, ctx.shapes)]

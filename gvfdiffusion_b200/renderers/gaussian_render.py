@@ -48,8 +48,10 @@ class GaussianRenderer:
         dev = gausssian._xyz.device
         res = int(opt["resolution"]) * int(opt["ssaa"])        # ssaa > 1: rendered large, reduced by render()
         bg = self._bg()
-        self.bg_color = torch.tensor(bg, dtype=torch.float32, device=dev)
+        from ..representations.gaussian.gaussian_model import _device_const
+        self.bg_color = _device_const(bg, dev)
         cams, tfx, tfy = R.pack_cameras(extrinsics, intrinsics, opt["near"], opt["far"])
+        cams = R.to_device_async(cams, dev)
         prm = R.make_params(res, res, tfx, tfy, gausssian.constants(), self.pipe.kernel_size if mip else 0.3,
                             self.pipe.scale_modifier, bg, mip_filter=mip)
         if self._rz is None:

@@ -10,6 +10,20 @@ from ... import ops
 from ... import raster as R
 
 
+_CONST_CACHE = {}
+
+
+def _device_const(values, device):
+    """Small constant tensors (aabb, ...) built once per (values, device): torch.tensor(..., device='cuda') is a blocking
+    host-to-device copy, i.e. a stream synchronisation per GaussianModel otherwise."""
+    key = (tuple(float(v) for v in values), str(device))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(key[0], dtype=torch.float32, device=device)
+        _CONST_CACHE[key] = t
+    return t
+
+
 class GaussianModel:
     def __init__(self, sh_degree: int = 0, aabb=(-0.5, -0.5, -0.5, 1.0, 1.0, 1.0), mininum_kernel_size: float = 0.0,
                  scaling_bias: float = 0.01, opacity_bias: float = 0.1, scaling_activation: str = "exp",
@@ -21,18 +35,31 @@ class GaussianModel:
         self.scaling_bias, self.opacity_bias = scaling_bias, opacity_bias
         self.scaling_activation_type = scaling_activation
         self.device = device
-        self.aabb = torch.tensor(aabb, dtype=torch.float32, device=device)
+        self._aabb = _device_const(aabb, device)
+        self._aabb_host = tuple(float(a) for a in aabb)     # constants() must not read the device tensor back
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
         self._xyz, self._features_dc, self._scaling = z(8, 3), z(8, 1, 3), z(8, 3)
         self._rotation, self._opacity = z(8, 4), z(8, 1)
         # setup_functions (:23-41): biases exactly as the reference derives them (fp32 torch scalars)
-        x = torch.tensor(scaling_bias)
-        sb = (x + torch.log(-torch.expm1(-x))) if scaling_activation == "softplus" else torch.log(x)
-        p = torch.tensor(opacity_bias)
-        self.scale_bias, self.opacity_logit_bias = float(sb), float(torch.log(p / (1 - p)))
+        key = ("bias", float(scaling_bias), float(opacity_bias), scaling_activation)
+        if key not in _CONST_CACHE:
+            x = torch.tensor(scaling_bias)
+            sb = (x + torch.log(-torch.expm1(-x))) if scaling_activation == "softplus" else torch.log(x)
+            p = torch.tensor(opacity_bias)
+            _CONST_CACHE[key] = (float(sb), float(torch.log(p / (1 - p))))
+        self.scale_bias, self.opacity_logit_bias = _CONST_CACHE[key]
+
+    @property
+    def aabb(self):
+        return self._aabb
+
+    @aabb.setter
+    def aabb(self, value):                                  # assigning a new box re-reads it once
+        self._aabb = value
+        self._aabb_host = tuple(float(a) for a in value.tolist())
 
     def constants(self):
-        return {"aabb": tuple(float(a) for a in self.aabb.tolist()), "scale_bias": self.scale_bias,
+        return {"aabb": self._aabb_host, "scale_bias": self.scale_bias,
                 "min_kernel": float(self.mininum_kernel_size), "opacity_bias": self.opacity_logit_bias,
                 "softplus": self.scaling_activation_type == "softplus"}
 

@@ -66,8 +66,10 @@ def build(dev, seed=0):
     g = torch.Generator().manual_seed(seed + 9)
     feats = torch.randn(coords.shape[0], CIN, generator=g).to(dev)
     noise = torch.randn(coords.shape[0], LAT, generator=g).to(dev)
-    ext = S.orbit_extrinsics(BATCH, radius=1.2).to(dev)
-    intr = S.intrinsics(40.0).to(dev)[None].repeat(BATCH, 1, 1)
+    # cameras stay host tensors, as a data loader hands them over: the renderer packs them on the host and uploads the
+    # 32 floats per view through pinned memory (device-resident intrinsics would cost a blocking read-back per render)
+    ext = S.orbit_extrinsics(BATCH, radius=1.2)
+    intr = S.intrinsics(40.0)[None].repeat(BATCH, 1, 1)
     x = SparseTensor(feats, coords)
     with torch.no_grad():                                   # target: the render of a perturbed posterior draw
         fw.renderers["MipGS"].rendering_options.resolution = RES_IMG
