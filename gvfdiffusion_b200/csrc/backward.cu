@@ -209,6 +209,47 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __half* __restrict
   *reinterpret_cast<uint4*>(dh + row * 2 * F + F + c) = *reinterpret_cast<uint4*>(og);
 }
 
+// ------------------------------------------------------------------------------------------------ get_gaussian_tensor
+// Backward of gvf_gaussian_tensor (reference train_vae.py:466-472 under autograd: the activated canonical Gaussians are
+// the motion VAE's decoder queries, so the deformation losses reach the static VAE through them).  g [P, 14] =
+// [xyz3 | rgb3 | opacity1 | scale3 | rot4] -> gradients of the raw tensors.
+__global__ void __launch_bounds__(256) gaussian_tensor_bwd_kernel(const gvf_raster_params prm, int P,
+                                                                  const float* __restrict__ scaling,
+                                                                  const float* __restrict__ rotation,
+                                                                  const float* __restrict__ opacity,
+                                                                  const float* __restrict__ g, float* __restrict__ d_xyz,
+                                                                  float* __restrict__ d_dc, float* __restrict__ d_scaling,
+                                                                  float* __restrict__ d_rotation,
+                                                                  float* __restrict__ d_opacity) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float* gi = g + (size_t)i * 14;
+  const float k2 = prm.min_kernel * prm.min_kernel;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    d_xyz[(size_t)i * 3 + c] = gi[c] * prm.aabb[3 + c];
+    d_dc[(size_t)i * 3 + c] = gi[3 + c];
+    const float r = scaling[(size_t)i * 3 + c] + prm.scale_bias;
+    // s = softplus(r) | exp(r);  ds/dr = sigmoid(r) | s;  out = sqrt(s^2 + k2): d out / ds = s / out
+    const float s = prm.softplus ? (r > 20.f ? r : log1pf(expf(r))) : expf(r);
+    const float ds = prm.softplus ? 1.0f / (1.0f + expf(-r)) : s;
+    const float o = sqrtf(s * s + k2);
+    d_scaling[(size_t)i * 3 + c] = gi[7 + c] * (o > 0.f ? s / o : 0.f) * ds;
+  }
+  const float op = 1.0f / (1.0f + expf(-(opacity[i] + prm.opacity_bias)));
+  d_opacity[i] = gi[6] * op * (1.0f - op);
+  float q[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) q[c] = rotation[(size_t)i * 4 + c] + (c == 0 ? 1.0f : 0.0f);
+  const float n = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+  float dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dot += gi[10 + c] * q[c];
+  // y = q / n:  dq = (g - y (g . y)) / n
+#pragma unroll
+  for (int c = 0; c < 4; ++c) d_rotation[(size_t)i * 4 + c] = (gi[10 + c] - q[c] * dot / (n * n)) / n;
+}
+
 // ------------------------------------------------------------------------------------------------ GELU (tanh)
 // The sparse trunk's MLP (sparse_transformer.py: nn.GELU(approximate="tanh")).  Inference fuses it into the fc1 epilogue;
 // the training forward keeps the pre-activation and applies the same tanh.approx form here.
@@ -595,6 +636,16 @@ GVF_API int gvf_geglu_bwd_f16(const void* h, const void* dG, long long M, int F,
   const long long n8 = M * (F / 8);
   geglu_bwd_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)h, (const __half*)dG, M, F,
                                                                         (__half*)dh);
+  RET();
+}
+
+GVF_API int gvf_gaussian_tensor_bwd(const gvf_raster_params* prm, int P, const float* scaling, const float* rotation,
+                                    const float* opacity, const float* g, float* d_xyz, float* d_dc, float* d_scaling,
+                                    float* d_rotation, float* d_opacity, void* stream) {
+  if (!prm || !scaling || !rotation || !opacity || !g || !d_xyz || !d_dc || !d_scaling || !d_rotation || !d_opacity || P <= 0)
+    return GVF_ERR_INVALID;
+  gaussian_tensor_bwd_kernel<<<(P + 255) / 256, 256, 0, ST(stream)>>>(*prm, P, scaling, rotation, opacity, g, d_xyz, d_dc,
+                                                                     d_scaling, d_rotation, d_opacity);
   RET();
 }
 

@@ -177,9 +177,10 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
             o = self.encode_engine().encode(static_pc, delta_pc, static_gs_list, noise)
         return o["kl"], o["x"], {"mean": o["mean"], "logvar": o["logvar"]}, o["sampled_static_gs"]
 
-    def forward(self, static_gs, static_pc, delta_pc):
-        """model/autoencoder.py:620-627: encode -> pad_static_gs -> decode."""
+    def forward(self, static_gs, static_pc, delta_pc, noise=None):
+        """model/autoencoder.py:620-627: encode -> pad_static_gs -> decode.  noise: the posterior's randn draw (the
+        reference draws it on the host, :316; a device tensor here avoids that blocking copy)."""
         from ..pipeline import pad_static_gs
-        kl, x, posterior, _ = self.encode(static_pc, delta_pc, static_gs)
+        kl, x, posterior, _ = self.encode(static_pc, delta_pc, static_gs, noise)
         padded, _ = pad_static_gs([g.to(x.device) for g in static_gs])
         return {"logits": self.decode(x, padded), "kl": kl, "posterior": posterior}

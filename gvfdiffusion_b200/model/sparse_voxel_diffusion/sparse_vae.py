@@ -131,8 +131,12 @@ class SparseVAE:
 
     def _backbone_forward(self, feats, noise=None):
         """`self.backbones['vae'](feats)` of :318 -> (out [Nvox, out_channels], kl, mean, logvar), out and kl on the graph."""
-        from ...sparse.transformer import sparse_vae_forward_autograd
-        return sparse_vae_forward_autograd(self.backbones["vae"], feats.feats, feats.coords, noise)
+        vae = self.backbones["vae"]
+        if isinstance(vae, torch.nn.Module):             # the nn.Module mirror: parameter gradients through autograd
+            out, mean, logvar = vae(feats, mem_ratio=self.mem_ratio, noise=noise)
+            return out.feats, vae.kl, mean, logvar
+        from ...sparse.transformer import sparse_vae_forward_autograd     # bare engine: gradients on engine.grads
+        return sparse_vae_forward_autograd(vae, feats.feats, feats.coords, noise)
 
     def training_losses(self, feats, image, extrinsics, intrinsics, return_aux=False, noise=None, **kwargs):
         """feats: SparseTensor [Nvox, in_channels]; image [N,3,H,W]; extrinsics [N,4,4]; intrinsics [N,3,3] ->

@@ -266,6 +266,27 @@ def gaussian_tensor(prm, arrays):
     return out
 
 
+class GaussianTensorFn(torch.autograd.Function):
+    """`gaussian_tensor` under autograd (forward gvf_gaussian_tensor, backward gvf_gaussian_tensor_bwd)."""
+
+    @staticmethod
+    def forward(ctx, prm, xyz, dc, scaling, rotation, opacity):
+        arrays = [t.detach().to(F32).contiguous() for t in (xyz, dc, scaling, rotation, opacity)]
+        ctx.prm, ctx.shapes = prm, [t.shape for t in (xyz, dc, scaling, rotation, opacity)]
+        ctx.save_for_backward(arrays[2], arrays[3], arrays[4])
+        return gaussian_tensor(prm, arrays)
+
+    @staticmethod
+    def backward(ctx, g):
+        scaling, rotation, opacity = ctx.saved_tensors
+        P = scaling.shape[0]
+        g = g.to(F32).contiguous()
+        outs = [torch.empty(s, dtype=F32, device=g.device) for s in ctx.shapes]
+        check(_lib.lib().gvf_gaussian_tensor_bwd(C.byref(ctx.prm), P, ptr(scaling), ptr(rotation), ptr(opacity), ptr(g),
+                                                 *[ptr(o) for o in outs], current_stream()), "gvf_gaussian_tensor_bwd")
+        return (None, *outs)
+
+
 def fps(points, K, start=0):
     """points [P, >=3] fp32 (xyz first) -> int32 indices [K] of a farthest point sample."""
     _req(points, F32, "points")

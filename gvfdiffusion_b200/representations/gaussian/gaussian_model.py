@@ -80,7 +80,13 @@ class GaussianModel:
     def gaussian_tensor(self):
         """[P,14] = [xyz3 | rgb3 | opacity1 | scale3 | rot4] (train_vae.py:466-472)."""
         prm = R.make_params(16, 16, 1.0, 1.0, self.constants())
-        return ops.gaussian_tensor(prm, R.canon_arrays(self.raw(), self._xyz.device))
+        raw = self.raw()
+        if torch.is_grad_enabled() and any(t.requires_grad for t in raw.values()):
+            P = raw["_xyz"].shape[0]                     # training: the queries carry gradients back to the static VAE
+            return ops.GaussianTensorFn.apply(prm, raw["_xyz"].reshape(P, 3), raw["_features_dc"].reshape(P, 3),
+                                              raw["_scaling"].reshape(P, 3), raw["_rotation"].reshape(P, 4),
+                                              raw["_opacity"].reshape(P))
+        return ops.gaussian_tensor(prm, R.canon_arrays(raw, self._xyz.device))
 
     @property
     def get_xyz(self):

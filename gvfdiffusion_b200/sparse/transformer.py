@@ -61,6 +61,27 @@ class SparseTransformerBlocks:
         if self.C // num_heads != 64:
             raise NotImplementedError("windowed sparse attention is built for head dim 64 (768 / 12 on the shipped config)")
 
+    def refresh(self, state_dict):
+        """New parameter values into the SAME device buffers (after an optimiser step): one foreach cast for the fp16
+        weights, one for the fp16-valued fp32 biases, and the transposes of the backward if they exist."""
+        dst_w, src_w, dst_b, src_b = [], [], [], []
+        for i, blk in enumerate(self.blocks):
+            p = f"{self.prefix}{i}."
+            for n, key in (("w_qkv", "attn.to_qkv"), ("w_out", "attn.to_out"), ("w1", "mlp.mlp.0"), ("w2", "mlp.mlp.2")):
+                w, b = state_dict[p + key + ".weight"], state_dict[p + key + ".bias"]
+                if n == "w_qkv" and self.qkv_perm is not None:
+                    perm = self.qkv_perm.to(w.device)
+                    w, b = w[perm], b[perm]
+                dst_w.append(blk[n]); src_w.append(w)
+                dst_b.append(blk["b" + n[1:]]); src_b.append(b)
+        with torch.no_grad():
+            torch._foreach_copy_(dst_w, src_w)
+            torch._foreach_copy_(dst_b, [b.to(F16) for b in src_b])
+            if "w_qkv_t" in self.blocks[0]:
+                for blk in self.blocks:
+                    for n in ("w_qkv", "w_out", "w1", "w2"):
+                        ops.transpose(blk[n], out=blk[n + "_t"])
+
     # ---------------------------------------------------------------------------------------- native driver
     def _parts(self, coords):
         """gvf_window_partition[2]: the un-shifted and the shifted window partition of `coords` (cached per tensor)."""
@@ -195,6 +216,20 @@ class SparseTransformerVAE:
                                                     use_old_attn_impl=use_old_attn_impl)
         self.encoder = mk("encoder.") if "encoder.0.attn.to_qkv.weight" in sd else None
         self.decoder = mk("decoder.") if "decoder.0.attn.to_qkv.weight" in sd else None
+
+    def refresh(self, state_dict):
+        """In-place update of every device copy from new parameter values (see SparseTransformerBlocks.refresh)."""
+        with torch.no_grad():
+            for n in ("input_layer", "to_latent", "from_latent", "out_layer"):
+                if n in self.lin:
+                    w, b = self.lin[n]
+                    w.copy_(state_dict[n + ".weight"])
+                    b.copy_(state_dict[n + ".bias"].to(F16))
+                    if n + "_t" in self.lin:
+                        ops.transpose(w, out=self.lin[n + "_t"])
+        for blocks in (self.encoder, self.decoder):
+            if blocks is not None:
+                blocks.refresh(state_dict)
 
     def _linear(self, name, x, add=None):
         """nn.Linear under autocast: fp16 operands, fp16-rounded result returned as fp32 (+ fp32 `add` rows)."""

@@ -154,6 +154,11 @@ GVF_API int gvf_raster_backward(const gvf_raster_params* prm, int F, int P, int 
 GVF_API int gvf_gaussian_tensor(const gvf_raster_params* prm, int P, const float* xyz, const float* dc,
                                 const float* scaling, const float* rotation, const float* opacity,
                                 float* out, void* stream);
+/* Backward of gvf_gaussian_tensor: g [P, 14] -> gradients of the raw tensors (train_vae.py:285-293 back-propagates the
+ * deformation losses into the static VAE through the activated Gaussians it hands to the motion VAE as queries). */
+GVF_API int gvf_gaussian_tensor_bwd(const gvf_raster_params* prm, int P, const float* scaling, const float* rotation,
+                                    const float* opacity, const float* g, float* d_xyz, float* d_dc, float* d_scaling,
+                                    float* d_rotation, float* d_opacity, void* stream);
 /* Farthest point sampling of K of P points (rows of `ld` floats, xyz first) -- replaces
  * torch_cluster.fps in sample_gs (reference utils/inference_utils.py:180-198).  Deterministic
  * (starts at `start`, ties -> lowest index).  workspace: P floats.  out_idx: K int32. */

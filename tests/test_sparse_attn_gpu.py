@@ -238,3 +238,44 @@ def test_sparse_vae_full_train_step_gradients_match_autograd():
     errs = {k: rel(grads[k], sdr[k].grad) for k in sd}
     worst = max(errs.items(), key=lambda kv: kv[1])
     assert worst[1] < 1.5e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_sparse_transformer_vae_module_trains_and_refreshes_in_place():
+    """The nn.Module mirror (reference constructor / parameter names): autograd delivers the same parameter gradients as
+    the engine-level step; after an optimiser step the engine's fp16 copies and transposes are refreshed IN PLACE and the
+    next forward equals a freshly built engine on the new weights."""
+    from gvfdiffusion_b200.model.sparse_voxel_diffusion import SparseTransformerVAE
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from gvfdiffusion_b200.sparse.transformer import SparseTransformerVAE as Engine
+    torch.manual_seed(5)
+    m = SparseTransformerVAE(64, 64, 128, 24, 8, 2, window_size=8, use_fp16=True, use_old_attn_impl=False, norm_output=True).to(DEV)
+    assert "encoder.1.mlp.mlp.2.weight" in m.state_dict() and "to_latent.bias" in m.state_dict()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.startswith(("to_latent", "out_layer")) and n.endswith("weight"):
+                p.normal_(0, 0.05)
+    coords = _voxels(400, 32, 2, seed=3).to(DEV)
+    g = torch.Generator().manual_seed(8)
+    x = SparseTensor(torch.randn(800, 64, generator=g).to(DEV), coords)
+    noise, dout = torch.randn(800, 8, generator=g).to(DEV), torch.randn(800, 24, generator=g).to(DEV)
+    out, mean, logvar = m(x, noise=noise)
+    ((out.feats * dout).sum() + 0.3 * m.kl).backward()
+    eng = Engine({k: v.detach() for k, v in m.state_dict().items()}, 2, 2, 8, use_fp16=True, norm_output=True, device=DEV)
+    o2, _, _, kl2, saved = eng.forward_train(x.feats, coords, noise)
+    g2 = eng.backward(saved, dout, torch.tensor(0.3, device=DEV))
+    assert torch.equal(out.feats, o2)
+    rl = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-20))
+    for n, p in m.named_parameters():          # split-K partial tiles are summed by TMA reduce-add in arrival order
+        assert p.grad is not None and rl(p.grad, g2[n]) < 1e-5, n
+    ptr0 = m.engine().decoder.blocks[0]["w_qkv"].data_ptr()
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    opt.step()
+    out3, _, _ = m(x, noise=noise)                                     # refreshes the engine in place
+    assert m.engine().decoder.blocks[0]["w_qkv"].data_ptr() == ptr0
+    eng3 = Engine({k: v.detach() for k, v in m.state_dict().items()}, 2, 2, 8, use_fp16=True, norm_output=True, device=DEV)
+    o4, _, _, _, sv4 = eng3.forward_train(x.feats, coords, noise)
+    assert torch.equal(out3.feats, o4) and not torch.equal(out3.feats, out.feats)
+    (out3.feats * dout).sum().backward()                                # transposes refreshed too: same gradients
+    g4 = eng3.backward(sv4, dout, None)
+    p = dict(m.named_parameters())["decoder.0.attn.to_qkv.weight"]
+    assert rl(p.grad - g2["decoder.0.attn.to_qkv.weight"], g4["decoder.0.attn.to_qkv.weight"]) < 1e-4

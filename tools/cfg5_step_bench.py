@@ -1,0 +1,175 @@
+"""BASELINE configs[4]: "main_vae.py train step (L1 + LPIPS + SSIM render loss), bs = 2 per GPU, DDP".
+
+One step = reference train_vae.py:263-375 (`forward_backward` + `optimize`) on synthetic data of the shipped shapes:
+
+  static VAE   SparseVAE.training_losses: 2 objects x 2048 voxels x 1024 features -> SparseTransformerVAE (12 + 12 swin
+               blocks, 768 ch) -> to_representation (16384 Gaussians / object) -> one 512^2 render each -> L1 + 0.2 (1 - SSIM)
+               + 1e-6 KL + volume / opacity regularisers
+  motion VAE   get_gaussian_tensor (differentiable) -> GSKLTemporalVariationalAutoEncoder.forward: encode (FPS, KNN
+               interpolation, cross attention, KL) + decode (12 layers, 24 x 512 latents, 16384 queries / object)
+  losses       + 1e-5 KL + 0.1 x interpolation (xyz) loss (KNN 8) + 24 frames x 2 objects rendered at 512^2 with the predicted
+               deltas (gradients to the deltas AND the canonical Gaussians) -> L1 + 0.2 (1 - SSIM)
+  backward     through everything above into both models (loss scale 2^16, fp16 activation gradients, fp32 parameter grads)
+  optimize     [DDP: one flat NCCL all-reduce of all gradients] -> un-scale -> clip_grad_norm 1.0 over both models -> AdamW
+               (lr, 0.1 lr) -> EMA 0.9999 of both models; the engines' fp16 weight copies are refreshed from the fp32
+               masters at the next forward (inside the timed steps, which run back to back)
+
+LPIPS (VGG16; its weights are a network download) is the one term left out.  Timed with CUDA events over whole steps.
+
+    python tools/cfg5_step_bench.py [--steps 5]         -> one JSON line
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+LOSS_SCALE = 65536.0
+KL_W, XYZ_W, L1_W, SSIM_W, KNN_K, BETA, LR, EMA = 1e-5, 0.1, 1.0, 0.2, 8, 7.0, 1e-4, 0.9999
+N_PC = 8192
+
+
+def build(dev, seed=0):
+    import bench as BN
+    from gvfdiffusion_b200 import synthetic as S
+    from gvfdiffusion_b200.model.sparse_voxel_diffusion import SparseTransformerVAE, SparseVAE
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from tools import static_vae_step_bench as SB
+    B, T = SB.BATCH, BN.T_FRAMES
+    torch.manual_seed(seed)
+    static = SparseTransformerVAE(SB.RES_GRID, SB.CIN, SB.C, SB.COUT, SB.LAT, SB.NB, window_size=SB.WIN, use_fp16=True,
+                                  use_old_attn_impl=False, norm_output=True)
+    static.load_state_dict(SB.state_dict(seed))                       # random init incl. the zero-initialised output layers
+    static = static.to(dev).train()
+    _, vae = BN.build_models(dev, seed=seed)
+    vae.train()
+    fw = SparseVAE({"vae": static}, resolution=SB.RES_GRID, representation_config=SB.REP, device=dev, lambda_ssim=0.2,
+                   lambda_lpips=0.0, lamda_kl=1e-6, regularizations=SB.REG)
+    coords = torch.cat([torch.cat([torch.full((SB.NVOX, 1), b), SB.surface_voxels(seed + 1 + b)], 1) for b in range(B)]).int().to(dev)
+    g = torch.Generator().manual_seed(seed + 9)
+    x = SparseTensor(torch.randn(coords.shape[0], SB.CIN, generator=g).to(dev), coords)
+    ext_s, intr_s = S.orbit_extrinsics(B, radius=1.2), S.intrinsics(40.0)[None].repeat(B, 1, 1)
+    ext = torch.stack([S.orbit_extrinsics(T, radius=1.2) for _ in range(B)])           # [B, T, 4, 4], host
+    intr = S.intrinsics(40.0)
+    # tracked points: N_PC voxel centres jittered inside their voxels, moving on a smooth field
+    pcs, deltas = [], []
+    for b in range(B):
+        c = coords[coords[:, 0] == b][:, 1:].float().cpu()
+        idx = torch.randint(0, c.shape[0], (N_PC,), generator=g)
+        p = (c[idx] + torch.rand(N_PC, 3, generator=g)) / SB.RES_GRID - 0.5
+        t = torch.linspace(0, 1, T)[:, None, None]
+        d = 0.05 * torch.sin(6.28 * t + 4.0 * p[None, :, [1, 2, 0]]) * t
+        pcs.append(p)
+        deltas.append(d)
+    static_pc, delta_pc = torch.stack(pcs).to(dev), torch.stack(deltas).to(dev)
+    moving_pc = static_pc.unsqueeze(1) + delta_pc
+    S_ = dict(static=static, vae=vae, fw=fw, x=x, ext_s=ext_s, intr_s=intr_s, ext=ext, intr=intr, static_pc=static_pc,
+              delta_pc=delta_pc, moving_pc=moving_pc, B=B, T=T, dev=dev, gen=torch.Generator(device=dev).manual_seed(seed + 3),
+              lat_shape=(B * T, BN.N_LAT, BN.C_LAT))
+    # targets: renders of the un-trained models under a different posterior draw
+    with torch.no_grad():
+        fw.renderers["MipGS"].rendering_options.resolution = SB.RES_IMG
+        z = static.encode(x, noise=torch.randn(coords.shape[0], SB.LAT, generator=g).to(dev))
+        reps = fw.to_representation(static.decode(z))["MipGS"]
+        S_["image_s"] = fw.render_batch({"MipGS": reps}, ext_s, intr_s)["MipGS"]["rgb"].clone()
+        gs = [m.gaussian_tensor() for m in reps]
+        out = vae(gs, static_pc, delta_pc)["logits"]
+        S_["image_m"] = torch.cat([fw.renderers["MipGS"].render_frames(reps[b], ext[b], intr, 1.2 * out[b])[0][:, :3] for b in range(B)]).clone()
+    S_["opt"] = torch.optim.AdamW(vae.parameters(), lr=LR, weight_decay=0.0, fused=True)
+    S_["opt_s"] = torch.optim.AdamW(static.parameters(), lr=LR * 0.1, weight_decay=0.0, fused=True)
+    S_["params"] = list(vae.parameters()) + list(static.parameters())
+    S_["ema"] = [p.detach().clone() for p in S_["params"]]
+    return S_
+
+
+def step(S_, world=1):
+    from gvfdiffusion_b200.train_vae import compute_interpolation_loss_delta_interp, get_gaussian_tensor
+    from gvfdiffusion_b200.utils.loss_util import ssim_l1
+    fw, vae, dev, B, T = S_["fw"], S_["vae"], S_["dev"], S_["B"], S_["T"]
+    for p in S_["params"]:
+        p.grad = None
+    # ---- forward_backward (train_vae.py:263-353)
+    noise_s = torch.randn(S_["x"].feats.shape[0], 8, device=dev, generator=S_["gen"])
+    terms, reps = fw.training_losses(S_["x"], S_["image_s"], S_["ext_s"], S_["intr_s"], noise=noise_s)
+    models = reps["MipGS"]
+    static_gs = [get_gaussian_tensor(m) for m in models]
+    loss = terms["loss"]
+    out = vae(static_gs, S_["static_pc"], S_["delta_pc"], noise=torch.randn(S_["lat_shape"], device=dev, generator=S_["gen"]))
+    loss = loss + out["kl"].mean() * KL_W
+    pred = out["logits"]
+    interp, _, _ = compute_interpolation_loss_delta_interp(static_gs, S_["static_pc"], S_["moving_pc"], pred, B, KNN_K, beta=BETA)
+    loss = loss + interp * XYZ_W
+    imgs = [fw.renderers["MipGS"].render_frames(models[b], S_["ext"][b], S_["intr"], pred[b], detach_static=False)[0][:, :3]
+            for b in range(B)]
+    ssim_v, l1 = ssim_l1(torch.cat(imgs), S_["image_m"])
+    loss = loss + l1 * L1_W + (1.0 - ssim_v) * SSIM_W
+    (loss * LOSS_SCALE).backward()
+    # ---- optimize (train_vae.py:355-375)
+    grads = [p.grad for p in S_["params"] if p.grad is not None]
+    if world > 1:
+        import torch.distributed as dist
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.mul_(1.0 / (world * LOSS_SCALE))
+        for g_, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g_.copy_(f)
+        S_["allreduce_bytes"] = flat.numel() * 4
+    else:
+        torch._foreach_mul_(grads, 1.0 / LOSS_SCALE)
+    torch.nn.utils.clip_grad_norm_(S_["params"], 1.0, foreach=True)
+    S_["opt"].step()
+    S_["opt_s"].step()
+    live = [(e, p) for e, p in zip(S_["ema"], S_["params"])]
+    torch._foreach_mul_([e for e, _ in live], EMA)
+    torch._foreach_add_([e for e, _ in live], [p.detach() for _, p in live], alpha=1 - EMA)
+    return loss
+
+
+def measure(steps=5, warmup=3, seed=0, world=1, device=None):
+    dev = device if device is not None else torch.device("cuda", 0)
+    S_ = build(dev, seed)
+    for _ in range(warmup):
+        step(S_, world)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step(S_, world)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    B, T = S_["B"], S_["T"]
+    n_static = sum(p.numel() for p in S_["static"].parameters())
+    n_motion = sum(p.numel() for p in S_["vae"].parameters())
+    res = {"metric": "train-step samples/s (main_vae.py joint step: static VAE + motion VAE + renders, fwd + bwd + optimizer)",
+           "value": world * B / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "loss": float(loss.detach()),
+           "dtype": "f16 (fp32 accumulate, fp32 master weights / gradients / AdamW)", "data": "synthetic",
+           "config": {"workload": f"BASELINE.json configs[4]: per-GPU batch {B}; static VAE 2 x 2048 voxels (12+12 swin blocks, 768 ch) + "
+                                  f"one 512^2 render each; motion VAE encode + decode (12 layers, {T} x 512 latents, 16384 queries / "
+                                  f"object) + {B * T} renders at 512^2 with predicted deltas; L1 + SSIM + KL + interpolation (KNN 8) + "
+                                  "regularisers; backward; grad clip; 2 x AdamW; EMA; no LPIPS",
+                      "parameters": {"static_vae": n_static, "motion_vae": n_motion}}}
+    if world > 1:
+        res["ddp"] = {"allreduce_bytes_per_step": S_.get("allreduce_bytes"), "where": "inside the step, after backward"}
+    return res
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    a = ap.parse_args()
+    print(json.dumps(measure(a.steps, a.warmup)))
