@@ -49,7 +49,29 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, False, []
 
+    def _run_nvml(self):
+        """In-process NVML sampling (nvidia_ml_py): ~0.1 ms per sample with the GIL released.  A `nvidia-smi` process per
+        sample (the fallback below) initialises NVML every time and holds driver locks long enough to slow a launch-heavy
+        step: the joint train step measured 129 ms / step under it against 88 ms without."""
+        import pynvml as N
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+        while not self.stop_flag:
+            r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.rows.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx)] +
+                             ["Active" if r & b else "Not Active" for b in bits.values()])
+            time.sleep(0.1)
+
     def run(self):
+        try:
+            return self._run_nvml()
+        except Exception:
+            self.rows = []
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
@@ -205,10 +227,12 @@ def main():
                          "GEMMs lose the SM the single-CTA FPS sits on), end to end 83.1 vs 88.0 frames/s -- default off")
     ap.add_argument("--attn-dbg", type=lambda v: int(v, 0), default=0, help="gvf_attn_set_debug value (kernel-variant A/B)")
     ap.add_argument("--pdl", action="store_true", help="launch with the programmatic-dependent-launch attribute (A/B; default off)")
-    ap.add_argument("--config", default="cfg1", choices=["cfg1", "cfg3"],
+    ap.add_argument("--config", default="cfg1", choices=["cfg1", "cfg3", "cfg5", "cfg5-static"],
                     help="cfg1 (default): BASELINE.json configs[1], the headline inference metric.  cfg3: configs[2], one "
-                         "training step of the motion-VAE decoder + 24-frame render, forward + backward (tools/train_step_bench.py; "
-                         "N = 1), printed as its own JSON line")
+                         "training step of the motion-VAE decoder + 24-frame render, forward + backward (tools/train_step_bench.py).  "
+                         "cfg5: configs[4], the joint main_vae.py train step with optimiser, DDP all-reduce for N > 1 "
+                         "(tools/cfg5_step_bench.py).  cfg5-static: its static-VAE half next to a flash-attn / cuBLAS / autograd "
+                         "stand-in (tools/static_vae_step_bench.py, N = 1).  Each prints its own JSON line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -230,6 +254,25 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.config in ("cfg5", "cfg5-static"):
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        mon = ClockSampler(local)
+        mon.start()
+        if args.config == "cfg5":
+            from tools import cfg5_step_bench as C5
+            res = C5.measure(steps=args.steps, warmup=max(args.warmup, 3), seed=rank, world=world, device=dev)
+        else:
+            from tools import static_vae_step_bench as SVB
+            res = SVB.measure(steps=args.steps, warmup=max(args.warmup, 3), standin=not args.no_gpu_reference, seed=rank, device=dev)
+            res.update({"n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+                        "scaling": "weak", "vs_baseline": None})
+        mon.stop_flag = True
+        mon.join(timeout=2)
+        if rank == 0:
+            res["clocks"] = mon.summary()
+            real_stdout.write(json.dumps(res) + "\n")
+            real_stdout.flush()
+        return
     if args.config == "cfg3":
         # BASELINE configs[2] (and, for N > 1, the data-parallel half of configs[4]: every rank steps its own object and the
         # fp32 parameter gradients are averaged with one NCCL all-reduce inside the timed step)

@@ -5,7 +5,7 @@
 //
 // Why: at the reference's per-GPU batch (2 objects x 2048 voxels = 4096 tokens) a block is ~7 (forward) / ~25 (backward)
 // kernels of 5-25 us each; driven from Python (ctypes marshalling + a torch allocation per launch, ~13 us) the step was
-// host-bound: 15.0 ms to enqueue 1100 launches against 16.1 ms until the GPU finished (tools/_host_bound_probe.py).  Here a
+// host-bound: 15.0 ms to enqueue 1100 launches against 16.1 ms until the GPU finished (a perf_counter probe around the un-synchronised step).  Here a
 // launch costs the CUDA runtime's ~2 us plus a cuTensorMapEncode per GEMM operand, and no allocator call: every
 // intermediate lives in the arena / scratch the caller passes in.
 //

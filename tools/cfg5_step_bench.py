@@ -171,5 +171,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--one-step", action="store_true", help="two un-timed steps (for ncu launch lists)")
     a = ap.parse_args()
+    if a.one_step:
+        S0 = build(torch.device("cuda", 0))
+        for _ in range(2):
+            step(S0)
+            torch.cuda.synchronize()
+        sys.exit(0)
     print(json.dumps(measure(a.steps, a.warmup)))
