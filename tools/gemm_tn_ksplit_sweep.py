@@ -42,7 +42,7 @@ def main():
         auto = timed(lambda: ops.gemm_tn(a, w, out=out))
         best = min(row, key=lambda kv: kv[1])
         gf = 2.0 * M * N * R / 1e9
-        print(f"M={M} N={N} R={R}: auto {auto:.1f} us ({gf / auto * 1e-3:.0f} TF/s) best ks={best[0]} {best[1]:.1f} us | " +
+        print(f"M={M} N={N} R={R}: auto {auto:.1f} us ({gf / auto:.0f} TF/s) best ks={best[0]} {best[1]:.1f} us | " +
               " ".join(f"{k}:{t:.1f}" for k, t in row), flush=True)
 
 
