@@ -33,7 +33,8 @@ class SparseBlock(C.Structure):
 
 
 class WindowPartition(C.Structure):
-    _fields_ = [("fwd_idx", C.c_void_p), ("cu_seqlens", C.c_void_p), ("num_windows", C.c_int), ("max_seqlen", C.c_int)]
+    _fields_ = [("fwd_idx", C.c_void_p), ("cu_seqlens", C.c_void_p), ("num_windows", C.c_int), ("max_seqlen", C.c_int),
+                ("seq_of_pos", C.c_void_p)]
 _SIGS = {
     # name: (restype, argtypes)
     "gvf_status_string": (C.c_char_p, [C.c_int]),
@@ -65,6 +66,9 @@ _SIGS = {
     "gvf_colsum": (C.c_int, [_P, C.c_int, C.c_longlong, C.c_int, C.c_longlong, _P, C.c_size_t, _P, C.c_int, _P]),
     "gvf_ln_bwd_f16": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
     "gvf_geglu_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P, _P]),
+    "gvf_sparse_packed_attn_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "gvf_sparse_packed_attn_bwd_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_longlong, C.c_int, C.c_int,
+                                                 C.c_float, _P]),
     "gvf_sparse_trunk_arena_bytes": (C.c_size_t, [C.c_int] * 6),
     "gvf_sparse_trunk_scratch_bytes": (C.c_size_t, [C.c_int] * 4),
     "gvf_sparse_trunk_forward": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t,

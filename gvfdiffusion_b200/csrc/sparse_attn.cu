@@ -16,6 +16,13 @@
 // warps x 16 rows, S = Q K^T and O = P V as mma.sync.m16n8k16 on ldmatrix fragments, flash-style running
 // maximum over 64-key chunks, K/V chunks double buffered with cp.async.  Head dim 64 (768 / 12 heads).
 // fp16 in / out, fp32 scores, statistics and accumulators; P rounded to fp16 for P V.
+//
+// PACKED form (round 2, the static VAE's trunk): on object surfaces a window holds ~16 of its 512 possible voxels, so one
+// CTA per (window, head) is a 64-row tile with 48 rows of padding and 3 000 mostly idle CTAs per launch.  The sequences are
+// contiguous ranges of ONE sorted position list, so a CTA can instead take 64 CONSECUTIVE positions -- several whole
+// windows -- as its query tile and walk the key range [start of its first window, end of its last window): attention
+// becomes block-diagonal over the sorted list, every row carries the [lo, hi) position range of its own window and a key
+// column takes part iff its position falls inside it.  4x fewer CTAs, all rows busy: 33 -> ~10 us per launch at 4096 voxels.
 #include "../../include/gvf_b200.h"
 #include "tc_common.cuh"
 
@@ -62,23 +69,49 @@ __device__ __forceinline__ void stage_rows(uint32_t dst, const __half* __restric
   }
 }
 
+// PACKED = false: CTA = (64-row tile blockIdx.x of sequence blockIdx.z, head).  PACKED = true: CTA = (positions
+// [64 blockIdx.x, +64) of the whole list, head); seq_of_pos[p] = sequence of position p, M = total positions.
+template <bool PACKED>
 __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
                                                                 const int* __restrict__ fwd_idx,
                                                                 const int* __restrict__ out_idx,
-                                                                const int* __restrict__ cu_seqlens, int H,
+                                                                const int* __restrict__ cu_seqlens,
+                                                                const int* __restrict__ seq_of_pos, int M, int H,
                                                                 float scale_log2e, float* __restrict__ lse2) {
   __shared__ __align__(128) uint8_t sm[(1 + 4) * 64 * 128];     // Q | K0 V0 | K1 V1   (40 KB)
-  const int w = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQB;
-  const int beg = __ldg(cu_seqlens + w), len = __ldg(cu_seqlens + w + 1) - beg;
-  if (q0 >= len) return;
+  const int h = blockIdx.y;
+  // positions: query tile [p0, pend) (at most 64), key range [kbeg, kend)
+  int p0, pend, kbeg, kend;
+  if (PACKED) {
+    p0 = blockIdx.x * kQB;
+    if (p0 >= M) return;
+    pend = M;
+    kbeg = __ldg(cu_seqlens + __ldg(seq_of_pos + p0));
+    kend = __ldg(cu_seqlens + __ldg(seq_of_pos + min(p0 + kQB, M) - 1) + 1);
+  } else {
+    kbeg = __ldg(cu_seqlens + blockIdx.z);
+    kend = __ldg(cu_seqlens + blockIdx.z + 1);
+    p0 = kbeg + blockIdx.x * kQB;
+    if (p0 >= kend) return;
+    pend = kend;
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
-  const int* idx = fwd_idx;                      // gather list (nullptr: rows beg.. of qkv itself)
+  const int* idx = fwd_idx;                      // gather list (nullptr: rows of qkv itself)
   const uint32_t sQ = smem_u32(sm), sKV = sQ + 64 * 128;
-  const int nchunks = (len + kKB - 1) / kKB;
+  const int nchunks = (kend - kbeg + kKB - 1) / kKB;
+  // [lo, hi): positions of the keys this thread's two rows (g, g + 8 of the warp's 16) attend to
+  int lo[2], hi[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int p = p0 + 16 * warp + g + 8 * r;
+    if (p >= pend) { lo[r] = 0; hi[r] = 0; }
+    else if (PACKED) { const int sq = __ldg(seq_of_pos + p); lo[r] = __ldg(cu_seqlens + sq); hi[r] = __ldg(cu_seqlens + sq + 1); }
+    else { lo[r] = kbeg; hi[r] = kend; }
+  }
 
-  stage_rows(sQ, qkv, idx, beg, q0, len, 0, h, H, tid);
-  stage_rows(sKV, qkv, idx, beg, 0, len, 1, h, H, tid);
-  stage_rows(sKV + 64 * 128, qkv, idx, beg, 0, len, 2, h, H, tid);
+  stage_rows(sQ, qkv, idx, 0, p0, pend, 0, h, H, tid);
+  stage_rows(sKV, qkv, idx, 0, kbeg, kend, 1, h, H, tid);
+  stage_rows(sKV + 64 * 128, qkv, idx, 0, kbeg, kend, 2, h, H, tid);
   asm volatile("cp.async.commit_group;" ::: "memory");
 
   uint32_t qa[4][4];
@@ -93,8 +126,8 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
     const uint32_t bK = sKV + (uint32_t)(j & 1) * 2 * 64 * 128, bV = bK + 64 * 128;
     if (j + 1 < nchunks) {
       const uint32_t nK = sKV + (uint32_t)((j + 1) & 1) * 2 * 64 * 128;
-      stage_rows(nK, qkv, idx, beg, (j + 1) * kKB, len, 1, h, H, tid);
-      stage_rows(nK + 64 * 128, qkv, idx, beg, (j + 1) * kKB, len, 2, h, H, tid);
+      stage_rows(nK, qkv, idx, 0, kbeg + (j + 1) * kKB, kend, 1, h, H, tid);
+      stage_rows(nK + 64 * 128, qkv, idx, 0, kbeg + (j + 1) * kKB, kend, 2, h, H, tid);
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -118,24 +151,26 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
         mma16816(s[nt], qa[2 * hf + 1], kb[2], kb[3]);
       }
     }
-    // ---- running softmax; rows g (e = 0,1) and g + 8 (e = 2,3), key = j*64 + 8 nt + 2 tg + (e & 1)
-    const int kvalid = len - j * kKB;
+    // ---- running softmax; rows g (e = 0,1) and g + 8 (e = 2,3), key position = kbeg + j*64 + 8 nt + 2 tg + (e & 1)
+    const int kp0 = kbeg + j * kKB + 2 * tg;
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int col = 8 * nt + 2 * tg + (e & 1);
-        s[nt][e] = (col < kvalid) ? s[nt][e] * scale_log2e : -INFINITY;
+        const int kp = kp0 + 8 * nt + (e & 1);
+        s[nt][e] = (kp >= lo[e >> 1] && kp < hi[e >> 1]) ? s[nt][e] * scale_log2e : -INFINITY;
         mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
       }
-    float alpha[2];
+    float alpha[2], msub[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float mn = fmaxf(mrow[r], mx[r]);       // finite: every chunk holds at least one valid key
-      alpha[r] = ex2f(mrow[r] - mn);
+      const float mn = fmaxf(mrow[r], mx[r]);
+      // a packed tile's chunk may hold none of this row's keys yet (mn = -inf): subtract 0 then, every p is exp2(-inf) = 0
+      msub[r] = (mn == -INFINITY) ? 0.f : mn;
+      alpha[r] = ex2f(mrow[r] - msub[r]);
       mrow[r] = mn;
       lrow[r] *= alpha[r];
     }
@@ -145,7 +180,7 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
       float p[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        p[e] = ex2f(s[nt][e] - mrow[e >> 1]);
+        p[e] = ex2f(s[nt][e] - msub[e >> 1]);
         lrow[e >> 1] += p[e];
       }
       const __half2 lo = __floats2half2_rn(p[0], p[1]), hi = __floats2half2_rn(p[2], p[3]);
@@ -179,9 +214,8 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
   if (lse2 && tg == 0) {                           // training: LSE2[row, h] = log2 sum_k exp(scale s) for the backward kernels
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      const int row = q0 + 16 * warp + g + 8 * r;
-      if (row < len) {
-        const int pos = beg + row;
+      const int pos = p0 + 16 * warp + g + 8 * r;
+      if (pos < pend) {
         const long long grow = out_idx ? (long long)__ldg(out_idx + pos) : (idx ? (long long)__ldg(idx + pos) : (long long)pos);
         if (grow >= 0) lse2[grow * H + h] = mrow[r] + log2f(lrow[r]);
       }
@@ -199,10 +233,10 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int e = it * 32 + lane, r = 16 * warp + (e >> 3), c = e & 7;
-    if (q0 + r < len) {
+    if (p0 + r < pend) {
       // destination row: the scatter list when given (negative = this position is padding of an overlapping window,
       // serialized attention), else the row the query came from
-      const int pos = beg + q0 + r;
+      const int pos = p0 + r;
       const long long grow = out_idx ? (long long)__ldg(out_idx + pos) : (idx ? (long long)__ldg(idx + pos) : (long long)pos);
       if (grow >= 0)
         *reinterpret_cast<uint4*>(out + (grow * H + h) * kD + c * 8) = *reinterpret_cast<const uint4*>(sm + slot(r, c));
@@ -226,8 +260,8 @@ extern "C" GVF_API int gvf_sparse_window_attn_f16(const void* qkv, void* out, co
   if (num_windows == 0 || max_seqlen == 0) return GVF_OK;
   if (num_windows > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_windows);
-  gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, fwd_idx, nullptr, cu_seqlens, H, scale * 1.4426950408889634f, nullptr);
+  gvf::sparse_window_attn_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __half*)qkv, (__half*)out, fwd_idx, nullptr, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, nullptr);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -246,8 +280,8 @@ extern "C" GVF_API int gvf_sparse_varlen_attn_f16(const void* qkv, void* out, co
   if (num_seqs == 0 || max_seqlen == 0) return GVF_OK;
   if (num_seqs > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_seqs);
-  gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, H, scale * 1.4426950408889634f, nullptr);
+  gvf::sparse_window_attn_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, nullptr);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -261,7 +295,24 @@ extern "C" GVF_API int gvf_sparse_varlen_attn_lse_f16(const void* qkv, void* out
   if (num_seqs == 0 || max_seqlen == 0) return GVF_OK;
   if (num_seqs > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_seqs);
-  gvf::sparse_window_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, H, scale * 1.4426950408889634f, lse2);
+  gvf::sparse_window_attn_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, lse2);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+// Packed form of the three entry points above (see the file header): the sequences must be contiguous ranges of one
+// position list of M entries, seq_of_pos [M] int32 = the sequence a position belongs to (non-decreasing).  One CTA per 64
+// consecutive positions and head, whatever the sequence lengths.  lse2 may be NULL (inference).
+extern "C" GVF_API int gvf_sparse_packed_attn_f16(const void* qkv, void* out, float* lse2, const int* gather_idx,
+                                                  const int* scatter_idx, const int* cu_seqlens, const int* seq_of_pos, int M,
+                                                  int H, int D, float scale, void* stream) {
+  if (!qkv || !out || !cu_seqlens || !seq_of_pos || M < 0 || H <= 0) return GVF_ERR_INVALID;
+  if (D != gvf::kD) return GVF_ERR_UNSUPPORTED;
+  if (((uintptr_t)qkv | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
+  if (M == 0) return GVF_OK;
+  if (H > 65535) return GVF_ERR_UNSUPPORTED;
+  const dim3 grid((M + gvf::kQB - 1) / gvf::kQB, H, 1);
+  gvf::sparse_window_attn_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, seq_of_pos, M, H, scale * 1.4426950408889634f, lse2);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }

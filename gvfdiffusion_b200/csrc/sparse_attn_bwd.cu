@@ -139,26 +139,60 @@ __global__ void __launch_bounds__(256) sparse_attn_bwd_prep_kernel(const __half*
   dsum[i] = s;
 }
 
+// Tile set-up shared by the two kernels.  PACKED = false: 64-row tile blockIdx.x of sequence blockIdx.z, the other operand
+// ranges over that sequence.  PACKED = true (see csrc/sparse_attn.cu): 64 consecutive positions of the whole list, the other
+// operand ranges over [start of the first, end of the last sequence the tile touches), rows masked by their own range.
+template <bool PACKED>
+__device__ __forceinline__ bool b_tile(const int* __restrict__ cu, const int* __restrict__ seq_of_pos, int M, int& p0, int& pend,
+                                       int& obeg, int& oend) {
+  if (PACKED) {
+    p0 = blockIdx.x * 64;
+    if (p0 >= M) return false;
+    pend = M;
+    obeg = __ldg(cu + __ldg(seq_of_pos + p0));
+    oend = __ldg(cu + __ldg(seq_of_pos + min(p0 + 64, M) - 1) + 1);
+  } else {
+    obeg = __ldg(cu + blockIdx.z);
+    oend = __ldg(cu + blockIdx.z + 1);
+    p0 = obeg + blockIdx.x * 64;
+    if (p0 >= oend) return false;
+    pend = oend;
+  }
+  return true;
+}
+template <bool PACKED>
+__device__ __forceinline__ void b_row_range(const int* __restrict__ cu, const int* __restrict__ seq_of_pos, int p, int pend, int obeg,
+                                            int oend, int& lo, int& hi) {
+  if (p >= pend) { lo = 0; hi = 0; }
+  else if (PACKED) { const int sq = __ldg(seq_of_pos + p); lo = __ldg(cu + sq); hi = __ldg(cu + sq + 1); }
+  else { lo = obeg; hi = oend; }
+}
+
+template <bool PACKED>
 __global__ void __launch_bounds__(128) sparse_attn_bwd_dq_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
                                                                 const float* __restrict__ lse2, const float* __restrict__ dsum,
                                                                 __half* __restrict__ dqkv, const int* __restrict__ idx,
-                                                                const int* __restrict__ cu, int H, float scale,
-                                                                float scale_log2e) {
+                                                                const int* __restrict__ cu, const int* __restrict__ seq_of_pos,
+                                                                int M, int H, float scale, float scale_log2e) {
   extern __shared__ __align__(128) uint8_t sm[];                // Q | dO | K0 V0 | K1 V1   (48 KB, dynamic)
-  const int w = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
-  const int beg = __ldg(cu + w), len = __ldg(cu + w + 1) - beg;
-  if (q0 >= len) return;
+  const int h = blockIdx.y;
+  int q0, len, kbeg, kend;                                      // positions: queries [q0, len), keys [kbeg, kend)
+  if (!b_tile<PACKED>(cu, seq_of_pos, M, q0, len, kbeg, kend)) return;
+  const int beg = 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  int lo[2], hi[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) b_row_range<PACKED>(cu, seq_of_pos, q0 + 16 * warp + g + 8 * r, len, kbeg, kend, lo[r], hi[r]);
   const long long qrow = 3LL * H * kD, orow = (long long)H * kD;
   const __half* qb = qkv + (long long)h * kD;
   const __half* kb_ = qkv + ((long long)H + h) * kD;
   const __half* vb_ = qkv + (2LL * H + h) * kD;
   const uint32_t sQ = smem_u32(sm), sDO = sQ + 64 * 128, sKV = sDO + 64 * 128;
-  const int nchunks = (len + 63) / 64;
+  const int nchunks = (kend - kbeg + 63) / 64;
   b_stage(sQ, qb, qrow, idx, beg, q0, len, tid);
   b_stage(sDO, dout + (long long)h * kD, orow, idx, beg, q0, len, tid);
-  b_stage(sKV, kb_, qrow, idx, beg, 0, len, tid);
-  b_stage(sKV + 64 * 128, vb_, qrow, idx, beg, 0, len, tid);
+  b_stage(sKV, kb_, qrow, idx, beg, kbeg, kend, tid);
+  b_stage(sKV + 64 * 128, vb_, qrow, idx, beg, kbeg, kend, tid);
   asm volatile("cp.async.commit_group;" ::: "memory");
   // statistics of this thread's two rows
   float lse_r[2], d_r[2];
@@ -180,8 +214,8 @@ __global__ void __launch_bounds__(128) sparse_attn_bwd_dq_kernel(const __half* _
     const uint32_t bK = sKV + (uint32_t)(j & 1) * 2 * 64 * 128, bV = bK + 64 * 128;
     if (j + 1 < nchunks) {
       const uint32_t nK = sKV + (uint32_t)((j + 1) & 1) * 2 * 64 * 128;
-      b_stage(nK, kb_, qrow, idx, beg, (j + 1) * 64, len, tid);
-      b_stage(nK + 64 * 128, vb_, qrow, idx, beg, (j + 1) * 64, len, tid);
+      b_stage(nK, kb_, qrow, idx, beg, kbeg + (j + 1) * 64, kend, tid);
+      b_stage(nK + 64 * 128, vb_, qrow, idx, beg, kbeg + (j + 1) * 64, kend, tid);
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -197,13 +231,13 @@ __global__ void __launch_bounds__(128) sparse_attn_bwd_dq_kernel(const __half* _
     float s[8][4], dp[8][4];
     b_mm_kmajor(s, qa, bK, lane);                  // S = Q K^T
     b_mm_kmajor(dp, doa, bV, lane);                // dP = dO V^T
-    const int kvalid = len - j * 64;
+    const int kp0 = kbeg + j * 64 + 2 * tg;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int col = 8 * nt + 2 * tg + (e & 1);
-        const float p = (col < kvalid) ? b_ex2(fmaf(s[nt][e], scale_log2e, -lse_r[e >> 1])) : 0.f;
+        const int kp = kp0 + 8 * nt + (e & 1);
+        const float p = (kp >= lo[e >> 1] && kp < hi[e >> 1]) ? b_ex2(fmaf(s[nt][e], scale_log2e, -lse_r[e >> 1])) : 0.f;
         s[nt][e] = p * (dp[nt][e] - d_r[e >> 1]);  // dS
       }
     uint32_t dsa[4][4];
@@ -214,28 +248,33 @@ __global__ void __launch_bounds__(128) sparse_attn_bwd_dq_kernel(const __half* _
   b_store_rows(sm, dq, scale, dqkv + (long long)h * kD, qrow, idx, beg, q0, len, warp, lane);
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(128) sparse_attn_bwd_dkdv_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
                                                                   const float* __restrict__ lse2, const float* __restrict__ dsum,
                                                                   __half* __restrict__ dqkv, const int* __restrict__ idx,
-                                                                  const int* __restrict__ cu, int H, float scale,
-                                                                  float scale_log2e) {
+                                                                  const int* __restrict__ cu, const int* __restrict__ seq_of_pos,
+                                                                  int M, int H, float scale, float scale_log2e) {
   extern __shared__ __align__(128) uint8_t sm[];                // K | V | Q0 dO0 | Q1 dO1 (48 KB) | LSE2, D of two chunks
   float (*s_lse)[64] = reinterpret_cast<float (*)[64]>(sm + 6 * 64 * 128);
   float (*s_d)[64] = reinterpret_cast<float (*)[64]>(sm + 6 * 64 * 128 + 512);
-  const int w = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 64;
-  const int beg = __ldg(cu + w), len = __ldg(cu + w + 1) - beg;
-  if (k0 >= len) return;
+  const int h = blockIdx.y;
+  int k0, len, qbeg, qend;                                      // positions: keys [k0, len), queries [qbeg, qend)
+  if (!b_tile<PACKED>(cu, seq_of_pos, M, k0, len, qbeg, qend)) return;
+  const int beg = 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, tg = lane & 3;
+  int lo[2], hi[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) b_row_range<PACKED>(cu, seq_of_pos, k0 + 16 * warp + (lane >> 2) + 8 * r, len, qbeg, qend, lo[r], hi[r]);
   const long long qrow = 3LL * H * kD, orow = (long long)H * kD;
   const __half* qb = qkv + (long long)h * kD;
   const __half* kb_ = qkv + ((long long)H + h) * kD;
   const __half* vb_ = qkv + (2LL * H + h) * kD;
   const __half* dob = dout + (long long)h * kD;
   const uint32_t sK = smem_u32(sm), sV = sK + 64 * 128, sQD = sV + 64 * 128;
-  const int nchunks = (len + 63) / 64;
+  const int nchunks = (qend - qbeg + 63) / 64;
   auto stage_stats = [&](int buf, int r0) {
     if (tid < 64) {
-      const bool ok = r0 + tid < len;
+      const bool ok = r0 + tid < qend;
       const long long grow = ok ? b_row(idx, beg + r0 + tid) : 0;
       s_lse[buf][tid] = ok ? __ldg(lse2 + grow * H + h) : INFINITY;
       s_d[buf][tid] = ok ? __ldg(dsum + grow * H + h) : 0.f;
@@ -243,10 +282,10 @@ __global__ void __launch_bounds__(128) sparse_attn_bwd_dkdv_kernel(const __half*
   };
   b_stage(sK, kb_, qrow, idx, beg, k0, len, tid);
   b_stage(sV, vb_, qrow, idx, beg, k0, len, tid);
-  b_stage(sQD, qb, qrow, idx, beg, 0, len, tid);
-  b_stage(sQD + 64 * 128, dob, orow, idx, beg, 0, len, tid);
+  b_stage(sQD, qb, qrow, idx, beg, qbeg, qend, tid);
+  b_stage(sQD + 64 * 128, dob, orow, idx, beg, qbeg, qend, tid);
   asm volatile("cp.async.commit_group;" ::: "memory");
-  stage_stats(0, 0);
+  stage_stats(0, qbeg);
   uint32_t ka[4][4], va[4][4];
   float dk[8][4], dv[8][4];
 #pragma unroll
@@ -257,9 +296,9 @@ __global__ void __launch_bounds__(128) sparse_attn_bwd_dkdv_kernel(const __half*
     const uint32_t bQ = sQD + (uint32_t)(j & 1) * 2 * 64 * 128, bDO = bQ + 64 * 128;
     if (j + 1 < nchunks) {
       const uint32_t nQ = sQD + (uint32_t)((j + 1) & 1) * 2 * 64 * 128;
-      b_stage(nQ, qb, qrow, idx, beg, (j + 1) * 64, len, tid);
-      b_stage(nQ + 64 * 128, dob, orow, idx, beg, (j + 1) * 64, len, tid);
-      stage_stats((j + 1) & 1, (j + 1) * 64);
+      b_stage(nQ, qb, qrow, idx, beg, qbeg + (j + 1) * 64, qend, tid);
+      b_stage(nQ + 64 * 128, dob, orow, idx, beg, qbeg + (j + 1) * 64, qend, tid);
+      stage_stats((j + 1) & 1, qbeg + (j + 1) * 64);
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -277,12 +316,15 @@ __global__ void __launch_bounds__(128) sparse_attn_bwd_dkdv_kernel(const __half*
     b_mm_kmajor(dp, va, bDO, lane);                // dP^T = V dO^T
     const float* lse = s_lse[j & 1];
     const float* dd = s_d[j & 1];
+    const int qp0 = qbeg + j * 64;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = 8 * nt + 2 * tg + (e & 1);
-        const float p = b_ex2(fmaf(s[nt][e], scale_log2e, -lse[col]));      // +inf for padded queries -> 0
+        const int qp = qp0 + col;                  // the query must sit in this key row's own sequence (packed tiles)
+        const float p = (!PACKED || (qp >= lo[e >> 1] && qp < hi[e >> 1]))
+                            ? b_ex2(fmaf(s[nt][e], scale_log2e, -lse[col])) : 0.f;   // +inf for padded queries -> 0
         s[nt][e] = p;
         dp[nt][e] = p * (dp[nt][e] - dd[col]);     // dS^T
       }
@@ -304,34 +346,62 @@ __global__ void __launch_bounds__(128) sparse_attn_bwd_dkdv_kernel(const __half*
 // Backward of gvf_sparse_varlen_attn_f16 for bijective lists (windowed / full attention: every voxel row appears exactly
 // once; the serialized form with padded windows is forward-only).  qkv [T, 3, H, 64], dout [T, H, 64] (gradient of the
 // attention output in voxel order), o [T, H, 64] the forward output, lse2 [T, H] from the forward, dsum [T, H] scratch,
-// dqkv [T, 3, H, 64] receives dq | dk | dv in voxel order.
-extern "C" GVF_API int gvf_sparse_varlen_attn_bwd_f16(const void* qkv, const void* o, const void* dout, const float* lse2,
-                                                      float* dsum, void* dqkv, const int* gather_idx, const int* cu_seqlens,
-                                                      int num_seqs, int max_seqlen, long long T, int H, int D, float scale,
-                                                      void* stream) {
+// dqkv [T, 3, H, 64] receives dq | dk | dv in voxel order.  seq_of_pos != NULL selects the packed tiling (M positions).
+static int sparse_attn_bwd_impl(const void* qkv, const void* o, const void* dout, const float* lse2, float* dsum, void* dqkv,
+                                const int* gather_idx, const int* cu_seqlens, const int* seq_of_pos, int M, int num_seqs,
+                                int max_seqlen, long long T, int H, int D, float scale, void* stream) {
   if (!qkv || !o || !dout || !lse2 || !dsum || !dqkv || !cu_seqlens || num_seqs < 0 || H <= 0 || T <= 0) return GVF_ERR_INVALID;
   if (D != gvf::kD) return GVF_ERR_UNSUPPORTED;
   if (((uintptr_t)qkv | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dqkv) & 15) return GVF_ERR_INVALID;
-  if (num_seqs == 0 || max_seqlen <= 0) return GVF_OK;
+  const bool packed = seq_of_pos != nullptr;
+  if (packed ? M <= 0 : (num_seqs == 0 || max_seqlen <= 0)) return GVF_OK;
   if (num_seqs > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = T * H;
   gvf::sparse_attn_bwd_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __half*)o, (const __half*)dout, n, dsum);
   if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
-  const dim3 grid((max_seqlen + 63) / 64, H, num_seqs);
   const float sl2 = scale * 1.4426950408889634f;
   constexpr int SMEM_DQ = 6 * 64 * 128, SMEM_KV = 6 * 64 * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gvf::sparse_attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ) != cudaSuccess ||
-        cudaFuncSetAttribute(gvf::sparse_attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_KV) != cudaSuccess)
+    if (cudaFuncSetAttribute(gvf::sparse_attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ) != cudaSuccess ||
+        cudaFuncSetAttribute(gvf::sparse_attn_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_KV) != cudaSuccess ||
+        cudaFuncSetAttribute(gvf::sparse_attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ) != cudaSuccess ||
+        cudaFuncSetAttribute(gvf::sparse_attn_bwd_dkdv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_KV) != cudaSuccess)
       return GVF_ERR_CUDA;
     configured = true;
   }
-  gvf::sparse_attn_bwd_dq_kernel<<<grid, 128, SMEM_DQ, st>>>((const __half*)qkv, (const __half*)dout, lse2, dsum, (__half*)dqkv,
-                                                      gather_idx, cu_seqlens, H, scale, sl2);
+  if (packed) {
+    const dim3 grid((M + 63) / 64, H, 1);
+    gvf::sparse_attn_bwd_dq_kernel<true><<<grid, 128, SMEM_DQ, st>>>((const __half*)qkv, (const __half*)dout, lse2, dsum, (__half*)dqkv,
+                                                                    gather_idx, cu_seqlens, seq_of_pos, M, H, scale, sl2);
+    if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
+    gvf::sparse_attn_bwd_dkdv_kernel<true><<<grid, 128, SMEM_KV, st>>>((const __half*)qkv, (const __half*)dout, lse2, dsum,
+                                                                      (__half*)dqkv, gather_idx, cu_seqlens, seq_of_pos, M, H, scale, sl2);
+    return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+  }
+  const dim3 grid((max_seqlen + 63) / 64, H, num_seqs);
+  gvf::sparse_attn_bwd_dq_kernel<false><<<grid, 128, SMEM_DQ, st>>>((const __half*)qkv, (const __half*)dout, lse2, dsum, (__half*)dqkv,
+                                                                   gather_idx, cu_seqlens, nullptr, 0, H, scale, sl2);
   if (cudaGetLastError() != cudaSuccess) return GVF_ERR_CUDA;
-  gvf::sparse_attn_bwd_dkdv_kernel<<<grid, 128, SMEM_KV, st>>>((const __half*)qkv, (const __half*)dout, lse2, dsum, (__half*)dqkv,
-                                                        gather_idx, cu_seqlens, H, scale, sl2);
+  gvf::sparse_attn_bwd_dkdv_kernel<false><<<grid, 128, SMEM_KV, st>>>((const __half*)qkv, (const __half*)dout, lse2, dsum,
+                                                                     (__half*)dqkv, gather_idx, cu_seqlens, nullptr, 0, H, scale, sl2);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+
+extern "C" GVF_API int gvf_sparse_varlen_attn_bwd_f16(const void* qkv, const void* o, const void* dout, const float* lse2,
+                                                      float* dsum, void* dqkv, const int* gather_idx, const int* cu_seqlens,
+                                                      int num_seqs, int max_seqlen, long long T, int H, int D, float scale,
+                                                      void* stream) {
+  return sparse_attn_bwd_impl(qkv, o, dout, lse2, dsum, dqkv, gather_idx, cu_seqlens, nullptr, 0, num_seqs, max_seqlen, T, H, D,
+                              scale, stream);
+}
+
+// Packed tiling of the same backward (csrc/sparse_attn.cu, PACKED): seq_of_pos [M] int32, M = positions in the list.
+extern "C" GVF_API int gvf_sparse_packed_attn_bwd_f16(const void* qkv, const void* o, const void* dout, const float* lse2,
+                                                      float* dsum, void* dqkv, const int* gather_idx, const int* cu_seqlens,
+                                                      const int* seq_of_pos, int M, long long T, int H, int D, float scale,
+                                                      void* stream) {
+  if (!seq_of_pos) return GVF_ERR_INVALID;
+  return sparse_attn_bwd_impl(qkv, o, dout, lse2, dsum, dqkv, gather_idx, cu_seqlens, seq_of_pos, M, 1, 1, T, H, D, scale, stream);
 }

@@ -106,8 +106,12 @@ GVF_API int gvf_sparse_trunk_forward(const gvf_sparse_block* blocks, int num_blo
       uint8_t *x0 = L.xslot(ar, i), *x2 = L.xslot(ar, i + 1);
       GVF_TRY(gvf_ln_mod_f16(x0, fp16_residual, s.A, T, C, 1e-6f, nullptr, nullptr, nullptr, nullptr, 0, 0, stream));
       GVF_TRY(gvf_gemm_f16(s.A, C, b.w_qkv, C, T, 3 * C, C, 0, b.b_qkv, s.QKV, 3 * C, nullptr, 0, 0, stream));
-      GVF_TRY(gvf_sparse_varlen_attn_lse_f16(s.QKV, s.AO, (float*)s.lse, pt.fwd_idx, nullptr, pt.cu_seqlens, pt.num_windows,
-                                             pt.max_seqlen, H, 64, scale, stream));
+      if (pt.seq_of_pos)
+        GVF_TRY(gvf_sparse_packed_attn_f16(s.QKV, s.AO, (float*)s.lse, pt.fwd_idx, nullptr, pt.cu_seqlens, pt.seq_of_pos, T, H, 64,
+                                           scale, stream));
+      else
+        GVF_TRY(gvf_sparse_varlen_attn_lse_f16(s.QKV, s.AO, (float*)s.lse, pt.fwd_idx, nullptr, pt.cu_seqlens, pt.num_windows,
+                                               pt.max_seqlen, H, 64, scale, stream));
       GVF_TRY(copy_async(s.x1, x0, xbytes, stream));
       GVF_TRY(gvf_gemm_f16(s.AO, C, b.w_out, C, T, C, C, epi, b.b_out, s.x1, C, nullptr, 0, 0, stream));
       GVF_TRY(gvf_ln_mod_f16(s.x1, fp16_residual, s.A2, T, C, 1e-6f, nullptr, nullptr, nullptr, nullptr, 0, 0, stream));
@@ -128,7 +132,10 @@ GVF_API int gvf_sparse_trunk_forward(const gvf_sparse_block* blocks, int num_blo
     const gvf_window_partition& pt = parts[i & 1];
     GVF_TRY(gvf_ln_mod_f16(x_out, fp16_residual, A16, T, C, 1e-6f, nullptr, nullptr, nullptr, nullptr, 0, 0, stream));
     GVF_TRY(gvf_gemm_f16(A16, C, b.w_qkv, C, T, 3 * C, C, 0, b.b_qkv, QKV, 3 * C, nullptr, 0, 0, stream));
-    GVF_TRY(gvf_sparse_window_attn_f16(QKV, AO, pt.fwd_idx, pt.cu_seqlens, pt.num_windows, pt.max_seqlen, H, 64, scale, stream));
+    if (pt.seq_of_pos)
+      GVF_TRY(gvf_sparse_packed_attn_f16(QKV, AO, nullptr, pt.fwd_idx, nullptr, pt.cu_seqlens, pt.seq_of_pos, T, H, 64, scale, stream));
+    else
+      GVF_TRY(gvf_sparse_window_attn_f16(QKV, AO, pt.fwd_idx, pt.cu_seqlens, pt.num_windows, pt.max_seqlen, H, 64, scale, stream));
     GVF_TRY(gvf_gemm_f16(AO, C, b.w_out, C, T, C, C, epi, b.b_out, x_out, C, nullptr, 0, 0, stream));
     GVF_TRY(gvf_ln_mod_f16(x_out, fp16_residual, A16, T, C, 1e-6f, nullptr, nullptr, nullptr, nullptr, 0, 0, stream));
     GVF_TRY(gvf_gemm_f16(A16, C, b.w1, C, T, F, C, 1, b.b1, H1, F, nullptr, 0, 0, stream));
@@ -210,8 +217,12 @@ GVF_API int gvf_sparse_trunk_backward(const gvf_sparse_block* blocks, int num_bl
     GVF_CU(cudaStreamWaitEvent(side, e[1], 0));
     GVF_TRY(gvf_gemm_tn_f16(dx1, C, s.AO, C, C, C, T, b.g_w_out, C, side));
     GVF_TRY(gvf_colsum(dx1, 1, T, C, C, reduce_ws, reduce_ws_bytes, b.g_b_out, 0, side));
-    GVF_TRY(gvf_sparse_varlen_attn_bwd_f16(s.QKV, s.AO, dAO, (const float*)s.lse, dsum, dQKV, pt.fwd_idx, pt.cu_seqlens,
-                                           pt.num_windows, pt.max_seqlen, T, H, 64, scale, ms));
+    if (pt.seq_of_pos)
+      GVF_TRY(gvf_sparse_packed_attn_bwd_f16(s.QKV, s.AO, dAO, (const float*)s.lse, dsum, dQKV, pt.fwd_idx, pt.cu_seqlens,
+                                             pt.seq_of_pos, T, T, H, 64, scale, ms));
+    else
+      GVF_TRY(gvf_sparse_varlen_attn_bwd_f16(s.QKV, s.AO, dAO, (const float*)s.lse, dsum, dQKV, pt.fwd_idx, pt.cu_seqlens,
+                                             pt.num_windows, pt.max_seqlen, T, H, 64, scale, ms));
     GVF_CU(cudaEventRecord(e[2], ms));
     GVF_TRY(gvf_gemm_f16(dQKV, 3 * C, b.w_qkv_t, 3 * C, T, C, 3 * C, 0, nullptr, dA, C, nullptr, 0, 0, ms));
     GVF_CU(cudaStreamWaitEvent(side, e[2], 0));

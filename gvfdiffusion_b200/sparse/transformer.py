@@ -85,13 +85,15 @@ class SparseTransformerBlocks:
     # ---------------------------------------------------------------------------------------- native driver
     def _parts(self, coords):
         """gvf_window_partition[2]: the un-shifted and the shifted window partition of `coords` (cached per tensor)."""
-        from .attention.windowed_attn import _partition
+        from .attention.windowed_attn import _partition, _seq_of_pos
         arr = (_lib.WindowPartition * 2)()
         keep = []
         for k, sh in enumerate((0, self.window // 2)):
             fwd, _bwd, cu, max_len = _partition(coords, self.window, (sh,) * 3)
-            arr[k] = _lib.WindowPartition(ptr(fwd), ptr(cu), cu.shape[0] - 1, max_len)
-            keep += [fwd, cu]
+            # short windows (object surfaces: ~16 voxels each): the packed tiling, several windows per 64-row tile
+            sop = _seq_of_pos(coords, self.window, (sh,) * 3) if max_len < 256 else None
+            arr[k] = _lib.WindowPartition(ptr(fwd), ptr(cu), cu.shape[0] - 1, max_len, ptr(sop))
+            keep += [fwd, cu, sop]
         return arr, keep
 
     def _block_structs(self, grads=None):

@@ -372,6 +372,16 @@ GVF_API int gvf_sparse_varlen_attn_lse_f16(const void* qkv, void* out, float* ls
 GVF_API int gvf_sparse_varlen_attn_bwd_f16(const void* qkv, const void* o, const void* dout, const float* lse2, float* dsum,
                                            void* dqkv, const int* gather_idx, const int* cu_seqlens, int num_seqs,
                                            int max_seqlen, long long T, int H, int D, float scale, void* stream);
+/* PACKED tiling of the forward (lse2 may be NULL) and backward above, for lists whose sequences are contiguous ranges of one
+ * position list of M entries (window partitions): one CTA per 64 CONSECUTIVE positions and head -- several short windows
+ * share a tile, rows are masked to their own window's key range -- instead of one CTA per (window, head, 64 rows), most of
+ * whose rows are padding when windows hold ~16 voxels.  seq_of_pos [M] int32 = the sequence of position p. */
+GVF_API int gvf_sparse_packed_attn_f16(const void* qkv, void* out, float* lse2, const int* gather_idx, const int* scatter_idx,
+                                       const int* cu_seqlens, const int* seq_of_pos, int M, int H, int D, float scale,
+                                       void* stream);
+GVF_API int gvf_sparse_packed_attn_bwd_f16(const void* qkv, const void* o, const void* dout, const float* lse2, float* dsum,
+                                           void* dqkv, const int* gather_idx, const int* cu_seqlens, const int* seq_of_pos,
+                                           int M, long long T, int H, int D, float scale, void* stream);
 
 /* Native driver of a stack of un-modulated SparseTransformerBlocks (reference sparse_transformer.py:126-192 stacked at
  * sparse_transformer_vae.py:55-91; block i uses partition parts[i % 2] = un-shifted / shifted windows): the whole launch
@@ -388,6 +398,7 @@ typedef struct gvf_window_partition {
   const int* fwd_idx;                              /* [T] token rows ordered by window */
   const int* cu_seqlens;                           /* [num_windows + 1] */
   int num_windows, max_seqlen;
+  const int* seq_of_pos;                           /* [T] window of sorted position p, or NULL: one CTA per window tile */
 } gvf_window_partition;
 GVF_API size_t gvf_sparse_trunk_arena_bytes(int T, int C, int H, int F, int num_blocks, int fp16_residual);
 GVF_API size_t gvf_sparse_trunk_scratch_bytes(int T, int C, int H, int F);

@@ -25,16 +25,17 @@ def _voxels(n_per_batch, res, batches, seed):
 @pytest.mark.parametrize("n,res,window,shift,H", [(1500, 64, 8, (0, 0, 0), 12), (1500, 64, 8, (4, 4, 4), 12),
                                                    (900, 16, 8, (0, 0, 0), 3),      # dense windows: up to 512 voxels, many key chunks
                                                    (70, 8, 8, (0, 0, 0), 2), (5, 32, 8, (4, 4, 4), 1)])
-def test_windowed_attention_matches_oracle(n, res, window, shift, H):
+@pytest.mark.parametrize("packed", [False, True])
+def test_windowed_attention_matches_oracle(n, res, window, shift, H, packed):
     from gvfdiffusion_b200.sparse.attention import sparse_windowed_scaled_dot_product_self_attention
     from oracle import sparse_window as OSW
     coords = _voxels(n, res, 2, seed=n + H)
     g = torch.Generator().manual_seed(7)
     qkv = (torch.randn(coords.shape[0], 3, H, 64, generator=g) * 1.5).half()
     ref = OSW.windowed_attention(qkv, coords, window, shift)
-    out = sparse_windowed_scaled_dot_product_self_attention(qkv.to(DEV), coords.to(DEV), window, shift).float().cpu()
+    out = sparse_windowed_scaled_dot_product_self_attention(qkv.to(DEV), coords.to(DEV), window, shift, packed=packed).float().cpu()
     err = (out - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 2e-3, err
+    assert err < 2e-3, err       # packed: 64 consecutive sorted positions per CTA, rows masked to their own window
 
 
 def test_windowed_attention_on_reference_partition_fixture():
@@ -110,7 +111,8 @@ def test_sparse_vae_decode_matches_oracle():
 
 @pytest.mark.parametrize("n_vox,res,window,shift", [(1500, 64, 8, (0, 0, 0)), (1500, 64, 8, (4, 4, 4)), (300, 16, 4, (2, 2, 2)),
                                                      (4000, 32, 8, (4, 4, 4)), (64, 8, 8, (0, 0, 0)), (3000, 16, 8, (0, 0, 0))])
-def test_windowed_attention_backward_matches_autograd(n_vox, res, window, shift):
+@pytest.mark.parametrize("packed", [False, True])
+def test_windowed_attention_backward_matches_autograd(n_vox, res, window, shift, packed):
     """csrc/sparse_attn_bwd.cu (dq + dk/dv kernels, gather fused) against torch autograd of the reference formulation:
     gather by window, softmax attention inside every window, scatter back.  fp16 gradients: 5e-3 rel. L2."""
     from gvfdiffusion_b200.sparse.attention.windowed_attn import calc_window_partition, sparse_windowed_attention_autograd
@@ -123,7 +125,7 @@ def test_windowed_attention_backward_matches_autograd(n_vox, res, window, shift)
     T, H, C = coords.shape[0], 3, 64
     qkv = (torch.randn(T, 3, H, C, generator=g) * 0.8).half().to(DEV).requires_grad_(True)
     dout = (torch.randn(T, H, C, generator=g) * 0.5).half().to(DEV)
-    out = sparse_windowed_attention_autograd(qkv, coords, window, shift)
+    out = sparse_windowed_attention_autograd(qkv, coords, window, shift, packed=packed)
     out.backward(dout)
     fwd, bwd, seq_lens, _ = calc_window_partition(coords, window, shift)
     qf = qkv.detach().float().requires_grad_(True)
