@@ -68,6 +68,8 @@ class ClockSampler(threading.Thread):
             time.sleep(0.1)
 
     def run(self):
+        if os.environ.get("GVF_BENCH_NO_CLOCKS"):          # A/B switch for the sampler's own cost
+            return
         try:
             return self._run_nvml()
         except Exception:
