@@ -75,6 +75,9 @@ _SIGS = {
                                            _P, C.c_size_t, _P, _P]),
     "gvf_sparse_trunk_backward": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P,
                                             _P, C.c_size_t, _P, C.c_size_t, _P, _P]),
+    "gvf_lpips_tap_blocks": (C.c_int, [C.c_int]),
+    "gvf_lpips_tap_fwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "gvf_lpips_tap_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gvf_gaussian_tensor_bwd": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_gelu_tanh_f16": (C.c_int, [_P, C.c_longlong, _P, _P]),
     "gvf_gelu_tanh_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),

@@ -19,6 +19,7 @@
 //     lowest index; rows beyond lengths1 / columns beyond lengths2 are zero like pytorch3d's.
 //   * gvf_knn_interp_deltas: the RBF-weighted neighbour-motion estimate of
 //     compute_interpolation_loss_delta_interp (train_vae.py:532-563) in one pass.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -373,7 +374,134 @@ __global__ void __launch_bounds__(256) knn_interp_kernel(const float* __restrict
   }
 }
 
+// =======================================================================================
+// LPIPS tail (reference utils/lpips/lpips.py:29-34, networks.py:60-62, utils.py:6-8) for one feature tap:
+//     d[n] = mean_pixels sum_c w_c (fx_c / (||fx|| + eps) - fy_c / (||fy|| + eps))^2
+// fx, fy fp16 [N, HW, C] (the channels-last activations cuDNN leaves), w fp32 [C].  The torch formulation (float copies,
+// square, channel sum, sqrt, broadcast divide, difference, square, 1x1 conv, spatial mean -- each a pass over up to 1.7 GB,
+// several through TensorIterator's strided slow path) cost 80 of the criterion's 146 ms on the joint train step's 2 x 50
+// images; here it is one read of fx and fy forward, one read + one write backward.  One warp per pixel, the pixel's C
+// channels in registers (C / 64 half2 per lane), deterministic: per-block partial sums, summed by the caller.
+template <int C>
+__global__ void __launch_bounds__(256) lpips_tap_fwd_kernel(const __half* __restrict__ fx, const __half* __restrict__ fy,
+                                                            const float* __restrict__ w, int HW, float* __restrict__ partial) {
+  constexpr int PER = C / 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = blockIdx.y;
+  float wr[2 * PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { wr[2 * k] = w[64 * k + 2 * lane]; wr[2 * k + 1] = w[64 * k + 2 * lane + 1]; }
+  float acc = 0.f;
+  for (int p = blockIdx.x * 8 + warp; p < HW; p += gridDim.x * 8) {
+    const __half2* px = reinterpret_cast<const __half2*>(fx + ((size_t)n * HW + p) * C);
+    const __half2* py = reinterpret_cast<const __half2*>(fy + ((size_t)n * HW + p) * C);
+    float2 x[PER], y[PER];
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      x[k] = __half22float2(px[32 * k + lane]);
+      y[k] = __half22float2(py[32 * k + lane]);
+      sx += x[k].x * x[k].x + x[k].y * x[k].y;
+      sy += y[k].x * y[k].x + y[k].y * y[k].y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+    const float ix = 1.0f / (sqrtf(sx) + 1e-10f), iy = 1.0f / (sqrtf(sy) + 1e-10f);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const float e0 = x[k].x * ix - y[k].x * iy, e1 = x[k].y * ix - y[k].y * iy;
+      acc += wr[2 * k] * e0 * e0 + wr[2 * k + 1] * e1 * e1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float red[8];
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    partial[(size_t)n * gridDim.x + blockIdx.x] = t;
+  }
+}
+// d d[n] / d fx:  a = fx / (r + eps), e = a - b, u_c = 2 w_c e_c:
+//     grad_fx_k = g[n] / HW * (u_k / (r + eps) - fx_k / (r (r + eps)^2) * sum_c u_c fx_c)
+template <int C>
+__global__ void __launch_bounds__(256) lpips_tap_bwd_kernel(const __half* __restrict__ fx, const __half* __restrict__ fy,
+                                                            const float* __restrict__ w, const float* __restrict__ gout,
+                                                            int HW, __half* __restrict__ gfx) {
+  constexpr int PER = C / 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = blockIdx.y;
+  float wr[2 * PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { wr[2 * k] = w[64 * k + 2 * lane]; wr[2 * k + 1] = w[64 * k + 2 * lane + 1]; }
+  const float g = gout[n] / (float)HW;
+  for (int p = blockIdx.x * 8 + warp; p < HW; p += gridDim.x * 8) {
+    const size_t base = ((size_t)n * HW + p) * C;
+    const __half2* px = reinterpret_cast<const __half2*>(fx + base);
+    const __half2* py = reinterpret_cast<const __half2*>(fy + base);
+    float2 x[PER], y[PER];
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      x[k] = __half22float2(px[32 * k + lane]);
+      y[k] = __half22float2(py[32 * k + lane]);
+      sx += x[k].x * x[k].x + x[k].y * x[k].y;
+      sy += y[k].x * y[k].x + y[k].y * y[k].y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+    const float r = sqrtf(sx), ix = 1.0f / (r + 1e-10f), iy = 1.0f / (sqrtf(sy) + 1e-10f);
+    float2 u[PER];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      u[k].x = 2.0f * wr[2 * k] * (x[k].x * ix - y[k].x * iy);
+      u[k].y = 2.0f * wr[2 * k + 1] * (x[k].y * ix - y[k].y * iy);
+      dot += u[k].x * x[k].x + u[k].y * x[k].y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float cr = (r > 0.f) ? dot * ix * ix / r : 0.f;
+    __half2* pg = reinterpret_cast<__half2*>(gfx + base);
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+      pg[32 * k + lane] = __floats2half2_rn(g * (u[k].x * ix - x[k].x * cr), g * (u[k].y * ix - x[k].y * cr));
+  }
+}
+
 }  // namespace gvf
+
+extern "C" GVF_API int gvf_lpips_tap_blocks(int HW) {
+  int b = (HW + 63) / 64;                       // 8 pixels per pass and block, at least 8 passes
+  return b < 1 ? 1 : (b > 296 ? 296 : b);
+}
+// partial fp32 [N, gvf_lpips_tap_blocks(HW)]: un-normalised block sums; d[n] = partial[n].sum() / HW
+extern "C" GVF_API int gvf_lpips_tap_fwd(const void* fx, const void* fy, const float* w, int N, int HW, int C, float* partial,
+                                         void* stream) {
+  if (!fx || !fy || !w || !partial || N <= 0 || HW <= 0 || N > 65535) return GVF_ERR_INVALID;
+  if (((uintptr_t)fx | (uintptr_t)fy) & 3) return GVF_ERR_INVALID;
+  const dim3 grid(gvf_lpips_tap_blocks(HW), N);
+  cudaStream_t st = (cudaStream_t)stream;
+#define GVF_LP(CC) if (C == CC) { gvf::lpips_tap_fwd_kernel<CC><<<grid, 256, 0, st>>>((const __half*)fx, (const __half*)fy, w, HW, partial); \
+                                  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA; }
+  GVF_LP(64) GVF_LP(128) GVF_LP(256) GVF_LP(512)
+#undef GVF_LP
+  return GVF_ERR_UNSUPPORTED;
+}
+// gout fp32 [N] = d loss / d d[n]; gfx fp16 [N, HW, C]
+extern "C" GVF_API int gvf_lpips_tap_bwd(const void* fx, const void* fy, const float* w, const float* gout, int N, int HW, int C,
+                                         void* gfx, void* stream) {
+  if (!fx || !fy || !w || !gout || !gfx || N <= 0 || HW <= 0 || N > 65535) return GVF_ERR_INVALID;
+  if (((uintptr_t)fx | (uintptr_t)fy | (uintptr_t)gfx) & 3) return GVF_ERR_INVALID;
+  const dim3 grid(gvf_lpips_tap_blocks(HW), N);
+  cudaStream_t st = (cudaStream_t)stream;
+#define GVF_LP(CC) if (C == CC) { gvf::lpips_tap_bwd_kernel<CC><<<grid, 256, 0, st>>>((const __half*)fx, (const __half*)fy, w, gout, HW, (__half*)gfx); \
+                                  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA; }
+  GVF_LP(64) GVF_LP(128) GVF_LP(256) GVF_LP(512)
+#undef GVF_LP
+  return GVF_ERR_UNSUPPORTED;
+}
 
 extern "C" GVF_API size_t gvf_ssim_l1_workspace_bytes(int planes, int H, int W) {
   if (planes <= 0 || H <= 0 || W <= 0) return 0;

@@ -4,8 +4,9 @@ reference's model/sparse_voxel_diffusion/sparse_vae.py:60-112 (configuration, Ha
 `gvfdiffusion_b200.sparse.transformer.SparseTransformerVAE`.  One kernel launch per representation type covers the whole
 batch; the per-entry `GaussianModel`s returned are views into its outputs.  `training_losses` (:303-362) is the static-VAE
 half of the reference's train step (BASELINE configs[4]): backbone forward / backward on the library's kernels as one
-autograd node, to_representation, one render per sample, L1 + lambda_ssim (1 - SSIM) [+ lambda_lpips LPIPS through a
-caller-supplied module: the VGG16 weights are a network download] + lamda_kl KL + volume / opacity regularisers."""
+autograd node, to_representation, one render per sample, L1 + lambda_ssim (1 - SSIM) + lambda_lpips LPIPS (VGG16 on library
+convolutions, utils/lpips; seeded-random weights unless a module with the downloaded ones is supplied) + lamda_kl KL +
+volume / opacity regularisers."""
 import copy
 
 import torch
@@ -167,10 +168,9 @@ class SparseVAE:
                 terms[k + "_ssim"] = 1 - s
                 terms["rec"] = terms["rec"] + self.lambda_ssim * terms[k + "_ssim"]
             if self.lambda_lpips > 0:
-                if self.lpips is None:
-                    raise RuntimeError("lambda_lpips > 0 needs an LPIPS module (SparseVAE(lpips=...)): its VGG16 weights are a "
-                                       "network download in the reference (utils/lpips)")
-                terms[k + "_lpips"] = self.lpips(rec, image)
+                # utils/loss_util.py:66-74; `lpips=` an LPIPS module with real weights, else the seeded-random one
+                from ...utils.loss_util import lpips as lpips_fn
+                terms[k + "_lpips"] = lpips_fn(rec, image, module=self.lpips)
                 terms["rec"] = terms["rec"] + self.lambda_lpips * terms[k + "_lpips"]
             terms["loss"] = terms["loss"] + terms["rec"]
         terms["kl"] = kl

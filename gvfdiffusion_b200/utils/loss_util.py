@@ -80,3 +80,21 @@ def l1_loss(network_output, gt):
 def l2_loss(network_output, gt):
     """utils/loss_util.py:20-21 (plain torch: not used by the training step)"""
     return ((network_output - gt) ** 2).mean()
+
+
+_loss_fn_vgg = {}
+
+
+def lpips(img1, img2, value_range=(0, 1), module=None):
+    """utils/loss_util.py:66-74: LPIPS-VGG16 of images in `value_range`, mapped to [-1, 1].  The reference builds its
+    (downloaded) criterion lazily and keeps it in a global; here the lazily built one has seeded random weights unless
+    `module` (an LPIPS with real weights, gvfdiffusion_b200.utils.lpips.LPIPS.load_pretrained) is passed."""
+    from .lpips import LPIPS
+    if module is None:
+        key = str(img1.device)
+        if key not in _loss_fn_vgg:
+            _loss_fn_vgg[key] = LPIPS(net_type="vgg").to(img1.device).eval()
+        module = _loss_fn_vgg[key]
+    a = (img1 - value_range[0]) / (value_range[1] - value_range[0]) * 2 - 1
+    b = (img2 - value_range[0]) / (value_range[1] - value_range[0]) * 2 - 1
+    return module(a, b).mean()

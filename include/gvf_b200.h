@@ -435,6 +435,13 @@ GVF_API int gvf_ssim_l1_bwd(const float* img1, const float* img2, const float* d
  * as called at train_vae.py:525-530.  queries [B,P1,3], refs [B,P2,3] fp32; lengths int64 [B] or NULL;
  * dists [B,P1,K] squared distances ascending ((dx*dx + dy*dy) + dz*dz, every operation rounded: no FMA),
  * idx [B,P1,K] int64, ties -> lowest index; rows >= lengths1 and columns >= lengths2 are zero. */
+/* LPIPS tail of one VGG16 feature tap (utils/lpips/lpips.py:29-34): d[n] = mean_pixels sum_c w_c (fx_c / (||fx|| + 1e-10) -
+ * fy_c / (||fy|| + 1e-10))^2 over channels-last fp16 activations fx, fy [N, HW, C], C in {64, 128, 256, 512}; one pass
+ * forward (block partial sums [N, gvf_lpips_tap_blocks(HW)], d[n] = their sum / HW), one pass backward (gradient of fx). */
+GVF_API int gvf_lpips_tap_blocks(int HW);
+GVF_API int gvf_lpips_tap_fwd(const void* fx, const void* fy, const float* w, int N, int HW, int C, float* partial, void* stream);
+GVF_API int gvf_lpips_tap_bwd(const void* fx, const void* fy, const float* w, const float* gout, int N, int HW, int C, void* gfx,
+                              void* stream);
 GVF_API int gvf_knn(const float* queries, const float* refs, int B, int P1, int P2, const long long* lengths1,
                     const long long* lengths2, int K, float* dists, long long* idx, void* stream);
 /* compute_interpolation_loss_delta_interp's neighbour-motion estimate (train_vae.py:532-563):

@@ -655,7 +655,39 @@ def gen_to_representation():
     return out
 
 
+def gen_lpips():
+    """The reference's own LPIPS(net_type='vgg') class (utils/lpips/lpips.py) with its two downloads replaced by seeded
+    random weights: torchvision's vgg16 un-pretrained, filled from gvfdiffusion_b200.utils.lpips.LPIPS(seed=3) -- whose
+    initialisation is a pure function of the seed -- and the linear heads from the same module.  Only the seed, the input
+    seeds and the resulting loss / input-gradient checksums are stored (the 59 MB of weights are regenerated by the test)."""
+    import torchvision
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(          # the one product file this generator reads: the seeded weight
+        "_gvf_lpips", os.path.join(HERE, "..", "..", "gvfdiffusion_b200", "utils", "lpips", "lpips.py"))    # initialiser
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ours = mod.LPIPS(seed=3).eval()
+    import utils.lpips.networks as RN
+    import utils.lpips.lpips as RL
+    _vgg16 = torchvision.models.vgg16
+    RN.models.vgg16 = lambda *a, **k: _vgg16(weights=None)            # no ImageNet download
+    lin_sd = {f"{i}.1.weight": l[1].weight.detach().clone() for i, l in enumerate(ours.lin)}
+    RL.get_state_dict = lambda net_type="vgg", version="0.1": lin_sd
+    ref = RL.LPIPS(net_type="vgg").eval()
+    ref.net.layers.load_state_dict(ours.layers.state_dict())
+    g = torch.Generator().manual_seed(11)
+    x = (torch.rand(2, 3, 96, 96, generator=g) * 2 - 1).requires_grad_(True)
+    y = torch.rand(2, 3, 96, 96, generator=g) * 2 - 1
+    loss = ref(x, y)
+    loss.backward()
+    return {"seed": 3, "input_seed": 11, "shape": (2, 3, 96, 96), "loss": float(loss), "grad_abs_sum": float(x.grad.abs().sum()),
+            "grad_probe": x.grad[0, :, ::16, ::16].clone()}
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "lpips":
+        torch.save(gen_lpips(), os.path.join(HERE, "lpips.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "render_call":
         torch.save(gen_render_call(), os.path.join(HERE, "render_call.pt"))
         return
@@ -698,6 +730,7 @@ def main():
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))
     torch.save(gen_sparse_vae(), os.path.join(HERE, "sparse_vae_tiny.pt"))
     torch.save(gen_render_call(), os.path.join(HERE, "render_call.pt"))
+    torch.save(gen_lpips(), os.path.join(HERE, "lpips.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

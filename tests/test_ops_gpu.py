@@ -483,3 +483,39 @@ def test_gemm_geglu_fused_is_bit_identical_to_the_two_kernels(M, F_, K):
     h = (a.float() @ w.float().T + b).half().float()
     ref = h[:, :F_] * F.gelu(h[:, F_:])
     _close(one, ref, 2e-3, "geglu fused")
+
+
+def test_lpips_cuda_path_matches_torch_formulation():
+    """LPIPS on the device (fp16 channels-last VGG16 through cuDNN, one batch for both images, the tail fused into
+    gvf_lpips_tap_fwd / _bwd) against the module's own plain-torch fp32 formulation run on the same device: loss and the
+    gradient of the prediction.  fp16 convolutions: 2e-2."""
+    from gvfdiffusion_b200.utils.lpips import LPIPS
+    m = LPIPS(seed=3).to(DEV).eval()
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(3, 3, 128, 96, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
+    y = (torch.rand(3, 3, 128, 96, generator=g) * 2 - 1).to(DEV)
+    loss = m(x, y)
+    (loss * 65536.0).backward()                        # fp16 activation gradients need the training step's loss scale
+    xr = x.detach().clone().requires_grad_(True)
+    fx = m.taps(xr)
+    with torch.no_grad():
+        fy = m.taps(y)
+    ref = torch.sum(torch.cat([l((m._unit(a) - m._unit(b)) ** 2).mean((2, 3), True) for a, b, l in zip(fx, fy, m.lin)], 0)) / 3
+    (ref * 65536.0).backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) < 2e-2 * abs(float(ref.detach())), (float(loss.detach()), float(ref.detach()))
+    rel = float((x.grad - xr.grad).norm() / xr.grad.norm())
+    assert rel < 5e-2, rel
+    # the fused tail alone, on identical fp16 activations: tight
+    from gvfdiffusion_b200.utils.lpips.lpips import _TapFn
+    f = (torch.randn(4, 128, 20, 24, generator=g) * 0.7).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    a, b = f[:2].clone().requires_grad_(True), f[2:]
+    w = torch.rand(128, generator=g).to(DEV)
+    d = _TapFn.apply(a, b, w)
+    gw = torch.tensor([0.7, -1.3], device=DEV)
+    (d * gw).sum().backward()
+    a32 = a.detach().float().requires_grad_(True)
+    e = (m._unit(a32) - m._unit(b.float())) ** 2
+    dr = (e * w[None, :, None, None]).sum(1).mean((1, 2))
+    (dr * gw).sum().backward()
+    assert torch.allclose(d, dr.detach(), rtol=1e-4, atol=1e-7)
+    assert float((a.grad.float() - a32.grad).norm() / a32.grad.norm()) < 2e-3

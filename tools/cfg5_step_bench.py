@@ -14,7 +14,9 @@ One step = reference train_vae.py:263-375 (`forward_backward` + `optimize`) on s
                (lr, 0.1 lr) -> EMA 0.9999 of both models; the engines' fp16 weight copies are refreshed from the fp32
                masters at the next forward (inside the timed steps, which run back to back)
 
-LPIPS (VGG16; its weights are a network download) is the one term left out.  Timed with CUDA events over whole steps.
+LPIPS-VGG16 (0.2 x, both the static and the 48-frame term) runs with seeded-random weights -- the ImageNet VGG16 and the
+v0.1 heads are a network download -- i.e. the criterion's full cost and gradient path (13 cuDNN convolutions on 2 x 50 images
+of 512^2 per step, forward + backward) is inside the timed step.  Timed with CUDA events over whole steps.
 
     python tools/cfg5_step_bench.py [--steps 5]         -> one JSON line
 """
@@ -29,11 +31,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 LOSS_SCALE = 65536.0
-KL_W, XYZ_W, L1_W, SSIM_W, KNN_K, BETA, LR, EMA = 1e-5, 0.1, 1.0, 0.2, 8, 7.0, 1e-4, 0.9999
+KL_W, XYZ_W, L1_W, SSIM_W, LPIPS_W, KNN_K, BETA, LR, EMA = 1e-5, 0.1, 1.0, 0.2, 0.2, 8, 7.0, 1e-4, 0.9999
 N_PC = 8192
 
 
-def build(dev, seed=0):
+def build(dev, seed=0, lpips=True):
     import bench as BN
     from gvfdiffusion_b200 import synthetic as S
     from gvfdiffusion_b200.model.sparse_voxel_diffusion import SparseTransformerVAE, SparseVAE
@@ -47,8 +49,10 @@ def build(dev, seed=0):
     static = static.to(dev).train()
     _, vae = BN.build_models(dev, seed=seed)
     vae.train()
+    from gvfdiffusion_b200.utils.lpips import LPIPS
+    vgg = LPIPS(net_type="vgg").to(dev).eval() if lpips else None                      # train_vae.py:93
     fw = SparseVAE({"vae": static}, resolution=SB.RES_GRID, representation_config=SB.REP, device=dev, lambda_ssim=0.2,
-                   lambda_lpips=0.0, lamda_kl=1e-6, regularizations=SB.REG)
+                   lambda_lpips=0.2 if lpips else 0.0, lamda_kl=1e-6, regularizations=SB.REG, lpips=vgg)
     coords = torch.cat([torch.cat([torch.full((SB.NVOX, 1), b), SB.surface_voxels(seed + 1 + b)], 1) for b in range(B)]).int().to(dev)
     g = torch.Generator().manual_seed(seed + 9)
     x = SparseTensor(torch.randn(coords.shape[0], SB.CIN, generator=g).to(dev), coords)
@@ -69,7 +73,7 @@ def build(dev, seed=0):
     moving_pc = static_pc.unsqueeze(1) + delta_pc
     S_ = dict(static=static, vae=vae, fw=fw, x=x, ext_s=ext_s, intr_s=intr_s, ext=ext, intr=intr, static_pc=static_pc,
               delta_pc=delta_pc, moving_pc=moving_pc, B=B, T=T, dev=dev, gen=torch.Generator(device=dev).manual_seed(seed + 3),
-              lat_shape=(B * T, BN.N_LAT, BN.C_LAT))
+              lat_shape=(B * T, BN.N_LAT, BN.C_LAT), vgg=vgg)
     # targets: renders of the un-trained models under a different posterior draw
     with torch.no_grad():
         fw.renderers["MipGS"].rendering_options.resolution = SB.RES_IMG
@@ -105,8 +109,11 @@ def step(S_, world=1):
     loss = loss + interp * XYZ_W
     imgs = [fw.renderers["MipGS"].render_frames(models[b], S_["ext"][b], S_["intr"], pred[b], detach_static=False)[0][:, :3]
             for b in range(B)]
-    ssim_v, l1 = ssim_l1(torch.cat(imgs), S_["image_m"])
+    pred_img = torch.cat(imgs)
+    ssim_v, l1 = ssim_l1(pred_img, S_["image_m"])
     loss = loss + l1 * L1_W + (1.0 - ssim_v) * SSIM_W
+    if S_["vgg"] is not None:                                                         # train_vae.py:329
+        loss = loss + S_["vgg"](pred_img * 2 - 1.0, S_["image_m"] * 2 - 1.0) * LPIPS_W
     (loss * LOSS_SCALE).backward()
     # ---- optimize (train_vae.py:355-375)
     grads = [p.grad for p in S_["params"] if p.grad is not None]
@@ -129,9 +136,9 @@ def step(S_, world=1):
     return loss
 
 
-def measure(steps=5, warmup=3, seed=0, world=1, device=None):
+def measure(steps=5, warmup=3, seed=0, world=1, device=None, lpips=True):
     dev = device if device is not None else torch.device("cuda", 0)
-    S_ = build(dev, seed)
+    S_ = build(dev, seed, lpips)
     for _ in range(warmup):
         step(S_, world)
     torch.cuda.synchronize()
@@ -160,7 +167,8 @@ def measure(steps=5, warmup=3, seed=0, world=1, device=None):
            "config": {"workload": f"BASELINE.json configs[4]: per-GPU batch {B}; static VAE 2 x 2048 voxels (12+12 swin blocks, 768 ch) + "
                                   f"one 512^2 render each; motion VAE encode + decode (12 layers, {T} x 512 latents, 16384 queries / "
                                   f"object) + {B * T} renders at 512^2 with predicted deltas; L1 + SSIM + KL + interpolation (KNN 8) + "
-                                  "regularisers; backward; grad clip; 2 x AdamW; EMA; no LPIPS",
+                                  "regularisers" + (" + 0.2 LPIPS-VGG16 (seeded-random weights) on all 50 renders" if lpips else "; no LPIPS") +
+                                  "; backward; grad clip; 2 x AdamW; EMA",
                       "parameters": {"static_vae": n_static, "motion_vae": n_motion}}}
     if world > 1:
         res["ddp"] = {"allreduce_bytes_per_step": S_.get("allreduce_bytes"), "where": "inside the step, after backward"}
@@ -172,6 +180,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--one-step", action="store_true", help="two un-timed steps (for ncu launch lists)")
+    ap.add_argument("--no-lpips", action="store_true", help="leave the LPIPS terms out (A/B: what the cuDNN convolutions cost)")
     a = ap.parse_args()
     if a.one_step:
         S0 = build(torch.device("cuda", 0))
@@ -179,4 +188,4 @@ if __name__ == "__main__":
             step(S0)
             torch.cuda.synchronize()
         sys.exit(0)
-    print(json.dumps(measure(a.steps, a.warmup)))
+    print(json.dumps(measure(a.steps, a.warmup, lpips=not a.no_lpips)))
