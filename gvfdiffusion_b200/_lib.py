@@ -76,6 +76,9 @@ _SIGS = {
     "gvf_sparse_trunk_backward": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P,
                                             _P, C.c_size_t, _P, C.c_size_t, _P, _P]),
     "gvf_lpips_tap_blocks": (C.c_int, [C.c_int]),
+    "gvf_bias_relu_nhwc_f16": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P]),
+    "gvf_maxpool2_nhwc_f16": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "gvf_maxpool2_nhwc_bwd_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "gvf_lpips_tap_fwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gvf_lpips_tap_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gvf_gaussian_tensor_bwd": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

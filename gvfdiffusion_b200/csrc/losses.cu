@@ -470,7 +470,104 @@ __global__ void __launch_bounds__(256) lpips_tap_bwd_kernel(const __half* __rest
   }
 }
 
+// Glue between the VGG16 convolutions (cuDNN, channels-last fp16): bias + ReLU in place (torch adds a channels-last bias
+// through TensorIterator's strided path: 16 ms per criterion call against 2 for this pass) and the 2 x 2 / stride 2 max pool
+// with its backward (torch's NHWC pool kernels: 13.5 ms per call).  Thread = 8 channels of one pixel.
+__global__ void __launch_bounds__(256) bias_relu_nhwc_kernel(__half* __restrict__ x, const float* __restrict__ bias, long long nvec,
+                                                             int C8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const int c = (int)(i % C8) * 8;
+  uint4 v = reinterpret_cast<uint4*>(x)[i];
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __half22float2(h[j]);
+    f.x = fmaxf(f.x + bias[c + 2 * j], 0.f);
+    f.y = fmaxf(f.y + bias[c + 2 * j + 1], 0.f);
+    h[j] = __floats2half2_rn(f.x, f.y);
+  }
+  reinterpret_cast<uint4*>(x)[i] = v;
+}
+__global__ void __launch_bounds__(256) maxpool2_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int Ho,
+                                                            int Wo, int C8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * Ho * Wo * C8;
+  if (i >= total) return;
+  const int c = (int)(i % C8);
+  long long p = i / C8;
+  const int wo = (int)(p % Wo); p /= Wo;
+  const int ho = (int)(p % Ho);
+  const int n = (int)(p / Ho);
+  const int W = 2 * Wo;
+  const uint4* src = reinterpret_cast<const uint4*>(x) + (((long long)n * 2 * Ho + 2 * ho) * W + 2 * wo) * C8 + c;
+  uint4 a = __ldg(src), b = __ldg(src + C8), d = __ldg(src + (long long)W * C8), e = __ldg(src + (long long)W * C8 + C8);
+  __half2 *pa = reinterpret_cast<__half2*>(&a), *pb = reinterpret_cast<__half2*>(&b), *pd = reinterpret_cast<__half2*>(&d),
+          *pe = reinterpret_cast<__half2*>(&e);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pa[j] = __hmax2(__hmax2(pa[j], pb[j]), __hmax2(pd[j], pe[j]));
+  reinterpret_cast<uint4*>(y)[i] = a;
+}
+// gx = gy at the FIRST position of the window (row-major) whose value equals the maximum, 0 elsewhere (torch's choice)
+__global__ void __launch_bounds__(256) maxpool2_nhwc_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ y,
+                                                                const __half* __restrict__ gy, __half* __restrict__ gx, int N,
+                                                                int Ho, int Wo, int C8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * Ho * Wo * C8;
+  if (i >= total) return;
+  const int c = (int)(i % C8);
+  long long p = i / C8;
+  const int wo = (int)(p % Wo); p /= Wo;
+  const int ho = (int)(p % Ho);
+  const int n = (int)(p / Ho);
+  const int W = 2 * Wo;
+  const long long base = (((long long)n * 2 * Ho + 2 * ho) * W + 2 * wo) * C8 + c;
+  const long long off[4] = {0, C8, (long long)W * C8, (long long)W * C8 + C8};
+  const uint4 m = __ldg(reinterpret_cast<const uint4*>(y) + i), g = __ldg(reinterpret_cast<const uint4*>(gy) + i);
+  const unsigned short* pm = reinterpret_cast<const unsigned short*>(&m);
+  const unsigned short* pg = reinterpret_cast<const unsigned short*>(&g);
+  unsigned found = 0;                                    // bit j: channel j already assigned
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + base + off[q]);
+    const unsigned short* pv = reinterpret_cast<const unsigned short*>(&v);
+    uint4 o;
+    unsigned short* po = reinterpret_cast<unsigned short*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool hit = !((found >> j) & 1u) && __heq(__ushort_as_half(pv[j]), __ushort_as_half(pm[j]));
+      po[j] = hit ? pg[j] : (unsigned short)0;
+      found |= (hit ? 1u : 0u) << j;
+    }
+    reinterpret_cast<uint4*>(gx)[base + off[q]] = o;
+  }
+}
+
 }  // namespace gvf
+
+extern "C" GVF_API int gvf_bias_relu_nhwc_f16(void* x, const float* bias, long long pixels, int C, void* stream) {
+  if (!x || !bias || pixels <= 0 || C <= 0 || (C % 8) || ((uintptr_t)x & 15)) return GVF_ERR_INVALID;
+  const long long nvec = pixels * (C / 8);
+  gvf::bias_relu_nhwc_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__half*)x, bias, nvec, C / 8);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+extern "C" GVF_API int gvf_maxpool2_nhwc_f16(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  if (!x || !y || N <= 0 || H <= 0 || W <= 0 || (H % 2) || (W % 2) || C <= 0 || (C % 8)) return GVF_ERR_INVALID;
+  if (((uintptr_t)x | (uintptr_t)y) & 15) return GVF_ERR_INVALID;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  gvf::maxpool2_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, N, H / 2,
+                                                                                             W / 2, C / 8);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
+extern "C" GVF_API int gvf_maxpool2_nhwc_bwd_f16(const void* x, const void* y, const void* gy, void* gx, int N, int H, int W, int C,
+                                                 void* stream) {
+  if (!x || !y || !gy || !gx || N <= 0 || H <= 0 || W <= 0 || (H % 2) || (W % 2) || C <= 0 || (C % 8)) return GVF_ERR_INVALID;
+  if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gy | (uintptr_t)gx) & 15) return GVF_ERR_INVALID;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  gvf::maxpool2_nhwc_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, (const __half*)y, (const __half*)gy, (__half*)gx, N, H / 2, W / 2, C / 8);
+  return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
+}
 
 extern "C" GVF_API int gvf_lpips_tap_blocks(int HW) {
   int b = (HW + 63) / 64;                       // 8 pixels per pass and block, at least 8 passes

@@ -15,7 +15,7 @@ The reference downloads torchvision's ImageNet VGG16 and the v0.1 linear heads; 
 initialises both randomly unless state dicts are handed in (`load_pretrained`) -- the structure, cost and gradient path are
 the ones of the real criterion, the values are not a perceptual metric until real weights are loaded.  Everything is
 frozen; gradients flow to `x` only.  Under CUDA the convolutions run in fp16 autocast and channels-last (what accelerate's
-mixed precision makes of them in the reference), both images go through the network as ONE batch, and everything after the
+mixed precision makes of them in the reference), the target's pass runs without a graph, and everything after the
 taps -- normalisation, difference, 1x1 head, spatial mean, and their backward -- is one kernel per tap and direction
 (csrc/losses.cu `gvf_lpips_tap_fwd / _bwd`: the torch formulation of that tail was 80 of the criterion's 146 ms per step)."""
 import torch
@@ -60,9 +60,55 @@ def _vgg16_features():
         if v == "M":
             layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
         else:
-            layers += [nn.Conv2d(cin, v, kernel_size=3, padding=1), nn.ReLU(inplace=False)]
+            layers += [nn.Conv2d(cin, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
             cin = v
     return nn.Sequential(*layers)     # module indices equal torchvision.models.vgg16().features'
+
+
+class _BiasReLUFn(torch.autograd.Function):
+    """relu(conv_out + bias) in place on the fresh channels-last convolution output (the bias is frozen)."""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        from ... import _lib
+        from ..._lib import check, current_stream, ptr
+        N, C, H, W = y.shape
+        assert y.is_contiguous(memory_format=torch.channels_last) and y.dtype == torch.float16
+        check(_lib.lib().gvf_bias_relu_nhwc_f16(ptr(y), ptr(bias), N * H * W, C, current_stream()), "gvf_bias_relu_nhwc_f16")
+        ctx.mark_dirty(y)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return torch.ops.aten.threshold_backward(g.contiguous(memory_format=torch.channels_last), y, 0), None
+
+
+class _MaxPool2Fn(torch.autograd.Function):
+    """2 x 2 / stride 2 max pool on channels-last fp16 activations."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from ... import _lib
+        from ..._lib import check, current_stream, ptr
+        N, C, H, W = x.shape
+        y = torch.empty((N, C, H // 2, W // 2), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        check(_lib.lib().gvf_maxpool2_nhwc_f16(ptr(x), ptr(y), N, H, W, C, current_stream()), "gvf_maxpool2_nhwc_f16")
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from ... import _lib
+        from ..._lib import check, current_stream, ptr
+        x, y = ctx.saved_tensors
+        N, C, H, W = x.shape
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty_like(x)
+        check(_lib.lib().gvf_maxpool2_nhwc_bwd_f16(ptr(x), ptr(y), ptr(gy), ptr(gx), N, H, W, C, current_stream()),
+              "gvf_maxpool2_nhwc_bwd_f16")
+        return gx
 
 
 class LPIPS(nn.Module):
@@ -83,6 +129,7 @@ class LPIPS(nn.Module):
         self.register_buffer("mean", torch.tensor([-.030, -.088, -.188])[None, :, None, None])
         self.register_buffer("std", torch.tensor([.458, .448, .450])[None, :, None, None])
         self.pretrained = False
+        self._w16 = {}                                 # fp16 channels-last copies of the (frozen) convolution weights
         if vgg_state_dict is not None or lin_state_dict is not None:
             self.load_pretrained(vgg_state_dict, lin_state_dict)
         for p in self.parameters():
@@ -94,6 +141,7 @@ class LPIPS(nn.Module):
         if vgg_state_dict is not None:
             sd = {k.replace("features.", ""): v for k, v in vgg_state_dict.items() if not k.startswith("classifier")}
             self.layers.load_state_dict(sd)
+            self._w16 = {}
         if lin_state_dict is not None:
             sd = {k.replace("lin", "").replace("model.", ""): v for k, v in lin_state_dict.items()}    # utils.py:22-27
             self.lin.load_state_dict(sd)
@@ -105,6 +153,26 @@ class LPIPS(nn.Module):
         out = []
         for i, layer in enumerate(self.layers, 1):
             x = layer(x)
+            if i in _TAPS:
+                out.append(x)
+        return out
+
+    def taps_cuda(self, x):
+        """`taps` for fp16 channels-last CUDA input: cuDNN convolutions without bias, bias + ReLU and the pools on the
+        library's own glue kernels (csrc/losses.cu)."""
+        import torch.nn.functional as F
+        x = ((x - self.mean) / self.std).to(torch.float16).contiguous(memory_format=torch.channels_last)
+        out = []
+        for i, layer in enumerate(self.layers, 1):
+            if isinstance(layer, nn.Conv2d):
+                if x.shape[2] % 2 or x.shape[3] % 2 or layer.out_channels % 8:
+                    return None
+                w16 = self._w16.get(i)
+                if w16 is None or w16.device != x.device:
+                    w16 = self._w16[i] = layer.weight.detach().to(torch.float16).contiguous(memory_format=torch.channels_last)
+                x = _BiasReLUFn.apply(F.conv2d(x, w16, None, padding=1), layer.bias.detach().float())
+            elif isinstance(layer, nn.MaxPool2d):
+                x = _MaxPool2Fn.apply(x)
             if i in _TAPS:
                 out.append(x)
         return out
@@ -121,12 +189,15 @@ class LPIPS(nn.Module):
                 fy = self.taps(y)
             res = [l((self._unit(a) - self._unit(b)) ** 2).mean((2, 3), True) for a, b, l in zip(fx, fy, self.lin)]
             return torch.sum(torch.cat(res, 0)) / N
-        with torch.autocast("cuda", dtype=torch.float16):
-            # one batch through the network: y's half is cut out of the graph after the taps
-            xy = torch.cat([x, y.detach()], 0).to(torch.float16).contiguous(memory_format=torch.channels_last)
-            feats = self.taps(xy)
+        fx = self.taps_cuda(x)
+        with torch.no_grad():                          # the target's half never enters the graph
+            fy = self.taps_cuda(y)
+        if fx is None or fy is None:                   # odd image sizes: torch's own pool / bias kernels
+            with torch.autocast("cuda", dtype=torch.float16):
+                fx = self.taps(x.to(torch.float16).contiguous(memory_format=torch.channels_last))
+                with torch.no_grad():
+                    fy = self.taps(y.to(torch.float16).contiguous(memory_format=torch.channels_last))
         total = 0.0
-        for f, l in zip(feats, self.lin):
-            d = _TapFn.apply(f[:N], f[N:].detach(), l[1].weight.reshape(-1).float().contiguous())
-            total = total + d.sum()
+        for a, b, l in zip(fx, fy, self.lin):
+            total = total + _TapFn.apply(a, b, l[1].weight.reshape(-1).float().contiguous()).sum()
         return total / N

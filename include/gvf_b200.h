@@ -439,6 +439,12 @@ GVF_API int gvf_ssim_l1_bwd(const float* img1, const float* img2, const float* d
  * fy_c / (||fy|| + 1e-10))^2 over channels-last fp16 activations fx, fy [N, HW, C], C in {64, 128, 256, 512}; one pass
  * forward (block partial sums [N, gvf_lpips_tap_blocks(HW)], d[n] = their sum / HW), one pass backward (gradient of fx). */
 GVF_API int gvf_lpips_tap_blocks(int HW);
+/* Glue between the criterion's cuDNN convolutions on channels-last fp16 activations: x[p, c] = max(x[p, c] + bias[c], 0) in
+ * place (C % 8 == 0), and the 2 x 2 / stride 2 max pool with its backward (first maximum of a window gets the gradient). */
+GVF_API int gvf_bias_relu_nhwc_f16(void* x, const float* bias, long long pixels, int C, void* stream);
+GVF_API int gvf_maxpool2_nhwc_f16(const void* x, void* y, int N, int H, int W, int C, void* stream);
+GVF_API int gvf_maxpool2_nhwc_bwd_f16(const void* x, const void* y, const void* gy, void* gx, int N, int H, int W, int C,
+                                      void* stream);
 GVF_API int gvf_lpips_tap_fwd(const void* fx, const void* fy, const float* w, int N, int HW, int C, float* partial, void* stream);
 GVF_API int gvf_lpips_tap_bwd(const void* fx, const void* fy, const float* w, const float* gout, int N, int HW, int C, void* gfx,
                               void* stream);
