@@ -187,6 +187,16 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = None
+
+
 def current_stream():
+    """cudaStream_t of torch's current stream on the current device.  Through torch's raw accessor when it exists: building a
+    torch.cuda.Stream object per launch (torch.cuda.current_stream()) costs ~6 us, a tenth of a launch-heavy training step."""
+    global _raw_stream
     import torch
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -126,7 +126,10 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("decode runs on a CUDA device only (no CPU fallback)")
-            self._engine = VAEDecodeEngine(self.state_dict(), self.heads, self.num_timesteps, dev, self.chunk_size)
+            if self._engine is not None and self._engine.dev == dev:
+                self._engine.refresh(self.state_dict())          # same buffers, new values (optimiser step)
+            else:
+                self._engine = VAEDecodeEngine(self.state_dict(), self.heads, self.num_timesteps, dev, self.chunk_size)
             self._sig = sig
         return self._engine
 
@@ -139,7 +142,10 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("encode runs on a CUDA device only (no CPU fallback)")
-            self._enc_engine = VAEEncodeEngine(self.state_dict(), self.heads, self.num_latents, self.knn_k, self.beta, dev)
+            if self._enc_engine is not None and self._enc_engine.dev == dev:
+                self._enc_engine.refresh(self.state_dict())
+            else:
+                self._enc_engine = VAEEncodeEngine(self.state_dict(), self.heads, self.num_latents, self.knn_k, self.beta, dev)
             self._enc_sig = sig
         return self._enc_engine
 
@@ -149,7 +155,10 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("decode runs on a CUDA device only (no CPU fallback)")
-            self._train_engine = VAEDecodeTrainEngine(self.state_dict(), self.heads, self.num_timesteps, dev)
+            if self._train_engine is not None and self._train_engine.dev == dev:
+                self._train_engine.refresh(self.state_dict())
+            else:
+                self._train_engine = VAEDecodeTrainEngine(self.state_dict(), self.heads, self.num_timesteps, dev)
             self._train_sig = sig
         return self._train_engine
 

@@ -35,11 +35,29 @@ class VAEEncodeEngine:
             self.w1g, self.b1g = ops.geglu_interleave(self.w1, self.b1)
         # mean_fc and logvar_fc as one GEMM
         self.latent = sd["mean_fc.weight"].shape[0]
-        wm = torch.cat([sd["mean_fc.weight"].detach().float().cpu(), sd["logvar_fc.weight"].detach().float().cpu()], 0)
-        bm = torch.cat([sd["mean_fc.bias"].detach().float().cpu(), sd["logvar_fc.bias"].detach().float().cpu()], 0)
+        wm = torch.cat([sd["mean_fc.weight"].detach().float().to(dev), sd["logvar_fc.weight"].detach().float().to(dev)], 0)
+        bm = torch.cat([sd["mean_fc.bias"].detach().float().to(dev), sd["logvar_fc.bias"].detach().float().to(dev)], 0)
         pad = (-wm.shape[0]) % 8
-        self.w_ml = h(torch.cat([wm, torch.zeros(pad, wm.shape[1])], 0))
-        self.b_ml = b(torch.cat([bm, torch.zeros(pad)], 0))
+        self.w_ml = h(torch.cat([wm, torch.zeros(pad, wm.shape[1], device=dev)], 0))
+        self.b_ml = b(torch.cat([bm, torch.zeros(pad, device=dev)], 0))
+
+    def refresh(self, sd):
+        """New parameter values into the same device buffers (see VAEDecodeEngine.refresh)."""
+        a, f, lat = "cross_attend_blocks.0.fn.", "cross_attend_blocks.1.fn.", self.latent
+        dw = [self.w_in, self.w_q, self.w_kv, self.w_out, self.w1, self.w2, self.w_ml[:lat], self.w_ml[lat:2 * lat]]
+        sw = [sd["input_embedding.0.weight"], sd[a + "to_q.weight"], sd[a + "to_kv.weight"], sd[a + "to_out.weight"],
+              sd[f + "net.0.weight"], sd[f + "net.2.weight"], sd["mean_fc.weight"], sd["logvar_fc.weight"]]
+        db = [self.b_in, self.b_out, self.b1, self.b2, self.b_ml[:lat], self.b_ml[lat:2 * lat]]
+        sb = [sd["input_embedding.0.bias"], sd[a + "to_out.bias"], sd[f + "net.0.bias"], sd[f + "net.2.bias"], sd["mean_fc.bias"],
+              sd["logvar_fc.bias"]]
+        with torch.no_grad():
+            torch._foreach_copy_(dw, [t.detach() for t in sw])
+            torch._foreach_copy_(db, [t.detach().to(F16) for t in sb])
+            if hasattr(self, "w1g"):
+                self.w1g, self.b1g = ops.geglu_interleave(self.w1, self.b1)
+            if hasattr(self, "w_q_t"):
+                for n in ("w_q", "w_kv", "w_out", "w1", "w2", "w_ml"):
+                    ops.transpose(getattr(self, n), out=getattr(self, n + "_t"))
 
     def _embed(self, disp, xyz, rows_per_xyz_row):
         """disp [R, 3] fp32 per (batch, frame, point) row, xyz [B * n, 3] per point -> fp32 [R, dim]."""

@@ -35,8 +35,8 @@ class VAEDecodeEngine:
         for i in range(self.depth):
             a, f = f"layers.{i}.0.fn.", f"layers.{i}.1.fn."
             self.layers.append(dict(
-                w_qkv=_h(torch.cat([sd[a + "to_q.weight"].detach().float().cpu(),
-                                    sd[a + "to_kv.weight"].detach().float().cpu()], 0), dev),
+                w_qkv=_h(torch.cat([sd[a + "to_q.weight"].detach().float().to(dev),
+                                    sd[a + "to_kv.weight"].detach().float().to(dev)], 0), dev),
                 w_out=_h(sd[a + "to_out.weight"], dev), b_out=_b(sd[a + "to_out.bias"], dev),
                 w1=_h(sd[f + "net.0.weight"], dev), b1=_b(sd[f + "net.0.bias"], dev),
                 w2=_h(sd[f + "net.2.weight"], dev), b2=_b(sd[f + "net.2.bias"], dev)))
@@ -47,11 +47,34 @@ class VAEDecodeEngine:
         c = "decoder_cross_attn.fn."
         self.w_dq, self.w_dkv = _h(sd[c + "to_q.weight"], dev), _h(sd[c + "to_kv.weight"], dev)
         self.w_dout, self.b_dout = _h(sd[c + "to_out.weight"], dev), _b(sd[c + "to_out.bias"], dev)
-        wo, bo = sd["to_outputs.weight"].detach().float().cpu(), sd["to_outputs.bias"].detach().float().cpu()
+        wo, bo = sd["to_outputs.weight"].detach().float().to(dev), sd["to_outputs.bias"].detach().float().to(dev)
         self.out_dim = wo.shape[0]
         pad = (-self.out_dim) % 8
-        self.w_o = _h(torch.cat([wo, torch.zeros(pad, wo.shape[1])], 0), dev)      # rows padded to 16
-        self.b_o = _b(torch.cat([bo, torch.zeros(pad)], 0), dev)
+        self.w_o = _h(torch.cat([wo, torch.zeros(pad, wo.shape[1], device=dev)], 0), dev)      # rows padded to 16
+        self.b_o = _b(torch.cat([bo, torch.zeros(pad, device=dev)], 0), dev)
+
+    def refresh(self, sd):
+        """New parameter values into the SAME device buffers (after an optimiser step): device-side foreach casts, no host
+        round trip, no allocation (the constructor's cost per training step otherwise)."""
+        dim = self.dim
+        dw, sw, db, sb = [self.w_proj], [sd["proj.weight"]], [self.b_proj], [sd["proj.bias"]]
+        for i, ly in enumerate(self.layers):
+            a, f = f"layers.{i}.0.fn.", f"layers.{i}.1.fn."
+            dw += [ly["w_qkv"][:dim], ly["w_qkv"][dim:], ly["w_out"], ly["w1"], ly["w2"]]
+            sw += [sd[a + "to_q.weight"], sd[a + "to_kv.weight"], sd[a + "to_out.weight"], sd[f + "net.0.weight"], sd[f + "net.2.weight"]]
+            db += [ly["b_out"], ly["b1"], ly["b2"]]
+            sb += [sd[a + "to_out.bias"], sd[f + "net.0.bias"], sd[f + "net.2.bias"]]
+        c = "decoder_cross_attn.fn."
+        dw += [self.w_gs, self.w_dq, self.w_dkv, self.w_dout, self.w_o[:self.out_dim]]
+        sw += [sd["gs_embedding.0.weight"], sd[c + "to_q.weight"], sd[c + "to_kv.weight"], sd[c + "to_out.weight"], sd["to_outputs.weight"]]
+        db += [self.b_gs, self.b_dout, self.b_o[:self.out_dim]]
+        sb += [sd["gs_embedding.0.bias"], sd[c + "to_out.bias"], sd["to_outputs.bias"]]
+        with torch.no_grad():
+            torch._foreach_copy_(dw, [t.detach() for t in sw])
+            torch._foreach_copy_(db, [t.detach().to(F16) for t in sb])              # fp16-valued fp32 biases
+            for ly in self.layers:
+                if "w1g" in ly:
+                    ly["w1g"], ly["b1g"] = ops.geglu_interleave(ly["w1"], ly["b1"])
 
     def latent_layers(self, z):
         """z [(B*T), L, latent] fp32 -> x [(B*T)*L, dim] fp16 after proj + depth x (attn, GEGLU FF)."""

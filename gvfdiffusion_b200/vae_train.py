@@ -30,6 +30,17 @@ class VAEDecodeTrainEngine(VAEDecodeEngine):
         self.w_dq_t, self.w_dkv_t, self.w_dout_t = T_(self.w_dq), T_(self.w_dkv), T_(self.w_dout)
         self.w_o_t = self.w_o[:self.out_dim].t().contiguous()            # [dim, out_dim]: d lat = d out @ w_o
 
+    def refresh(self, sd):
+        super().refresh(sd)
+        with torch.no_grad():
+            for ly in self.layers:
+                for n in ("w_qkv", "w_out", "w1", "w2"):
+                    ops.transpose(ly[n], out=ly[n + "_t"])
+            ops.transpose(self.w_dq, out=self.w_dq_t)
+            ops.transpose(self.w_dkv, out=self.w_dkv_t)
+            ops.transpose(self.w_dout, out=self.w_dout_t)
+            self.w_o_t.copy_(self.w_o[:self.out_dim].t())
+
     # ------------------------------------------------------------------------------------------------ forward
     def forward_train(self, z, queries):
         """z [(B*T), L, latent] fp32, queries [B, Q, 14] fp32 -> (out [B, T, Q, out_dim] fp32, saved activations)."""

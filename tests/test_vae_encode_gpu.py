@@ -136,3 +136,44 @@ def test_model_forward_is_differentiable_end_to_end():
     for n in v._enc_names + v._param_names:
         assert named[n].grad is not None and torch.isfinite(named[n].grad).all(), n
     assert float(named["cross_attend_blocks.0.fn.to_q.weight"].grad.abs().max()) > 0
+
+
+def test_engines_refresh_in_place_after_an_optimiser_step():
+    """After optimiser steps the three engines (inference decode, training decode, encode) keep their device buffers and
+    take the new values by device-side casts (`refresh`): forward + backward of the stepped model must equal a model built
+    fresh from its state dict, and the weight buffers must not have moved."""
+    from gvfdiffusion_b200.model.autoencoder import GSKLTemporalVariationalAutoEncoder as VAE
+    g = torch.load(os.path.join(G, "vae_encode_tiny.pt"), weights_only=False)
+    dec = torch.load(os.path.join(G, "vae_tiny.pt"), weights_only=False)
+    v = VAE(**g["cfg"])
+    v.load_state_dict({**dec["state_dict"], **g["state_dict"]})
+    v = v.to(DEV)
+    gs, pc, dpc = [t.to(DEV) for t in g["static_gs"]], g["static_pc"].to(DEV), g["delta_pc"].to(DEV)
+    noise = torch.randn(pc.shape[0] * g["cfg"]["num_timesteps"], g["cfg"]["num_latents"], g["cfg"]["latent_dim"],
+                        generator=torch.Generator().manual_seed(2)).to(DEV)
+    opt = torch.optim.SGD(v.parameters(), lr=1e-3)
+    ptrs = None
+    for it in range(2):                                    # step twice: the second forward runs on refreshed engines
+        out = v(gs, pc, dpc, noise=noise)
+        (out["logits"].square().sum() + out["kl"].sum()).backward()
+        with torch.no_grad():
+            v.decode(out["posterior"]["mean"], torch.stack([t[:64] for t in gs]))      # builds the inference engine too
+        now = (v.train_engine().layers[0]["w_qkv"].data_ptr(), v.train_engine().layers[0]["w1_t"].data_ptr(),
+               v.encode_engine().w_kv.data_ptr(), v.engine().w_dkv.data_ptr())
+        assert ptrs is None or now == ptrs
+        ptrs = now
+        opt.step()
+        opt.zero_grad()
+    fresh = VAE(**g["cfg"])
+    fresh.load_state_dict(v.state_dict())
+    fresh = fresh.to(DEV)
+    o1, o2 = v(gs, pc, dpc, noise=noise), fresh(gs, pc, dpc, noise=noise)
+    assert torch.equal(o1["logits"], o2["logits"]) and torch.equal(o1["kl"], o2["kl"])
+    (o1["logits"].square().sum() + o1["kl"].sum()).backward()
+    (o2["logits"].square().sum() + o2["kl"].sum()).backward()
+    a, b = dict(v.named_parameters()), dict(fresh.named_parameters())
+    for n in v._enc_names + v._param_names:
+        assert rel(a[n].grad, b[n].grad) < 1e-5, n         # split-K reduce-adds arrive in any order
+    with torch.no_grad():
+        q = torch.stack([t[:64] for t in gs])
+        assert torch.equal(v.decode(o1["posterior"]["mean"], q), fresh.decode(o2["posterior"]["mean"], q))
