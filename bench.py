@@ -262,7 +262,8 @@ def main():
         mon.start()
         if args.config == "cfg5":
             from tools import cfg5_step_bench as C5
-            res = C5.measure(steps=args.steps, warmup=max(args.warmup, 3), seed=rank, world=world, device=dev)
+            res = C5.measure(steps=args.steps, warmup=max(args.warmup, 3), seed=rank, world=world, device=dev,
+                             standin=(not args.no_gpu_reference) and world == 1)
         else:
             from tools import static_vae_step_bench as SVB
             res = SVB.measure(steps=args.steps, warmup=max(args.warmup, 3), standin=not args.no_gpu_reference, seed=rank, device=dev)

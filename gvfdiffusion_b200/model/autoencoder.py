@@ -19,7 +19,7 @@ class _DecodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, z, queries, *params):
-        eng = module.train_engine()
+        eng = module.train_engine(force_refresh=True)
         out, saved = eng.forward_train(z, queries)
         ctx.eng, ctx.saved, ctx.names = eng, saved, module._param_names
         ctx.z_shape, ctx.q_dtype = z.shape, queries.dtype
@@ -38,7 +38,7 @@ class _EncodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, static_pc, delta_pc, gs_list, noise, *params):
-        eng = module.encode_engine()
+        eng = module.encode_engine(force_refresh=True)
         o, saved = eng.forward_train(static_pc, delta_pc, gs_list, noise)
         ctx.eng, ctx.saved, ctx.names = eng, saved, module._enc_names
         ctx.mark_non_differentiable(o["mean"], o["logvar"], o["sampled_static_gs"])
@@ -120,6 +120,16 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         self._encoder_loaded = not missing              # decode-only checkpoints are fine for decode()
         return super().load_state_dict(sub, strict=False)
 
+    def train(self, mode=True):
+        """Switching between training and evaluation invalidates the engines' weight copies: parameters updated by a fused
+        optimiser carry no version bump (see train_engine), so the inference engine must not trust its signature."""
+        self._sig = self._enc_sig = self._train_sig = None
+        return super().train(mode)
+
+    def refresh_engines(self):
+        """Force every existing engine to re-read the parameters at its next use."""
+        self._sig = self._enc_sig = self._train_sig = None
+
     def engine(self):
         sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._engine is None or sig != self._sig:
@@ -133,12 +143,12 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
             self._sig = sig
         return self._engine
 
-    def encode_engine(self):
+    def encode_engine(self, force_refresh=False):
         if not self._encoder_loaded:
             raise RuntimeError("this checkpoint carried no encoder weights (cross_attend_blocks / input_embedding / mean_fc / "
                                "logvar_fc)")
         sig = tuple((p.data_ptr(), p._version) for n, p in self.named_parameters() if n.startswith(self._ENC))
-        if self._enc_engine is None or sig != self._enc_sig:
+        if self._enc_engine is None or sig != self._enc_sig or force_refresh:
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("encode runs on a CUDA device only (no CPU fallback)")
@@ -149,9 +159,13 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
             self._enc_sig = sig
         return self._enc_engine
 
-    def train_engine(self):
+    def train_engine(self, force_refresh=False):
+        """force_refresh (the training Functions pass it): take the parameter values anew even when the version counters
+        have not moved -- torch's FUSED optimisers update parameters without bumping `_version` (measured with
+        AdamW(fused=True): the engines kept stepping on the initial weights), so under autograd the copies are refreshed on
+        every forward (a foreach cast + the transposes, ~1 ms)."""
         sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self._train_engine is None or sig != self._train_sig:
+        if self._train_engine is None or sig != self._train_sig or force_refresh:
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("decode runs on a CUDA device only (no CPU fallback)")

@@ -23,7 +23,7 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, feats, coords, noise, *params):
-        eng = module.engine()
+        eng = module.engine(force_refresh=True)
         out, mean, logvar, kl, saved = eng.forward_train(feats, coords, noise)
         ctx.eng, ctx.saved, ctx.names = eng, saved, module._names
         ctx.mark_non_differentiable(mean, logvar)
@@ -87,8 +87,17 @@ class SparseTransformerVAE(nn.Module):
                 p.requires_grad_(False)
 
     # ---------------------------------------------------------------------------------------- engine
-    def engine(self):
-        """The device engine over the current parameter values (fp16 copies refreshed in place when they changed)."""
+    def train(self, mode=True):
+        self._sig = None              # fused optimisers do not bump version counters: re-read the weights after a mode switch
+        return super().train(mode)
+
+    def refresh_engines(self):
+        self._sig = None
+
+    def engine(self, force_refresh=False):
+        """The device engine over the current parameter values (fp16 copies refreshed in place when they changed).
+        force_refresh (the training Function passes it): torch's FUSED optimisers update parameters without bumping their
+        version counters, so under autograd the copies are refreshed on every forward."""
         named = dict(self.named_parameters())
         sig = tuple((p.data_ptr(), p._version) for p in named.values())
         if self._engine is None:
@@ -97,7 +106,7 @@ class SparseTransformerVAE(nn.Module):
             self._engine = _Engine({k: v.detach() for k, v in named.items()}, self.num_blocks, self.num_heads, self.window_size,
                                    use_fp16=self.use_fp16, norm_output=self.norm_output, device=self.device,
                                    use_old_attn_impl=self.use_old_attn_impl)
-        elif sig != self._sig:
+        elif sig != self._sig or force_refresh:
             self._engine.refresh({k: v.detach() for k, v in named.items()})
         self._sig = sig
         return self._engine

@@ -270,7 +270,7 @@ def test_sparse_transformer_vae_module_trains_and_refreshes_in_place():
     for n, p in m.named_parameters():          # split-K partial tiles are summed by TMA reduce-add in arrival order
         assert p.grad is not None and rl(p.grad, g2[n]) < 1e-5, n
     ptr0 = m.engine().decoder.blocks[0]["w_qkv"].data_ptr()
-    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    opt = torch.optim.AdamW(m.parameters(), lr=0.01, fused=True)     # fused: no version bump on the parameters
     opt.step()
     out3, _, _ = m(x, noise=noise)                                     # refreshes the engine in place
     assert m.engine().decoder.blocks[0]["w_qkv"].data_ptr() == ptr0

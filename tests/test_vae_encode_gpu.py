@@ -151,7 +151,9 @@ def test_engines_refresh_in_place_after_an_optimiser_step():
     gs, pc, dpc = [t.to(DEV) for t in g["static_gs"]], g["static_pc"].to(DEV), g["delta_pc"].to(DEV)
     noise = torch.randn(pc.shape[0] * g["cfg"]["num_timesteps"], g["cfg"]["num_latents"], g["cfg"]["latent_dim"],
                         generator=torch.Generator().manual_seed(2)).to(DEV)
-    opt = torch.optim.SGD(v.parameters(), lr=1e-3)
+    # AdamW(fused=True) updates the parameters WITHOUT bumping their version counters: the training Functions refresh the
+    # engines on every forward, the inference engine after train() / eval() switches
+    opt = torch.optim.AdamW(v.parameters(), lr=1e-3, fused=True)
     ptrs = None
     for it in range(2):                                    # step twice: the second forward runs on refreshed engines
         out = v(gs, pc, dpc, noise=noise)
@@ -167,6 +169,8 @@ def test_engines_refresh_in_place_after_an_optimiser_step():
     fresh = VAE(**g["cfg"])
     fresh.load_state_dict(v.state_dict())
     fresh = fresh.to(DEV)
+    v.eval()
+    v.train()                                              # mode switch: the inference engine re-reads the weights too
     o1, o2 = v(gs, pc, dpc, noise=noise), fresh(gs, pc, dpc, noise=noise)
     assert torch.equal(o1["logits"], o2["logits"]) and torch.equal(o1["kl"], o2["kl"])
     (o1["logits"].square().sum() + o1["kl"].sum()).backward()
