@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from ..vae_encode import VAEEncodeEngine
+from .. import _param_epoch
 from ..vae_engine import VAEDecodeEngine
 from ..vae_train import VAEDecodeTrainEngine
 
@@ -19,7 +20,7 @@ class _DecodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, z, queries, *params):
-        eng = module.train_engine(force_refresh=True)
+        eng = module.train_engine(force_refresh=not _param_epoch.HOOKED)
         out, saved = eng.forward_train(z, queries)
         ctx.eng, ctx.saved, ctx.names = eng, saved, module._param_names
         ctx.z_shape, ctx.q_dtype = z.shape, queries.dtype
@@ -38,7 +39,7 @@ class _EncodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, static_pc, delta_pc, gs_list, noise, *params):
-        eng = module.encode_engine(force_refresh=True)
+        eng = module.encode_engine(force_refresh=not _param_epoch.HOOKED)
         o, saved = eng.forward_train(static_pc, delta_pc, gs_list, noise)
         ctx.eng, ctx.saved, ctx.names = eng, saved, module._enc_names
         ctx.mark_non_differentiable(o["mean"], o["logvar"], o["sampled_static_gs"])
@@ -131,7 +132,7 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         self._sig = self._enc_sig = self._train_sig = None
 
     def engine(self):
-        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        sig = (_param_epoch.epoch(),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._engine is None or sig != self._sig:
             dev = next(self.parameters()).device
             if dev.type != "cuda":
@@ -147,7 +148,7 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         if not self._encoder_loaded:
             raise RuntimeError("this checkpoint carried no encoder weights (cross_attend_blocks / input_embedding / mean_fc / "
                                "logvar_fc)")
-        sig = tuple((p.data_ptr(), p._version) for n, p in self.named_parameters() if n.startswith(self._ENC))
+        sig = (_param_epoch.epoch(),) + tuple((p.data_ptr(), p._version) for n, p in self.named_parameters() if n.startswith(self._ENC))
         if self._enc_engine is None or sig != self._enc_sig or force_refresh:
             dev = next(self.parameters()).device
             if dev.type != "cuda":
@@ -160,11 +161,10 @@ class GSKLTemporalVariationalAutoEncoder(nn.Module):
         return self._enc_engine
 
     def train_engine(self, force_refresh=False):
-        """force_refresh (the training Functions pass it): take the parameter values anew even when the version counters
-        have not moved -- torch's FUSED optimisers update parameters without bumping `_version` (measured with
-        AdamW(fused=True): the engines kept stepping on the initial weights), so under autograd the copies are refreshed on
-        every forward (a foreach cast + the transposes, ~1 ms)."""
-        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """The signature that decides whether the engine's copies are current = optimiser-step counter (_param_epoch: torch's
+        FUSED optimisers update parameters without bumping `_version` -- measured with AdamW(fused=True), the engines kept
+        stepping on the initial weights) + every parameter's (data_ptr, _version).  force_refresh re-reads regardless."""
+        sig = (_param_epoch.epoch(),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._train_engine is None or sig != self._train_sig or force_refresh:
             dev = next(self.parameters()).device
             if dev.type != "cuda":

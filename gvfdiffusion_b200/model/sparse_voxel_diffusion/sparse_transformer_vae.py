@@ -11,7 +11,7 @@ Only the shipped configuration family is built: attn_mode "swin", pe_mode "ape",
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import _param_epoch, ops
 from ...sparse.basic import SparseTensor
 from ...sparse.transformer import SparseTransformerVAE as _Engine
 
@@ -23,7 +23,7 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, feats, coords, noise, *params):
-        eng = module.engine(force_refresh=True)
+        eng = module.engine(force_refresh=not _param_epoch.HOOKED)
         out, mean, logvar, kl, saved = eng.forward_train(feats, coords, noise)
         ctx.eng, ctx.saved, ctx.names = eng, saved, module._names
         ctx.mark_non_differentiable(mean, logvar)
@@ -96,10 +96,10 @@ class SparseTransformerVAE(nn.Module):
 
     def engine(self, force_refresh=False):
         """The device engine over the current parameter values (fp16 copies refreshed in place when they changed).
-        force_refresh (the training Function passes it): torch's FUSED optimisers update parameters without bumping their
-        version counters, so under autograd the copies are refreshed on every forward."""
+        "Changed" = any optimiser step since (gvfdiffusion_b200/_param_epoch.py: torch's FUSED optimisers update parameters
+        without bumping their version counters) or a moved (data_ptr, _version); force_refresh re-reads regardless."""
         named = dict(self.named_parameters())
-        sig = tuple((p.data_ptr(), p._version) for p in named.values())
+        sig = (_param_epoch.epoch(),) + tuple((p.data_ptr(), p._version) for p in named.values())
         if self._engine is None:
             if self.device.type != "cuda":
                 raise RuntimeError("SparseTransformerVAE runs on a CUDA device only (no CPU fallback)")
