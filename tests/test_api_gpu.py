@@ -184,3 +184,31 @@ def test_prepare_object_async_equals_sync():
     torch.cuda.synchronize()
     for o in (b, c):
         assert torch.equal(a.static_gs, o.static_gs) and torch.equal(a.fps512, o.fps512) and torch.equal(a.fps4096, o.fps4096)
+
+
+@pytest.mark.parametrize("softplus,min_kernel", [(True, 0.0009), (False, 0.0)])
+def test_gaussian_tensor_backward_matches_autograd(softplus, min_kernel):
+    """get_gaussian_tensor under autograd (gvf_gaussian_tensor_bwd; train_vae.py:285-293 sends the deformation losses back to
+    the static VAE through it) against torch autograd of the oracle's activations: fp32, 1e-5."""
+    from gvfdiffusion_b200.representations.gaussian import GaussianModel
+    g = torch.Generator().manual_seed(5)
+    P = 777
+    canon = {"_xyz": torch.rand(P, 3, generator=g), "_features_dc": torch.randn(P, 1, 3, generator=g),
+             "_scaling": torch.randn(P, 3, generator=g), "_rotation": torch.randn(P, 4, generator=g) * 0.5,
+             "_opacity": torch.randn(P, 1, generator=g)}
+    gm = GaussianModel(sh_degree=0, mininum_kernel_size=min_kernel, scaling_bias=0.004, opacity_bias=0.1,
+                       scaling_activation="softplus" if softplus else "exp", device=DEV)
+    leaves = {k: v.to(DEV).requires_grad_(True) for k, v in canon.items()}
+    gm._xyz, gm._features_dc, gm._scaling, gm._rotation, gm._opacity = (leaves[k] for k in
+                                                                       ("_xyz", "_features_dc", "_scaling", "_rotation", "_opacity"))
+    w = torch.randn(P, 14, generator=g)
+    gt = gm.gaussian_tensor()
+    assert gt.requires_grad
+    (gt * w.to(DEV)).sum().backward()
+    ref_leaves = {k: v.clone().requires_grad_(True) for k, v in canon.items()}
+    ref = OG.gaussian_tensor(ref_leaves, gm.constants())
+    (ref * w).sum().backward()
+    assert torch.allclose(gt.detach().cpu(), ref.detach(), rtol=3e-6, atol=1e-7)
+    for k in canon:
+        a, b = leaves[k].grad.cpu().reshape(-1), ref_leaves[k].grad.reshape(-1)
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-7, k
