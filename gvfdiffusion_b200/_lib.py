@@ -66,6 +66,7 @@ _SIGS = {
     "gvf_colsum": (C.c_int, [_P, C.c_int, C.c_longlong, C.c_int, C.c_longlong, _P, C.c_size_t, _P, C.c_int, _P]),
     "gvf_ln_bwd_f16": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
     "gvf_geglu_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P, _P]),
+    "gvf_sparse_attn_set_tma": (None, [C.c_int]),
     "gvf_sparse_packed_attn_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "gvf_sparse_packed_attn_bwd_f16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                                  C.c_float, _P]),

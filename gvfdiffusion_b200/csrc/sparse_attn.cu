@@ -25,6 +25,7 @@
 // column takes part iff its position falls inside it.  4x fewer CTAs, all rows busy: 33 -> ~10 us per launch at 4096 voxels.
 #include "../../include/gvf_b200.h"
 #include "tc_common.cuh"
+#include "tma_host.h"
 
 namespace gvf {
 using namespace tc;
@@ -69,16 +70,39 @@ __device__ __forceinline__ void stage_rows(uint32_t dst, const __half* __restric
   }
 }
 
+// TMA staging (TMA = true): the 64 rows of a tile are fetched by 16 `cp.async.bulk.tensor ... tile::gather4` instructions
+// (four gathered rows of 128 B each, out-of-range rows zero-filled) through one tensor map over qkv viewed as [T, 3 H 64],
+// SWIZZLE_128B -- the same XOR pattern `slot` implements -- completing on an mbarrier, instead of 512 per-thread cp.async
+// copies with their address arithmetic.  The gather stays fused into the staging load; only lanes 0-15 of warp 0 issue.
+__device__ __forceinline__ void stage_rows_tma(uint32_t dst, const CUtensorMap* map, uint64_t* bar, const int* __restrict__ idx,
+                                               int r0, int rend, int col, int tid) {
+  if (tid < 16) {
+    int rr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pos = r0 + 4 * tid + j;
+      rr[j] = pos < rend ? (idx ? __ldg(idx + pos) : pos) : -1;          // -1: outside the tensor -> zeros
+    }
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst + (uint32_t)tid * 512u),
+        "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(rr[0]), "r"(rr[1]), "r"(rr[2]), "r"(rr[3])
+        : "memory");
+  }
+}
+
 // PACKED = false: CTA = (64-row tile blockIdx.x of sequence blockIdx.z, head).  PACKED = true: CTA = (positions
 // [64 blockIdx.x, +64) of the whole list, head); seq_of_pos[p] = sequence of position p, M = total positions.
-template <bool PACKED>
-__global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
+template <bool PACKED, bool TMA>
+__global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __grid_constant__ CUtensorMap mapQKV,
+                                                                const __half* __restrict__ qkv, __half* __restrict__ out,
                                                                 const int* __restrict__ fwd_idx,
                                                                 const int* __restrict__ out_idx,
                                                                 const int* __restrict__ cu_seqlens,
                                                                 const int* __restrict__ seq_of_pos, int M, int H,
                                                                 float scale_log2e, float* __restrict__ lse2) {
-  __shared__ __align__(128) uint8_t sm[(1 + 4) * 64 * 128];     // Q | K0 V0 | K1 V1   (40 KB)
+  __shared__ __align__(1024) uint8_t sm[(1 + 4) * 64 * 128];    // Q | K0 V0 | K1 V1   (40 KB)
+  __shared__ uint64_t bar_q, bar_kv[2];
   const int h = blockIdx.y;
   // positions: query tile [p0, pend) (at most 64), key range [kbeg, kend)
   int p0, pend, kbeg, kend;
@@ -109,10 +133,28 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
     else { lo[r] = kbeg; hi[r] = kend; }
   }
 
-  stage_rows(sQ, qkv, idx, 0, p0, pend, 0, h, H, tid);
-  stage_rows(sKV, qkv, idx, 0, kbeg, kend, 1, h, H, tid);
-  stage_rows(sKV + 64 * 128, qkv, idx, 0, kbeg, kend, 2, h, H, tid);
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(&bar_q, 1);
+      mbar_init(&bar_kv[0], 1);
+      mbar_init(&bar_kv[1], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar_q, 64 * 128);
+      mbar_arrive_expect_tx(&bar_kv[0], 2 * 64 * 128);
+    }
+    __syncwarp();
+    stage_rows_tma(sQ, &mapQKV, &bar_q, idx, p0, pend, h * kD, tid);
+    stage_rows_tma(sKV, &mapQKV, &bar_kv[0], idx, kbeg, kend, (H + h) * kD, tid);
+    stage_rows_tma(sKV + 64 * 128, &mapQKV, &bar_kv[0], idx, kbeg, kend, (2 * H + h) * kD, tid);
+  } else {
+    stage_rows(sQ, qkv, idx, 0, p0, pend, 0, h, H, tid);
+    stage_rows(sKV, qkv, idx, 0, kbeg, kend, 1, h, H, tid);
+    stage_rows(sKV + 64 * 128, qkv, idx, 0, kbeg, kend, 2, h, H, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 
   uint32_t qa[4][4];
   float o[8][4];
@@ -124,6 +166,17 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
 
   for (int j = 0; j < nchunks; ++j) {
     const uint32_t bK = sKV + (uint32_t)(j & 1) * 2 * 64 * 128, bV = bK + 64 * 128;
+    if (TMA) {
+      if (j + 1 < nchunks) {                       // the buffer was released by the __syncthreads that ended chunk j - 1
+        const uint32_t nK = sKV + (uint32_t)((j + 1) & 1) * 2 * 64 * 128;
+        if (tid == 0) mbar_arrive_expect_tx(&bar_kv[(j + 1) & 1], 2 * 64 * 128);
+        __syncwarp();
+        stage_rows_tma(nK, &mapQKV, &bar_kv[(j + 1) & 1], idx, kbeg + (j + 1) * kKB, kend, (H + h) * kD, tid);
+        stage_rows_tma(nK + 64 * 128, &mapQKV, &bar_kv[(j + 1) & 1], idx, kbeg + (j + 1) * kKB, kend, (2 * H + h) * kD, tid);
+      }
+      if (j == 0) mbar_wait(&bar_q, 0);
+      mbar_wait(&bar_kv[j & 1], (uint32_t)(j >> 1) & 1u);
+    } else {
     if (j + 1 < nchunks) {
       const uint32_t nK = sKV + (uint32_t)((j + 1) & 1) * 2 * 64 * 128;
       stage_rows(nK, qkv, idx, 0, kbeg + (j + 1) * kKB, kend, 1, h, H, tid);
@@ -133,6 +186,7 @@ __global__ void __launch_bounds__(128) sparse_window_attn_kernel(const __half* _
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    }
     if (j == 0) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) ldsm4(qa[ks], sQ + slot(16 * warp + (lane & 15), 2 * ks + (lane >> 4)));
@@ -260,8 +314,8 @@ extern "C" GVF_API int gvf_sparse_window_attn_f16(const void* qkv, void* out, co
   if (num_windows == 0 || max_seqlen == 0) return GVF_OK;
   if (num_windows > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_windows);
-  gvf::sparse_window_attn_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, fwd_idx, nullptr, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, nullptr);
+  gvf::sparse_window_attn_kernel<false, false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+      CUtensorMap{}, (const __half*)qkv, (__half*)out, fwd_idx, nullptr, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, nullptr);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -280,8 +334,8 @@ extern "C" GVF_API int gvf_sparse_varlen_attn_f16(const void* qkv, void* out, co
   if (num_seqs == 0 || max_seqlen == 0) return GVF_OK;
   if (num_seqs > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_seqs);
-  gvf::sparse_window_attn_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, nullptr);
+  gvf::sparse_window_attn_kernel<false, false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+      CUtensorMap{}, (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, nullptr);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
@@ -295,24 +349,43 @@ extern "C" GVF_API int gvf_sparse_varlen_attn_lse_f16(const void* qkv, void* out
   if (num_seqs == 0 || max_seqlen == 0) return GVF_OK;
   if (num_seqs > 65535 || H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((max_seqlen + gvf::kQB - 1) / gvf::kQB, H, num_seqs);
-  gvf::sparse_window_attn_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, lse2);
+  gvf::sparse_window_attn_kernel<false, false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+      CUtensorMap{}, (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, nullptr, 0, H, scale * 1.4426950408889634f, lse2);
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
 // Packed form of the three entry points above (see the file header): the sequences must be contiguous ranges of one
 // position list of M entries, seq_of_pos [M] int32 = the sequence a position belongs to (non-decreasing).  One CTA per 64
 // consecutive positions and head, whatever the sequence lengths.  lse2 may be NULL (inference).
+// 0 (default): per-thread cp.async staging, 1: TMA tile::gather4 staging.  Measured on B200 at the static VAE's shape
+// (tools/window_attn_bench.py, 2 x 2048 surface voxels, 12 heads): per-window tiling 30.7 us, packed + cp.async 17.7-18.3 us,
+// packed + TMA 18.8-18.9 us -- the kernel is bound by its chain of dependent index loads, not by the staging instructions,
+// so the bulk-tensor path buys nothing here and stays an option.
+static int g_sparse_attn_tma = 0;
+extern "C" GVF_API void gvf_sparse_attn_set_tma(int on) { g_sparse_attn_tma = on ? 1 : 0; }
+
 extern "C" GVF_API int gvf_sparse_packed_attn_f16(const void* qkv, void* out, float* lse2, const int* gather_idx,
                                                   const int* scatter_idx, const int* cu_seqlens, const int* seq_of_pos, int M,
                                                   int H, int D, float scale, void* stream) {
+  const int T_rows = M;               // windowed / full attention: the packed list is a permutation of the tensor's rows
   if (!qkv || !out || !cu_seqlens || !seq_of_pos || M < 0 || H <= 0) return GVF_ERR_INVALID;
   if (D != gvf::kD) return GVF_ERR_UNSUPPORTED;
   if (((uintptr_t)qkv | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
   if (M == 0) return GVF_OK;
   if (H > 65535) return GVF_ERR_UNSUPPORTED;
   const dim3 grid((M + gvf::kQB - 1) / gvf::kQB, H, 1);
-  gvf::sparse_window_attn_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, seq_of_pos, M, H, scale * 1.4426950408889634f, lse2);
+  if (g_sparse_attn_tma) {
+    // qkv as a 2-D tensor [rows, 3 H 64]: the gather lists address its rows, so the map must cover the largest row index --
+    // the caller's tensor has at least M rows (windowed / full attention: exactly M)
+    CUtensorMap map;
+    if (!gvf::make_tmap_2d(&map, qkv, 2, (uint64_t)3 * H * gvf::kD, (uint64_t)(T_rows > 0 ? T_rows : M), (uint64_t)3 * H * gvf::kD, 64, 1))
+      return GVF_ERR_CUDA;
+    gvf::sparse_window_attn_kernel<true, true><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        map, (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, seq_of_pos, M, H, scale * 1.4426950408889634f, lse2);
+  } else {
+    gvf::sparse_window_attn_kernel<true, false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        CUtensorMap{}, (const __half*)qkv, (__half*)out, gather_idx, scatter_idx, cu_seqlens, seq_of_pos, M, H,
+        scale * 1.4426950408889634f, lse2);
+  }
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }

@@ -84,3 +84,14 @@ def test_round2_kernels_are_blackwell_native(sass_by_kernel):
     gath = {k: b for k, b in _kernels(sass_by_kernel, "gemm_ws_kernel").items() if "ELb0ELb1EEEv" in k}
     assert trans and gath
     assert all(re.search(r"UTMALDG\S*(GATHER4|G4)", b) or "GATHER" in b for b in gath.values()), "no gather4 TMA load in the sparse-conv GEMM"
+
+
+def test_packed_window_attention_has_a_tma_gather_variant(sass_by_kernel):
+    """sparse_window_attn_kernel<PACKED, TMA = true>: rows staged by `cp.async.bulk.tensor ... tile::gather4` (UTMALDG) on an
+    mbarrier; the cp.async variant (the measured default) has none."""
+    ks = _kernels(sass_by_kernel, "sparse_window_attn_kernel")
+    tma = [b for k, b in ks.items() if "Lb1ELb1E" in k]
+    plain = [b for k, b in ks.items() if "Lb1ELb0E" in k]
+    assert tma and plain
+    assert all("UTMALDG" in b and "SYNCS" in b for b in tma)
+    assert all("UTMALDG" not in b and "LDGSTS" in b for b in plain)

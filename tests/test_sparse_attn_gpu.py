@@ -25,7 +25,7 @@ def _voxels(n_per_batch, res, batches, seed):
 @pytest.mark.parametrize("n,res,window,shift,H", [(1500, 64, 8, (0, 0, 0), 12), (1500, 64, 8, (4, 4, 4), 12),
                                                    (900, 16, 8, (0, 0, 0), 3),      # dense windows: up to 512 voxels, many key chunks
                                                    (70, 8, 8, (0, 0, 0), 2), (5, 32, 8, (4, 4, 4), 1)])
-@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("packed", [False, True, "tma"])
 def test_windowed_attention_matches_oracle(n, res, window, shift, H, packed):
     from gvfdiffusion_b200.sparse.attention import sparse_windowed_scaled_dot_product_self_attention
     from oracle import sparse_window as OSW
@@ -33,7 +33,12 @@ def test_windowed_attention_matches_oracle(n, res, window, shift, H, packed):
     g = torch.Generator().manual_seed(7)
     qkv = (torch.randn(coords.shape[0], 3, H, 64, generator=g) * 1.5).half()
     ref = OSW.windowed_attention(qkv, coords, window, shift)
-    out = sparse_windowed_scaled_dot_product_self_attention(qkv.to(DEV), coords.to(DEV), window, shift, packed=packed).float().cpu()
+    from gvfdiffusion_b200 import _lib
+    _lib.lib().gvf_sparse_attn_set_tma(int(packed == "tma"))        # rows staged by TMA tile::gather4 instead of cp.async
+    try:
+        out = sparse_windowed_scaled_dot_product_self_attention(qkv.to(DEV), coords.to(DEV), window, shift, packed=bool(packed)).float().cpu()
+    finally:
+        _lib.lib().gvf_sparse_attn_set_tma(0)
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-3, err       # packed: 64 consecutive sorted positions per CTA, rows masked to their own window
 
