@@ -184,3 +184,47 @@ def test_to_representation_backward_matches_autograd(kind, reg, perturb):
     assert (got[:, :lo] == 0).all() and (got[:, lo + 112:] == 0).all()
     err = (got - fr.grad).abs().max() / fr.grad.abs().max()
     assert err < 1e-5, float(err)
+
+
+def test_sparse_vae_training_losses_terms_and_gradients():
+    """SparseVAE.training_losses (sparse_vae.py:303-362) over the nn.Module backbone: the terms add up the way the reference
+    adds them, every backbone parameter receives a finite gradient through render -> to_representation -> decoder ->
+    posterior -> encoder, and the LPIPS term (seeded-random VGG16) changes the loss and the gradients."""
+    from gvfdiffusion_b200 import synthetic as S
+    from gvfdiffusion_b200.model.sparse_voxel_diffusion import SparseTransformerVAE, SparseVAE
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    torch.manual_seed(4)
+    rep = {"MipGS": {"lr": {"_xyz": 1.0, "_features_dc": 1.0, "_opacity": 1.0, "_scaling": 1.0, "_rotation": 0.1},
+                     "perturb_offset": True, "reg_mode": "soft_invoxel", "voxel_size": 1.5, "num_gaussians": 8,
+                     "2d_filter_kernel_size": 0.1, "3d_filter_kernel_size": 0.0009, "scaling_bias": 0.004, "opacity_bias": 0.1,
+                     "scaling_activation": "softplus"}}
+    reg = {"MipGS": {"lambda_vol": 10000.0, "lambda_opacity": 0.001}}
+    m = SparseTransformerVAE(32, 64, 128, 112, 8, 2, window_size=8, use_fp16=True, use_old_attn_impl=False, norm_output=True).to(DEV)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.startswith(("to_latent", "out_layer")) and n.endswith("weight"):
+                p.normal_(0, 0.05)
+    coords = _voxels(300, 32, 2, seed=8).to(DEV)
+    g = torch.Generator().manual_seed(9)
+    x = SparseTensor(torch.randn(600, 64, generator=g).to(DEV), coords)
+    noise = torch.randn(600, 8, generator=g).to(DEV)
+    ext, intr = S.orbit_extrinsics(2, radius=1.2), S.intrinsics(40.0)[None].repeat(2, 1, 1)
+    image = torch.rand(2, 3, 64, 64, generator=g).to(DEV)
+    out = {}
+    for lam in (0.0, 0.2):
+        fw = SparseVAE({"vae": m}, resolution=32, representation_config=rep, device=DEV, lambda_ssim=0.2, lambda_lpips=lam,
+                       lamda_kl=1e-6, regularizations=reg)
+        for p in m.parameters():
+            p.grad = None
+        terms, reps = fw.training_losses(x, image, ext, intr, noise=noise)
+        assert len(reps["MipGS"]) == 2 and reps["MipGS"][0]._xyz.shape == (300 * 8, 3)
+        rec = terms["MipGS_l1"] + 0.2 * terms["MipGS_ssim"] + (lam * terms["MipGS_lpips"] if lam else 0.0)
+        total = rec + 1e-6 * terms["kl"] + 10000.0 * terms["reg_MipGS_vol"] + 0.001 * terms["reg_MipGS_opacity"]
+        assert abs(float(terms["loss"].detach()) - float(total.detach())) < 1e-6 * abs(float(total.detach())) + 1e-7
+        (terms["loss"] * 65536.0).backward()
+        grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+        assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
+        assert float(grads["encoder.0.attn.to_qkv.weight"].abs().max()) > 0 and float(grads["out_layer.weight"].abs().max()) > 0
+        out[lam] = (float(terms["loss"].detach()), grads)
+    assert out[0.2][0] > out[0.0][0]
+    assert float((out[0.2][1]["out_layer.weight"] - out[0.0][1]["out_layer.weight"]).abs().max()) > 0
