@@ -83,6 +83,7 @@ _SIGS = {
     "gvf_lpips_tap_fwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gvf_lpips_tap_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gvf_gaussian_tensor_bwd": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gvf_gemm_nn_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "gvf_gelu_tanh_f16": (C.c_int, [_P, C.c_longlong, _P, _P]),
     "gvf_gelu_tanh_bwd_f16": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),
     "gvf_to_representation_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_float), C.c_float, C.c_int,

@@ -416,7 +416,10 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 // with 32 `cp.async.bulk.tensor.2d.tile::gather4` loads (lane l: rows 4 l .. 4 l + 3 of the tile, row indices read
 // from the neighbour map, out-of-range = zero-filled), each landing as four 128 B rows exactly where the one-box load
 // of the dense kernel would have put them (TMA swizzling is a function of the shared-memory address).
-template <int BN, int STAGES, int MODE, int NCTA, bool TRANS = false, bool GATHER = false>
+// TRANSB (NCTA = 1 only): only W is MN-major -- out[m, n] = sum_r A[m, r] W[r, n] with A [M, R] row-major (K-major, as in
+// the plain kernel) and W [R, N] row-major: the input gradient dX = dY W of a Linear straight from its [out, in] weight, no
+// transposed weight copy.  A is staged as one 128 x 64 box, W as BN / 64 boxes of 64 reduction rows like TRANS does.
+template <int BN, int STAGES, int MODE, int NCTA, bool TRANS = false, bool GATHER = false, bool TRANSB = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ CUtensorMap mapO, int M, int N, int K, GemmEpi ep, int ksplit) {
@@ -463,9 +466,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           uint8_t* st = smem + kb * STAGE_BYTES;
           if constexpr (TRANS) {
             for (int b = 0; b < kBM / 64; ++b) tma_load_2d(st + b * 8192, &mapA, &full_bar[kb], tile_m * kBM + b * 64, (kb0 + kb) * kBK);
-            for (int b = 0; b < BN / 64; ++b) tma_load_2d(st + A_BYTES + b * 8192, &mapW, &full_bar[kb], tile_n * BN + b * 64, (kb0 + kb) * kBK);
           } else {
             tma_load_2d(st, &mapA, &full_bar[kb], (kb0 + kb) * kBK, tile_m * kBM);
+          }
+          if constexpr (TRANS || TRANSB) {
+            for (int b = 0; b < BN / 64; ++b) tma_load_2d(st + A_BYTES + b * 8192, &mapW, &full_bar[kb], tile_n * BN + b * 64, (kb0 + kb) * kBK);
+          } else {
             tma_load_2d(st + A_BYTES, &mapW, &full_bar[kb], (kb0 + kb) * kBK, tile_n * BN);
           }
         }
@@ -526,9 +532,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
               tma_load_2d_2cta(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
               tma_load_2d_2cta(st + A_BYTES, &mapW, &full_bar[s], kb * kBK, tile_n * BN + (int)rank * WROWS);
-            } else if constexpr (TRANS) {
+            } else if constexpr (TRANS || TRANSB) {
               mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-              for (int b = 0; b < kBM / 64; ++b) tma_load_2d(st + b * 8192, &mapA, &full_bar[s], tile_m * kBM + b * 64, kb * kBK);
+              if constexpr (TRANS) {
+                for (int b = 0; b < kBM / 64; ++b) tma_load_2d(st + b * 8192, &mapA, &full_bar[s], tile_m * kBM + b * 64, kb * kBK);
+              } else {
+                tma_load_2d(st, &mapA, &full_bar[s], kb * kBK, tile_m * kBM);
+              }
               for (int b = 0; b < BN / 64; ++b) tma_load_2d(st + A_BYTES + b * 8192, &mapW, &full_bar[s], tile_n * BN + b * 64, kb * kBK);
             } else {
               mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -545,12 +555,16 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // MMA issuer (leader CTA of a pair): warp-uniform loop; the descriptors' high words are constants, the low
     // words (address >> 4 | LBO field) advance by adds; only tcgen05.mma / commit sit behind elect.sync
     if (rank == 0) {
-      const uint32_t idesc = make_idesc_f16(kBM * NCTA, BN, TRANS ? 1 : 0, TRANS ? 1 : 0);
-      constexpr uint32_t LBO = TRANS ? 8192u : 16u;          // MN-major: between 64-column blocks; K-major: unused
-      constexpr uint32_t KSTEP16 = TRANS ? 128u : 2u;        // descriptor advance per 16-deep k-step (16 B units)
-      const uint32_t d_hi = (uint32_t)(make_smem_desc(0, LBO, 1024, SWZ_128B) >> 32);
+      constexpr bool TA = TRANS, TB = TRANS || TRANSB;
+      const uint32_t idesc = make_idesc_f16(kBM * NCTA, BN, TA ? 1 : 0, TB ? 1 : 0);
+      constexpr uint32_t LBO = TA ? 8192u : 16u;             // MN-major: between 64-column blocks; K-major: unused
+      constexpr uint32_t LBO_W = TB ? 8192u : 16u;
+      constexpr uint32_t KSTEP16 = TA ? 128u : 2u;           // descriptor advance per 16-deep k-step (16 B units)
+      constexpr uint32_t KSTEP16_W = TB ? 128u : 2u;
+      const uint32_t d_hi = (uint32_t)(make_smem_desc(0, LBO, 1024, SWZ_128B) >> 32);      // SBO / swizzle: same for both
       const uint32_t a_lo0 = (uint32_t)make_smem_desc(smem_u32(smem), LBO, 1024, SWZ_128B);
-      constexpr uint32_t STAGE16 = STAGE_BYTES >> 4, A16 = A_BYTES >> 4;
+      // W's low word relative to A's: its address offset plus the difference of the LBO fields (bits 16..29)
+      constexpr uint32_t STAGE16 = STAGE_BYTES >> 4, A16 = (A_BYTES >> 4) + (((LBO_W >> 4) - (LBO >> 4)) << 16);
       const uint32_t b_full = smem_u32(&full_bar[0]), b_empty = smem_u32(&empty_bar[0]);
       int s = 0, lt = 0;
       uint32_t ph = 0, s_lo = a_lo0;
@@ -567,7 +581,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t ad = ((uint64_t)d_hi << 32) | (s_lo + KSTEP16 * k);
-              const uint64_t wd = ((uint64_t)d_hi << 32) | (s_lo + A16 + KSTEP16 * k);
+              const uint64_t wd = ((uint64_t)d_hi << 32) | (s_lo + A16 + KSTEP16_W * k);
               if constexpr (NCTA == 2) mma_ss_2cta(d_tmem, ad, wd, idesc, ((kb - kb0) | k) != 0);
               else mma_ss(d_tmem, ad, wd, idesc, ((kb - kb0) | k) != 0);
             }
@@ -875,14 +889,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
-template <int BN, int STAGES, int MODE, int NCTA = 1, bool TRANS = false, bool GATHER = false>
+template <int BN, int STAGES, int MODE, int NCTA = 1, bool TRANS = false, bool GATHER = false, bool TRANSB = false>
 static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CUtensorMap& mO, int M, int N, int K,
                           const GemmEpi& ep, cudaStream_t st, int ksplit = 1) {
   constexpr int SMEM = STAGES * (kBM * kBK * 2 + (BN / NCTA) * kBK * 2) + 8 * 2 * 4096 + 1024;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE, NCTA, TRANS, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, STAGES, MODE, NCTA, TRANS, GATHER, TRANSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
         cudaSuccess)
       return GVF_ERR_CUDA;
     int dev = 0;
@@ -894,7 +908,7 @@ static int launch_gemm_ws(const CUtensorMap& mA, const CUtensorMap& mW, const CU
   const int slots = num_sms / NCTA;
   const int grid = (tiles < slots ? tiles : slots) * NCTA;
   if constexpr (NCTA == 1) {
-    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1, TRANS, GATHER>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep, ksplit) == cudaSuccess
+    return launch_pdl(gemm_ws_kernel<BN, STAGES, MODE, 1, TRANS, GATHER, TRANSB>, dim3(grid), dim3(320), SMEM, st, mA, mW, mO, M, N, K, ep, ksplit) == cudaSuccess
                ? GVF_OK : GVF_ERR_CUDA;
   } else {
     cudaLaunchConfig_t cfg = {};
@@ -1478,6 +1492,35 @@ extern "C" GVF_API int gvf_gemm_tn_f16(const void* A, int lda, const void* W, in
   if (ksplit > 1 && cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)N * 4, (size_t)M, cs) != cudaSuccess) return GVF_ERR_CUDA;
   return wide ? launch_gemm_ws<256, 3, 4, 1, true>(mA, mW, mO, M, N, R, ep, cs, ksplit)
               : launch_gemm_ws<128, 4, 4, 1, true>(mA, mW, mO, M, N, R, ep, cs, ksplit);
+}
+
+// Input gradient without a transposed weight copy: out[M, N] fp16 = epilogue(A[M, R] W[R, N]), A fp16 row-major (dY), W fp16
+// row-major [R, N] = the Linear's own [out_features, in_features] weight.  epilogue 0 (fp16 store) or 8 (GELU': out =
+// fp16(acc) * gelu_tanh'(gate[m, n]), gate = the saved fp16 pre-activation [M, gate_stride]).  N, R multiples of 8.
+extern "C" GVF_API int gvf_gemm_nn_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int R, int epilogue, void* out,
+                                       int ldo, const void* gate, int gate_stride, void* stream) {
+  if (!A || !W || !out || M <= 0 || N <= 0 || R <= 0 || (epilogue != 0 && epilogue != 8)) return GVF_ERR_INVALID;
+  if ((N % 8) || (R % 8) || (lda % 8) || (ldw % 8) || (ldo % 8) || lda < R || ldw < N || ldo < N) return GVF_ERR_INVALID;
+  if (epilogue == 8 && (!gate || (gate_stride % 8) || ((uintptr_t)gate & 15))) return GVF_ERR_INVALID;
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
+  const bool wide = (N % 256) == 0;
+  const int BN = wide ? 256 : 128;
+  CUtensorMap mA, mW, mO;
+  const uint64_t dA[2] = {(uint64_t)R, (uint64_t)M}, sA[2] = {1, (uint64_t)lda};
+  const uint64_t dW[2] = {(uint64_t)N, (uint64_t)R}, sW[2] = {1, (uint64_t)ldw};
+  const uint32_t bA[2] = {kBK, kBM}, bW[2] = {64, kBK};
+  if (!make_tmap_f16(&mA, A, 2, dA, sA, bA, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
+  if (!make_tmap_f16(&mW, W, 2, dW, sW, bW, CU_TENSOR_MAP_SWIZZLE_128B)) return GVF_ERR_CUDA;
+  if (!make_tmap_2d(&mO, out, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, 64, 32)) return GVF_ERR_CUDA;
+  GemmEpi ep;
+  ep.mode = epilogue; ep.bias = nullptr; ep.out = out; ep.gate = (const __half*)gate; ep.gate_stride = gate_stride;
+  ep.rows_per_batch = 1; ep.ldo = ldo; ep.gamma_q = nullptr; ep.gamma_k = nullptr; ep.norm_cols = 0;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (epilogue == 8)
+    return wide ? launch_gemm_ws<256, 3, 8, 1, false, false, true>(mA, mW, mO, M, N, R, ep, cs)
+                : launch_gemm_ws<128, 4, 8, 1, false, false, true>(mA, mW, mO, M, N, R, ep, cs);
+  return wide ? launch_gemm_ws<256, 3, 0, 1, false, false, true>(mA, mW, mO, M, N, R, ep, cs)
+              : launch_gemm_ws<128, 4, 0, 1, false, false, true>(mA, mW, mO, M, N, R, ep, cs);
 }
 
 // Submanifold sparse convolution as ONE kernel (reference sparse/conv/conv_spconv.py:6-15 ->

@@ -192,9 +192,7 @@ GVF_API int gvf_sparse_trunk_backward(const gvf_sparse_block* blocks, int num_bl
   GVF_CU(cudaStreamWaitEvent(side, ev[5 * num_blocks], 0));
   for (int i = num_blocks - 1; i >= 0; --i) {
     const gvf_sparse_block& b = blocks[i];
-    if (!b.w_qkv_t || !b.w_out_t || !b.w1_t || !b.w2_t || !b.g_w_qkv || !b.g_b_qkv || !b.g_w_out || !b.g_b_out || !b.g_w1 ||
-        !b.g_b1 || !b.g_w2 || !b.g_b2)
-      return GVF_ERR_INVALID;
+    if (!b.g_w_qkv || !b.g_b_qkv || !b.g_w_out || !b.g_b_out || !b.g_w1 || !b.g_b1 || !b.g_w2 || !b.g_b2) return GVF_ERR_INVALID;
     const gvf_window_partition& pt = parts[i & 1];
     const BlockSlots s = L.block(ar, num_blocks, i);
     const uint8_t* x0 = L.xslot(ar, i);
@@ -202,18 +200,19 @@ GVF_API int gvf_sparse_trunk_backward(const gvf_sparse_block* blocks, int num_bl
     uint8_t *dx1 = dx1b[i & 1], *dH0 = dH0b[i & 1], *dQKV = dQKVb[i & 1];
     if (i + 2 < num_blocks) GVF_CU(cudaStreamWaitEvent(ms, ev[5 * (i + 2) + 4], 0));
     // x2 = x1 + fc2(GELU(fc1(LN x1)))
-    GVF_TRY(gvf_gemm_f16(dx, C, b.w2_t, C, T, F, C, 8, nullptr, dH0, F, s.H0, F, 0, ms));          // dgrad x GELU'
+    // dgrad GEMMs read the [out, in] weights as MN-major B operands (gvf_gemm_nn_f16): no transposed copies
+    GVF_TRY(gvf_gemm_nn_f16(dx, C, b.w2, F, T, F, C, 8, dH0, F, s.H0, F, ms));                   // dgrad x GELU'
     GVF_CU(cudaEventRecord(e[0], ms));
     GVF_TRY(gvf_gemm_tn_f16(dx, C, s.Hg, F, C, F, T, b.g_w2, F, side));
     GVF_TRY(gvf_colsum(dx, 1, T, C, C, reduce_ws, reduce_ws_bytes, b.g_b2, 0, side));
-    GVF_TRY(gvf_gemm_f16(dH0, F, b.w1_t, F, T, C, F, 0, nullptr, dA2, C, nullptr, 0, 0, ms));
+    GVF_TRY(gvf_gemm_nn_f16(dH0, F, b.w1, C, T, C, F, 0, dA2, C, nullptr, 0, ms));
     GVF_CU(cudaStreamWaitEvent(side, e[0], 0));
     GVF_TRY(gvf_gemm_tn_f16(dH0, F, s.A2, C, F, C, T, b.g_w1, C, side));
     GVF_TRY(gvf_colsum(dH0, 1, T, F, F, reduce_ws, reduce_ws_bytes, b.g_b1, 0, side));
     GVF_TRY(gvf_ln_bwd_f16(s.x1, fp16_residual, dA2, dx, dx1, T, C, 1e-6f, ms));
     GVF_CU(cudaEventRecord(e[1], ms));
     // x1 = x0 + to_out(window attention(to_qkv(LN x0)))
-    GVF_TRY(gvf_gemm_f16(dx1, C, b.w_out_t, C, T, C, C, 0, nullptr, dAO, C, nullptr, 0, 0, ms));
+    GVF_TRY(gvf_gemm_nn_f16(dx1, C, b.w_out, C, T, C, C, 0, dAO, C, nullptr, 0, ms));
     GVF_CU(cudaStreamWaitEvent(side, e[1], 0));
     GVF_TRY(gvf_gemm_tn_f16(dx1, C, s.AO, C, C, C, T, b.g_w_out, C, side));
     GVF_TRY(gvf_colsum(dx1, 1, T, C, C, reduce_ws, reduce_ws_bytes, b.g_b_out, 0, side));
@@ -224,7 +223,7 @@ GVF_API int gvf_sparse_trunk_backward(const gvf_sparse_block* blocks, int num_bl
       GVF_TRY(gvf_sparse_varlen_attn_bwd_f16(s.QKV, s.AO, dAO, (const float*)s.lse, dsum, dQKV, pt.fwd_idx, pt.cu_seqlens,
                                              pt.num_windows, pt.max_seqlen, T, H, 64, scale, ms));
     GVF_CU(cudaEventRecord(e[2], ms));
-    GVF_TRY(gvf_gemm_f16(dQKV, 3 * C, b.w_qkv_t, 3 * C, T, C, 3 * C, 0, nullptr, dA, C, nullptr, 0, 0, ms));
+    GVF_TRY(gvf_gemm_nn_f16(dQKV, 3 * C, b.w_qkv, C, T, C, 3 * C, 0, dA, C, nullptr, 0, ms));
     GVF_CU(cudaStreamWaitEvent(side, e[2], 0));
     GVF_TRY(gvf_gemm_tn_f16(dQKV, 3 * C, s.A, C, 3 * C, C, T, b.g_w_qkv, C, side));
     GVF_TRY(gvf_colsum(dQKV, 1, T, 3 * C, 3 * C, reduce_ws, reduce_ws_bytes, b.g_b_qkv, 0, side));

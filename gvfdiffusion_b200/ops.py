@@ -565,6 +565,25 @@ def skinny_expand(x, wt, out_f16=True):
     return out
 
 
+def gemm_nn(a, w, out=None, gelu_bwd_gate=None):
+    """fp16 [M, N] = a[M, R] @ w[R, N] (w row-major = a Linear's own [out, in] weight): the input gradient dX = dY W with no
+    transposed weight copy.  gelu_bwd_gate: the saved fp16 pre-activation [M, N] -> the result is multiplied by gelu_tanh'."""
+    _req(a, F16, "a")
+    _req(w, F16, "w")
+    M, R = a.shape
+    N = w.shape[1]
+    assert w.shape[0] == R and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=F16, device=a.device)
+    g = gelu_bwd_gate
+    if g is not None:
+        _req(g, F16, "gate")
+        assert g.shape == (M, N) and g.stride(1) == 1
+    check(_lib.lib().gvf_gemm_nn_f16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, R, 8 if g is not None else 0, ptr(out),
+                                     out.stride(0), ptr(g), g.stride(0) if g is not None else 0, current_stream()), "gvf_gemm_nn_f16")
+    return out
+
+
 def gemm_tn(a, w, out=None):
     """fp32 [M, N] = a[R, M]^T @ w[R, N] (fp16 row-major activations): the weight gradient dW = dY^T X, no transposes."""
     _req(a, F16, "a")

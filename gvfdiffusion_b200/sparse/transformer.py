@@ -77,10 +77,6 @@ class SparseTransformerBlocks:
         with torch.no_grad():
             torch._foreach_copy_(dst_w, src_w)
             torch._foreach_copy_(dst_b, [b.to(F16) for b in src_b])
-            if "w_qkv_t" in self.blocks[0]:
-                for blk in self.blocks:
-                    for n in ("w_qkv", "w_out", "w1", "w2"):
-                        ops.transpose(blk[n], out=blk[n + "_t"])
 
     # ---------------------------------------------------------------------------------------- native driver
     def _parts(self, coords):
@@ -102,7 +98,6 @@ class SparseTransformerBlocks:
         for i, blk in enumerate(self.blocks):
             vals = {n: ptr(blk[n]) for n in ("w_qkv", "w_out", "w1", "w2", "b_qkv", "b_out", "b1", "b2")}
             if grads is not None:
-                vals.update({n + "_t": ptr(blk[n + "_t"]) for n in ("w_qkv", "w_out", "w1", "w2")})
                 vals.update({"g_" + n: ptr(t) for n, t in grads[i].items()})
             arr[i] = _lib.SparseBlock(**vals)
         return arr
@@ -148,22 +143,15 @@ class SparseTransformerBlocks:
               "gvf_sparse_trunk_forward")
         return X, {"coords": coords, "arena": arena, "parts": parts, "keep": keep, "T": T}
 
-    def _transposed(self):
-        if "w_qkv_t" not in self.blocks[0]:
-            for blk in self.blocks:
-                for n in ("w_qkv", "w_out", "w1", "w2"):
-                    blk[n + "_t"] = ops.transpose(blk[n])
-        return self.blocks
-
     def backward(self, saved, dX):
         """dX [T, C] (gradient of forward_train's output) -> ({reference parameter name: fp32 gradient}, d feats fp16).
         Per block, in reverse (csrc/sparse_trunk.cu): fc2 dgrad with GELU' in its epilogue / wgrad -> fc1 dgrad / wgrad ->
         LayerNorm backward (+ residual) -> to_out dgrad / wgrad -> window attention backward -> to_qkv dgrad / wgrad ->
-        LayerNorm backward (+ residual); bias gradients = one-launch column sums.  Activation gradients are fp16 (fp32
+        LayerNorm backward (+ residual); the dgrads read the [out, in] weights directly (no transposed copies); bias
+        gradients = one-launch column sums.  Activation gradients are fp16 (fp32
         accumulation inside every kernel), parameter gradients fp32 views of one flat buffer."""
         T, C, F_, nb = saved["T"], self.C, self.F, len(self.blocks)
         dx = dX.detach().to(F16).contiguous()
-        self._transposed()
         shapes = (("w_qkv", (3 * C, C)), ("b_qkv", (3 * C,)), ("w_out", (C, C)), ("b_out", (C,)), ("w1", (F_, C)), ("b1", (F_,)),
                   ("w2", (C, F_)), ("b2", (C,)))
         per = sum(int(torch.Size(s).numel()) for _, s in shapes)
@@ -277,9 +265,7 @@ class SparseTransformerVAE:
         g[first + ".weight"] = ops.gemm_tn(dx, x)
         if not need_input_grad:
             return None
-        if first + "_t" not in self.lin:
-            self.lin[first + "_t"] = ops.transpose(w)
-        return ops.gemm(dx, self.lin[first + "_t"], None, ops.EPI_F32)
+        return ops.gemm_nn(dx, w).float()
 
     def _last_backward(self, last, saved, dout, g):
         """gradients of the trunk's last Linear (+ the affine-free LayerNorm in front of it) -> d block output fp16."""
@@ -288,11 +274,14 @@ class SparseTransformerVAE:
         N8 = (N + 7) // 8 * 8
         d16 = torch.zeros((T, N8), dtype=F16, device=self.dev)
         d16[:, :N] = dout.detach()
-        if last + "_t" not in self.lin:
-            self.lin[last + "_t"] = ops.transpose(w)                          # [C, N8]
         g[last + ".weight"] = ops.gemm_tn(d16, saved["hn"])[:N]
         g[last + ".bias"] = ops.colsum(d16)[:N]
-        dh = ops.gemm(d16, self.lin[last + "_t"], None, ops.EPI_F16)
+        if N == N8:
+            dh = ops.gemm_nn(d16, w)                                          # d h = d out W, W read as it lies in memory
+        else:                                                                 # odd widths: a zero-padded transposed copy
+            if last + "_t" not in self.lin:
+                self.lin[last + "_t"] = ops.transpose(w)                      # [C, N8]
+            dh = ops.gemm(d16, self.lin[last + "_t"], None, ops.EPI_F16)
         if self.norm_output:
             dh = ops.ln_bwd(saved["x_last"], dh, None, eps=1e-5)
         return dh

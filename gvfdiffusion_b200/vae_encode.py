@@ -55,9 +55,6 @@ class VAEEncodeEngine:
             torch._foreach_copy_(db, [t.detach().to(F16) for t in sb])
             if hasattr(self, "w1g"):
                 self.w1g, self.b1g = ops.geglu_interleave(self.w1, self.b1)
-            if hasattr(self, "w_q_t"):
-                for n in ("w_q", "w_kv", "w_out", "w1", "w2", "w_ml"):
-                    ops.transpose(getattr(self, n), out=getattr(self, n + "_t"))
 
     def _embed(self, disp, xyz, rows_per_xyz_row):
         """disp [R, 3] fp32 per (batch, frame, point) row, xyz [B * n, 3] per point -> fp32 [R, dim]."""
@@ -152,10 +149,7 @@ class VAEEncodeEngine:
     def backward(self, sv, dx, dkl):
         """dx [(B T), L, latent] (gradient of the sampled latent), dkl [(B T)] or None -> {encoder parameter name: fp32 grad}.
         static_pc / delta_pc / the Gaussians are data (the reference interpolates them under no_grad, :470)."""
-        if not hasattr(self, "w_q_t"):
-            T_ = ops.transpose
-            self.w_q_t, self.w_kv_t, self.w_out_t = T_(self.w_q), T_(self.w_kv), T_(self.w_out)
-            self.w1_t, self.w2_t, self.w_ml_t = T_(self.w1), T_(self.w2), T_(self.w_ml)
+        # dgrad GEMMs read the [out, in] weights directly (ops.gemm_nn): no transposed copies
         dev, L, H, d, dim, lat = self.dev, self.L, self.H, self.d, self.dim, self.latent
         B, T, N = sv["shape"]
         M = B * T * L
@@ -175,16 +169,16 @@ class VAEEncodeEngine:
         g["mean_fc.weight"], g["logvar_fc.weight"] = wml[:lat], wml[lat:2 * lat]
         bml = ops.colsum(dml)
         g["mean_fc.bias"], g["logvar_fc.bias"] = bml[:lat], bml[lat:2 * lat]
-        dx2 = ops.gemm(dml, self.w_ml_t, None, ops.EPI_F16)                      # [M, dim]
+        dx2 = ops.gemm_nn(dml, self.w_ml)                      # [M, dim]
         # feed-forward block: x2 = x1 + net.2(GEGLU(net.0(LN x1)))
-        dG = ops.gemm(dx2, self.w2_t, None, ops.EPI_F16)
+        dG = ops.gemm_nn(dx2, self.w2)
         g[f + "net.2.weight"], g[f + "net.2.bias"] = wg(dx2, sv["G"]), ops.colsum(dx2)
         dHf = ops.geglu_bwd(sv["Hf"], dG)
-        dh = ops.gemm(dHf, self.w1_t, None, ops.EPI_F16)
+        dh = ops.gemm_nn(dHf, self.w1)
         g[f + "net.0.weight"], g[f + "net.0.bias"] = wg(dHf, sv["hmid"]), ops.colsum(dHf)
         dx1 = ops.ln_bwd(sv["x1"], dh, dx2, eps=1e-6)
         # cross-attention block: x1 = a + to_out(attention(to_q(LN a), to_kv(LN ctx)))
-        dao = ops.gemm(dx1, self.w_out_t, None, ops.EPI_F16)
+        dao = ops.gemm_nn(dx1, self.w_out)
         g[a + "to_out.weight"], g[a + "to_out.bias"] = wg(dx1, sv["ao"].view(M, dim)), ops.colsum(dx1)
         kv = sv["kv"]
         dq, dkv = torch.empty_like(sv["q"]), torch.empty_like(kv)
@@ -193,8 +187,8 @@ class VAEEncodeEngine:
         dkv2 = dkv.view(B * T * N, 2 * dim)
         g[a + "to_q.weight"] = wg(dq, sv["qn"])
         g[a + "to_kv.weight"] = wg(dkv2, sv["cn"])
-        dqn = ops.gemm(dq, self.w_q_t, None, ops.EPI_F16)
-        dcn = ops.gemm(dkv2, self.w_kv_t, None, ops.EPI_F16)
+        dqn = ops.gemm_nn(dq, self.w_q)
+        dcn = ops.gemm_nn(dkv2, self.w_kv)
         dA = ops.ln_bwd(sv["A"], dqn, dx1, eps=1e-6)                              # + the residual branch
         dC = ops.ln_bwd(sv["Cx"], dcn, None, eps=1e-6)
         # token embeddings: LN_1e-5(Linear(3 -> dim)(disp)) + LN_1e-5(PointEmbed) -- only the Linear has parameters

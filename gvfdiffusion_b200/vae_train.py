@@ -24,21 +24,12 @@ F16, F32 = torch.float16, torch.float32
 class VAEDecodeTrainEngine(VAEDecodeEngine):
     def __init__(self, state_dict, heads, num_timesteps, device="cuda"):
         super().__init__(state_dict, heads, num_timesteps, device, chunk_size=1 << 30)
-        T_ = ops.transpose
-        for ly in self.layers:
-            ly["w_qkv_t"], ly["w_out_t"], ly["w1_t"], ly["w2_t"] = T_(ly["w_qkv"]), T_(ly["w_out"]), T_(ly["w1"]), T_(ly["w2"])
-        self.w_dq_t, self.w_dkv_t, self.w_dout_t = T_(self.w_dq), T_(self.w_dkv), T_(self.w_dout)
+        # no transposed weight copies: the dgrad GEMMs read the [out, in] weights as MN-major B operands (ops.gemm_nn)
         self.w_o_t = self.w_o[:self.out_dim].t().contiguous()            # [dim, out_dim]: d lat = d out @ w_o
 
     def refresh(self, sd):
         super().refresh(sd)
         with torch.no_grad():
-            for ly in self.layers:
-                for n in ("w_qkv", "w_out", "w1", "w2"):
-                    ops.transpose(ly[n], out=ly[n + "_t"])
-            ops.transpose(self.w_dq, out=self.w_dq_t)
-            ops.transpose(self.w_dkv, out=self.w_dkv_t)
-            ops.transpose(self.w_dout, out=self.w_dout_t)
             self.w_o_t.copy_(self.w_o[:self.out_dim].t())
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -128,7 +119,7 @@ class VAEDecodeTrainEngine(VAEDecodeEngine):
             ops.attention_bwd(sv["qd"][b * Q:(b + 1) * Q].view(Q, H, d), kv4[b, :, :, 0], kv4[b, :, :, 1], sv["ao"][b], dao[b],
                               sv["lse"][b], scale, dqd[b * Q:(b + 1) * Q].view(Q, H, d), dkv4[b, :, :, 0], dkv4[b, :, :, 1],
                               q_shared=True)
-        dqe = ops.gemm(dqd, self.w_dq_t, None, ops.EPI_F16)
+        dqe = ops.gemm_nn(dqd, self.w_dq)
         g[c + "to_q.weight"] = self._wgrad(dqd, sv["qe"])
         # query embedding: LN(LN(gs_embedding(q)) + LN(PointEmbed(q.xyz)))
         dgs, _ = ops.vae_query_embed_bwd(q2, sv["gs"], dqe)
@@ -138,23 +129,23 @@ class VAEDecodeTrainEngine(VAEDecodeEngine):
         g["gs_embedding.0.weight"] = ops.skinny_outer(q2, dgs).t().contiguous()
         g["gs_embedding.0.bias"] = ops.colsum(dgs)
         # to_kv of the decoder over all batch entries, PreNorm.norm_context
-        dctx = ops.gemm(dKV, self.w_dkv_t, None, ops.EPI_F16)
+        dctx = ops.gemm_nn(dKV, self.w_dkv)
         g[c + "to_kv.weight"] = self._wgrad(dKV, sv["ctx"])
         dx = ops.ln_bwd(sv["x_last"], dctx, None, eps=1e-6)
         for i in reversed(range(self.depth)):
             ly, s = self.layers[i], sv["layers"][i]
             a, f = f"layers.{i}.0.fn.", f"layers.{i}.1.fn."
             # x2 = x1 + net.2(GEGLU(net.0(LN x1)))
-            dG = ops.gemm(dx, ly["w2_t"], None, ops.EPI_F16)
+            dG = ops.gemm_nn(dx, ly["w2"])
             g[f + "net.2.weight"] = self._wgrad(dx, s["G"])
             g[f + "net.2.bias"] = ops.colsum(dx)
             dHf = ops.geglu_bwd(s["Hf"], dG)
-            dA2 = ops.gemm(dHf, ly["w1_t"], None, ops.EPI_F16)
+            dA2 = ops.gemm_nn(dHf, ly["w1"])
             g[f + "net.0.weight"] = self._wgrad(dHf, s["A2"])
             g[f + "net.0.bias"] = ops.colsum(dHf)
             dx1 = ops.ln_bwd(s["x1"], dA2, dx, eps=1e-6)
             # x1 = x0 + to_out(attention(to_q(LN x0), to_kv(LN x0)))
-            dAO = ops.gemm(dx1, ly["w_out_t"], None, ops.EPI_F16)
+            dAO = ops.gemm_nn(dx1, ly["w_out"])
             g[a + "to_out.weight"] = self._wgrad(dx1, s["AO"].view(M, dim))
             g[a + "to_out.bias"] = ops.colsum(dx1)
             q5 = s["QKV"].view(BT, L, 3, H, d)
@@ -162,7 +153,7 @@ class VAEDecodeTrainEngine(VAEDecodeEngine):
             d5 = dQKV.view(BT, L, 3, H, d)
             ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], s["AO"], dAO.view(BT, L, H, d), s["lse"], scale,
                               d5[:, :, 0], d5[:, :, 1], d5[:, :, 2])
-            dA = ops.gemm(dQKV, ly["w_qkv_t"], None, ops.EPI_F16)
+            dA = ops.gemm_nn(dQKV, ly["w_qkv"])
             wqkv = self._wgrad(dQKV, s["A"])
             g[a + "to_q.weight"], g[a + "to_kv.weight"] = wqkv[:dim], wqkv[dim:]
             dx = ops.ln_bwd(s["x0"], dA, dx1, eps=1e-6)

@@ -394,7 +394,7 @@ GVF_API int gvf_sparse_packed_attn_bwd_f16(const void* qkv, const void* o, const
 typedef struct gvf_sparse_block {
   const void *w_qkv, *w_out, *w1, *w2;             /* fp16 [3C,C] ([3][H][d] rows), [C,C], [F,C], [C,F] */
   const float *b_qkv, *b_out, *b1, *b2;            /* fp32 */
-  const void *w_qkv_t, *w_out_t, *w1_t, *w2_t;     /* fp16 transposes [C,3C], [C,C], [C,F], [F,C] (backward only) */
+  const void *w_qkv_t, *w_out_t, *w1_t, *w2_t;     /* unused since the dgrad GEMMs read the weights directly (gvf_gemm_nn_f16) */
   float *g_w_qkv, *g_b_qkv, *g_w_out, *g_b_out, *g_w1, *g_b1, *g_w2, *g_b2;   /* fp32 gradient outputs (backward only) */
 } gvf_sparse_block;
 typedef struct gvf_window_partition {
@@ -529,6 +529,10 @@ GVF_API void gvf_attn_bwd_set_serial(int v);
  * TMA reduce-add.  M, N multiples of 8. */
 GVF_API int gvf_gemm_tn_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int R, float* out, int ldo,
                             void* stream);
+/* Input gradient of a Linear without a transposed weight copy: out[M, N] fp16 = epilogue(A[M, R] W[R, N]) with W row-major
+ * [R, N] = the Linear's own [out_features, in_features] weight (MN-major B operand).  epilogue 0 or 8 (GELU', see section 3). */
+GVF_API int gvf_gemm_nn_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int R, int epilogue, void* out, int ldo,
+                            const void* gate, int gate_stride, void* stream);
 /* out[C, ld_out] = in[R, C]^T (fp16); columns [R, ld_out) of every output row are zero (ld_out = R rounded up to 8
  * so that the transposed tensor is a legal GEMM operand). */
 GVF_API int gvf_transpose_f16(const void* in, int R, int C, long long ld_in, void* out, long long ld_out, void* stream);

@@ -241,3 +241,24 @@ def test_colsum_single_launch_form_and_gelu_epilogues():
     hr = h0.float().requires_grad_(True)
     F.gelu(hr, approximate="tanh").backward(dy.float() @ w.float().t())
     assert _rel(fused, hr.grad) < 2e-3
+
+
+@pytest.mark.parametrize("M,R,N", [(4096, 3072, 768), (1000, 768, 3072), (12288, 2304, 768), (333, 64, 96), (257, 16, 128),
+                                   (4096, 768, 2304)])
+def test_gemm_nn_input_gradient_without_transposed_weights(M, R, N):
+    """dX = dY W straight from the row-major [out, in] weight (W as the MN-major B operand of the tcgen05 GEMM): equal to the
+    GEMM over a transposed copy bit for bit, also with GELU' in the epilogue, and on a strided column sub-block of dY."""
+    from gvfdiffusion_b200 import ops
+    g = _g(M + R + N)
+    dy = _rand((M, R), g, 0.5).half()
+    w = _rand((R, N), g, 0.05).half()
+    ref = dy.float() @ w.float()
+    out = ops.gemm_nn(dy, w)
+    assert _rel(out, ref) < 1e-3
+    assert torch.equal(out, ops.gemm(dy, ops.transpose(w)[:, :R].contiguous() if R % 8 == 0 else ops.transpose(w), None, ops.EPI_F16))
+    h0 = _rand((M, N), g, 1.5).half()
+    fused = ops.gemm_nn(dy, w, gelu_bwd_gate=h0)
+    assert _rel(fused, ops.gelu_tanh_bwd(h0, out)) < 1e-3
+    if R >= 128:
+        sub = dy[:, R // 2:]
+        assert _rel(ops.gemm_nn(sub, w[R // 2:]), sub.float() @ w[R // 2:].float()) < 1e-3

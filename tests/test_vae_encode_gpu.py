@@ -160,7 +160,7 @@ def test_engines_refresh_in_place_after_an_optimiser_step():
         (out["logits"].square().sum() + out["kl"].sum()).backward()
         with torch.no_grad():
             v.decode(out["posterior"]["mean"], torch.stack([t[:64] for t in gs]))      # builds the inference engine too
-        now = (v.train_engine().layers[0]["w_qkv"].data_ptr(), v.train_engine().layers[0]["w1_t"].data_ptr(),
+        now = (v.train_engine().layers[0]["w_qkv"].data_ptr(), v.train_engine().layers[0]["w1"].data_ptr(),
                v.encode_engine().w_kv.data_ptr(), v.engine().w_dkv.data_ptr())
         assert ptrs is None or now == ptrs
         ptrs = now
