@@ -80,9 +80,13 @@ def test_round2_kernels_are_blackwell_native(sass_by_kernel):
     m4 = {k: b for k, b in _kernels(sass_by_kernel, "gemm_ws_kernel").items() if re.search(r"ELi4ELi[12]ELb", k)}
     assert m4 and all("UTMAREDG" in b for b in m4.values()), list(m4)[:2]
     # MN-major (TRANS) and gather instantiations exist and are tcgen05 kernels
-    trans = [k for k in _kernels(sass_by_kernel, "gemm_ws_kernel") if k.endswith("ELb1ELb0EEEv14CUtensorMap_stS1_S1_iiiNS_7GemmEpiEi")]
-    gath = {k: b for k, b in _kernels(sass_by_kernel, "gemm_ws_kernel").items() if "ELb0ELb1EEEv" in k}
-    assert trans and gath
+    # template tail: <..., TRANS, GATHER, TRANSB>
+    ws = _kernels(sass_by_kernel, "gemm_ws_kernel")
+    trans = [k for k in ws if "ELb1ELb0ELb0EEEv" in k]
+    gath = {k: b for k, b in ws.items() if "ELb0ELb1ELb0EEEv" in k}
+    transb = {k: b for k, b in ws.items() if "ELb0ELb0ELb1EEEv" in k}
+    assert trans and gath and transb
+    assert all(re.search(r"UTC\w*MMA", b) and "UTMALDG" in b for b in transb.values())
     assert all(re.search(r"UTMALDG\S*(GATHER4|G4)", b) or "GATHER" in b for b in gath.values()), "no gather4 TMA load in the sparse-conv GEMM"
 
 
