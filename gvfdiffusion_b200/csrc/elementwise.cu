@@ -28,7 +28,9 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 // LayerNorm (no affine or affine) + optional adaLN modulate -> fp16 GEMM operand.
 // reference model/dit.py:246-247,254-255,263,268,273-274 (norm1..5 + modulate) and
 // model/autoencoder.py:73-88 (PreNorm).  One warp per row, row kept in registers.
-template <typename TIn, int C, bool VEC>
+// ACT: SiLU on the normalised / modulated value before the single fp16 rounding (the `norm -> SiLU -> conv` pairs of the
+// TRELLIS SparseResBlock3d, trellis/models/structured_latent_flow.py:57-62).
+template <typename TIn, int C, bool VEC, bool ACT = false>
 __global__ void __launch_bounds__(256) ln_mod_kernel(const TIn* __restrict__ x, __half* __restrict__ out,
                                                      int M, float eps, const float* __restrict__ w,
                                                      const float* __restrict__ bvec,
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const TIn* __restrict__ x, 
       if (w) y = y * w[c] + bvec[c];
       if (scale) y = y * (1.0f + __half2float(scale[(size_t)b * mod_stride + c])) +
                      __half2float(shift[(size_t)b * mod_stride + c]);
+      if constexpr (ACT) y = y / (1.0f + __expf(-y));
       orow[c] = __float2half_rn(y);
     }
   } else
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const TIn* __restrict__ x, 
       float y = (v[i * 4 + t] - mean) * rstd;
       if (w) y = y * wv[t] + bv[t];
       if (scale) y = y * (1.0f + sc[t]) + sh[t];
+      if constexpr (ACT) y = y / (1.0f + __expf(-y));
       h[t] = __float2half_rn(y);
     }
     *reinterpret_cast<uint2*>(orow + c) = *reinterpret_cast<uint2*>(h);
@@ -528,9 +532,8 @@ using namespace gvf;
 
 extern "C" {
 
-GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
-                           const float* w, const float* b, const void* shift, const void* scale,
-                           int mod_stride, int rows_per_batch, void* stream) {
+static int ln_mod_launch(const void* x, int x_is_f16, void* out, int M, int C, float eps, const float* w, const float* b,
+                         const void* shift, const void* scale, int mod_stride, int rows_per_batch, int act, void* stream) {
   if (!x || !out || M <= 0) return GVF_ERR_INVALID;
   if ((w == nullptr) != (b == nullptr) || (shift == nullptr) != (scale == nullptr)) return GVF_ERR_INVALID;
   const int rpb = rows_per_batch > 0 ? rows_per_batch : M;
@@ -545,14 +548,20 @@ GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C,
   }
   const int want = (M + 7) / 8, cap = num_sms * 8;
   const dim3 grid(want < cap ? want : cap);
-#define LN_CASE(T, CC, V)                                                                          \
-  launch_pdl(ln_mod_kernel<T, CC, V>, grid, dim3(256), 0, ST(stream), (const T*)x, (__half*)out, M, eps, w, b, \
+#define LN_CASE(T, CC, V, A)                                                                          \
+  launch_pdl(ln_mod_kernel<T, CC, V, A>, grid, dim3(256), 0, ST(stream), (const T*)x, (__half*)out, M, eps, w, b, \
              (const __half*)shift, (const __half*)scale, mod_stride, rpb)
-#define LN_BOTH(CC, V)                       \
-  if (C == CC) {                             \
-    if (x_is_f16) LN_CASE(__half, CC, V);    \
-    else LN_CASE(float, CC, V);              \
-    RET();                                   \
+#define LN_BOTH(CC, V)                              \
+  if (C == CC && !act) {                            \
+    if (x_is_f16) LN_CASE(__half, CC, V, false);    \
+    else LN_CASE(float, CC, V, false);              \
+    RET();                                          \
+  }
+#define LN_ACT(CC, V)                               \
+  if (C == CC && act == 1) {                        \
+    if (x_is_f16) LN_CASE(__half, CC, V, true);     \
+    else LN_CASE(float, CC, V, true);               \
+    RET();                                          \
   }
   LN_BOTH(512, true)
   LN_BOTH(768, true)
@@ -561,10 +570,31 @@ GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C,
   LN_BOTH(192, false)
   LN_BOTH(128, true)
   LN_BOTH(384, true)
+  LN_BOTH(256, true)
+  LN_BOTH(1024, true)
+  // the ResBlock widths of the structured-latent flow model (io 64 / 128, their skip concatenations, model 1024 / 2048)
+  LN_ACT(64, false)
+  LN_ACT(128, true)
+  LN_ACT(256, true)
+  LN_ACT(1024, true)
+  LN_ACT(2048, true)
+#undef LN_ACT
 #undef LN_BOTH
 #undef LN_CASE
   return GVF_ERR_UNSUPPORTED;
-  RET();
+}
+
+GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
+                           const float* w, const float* b, const void* shift, const void* scale,
+                           int mod_stride, int rows_per_batch, void* stream) {
+  return ln_mod_launch(x, x_is_f16, out, M, C, eps, w, b, shift, scale, mod_stride, rows_per_batch, 0, stream);
+}
+
+GVF_API int gvf_ln_mod_act_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
+                               const float* w, const float* b, const void* shift, const void* scale,
+                               int mod_stride, int rows_per_batch, int act, void* stream) {
+  if (act != 0 && act != 1) return GVF_ERR_INVALID;
+  return ln_mod_launch(x, x_is_f16, out, M, C, eps, w, b, shift, scale, mod_stride, rows_per_batch, act, stream);
 }
 
 GVF_API int gvf_rmsnorm_heads_f16(void* buf, long long rows, int ld, int H, int D, int k_off,

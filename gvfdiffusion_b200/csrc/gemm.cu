@@ -1527,13 +1527,14 @@ extern "C" GVF_API int gvf_gemm_nn_f16(const void* A, int lda, const void* W, in
 // spconv.SubMConv3d): out[n, :] = epilogue(sum_k W[:, k, :] x[nbr[n, k]] + bias).  x fp16 [N, Cin] (row stride ldx), nbr
 // int32 [N, K3] from gvf_sparse_neighbor_map (-1 = absent), W fp16 [Cout, K3 * Cin].  The im2col operand of
 // gvf_sparse_im2col_f16 + gvf_gemm_f16 is never written: the GEMM's TMA producer gathers the neighbour rows itself
-// (tile::gather4).  Cin % 64 == 0; epilogue 0 (fp16 store) or 4 (fp32 store).  Bit-identical to the two-kernel path.
+// (tile::gather4).  Cin % 64 == 0; epilogue 0 (fp16 store), 3 (fp16 residual: out += fp16(conv + bias), in place) or 4 (fp32
+// store).  Bit-identical to the two-kernel path.
 extern "C" GVF_API int gvf_sparse_conv_gemm_f16(const void* x, int ldx, const int* nbr, int N, int K3, int Cin, const void* W,
                                                 int ldw, int Cout, const float* bias, void* out, int ldo, int epilogue,
                                                 void* stream) {
   if (!x || !nbr || !W || !out || N <= 0 || K3 <= 0 || Cin <= 0 || Cout <= 0) return GVF_ERR_INVALID;
   if ((Cin % 64) || (Cout % 8) || (ldx % 8) || (ldw % 8) || ldx < Cin || ldw < K3 * Cin) return GVF_ERR_UNSUPPORTED;
-  if (epilogue != 0 && epilogue != 4) return GVF_ERR_UNSUPPORTED;
+  if (epilogue != 0 && epilogue != 3 && epilogue != 4) return GVF_ERR_UNSUPPORTED;
   if (((uintptr_t)x | (uintptr_t)W | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
   if ((ldo * (epilogue == 4 ? 4 : 2)) % 16) return GVF_ERR_INVALID;
   const int K = K3 * Cin;
@@ -1554,6 +1555,9 @@ extern "C" GVF_API int gvf_sparse_conv_gemm_f16(const void* x, int ldx, const in
   if (epilogue == 0)
     return wide ? launch_gemm_ws<256, 3, 0, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs)
                 : launch_gemm_ws<128, 4, 0, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs);
+  if (epilogue == 3)      // out (fp16, pre-filled with the skip path) += fp16(conv): SparseResBlock3d's `h + skip_connection(x)`
+    return wide ? launch_gemm_ws<256, 3, 3, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs)
+                : launch_gemm_ws<128, 4, 3, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs);
   return wide ? launch_gemm_ws<256, 3, 4, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs)
               : launch_gemm_ws<128, 4, 4, 1, false, true>(mA, mW, mO, N, Cout, K, ep, cs);
 }

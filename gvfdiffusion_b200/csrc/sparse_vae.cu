@@ -156,6 +156,55 @@ __global__ void __launch_bounds__(256) sparse_im2col_kernel(const TIn* __restric
   reinterpret_cast<uint4*>(out)[t] = o;
 }
 
+// ---------------------------------------------------------------------------------------
+// SparseDownsample / SparseUpsample of the TRELLIS stage (trellis/modules/sparse/spatial.py:13-80).
+// pool: out[p] = (sum of the rows of cell p) / (count + 1) -- the reference's torch.scatter_reduce(zeros, ..., 'mean') keeps
+// its default include_self = True, so the zero initial value counts as one more element.  The children of a cell are
+// listed in order[offsets[p] .. offsets[p + 1]) (ascending row order: the sum is deterministic, fp32, one fp16 rounding).
+// One thread per (cell, 8 channels).
+__global__ void __launch_bounds__(256) sparse_pool_mean_kernel(const __half* __restrict__ x, int ldx, const int* __restrict__ order,
+                                                               const int* __restrict__ offsets, long long cells, int c8,
+                                                               __half* __restrict__ out, int ldo) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= cells * c8) return;
+  const long long p = gid / c8;
+  const int c = (int)(gid - p * c8) * 8;
+  const int s = offsets[p], e = offsets[p + 1];
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = s; i < e; ++i) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + (size_t)order[i] * ldx + c));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = __half22float2(h2[u]);
+      acc[2 * u] += f.x;
+      acc[2 * u + 1] += f.y;
+    }
+  }
+  const float inv = 1.0f / (float)(e - s + 1);
+  uint4 pk;
+  __half2* o2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) o2[u] = __floats2half2_rn(acc[2 * u] * inv, acc[2 * u + 1] * inv);
+  *reinterpret_cast<uint4*>(out + (size_t)p * ldo + c) = pk;
+}
+
+// out[i] = [ a[idx ? idx[i] : i, 0:Ca] | b[i, 0:Cb] ]: the nearest-neighbour upsample (a gather through the cached cell
+// index) and / or the skip concatenation of structured_latent_flow.py:253-256 in one pass.  One thread per 16 B piece.
+__global__ void __launch_bounds__(256) gather_concat_kernel(const __half* __restrict__ a, int lda, int ca8, const int* __restrict__ idx,
+                                                            const __half* __restrict__ b, int ldb, int cb8, long long rows,
+                                                            __half* __restrict__ out, int ldo) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w8 = ca8 + cb8;
+  if (gid >= rows * w8) return;
+  const long long r = gid / w8;
+  const int c = (int)(gid - r * w8);
+  uint4 v;
+  if (c < ca8) v = __ldg(reinterpret_cast<const uint4*>(a + (size_t)(idx ? idx[r] : r) * lda + c * 8));
+  else v = __ldg(reinterpret_cast<const uint4*>(b + (size_t)r * ldb + (c - ca8) * 8));
+  *reinterpret_cast<uint4*>(out + (size_t)r * ldo + c * 8) = v;
+}
+
 }  // namespace gvf
 
 using namespace gvf;
@@ -228,6 +277,27 @@ GVF_API int gvf_sparse_im2col_f16(const void* x, int x_is_f16, int ldx, const in
     sparse_im2col_kernel<__half><<<blocks, 256, 0, ST(stream)>>>((const __half*)x, ldx, nbr, pairs, cin8, (__half*)out);
   else
     sparse_im2col_kernel<float><<<blocks, 256, 0, ST(stream)>>>((const float*)x, ldx, nbr, pairs, cin8, (__half*)out);
+  RET();
+}
+
+GVF_API int gvf_sparse_pool_mean_f16(const void* x, int ldx, const int* order, const int* offsets, int cells, int C,
+                                     void* out, int ldo, void* stream) {
+  if (!x || !order || !offsets || !out || cells <= 0 || C <= 0) return GVF_ERR_INVALID;
+  if ((C % 8) || (ldx % 8) || (ldo % 8) || (((uintptr_t)x | (uintptr_t)out) & 15)) return GVF_ERR_INVALID;
+  const long long t = (long long)cells * (C / 8);
+  sparse_pool_mean_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>((const __half*)x, ldx, order, offsets, cells,
+                                                                            C / 8, (__half*)out, ldo);
+  RET();
+}
+
+GVF_API int gvf_gather_concat_f16(const void* a, int lda, int Ca, const int* idx, const void* b, int ldb, int Cb, int rows,
+                                  void* out, int ldo, void* stream) {
+  if (!out || rows <= 0 || Ca < 0 || Cb < 0 || Ca + Cb <= 0 || (Ca > 0 && !a) || (Cb > 0 && !b)) return GVF_ERR_INVALID;
+  if ((Ca % 8) || (Cb % 8) || (lda % 8) || (ldb % 8) || (ldo % 8) || ldo < Ca + Cb) return GVF_ERR_INVALID;
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) return GVF_ERR_INVALID;
+  const long long t = (long long)rows * ((Ca + Cb) / 8);
+  gather_concat_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>((const __half*)a, lda, Ca / 8, idx, (const __half*)b,
+                                                                         ldb, Cb / 8, rows, (__half*)out, ldo);
   RET();
 }
 

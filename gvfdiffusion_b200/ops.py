@@ -170,6 +170,55 @@ def ln_mod(x, out=None, eps=1e-6, w=None, b=None, shift=None, scale=None, mod_st
     return out
 
 
+def ln_mod_act(x, out=None, eps=1e-6, w=None, b=None, shift=None, scale=None, mod_stride=0, rows_per_batch=0, act=1):
+    """ln_mod with an activation before the fp16 rounding (act 1 = SiLU): the norm -> SiLU pairs of SparseResBlock3d."""
+    M, Cc = x.shape
+    assert x.is_contiguous() and x.dtype in (F16, F32)
+    if out is None:
+        out = torch.empty((M, Cc), dtype=F16, device=x.device)
+    st = _lib.lib().gvf_ln_mod_act_f16(ptr(x), int(x.dtype == F16), ptr(out), M, Cc, eps, ptr(w), ptr(b),
+                                       ptr(shift), ptr(scale), mod_stride, rows_per_batch, act, current_stream())
+    check(st, "gvf_ln_mod_act_f16")
+    return out
+
+
+def sparse_pool_mean(x, order, offsets, out=None):
+    """SparseDownsample's pooling: x fp16 [N, C]; order int32 [N] (fine rows grouped by coarse cell), offsets int32
+    [cells + 1] -> fp16 [cells, C] = sum / (count + 1) (the reference's include_self mean)."""
+    _req(x, F16, "x")
+    _req(order, torch.int32, "order")
+    _req(offsets, torch.int32, "offsets")
+    cells, Cc = offsets.shape[0] - 1, x.shape[1]
+    assert x.stride(1) == 1 and order.is_contiguous() and offsets.is_contiguous() and order.shape[0] == x.shape[0]
+    if out is None:
+        out = torch.empty((cells, Cc), dtype=F16, device=x.device)
+    check(_lib.lib().gvf_sparse_pool_mean_f16(ptr(x), x.stride(0), ptr(order), ptr(offsets), cells, Cc, ptr(out), out.stride(0),
+                                              current_stream()), "gvf_sparse_pool_mean_f16")
+    return out
+
+
+def gather_concat(a=None, idx=None, b=None, out=None):
+    """out[i] = [a[idx[i]] (or a[i]) | b[i]] (fp16): SparseUpsample's gather and / or the skip concatenation."""
+    rows = idx.shape[0] if idx is not None else (a.shape[0] if a is not None else b.shape[0])
+    Ca = 0 if a is None else a.shape[1]
+    Cb = 0 if b is None else b.shape[1]
+    for t, nm in ((a, "a"), (b, "b")):
+        if t is not None:
+            _req(t, F16, nm)
+            assert t.stride(1) == 1
+    if idx is not None:
+        _req(idx, torch.int32, "idx")
+        assert idx.is_contiguous()
+    if b is not None:
+        assert b.shape[0] == rows
+    if out is None:
+        out = torch.empty((rows, Ca + Cb), dtype=F16, device=(a if a is not None else b).device)
+    check(_lib.lib().gvf_gather_concat_f16(ptr(a), a.stride(0) if a is not None else 8, Ca, ptr(idx), ptr(b),
+                                           b.stride(0) if b is not None else 8, Cb, rows, ptr(out), out.stride(0),
+                                           current_stream()), "gvf_gather_concat_f16")
+    return out
+
+
 def rmsnorm_heads_(buf, H, D, k_off, gamma_q, gamma_k):
     rows, ld = buf.shape[0], buf.stride(0)
     st = _lib.lib().gvf_rmsnorm_heads_f16(ptr(buf), rows, ld, H, D, k_off, ptr(gamma_q), ptr(gamma_k),
@@ -598,8 +647,9 @@ def gemm_tn(a, w, out=None):
     return out
 
 
-def sparse_conv_gemm(x, nbr, w, bias=None, out_f32=False, out=None):
-    """Gather-fused submanifold convolution: x fp16 [N, Cin], nbr int32 [N, K3], w fp16 [Cout, K3 * Cin] -> [N, Cout]."""
+def sparse_conv_gemm(x, nbr, w, bias=None, out_f32=False, out=None, residual=False):
+    """Gather-fused submanifold convolution: x fp16 [N, Cin], nbr int32 [N, K3], w fp16 [Cout, K3 * Cin] -> [N, Cout].
+    residual: `out` (fp16, given) += fp16(conv + bias) in place."""
     _req(x, F16, "x")
     _req(w, F16, "w")
     _req(nbr, torch.int32, "nbr")
@@ -607,8 +657,11 @@ def sparse_conv_gemm(x, nbr, w, bias=None, out_f32=False, out=None):
     K3, Cout = nbr.shape[1], w.shape[0]
     assert x.stride(1) == 1 and w.stride(1) == 1 and nbr.is_contiguous() and w.shape[1] == K3 * Cin
     if out is None:
+        assert not residual
         out = torch.empty((N, Cout), dtype=F32 if out_f32 else F16, device=x.device)
+    assert not residual or out.dtype == F16
     check(_lib.lib().gvf_sparse_conv_gemm_f16(ptr(x), x.stride(0), ptr(nbr), N, K3, Cin, ptr(w), w.stride(0), Cout, ptr(bias),
-                                              ptr(out), out.stride(0), 4 if out.dtype == F32 else 0, current_stream()),
+                                              ptr(out), out.stride(0), 3 if residual else (4 if out.dtype == F32 else 0),
+                                              current_stream()),
           "gvf_sparse_conv_gemm_f16")
     return out

@@ -30,21 +30,27 @@ class FlowEulerSampler:
         return self._inference_model(model, x_t, t, cond, **kwargs), None, 0.0
 
     def _inference_model(self, model, x_t, t, cond=None, **kwargs):
-        tt = torch.tensor([1000 * t] * x_t.shape[0], device=x_t.device, dtype=torch.float32)
+        tt = torch.tensor([1000 * t] * x_t.shape[0], device=x_t.device, dtype=torch.float32)      # SparseTensor: shape[0] = batch
         return model(x_t, tt, cond, **kwargs)
 
     @torch.no_grad()
     def sample_once(self, model, x_t, t: float, t_prev: float, cond=None, **kwargs):
-        if not x_t.is_cuda:
+        """x_t: a dense tensor, or a SparseTensor (the structured-latent stage, trellis_image_to_3d.py:238-248) whose
+        feature rows are stepped and re-wrapped on the same coordinates."""
+        sparse = hasattr(x_t, "feats") and hasattr(x_t, "replace")
+        if not (x_t.feats if sparse else x_t).is_cuda:
             raise RuntimeError("FlowEulerSampler runs on CUDA tensors only (no CPU fallback)")
         v, vn, s = self._predictions(model, x_t, t, cond, **kwargs)
-        x = x_t.float().contiguous()
-        v = v.float().contiguous()
-        vn = None if vn is None else vn.float().contiguous()
+        feats = lambda a: a.feats if sparse else a
+        x = feats(x_t).float().contiguous()
+        v = feats(v).float().contiguous()
+        vn = None if vn is None else feats(vn).float().contiguous()
         x_prev, x_0 = torch.empty_like(x), torch.empty_like(x)
         check(_lib.lib().gvf_flow_euler_step(ptr(x), ptr(v), ptr(vn), x.numel(), float(s), float(t), float(t_prev),
                                              float(self.sigma_min), ptr(x_prev), ptr(x_0), current_stream()),
               "gvf_flow_euler_step")
+        if sparse:
+            x_prev, x_0 = x_t.replace(x_prev), x_t.replace(x_0)
         return edict({"pred_x_prev": x_prev, "pred_x_0": x_0})
 
     @torch.no_grad()

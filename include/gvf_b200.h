@@ -270,6 +270,12 @@ GVF_API int gvf_small_linear(const float* x, int ldx, const void* W, const float
 GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
                            const float* w, const float* b, const void* shift, const void* scale,
                            int mod_stride, int rows_per_batch, void* stream);
+/* Same with an activation applied before the single fp16 rounding: act 0 none, 1 SiLU -- the `norm1 -> SiLU -> conv1` and
+ * `norm2 * (1 + scale) + shift -> SiLU -> conv2` pairs of SparseResBlock3d (trellis/models/structured_latent_flow.py:57-62).
+ * Widths 64 / 128 / 256 / 1024 / 2048 for act 1. */
+GVF_API int gvf_ln_mod_act_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
+                               const float* w, const float* b, const void* shift, const void* scale,
+                               int mod_stride, int rows_per_batch, int act, void* stream);
 /* MultiHeadRMSNorm on q and k, in place (model/attention/modules.py:8-15,122-125). */
 GVF_API int gvf_rmsnorm_heads_f16(void* buf, long long rows, int ld, int H, int D, int k_off,
                                   const float* gamma_q, const float* gamma_k, void* stream);
@@ -496,6 +502,15 @@ GVF_API int gvf_sparse_neighbor_map(const int* coords, int N, int B, int D, int 
                                     size_t workspace_bytes, int* nbr, int* status, void* stream);
 GVF_API int gvf_sparse_im2col_f16(const void* x, int x_is_f16, int ldx, const int* nbr, int N, int K3, int Cin,
                                   void* out, void* stream);
+/* SparseDownsample (trellis/modules/sparse/spatial.py:13-52): out[p] = (sum of the rows of coarse cell p) / (count + 1)
+ * -- the reference's scatter_reduce(zeros, 'mean') counts its zero initial value (include_self).  order int32 [N] = the
+ * fine rows grouped by cell, offsets int32 [cells + 1]; x, out fp16; C % 8 == 0. */
+GVF_API int gvf_sparse_pool_mean_f16(const void* x, int ldx, const int* order, const int* offsets, int cells, int C,
+                                     void* out, int ldo, void* stream);
+/* SparseUpsample (spatial.py:55-80: `input.feats[idx]`) and / or the skip concatenation of the flow model's output blocks
+ * (structured_latent_flow.py:253-256): out[i] = [ a[idx ? idx[i] : i, 0:Ca] | b[i, 0:Cb] ], fp16, either part may be empty. */
+GVF_API int gvf_gather_concat_f16(const void* a, int lda, int Ca, const int* idx, const void* b, int ldb, int Cb, int rows,
+                                  void* out, int ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * 8. Training step of the motion VAE (SURVEY.md rows g / a9 backward; BASELINE configs[2] and [4]).
@@ -568,7 +583,8 @@ GVF_API int gvf_vae_query_embed_bwd(const float* queries, int ldq, const void* g
 
 /* The same convolution as ONE kernel: the GEMM's TMA producer gathers the neighbour rows itself
  * (cp.async.bulk.tensor tile::gather4 through nbr, absent neighbours zero-filled), so the [N, K3 * Cin] im2col operand is
- * never written.  x fp16 [N, Cin] (row stride ldx), W fp16 [Cout, K3 * Cin], out fp16 (epilogue 0) or fp32 (4) [N, Cout].
+ * never written.  x fp16 [N, Cin] (row stride ldx), W fp16 [Cout, K3 * Cin], out fp16 (epilogue 0; epilogue 3 = fp16
+ * residual, out += fp16(conv + bias) in place: SparseResBlock3d's `h + skip_connection(x)`) or fp32 (4) [N, Cout].
  * Cin % 64 == 0, else GVF_ERR_UNSUPPORTED (callers fall back to im2col + gvf_gemm_f16).  Bit-identical to that path. */
 GVF_API int gvf_sparse_conv_gemm_f16(const void* x, int ldx, const int* nbr, int N, int K3, int Cin, const void* W, int ldw,
                                      int Cout, const float* bias, void* out, int ldo, int epilogue, void* stream);

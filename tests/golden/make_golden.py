@@ -365,6 +365,140 @@ def gen_flow_euler():
     return out
 
 
+def gen_slat_flow():
+    """The reference's own SLatFlowModel (trellis/models/structured_latent_flow.py:69-262: SparseResBlock3d down / up
+    blocks around ModulatedSparseTransformerCrossBlocks with full sparse self-attention and dense-context cross-attention)
+    on the CPU in fp32, seeded two-entry batch, plus two Euler steps of the reference's FlowEulerSampler over it.
+    Stand-ins (third-party code that is absent or CUDA-only): spconv.pytorch.SparseConvTensor as a container,
+    spconv.pytorch.SubMConv3d restated as the dense cross-correlation at the active sites (oracle.sparse_vae.subm_conv3d:
+    the submanifold definition; spconv itself is absent, so that arithmetic stays unpinned), flash_attn's varlen entry
+    points restated as plain softmax attention inside each cu_seqlens segment."""
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import sparse_vae as OSV
+
+    class _SCT:
+        def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None, **kw):
+            self._features, self.indices, self.spatial_shape, self.batch_size = features, indices, spatial_shape, batch_size
+            self.grid, self.voxel_num, self.indice_dict = grid, voxel_num, indice_dict
+            self.benchmark = self.benchmark_record = self.thrust_allocator = self._timer = None
+            self.force_algo = self.int8_scale = None
+
+        @property
+        def features(self):
+            return self._features
+
+        def replace_feature(self, f):
+            return _SCT(f, self.indices, self.spatial_shape, self.batch_size)
+
+    class SubMConv3d(torch.nn.Module):
+        def __init__(self, cin, cout, ks, dilation=1, bias=True, indice_key=None, algo=None):
+            super().__init__()
+            self.in_channels, self.out_channels, self.ks, self.dilation = cin, cout, ks, dilation
+            self.weight = torch.nn.Parameter(torch.zeros(cout, ks, ks, ks, cin))
+            self.bias = torch.nn.Parameter(torch.zeros(cout)) if bias else None
+
+        def forward(self, x):
+            grid = int(x.indices[:, 1:].max()) + 1
+            return x.replace_feature(OSV.subm_conv3d(x.features, x.indices, self.weight, self.bias, x.batch_size, grid,
+                                                     self.dilation))
+
+    spp = sys.modules["spconv.pytorch"]
+    saved_sct = spp.SparseConvTensor
+    spp.SparseConvTensor, spp.SubMConv3d = _SCT, SubMConv3d
+    sdpa = torch.nn.functional.scaled_dot_product_attention
+
+    def _seg(q, k, v, cq, ck):
+        out = torch.empty_like(q)
+        for i in range(len(cq) - 1):
+            a, b, c, d = int(cq[i]), int(cq[i + 1]), int(ck[i]), int(ck[i + 1])
+            out[a:b] = sdpa(q[a:b].transpose(0, 1).float(), k[c:d].transpose(0, 1).float(),
+                            v[c:d].transpose(0, 1).float()).transpose(0, 1).to(q.dtype)
+        return out
+
+    fa = types.ModuleType("flash_attn")
+    fa.flash_attn_varlen_qkvpacked_func = lambda qkv, cu, maxlen: _seg(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu, cu)
+    fa.flash_attn_varlen_kvpacked_func = lambda q, kv, cq, ck, mq, mk: _seg(q, kv[:, 0], kv[:, 1], cq, ck)
+    fa.flash_attn_varlen_func = lambda q, k, v, cq, ck, mq, mk: _seg(q, k, v, cq, ck)
+    saved_fa = sys.modules.get("flash_attn")
+    sys.modules["flash_attn"] = fa
+    pkg = types.ModuleType("trellis")           # a bare package: trellis/__init__.py pulls in renderers / pipelines
+    pkg.__path__ = [os.path.join(_ref_import.REF, "trellis")]
+    sys.modules["trellis"] = pkg
+    try:
+        from trellis.models.structured_latent_flow import SLatFlowModel
+        from trellis.modules import sparse as tsp
+        cfg = dict(resolution=16, in_channels=8, model_channels=128, cond_channels=128, out_channels=8, num_blocks=2,
+                   num_head_channels=64, mlp_ratio=4, patch_size=2, num_io_res_blocks=2, io_block_channels=[64],
+                   pe_mode="ape", use_fp16=False, use_skip_connection=True, share_mod=False, qk_rms_norm=True,
+                   qk_rms_norm_cross=False)
+        torch.manual_seed(0)
+        m = SLatFlowModel(**cfg).eval()
+        g0 = torch.Generator().manual_seed(77)
+        for mod in m.modules():                 # the stand-in convolutions: a seeded draw at Kaiming scale
+            if isinstance(mod, SubMConv3d):
+                mod.weight.data = torch.randn(mod.weight.shape, generator=g0) / (mod.in_channels * 27) ** 0.5
+        rerandomise_zero_layers(m)
+        for mod in m.modules():                 # norm affines / rms gammas / biases away from their 1 / 0 initial values
+            if isinstance(mod, torch.nn.LayerNorm) and mod.elementwise_affine:
+                mod.weight.data += 0.1 * torch.randn(mod.weight.shape, generator=g0)
+                mod.bias.data += 0.1 * torch.randn(mod.bias.shape, generator=g0)
+        for n_, p_ in m.named_parameters():
+            if n_.endswith("gamma") or (n_.endswith(".bias") and "norm" not in n_):
+                p_.data += 0.1 * torch.randn(p_.shape, generator=g0)
+        for p_ in m.parameters():               # fp16-representable values: the fixture stores them as halves, exactly
+            p_.data = p_.data.half().float()
+        g = torch.Generator().manual_seed(5)
+        coords = []
+        for b, n in enumerate((260, 140)):
+            lin = torch.randperm(16 ** 3, generator=g)[:n].sort().values
+            coords.append(torch.stack([torch.full((n,), b), lin // 256, (lin // 16) % 16, lin % 16], 1))
+        coords = torch.cat(coords).int()
+        x = torch.randn(coords.shape[0], 8, generator=g)
+        cond = torch.randn(2, 24, 128, generator=g)
+        t = torch.tensor([650.0, 120.0])
+        with torch.no_grad():
+            out = m(tsp.SparseTensor(x, coords), t, cond).feats
+            # hand-checked quirk: SparseDownsample's scatter_reduce(zeros, 'mean') counts the initial zero
+            down = tsp.SparseDownsample(2)(tsp.SparseTensor(x, coords))
+        import importlib.util
+        try:
+            import easydict  # noqa: F401
+        except ImportError:
+            ed = types.ModuleType("easydict")
+
+            class EasyDict(dict):
+                __getattr__ = dict.get
+
+                def __setattr__(self, k, v):
+                    self[k] = v
+            ed.EasyDict = EasyDict
+            sys.modules["easydict"] = ed
+        d = os.path.join(_ref_import.REF, "trellis", "pipelines", "samplers")
+        spk = types.ModuleType("refsamplers2")
+        spk.__path__ = [d]
+        sys.modules["refsamplers2"] = spk
+        spec = importlib.util.spec_from_file_location("refsamplers2.flow_euler", os.path.join(d, "flow_euler.py"))
+        fe = importlib.util.module_from_spec(spec)
+        sys.modules["refsamplers2.flow_euler"] = fe
+        spec.loader.exec_module(fe)
+        with torch.no_grad():
+            r = fe.FlowEulerSampler(1e-5).sample(m, tsp.SparseTensor(x, coords), cond=cond, steps=2, rescale_t=3.0,
+                                                 verbose=False)
+        return {"cfg": cfg, "state_dict": {k: v.half() for k, v in m.state_dict().items()}, "coords": coords, "x": x,
+                "cond": cond, "t": t, "out": out, "down_feats": down.feats, "down_coords": down.coords.int(),
+                "euler_samples": r.samples.feats, "euler_args": dict(steps=2, rescale_t=3.0)}
+    finally:
+        spp.SparseConvTensor = saved_sct
+        sys.modules.pop("trellis", None)
+        for k in [k for k in sys.modules if k.startswith("trellis.")]:
+            sys.modules.pop(k)
+        if saved_fa is not None:
+            sys.modules["flash_attn"] = saved_fa
+        else:
+            sys.modules.pop("flash_attn", None)
+
+
 def _bruteforce_knn_points(p1, p2, lengths1=None, lengths2=None, K=1):
     """Stand-in for pytorch3d.ops.knn_points (absent here) with its documented semantics: exact squared
     distances ((dx*dx + dy*dy) + dz*dz in fp32), ascending, ties -> lowest index, padded rows zero."""
@@ -703,6 +837,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "vae_encode":
         torch.save(gen_vae_encode(), os.path.join(HERE, "vae_encode_tiny.pt"))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "slat_flow":
+        torch.save(gen_slat_flow(), os.path.join(HERE, "slat_flow_tiny.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "flow_euler":
         torch.save(gen_flow_euler(), os.path.join(HERE, "flow_euler.pt"))
         return
@@ -725,6 +862,7 @@ def main():
     torch.save(gen_respace(), os.path.join(HERE, "respace.pt"))
     torch.save(gen_serialization(), os.path.join(HERE, "serialization.pt"))
     torch.save(gen_flow_euler(), os.path.join(HERE, "flow_euler.pt"))
+    torch.save(gen_slat_flow(), os.path.join(HERE, "slat_flow_tiny.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))

@@ -1,0 +1,164 @@
+"""TRELLIS structured-latent flow model on the device (reference
+trellis/models/structured_latent_flow.py:69-262) against oracle/slat_flow.py -- the fp32 CPU restatement pinned to the
+reference's own class by tests/golden/slat_flow_tiny.pt -- plus the two resampling kernels and the sampler over sparse
+samples.  Tolerances are relative L2 of fp16 execution against the fp32 oracle; the measured errors are printed."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+G = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "slat_flow_tiny.pt"), weights_only=False)
+
+
+def _rel(a, b):
+    return float((a.float().cpu() - b).norm() / b.norm())
+
+
+def _model(cfg, sd):
+    from gvfdiffusion_b200.trellis.models import SLatFlowModel
+    return SLatFlowModel(**cfg, device=DEV).load_state_dict(sd)
+
+
+def test_pool_mean_and_gather_concat_kernels():
+    from gvfdiffusion_b200 import ops
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from gvfdiffusion_b200.sparse.spatial import SparseDownsample, SparseUpsample
+    from oracle import slat_flow as O
+    g = torch.Generator().manual_seed(3)
+    coords = G["coords"]
+    x = torch.randn(coords.shape[0], 64, generator=g).half()
+    f_ref, c_ref, idx_ref = O.downsample(x.float(), coords)
+    st = SparseTensor(x.to(DEV), coords.to(DEV))
+    down = SparseDownsample(2)(st)
+    assert torch.equal(down.coords.cpu(), c_ref)
+    assert float((down.feats.float().cpu() - f_ref).abs().max()) < 2e-3           # one fp16 rounding of an fp32 sum
+    up = SparseUpsample(2)(down)
+    assert torch.equal(up.coords.cpu(), coords) and torch.equal(up.feats.cpu(), down.feats.cpu()[idx_ref])
+    b = torch.randn(coords.shape[0], 24, generator=g).half().to(DEV)
+    cat = ops.gather_concat(a=down.feats, idx=down.get_spatial_cache("upsample_(2, 2, 2)_idx"), b=b)
+    assert torch.equal(cat.cpu(), torch.cat([down.feats.cpu()[idx_ref], b.cpu()], 1))
+    assert torch.equal(ops.gather_concat(a=x.to(DEV), b=b).cpu(), torch.cat([x, b.cpu()], 1))
+
+
+def test_ln_silu_kernel():
+    from gvfdiffusion_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for C in (64, 128, 256, 1024, 2048):
+        x = torch.randn(77, C, generator=g).half()
+        w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        ref = torch.nn.functional.silu(torch.nn.functional.layer_norm(x.float(), (C,), w, b, 1e-6))
+        got = ops.ln_mod_act(x.to(DEV), w=w.to(DEV), b=b.to(DEV), act=1)
+        assert _rel(got, ref) < 1e-3, C
+        sc, sh = (torch.randn(1, C, generator=g) * 0.3).half(), (torch.randn(1, C, generator=g) * 0.3).half()
+        mod = torch.cat([sc, sh], 1).to(DEV)
+        ref = torch.nn.functional.silu(torch.nn.functional.layer_norm(x.float(), (C,), None, None, 1e-6) * (1 + sc.float()) + sh.float())
+        got = ops.ln_mod_act(x.to(DEV), scale=mod[0, :C], shift=mod[0, C:], mod_stride=2 * C, act=1)
+        assert _rel(got, ref) < 1e-3, C
+
+
+def test_conv_residual_epilogue_matches_two_kernel_path():
+    from gvfdiffusion_b200 import ops
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from gvfdiffusion_b200.sparse.conv import SparseConv3d
+    g = torch.Generator().manual_seed(6)
+    coords = G["coords"].to(DEV)
+    x = torch.randn(coords.shape[0], 64, generator=g).half().to(DEV)
+    conv = SparseConv3d(64, 128, 3, device=DEV)
+    conv.weight = (torch.randn(128, 27 * 64, generator=g) / 40).half().to(DEV)
+    conv.bias = torch.randn(128, generator=g).to(DEV)
+    st = SparseTensor(x, coords)
+    base = torch.randn(coords.shape[0], 128, generator=g).half().to(DEV)
+    y = conv(st).feats
+    out = base.clone()
+    ops.sparse_conv_gemm(x, conv.neighbor_map(st), conv.weight, conv.bias, out=out, residual=True)
+    assert torch.equal(out, (y.float() + base.float()).half())
+
+
+def test_forward_tiny_golden():
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    m = _model(G["cfg"], G["state_dict"])
+    out = m(SparseTensor(G["x"].to(DEV), G["coords"].to(DEV)), G["t"].to(DEV), G["cond"].to(DEV))
+    err = _rel(out.feats, G["out"])
+    print(f"\nslat flow tiny vs the reference's own class (fp32): rel L2 {err:.2e}")
+    assert out.feats.shape == G["out"].shape and err < 5e-3, err
+    # a second call (conditioning K / V and neighbour maps from their caches) gives the same bits
+    out2 = m(SparseTensor(G["x"].to(DEV), G["coords"].to(DEV)), G["t"].to(DEV), G["cond"].to(DEV))
+    assert torch.equal(out.feats, out2.feats)
+
+
+def test_sampler_over_sparse_samples_matches_reference():
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from gvfdiffusion_b200.trellis.pipelines.samplers import FlowEulerSampler
+    m = _model(G["cfg"], G["state_dict"])
+    noise = SparseTensor(G["x"].to(DEV), G["coords"].to(DEV))
+    r = FlowEulerSampler(1e-5).sample(m, noise, cond=G["cond"].to(DEV), verbose=False, **G["euler_args"])
+    err = _rel(r.samples.feats, G["euler_samples"])
+    print(f"\nslat flow, 2 Euler steps vs the reference's sampler + model: rel L2 {err:.2e}")
+    assert err < 5e-3, err
+
+
+def test_forward_shipped_widths():
+    """The widths of the shipped checkpoint (model 1024, 16 heads x 64, io 128, cond 1024, q / k RMS-norm) at depth 2 on
+    ~3000 voxels of a 32^3 grid, one entry, against the oracle."""
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from oracle import slat_flow as O
+    cfg = dict(resolution=32, in_channels=8, model_channels=1024, cond_channels=1024, out_channels=8, num_blocks=2,
+               num_heads=16, mlp_ratio=4, patch_size=2, num_io_res_blocks=2, io_block_channels=[128], pe_mode="ape",
+               use_fp16=True, qk_rms_norm=True)
+    g = torch.Generator().manual_seed(11)
+    ref_sd = {k: v for k, v in G["state_dict"].items()}
+    shapes = {}
+    C, io = 1024, 128
+
+    def res(p, cin, cout):
+        shapes.update({p + "norm1.weight": (cin,), p + "norm1.bias": (cin,), p + "conv1.conv.weight": (cout, 3, 3, 3, cin),
+                       p + "conv1.conv.bias": (cout,), p + "conv2.conv.weight": (cout, 3, 3, 3, cout), p + "conv2.conv.bias": (cout,),
+                       p + "emb_layers.1.weight": (2 * cout, C), p + "emb_layers.1.bias": (2 * cout,)})
+        if cin != cout:
+            shapes.update({p + "skip_connection.weight": (cout, cin), p + "skip_connection.bias": (cout,)})
+    res("input_blocks.0.", io, io)
+    res("input_blocks.1.", io, C)
+    res("out_blocks.0.", 2 * C, io)
+    res("out_blocks.1.", 2 * io, io)
+    shapes.update({"t_embedder.mlp.0.weight": (C, 256), "t_embedder.mlp.0.bias": (C,), "t_embedder.mlp.2.weight": (C, C),
+                   "t_embedder.mlp.2.bias": (C,), "input_layer.weight": (io, 8), "input_layer.bias": (io,),
+                   "out_layer.weight": (8, io), "out_layer.bias": (8,)})
+    for i in range(2):
+        p = f"blocks.{i}."
+        shapes.update({p + "norm2.weight": (C,), p + "norm2.bias": (C,), p + "self_attn.to_qkv.weight": (3 * C, C),
+                       p + "self_attn.to_qkv.bias": (3 * C,), p + "self_attn.q_rms_norm.gamma": (16, 64),
+                       p + "self_attn.k_rms_norm.gamma": (16, 64), p + "self_attn.to_out.weight": (C, C),
+                       p + "self_attn.to_out.bias": (C,), p + "cross_attn.to_q.weight": (C, C), p + "cross_attn.to_q.bias": (C,),
+                       p + "cross_attn.to_kv.weight": (2 * C, C), p + "cross_attn.to_kv.bias": (2 * C,),
+                       p + "cross_attn.to_out.weight": (C, C), p + "cross_attn.to_out.bias": (C,),
+                       p + "mlp.mlp.0.weight": (4 * C, C), p + "mlp.mlp.0.bias": (4 * C,), p + "mlp.mlp.2.weight": (C, 4 * C),
+                       p + "mlp.mlp.2.bias": (C,), p + "adaLN_modulation.1.weight": (6 * C, C), p + "adaLN_modulation.1.bias": (6 * C,)})
+    assert {k.split(".", 2)[-1] for k in ref_sd if k.startswith("blocks.0.")} == {k.split(".", 2)[-1] for k in shapes if k.startswith("blocks.0.")}
+    sd = {}
+    for k, shp in shapes.items():
+        if k.endswith("norm1.weight") or k.endswith("norm2.weight") or k.endswith("gamma"):
+            v = 1 + 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith("bias"):
+            v = 0.05 * torch.randn(shp, generator=g)
+        elif "adaLN" in k or "emb_layers" in k:
+            v = 0.02 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for s in shp[1:]:
+                fan_in *= s
+            v = torch.randn(shp, generator=g) / fan_in ** 0.5
+        sd[k] = v.half().float()
+    n = 3000
+    lin = torch.randperm(32 ** 3, generator=g)[:n].sort().values
+    coords = torch.stack([torch.zeros(n, dtype=torch.long), lin // 1024, (lin // 32) % 32, lin % 32], 1).int()
+    x = torch.randn(n, 8, generator=g)
+    cond = torch.randn(1, 1374, 1024, generator=g)
+    t = torch.tensor([437.0])
+    ref = O.slat_flow_forward(sd, cfg, x, coords, t, cond)
+    m = _model(cfg, sd)
+    out = m(SparseTensor(x.to(DEV), coords.to(DEV)), t.to(DEV), cond.to(DEV))
+    err = _rel(out.feats, ref)
+    print(f"\nslat flow at the shipped widths (depth 2, {n} voxels) vs the fp32 oracle: rel L2 {err:.2e}")
+    assert err < 5e-3, err
