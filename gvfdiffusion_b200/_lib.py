@@ -118,6 +118,7 @@ _SIGS = {
     "gvf_ln_mod_act_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "gvf_sparse_pool_mean_f16": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "gvf_gather_concat_f16": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "gvf_sparse_tap_gather_sum_f16": (C.c_int, [_P, C.c_longlong, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "gvf_rmsnorm_heads_f16": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "gvf_dit_modulation": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
     "gvf_ape": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),

@@ -205,6 +205,38 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const __half* __rest
   *reinterpret_cast<uint4*>(out + (size_t)r * ldo + c * 8) = v;
 }
 
+// Submanifold convolution of a nearest-neighbour UPSAMPLED tensor without materialising it (the first output block of the
+// structured-latent flow model, structured_latent_flow.py:166-172: 2 x 1024 channels at every fine voxel).  Every fine row
+// is a copy of its coarse cell's row, so the per-tap products are computed ONCE per coarse row by a plain GEMM,
+// P[c, k * Cout + o] = sum_i W[o, k, i] a[c, i] (fp32), and the convolution is a gather-sum over the 27 taps:
+//   out[n, o] = fp16( bias[o] + sum_k P[idx[nbr[n, k]], k * Cout + o] )       (nbr < 0: absent neighbour)
+// 5.4 x fewer flops than the convolution at the fine level (19792 vs 3656 rows) and no [N, 2048] operand.  idx == NULL:
+// P is indexed by the neighbour row itself (the same formulation for a tensor that is not upsampled).
+// One thread per (row, 4 channels): a warp reads 512 contiguous bytes of a P row per tap.
+__global__ void __launch_bounds__(256) sparse_tap_gather_sum_kernel(const float* __restrict__ P, long long ldp, const int* __restrict__ nbr,
+                                                                    const int* __restrict__ idx, long long rows, int K3, int co4,
+                                                                    const float* __restrict__ bias, __half* __restrict__ out, int ldo) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * co4) return;
+  const long long r = gid / co4;
+  const int c = (int)(gid - r * co4) * 4;
+  const int cout = co4 * 4;
+  float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int* nr = nbr + r * K3;
+  for (int k = 0; k < K3; ++k) {
+    int j = __ldg(nr + k);
+    if (j < 0) continue;
+    if (idx) j = __ldg(idx + j);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(P + (long long)j * ldp + (long long)k * cout + c));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(out + r * ldo + c) = pk;
+}
+
 }  // namespace gvf
 
 using namespace gvf;
@@ -298,6 +330,17 @@ GVF_API int gvf_gather_concat_f16(const void* a, int lda, int Ca, const int* idx
   const long long t = (long long)rows * ((Ca + Cb) / 8);
   gather_concat_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>((const __half*)a, lda, Ca / 8, idx, (const __half*)b,
                                                                          ldb, Cb / 8, rows, (__half*)out, ldo);
+  RET();
+}
+
+GVF_API int gvf_sparse_tap_gather_sum_f16(const float* P, long long ldp, const int* nbr, const int* idx, int N, int K3, int Cout,
+                                          const float* bias, void* out, int ldo, void* stream) {
+  if (!P || !nbr || !out || N <= 0 || K3 <= 0 || Cout <= 0) return GVF_ERR_INVALID;
+  if ((Cout % 4) || (ldp % 4) || (ldo % 4) || ldp < (long long)K3 * Cout) return GVF_ERR_INVALID;
+  if ((((uintptr_t)P | (uintptr_t)bias) & 15) || ((uintptr_t)out & 7)) return GVF_ERR_INVALID;
+  const long long t = (long long)N * (Cout / 4);
+  sparse_tap_gather_sum_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>(P, ldp, nbr, idx, N, K3, Cout / 4, bias,
+                                                                                 (__half*)out, ldo);
   RET();
 }
 

@@ -219,6 +219,24 @@ def gather_concat(a=None, idx=None, b=None, out=None):
     return out
 
 
+def sparse_tap_gather_sum(P, nbr, idx=None, bias=None, out=None):
+    """P fp32 [Nc, K3 * Cout] (per-tap products of the coarse rows), nbr int32 [N, K3], idx int32 [N] or None ->
+    fp16 [N, Cout] = bias + sum_k P[idx[nbr[:, k]], k * Cout : (k + 1) * Cout]."""
+    _req(P, F32, "P")
+    _req(nbr, torch.int32, "nbr")
+    N, K3 = nbr.shape
+    Cout = P.shape[1] // K3
+    assert P.stride(1) == 1 and nbr.is_contiguous() and P.shape[1] == K3 * Cout
+    if idx is not None:
+        _req(idx, torch.int32, "idx")
+        assert idx.is_contiguous()
+    if out is None:
+        out = torch.empty((N, Cout), dtype=F16, device=P.device)
+    check(_lib.lib().gvf_sparse_tap_gather_sum_f16(ptr(P), P.stride(0), ptr(nbr), ptr(idx), N, K3, Cout, ptr(bias), ptr(out),
+                                                   out.stride(0), current_stream()), "gvf_sparse_tap_gather_sum_f16")
+    return out
+
+
 def rmsnorm_heads_(buf, H, D, k_off, gamma_q, gamma_k):
     rows, ld = buf.shape[0], buf.stride(0)
     st = _lib.lib().gvf_rmsnorm_heads_f16(ptr(buf), rows, ld, H, D, k_off, ptr(gamma_q), ptr(gamma_k),

@@ -40,8 +40,13 @@ def downsample_plan(x: SparseTensor, factor: int):
         order = torch.sort(idx, stable=True).indices.int()
         offsets = torch.zeros(ucode.shape[0] + 1, dtype=torch.int32, device=idx.device)
         offsets[1:] = torch.cumsum(torch.bincount(idx, minlength=ucode.shape[0]), 0)
+        counts = torch.bincount(coords[:, 0].long(), minlength=x.shape[0]).tolist()
+        off, layout = 0, []
+        for cnt in counts:                                  # the coarse level's batch layout, like SparseTensor would derive it
+            layout.append(slice(off, off + cnt))
+            off += cnt
         plan = dict(n=x.coords.shape[0], coords=coords.contiguous(), idx=idx.int().contiguous(), order=order.contiguous(),
-                    offsets=offsets)
+                    offsets=offsets, layout=layout)
         x.register_spatial_cache(key, plan)
     return plan
 
@@ -58,7 +63,7 @@ class SparseDownsample:
         f = self.factor
         plan = downsample_plan(input, f)
         feats = ops.sparse_pool_mean(input.feats, plan["order"], plan["offsets"])
-        out = SparseTensor(feats, plan["coords"], torch.Size([input.shape[0], *feats.shape[1:]]), None,
+        out = SparseTensor(feats, plan["coords"], torch.Size([input.shape[0], *feats.shape[1:]]), plan["layout"],
                            input._spatial_cache, _rescale(input._scale, 1.0 / f))
         # what SparseUpsample looks up (spatial.py:49-51)
         fac = (f,) * 3

@@ -57,6 +57,7 @@ class SparseResBlock3d:
         self.conv2 = SparseConv3d(self.out_channels, self.out_channels, 3, device=device)
         self.device = torch.device(device)
         self.mod_off = 0
+        self.conv_mode = "auto"                # "fused" (TMA gather in the GEMM) | "im2col" | "auto" (measured rule below)
 
     def load_state_dict(self, sd, prefix):
         dev = self.device
@@ -64,15 +65,27 @@ class SparseResBlock3d:
         self.conv1.load_state_dict(sd, prefix + "conv1.")
         self.conv2.load_state_dict(sd, prefix + "conv2.")
         self.emb_w, self.emb_b = sd[prefix + "emb_layers.1.weight"], sd[prefix + "emb_layers.1.bias"]
+        if self.upsample:
+            # conv1 acts on a nearest-neighbour upsampled tensor: per-tap weights [(k, out), in] for the coarse-level GEMM
+            w = sd[prefix + "conv1.conv.weight"].detach()
+            self.tap_w = _h(w.reshape(w.shape[0], 27, w.shape[-1]).permute(1, 0, 2).reshape(27 * w.shape[0], w.shape[-1]), dev)
         self.skip_w = self.skip_b = None
         if prefix + "skip_connection.weight" in sd:
             self.skip_w, self.skip_b = _h(sd[prefix + "skip_connection.weight"], dev), _f(sd[prefix + "skip_connection.bias"], dev)
         return self
 
-    @staticmethod
-    def _conv(conv, st, a, out=None, residual=False):
+    def _conv(self, conv, st, a, out=None, residual=False):
+        """One submanifold convolution.  Two executions of the same arithmetic (bit-identical): the GEMM whose TMA producer
+        gathers the neighbour rows (no im2col operand), or an explicit fp16 im2col operand + the plain GEMM.  On the B200
+        the gather form is bound by the issue rate of its `tile::gather4` loads (one 4 x 128 B box per instruction, ~37 ns
+        each: 1.2 us per 128 x 64 operand block, tools/slat_flow_bench.py --conv-ab), so `auto` takes im2col while its
+        operand stays below 1 GB and keeps the gather form for larger ones."""
         nbr = conv.neighbor_map(st)
-        if conv.in_channels % 64 == 0:
+        fused_ok = conv.in_channels % 64 == 0
+        mode = self.conv_mode
+        if mode == "auto":
+            mode = "fused" if fused_ok and a.shape[0] * 27 * conv.in_channels * 2 > (1 << 30) else "im2col"
+        if mode == "fused" and fused_ok:
             return ops.sparse_conv_gemm(a, nbr, conv.weight, conv.bias, out=out, residual=residual)
         cols = ops.sparse_im2col(a, nbr)
         return ops.gemm(cols, conv.weight, conv.bias, ops.EPI_RESID_F16 if residual else ops.EPI_F16, out=out)
@@ -84,11 +97,14 @@ class SparseResBlock3d:
         a = ops.ln_mod_act(feats, w=self.n1w, b=self.n1b, act=1)                       # silu(norm1(x)), :57-58
         skip = feats if self.skip_w is None else ops.gemm(feats, self.skip_w, self.skip_b, ops.EPI_F16)
         if idx is not None:                                                            # _updown (:56) after the row-wise work
-            a = ops.gather_concat(a=a, idx=idx)
+            # conv1 of the upsampled tensor = per-tap products of the COARSE rows (one GEMM) + a gather-sum over the taps
+            P = ops.gemm(a, self.tap_w, None, ops.EPI_F32)
+            h = ops.sparse_tap_gather_sum(P, self.conv1.neighbor_map(st), idx, self.conv1.bias)
             skip = ops.gather_concat(a=skip, idx=idx)
-        elif self.skip_w is None:
-            skip = skip.clone()                                                        # conv2 accumulates in place
-        h = self._conv(self.conv1, st, a)
+        else:
+            if self.skip_w is None:
+                skip = skip.clone()                                                    # conv2 accumulates in place
+            h = self._conv(self.conv1, st, a)
         a2 = torch.empty_like(h)
         for b, s in enumerate(st.layout):                                              # norm2 * (1 + scale) + shift, silu (:60-61)
             if s.stop > s.start:
@@ -191,6 +207,7 @@ class SLatFlowModel:
         self._kv_cache = {}
         self._ws = {}
         self._loaded = False
+        self.use_graphs = False               # True: __call__ replays a captured graph per (coordinates, conditioning)
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, sd, strict=True):
@@ -226,32 +243,71 @@ class SLatFlowModel:
         return self
 
     # ------------------------------------------------------------------ caches
-    def _context(self, cond):
-        """K / V of every block for one conditioning tensor, computed once (the sampler calls the model `steps` times with
-        the same `cond` / `neg_cond`).  The entry keeps `cond` alive so that its address cannot be recycled."""
+    def _context_entry(self, cond):
+        """Per conditioning tensor: the K / V of every block, computed once (the sampler calls the model `steps` times with
+        the same `cond` / `neg_cond`), and the CUDA graphs captured against them.  The entry keeps `cond` alive so that its
+        address cannot be recycled; evicting an entry drops its graphs with it."""
         key = (cond.data_ptr(), cond._version, tuple(cond.shape), cond.dtype)
         hit = self._kv_cache.get(key)
         if hit is None:
             if len(self._kv_cache) >= 4:
                 self._kv_cache.pop(next(iter(self._kv_cache)))
             c16 = cond.detach().to(self.device, F16).contiguous()
-            hit = (cond, [blk.context_kv(c16) for blk in self.blocks])
+            hit = {"cond": cond, "kv": [blk.context_kv(c16) for blk in self.blocks], "graphs": {}}
             self._kv_cache[key] = hit
-        return hit[1]
+        return hit
+
+    def _context(self, cond):
+        return self._context_entry(cond)["kv"]
 
     def reset_conditioning(self):
         self._kv_cache.clear()
 
     def _workspace(self, n):
+        """One set of activation buffers per row count, kept for the engine's lifetime (captured graphs point into them)."""
         ws = self._ws.get(n)
         if ws is None:
             C, dev = self.model_channels, self.device
-            self._ws.clear()
             ws = dict(A=torch.empty((n, C), dtype=F16, device=dev), QKV=torch.empty((n, 3 * C), dtype=F16, device=dev),
                       AO=torch.empty((n, C), dtype=F16, device=dev),
                       H1=torch.empty((n, int(C * self.mlp_ratio)), dtype=F16, device=dev))
             self._ws[n] = ws
         return ws
+
+    # ------------------------------------------------------------------ CUDA-graph replay of one call
+    @torch.no_grad()
+    def forward_graphed(self, x: SparseTensor, t: torch.Tensor, cond: torch.Tensor) -> SparseTensor:
+        """forward() replayed from a CUDA graph (one call = ~450 launches; the sampler repeats it 25 x 2 times on the same
+        coordinates and conditioning).  Keyed on the coordinate tensor and the conditioning entry; inputs are copied into
+        the graph's static buffers, the result is copied out."""
+        if not (x.feats.is_cuda and cond.is_cuda):
+            raise RuntimeError("SLatFlowModel runs on CUDA tensors only (no CPU fallback)")
+        ent = self._context_entry(cond)
+        B = x.shape[0]
+        key = (x.coords.data_ptr(), x.coords.shape[0], B)
+        g = ent["graphs"].get(key)
+        tt = t.to(self.device, F32).reshape(-1)
+        if tt.numel() == 1 and B > 1:
+            tt = tt.expand(B)
+        if g is None:
+            xs = x.feats.to(F32).clone()
+            ts = tt.clone()
+            sx = x.replace(xs)
+            self.forward(sx, ts, cond)                         # warm-up: resampling plan, neighbour maps, workspace
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.forward(sx, ts, cond).feats
+            # `sx` stays with the graph: its spatial cache owns the neighbour maps / resampling plan / APE the graph reads
+            g = (graph, xs, ts, out, sx)
+            if len(ent["graphs"]) >= 4:
+                ent["graphs"].clear()
+            ent["graphs"][key] = g
+        graph, xs, ts, out, _ = g
+        xs.copy_(x.feats)
+        ts.copy_(tt)
+        graph.replay()
+        return x.replace(out.clone())
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -308,4 +364,5 @@ class SLatFlowModel:
         ops.gemm(a, self.out_w, self.out_b, ops.EPI_F32_COMPACT, out=out)                            # out_layer (:259)
         return x.replace(out)
 
-    __call__ = forward
+    def __call__(self, x, t, cond):
+        return self.forward_graphed(x, t, cond) if self.use_graphs else self.forward(x, t, cond)

@@ -511,6 +511,14 @@ GVF_API int gvf_sparse_pool_mean_f16(const void* x, int ldx, const int* order, c
  * (structured_latent_flow.py:253-256): out[i] = [ a[idx ? idx[i] : i, 0:Ca] | b[i, 0:Cb] ], fp16, either part may be empty. */
 GVF_API int gvf_gather_concat_f16(const void* a, int lda, int Ca, const int* idx, const void* b, int ldb, int Cb, int rows,
                                   void* out, int ldo, void* stream);
+/* Submanifold convolution of a nearest-neighbour upsampled tensor without materialising it (the first output block of the
+ * flow model, structured_latent_flow.py:166-172 -> SparseUpsample then SparseConv3d): the per-tap products
+ * P[c, k * Cout + o] = sum_i W[o, k, i] a[c, i] are computed once per COARSE row by gvf_gemm_f16 (fp32 store), then
+ *   out[n, o] = fp16(bias[o] + sum_k P[idx[nbr[n, k]], k * Cout + o])
+ * with nbr int32 [N, K3] the fine level's neighbour map (-1 = absent) and idx int32 [N] the coarse cell of every fine row
+ * (NULL: P is indexed by the neighbour row itself).  Cout % 4 == 0. */
+GVF_API int gvf_sparse_tap_gather_sum_f16(const float* P, long long ldp, const int* nbr, const int* idx, int N, int K3, int Cout,
+                                          const float* bias, void* out, int ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * 8. Training step of the motion VAE (SURVEY.md rows g / a9 backward; BASELINE configs[2] and [4]).

@@ -229,10 +229,10 @@ def test_ln_mod(C, dt):
     _close(ops.ln_mod(x, eps=1e-5), F.layer_norm(x.float(), (C,), None, None, 1e-5), 1e-3)
 
 
-def test_rmsnorm_heads():
+@pytest.mark.parametrize("rows,H,D", [(200, 4, 32), (203, 16, 64), (77, 2, 64)])
+def test_rmsnorm_heads(rows, H, D):
     from gvfdiffusion_b200 import ops
     g = _g(9)
-    rows, H, D = 200, 4, 32
     qkv = _rand((rows, 3 * H * D), g).half()
     gq, gk = _rand((H, D), g) + 1, _rand((H, D), g) + 1
     q, k, v = qkv.float().reshape(rows, 3, H, D).unbind(1)

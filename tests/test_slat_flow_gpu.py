@@ -76,6 +76,46 @@ def test_conv_residual_epilogue_matches_two_kernel_path():
     assert torch.equal(out, (y.float() + base.float()).half())
 
 
+def test_upsampled_conv_as_tap_products_plus_gather_sum():
+    """conv(upsample(a)) == gather-sum over the taps of the coarse rows' per-tap products (fp32 until the single rounding)."""
+    from gvfdiffusion_b200 import ops
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from gvfdiffusion_b200.sparse.conv import SparseConv3d
+    from gvfdiffusion_b200.sparse.spatial import downsample_plan
+    from oracle import sparse_vae as OSV
+    g = torch.Generator().manual_seed(8)
+    coords = G["coords"]
+    st = SparseTensor(torch.zeros(coords.shape[0], 8, device=DEV), coords.to(DEV))
+    plan = downsample_plan(st, 2)
+    cells, Cin, Cout = plan["coords"].shape[0], 128, 64
+    a = torch.randn(cells, Cin, generator=g).half()
+    w = (torch.randn(Cout, 3, 3, 3, Cin, generator=g) / (27 * Cin) ** 0.5).half()
+    bias = torch.randn(Cout, generator=g)
+    idx = plan["idx"].cpu().long()
+    ref = OSV.subm_conv3d(a.float()[idx], coords, w.float(), bias, 2, 16)
+    tap_w = w.reshape(Cout, 27, Cin).permute(1, 0, 2).reshape(27 * Cout, Cin).contiguous().to(DEV)
+    P = ops.gemm(a.to(DEV), tap_w, None, ops.EPI_F32)
+    conv = SparseConv3d(Cin, Cout, 3, device=DEV)
+    got = ops.sparse_tap_gather_sum(P, conv.neighbor_map(st), plan["idx"], bias.to(DEV))
+    assert _rel(got, ref) < 1e-3
+    # idx = None: the same formulation for a tensor that is not upsampled
+    x = torch.randn(coords.shape[0], Cin, generator=g).half()
+    P = ops.gemm(x.to(DEV), tap_w, None, ops.EPI_F32)
+    got = ops.sparse_tap_gather_sum(P, conv.neighbor_map(st), None, bias.to(DEV))
+    assert _rel(got, OSV.subm_conv3d(x.float(), coords, w.float(), bias, 2, 16)) < 1e-3
+
+
+def test_conv_modes_are_bit_identical():
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    outs = []
+    for mode in ("fused", "im2col"):
+        m = _model(G["cfg"], G["state_dict"])
+        for blk in m.input_blocks + m.out_blocks:
+            blk.conv_mode = mode
+        outs.append(m(SparseTensor(G["x"].to(DEV), G["coords"].to(DEV)), G["t"].to(DEV), G["cond"].to(DEV)).feats)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_forward_tiny_golden():
     from gvfdiffusion_b200.sparse.basic import SparseTensor
     m = _model(G["cfg"], G["state_dict"])
@@ -86,6 +126,26 @@ def test_forward_tiny_golden():
     # a second call (conditioning K / V and neighbour maps from their caches) gives the same bits
     out2 = m(SparseTensor(G["x"].to(DEV), G["coords"].to(DEV)), G["t"].to(DEV), G["cond"].to(DEV))
     assert torch.equal(out.feats, out2.feats)
+
+
+def test_graph_replay_is_bit_identical_to_eager():
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    m = _model(G["cfg"], G["state_dict"])
+    coords, cond = G["coords"].to(DEV), G["cond"].to(DEV)
+    g = torch.Generator().manual_seed(9)
+    m.use_graphs = True
+    for i in range(3):                                                   # capture, then two replays with new inputs
+        x = torch.randn(coords.shape[0], 8, generator=g).to(DEV)
+        t = torch.tensor([100.0 + 300 * i, 900.0 - 200 * i], device=DEV)
+        got = m(SparseTensor(x, coords), t, cond).feats
+        want = m.forward(SparseTensor(x, coords), t, cond).feats
+        assert torch.equal(got, want), i
+    # another conditioning tensor gets its own K / V and graph
+    cond2 = (cond * 0.5).contiguous()
+    x = torch.randn(coords.shape[0], 8, generator=g).to(DEV)
+    t = torch.tensor([500.0, 500.0], device=DEV)
+    assert torch.equal(m(SparseTensor(x, coords), t, cond2).feats, m.forward(SparseTensor(x, coords), t, cond2).feats)
+    assert torch.equal(m(SparseTensor(x, coords), t, cond).feats, m.forward(SparseTensor(x, coords), t, cond).feats)
 
 
 def test_sampler_over_sparse_samples_matches_reference():
