@@ -499,6 +499,106 @@ def gen_slat_flow():
             sys.modules.pop("flash_attn", None)
 
 
+def gen_slat_decoder_gs():
+    """The reference's own SLatGaussianDecoder (trellis/models/structured_latent_vae/decoder_gs.py:10-122 over
+    SparseTransformerBase, base.py:36-117: input_layer + APE -> swin SparseTransformerBlocks -> layer_norm -> out_layer ->
+    to_representation) on the CPU in fp32.  Stand-ins: the SparseConvTensor container, flash_attn's packed-QKV calls as
+    per-segment SDPA, and a plain attribute container for trellis.representations.Gaussian (its constructor needs CUDA and
+    utils3d; the decoder only sets attributes on it)."""
+    import types
+
+    class _SCT:
+        def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None, **kw):
+            self._features, self.indices, self.spatial_shape, self.batch_size = features, indices, spatial_shape, batch_size
+            self.grid, self.voxel_num, self.indice_dict = grid, voxel_num, indice_dict
+            self.benchmark = self.benchmark_record = self.thrust_allocator = self._timer = None
+            self.force_algo = self.int8_scale = None
+
+        @property
+        def features(self):
+            return self._features
+
+        def replace_feature(self, f):
+            return _SCT(f, self.indices, self.spatial_shape, self.batch_size)
+
+    class Gaussian:
+        def __init__(self, **kw):
+            self.init_params = kw
+
+    spp = sys.modules["spconv.pytorch"]
+    saved_sct = spp.SparseConvTensor
+    spp.SparseConvTensor = _SCT
+    sdpa = torch.nn.functional.scaled_dot_product_attention
+
+    def varlen(qkv, cu, maxlen):
+        out = torch.empty_like(qkv[:, 0])
+        for i in range(len(cu) - 1):
+            a, b = int(cu[i]), int(cu[i + 1])
+            q, k, v = (t.transpose(0, 1).float() for t in qkv[a:b].unbind(1))
+            out[a:b] = sdpa(q, k, v).transpose(0, 1).to(qkv.dtype)
+        return out
+
+    def packed(qkv):
+        q, k, v = (t.transpose(1, 2).float() for t in qkv.unbind(2))
+        return sdpa(q, k, v).transpose(1, 2).to(qkv.dtype)
+
+    fa = types.ModuleType("flash_attn")
+    fa.flash_attn_varlen_qkvpacked_func, fa.flash_attn_qkvpacked_func = varlen, packed
+    saved_fa = sys.modules.get("flash_attn")
+    sys.modules["flash_attn"] = fa
+
+    def bare(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+    T = os.path.join(_ref_import.REF, "trellis")
+    bare("trellis", T)
+    bare("trellis.models", os.path.join(T, "models"))
+    bare("trellis.models.structured_latent_vae", os.path.join(T, "models", "structured_latent_vae"))
+    bare("trellis.utils", os.path.join(T, "utils"))
+    rep = types.ModuleType("trellis.representations")
+    rep.Gaussian = Gaussian
+    sys.modules["trellis.representations"] = rep
+    try:
+        from trellis.models.structured_latent_vae.decoder_gs import SLatGaussianDecoder
+        from trellis.modules import sparse as tsp
+        rep_cfg = {"lr": {"_xyz": 1.0, "_features_dc": 1.0, "_opacity": 1.0, "_scaling": 1.0, "_rotation": 0.1},
+                   "perturb_offset": True, "voxel_size": 1.5, "num_gaussians": 4, "2d_filter_kernel_size": 0.1,
+                   "3d_filter_kernel_size": 9e-4, "scaling_bias": 4e-3, "opacity_bias": 0.1, "scaling_activation": "softplus"}
+        cfg = dict(resolution=16, model_channels=128, latent_channels=8, num_blocks=2, num_head_channels=64, mlp_ratio=4,
+                   attn_mode="swin", window_size=8, pe_mode="ape", use_fp16=False, qk_rms_norm=False,
+                   representation_config=rep_cfg)
+        torch.manual_seed(0)
+        m = SLatGaussianDecoder(**cfg).eval()
+        rerandomise_zero_layers(m, std=0.05)
+        g = torch.Generator().manual_seed(15)
+        coords = []
+        for b, n in enumerate((170, 110)):
+            lin = torch.randperm(16 ** 3, generator=g)[:n].sort().values
+            coords.append(torch.stack([torch.full((n,), b), lin // 256, (lin // 16) % 16, lin % 16], 1))
+        coords = torch.cat(coords).int()
+        latent = torch.randn(coords.shape[0], 8, generator=g)
+        rows = {}
+        def _keep(mod, i, o):                   # a forward hook that returns a value would replace the output
+            rows["feats"] = o.feats.detach().clone()
+        hook = m.out_layer.register_forward_hook(_keep)
+        with torch.no_grad():
+            reps = m(tsp.SparseTensor(latent, coords))
+        hook.remove()
+        names = ("_xyz", "_features_dc", "_scaling", "_rotation", "_opacity")
+        return {"cfg": cfg, "state_dict": {k: v.clone() for k, v in m.state_dict().items()}, "coords": coords, "latent": latent,
+                "rows": rows["feats"], "reps": [{n: getattr(r, n).clone() for n in names} for r in reps],
+                "init_params": [r.init_params for r in reps]}
+    finally:
+        spp.SparseConvTensor = saved_sct
+        for k in [k for k in sys.modules if k == "trellis" or k.startswith("trellis.")]:
+            sys.modules.pop(k)
+        if saved_fa is not None:
+            sys.modules["flash_attn"] = saved_fa
+        else:
+            sys.modules.pop("flash_attn", None)
+
+
 def _bruteforce_knn_points(p1, p2, lengths1=None, lengths2=None, K=1):
     """Stand-in for pytorch3d.ops.knn_points (absent here) with its documented semantics: exact squared
     distances ((dx*dx + dy*dy) + dz*dz in fp32), ascending, ties -> lowest index, padded rows zero."""
@@ -837,6 +937,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "vae_encode":
         torch.save(gen_vae_encode(), os.path.join(HERE, "vae_encode_tiny.pt"))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "slat_decoder_gs":
+        torch.save(gen_slat_decoder_gs(), os.path.join(HERE, "slat_decoder_gs_tiny.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "slat_flow":
         torch.save(gen_slat_flow(), os.path.join(HERE, "slat_flow_tiny.pt"))
         return
@@ -863,6 +966,7 @@ def main():
     torch.save(gen_serialization(), os.path.join(HERE, "serialization.pt"))
     torch.save(gen_flow_euler(), os.path.join(HERE, "flow_euler.pt"))
     torch.save(gen_slat_flow(), os.path.join(HERE, "slat_flow_tiny.pt"))
+    torch.save(gen_slat_decoder_gs(), os.path.join(HERE, "slat_decoder_gs_tiny.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))

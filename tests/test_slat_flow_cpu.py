@@ -49,3 +49,41 @@ def test_product_mirror_builds_the_reference_block_lists():
     for i, b in enumerate(m.out_blocks):
         assert tuple(sd[f"out_blocks.{i}.conv1.conv.weight"].shape) == (b.out_channels, 3, 3, 3, b.channels)
     assert m.input_blocks[-1].downsample and m.out_blocks[0].upsample
+
+
+# ---------------------------------------------------------------------------------------------- SLatGaussianDecoder
+GD = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "slat_decoder_gs_tiny.pt"), weights_only=False)
+
+
+def _gvf_names(sd):
+    """The reference's TRELLIS decoder under the names of GVF's own static-VAE decoder (same architecture)."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("blocks."):
+            out["decoder." + k[7:]] = v
+        elif k.startswith("input_layer."):
+            out["from_latent." + k[12:]] = v
+        elif k.startswith("out_layer."):
+            out[k] = v
+    return out
+
+
+def test_gaussian_decoder_oracle_matches_reference_class():
+    """oracle.sparse_window.vae_decode / oracle.sparse_vae.to_representation (the static-VAE restatements) reproduce the
+    reference's own SLatGaussianDecoder: out_layer rows and the raw tensors of every batch entry's Gaussian model."""
+    from oracle import sparse_vae as OSV
+    from oracle import sparse_window as OSW
+    cfg = GD["cfg"]
+    rows = OSW.vae_decode(_gvf_names(GD["state_dict"]), cfg["num_blocks"], cfg["model_channels"] // cfg["num_head_channels"],
+                          GD["latent"], GD["coords"], cfg["window_size"], precision="fp32", use_fp16=False, norm_output=True)
+    assert float((rows - GD["rows"]).norm() / GD["rows"].norm()) < 1e-5
+    rc = dict(cfg["representation_config"], reg_mode="soft_invoxel")
+    pert = OSV.build_perturbation(rc["num_gaussians"], "soft_invoxel", rc["voxel_size"])
+    assert float((pert - GD["state_dict"]["offset_perturbation"]).abs().max()) < 1e-6
+    raw = OSV.to_representation(GD["rows"], GD["coords"], rc, cfg["resolution"], pert)
+    G, off = rc["num_gaussians"], 0
+    for b, rep in enumerate(GD["reps"]):
+        n = int((GD["coords"][:, 0] == b).sum()) * G
+        for name, want in rep.items():
+            assert float((raw[name][off:off + n] - want).abs().max()) < 1e-6, (b, name)
+        off += n

@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=24)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--no-standin", action="store_true")
+    ap.add_argument("--stage", action="store_true", help="time sample_slat (25 steps, guidance interval) + decode_slat")
     ap.add_argument("--conv-ab", action="store_true", help="time the ResBlock convolutions as gather-fused GEMM vs im2col + GEMM")
     ap.add_argument("--profile-one", action="store_true", help="one eager call between cudaProfilerStart / Stop (for "
                     "ncu --profile-from-start off), no timing")
@@ -202,6 +203,44 @@ def main():
     out = model(st, t, cond).feats
     plan = downsample_plan(st, 2)
     n, nc = coords.shape[0], plan["coords"].shape[0]
+    if a.stage:
+        from gvfdiffusion_b200.trellis.models import SLatGaussianDecoder
+        from gvfdiffusion_b200.trellis.pipelines.trellis_image_to_3d import TrellisImageTo3DPipeline
+        DC, DH, DB, NG = 768, 12, 12, 8
+        dsd = {}
+        gg = torch.Generator().manual_seed(3)
+        for nm, (o, i) in {"input_layer": (DC, 8), "out_layer": (14 * NG, DC)}.items():
+            dsd[nm + ".weight"], dsd[nm + ".bias"] = torch.randn(o, i, generator=gg) / math.sqrt(i), torch.zeros(o)
+        for b in range(DB):
+            for nm, (o, i) in {"attn.to_qkv": (3 * DC, DC), "attn.to_out": (DC, DC), "mlp.mlp.0": (4 * DC, DC), "mlp.mlp.2": (DC, 4 * DC)}.items():
+                dsd[f"blocks.{b}.{nm}.weight"], dsd[f"blocks.{b}.{nm}.bias"] = torch.randn(o, i, generator=gg) / math.sqrt(i), torch.zeros(o)
+        rep_cfg = {"lr": {"_xyz": 1.0, "_features_dc": 1.0, "_opacity": 1.0, "_scaling": 1.0, "_rotation": 0.1},
+                   "perturb_offset": True, "voxel_size": 1.5, "num_gaussians": NG, "2d_filter_kernel_size": 0.1,
+                   "3d_filter_kernel_size": 9e-4, "scaling_bias": 4e-3, "opacity_bias": 0.1, "scaling_activation": "softplus"}
+        dec = SLatGaussianDecoder(resolution=64, model_channels=DC, latent_channels=8, num_blocks=DB, num_heads=DH, use_fp16=True,
+                                  representation_config=rep_cfg, device=dev).load_state_dict(dsd)
+        model.use_graphs = True
+        args = {"slat_sampler": {"name": "FlowEulerGuidanceIntervalSampler", "args": {"sigma_min": 1e-5},
+                                 "params": {"steps": 25, "cfg_strength": 3.0, "cfg_interval": [0.5, 1.0], "rescale_t": 3.0}},
+                "slat_normalization": {"mean": [0.0] * 8, "std": [1.0] * 8}}
+        pipe = TrellisImageTo3DPipeline.from_args(args, {"slat_flow_model": model, "slat_decoder_gs": dec}, device=dev)
+        cd = {"cond": cond, "neg_cond": torch.zeros_like(cond)}
+        calls = [0]
+        fwd = model.forward_graphed
+        def counted(*aa):
+            calls[0] += 1
+            return fwd(*aa)
+        model.forward_graphed = counted
+        pipe.sample_slat(cd, coords, noise=x)
+        ncalls, calls[0] = calls[0], 0
+        ms_sample = timed(lambda: pipe.sample_slat(cd, coords, noise=x), 3, warmup=1)
+        slat = pipe.sample_slat(cd, coords, noise=x)
+        ms_dec = timed(lambda: pipe.decode_slat(slat), 5, warmup=2)
+        print(json.dumps({"metric": "TRELLIS structured-latent stage (sample_slat 25 steps with guidance interval + decode_slat)",
+                          "value": ms_sample + ms_dec, "unit": "ms", "higher_is_better": False, "sample_slat_ms": ms_sample,
+                          "model_calls": ncalls, "decode_slat_ms": ms_dec, "voxels": n, "gaussians": n * NG,
+                          "coarse_tokens": nc, "cond_tokens": L}))
+        return
     if a.conv_ab:
         from gvfdiffusion_b200.sparse.conv import SparseConv3d
         res = {}
