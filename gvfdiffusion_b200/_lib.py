@@ -52,6 +52,7 @@ _SIGS = {
                                       _P, _P, _P, C.c_size_t, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_gaussian_tensor": (C.c_int, [C.POINTER(RasterParams), C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "gvf_fps": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "gvf_fps_ordered": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "gvf_vox2seq_encode": (C.c_int, [_P, C.c_longlong, C.POINTER(C.c_int), C.c_int, _P, _P]),
     "gvf_vox2seq_decode": (C.c_int, [_P, C.c_longlong, C.POINTER(C.c_int), C.c_int, _P, _P]),
     "gvf_attn_fwd_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

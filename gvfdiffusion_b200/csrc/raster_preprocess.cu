@@ -442,6 +442,87 @@ __global__ void __launch_bounds__(1024, 1) fps_smem2_kernel(const float* __restr
   }
 }
 
+// Third generation: exact pruning.  Every thread owns PER CONSECUTIVE points (thread (w, l): points [PER (32 w + l), + PER)),
+// keeps their bounding box in registers next to their running minimum distances, and caches its candidate (its largest
+// running minimum and the lowest index that attains it).  Rows of the path's clouds are voxel-major with the voxels in
+// lexicographic order (sparse/basic.py layout, `argwhere` of the occupancy grid), so 16 consecutive points are two
+// neighbouring voxels and the box is small.  A new sample c can only lower a running minimum that is larger than the
+// point's distance to c, so a thread whose box is at least `best` away from c has nothing to update and its cached
+// candidate stays valid; a warp in which no thread is active goes straight to the reductions.  The bound is evaluated with
+// the SAME individually rounded operations as the distance itself ((ex*ex + ey*ey) + ez*ez, ex = the per-axis gap to the
+// box): subtraction, multiplication and addition are monotone under round-to-nearest, so bound <= distance holds in floating
+// point, not just in exact arithmetic, and the skipped points' minima are provably unchanged -- the selected indices are
+// those of the brute-force kernels bit for bit, whatever the row order (an unordered cloud only prunes less and then costs
+// what the second generation costs plus the box test).  Shared memory holds the coordinates transposed per warp
+// (point j of lane l at 32 PER w + 32 j + l) so that the lanes' loads stay conflict-free.  Tie rule unchanged (lowest index).
+template <int PER>
+__global__ void __launch_bounds__(1024, 1) fps_pruned_kernel(const float* __restrict__ pts, int ld, int P, int K,
+                                                              int start, int* __restrict__ out_idx) {
+  extern __shared__ float sxyz[];                  // x[0..Pp) | y | z, Pp = PER * 1024, transposed per warp
+  __shared__ unsigned sd[2][32];
+  __shared__ unsigned si[2][32];
+  constexpr int Pp = PER * 1024;
+  float* sx = sxyz; float* sy = sxyz + Pp; float* sz = sxyz + 2 * Pp;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int first = (w * 32 + lane) * PER;         // this thread's first point
+  const int sbase = w * 32 * PER + lane;           // its shared-memory slot for j = 0 (stride 32 per j)
+  float md[PER], px[PER];
+  float lox = 3.0e38f, loy = 3.0e38f, loz = 3.0e38f, hix = -3.0e38f, hiy = -3.0e38f, hiz = -3.0e38f;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = first + j;
+    const bool ok = i < P;
+    const float x = ok ? pts[(size_t)i * ld] : 0.f, y = ok ? pts[(size_t)i * ld + 1] : 0.f, z = ok ? pts[(size_t)i * ld + 2] : 0.f;
+    px[j] = x; sx[sbase + 32 * j] = x; sy[sbase + 32 * j] = y; sz[sbase + 32 * j] = z;
+    md[j] = ok ? 3.0e38f : -1.0f;                  // padding never wins: min(-1, d) = -1 < any distance
+    if (ok) {
+      lox = fminf(lox, x); loy = fminf(loy, y); loz = fminf(loz, z);
+      hix = fmaxf(hix, x); hiy = fmaxf(hiy, y); hiz = fmaxf(hiz, z);
+    }
+  }
+  float best = first < P ? 3.0e38f : -1.0f;        // cached candidate of this thread
+  unsigned bi = first < P ? (unsigned)first : 0xffffffffu;
+  unsigned cur = (unsigned)start;
+  if (tid == 0) out_idx[0] = start;
+  __syncthreads();
+  for (int k = 1; k < K; ++k) {
+    const unsigned cw = cur / (32 * PER), cr = cur % (32 * PER);
+    const unsigned ca = cw * (32 * PER) + (cr % PER) * 32 + cr / PER;
+    const float cx = sx[ca], cy = sy[ca], cz = sz[ca];
+    // gap to the box per axis, then the distance's own operation sequence on the gaps
+    const float ex = cx < lox ? __fsub_rn(lox, cx) : (cx > hix ? __fsub_rn(cx, hix) : 0.f);
+    const float ey = cy < loy ? __fsub_rn(loy, cy) : (cy > hiy ? __fsub_rn(cy, hiy) : 0.f);
+    const float ez = cz < loz ? __fsub_rn(loz, cz) : (cz > hiz ? __fsub_rn(cz, hiz) : 0.f);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+    const bool active = lb < best;                  // best < 0 (padding only): never
+    if (__any_sync(0xffffffffu, active)) {
+      if (active) {
+        float nb = -1.0f;
+        unsigned ni = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(sy[sbase + 32 * j], cy), dz = __fsub_rn(sz[sbase + 32 * j], cz);
+          const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          const float m = fminf(md[j], d);
+          md[j] = m;
+          if (m > nb) { nb = m; ni = (unsigned)(first + j); }     // ascending index: first maximum kept
+        }
+        best = nb; bi = ni;
+      }
+    }
+    unsigned ub = best < 0.f ? 0u : __float_as_uint(best);
+    unsigned wm = __reduce_max_sync(0xffffffffu, ub);
+    const unsigned wi = __reduce_min_sync(0xffffffffu, ub == wm ? bi : 0xffffffffu);
+    if (lane == 0) { sd[k & 1][w] = wm; si[k & 1][w] = wi; }
+    __syncthreads();
+    ub = sd[k & 1][lane];
+    const unsigned ci = si[k & 1][lane];
+    wm = __reduce_max_sync(0xffffffffu, ub);
+    cur = __reduce_min_sync(0xffffffffu, ub == wm ? ci : 0xffffffffu);
+    if (tid == 0) out_idx[k] = (int)cur;
+  }
+}
+
 // Cluster variant: the cloud is spread over the 8 CTAs of one thread-block cluster, 512 threads each, every
 // thread keeps the coordinates and running minimum distances of its PER points in REGISTERS (the single-CTA
 // kernel above re-reads all 196 KB of coordinates from shared memory for every sample: 1536 clocks of
@@ -539,8 +620,21 @@ extern "C" GVF_API int gvf_gaussian_tensor(const gvf_raster_params* prm, int P, 
   return cudaGetLastError() == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
 }
 
+static int fps_impl(const float* pts, int ld, int P, int K, int start, float* workspace, int32_t* out_idx, void* stream,
+                    bool ordered);
 extern "C" GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start, float* workspace,
                                int32_t* out_idx, void* stream) {
+  return fps_impl(pts, ld, P, K, start, workspace, out_idx, stream, false);
+}
+// Same result, for clouds whose rows are spatially ordered (voxel-major Gaussians of lexicographically ordered voxels: every
+// cloud the path samples): the exactly pruned kernel, 3.1 ms instead of 5.0 at 16384 -> 4096.  On an unordered cloud it is
+// still exact but slower than gvf_fps (6.3 ms), hence the separate entry point.
+extern "C" GVF_API int gvf_fps_ordered(const float* pts, int ld, int P, int K, int start, float* workspace,
+                                       int32_t* out_idx, void* stream) {
+  return fps_impl(pts, ld, P, K, start, workspace, out_idx, stream, true);
+}
+static int fps_impl(const float* pts, int ld, int P, int K, int start, float* workspace, int32_t* out_idx, void* stream,
+                    bool ordered) {
   if (!pts || !workspace || !out_idx || P <= 0 || K <= 0 || K > P || start < 0 || start >= P || ld < 3)
     return GVF_ERR_INVALID;
   auto launch_smem = [&](auto kern, int per) {
@@ -551,13 +645,15 @@ extern "C" GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start
   };
   bool ok = true;
   // MEASURED (tools/fps_bench.py, 16384 -> 4096): cluster kernel 7.2 - 9.2 ms, single-CTA shared-memory kernel 5.66 ms,
-  // its second generation (x in registers, packed f32x2 arithmetic) 5.02 ms = the default --
+  // its second generation (x in registers, packed f32x2 arithmetic) 5.02 ms, the exactly pruned third generation = the default --
   // the cluster barrier costs more per sample (~1.7 us) than the shared-memory re-read it removes, so the
   // single-CTA kernels stay the default; GVF_FPS=cluster selects the cluster kernel (identical indices).
   static int fps_mode = -1;
   if (fps_mode < 0) {
     const char* e = getenv("GVF_FPS");
-    fps_mode = (e && e[0] == 'c') ? 0 : (e && e[0] == 's') ? 1 : 2;     // "cluster" / "smem" (generation 1) / default
+    // "cluster" / "smem" (generation 1) / "pruned" (generation 3 for every call) / default: generation 2, and generation 3
+    // through gvf_fps_ordered
+    fps_mode = (e && e[0] == 'c') ? 0 : (e && e[0] == 's') ? 1 : (e && e[0] == 'p') ? 3 : 2;
   }
   auto launch_cluster = [&](auto kern) {
     cudaLaunchConfig_t cfg = {};
@@ -578,6 +674,12 @@ extern "C" GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start
     const int per = (P + gvf::kFpsCluster * gvf::kFpsThreads - 1) / (gvf::kFpsCluster * gvf::kFpsThreads);
     ok = per <= 1 ? launch_cluster(gvf::fps_cluster_kernel<1>) : per <= 2 ? launch_cluster(gvf::fps_cluster_kernel<2>)
                                                                            : launch_cluster(gvf::fps_cluster_kernel<4>);
+    return (ok && cudaGetLastError() == cudaSuccess) ? GVF_OK : GVF_ERR_CUDA;
+  }
+  if ((fps_mode == 3 || (fps_mode == 2 && ordered)) && P <= 16384) {
+    if (P <= 4096) ok = launch_smem(gvf::fps_pruned_kernel<4>, 4);
+    else if (P <= 8192) ok = launch_smem(gvf::fps_pruned_kernel<8>, 8);
+    else ok = launch_smem(gvf::fps_pruned_kernel<16>, 16);
     return (ok && cudaGetLastError() == cudaSuccess) ? GVF_OK : GVF_ERR_CUDA;
   }
   if (fps_mode == 2 && P <= 16384) {

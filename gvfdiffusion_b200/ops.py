@@ -354,15 +354,16 @@ class GaussianTensorFn(torch.autograd.Function):
         return (None, *outs)
 
 
-def fps(points, K, start=0):
-    """points [P, >=3] fp32 (xyz first) -> int32 indices [K] of a farthest point sample."""
+def fps(points, K, start=0, spatially_ordered=False):
+    """points [P, >=3] fp32 (xyz first) -> int32 indices [K] of a farthest point sample.  spatially_ordered: the rows are
+    voxel-major in lexicographic voxel order (what to_representation emits) -> the exactly pruned kernel, same indices."""
     _req(points, F32, "points")
     P = points.shape[0]
     assert points.stride(1) == 1
     ws = torch.empty(P, dtype=F32, device=points.device)
     idx = torch.empty(K, dtype=torch.int32, device=points.device)
-    check(_lib.lib().gvf_fps(ptr(points), points.stride(0), P, K, start, ptr(ws), ptr(idx), current_stream()),
-          "gvf_fps")
+    fn = _lib.lib().gvf_fps_ordered if spatially_ordered else _lib.lib().gvf_fps
+    check(fn(ptr(points), points.stride(0), P, K, start, ptr(ws), ptr(idx), current_stream()), "gvf_fps")
     return idx
 
 

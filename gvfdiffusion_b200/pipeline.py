@@ -27,7 +27,7 @@ def sample_gs(static_gs_list, num_latents):
     out = []
     for g in static_gs_list:
         g = g.contiguous()
-        idx = ops.fps(g, min(num_latents, g.shape[0])).long()
+        idx = ops.fps(g, min(num_latents, g.shape[0]), spatially_ordered=True).long()    # rows come from to_representation
         out.append(g.index_select(0, idx))
     return torch.stack(out, 0)
 
@@ -64,7 +64,7 @@ class GVFPipeline:
         # farthest point sampling is greedy: from one start point the K-sample is a prefix of any longer
         # sample, so the two sample_gs calls of the reference share one run
         n1, n2 = min(self.num_latents, P), min(self.num_static, P)
-        idx = ops.fps(o.static_gs, max(n1, n2)).long()
+        idx = ops.fps(o.static_gs, max(n1, n2), spatially_ordered=True).long()      # voxel-major rows: exact pruning
         i512, i4096 = idx[:n1], idx[:n2]
         o.fps512 = o.static_gs.index_select(0, i512)
         o.fps4096 = o.static_gs.index_select(0, i4096)

@@ -164,6 +164,13 @@ GVF_API int gvf_gaussian_tensor_bwd(const gvf_raster_params* prm, int P, const f
  * (starts at `start`, ties -> lowest index).  workspace: P floats.  out_idx: K int32. */
 GVF_API int gvf_fps(const float* pts, int ld, int P, int K, int start, float* workspace,
                     int32_t* out_idx, void* stream);
+/* The same indices, bit for bit, through the exactly pruned kernel: for clouds whose rows are spatially ordered (the
+ * voxel-major Gaussians of lexicographically ordered voxels that sample_gs receives from to_representation).  Threads skip
+ * runs of consecutive points whose bounding box is farther from the new sample than their largest running minimum; the
+ * bound uses the distance's own rounded operations, so skipping is exact in floating point.  Any row order is correct;
+ * unordered clouds are faster through gvf_fps. */
+GVF_API int gvf_fps_ordered(const float* pts, int ld, int P, int K, int start, float* workspace,
+                            int32_t* out_idx, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * 2. Dense attention -- replaces flash_attn.flash_attn_{func,kvpacked_func,qkvpacked_func}

@@ -107,6 +107,33 @@ def test_gaussian_tensor_and_fps():
     assert np.array_equal(ops.fps(gt, 50).cpu().numpy(), idx[:50])
 
 
+def _fps_numpy(pn, K, start=0):
+    mind = np.full(pn.shape[0], 3.0e38, np.float32)
+    cur, ref_idx = start, [start]
+    for _ in range(1, K):
+        d = pn - pn[cur]
+        dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        mind = np.minimum(mind, dist.astype(np.float32))
+        cur = int(np.argmax(mind))
+        ref_idx.append(cur)
+    return np.array(ref_idx, np.int32)
+
+
+@pytest.mark.parametrize("order", ["voxel-major", "shuffled"])
+def test_fps_pruned_kernel_at_the_benchmark_size(order):
+    """The exactly pruned kernel (default) on the benchmark object's own cloud -- 16384 Gaussians of 2048 shell voxels,
+    4096 samples -- in its voxel-major row order (where nearly every sub-bucket is skipped) and shuffled (where little is):
+    the same indices as brute force, bit for bit, both times."""
+    from gvfdiffusion_b200 import ops, synthetic
+    xyz = synthetic.canonical_gaussians()["_xyz"]
+    if order == "shuffled":
+        xyz = xyz[torch.randperm(xyz.shape[0], generator=torch.Generator().manual_seed(2))]
+    xyz = xyz.contiguous()
+    idx = ops.fps(xyz.cuda(), 4096, spatially_ordered=True).cpu().numpy()
+    assert np.array_equal(idx, _fps_numpy(xyz.numpy(), 4096))
+    assert np.array_equal(idx, ops.fps(xyz.cuda(), 4096).cpu().numpy())
+
+
 @pytest.mark.parametrize("P", [1000, 5000, 16384, 20000])
 def test_fps_sizes(P):
     """every kernel variant of gvf_fps (smem-resident 4/8/16 points per thread, global fallback),
@@ -117,6 +144,7 @@ def test_fps_sizes(P):
     p[P // 2:P // 2 + 100] = p[:100]
     K = 48
     idx = ops.fps(p.cuda(), K, start=7).cpu().numpy()
+    assert np.array_equal(idx, ops.fps(p.cuda(), K, start=7, spatially_ordered=True).cpu().numpy())
     pn = p.numpy()
     mind = np.full(P, 3.0e38, np.float32)
     cur, ref_idx = 7, [7]
