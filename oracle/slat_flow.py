@@ -193,3 +193,41 @@ def flow_euler_sample(model_fn, noise, steps, rescale_t=1.0, sigma_min=1e-5):
         v = model_fn(x, 1000.0 * t)
         x = x - (t - tp) * v
     return x
+
+
+def patchify(x, ps):
+    """trellis/modules/spatial.py:16-31 for [N, C, D, D, D]."""
+    N, C, D = x.shape[0], x.shape[1], x.shape[2] // ps
+    x = x.reshape(N, C, D, ps, D, ps, D, ps).permute(0, 1, 3, 5, 7, 2, 4, 6)
+    return x.reshape(N, C * ps ** 3, D, D, D)
+
+
+def unpatchify(x, ps):
+    """trellis/modules/spatial.py:34-48."""
+    N, C, D = x.shape[0], x.shape[1] // ps ** 3, x.shape[2]
+    x = x.reshape(N, C, ps, ps, ps, D, D, D).permute(0, 1, 5, 2, 6, 3, 7, 4)
+    return x.reshape(N, C, D * ps, D * ps, D * ps)
+
+
+def sparse_structure_flow_forward(sd, cfg, x, t, cond):
+    """SparseStructureFlowModel.forward (trellis/models/sparse_structure_flow.py:174-200): the dense DiT over the occupancy
+    latent x [B, C, R, R, R] -- patchify, input_layer + APE of the patch grid, ModulatedTransformerCrossBlocks
+    (trellis/modules/transformer/modulated.py:132-150, the same arithmetic as the sparse blocks above on one full sequence per
+    batch entry), layer_norm, out_layer, unpatchify.  Pinned by tests/golden/sparse_structure_flow_tiny.pt."""
+    sd = {k: v.float() for k, v in sd.items()}
+    ps, C, B = cfg["patch_size"], cfg["model_channels"], x.shape[0]
+    heads = cfg.get("num_heads") or C // cfg.get("num_head_channels", 64)
+    h = patchify(x.float(), ps)
+    R = h.shape[2]
+    h = h.reshape(B, h.shape[1], -1).permute(0, 2, 1)
+    h = F.linear(h, sd["input_layer.weight"], sd["input_layer.bias"])
+    grid = torch.stack(torch.meshgrid(*[torch.arange(R)] * 3, indexing="ij"), dim=-1).reshape(-1, 3)
+    h = (h + ape(grid, C)[None]).reshape(B * R ** 3, C)
+    emb = t_embedder(sd, t)
+    layout = [slice(b * R ** 3, (b + 1) * R ** 3) for b in range(B)]
+    for i in range(cfg["num_blocks"]):
+        h = cross_block(sd, f"blocks.{i}.", h, layout, emb, cond.float(), heads, cfg.get("qk_rms_norm", False),
+                        cfg.get("qk_rms_norm_cross", False))
+    h = F.linear(F.layer_norm(h, h.shape[-1:]), sd["out_layer.weight"], sd["out_layer.bias"])
+    h = h.reshape(B, R ** 3, -1).permute(0, 2, 1).reshape(B, -1, R, R, R)
+    return unpatchify(h, ps).contiguous()

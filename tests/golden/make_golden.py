@@ -599,6 +599,44 @@ def gen_slat_decoder_gs():
             sys.modules.pop("flash_attn", None)
 
 
+def gen_sparse_structure_flow():
+    """The reference's own SparseStructureFlowModel (trellis/models/sparse_structure_flow.py:55-200: the dense DiT over the
+    16^3 occupancy latent that precedes the structured-latent stage) on the CPU in fp32 (attention backend sdpa), for patch
+    sizes 1 (shipped) and 2."""
+    import types
+    pkg = types.ModuleType("trellis")
+    pkg.__path__ = [os.path.join(_ref_import.REF, "trellis")]
+    sys.modules["trellis"] = pkg
+    try:
+        from trellis.models.sparse_structure_flow import SparseStructureFlowModel
+        out = {}
+        for name, ps in (("p1", 1), ("p2", 2)):
+            cfg = dict(resolution=8, in_channels=8, model_channels=128, cond_channels=128, out_channels=8, num_blocks=2,
+                       num_head_channels=64, mlp_ratio=4, patch_size=ps, pe_mode="ape", use_fp16=False, share_mod=False,
+                       qk_rms_norm=True, qk_rms_norm_cross=False)
+            torch.manual_seed(3 + ps)
+            m = SparseStructureFlowModel(**cfg).eval()
+            rerandomise_zero_layers(m)
+            g0 = torch.Generator().manual_seed(21)
+            for n_, p_ in m.named_parameters():
+                if n_.endswith("gamma") or n_.endswith(".bias") or ("norm" in n_ and n_.endswith(".weight")):
+                    p_.data += 0.1 * torch.randn(p_.shape, generator=g0)
+            for p_ in m.parameters():
+                p_.data = p_.data.half().float()
+            g = torch.Generator().manual_seed(8)
+            x = torch.randn(2, 8, 8, 8, 8, generator=g)
+            cond = torch.randn(2, 20, 128, generator=g)
+            t = torch.tensor([700.0, 55.0])
+            with torch.no_grad():
+                y = m(x, t, cond)
+            out[name] = {"cfg": cfg, "state_dict": {k: v.half() for k, v in m.state_dict().items() if k != "pos_emb"},
+                         "pos_emb": m.pos_emb.clone(), "x": x, "cond": cond, "t": t, "out": y}
+        return out
+    finally:
+        for k in [k for k in sys.modules if k == "trellis" or k.startswith("trellis.")]:
+            sys.modules.pop(k)
+
+
 def _bruteforce_knn_points(p1, p2, lengths1=None, lengths2=None, K=1):
     """Stand-in for pytorch3d.ops.knn_points (absent here) with its documented semantics: exact squared
     distances ((dx*dx + dy*dy) + dz*dz in fp32), ascending, ties -> lowest index, padded rows zero."""
@@ -940,6 +978,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "slat_decoder_gs":
         torch.save(gen_slat_decoder_gs(), os.path.join(HERE, "slat_decoder_gs_tiny.pt"))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "sparse_structure_flow":
+        torch.save(gen_sparse_structure_flow(), os.path.join(HERE, "sparse_structure_flow_tiny.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "slat_flow":
         torch.save(gen_slat_flow(), os.path.join(HERE, "slat_flow_tiny.pt"))
         return
@@ -967,6 +1008,7 @@ def main():
     torch.save(gen_flow_euler(), os.path.join(HERE, "flow_euler.pt"))
     torch.save(gen_slat_flow(), os.path.join(HERE, "slat_flow_tiny.pt"))
     torch.save(gen_slat_decoder_gs(), os.path.join(HERE, "slat_decoder_gs_tiny.pt"))
+    torch.save(gen_sparse_structure_flow(), os.path.join(HERE, "sparse_structure_flow_tiny.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))

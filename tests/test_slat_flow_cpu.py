@@ -87,3 +87,17 @@ def test_gaussian_decoder_oracle_matches_reference_class():
         for name, want in rep.items():
             assert float((raw[name][off:off + n] - want).abs().max()) < 1e-6, (b, name)
         off += n
+
+
+# ---------------------------------------------------------------------------------------------- SparseStructureFlowModel
+GS = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sparse_structure_flow_tiny.pt"), weights_only=False)
+
+
+def test_sparse_structure_flow_oracle_matches_reference_class():
+    for name, c in GS.items():
+        out = O.sparse_structure_flow_forward(c["state_dict"], c["cfg"], c["x"], c["t"], c["cond"])
+        assert out.shape == c["out"].shape
+        assert float((out - c["out"]).norm() / c["out"].norm()) < 1e-5, name
+        # patchify / unpatchify are inverse permutations
+        ps = c["cfg"]["patch_size"]
+        assert torch.equal(O.unpatchify(O.patchify(c["x"], ps), ps), c["x"])

@@ -279,3 +279,50 @@ def test_pipeline_sample_slat_and_decode_slat():
     assert all(torch.isfinite(getattr(g_, n)).all() for g_ in out for n in ("_xyz", "_scaling", "_rotation", "_opacity"))
     with pytest.raises(NotImplementedError):
         pipe.decode_slat(slat, ["mesh"])
+
+
+@pytest.mark.parametrize("case", ["p1", "p2"])
+def test_sparse_structure_flow_matches_reference_class(case):
+    """SparseStructureFlowModel (sparse_structure_flow.py:55-200) against the reference's own class (CPU fp32), patch sizes
+    1 (shipped) and 2; eager and graph replay give the same bits."""
+    from gvfdiffusion_b200.trellis.models import SparseStructureFlowModel
+    GS = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sparse_structure_flow_tiny.pt"), weights_only=False)
+    c = GS[case]
+    m = SparseStructureFlowModel(**c["cfg"], device=DEV).load_state_dict(c["state_dict"])
+    assert float((m.pos_emb.cpu() - c["pos_emb"]).abs().max()) < 1e-5
+    x, t, cond = c["x"].to(DEV), c["t"].to(DEV), c["cond"].to(DEV)
+    out = m(x, t, cond)
+    err = _rel(out, c["out"])
+    print(f"\nsparse-structure flow ({case}) vs the reference's own class (fp32): rel L2 {err:.2e}")
+    assert out.shape == c["out"].shape and err < 5e-3, err
+    m.use_graphs = True
+    assert torch.equal(m(x, t, cond), out) and torch.equal(m(x, t, cond), out)
+
+
+def test_pipeline_sample_sparse_structure_and_run_from_cond():
+    """trellis_image_to_3d.py:165-195,279-284: occupancy-latent sampling over SparseStructureFlowModel, a caller-supplied
+    occupancy decoder (here: nearest upsampling of one latent channel), argwhere -> coords -> sample_slat -> decode_slat."""
+    from gvfdiffusion_b200.trellis.models import SLatGaussianDecoder, SparseStructureFlowModel
+    from gvfdiffusion_b200.trellis.pipelines.trellis_image_to_3d import TrellisImageTo3DPipeline
+    here = os.path.dirname(os.path.abspath(__file__))
+    GS = torch.load(os.path.join(here, "golden", "sparse_structure_flow_tiny.pt"), weights_only=False)["p1"]
+    GD = torch.load(os.path.join(here, "golden", "slat_decoder_gs_tiny.pt"), weights_only=False)
+    ss = SparseStructureFlowModel(**GS["cfg"], device=DEV).load_state_dict(GS["state_dict"])
+    flow = _model(G["cfg"], G["state_dict"])
+    dec = SLatGaussianDecoder(**GD["cfg"], device=DEV).load_state_dict(GD["state_dict"])
+    occ = lambda z: torch.nn.functional.interpolate(z[:, :1], scale_factor=2, mode="nearest") - 0.8      # 8^3 -> 16^3 logits
+    euler = {"name": "FlowEulerGuidanceIntervalSampler", "args": {"sigma_min": 1e-5},
+             "params": {"steps": 4, "cfg_strength": 5.0, "cfg_interval": [0.5, 1.0], "rescale_t": 3.0}}
+    args = {"sparse_structure_sampler": euler, "slat_sampler": euler, "slat_normalization": {"mean": [0.0] * 8, "std": [1.0] * 8}}
+    pipe = TrellisImageTo3DPipeline.from_args(args, {"sparse_structure_flow_model": ss, "sparse_structure_decoder": occ,
+                                                     "slat_flow_model": flow, "slat_decoder_gs": dec}, device=DEV)
+    cond = {"cond": G["cond"].to(DEV), "neg_cond": torch.zeros_like(G["cond"]).to(DEV)}
+    torch.manual_seed(0)
+    coords = pipe.sample_sparse_structure(cond, num_samples=2)
+    assert coords.dtype == torch.int32 and coords.shape[1] == 4 and coords.shape[0] > 0
+    assert int(coords[:, 0].max()) <= 1 and int(coords[:, 1:].max()) < 16
+    assert torch.equal(coords[:, 0], coords[:, 0].sort().values)            # rows grouped by batch entry (argwhere order)
+    torch.manual_seed(0)
+    out = pipe.run_from_cond(cond, num_samples=2)["gaussian"]
+    assert len(out) == int(coords[:, 0].max()) + 1
+    assert sum(g_._xyz.shape[0] for g_ in out) == coords.shape[0] * 4
