@@ -282,15 +282,18 @@ __global__ void __launch_bounds__(256) mod_gemv_kernel(const __half* __restrict_
 // used for input_layer (16->512, + APE; reference model/dit.py:457,470-472), static_cond_proj
 // (14->512, :465), VAE proj (16->768, autoencoder.py:585) and gs_embedding (14->768, :389).
 // x fp32 (rounded to fp16 on load like autocast does), W fp16 [N,K], out fp32 or fp16.
-template <typename TOut>
+// RPB rows per block: a thread loads its weight row once per block, so 8 rows (the first form) re-read the 16 KB of weights
+// 1536 times at M = 12288 with 32 B-strided loads and ran 48 us for a 25 MB pass; 64 rows per block for large M make the
+// pass bandwidth-shaped.  Per-output arithmetic (k ascending, then bias, rounding, + add) is unchanged: identical bits.
+template <typename TOut, int RPB>
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, int ldx,
                                                            const __half* __restrict__ W,
                                                            const float* __restrict__ bias, int M, int N,
                                                            int K, const float* __restrict__ add,
                                                            int add_rows, TOut* __restrict__ out) {
-  __shared__ float xs[8][32];
-  const int row0 = blockIdx.y * 8;
-  for (int i = threadIdx.x; i < 8 * K; i += 256) {
+  __shared__ float xs[RPB][32];
+  const int row0 = blockIdx.y * RPB;
+  for (int i = threadIdx.x; i < RPB * K; i += 256) {
     const int r = i / K, k = i - r * K;
     xs[r][k] = (row0 + r < M) ? r16f(x[(size_t)(row0 + r) * ldx + k]) : 0.f;
   }
@@ -300,11 +303,13 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   float wv[32];
   for (int k = 0; k < K; ++k) wv[k] = __half2float(W[(size_t)n * K + k]);
   const float bn = bias ? bias[n] : 0.f;
-  for (int r = 0; r < 8 && row0 + r < M; ++r) {
+  int ar = row0 % add_rows;
+  for (int r = 0; r < RPB && row0 + r < M; ++r) {
     float acc = 0.f;
     for (int k = 0; k < K; ++k) acc += xs[r][k] * wv[k];
     float y = r16f(acc + bn);
-    if (add) y += add[(size_t)((row0 + r) % add_rows) * N + n];
+    if (add) y += add[(size_t)ar * N + n];
+    if (++ar == add_rows) ar = 0;
     if constexpr (sizeof(TOut) == 4) out[(size_t)(row0 + r) * N + n] = y;
     else out[(size_t)(row0 + r) * N + n] = __float2half_rn(y);
   }
@@ -422,6 +427,10 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------
 // FinalLayer (reference model/dit.py:287-303): LN -> modulate(shift, scale) -> Linear(C -> O<=16)
 // X fp32 [M,C] -> out fp32 [M,O] (fp16-valued, as the autocast module returns).  Warp per row.
+// Four rows per warp: a weight value loaded once serves four rows (the one-row form issued 256 loads + 80 shuffles per row
+// and lane: 46 us for a 25 MB pass).  The O = 16 dot products of a row are reduced together by a transposed butterfly --
+// at offset 16 every lane keeps half of the outputs and hands the other half to its partner, and so on: 8 + 4 + 2 + 1 + 1
+// shuffles instead of 80 -- which adds the same pairs in the same order as sixteen warp_sum trees: identical bits.
 template <int C, int O>
 __global__ void __launch_bounds__(256) final_layer_kernel(const float* __restrict__ x, int M,
                                                           const __half* __restrict__ shift,
@@ -429,32 +438,63 @@ __global__ void __launch_bounds__(256) final_layer_kernel(const float* __restric
                                                           int rows_per_batch, const __half* __restrict__ W,
                                                           const float* __restrict__ bias,
                                                           float* __restrict__ out) {
-  constexpr int PER = C / 32;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float v[PER];
-  float s = 0.f;
+  static_assert(O == 16, "the transposed reduction is written for 16 outputs");
+  constexpr int PER = C / 32, RW = 4;
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RW;
+  if (row0 >= M) return;
+  float v[RW][PER];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) { v[i] = x[(size_t)row * C + i * 32 + lane]; s += v[i]; }
-  const float mean = warp_sum(s) / C;
-  float q = 0.f;
+  for (int r = 0; r < RW; ++r) {
+    const int row = row0 + r < M ? row0 + r : M - 1;           // tail rows: recompute the last row, not stored
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER; ++i) q += (v[i] - mean) * (v[i] - mean);
-  const float rstd = rsqrtf(warp_sum(q) / C + 1e-6f);
-  const int b = row / rows_per_batch;
+    for (int i = 0; i < PER; ++i) { v[r][i] = x[(size_t)row * C + i * 32 + lane]; s += v[r][i]; }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int c = i * 32 + lane;
-    const float y = (v[i] - mean) * rstd * (1.0f + __half2float(scale[(size_t)b * mod_stride + c])) +
-                    __half2float(shift[(size_t)b * mod_stride + c]);
-    v[i] = r16f(y);
+    for (int i = 0; i < PER; ++i) q += (v[r][i] - mean) * (v[r][i] - mean);
+    const float rstd = rsqrtf(warp_sum(q) / C + 1e-6f);
+    const int b = row / rows_per_batch;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = i * 32 + lane;
+      const float y = (v[r][i] - mean) * rstd * (1.0f + __half2float(scale[(size_t)b * mod_stride + c])) +
+                      __half2float(shift[(size_t)b * mod_stride + c]);
+      v[r][i] = r16f(y);
+    }
   }
-  for (int o = 0; o < O; ++o) {
-    float acc = 0.f;
+  float acc[RW][O];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) acc += v[i] * __half2float(W[(size_t)o * C + i * 32 + lane]);
-    acc = warp_sum(acc);
-    if (lane == 0) out[(size_t)row * O + o] = r16f(acc + bias[o]);
+  for (int r = 0; r < RW; ++r)
+#pragma unroll
+    for (int o = 0; o < O; ++o) acc[r][o] = 0.f;
+#pragma unroll
+  for (int o = 0; o < O; ++o) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float w = __half2float(W[(size_t)o * C + i * 32 + lane]);
+#pragma unroll
+      for (int r = 0; r < RW; ++r) acc[r][o] += v[r][i] * w;
+    }
+  }
+  // lane l ends with output o(l) = 8 [l & 16] + 4 [l & 8] + 2 [l & 4] + [l & 2]
+  const int o_mine = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+  const float bo = bias[o_mine];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+#pragma unroll
+    for (int off = 16, n = O; off >= 2; off >>= 1, n >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < n / 2; ++j) {
+        const float send = upper ? acc[r][j] : acc[r][j + n / 2];
+        const float keep = upper ? acc[r][j + n / 2] : acc[r][j];
+        acc[r][j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    const float tot = acc[r][0] + __shfl_xor_sync(0xffffffffu, acc[r][0], 1);
+    if (!(lane & 1) && row0 + r < M) out[(size_t)(row0 + r) * O + o_mine] = r16f(tot + bo);
   }
 }
 
@@ -659,12 +699,20 @@ GVF_API int gvf_small_linear(const float* x, int ldx, const void* W, const float
                              int K, const float* add, int add_rows, void* out, int out_is_f16,
                              void* stream) {
   if (!x || !W || !out || K > 32 || K <= 0 || M <= 0 || N <= 0) return GVF_ERR_INVALID;
-  const dim3 grid((N + 255) / 256, (M + 7) / 8);
   const int ar = add_rows > 0 ? add_rows : 1;
+  if (M >= 4096) {
+    const dim3 grid((N + 255) / 256, (M + 63) / 64);
+    if (out_is_f16)
+      small_linear_kernel<__half, 64><<<grid, 256, 0, ST(stream)>>>(x, ldx, (const __half*)W, bias, M, N, K, add, ar, (__half*)out);
+    else
+      small_linear_kernel<float, 64><<<grid, 256, 0, ST(stream)>>>(x, ldx, (const __half*)W, bias, M, N, K, add, ar, (float*)out);
+    RET();
+  }
+  const dim3 grid((N + 255) / 256, (M + 7) / 8);
   if (out_is_f16)
-    small_linear_kernel<__half><<<grid, 256, 0, ST(stream)>>>(x, ldx, (const __half*)W, bias, M, N, K, add, ar, (__half*)out);
+    small_linear_kernel<__half, 8><<<grid, 256, 0, ST(stream)>>>(x, ldx, (const __half*)W, bias, M, N, K, add, ar, (__half*)out);
   else
-    small_linear_kernel<float><<<grid, 256, 0, ST(stream)>>>(x, ldx, (const __half*)W, bias, M, N, K, add, ar, (float*)out);
+    small_linear_kernel<float, 8><<<grid, 256, 0, ST(stream)>>>(x, ldx, (const __half*)W, bias, M, N, K, add, ar, (float*)out);
   RET();
 }
 
@@ -776,7 +824,7 @@ GVF_API int gvf_dit_final_layer(const float* x, int M, int C, int O, const void*
                                 int mod_stride, int rows_per_batch, const void* W, const float* bias,
                                 float* out, void* stream) {
   if (!x || !shift || !scale || !W || !bias || !out || M <= 0 || rows_per_batch <= 0) return GVF_ERR_INVALID;
-  const dim3 grid((M + 7) / 8);
+  const dim3 grid((M + 31) / 32);
   if (C == 512 && O == 16)
     final_layer_kernel<512, 16><<<grid, 256, 0, ST(stream)>>>(x, M, (const __half*)shift, (const __half*)scale,
                                                               mod_stride, rows_per_batch, (const __half*)W, bias, out);

@@ -185,6 +185,10 @@ class DiT(nn.Module):
             tt = tt.expand(xt.shape[0]).contiguous()
         return eng.forward(xt, tt, kv_img, kv_st, pos).clone()
 
+    def precompute_modulation(self, t_inputs):
+        """Hook of DPM_Solver.sample: the model times of the whole run, known before the first NFE."""
+        self.engine().precompute_modulation(t_inputs)
+
     @torch.no_grad()
     def forward_branches(self, x, t_input, conds):
         """All guidance branches of one NFE in a single engine pass (used by DPM_Solver):

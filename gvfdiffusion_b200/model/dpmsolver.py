@@ -183,6 +183,13 @@ class DPM_Solver:
         cm = f32(f32(np.exp(ns.marginal_log_mean_coeff(t))) * f32(np.expm1(-h)))
         return ops.dpm_update(x, m0, m1, float(cx), float(cm), float(f32(1.0) / r0), 2, out)
 
+    def _announce_times(self, ts):
+        """A fixed-step run knows every model time in advance: let the model precompute what depends on time only."""
+        m = self.fn
+        inner = getattr(m, "model", None)
+        if isinstance(m, _WrappedModel) and hasattr(inner, "precompute_modulation"):
+            inner.precompute_modulation([float(m.t_input(t)) for t in ts])
+
     def sample(self, x, steps=20, t_start=None, t_end=None, order=2, skip_type="time_uniform",
                method="multistep", lower_order_final=True, denoise_to_zero=False, solver_type="dpmsolver",
                atol=0.0078, rtol=0.05, return_intermediate=False):
@@ -201,6 +208,7 @@ class DPM_Solver:
                 raise NotImplementedError("method must be 'multistep' or 'adaptive'")
             assert steps >= order
             ts = torch.linspace(t_T, t_0, steps + 1).numpy().astype(f32)          # get_time_steps :491
+            self._announce_times(ts[:-1])                                        # the model is evaluated at ts[0 .. steps - 1]
             bufs = [torch.empty_like(x) for _ in range(2)]
             xn = torch.empty_like(x)
             m_prev = [self._x0(x, ts[0], bufs[0])]

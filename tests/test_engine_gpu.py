@@ -151,3 +151,38 @@ def test_vae_decode_golden_fixture_and_full_width():
         d = v.to(DEV).decode(z.to(DEV), q.to(DEV))
     d16 = OVAE.vae_decode(sd, z, q, 12, 2, "fp16")
     assert rel(d, d16) < 1.5e-3, rel(d, d16)
+
+
+def test_precomputed_modulation_table_is_bit_identical():
+    """DiTEngine.precompute_modulation (the model times of a fixed-step DPM-Solver run are known in advance): NFEs replayed
+    with the table row copied into the workspace give the same bits as NFEs that compute the timestep MLP + adaLN GEMV
+    inside the graph; the solver announces its times, so a sampled latent is identical with the table on and off."""
+    from gvfdiffusion_b200.model import dpmsolver as DPM
+    g, m = _dit_from_golden()
+    cond = {k: g[k].to(DEV) for k in ("cond_images", "static_latent", "deformation_position_xyz")}
+    eng = m.engine()
+    x = g["x"].to(DEV)
+
+    def nfe(t):
+        return m.forward_branches(x, t, [cond]).clone()
+
+    times = [873.25, 500.0, 12.5, 999.0, 640.0, 333.0, 250.75, 100.0, 77.0, 1.0]       # > 8: two table launches
+    eng.use_premod = False
+    want = [nfe(t) for t in times]
+    eng.use_premod = True
+    m.precompute_modulation(times)
+    assert len(eng._modtab) == len(times)
+    for t, w in zip(times, want):
+        assert torch.equal(nfe(t), w), t
+    assert torch.equal(nfe(55.5), m.forward_branches(x, 55.5, [cond]))                    # a time outside the table still works
+    # whole sampler runs, table on / off
+    ns = DPM.NoiseScheduleVP("discrete", betas=torch.from_numpy(ODPM.reference_betas(1000)))
+    outs = []
+    for on in (False, True):
+        eng.use_premod = on
+        eng._modtab.clear()
+        fn = DPM.model_wrapper(m, ns, model_type="v", guidance_type="classifier-free", condition=cond,
+                               unconditional_condition=None, guidance_scale=1.0, guidance_scale2=1.0)
+        outs.append(DPM.DPM_Solver(fn, ns).sample(x, steps=6, order=2, method="multistep").clone())
+        assert (len(eng._modtab) == 6) == on
+    assert torch.equal(outs[0], outs[1])

@@ -287,6 +287,37 @@ def test_modulation_small_linear_ape_final():
     _close(ops.dit_final_layer(X, modf[:, :512], modf[:, 512:], 1024, 32, Wf, bf), ref, 2e-3, "final layer")
 
 
+def test_small_linear_and_final_layer_large_m():
+    """The 64-rows-per-block small linear and the 4-rows-per-warp final layer at the benchmark row count and at ragged
+    row counts, against torch and against the small-M code path (same per-output arithmetic: identical bits)."""
+    from gvfdiffusion_b200 import ops
+    g = _g(77)
+    for M, add_rows in ((12288, 512), (4100, 205), (4097, 4097)):
+        x = _rand((M, 16), g)
+        W = _rand((512, 16), g, 0.2).half()
+        bb = _rand((512,), g, 0.1)
+        pos = _rand((add_rows, 512), g)
+        y = ops.small_linear(x, W, bb, out_f16=False, add=pos, add_rows=add_rows)
+        ref = F.linear(x.half().float(), W.float(), bb) + pos.repeat((M + add_rows - 1) // add_rows, 1)[:M]
+        _close(y, ref, 1e-3, f"small linear M={M}")
+        # the small-M kernel on row slices that keep the add phase: identical bits
+        y_small = torch.cat([ops.small_linear(x[i:i + add_rows], W, bb, out_f16=False, add=pos, add_rows=add_rows)
+                             for i in range(0, M, add_rows)], 0) if add_rows < 4096 else None
+        if y_small is not None:
+            assert torch.equal(y, y_small)
+        y16 = ops.small_linear(x, W, bb, out_f16=True)
+        _close(y16, F.linear(x.half().float(), W.float(), bb), 2e-3, f"small linear fp16 M={M}")
+    for M, rpb in ((12288, 12288), (1003, 1003), (96, 32)):
+        X = _rand((M, 512), g)
+        nb = M // rpb
+        modf = _rand((nb, 1024), g, 0.3).half()
+        Wf, bf = _rand((16, 512), g, 0.05).half(), _rand((16,), g, 0.1)
+        ln = F.layer_norm(X, (512,), None, None, 1e-6)
+        ref = F.linear(ln * (1 + modf[:, 512:].float().repeat_interleave(rpb, 0)) + modf[:, :512].float().repeat_interleave(rpb, 0),
+                       Wf.float(), bf)
+        _close(ops.dit_final_layer(X, modf[:, :512], modf[:, 512:], 1024, rpb, Wf, bf), ref, 2e-3, f"final layer M={M}")
+
+
 def test_geglu_cast_dpm():
     from gvfdiffusion_b200 import ops
     g = _g(31)
