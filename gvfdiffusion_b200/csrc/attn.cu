@@ -1389,6 +1389,144 @@ __global__ void __launch_bounds__(HC * 32) attn_small_mma_kernel(const __half* _
   }
 }
 
+// Pipelined form of the kernel above (the DiT's temporal attention: 512 tokens x 16 heads, sequences of 24, 50 MB per
+// launch): a CTA walks over several sequences with two shared-memory buffers, the cp.async loads of sequence i + 1 issued
+// before sequence i is computed, the grid sized so that every CTA gets the same number of sequences.  Identical bits.
+// Measured SLOWER than one sequence per CTA (see the launch site) and kept opt-in only.
+template <int HC>
+__global__ void __launch_bounds__(HC * 32, 2) attn_small_mma_pipe_kernel(const __half* __restrict__ q,
+                                                                        const __half* __restrict__ k,
+                                                                        const __half* __restrict__ v, __half* __restrict__ o,
+                                                                        int L, int NB, long long sb, long long sl,
+                                                                        long long osb, long long osl, float scale_log2e) {
+  extern __shared__ uint4 sm4_all[];                // 2 x [HC][3 (q,k,v)][32 rows][4 chunks of 16 B]
+  constexpr int BUF = HC * 3 * 32 * 4;              // uint4 per buffer
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hb = blockIdx.x * HC;
+  pdl_wait();
+  auto slot = [](int hs, int ts, int row, int chunk) { return ((hs * 3 + ts) * 32 + row) * 4 + (chunk ^ ((row >> 1) & 3)); };
+  const int per_t = L * HC * 4;
+  auto stage = [&](long long nb, int b) {
+    const uint32_t sbase = smem_u32(sm4_all + b * BUF);
+    for (int idx = tid; idx < 3 * per_t; idx += HC * 32) {
+      const int ts = idx / per_t, r0 = idx - ts * per_t;
+      const int t = r0 / (HC * 4), r1 = r0 - t * (HC * 4);
+      const int hs = r1 >> 2, c = r1 & 3;
+      const __half* src = (ts == 0 ? q : ts == 1 ? k : v) + nb * sb + (long long)t * sl + (hb + hs) * 32 + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + slot(hs, ts, t, c) * 16), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // padding rows of both buffers: zero once (cp.async only ever writes rows < L; parked outputs only touch q slots)
+  for (int idx = tid; idx < 2 * 3 * (32 - L) * HC * 4; idx += HC * 32) {
+    const int b = idx / (3 * (32 - L) * HC * 4), i2 = idx - b * (3 * (32 - L) * HC * 4);
+    const int c = i2 & 3, hs = (i2 >> 2) % HC, r = (i2 >> 2) / HC;
+    const int ts = r / (32 - L), t = L + r - ts * (32 - L);
+    sm4_all[b * BUF + slot(hs, ts, t, c)] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  long long nb = blockIdx.y;
+  if (nb < NB) stage(nb, 0);
+  const int hs = warp, g = lane >> 2, tg = lane & 3;
+  const int n_mt = (L + 15) >> 4;
+  for (int it = 0; nb < NB; nb += gridDim.y, ++it) {
+    const int b = it & 1;
+    uint4* sm4 = sm4_all + b * BUF;
+    const uint32_t sbase = smem_u32(sm4);
+    const long long nxt = nb + gridDim.y;
+    if (nxt < NB) {
+      stage(nxt, b ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    for (int mt = 0; mt < n_mt; ++mt) {
+      uint32_t qa[2][4];
+  #pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        ldsm_x4(qa[ks], sbase + slot(hs, 0, 16 * mt + (lane & 15), 2 * ks + (lane >> 4)) * 16);
+      float sc[4][4];
+  #pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t kb[4];
+        ldsm_x4(kb, sbase + slot(hs, 1, 8 * nt + (lane & 7), lane >> 3) * 16);
+  #pragma unroll
+        for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+        mma_16816(sc[nt], qa[0], kb[0], kb[1]);
+        mma_16816(sc[nt], qa[1], kb[2], kb[3]);
+      }
+      // rows g (e = 0,1) and g + 8 (e = 2,3) of this 16-row tile; columns 8 nt + 2 tg + (e & 1)
+      float mx[2] = {-INFINITY, -INFINITY};
+  #pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+  #pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = 8 * nt + 2 * tg + (e & 1);
+          sc[nt][e] = (col < L) ? sc[nt][e] * scale_log2e : -INFINITY;
+          mx[e >> 1] = fmaxf(mx[e >> 1], sc[nt][e]);
+        }
+  #pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      }
+      float l[2] = {0.f, 0.f};
+      uint32_t pa[2][4];
+  #pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float p[4];
+  #pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          p[e] = fast_exp2(sc[nt][e] - mx[e >> 1]);
+          l[e >> 1] += p[e];
+        }
+        const __half2 lo = __floats2half2_rn(p[0], p[1]), hi = __floats2half2_rn(p[2], p[3]);
+        pa[nt >> 1][(nt & 1) * 2] = *reinterpret_cast<const uint32_t*>(&lo);        // a0 / a2: row g
+        pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);    // a1 / a3: row g + 8
+      }
+  #pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+      }
+      float oc[4][4];
+  #pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+  #pragma unroll
+        for (int e = 0; e < 4; ++e) oc[nt][e] = 0.f;
+  #pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+  #pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t vb[4];
+          ldsm_x4_t(vb, sbase + slot(hs, 2, 16 * ks + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * c2 + (lane >> 4)) * 16);
+          mma_16816(oc[2 * c2], pa[ks], vb[0], vb[1]);
+          mma_16816(oc[2 * c2 + 1], pa[ks], vb[2], vb[3]);
+        }
+      // park the output rows in this head's own q slot (its fragments are already in registers)
+      __syncwarp();
+      const float inv[2] = {1.0f / l[0], 1.0f / l[1]};
+      __half* sq = reinterpret_cast<__half*>(sm4);
+  #pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+  #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = 16 * mt + g + 8 * r;
+          *reinterpret_cast<__half2*>(sq + slot(hs, 0, row, nt) * 8 + 2 * tg) =
+              __floats2half2_rn(oc[nt][2 * r] * inv[r], oc[nt][2 * r + 1] * inv[r]);
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < per_t; idx += HC * 32) {
+      const int t = idx / (HC * 4), r1 = idx - t * (HC * 4);
+      const int h2 = r1 >> 2, c = r1 & 3;
+      *reinterpret_cast<uint4*>(o + nb * osb + (long long)t * osl + (hb + h2) * 32 + c * 8) = sm4[slot(h2, 0, t, c)];
+    }
+    __syncthreads();                                // the buffer is refilled by the prefetch of the next iteration
+  }
+  pdl_launch_dependents();
+}
+
 template <int D, int POLY>
 static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnArgs& a,
                        int Nb, cudaStream_t st) {
@@ -1874,6 +2012,30 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
         if (cudaFuncSetAttribute(attn_small_mma_kernel<HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
             cudaSuccess) return GVF_ERR_CUDA;
         configured_mma = true;
+      }
+      if ((g_attn_dbg & 0x10000) && Nb >= 64) {
+        // pipelined persistent form (opt-in, gvf_attn_set_debug(0x10000)): two buffers per CTA, two CTAs per SM, the same
+        // number of sequences for every CTA.  MEASURED (tools/temporal_bench.py, cold L2): 22.5 us against 20.5 us for the
+        // one-sequence-per-CTA kernel below, 22.5 against 18.5 us inside the NFE -- four independent 49 KB CTAs per SM
+        // already overlap each other's loads and compute better than two double-buffered 98 KB ones.
+        static bool configured_pipe = false;
+        static int num_sms = 0;
+        if (!configured_pipe) {
+          if (cudaFuncSetAttribute(attn_small_mma_pipe_kernel<HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SMEM) !=
+              cudaSuccess) return GVF_ERR_CUDA;
+          int dev = 0;
+          cudaGetDevice(&dev);
+          cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+          configured_pipe = true;
+        }
+        const int gx = H / HC;
+        const int cap = (2 * num_sms) / gx > 0 ? (2 * num_sms) / gx : 1;
+        const int per = (Nb + cap - 1) / cap;
+        const int gy = (Nb + per - 1) / per;
+        return launch_pdl(attn_small_mma_pipe_kernel<HC>, dim3(gx, gy), dim3(HC * 32), 2 * SMEM, st, (const __half*)q,
+                          (const __half*)k, (const __half*)v, (__half*)o, Lq, Nb, (long long)q_strides[0],
+                          (long long)q_strides[1], (long long)o_strides[0], (long long)o_strides[1],
+                          scale * 1.4426950408889634f) == cudaSuccess ? GVF_OK : GVF_ERR_CUDA;
       }
       return launch_pdl(attn_small_mma_kernel<HC>, dim3(H / HC, Nb), dim3(HC * 32), SMEM, st, (const __half*)q,
                         (const __half*)k, (const __half*)v, (__half*)o, Lq, (long long)q_strides[0],
