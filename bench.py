@@ -569,6 +569,8 @@ def main():
         "config": {"workload": WORKLOAD, "objects_per_step": world, "nfe": NFE, "guidance": "1.0/1.0 (1 branch)",
                    "l2": "inputs larger than L2 (808 MB hoisted image K/V + 1.2 GB activations per step; no flush)",
                    "num_rendered": Rn,
+                   "modulation": "timestep MLP + adaLN vectors of the run's 32 model times computed once PER OBJECT inside the "
+                                 "timed region (4 batched launch pairs), not once per NFE; nothing is carried between objects",
                    "object_prefetch": ("sample_gs (FPS) of object k+1 on a side stream during the sampling of object k; "
                                        "one prepare_object per step" if prefetch else "off")},
         "clocks": sampler.summary(),
@@ -692,10 +694,11 @@ def ncu_traffic(kernel_prefix):
 def launch_estimate():
     """Kernel launches of ours per object, counted from the engine structure and checked against the committed
     ncu launch list (profiles/r01_nfe_launch_list.csv: 471 launches for 2 NFE incl. 4 torch copies, 117 for
-    decode + render): per NFE 2 (modulation) + 1 (input) + 12 blocks x 19 (5 LayerNorm, 2 qkv, 4 attention,
-    4 out-proj, 2 q-proj, fc1, fc2) + 1 (final) + 2 (DPM)."""
-    per_nfe = 2 + 1 + 12 * 19 + 1 + 2
-    hoist = 2 + 12 + 1 + 12 + 1 + 3
+    decode + render): per NFE 1 (input) + 12 blocks x 19 (5 LayerNorm, 2 qkv, 4 attention, 4 out-proj, 2 q-proj,
+    fc1, fc2) + 1 (final) + 2 (DPM); the modulation vectors of the 32 model times are 4 batched launch pairs per object
+    (they were 2 launches per NFE until the table of dit_engine.precompute_modulation)."""
+    per_nfe = 1 + 12 * 19 + 1 + 2
+    hoist = 2 + 12 + 1 + 12 + 1 + 3 + 2 * ((NFE + 7) // 8)
     decode_render = 112 + 5
     return NFE * per_nfe + hoist + decode_render
 
