@@ -116,6 +116,7 @@ _SIGS = {
     "gvf_set_pdl": (None, [C.c_int]),
     "gvf_small_linear": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "gvf_ln_mod_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "gvf_ln_set_two_rows": (None, [C.c_int]),
     "gvf_ln_mod_act_f16": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "gvf_sparse_pool_mean_f16": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "gvf_gather_concat_f16": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),

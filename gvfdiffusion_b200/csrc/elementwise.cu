@@ -119,6 +119,82 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const TIn* __restrict__ x, 
   }
 }
 
+// Two rows per warp IN FLIGHT (the vector path of ln_mod_kernel, same per-row arithmetic: identical bits): a warp issues the
+// loads of both of its rows before it reduces either, so that 6144 warps cover the DiT's 12288 rows in one pass instead of
+// 30 % of 9472 warps walking a second row.  An experiment that LOST its A/B (see g_ln_two_rows below); opt-in only.
+template <typename TIn, int C>
+__global__ void __launch_bounds__(256) ln_mod2_kernel(const TIn* __restrict__ x, __half* __restrict__ out, int M, float eps,
+                                                      const float* __restrict__ w, const float* __restrict__ bvec,
+                                                      const __half* __restrict__ shift, const __half* __restrict__ scale,
+                                                      int mod_stride, int rows_per_batch) {
+  constexpr int PER = C / 32, RPW = 2;
+  const int lane = threadIdx.x & 31;
+  tc::pdl_wait();
+  for (int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW; row0 < M; row0 += gridDim.x * 8 * RPW) {
+    float v[RPW][PER];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int row = row0 + r < M ? row0 + r : M - 1;
+      const TIn* xr = x + (size_t)row * C;
+#pragma unroll
+      for (int i = 0; i < PER / 4; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if constexpr (sizeof(TIn) == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(xr + c);
+          v[r][i * 4] = t.x; v[r][i * 4 + 1] = t.y; v[r][i * 4 + 2] = t.z; v[r][i * 4 + 3] = t.w;
+        } else {
+          const uint2 t = *reinterpret_cast<const uint2*>(xr + c);
+          const __half2 a = *reinterpret_cast<const __half2*>(&t.x), b2 = *reinterpret_cast<const __half2*>(&t.y);
+          v[r][i * 4] = __low2float(a); v[r][i * 4 + 1] = __high2float(a);
+          v[r][i * 4 + 2] = __low2float(b2); v[r][i * 4 + 3] = __high2float(b2);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int row = row0 + r;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) s += v[r][i];
+      const float mean = warp_sum(s) * (1.0f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { const float d = v[r][i] - mean; q += d * d; }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+      if (row >= M) continue;
+      const int b = (shift || scale) ? row / rows_per_batch : 0;
+      __half* orow = out + (size_t)row * C;
+#pragma unroll
+      for (int i = 0; i < PER / 4; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        __align__(8) __half h[4];
+        float wv[4] = {1.f, 1.f, 1.f, 1.f}, bv[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (w) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c)), b4 = __ldg(reinterpret_cast<const float4*>(bvec + c));
+          wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+          bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w;
+        }
+        if (scale) {
+          const uint2 s2 = *reinterpret_cast<const uint2*>(scale + (size_t)b * mod_stride + c);
+          const uint2 h2 = *reinterpret_cast<const uint2*>(shift + (size_t)b * mod_stride + c);
+          const __half* sp = reinterpret_cast<const __half*>(&s2);
+          const __half* hp = reinterpret_cast<const __half*>(&h2);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { sc[t] = __half2float(sp[t]); sh[t] = __half2float(hp[t]); }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float y = (v[r][i * 4 + t] - mean) * rstd;
+          if (w) y = y * wv[t] + bv[t];
+          if (scale) y = y * (1.0f + sc[t]) + sh[t];
+          h[t] = __float2half_rn(y);
+        }
+        *reinterpret_cast<uint2*>(orow + c) = *reinterpret_cast<uint2*>(h);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // MultiHeadRMSNorm on q and k in place (reference model/attention/modules.py:8-15,122-125):
 // x <- fp16( x.float() / max(||x||, 1e-12) * gamma[h] * sqrt(d) ).  buf rows of `ld` halfs;
@@ -605,6 +681,10 @@ using namespace gvf;
 
 extern "C" {
 
+// MEASURED (tools/ln_bench.py, 50 launches per graph): one row per warp 6.52 us (5.8 TB/s) at 12288 x 512, two rows in
+// flight 7.48 us; 8.66 vs 10.66 at width 768, 5.00 vs 6.48 at 3656 x 1024 -- the one-row kernel already runs at the HBM
+// rate and the wider per-warp footprint only costs occupancy.  Opt-in (gvf_ln_set_two_rows(1)), default off.
+static int g_ln_two_rows = 0;
 static int ln_mod_launch(const void* x, int x_is_f16, void* out, int M, int C, float eps, const float* w, const float* b,
                          const void* shift, const void* scale, int mod_stride, int rows_per_batch, int act, void* stream) {
   if (!x || !out || M <= 0) return GVF_ERR_INVALID;
@@ -618,6 +698,17 @@ static int ln_mod_launch(const void* x, int x_is_f16, void* out, int M, int C, f
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!act && g_ln_two_rows && M >= 2048 && (C == 512 || C == 768 || C == 1024)) {
+    const int want2 = (M + 15) / 16, cap2 = num_sms * 8;
+    const dim3 grid2(want2 < cap2 ? want2 : cap2);
+#define LN2(T, CC) launch_pdl(ln_mod2_kernel<T, CC>, grid2, dim3(256), 0, ST(stream), (const T*)x, (__half*)out, M, eps, w, b, \
+                              (const __half*)shift, (const __half*)scale, mod_stride, rpb)
+    if (C == 512) { if (x_is_f16) LN2(__half, 512); else LN2(float, 512); }
+    else if (C == 768) { if (x_is_f16) LN2(__half, 768); else LN2(float, 768); }
+    else { if (x_is_f16) LN2(__half, 1024); else LN2(float, 1024); }
+#undef LN2
+    RET();
   }
   const int want = (M + 7) / 8, cap = num_sms * 8;
   const dim3 grid(want < cap ? want : cap);
@@ -656,6 +747,8 @@ static int ln_mod_launch(const void* x, int x_is_f16, void* out, int M, int C, f
 #undef LN_CASE
   return GVF_ERR_UNSUPPORTED;
 }
+
+GVF_API void gvf_ln_set_two_rows(int on) { g_ln_two_rows = on ? 1 : 0; }
 
 GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
                            const float* w, const float* b, const void* shift, const void* scale,

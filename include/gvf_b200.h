@@ -277,6 +277,9 @@ GVF_API int gvf_small_linear(const float* x, int ldx, const void* W, const float
 GVF_API int gvf_ln_mod_f16(const void* x, int x_is_f16, void* out, int M, int C, float eps,
                            const float* w, const float* b, const void* shift, const void* scale,
                            int mod_stride, int rows_per_batch, void* stream);
+/* Tuning hook for A/B runs: 1 = widths 512 / 768 / 1024 with >= 2048 rows keep two rows per warp in flight (identical
+ * bits; measured slower than the one-row-per-warp kernel, so the default is 0). */
+GVF_API void gvf_ln_set_two_rows(int on);
 /* Same with an activation applied before the single fp16 rounding: act 0 none, 1 SiLU -- the `norm1 -> SiLU -> conv1` and
  * `norm2 * (1 + scale) + shift -> SiLU -> conv2` pairs of SparseResBlock3d (trellis/models/structured_latent_flow.py:57-62).
  * Widths 64 / 128 / 256 / 1024 / 2048 for act 1. */

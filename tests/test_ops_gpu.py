@@ -318,6 +318,29 @@ def test_small_linear_and_final_layer_large_m():
         _close(ops.dit_final_layer(X, modf[:, :512], modf[:, 512:], 1024, rpb, Wf, bf), ref, 2e-3, f"final layer M={M}")
 
 
+def test_ln_two_rows_per_warp_is_bit_identical():
+    """ln_mod2_kernel (two rows per warp in flight: widths 512 / 768 / 1024, >= 2048 rows) against the one-row kernel."""
+    from gvfdiffusion_b200 import _lib, ops
+    g = _g(5)
+    try:
+        for M, C, rpb in ((12288, 512, 12288), (2049, 768, 683), (4097, 1024, 4097), (6144, 512, 512)):
+            nb = (M + rpb - 1) // rpb
+            for dt in (torch.float32, torch.float16):
+                x = _rand((M, C), g).to(dt)
+                w, b = _rand((C,), g) + 1, _rand((C,), g)
+                mod = _rand((nb, 2 * C), g, 0.3).half()
+                outs = []
+                for two in (1, 0):
+                    _lib.lib().gvf_ln_set_two_rows(two)
+                    outs.append((ops.ln_mod(x), ops.ln_mod(x, w=w, b=b),
+                                 ops.ln_mod(x, shift=mod[:, :C], scale=mod[:, C:], mod_stride=2 * C, rows_per_batch=rpb)))
+                for a, r in zip(*outs):
+                    assert torch.equal(a, r), (M, C, dt)
+                _close(outs[0][1], F.layer_norm(x.float(), (C,), w, b, 1e-6), 1e-3)
+    finally:
+        _lib.lib().gvf_ln_set_two_rows(0)
+
+
 def test_geglu_cast_dpm():
     from gvfdiffusion_b200 import ops
     g = _g(31)
