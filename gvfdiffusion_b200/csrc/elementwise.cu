@@ -737,8 +737,10 @@ static int ln_mod_launch(const void* x, int x_is_f16, void* out, int M, int C, f
   LN_BOTH(256, true)
   LN_BOTH(1024, true)
   // the ResBlock widths of the structured-latent flow model (io 64 / 128, their skip concatenations, model 1024 / 2048)
+  LN_ACT(32, false)
   LN_ACT(64, false)
   LN_ACT(128, true)
+  LN_ACT(512, true)
   LN_ACT(256, true)
   LN_ACT(1024, true)
   LN_ACT(2048, true)

@@ -263,15 +263,25 @@ class SLatFlowModel:
     def reset_conditioning(self):
         self._kv_cache.clear()
 
+    _MAX_WORKSPACES = 4
+
     def _workspace(self, n):
-        """One set of activation buffers per row count, kept for the engine's lifetime (captured graphs point into them)."""
-        ws = self._ws.get(n)
+        """One set of activation buffers per token count (every object has its own).  Captured graphs point into the
+        workspace they were recorded with, so the sets are kept in a small LRU and evicting one drops the graphs that were
+        captured at its token count -- memory stays bounded over a stream of objects, no graph ever sees freed buffers."""
+        ws = self._ws.pop(n, None)
         if ws is None:
+            while len(self._ws) >= self._MAX_WORKSPACES:
+                gone = next(iter(self._ws))
+                del self._ws[gone]
+                for ent in self._kv_cache.values():
+                    for k in [k for k, g in ent["graphs"].items() if g[5] == gone]:
+                        del ent["graphs"][k]
             C, dev = self.model_channels, self.device
             ws = dict(A=torch.empty((n, C), dtype=F16, device=dev), QKV=torch.empty((n, 3 * C), dtype=F16, device=dev),
                       AO=torch.empty((n, C), dtype=F16, device=dev),
                       H1=torch.empty((n, int(C * self.mlp_ratio)), dtype=F16, device=dev))
-            self._ws[n] = ws
+        self._ws[n] = ws                                  # most recently used last
         return ws
 
     # ------------------------------------------------------------------ CUDA-graph replay of one call
@@ -298,12 +308,14 @@ class SLatFlowModel:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self.forward(sx, ts, cond).feats
-            # `sx` stays with the graph: its spatial cache owns the neighbour maps / resampling plan / APE the graph reads
-            g = (graph, xs, ts, out, sx)
+            # `sx` stays with the graph: its spatial cache owns the neighbour maps / resampling plan / APE the graph reads;
+            # the last field is the token count of the workspace the graph points into (see _workspace)
+            g = (graph, xs, ts, out, sx, next(reversed(self._ws)))
             if len(ent["graphs"]) >= 4:
                 ent["graphs"].clear()
             ent["graphs"][key] = g
-        graph, xs, ts, out, _ = g
+        graph, xs, ts, out, _, n_ws = g
+        self._workspace(n_ws)                              # touch: keeps this graph's workspace at the young end of the LRU
         xs.copy_(x.feats)
         ts.copy_(tt)
         graph.replay()

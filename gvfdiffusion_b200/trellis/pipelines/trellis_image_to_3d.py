@@ -3,9 +3,9 @@
 `argwhere(> 0)` -- `sample_slat` -- the flow sampler over `SLatFlowModel` on the active voxels, then de-normalisation --
 `decode_slat` to canonical Gaussians, and `run_from_cond` = the body of `run()` after `get_cond`.  Same method names,
 arguments and `models` / `*_sampler` / `*_sampler_params` / `slat_normalization` attributes as the reference class.
-Out of scope here: image preprocessing (rembg), the DINOv2 conditioning encoder (`get_cond`), the mesh / radiance-field
-decoders, and `models['sparse_structure_decoder']` itself -- a small dense Conv3d network (sparse_structure_vae.py) that the
-caller supplies as any callable z_s [B, C, 16, 16, 16] -> occupancy logits [B, 1, 64, 64, 64]."""
+`models['sparse_structure_decoder']` is `trellis.models.SparseStructureDecoder` (or any callable z_s [B, C, 16, 16, 16] ->
+occupancy logits [B, 1, 64, 64, 64]).  Out of scope here: image preprocessing (rembg), the DINOv2 conditioning encoder
+(`get_cond`), the mesh / radiance-field decoders."""
 import torch
 
 from ... import ops

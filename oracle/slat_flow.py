@@ -231,3 +231,43 @@ def sparse_structure_flow_forward(sd, cfg, x, t, cond):
     h = F.linear(F.layer_norm(h, h.shape[-1:]), sd["out_layer.weight"], sd["out_layer.bias"])
     h = h.reshape(B, R ** 3, -1).permute(0, 2, 1).reshape(B, -1, R, R, R)
     return unpatchify(h, ps).contiguous()
+
+
+def pixel_shuffle_3d(x, s=2):
+    """trellis/modules/spatial.py:4-13."""
+    B, C, H, W, D = x.shape
+    c = C // s ** 3
+    return x.reshape(B, c, s, s, s, H, W, D).permute(0, 1, 5, 2, 6, 3, 7, 4).reshape(B, c, H * s, W * s, D * s)
+
+
+def _channel_ln(x, w, b):
+    """ChannelLayerNorm32 (trellis/modules/norm.py:19-25): LayerNorm over the channel axis of [B, C, H, W, D], eps 1e-5."""
+    return F.layer_norm(x.permute(0, 2, 3, 4, 1), (x.shape[1],), w, b, 1e-5).permute(0, 4, 1, 2, 3)
+
+
+def _res_block3d(sd, p, x):
+    """ResBlock3d.forward (trellis/models/sparse_structure_vae.py:37-45)."""
+    h = F.conv3d(F.silu(_channel_ln(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])), sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
+    h = F.conv3d(F.silu(_channel_ln(h, sd[p + "norm2.weight"], sd[p + "norm2.bias"])), sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
+    if p + "skip_connection.weight" in sd:
+        x = F.conv3d(x, sd[p + "skip_connection.weight"], sd[p + "skip_connection.bias"])
+    return h + x
+
+
+def sparse_structure_decoder_forward(sd, cfg, z):
+    """SparseStructureDecoder.forward (sparse_structure_vae.py:296-306; norm_type 'layer'): z [B, C, R, R, R] -> occupancy
+    logits [B, out, R 2^(levels - 1), ...].  Pinned by tests/golden/sparse_structure_decoder_tiny.pt."""
+    sd = {k: v.float() for k, v in sd.items()}
+    h = F.conv3d(z.float(), sd["input_layer.weight"], sd["input_layer.bias"], padding=1)
+    for i in range(cfg["num_res_blocks_middle"]):
+        h = _res_block3d(sd, f"middle_block.{i}.", h)
+    bi = 0
+    for lvl in range(len(cfg["channels"])):
+        for _ in range(cfg["num_res_blocks"]):
+            h = _res_block3d(sd, f"blocks.{bi}.", h)
+            bi += 1
+        if lvl < len(cfg["channels"]) - 1:                       # UpsampleBlock3d, mode 'conv' (:97-101)
+            h = pixel_shuffle_3d(F.conv3d(h, sd[f"blocks.{bi}.conv.weight"], sd[f"blocks.{bi}.conv.bias"], padding=1), 2)
+            bi += 1
+    h = F.silu(_channel_ln(h, sd["out_layer.0.weight"], sd["out_layer.0.bias"]))
+    return F.conv3d(h, sd["out_layer.2.weight"], sd["out_layer.2.bias"], padding=1)

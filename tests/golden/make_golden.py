@@ -637,6 +637,36 @@ def gen_sparse_structure_flow():
             sys.modules.pop(k)
 
 
+def gen_sparse_structure_decoder():
+    """The reference's own SparseStructureDecoder (trellis/models/sparse_structure_vae.py:209-306: dense Conv3d ResNet,
+    ChannelLayerNorm32, pixel-shuffle upsampling; occupancy latent -> occupancy logits) on the CPU in fp32."""
+    import types
+    pkg = types.ModuleType("trellis")
+    pkg.__path__ = [os.path.join(_ref_import.REF, "trellis")]
+    sys.modules["trellis"] = pkg
+    try:
+        from trellis.models.sparse_structure_vae import SparseStructureDecoder
+        cfg = dict(out_channels=1, latent_channels=8, num_res_blocks=1, channels=[64, 32, 32], num_res_blocks_middle=1,
+                   norm_type="layer", use_fp16=False)
+        torch.manual_seed(9)
+        m = SparseStructureDecoder(**cfg).eval()
+        rerandomise_zero_layers(m, std=0.05)
+        g0 = torch.Generator().manual_seed(4)
+        for n_, p_ in m.named_parameters():
+            if "norm" in n_ or n_.endswith(".bias") or n_.startswith("out_layer.0"):
+                p_.data += 0.1 * torch.randn(p_.shape, generator=g0)
+        for p_ in m.parameters():
+            p_.data = p_.data.half().float()
+        g = torch.Generator().manual_seed(6)
+        z = torch.randn(2, 8, 4, 4, 4, generator=g)
+        with torch.no_grad():
+            y = m(z)
+        return {"cfg": cfg, "state_dict": {k: v.half() for k, v in m.state_dict().items()}, "z": z, "out": y}
+    finally:
+        for k in [k for k in sys.modules if k == "trellis" or k.startswith("trellis.")]:
+            sys.modules.pop(k)
+
+
 def _bruteforce_knn_points(p1, p2, lengths1=None, lengths2=None, K=1):
     """Stand-in for pytorch3d.ops.knn_points (absent here) with its documented semantics: exact squared
     distances ((dx*dx + dy*dy) + dz*dz in fp32), ascending, ties -> lowest index, padded rows zero."""
@@ -981,6 +1011,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "sparse_structure_flow":
         torch.save(gen_sparse_structure_flow(), os.path.join(HERE, "sparse_structure_flow_tiny.pt"))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "sparse_structure_decoder":
+        torch.save(gen_sparse_structure_decoder(), os.path.join(HERE, "sparse_structure_decoder_tiny.pt"))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "slat_flow":
         torch.save(gen_slat_flow(), os.path.join(HERE, "slat_flow_tiny.pt"))
         return
@@ -1009,6 +1042,7 @@ def main():
     torch.save(gen_slat_flow(), os.path.join(HERE, "slat_flow_tiny.pt"))
     torch.save(gen_slat_decoder_gs(), os.path.join(HERE, "slat_decoder_gs_tiny.pt"))
     torch.save(gen_sparse_structure_flow(), os.path.join(HERE, "sparse_structure_flow_tiny.pt"))
+    torch.save(gen_sparse_structure_decoder(), os.path.join(HERE, "sparse_structure_decoder_tiny.pt"))
     torch.save(gen_window_partition(), os.path.join(HERE, "window_partition.pt"))
     torch.save(gen_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(gen_to_representation(), os.path.join(HERE, "to_representation.pt"))

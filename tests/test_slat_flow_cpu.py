@@ -101,3 +101,10 @@ def test_sparse_structure_flow_oracle_matches_reference_class():
         # patchify / unpatchify are inverse permutations
         ps = c["cfg"]["patch_size"]
         assert torch.equal(O.unpatchify(O.patchify(c["x"], ps), ps), c["x"])
+
+
+def test_sparse_structure_decoder_oracle_matches_reference_class():
+    c = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sparse_structure_decoder_tiny.pt"), weights_only=False)
+    out = O.sparse_structure_decoder_forward(c["state_dict"], c["cfg"], c["z"])
+    assert out.shape == c["out"].shape
+    assert float((out - c["out"]).norm() / c["out"].norm()) < 1e-5

@@ -223,7 +223,45 @@ def main():
         args = {"slat_sampler": {"name": "FlowEulerGuidanceIntervalSampler", "args": {"sigma_min": 1e-5},
                                  "params": {"steps": 25, "cfg_strength": 3.0, "cfg_interval": [0.5, 1.0], "rescale_t": 3.0}},
                 "slat_normalization": {"mean": [0.0] * 8, "std": [1.0] * 8}}
-        pipe = TrellisImageTo3DPipeline.from_args(args, {"slat_flow_model": model, "slat_decoder_gs": dec}, device=dev)
+        # the sparse-structure half at the shipped sizes: dense DiT over the 16^3 x 8 occupancy latent (4096 tokens x 1024,
+        # 24 blocks), 25 steps with guidance 7.5 on [0.5, 1], then the Conv3d decoder [512, 128, 32] to 64^3 logits
+        from gvfdiffusion_b200.trellis.models import SparseStructureDecoder, SparseStructureFlowModel
+        ssd = {k: v for k, v in sd.items() if k.startswith("blocks.") or k.startswith("t_embedder.")}
+        ssd["input_layer.weight"], ssd["input_layer.bias"] = torch.randn(C, 8, generator=gg) / math.sqrt(8), torch.zeros(C)
+        ssd["out_layer.weight"], ssd["out_layer.bias"] = torch.randn(8, C, generator=gg) / math.sqrt(C), torch.zeros(8)
+        ss = SparseStructureFlowModel(resolution=16, in_channels=8, model_channels=C, cond_channels=CC, out_channels=8,
+                                      num_blocks=a.blocks, num_heads=HEADS, patch_size=1, use_fp16=True, qk_rms_norm=True,
+                                      device=dev).load_state_dict(ssd)
+        ss.use_graphs = True
+        chs = [512, 128, 32]
+        dd = {}
+
+        def dconv(name, o, i, k=3):
+            dd[name + ".weight"], dd[name + ".bias"] = torch.randn(o, i, k, k, k, generator=gg) / math.sqrt(i * k ** 3), torch.zeros(o)
+
+        def dres(p_, c_):
+            for nm in ("norm1", "norm2"):
+                dd[p_ + nm + ".weight"], dd[p_ + nm + ".bias"] = torch.ones(c_), torch.zeros(c_)
+            dconv(p_ + "conv1", c_, c_)
+            dconv(p_ + "conv2", c_, c_)
+        dconv("input_layer", chs[0], 8)
+        for i_ in range(2):
+            dres(f"middle_block.{i_}.", chs[0])
+        bi_ = 0
+        for lv, c_ in enumerate(chs):
+            for _ in range(2):
+                dres(f"blocks.{bi_}.", c_)
+                bi_ += 1
+            if lv < len(chs) - 1:
+                dconv(f"blocks.{bi_}.conv", chs[lv + 1] * 8, c_)
+                bi_ += 1
+        dd["out_layer.0.weight"], dd["out_layer.0.bias"] = torch.ones(chs[-1]), torch.zeros(chs[-1])
+        dconv("out_layer.2", 1, chs[-1])
+        ssdec = SparseStructureDecoder(out_channels=1, latent_channels=8, num_res_blocks=2, channels=chs, device=dev).load_state_dict(dd)
+        pipe = TrellisImageTo3DPipeline.from_args(args, {"slat_flow_model": model, "slat_decoder_gs": dec,
+                                                         "sparse_structure_flow_model": ss, "sparse_structure_decoder": ssdec}, device=dev)
+        pipe.sparse_structure_sampler = pipe.slat_sampler
+        pipe.sparse_structure_sampler_params = {"steps": 25, "cfg_strength": 7.5, "cfg_interval": [0.5, 1.0], "rescale_t": 3.0}
         cd = {"cond": cond, "neg_cond": torch.zeros_like(cond)}
         calls = [0]
         fwd = model.forward_graphed
@@ -236,8 +274,17 @@ def main():
         ms_sample = timed(lambda: pipe.sample_slat(cd, coords, noise=x), 3, warmup=1)
         slat = pipe.sample_slat(cd, coords, noise=x)
         ms_dec = timed(lambda: pipe.decode_slat(slat), 5, warmup=2)
-        print(json.dumps({"metric": "TRELLIS structured-latent stage (sample_slat 25 steps with guidance interval + decode_slat)",
-                          "value": ms_sample + ms_dec, "unit": "ms", "higher_is_better": False, "sample_slat_ms": ms_sample,
+        cd_ss = {"cond": cond, "neg_cond": torch.zeros_like(cond)}
+        zn = torch.randn(1, 8, 16, 16, 16, generator=g).to(dev)
+        pipe.sample_sparse_structure(cd_ss, noise=zn)
+        ms_ss = timed(lambda: pipe.sample_sparse_structure(cd_ss, noise=zn), 3, warmup=1)
+        z_lat = torch.randn(1, 8, 16, 16, 16, generator=g).to(dev)
+        ms_ssdec = timed(lambda: ssdec(z_lat), 5, warmup=2)
+        ms_ssflow = timed(lambda: ss(zn, t, cond), 10, warmup=3)
+        print(json.dumps({"metric": "TRELLIS sampling stages at the shipped sizes (random weights): sample_sparse_structure + sample_slat + decode_slat",
+                          "value": ms_ss + ms_sample + ms_dec, "unit": "ms", "higher_is_better": False,
+                          "sample_sparse_structure_ms": ms_ss, "sparse_structure_flow_call_ms": ms_ssflow,
+                          "sparse_structure_decoder_ms": ms_ssdec, "sample_slat_ms": ms_sample,
                           "model_calls": ncalls, "decode_slat_ms": ms_dec, "voxels": n, "gaussians": n * NG,
                           "coarse_tokens": nc, "cond_tokens": L}))
         return
