@@ -55,7 +55,7 @@ def test_legacy_mma_only_where_intended(sass_by_kernel):
     with_hmma = {k for k, b in sass_by_kernel.items() if LEGACY.search(b)}
     assert with_hmma, "the small-tile kernels are expected to use mma.sync"
     for k in with_hmma:
-        assert "attn_small_mma_kernel" in k or "sparse_window_attn_kernel" in k or "sparse_attn_bwd_" in k, k
+        assert "attn_small_mma_" in k or "sparse_window_attn_kernel" in k or "sparse_attn_bwd_" in k, k
 
 
 def test_rasteriser_has_no_tensor_core_instructions(sass_by_kernel):
