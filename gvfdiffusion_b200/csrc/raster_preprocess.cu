@@ -455,13 +455,13 @@ __global__ void __launch_bounds__(1024, 1) fps_smem2_kernel(const float* __restr
 // those of the brute-force kernels bit for bit, whatever the row order (an unordered cloud only prunes less and then costs
 // what the second generation costs plus the box test).  Shared memory holds the coordinates transposed per warp
 // (point j of lane l at 32 PER w + 32 j + l) so that the lanes' loads stay conflict-free.  Tie rule unchanged (lowest index).
-template <int PER>
-__global__ void __launch_bounds__(1024, 1) fps_pruned_kernel(const float* __restrict__ pts, int ld, int P, int K,
+template <int PER, int NT = 1024>
+__global__ void __launch_bounds__(NT, 1) fps_pruned_kernel(const float* __restrict__ pts, int ld, int P, int K,
                                                               int start, int* __restrict__ out_idx) {
   extern __shared__ float sxyz[];                  // x[0..Pp) | y | z, Pp = PER * 1024, transposed per warp
   __shared__ unsigned sd[2][32];
   __shared__ unsigned si[2][32];
-  constexpr int Pp = PER * 1024;
+  constexpr int Pp = PER * NT, NW = NT / 32;       // NT = 512: half the per-step warp overhead, twice the points per thread
   float* sx = sxyz; float* sy = sxyz + Pp; float* sz = sxyz + 2 * Pp;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int first = (w * 32 + lane) * PER;         // this thread's first point
@@ -515,8 +515,8 @@ __global__ void __launch_bounds__(1024, 1) fps_pruned_kernel(const float* __rest
     const unsigned wi = __reduce_min_sync(0xffffffffu, ub == wm ? bi : 0xffffffffu);
     if (lane == 0) { sd[k & 1][w] = wm; si[k & 1][w] = wi; }
     __syncthreads();
-    ub = sd[k & 1][lane];
-    const unsigned ci = si[k & 1][lane];
+    ub = lane < NW ? sd[k & 1][lane] : 0u;
+    const unsigned ci = lane < NW ? si[k & 1][lane] : 0xffffffffu;
     wm = __reduce_max_sync(0xffffffffu, ub);
     cur = __reduce_min_sync(0xffffffffu, ub == wm ? ci : 0xffffffffu);
     if (tid == 0) out_idx[k] = (int)cur;
@@ -677,9 +677,19 @@ static int fps_impl(const float* pts, int ld, int P, int K, int start, float* wo
     return (ok && cudaGetLastError() == cudaSuccess) ? GVF_OK : GVF_ERR_CUDA;
   }
   if ((fps_mode == 3 || (fps_mode == 2 && ordered)) && P <= 16384) {
+    static int half_block = -1;                    // GVF_FPS_THREADS=1024: the 1024-thread form at every size (A/B)
+    if (half_block < 0) {
+      const char* e2 = getenv("GVF_FPS_THREADS");
+      half_block = (e2 && atoi(e2) == 1024) ? 0 : 1;
+    }
     if (P <= 4096) ok = launch_smem(gvf::fps_pruned_kernel<4>, 4);
     else if (P <= 8192) ok = launch_smem(gvf::fps_pruned_kernel<8>, 8);
-    else ok = launch_smem(gvf::fps_pruned_kernel<16>, 16);
+    else if (half_block) {
+      const int bytes = 32 * 512 * 3 * (int)sizeof(float);
+      auto kern = gvf::fps_pruned_kernel<32, 512>;
+      ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      if (ok) kern<<<1, 512, bytes, (cudaStream_t)stream>>>(pts, ld, P, K, start, out_idx);
+    } else ok = launch_smem(gvf::fps_pruned_kernel<16>, 16);
     return (ok && cudaGetLastError() == cudaSuccess) ? GVF_OK : GVF_ERR_CUDA;
   }
   if (fps_mode == 2 && P <= 16384) {
