@@ -229,6 +229,8 @@ def main():
                          "GEMMs lose the SM the single-CTA FPS sits on), end to end 83.1 vs 88.0 frames/s -- default off")
     ap.add_argument("--attn-dbg", type=lambda v: int(v, 0), default=0, help="gvf_attn_set_debug value (kernel-variant A/B)")
     ap.add_argument("--pdl", action="store_true", help="launch with the programmatic-dependent-launch attribute (A/B; default off)")
+    ap.add_argument("--sampler-graph", type=int, default=None, help="1 / 0: the whole fixed-step sampling run as one CUDA graph "
+                    "(GVFPipeline.sampler_graph) on / off for A/B runs; default = the pipeline's default")
     ap.add_argument("--config", default="cfg1", choices=["cfg1", "cfg3", "cfg5", "cfg5-static"],
                     help="cfg1 (default): BASELINE.json configs[1], the headline inference metric.  cfg3: configs[2], one "
                          "training step of the motion-VAE decoder + 24-frame render, forward + backward (tools/train_step_bench.py).  "
@@ -302,6 +304,8 @@ def main():
 
     dit, vae = build_models(dev, seed=0)                      # replicated weights
     pipe = GVFPipeline(dit, vae, reference_betas(), device=dev, resolution=RES)
+    if args.sampler_graph is not None:
+        pipe.sampler_graph = bool(args.sampler_graph)
     hin = host_inputs(seed=rank)                              # a different object per rank
     out_host = torch.empty((T_FRAMES, 4, RES, RES), dtype=torch.float32).pin_memory()
     out_dev = torch.empty((T_FRAMES, 4, RES, RES), dtype=torch.float32, device=dev)
@@ -571,6 +575,8 @@ def main():
                    "num_rendered": Rn,
                    "modulation": "timestep MLP + adaLN vectors of the run's 32 model times computed once PER OBJECT inside the "
                                  "timed region (4 batched launch pairs), not once per NFE; nothing is carried between objects",
+                   "sampling": ("the 32 NFEs + solver updates of an object replayed as one CUDA graph" if getattr(pipe, "sampler_graph", False)
+                                else "one CUDA graph per NFE"),
                    "object_prefetch": ("sample_gs (FPS) of object k+1 on a side stream during the sampling of object k; "
                                        "one prepare_object per step" if prefetch else "off")},
         "clocks": sampler.summary(),

@@ -95,6 +95,8 @@ class DiTEngine:
         self._graphs = {}
         self.use_graphs = True
         self._modtab = {}                             # model time -> [1, R] fp16 modulation row (precompute_modulation)
+        self._modbufs = {}                            # time grid -> persistent table buffers
+        self.mod_epoch = 0
         self.use_premod = True
         self.fuse_resid_ln = False
 
@@ -155,6 +157,13 @@ class DiTEngine:
         # modulation vectors of this model time out of the precomputed table (precompute_modulation): the graph then
         # starts at the input layer and the table row is copied into the workspace's `mod` buffer before the replay
         row = self._modtab.get(float(t_value)) if self.use_premod else None
+        if torch.cuda.is_current_stream_capturing():
+            # inside a whole-run graph (pipeline.sample): no nested replay, the NFE's launches are recorded in place
+            if row is not None:
+                self._workspace(x.shape[0], x.shape[1], x.shape[2])["mod"].copy_(row.expand(x.shape[0], -1))
+                return self.forward(x, None, kv_img, kv_static, pos, premod=True)
+            tt = torch.full((x.shape[0],), float(t_value), dtype=F32, device=self.dev)
+            return self.forward(x, tt, kv_img, kv_static, pos)
         key = (tuple(x.shape),
                tuple(t.data_ptr() for e in kv_img for t in e), tuple(t.data_ptr() for e in kv_static for t in e),
                tuple(p.data_ptr() for p in pos), row is not None)
@@ -196,19 +205,31 @@ class DiTEngine:
         carried from one object to the next (4 launch pairs = ~0.4 ms per 32-step object instead of 32 x 88 us)."""
         if not self.use_premod:
             return
-        todo = [float(t) for t in dict.fromkeys(float(t) for t in t_values) if refresh or float(t) not in self._modtab]
-        if len(self._modtab) + len(todo) > 4096:
-            self._modtab.clear()
-        for i in range(0, len(todo), 8):
-            chunk = todo[i:i + 8]
-            n = len(chunk)
-            tt = torch.tensor(chunk, dtype=F32, device=self.dev)
-            temb = torch.empty((n, self.C), dtype=F16, device=self.dev)
-            stemb = torch.empty((n, self.C), dtype=F16, device=self.dev)
-            mod = torch.empty((n, self.R), dtype=F16, device=self.dev)
-            ops.dit_modulation(tt, self.t_w0, self.t_b0, self.t_w2, self.t_b2, self.w_mod, self.b_mod, temb, stemb, mod)
-            for j, t in enumerate(chunk):
-                self._modtab[t] = mod[j:j + 1]
+        if torch.cuda.is_current_stream_capturing():
+            return                                    # a whole-run graph (pipeline.sample) reads the rows computed before it
+        times = list(dict.fromkeys(float(t) for t in t_values))
+        key = tuple(times)
+        tab = self._modbufs.get(key)
+        fresh = tab is None
+        if fresh:
+            if len(self._modbufs) >= 16:              # rows are referenced by captured graphs: eviction bumps the epoch
+                self._modbufs.clear()
+                self._modtab.clear()
+                self.mod_epoch += 1
+            n = len(times)
+            # persistent buffers per time grid: stable row addresses (whole-run graphs copy from them), one H2D of the
+            # times per grid instead of one per object
+            tab = dict(tt=torch.tensor(times, dtype=F32, device=self.dev),
+                       temb=torch.empty((n, self.C), dtype=F16, device=self.dev),
+                       stemb=torch.empty((n, self.C), dtype=F16, device=self.dev),
+                       mod=torch.empty((n, self.R), dtype=F16, device=self.dev))
+            self._modbufs[key] = tab
+        if fresh or refresh:
+            for i in range(0, len(times), 8):
+                ops.dit_modulation(tab["tt"][i:i + 8], self.t_w0, self.t_b0, self.t_w2, self.t_b2, self.w_mod, self.b_mod,
+                                   tab["temb"][i:i + 8], tab["stemb"][i:i + 8], tab["mod"][i:i + 8])
+        for j, t in enumerate(times):
+            self._modtab[t] = tab["mod"][j:j + 1]
 
     # ------------------------------------------------------------------ forward
     def _workspace(self, Bx, T, N):

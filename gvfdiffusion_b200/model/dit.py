@@ -185,6 +185,19 @@ class DiT(nn.Module):
             tt = tt.expand(xt.shape[0]).contiguous()
         return eng.forward(xt, tt, kv_img, kv_st, pos).clone()
 
+    @torch.no_grad()
+    def prepare_conditioning(self, conds):
+        """Hoist the per-object projections of every guidance branch now (normally the first NFE does it) and return a
+        hashable key of the engine buffers they live in -- what a whole-run CUDA graph (GVFPipeline.sample) is keyed on."""
+        eng = self.engine()
+        self._cond_gen += 1
+        key = []
+        for c in conds:
+            a, b, p = self._cond_sets(eng, c["cond_images"], c["static_latent"], c["deformation_position_xyz"])
+            key.append((tuple(t.data_ptr() for e in a for t in e), tuple(t.data_ptr() for e in b for t in e),
+                        tuple(t.data_ptr() for t in p)))
+        return tuple(key), eng.mod_epoch
+
     def precompute_modulation(self, t_inputs):
         """Hook of DPM_Solver.sample: the model times of the whole run, known before the first NFE."""
         self.engine().precompute_modulation(t_inputs)

@@ -185,3 +185,39 @@ def test_pipeline_end_to_end_tiny_vs_oracle_chain():
     assert e_lat < 1e-3, e_lat
     assert e_delta < 2e-3, e_delta
     assert e_rgba < 1e-3, e_rgba
+
+
+
+def test_whole_run_sampling_graph_is_bit_identical():
+    """GVFPipeline.sampler_graph: the fixed-step DPM-Solver++ run recorded once as ONE CUDA graph and replayed per object
+    (after the hoist and the modulation-table refresh) gives the latents of the per-NFE-graph path bit for bit, for several
+    objects in a row and with 3-branch guidance."""
+    from gvfdiffusion_b200 import synthetic as S
+    from gvfdiffusion_b200.model.autoencoder import GSKLTemporalVariationalAutoEncoder as VAE
+    from gvfdiffusion_b200.model.dit import DiT
+    from gvfdiffusion_b200.pipeline import GVFPipeline
+    gd = torch.load(os.path.join(G, "dit_tiny.pt"), weights_only=False)
+    gv = torch.load(os.path.join(G, "vae_tiny.pt"), weights_only=False)
+    T, N = gv["cfg"]["num_timesteps"], gd["cfg"]["resolution"]
+    betas = torch.from_numpy(ODPM.reference_betas(1000))
+
+    def make():
+        dit = DiT(**gd["cfg"])
+        dit.load_state_dict(gd["state_dict"])
+        vae = VAE(**gv["cfg"])
+        vae.load_state_dict(gv["state_dict"])
+        return GVFPipeline(dit.to(DEV).eval(), vae.to(DEV).eval(), betas, device=DEV, resolution=96, num_latents=N, num_static=40)
+    ref_pipe, pipe = make(), make()
+    ref_pipe.sampler_graph, pipe.sampler_graph = False, True
+    g = torch.Generator().manual_seed(3)
+    for i in range(3):                                      # capture on the first object, replay on the next two
+        canon = S.canonical_gaussians(num_voxels=64, seed=20 + i)
+        cond_images = torch.randn(1, T, 10, gd["cfg"]["image_cond_channels"], generator=g).to(DEV)
+        noise = torch.randn(1, T, N, 16, generator=g).to(DEV)
+        for gs in ((1.0, 1.0), (2.0, 1.5)):
+            outs = []
+            for p_ in (ref_pipe, pipe):
+                obj = p_.prepare_object({k: v.to(DEV) for k, v in canon.items()})
+                outs.append(p_.sample(obj, cond_images, noise, steps=6, guidance_scale=gs[0], guidance_scale2=gs[1]).clone())
+            assert torch.equal(outs[0], outs[1]), (i, gs)
+    assert len(pipe._sample_graphs) == 2
