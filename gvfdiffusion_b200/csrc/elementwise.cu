@@ -380,14 +380,33 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   for (int k = 0; k < K; ++k) wv[k] = __half2float(W[(size_t)n * K + k]);
   const float bn = bias ? bias[n] : 0.f;
   int ar = row0 % add_rows;
-  for (int r = 0; r < RPB && row0 + r < M; ++r) {
-    float acc = 0.f;
-    for (int k = 0; k < K; ++k) acc += xs[r][k] * wv[k];
-    float y = r16f(acc + bn);
-    if (add) y += add[(size_t)ar * N + n];
-    if (++ar == add_rows) ar = 0;
-    if constexpr (sizeof(TOut) == 4) out[(size_t)(row0 + r) * N + n] = y;
-    else out[(size_t)(row0 + r) * N + n] = __float2half_rn(y);
+  // four rows per trip: the four `add` loads are issued before any of them is needed (the loop is latency-bound at the
+  // ~20 warps per SM a 384-block grid leaves resident), per-output arithmetic unchanged
+  constexpr int U = RPB >= 4 ? 4 : 1;
+  for (int r = 0; r < RPB && row0 + r < M; r += U) {
+    float av[U];
+    int arr = ar;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      av[u] = (add && row0 + r + u < M) ? __ldg(add + (size_t)arr * N + n) : 0.f;
+      if (++arr == add_rows) arr = 0;
+    }
+    ar = arr;
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.f;
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] += xs[r + u][k] * wv[k];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (row0 + r + u >= M) break;
+      float y = r16f(acc[u] + bn);
+      if (add) y += av[u];
+      if constexpr (sizeof(TOut) == 4) out[(size_t)(row0 + r + u) * N + n] = y;
+      else out[(size_t)(row0 + r + u) * N + n] = __float2half_rn(y);
+    }
   }
 }
 

@@ -53,6 +53,7 @@ def main():
     noise, cond = hin["noise"].to(dev), hin["cond_images"].to(dev)
     obj = pipe.prepare_object(canon)
     dit.engine().use_graphs = False
+    pipe.sampler_graph = False                                      # eager launches: what a replayed object consists of
     lat = pipe.sample(obj, cond, noise, steps=2)                   # warm-up, hoisted projections
     delta = pipe.decode(lat, obj)
     pipe.render(obj, delta, hin["ext"], hin["intr"])
