@@ -108,3 +108,25 @@ def test_sparse_structure_decoder_oracle_matches_reference_class():
     out = O.sparse_structure_decoder_forward(c["state_dict"], c["cfg"], c["z"])
     assert out.shape == c["out"].shape
     assert float((out - c["out"]).norm() / c["out"].norm()) < 1e-5
+
+
+def test_downsample_plan_bookkeeping_matches_oracle_on_the_host():
+    """The integer part of SparseDownsample (cell codes, unique, fine rows grouped by cell, coarse layout) is torch index work
+    and runs anywhere: it must reproduce the reference's coarse coordinates and cell index (through the oracle, which is
+    pinned to the reference's own SparseDownsample by the fixture)."""
+    from gvfdiffusion_b200.sparse.basic import SparseTensor
+    from gvfdiffusion_b200.sparse.spatial import downsample_plan
+    coords = G["coords"]
+    st = SparseTensor(torch.zeros(coords.shape[0], 8), coords)
+    plan = downsample_plan(st, 2)
+    _, c_ref, idx_ref = O.downsample(G["x"], coords)
+    assert torch.equal(plan["coords"], c_ref) and torch.equal(plan["idx"].long(), idx_ref)
+    assert torch.equal(plan["coords"], G["down_coords"])
+    # order / offsets: the fine rows of cell p, ascending
+    off = plan["offsets"].tolist()
+    order = plan["order"].long()
+    for p in (0, 1, len(off) - 2):
+        rows = order[off[p]:off[p + 1]]
+        assert torch.equal(rows, (idx_ref == p).nonzero().flatten())
+    assert [s.stop - s.start for s in plan["layout"]] == torch.bincount(c_ref[:, 0].long()).tolist()
+    assert downsample_plan(st, 2) is plan                              # cached on the tensor's spatial cache
